@@ -1,0 +1,322 @@
+"""Host-side mirror of the reference's TrajectoryGeneratorTool interface over the C ABI (include/msnap.h).
+
+Names, argument meaning and error behaviour follow ``/root/reference/math_util/minimum_snap.hpp:9-63``:
+``MinimumSnapConfig``, ``TrajectoryGeneratorTool.SolveQPClosedForm`` and
+``TrajectoryGeneratorTool.GenerateTrajectoryMatrix``; the batched entry points are the addition this repo makes.
+Every compute call goes through ``libmsnap_b200.so`` (CUDA, sm_100a).  Nothing here computes trajectories on the
+CPU, and nothing here imports ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import MsnapError, msnap_config
+
+
+@dataclass
+class MinimumSnapConfig:
+    """minimum_snap.hpp:9-33 -- same field names, same defaults."""
+
+    order: int = 3
+    path_weight: float = 0.0
+    vel_zero_weight: float = 0.0
+    V_avg: float = 5.0
+    min_time_s: float = 0.1
+    sample_distance: float = 1.0
+    start_vel: Sequence[float] = (0.0, 0.0, 0.0)
+    end_vel: Sequence[float] = (0.0, 0.0, 0.0)
+    start_acc: Sequence[float] = (0.0, 0.0, 0.0)
+    end_acc: Sequence[float] = (0.0, 0.0, 0.0)
+
+    def to_c(self) -> msnap_config:
+        c = msnap_config()
+        c.order = int(self.order)
+        c.path_weight = float(self.path_weight)
+        c.vel_zero_weight = float(self.vel_zero_weight)
+        c.V_avg = float(self.V_avg)
+        c.min_time_s = float(self.min_time_s)
+        c.sample_distance = float(self.sample_distance)
+        for name in ("start_vel", "end_vel", "start_acc", "end_acc"):
+            v = [float(x) for x in getattr(self, name)]
+            if len(v) != 3:
+                raise ValueError(f"{name} must have 3 components")
+            setattr(c, name, (C.c_double * 3)(*v))
+        return c
+
+    @staticmethod
+    def from_c(c: msnap_config) -> "MinimumSnapConfig":
+        return MinimumSnapConfig(
+            c.order, c.path_weight, c.vel_zero_weight, c.V_avg, c.min_time_s, c.sample_distance,
+            tuple(c.start_vel), tuple(c.end_vel), tuple(c.start_acc), tuple(c.end_acc),
+        )
+
+
+def shipped_config(**over) -> MinimumSnapConfig:
+    """The parameters the reference ships in math_util/minimum_snap_config.yaml:5-27."""
+    cfg = MinimumSnapConfig(order=2, vel_zero_weight=0.01, path_weight=1e-7, V_avg=200.0, min_time_s=1.0,
+                            sample_distance=300.0)
+    for k, v in over.items():
+        if not hasattr(cfg, k):
+            raise AttributeError(k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+def load_minimum_snap_config(path: str, base: Optional[MinimumSnapConfig] = None) -> MinimumSnapConfig:
+    """Read the min-snap YAML the way UavPathPlanner::loadFromYAML does (uavPathPlanning.cpp:851-879): keys that are
+    absent or malformed keep the value they had in ``base`` (default: struct defaults)."""
+    L = _lib.lib()
+    c = (base or MinimumSnapConfig()).to_c()
+    rc = L.msnap_config_load_yaml(path.encode(), C.byref(c))
+    if rc != _lib.OK:
+        raise MsnapError(rc, path)
+    return MinimumSnapConfig.from_c(c)
+
+
+@dataclass
+class BatchResult:
+    """Outputs of one batched GenerateTrajectoryMatrix (host arrays)."""
+
+    seg_offset: np.ndarray           # [B+1]
+    times: np.ndarray                # [sum ns]
+    coeff: np.ndarray                # [sum ns, 3, 2*order]  highest power first
+    max_dev: np.ndarray              # [B]
+    iters: np.ndarray                # [B] int32
+    vw_final: np.ndarray             # [B]
+    best_s: np.ndarray               # [sum ns] int32: worst-deviation sample index per segment (0 if path_weight<=0)
+    sample_offset: np.ndarray        # [B+1] int64
+    samples: np.ndarray              # [rows, 3]
+    stats: np.ndarray                # [B, 2]  max climb rate, min turn radius
+    flags: np.ndarray                # [B] uint32
+
+    def trajectory(self, b: int) -> np.ndarray:
+        return self.samples[self.sample_offset[b]:self.sample_offset[b + 1]]
+
+    def segment_slice(self, b: int) -> slice:
+        return slice(int(self.seg_offset[b]), int(self.seg_offset[b + 1]))
+
+
+def _f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a) -> Optional[int]:
+    return None if a is None else a.ctypes.data
+
+
+def _layout(waypoints: np.ndarray, ns: Optional[int], seg_offset):
+    """Normalise the (uniform | CSR) batch description.  Returns (B, ns_uniform, seg_offset int64 or None, n_seg)."""
+    n_pts = waypoints.shape[0]
+    if seg_offset is not None:
+        so = np.ascontiguousarray(seg_offset, dtype=np.int64)
+        B = so.shape[0] - 1
+        if B < 0 or (B >= 0 and so[0] != 0) or np.any(np.diff(so) < 1) or so[-1] + B != n_pts:
+            raise ValueError("seg_offset must start at 0, be strictly increasing and cover waypoints (sum ns + B rows)")
+        return B, 0, so, int(so[-1])
+    if ns is None or ns < 1:
+        raise ValueError("give ns (uniform segment count >= 1) or seg_offset")
+    if n_pts % (ns + 1) != 0:
+        raise ValueError("waypoint rows must be a multiple of ns + 1")
+    B = n_pts // (ns + 1)
+    return B, int(ns), None, B * int(ns)
+
+
+class TrajectoryGeneratorTool:
+    """GPU-backed stand-in for the reference class of the same name (minimum_snap.hpp:36-63).
+
+    One instance owns one ``msnap_handle`` (device + stream + workspace) and, like the reference object, is not
+    re-entrant."""
+
+    def __init__(self, device: int = 0):
+        self._L = _lib.lib()
+        h = C.c_void_p()
+        rc = self._L.msnap_create(int(device), C.byref(h))
+        if rc != _lib.OK:
+            raise MsnapError(rc, f"msnap_create(device={device})")
+        self._h = h
+        self.device = int(device)
+
+    # ------------------------------------------------------------------ lifetime / plumbing
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.msnap_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int, allow=()):
+        if rc != _lib.OK and rc not in allow:
+            raise MsnapError(rc, self._L.msnap_last_error(self._h).decode())
+        return rc
+
+    def set_stream(self, cuda_stream: Optional[int]):
+        self._check(self._L.msnap_set_stream(self._h, cuda_stream))
+
+    def synchronize(self):
+        self._check(self._L.msnap_synchronize(self._h))
+
+    def set_reweight_policy(self, policy: int):
+        self._check(self._L.msnap_set_reweight_policy(self._h, int(policy)))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.msnap_launch_count(self._h))
+
+    def measure_fp64_peak(self) -> float:
+        out = C.c_double(0.0)
+        self._check(self._L.msnap_measure_fp64_peak(self._h, C.byref(out)))
+        return out.value
+
+    # ------------------------------------------------------------------ the reference's two methods
+    def SolveQPClosedForm(self, order, Path, Vel, Acc, Time, path_weight=0.0, vel_zero_weight=0.0,
+                          return_max_deviation=False):
+        """minimum_snap.hpp:45-53.  Path (n,3), Vel/Acc (2,3), Time (n-1,)  ->  PolyCoeff (n-1, 3*2*order)
+        (and max_deviation when asked, the reference's optional out-parameter)."""
+        Path, Vel, Acc, Time = _f64(Path), _f64(Vel), _f64(Acc), _f64(Time)
+        ns = Time.shape[0]
+        if Path.ndim != 2 or Path.shape != (ns + 1, 3) or Vel.shape != (2, 3) or Acc.shape != (2, 3) or ns < 1:
+            raise ValueError("Path must be (ns+1,3), Vel/Acc (2,3), Time (ns,)")
+        coeff, max_dev, _ = self.solve_qp_batch(order, Path, Time, ns=ns, vel=Vel[None], acc=Acc[None],
+                                                path_weight=path_weight, vel_zero_weight=vel_zero_weight)
+        poly = coeff.reshape(ns, 3 * 2 * order)
+        return (poly, float(max_dev[0])) if return_max_deviation else poly
+
+    def GenerateTrajectoryMatrix(self, Path, cfg: MinimumSnapConfig, sample_distance_override=-1.0,
+                                 v_avg_override=-1.0) -> np.ndarray:
+        """minimum_snap.hpp:60-61.  Path (n,3) -> sampled trajectory (S,3).  An input with fewer than 2 rows or 3
+        columns returns an empty (0,0) matrix, as ms.cpp:54-57 does."""
+        Path = np.asarray(Path, dtype=np.float64)
+        if Path.ndim != 2 or Path.shape[0] < 2 or Path.shape[1] < 3:
+            return np.zeros((0, 0))
+        wp = _f64(Path[:, :3])
+        c = cfg.to_c()
+        n = wp.shape[0]
+        bound = C.c_longlong(0)
+        self._check(self._L.msnap_sample_bound_host(self._h, C.byref(c), v_avg_override, 1, n - 1, None, _ptr(wp),
+                                                    C.byref(bound)))
+        out = np.empty((max(bound.value, 1), 3))
+        cnt = C.c_longlong(0)
+        self._check(self._L.msnap_generate_one_host(self._h, C.byref(c), sample_distance_override, v_avg_override, n,
+                                                    _ptr(wp), out.shape[0], _ptr(out), C.byref(cnt)))
+        return out[:cnt.value].copy()
+
+    # ------------------------------------------------------------------ batched, host buffers
+    def solve_qp_batch(self, order, waypoints, times, ns=None, seg_offset=None, vel=None, acc=None,
+                       path_weight=0.0, vel_zero_weight=0.0):
+        """B closed-form solves (no time allocation, no reweighting).  Returns (coeff [sum ns,3,2o], max_dev [B],
+        flags [B])."""
+        wp, times = _f64(waypoints), _f64(times)
+        B, nsu, so, n_seg = _layout(wp, ns, seg_offset)
+        if times.shape != (n_seg,):
+            raise ValueError("times must have one entry per segment")
+        vel = None if vel is None else _f64(vel).reshape(B, 2, 3)
+        acc = None if acc is None else _f64(acc).reshape(B, 2, 3)
+        coeff = np.empty((n_seg, 3, 2 * int(order)))
+        max_dev = np.empty(B)
+        flags = np.zeros(B, dtype=np.uint32)
+        best_s = np.zeros(n_seg, dtype=np.int32)
+        self._check(self._L.msnap_solve_qp_batch_host(
+            self._h, int(order), float(path_weight), float(vel_zero_weight), B, nsu, _ptr(so), _ptr(wp), _ptr(vel),
+            _ptr(acc), _ptr(times), _ptr(coeff), _ptr(max_dev), _ptr(best_s), _ptr(flags)))
+        self.last_best_s = best_s
+        return coeff, max_dev, flags
+
+    def sample_bound(self, cfg: MinimumSnapConfig, waypoints, ns=None, seg_offset=None, v_avg_override=-1.0) -> int:
+        wp = _f64(waypoints)
+        B, nsu, so, _ = _layout(wp, ns, seg_offset)
+        c = cfg.to_c()
+        out = C.c_longlong(0)
+        self._check(self._L.msnap_sample_bound_host(self._h, C.byref(c), v_avg_override, B, nsu, _ptr(so), _ptr(wp),
+                                                    C.byref(out)))
+        return int(out.value)
+
+    def generate_batch(self, cfg: MinimumSnapConfig, waypoints, ns=None, seg_offset=None,
+                       sample_distance_override=-1.0, v_avg_override=-1.0, capacity: Optional[int] = None,
+                       out: Optional[dict] = None) -> BatchResult:
+        """B independent GenerateTrajectoryMatrix calls in one launch sequence; host arrays in, host arrays out.
+        ``capacity`` rows are reserved for the samples (default: the exact-safe upper bound from
+        ``msnap_sample_bound``); if it is too small MsnapError(ERR_CAPACITY) is raised with the exact layout
+        available in ``.sample_offset`` of the exception's ``partial`` attribute."""
+        wp = _f64(waypoints)
+        B, nsu, so, n_seg = _layout(wp, ns, seg_offset)
+        c = cfg.to_c()
+        if capacity is None:
+            capacity = self.sample_bound(cfg, wp, ns=ns, seg_offset=seg_offset, v_avg_override=v_avg_override)
+        m = 2 * int(cfg.order)
+        o = out or {}
+        times = o.get("times", np.empty(n_seg))
+        coeff = o.get("coeff", np.empty((n_seg, 3, m)))
+        max_dev = o.get("max_dev", np.empty(B))
+        iters = o.get("iters", np.empty(B, dtype=np.int32))
+        vw_final = o.get("vw_final", np.empty(B))
+        best_s = o.get("best_s", np.zeros(n_seg, dtype=np.int32))
+        sample_offset = o.get("sample_offset", np.empty(B + 1, dtype=np.int64))
+        samples = o.get("samples", np.empty((max(int(capacity), 1), 3)))
+        stats = o.get("stats", np.empty((B, 2)))
+        flags = o.get("flags", np.zeros(B, dtype=np.uint32))
+        rc = self._L.msnap_generate_batch_host(
+            self._h, C.byref(c), float(sample_distance_override), float(v_avg_override), B, nsu, _ptr(so), _ptr(wp),
+            _ptr(times), _ptr(coeff), _ptr(max_dev), _ptr(iters), _ptr(vw_final), _ptr(best_s), int(capacity),
+            _ptr(sample_offset), _ptr(samples), _ptr(stats), _ptr(flags))
+        seg_off = so if so is not None else np.arange(B + 1, dtype=np.int64) * nsu
+        rows = int(min(sample_offset[B], capacity)) if rc in (_lib.OK, _lib.ERR_CAPACITY) else 0
+        res = BatchResult(seg_off, times, coeff, max_dev, iters, vw_final, best_s, sample_offset, samples[:rows], stats,
+                          flags)
+        if rc != _lib.OK:
+            err = MsnapError(rc, self._L.msnap_last_error(self._h).decode())
+            err.partial = res
+            raise err
+        return res
+
+    # ------------------------------------------------------------------ batched, device-resident (torch tensors)
+    def generate_batch_dev(self, cfg: MinimumSnapConfig, waypoints, sample_offset, samples, ns=None, seg_offset=None,
+                           sample_distance_override=-1.0, v_avg_override=-1.0, times=None, coeff=None, max_dev=None,
+                           iters=None, vw_final=None, best_s=None, stats=None, flags=None):
+        """Enqueue one batched generate on the handle's stream.  Every array argument is a CUDA ``torch.Tensor`` on
+        this handle's device (fp64 / int64 / int32 / uint32-as-int32 as in include/msnap.h); nothing is copied and
+        the host is not synchronised."""
+        B = int(sample_offset.numel()) - 1
+        c = cfg.to_c()
+
+        def dp(t):
+            return None if t is None else int(t.data_ptr())
+
+        rc = self._L.msnap_generate_batch_dev(
+            self._h, C.byref(c), float(sample_distance_override), float(v_avg_override), B, int(ns or 0),
+            dp(seg_offset), dp(waypoints), dp(times), dp(coeff), dp(max_dev), dp(iters), dp(vw_final), dp(best_s),
+            int(samples.shape[0]), dp(sample_offset), dp(samples), dp(stats), dp(flags))
+        self._check(rc)
+
+    def solve_qp_batch_dev(self, order, waypoints, times, coeff, B, ns=None, seg_offset=None, vel=None, acc=None,
+                           path_weight=0.0, vel_zero_weight=0.0, max_dev=None, best_s=None, flags=None):
+        def dp(t):
+            return None if t is None else int(t.data_ptr())
+
+        rc = self._L.msnap_solve_qp_batch_dev(
+            self._h, int(order), float(path_weight), float(vel_zero_weight), int(B), int(ns or 0), dp(seg_offset),
+            dp(waypoints), dp(vel), dp(acc), dp(times), dp(coeff), dp(max_dev), dp(best_s), dp(flags))
+        self._check(rc)
+
+    def sample_bound_dev(self, cfg: MinimumSnapConfig, waypoints, B, rows_out, ns=None, seg_offset=None,
+                         v_avg_override=-1.0):
+        c = cfg.to_c()
+        rc = self._L.msnap_sample_bound_dev(
+            self._h, C.byref(c), float(v_avg_override), int(B), int(ns or 0),
+            None if seg_offset is None else int(seg_offset.data_ptr()), int(waypoints.data_ptr()),
+            int(rows_out.data_ptr()))
+        self._check(rc)

@@ -1,0 +1,789 @@
+// msnap_capi.cu -- handle, workspace, kernel launch sequences and the extern "C" boundary of include/msnap.h.
+// Compiled for sm_100a only; there is no CPU code path behind any compute entry point.
+#include "../../include/msnap.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "msnap_device.cuh"
+#include "msnap_generic.cuh"
+
+static const MsnapOrderTab h_tab[MSNAP_MAX_ORDER - MSNAP_MIN_ORDER + 1] = MSNAP_ORDER_TABLES;
+
+using namespace msnap;
+
+// ------------------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------------------
+struct Arena {  // grow-only device buffer with bump allocation, reset per call
+    char *base = nullptr;
+    size_t cap = 0, used = 0;
+};
+
+struct msnap_context {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    MsnapOrderTab *d_tab = nullptr;  // global-memory copy of the tables (lane-divergent lookups)
+    Arena ws;                        // solver workspace
+    Arena io;                        // device mirrors of host buffers (_host entry points)
+    long long launches = 0;
+    int policy = 0;
+    int sm_count = 0;
+    std::string last_error;
+};
+
+namespace {
+
+#define MS_CUDA(h, expr)                                                                         \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            (h)->last_error = std::string(#expr) + ": " + cudaGetErrorString(e__);               \
+            return MSNAP_ERR_CUDA;                                                               \
+        }                                                                                        \
+    } while (0)
+
+struct DeviceGuard {  // make the handle's device current for the duration of a call
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int arena_reserve(msnap_context *h, Arena &a, size_t bytes) {
+    a.used = 0;
+    if (bytes <= a.cap) return MSNAP_OK;
+    if (a.base) {
+        MS_CUDA(h, cudaStreamSynchronize(h->stream));
+        MS_CUDA(h, cudaFree(a.base));
+        a.base = nullptr;
+        a.cap = 0;
+    }
+    const size_t want = bytes + bytes / 8 + (1u << 20);
+    cudaError_t e = cudaMalloc(&a.base, want);
+    if (e != cudaSuccess) {
+        h->last_error = std::string("cudaMalloc(workspace): ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return MSNAP_ERR_ALLOC;
+    }
+    a.cap = want;
+    return MSNAP_OK;
+}
+
+template <class T>
+T *arena_take(Arena &a, size_t n) {
+    const size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+    T *p = reinterpret_cast<T *>(a.base + a.used);
+    a.used += bytes;
+    return p;
+}
+inline size_t padded(size_t bytes) { return (bytes + 255) & ~size_t(255); }
+
+inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
+
+#define MS_LAUNCH(h, kernel, grid, block, ...)                                                   \
+    do {                                                                                         \
+        kernel<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);                                \
+        ++(h)->launches;                                                                         \
+        cudaError_t e__ = cudaPeekAtLastError();                                                 \
+        if (e__ != cudaSuccess) {                                                                \
+            (h)->last_error = std::string(#kernel) + ": " + cudaGetErrorString(e__);             \
+            cudaGetLastError();                                                                  \
+            return MSNAP_ERR_CUDA;                                                               \
+        }                                                                                        \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------------------
+// generic (per-phase) pipeline
+// ------------------------------------------------------------------------------------------------------------
+struct SolveIO {
+    const double *wp = nullptr;   // device
+    const double *times_in = nullptr;  // device, or nullptr => allocate (v_avg, min_time)
+    double v_avg = 0, min_time = 0;
+    double *times_out = nullptr, *coeff_out = nullptr, *max_dev_out = nullptr, *vw_final_out = nullptr;
+    int *iters_out = nullptr, *best_s_out = nullptr;
+    unsigned *flags_out = nullptr;
+};
+
+struct SolveWs {
+    double *T, *base, *state, *segx, *coeff;
+    int *s_star;
+};
+
+template <int O>
+size_t solve_ws_bytes(long long n_seg, bool need_T, bool need_coeff) {
+    using D = Dim<O>;
+    size_t b = 0;
+    if (need_T) b += padded(n_seg * sizeof(double));
+    b += padded((size_t)n_seg * D::NBASE * sizeof(double));
+    b += padded((size_t)(n_seg + 1) * D::NSTATE * sizeof(double));
+    b += padded((size_t)n_seg * D::NSEGX * sizeof(double));
+    b += padded((size_t)n_seg * sizeof(int));
+    if (need_coeff) b += padded((size_t)n_seg * 3 * D::M * sizeof(double));
+    return b;
+}
+
+// Enqueue the closed-form solve (with or without the reweighting loop) for the whole batch.
+template <int O>
+int run_solve(msnap_context *h, const BatchIdx &bi, const SolveParams &sp, const SolveIO &io, SolveWs &w) {
+    using D = Dim<O>;
+    const int blk = 128;
+    const unsigned gs = grid_for(bi.n_seg, blk), gb = grid_for(bi.B, blk);
+    const double *ht = &h->d_tab[O - MSNAP_MIN_ORDER].HT[0][0];
+    const double *T = io.times_in;
+    if (!T) {
+        MS_LAUNCH(h, k_times, gs, blk, bi, io.wp, io.v_avg, io.min_time, w.T);
+        T = w.T;
+    }
+    if (io.flags_out) MS_CUDA(h, cudaMemsetAsync(io.flags_out, 0, bi.B * sizeof(unsigned), h->stream));
+    const bool use_pw = sp.pw > 0.0;
+    if (io.best_s_out) {
+        w.s_star = io.best_s_out;  // the caller's buffer doubles as the decision workspace
+        if (!use_pw) MS_CUDA(h, cudaMemsetAsync(io.best_s_out, 0, bi.n_seg * sizeof(int), h->stream));
+    }
+    if (use_pw) {
+        // pass 1: snap cost only (no path penalty, no velocity penalty) -> worst-deviation sample per segment
+        MS_LAUNCH(h, (k_rows<O>), gs, blk, bi, sp, io.wp, T, false, (const int *)nullptr, ht, w.base, w.segx);
+        SolveParams sp1 = sp;
+        sp1.max_iter = 0;
+        MS_LAUNCH(h, (k_thomas<O>), gb, blk, bi, sp1, io.wp, w.base, w.state, w.segx, false, false,
+                  (double *)nullptr, (int *)nullptr, (double *)nullptr, io.flags_out);
+        MS_LAUNCH(h, (k_search<O>), gs, blk, bi, sp, io.wp, T, w.state, w.s_star);
+    }
+    MS_LAUNCH(h, (k_rows<O>), gs, blk, bi, sp, io.wp, T, use_pw, w.s_star, ht, w.base, w.segx);
+    MS_LAUNCH(h, (k_thomas<O>), gb, blk, bi, sp, io.wp, w.base, w.state, w.segx, use_pw, true, io.max_dev_out,
+              io.iters_out, io.vw_final_out, io.flags_out);
+    MS_LAUNCH(h, (k_coeff<O>), gs, blk, bi, sp, io.wp, T, w.state, w.coeff, io.flags_out);
+    if (io.times_out && io.times_out != T)
+        MS_CUDA(h, cudaMemcpyAsync(io.times_out, T, bi.n_seg * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    (void)D::M;
+    return MSNAP_OK;
+}
+
+template <int O>
+void carve_solve_ws(Arena &a, long long n_seg, bool need_T, double *coeff_out, SolveWs &w) {
+    using D = Dim<O>;
+    w.T = need_T ? arena_take<double>(a, n_seg) : nullptr;
+    w.base = arena_take<double>(a, (size_t)n_seg * D::NBASE);
+    w.state = arena_take<double>(a, (size_t)(n_seg + 1) * D::NSTATE);
+    w.segx = arena_take<double>(a, (size_t)n_seg * D::NSEGX);
+    w.s_star = arena_take<int>(a, n_seg);
+    w.coeff = coeff_out ? coeff_out : arena_take<double>(a, (size_t)n_seg * 3 * D::M);
+}
+
+struct SampleWs {
+    int *seg_count, *append_end;
+    double *seg_last;
+    long long *seg_start, *traj_count, *partial;
+};
+size_t sample_ws_bytes(long long n_seg, long long B) {
+    return padded(n_seg * sizeof(int)) + padded(B * sizeof(int)) + padded((size_t)n_seg * 3 * sizeof(double)) +
+           padded(n_seg * sizeof(long long)) + padded(B * sizeof(long long)) +
+           padded((size_t)(B / SCAN_BLOCK + 2) * sizeof(long long));
+}
+void carve_sample_ws(Arena &a, long long n_seg, long long B, SampleWs &s) {
+    s.seg_count = arena_take<int>(a, n_seg);
+    s.append_end = arena_take<int>(a, B);
+    s.seg_last = arena_take<double>(a, (size_t)n_seg * 3);
+    s.seg_start = arena_take<long long>(a, n_seg);
+    s.traj_count = arena_take<long long>(a, B);
+    s.partial = arena_take<long long>(a, B / SCAN_BLOCK + 2);
+}
+
+template <int O>
+int run_sample(msnap_context *h, const BatchIdx &bi, const double *coeff, const double *T, double sd,
+               long long capacity, long long *sample_offset, double *samples, double *stats, unsigned *flags,
+               SampleWs &s) {
+    const int blk = 128;
+    const unsigned gs = grid_for(bi.n_seg, blk), gb = grid_for(bi.B, blk);
+    MS_LAUNCH(h, (k_sample<O, false>), gs, blk, bi, coeff, T, sd, s.seg_count, s.seg_last, (const long long *)nullptr,
+              (const long long *)nullptr, (const int *)nullptr, 0LL, (double *)nullptr, (unsigned *)nullptr);
+    MS_LAUNCH(h, (k_traj_count<O>), gb, blk, bi, coeff, T, s.seg_count, s.seg_last, s.seg_start, s.append_end,
+              s.traj_count);
+    const int nblk = (int)grid_for(bi.B, SCAN_BLOCK);
+    MS_LAUNCH(h, k_scan_reduce, nblk, SCAN_BLOCK, s.traj_count, bi.B, s.partial);
+    MS_LAUNCH(h, k_scan_partials, 1, SCAN_BLOCK, s.partial, nblk, sample_offset + bi.B);
+    MS_LAUNCH(h, k_scan_apply, nblk, SCAN_BLOCK, s.traj_count, bi.B, s.partial, sample_offset);
+    MS_LAUNCH(h, (k_sample<O, true>), gs, blk, bi, coeff, T, sd, (int *)nullptr, (double *)nullptr, s.seg_start,
+              sample_offset, s.append_end, capacity, samples, flags);
+    if (stats) MS_LAUNCH(h, k_stats, grid_for(bi.B * 32, 256), 256, bi.B, sample_offset, samples, capacity, stats);
+    return MSNAP_OK;
+}
+
+int check_batch(long long B, int ns_uniform, const long long *seg_offset, const double *waypoints) {
+    if (B < 0 || !waypoints) return MSNAP_ERR_INVALID_ARG;
+    if (ns_uniform <= 0 && !seg_offset) return MSNAP_ERR_INVALID_ARG;
+    return MSNAP_OK;
+}
+
+template <int O>
+int solve_qp_dev(msnap_context *h, double pw, double vw, long long B, int ns_uniform, const long long *seg_offset,
+                 long long n_seg, const double *wp, const double *vel, const double *acc, const double *times,
+                 double *coeff_out, double *max_dev_out, int *best_s_out, unsigned *flags_out) {
+    BatchIdx bi{B, n_seg, ns_uniform > 0 ? ns_uniform : 0, ns_uniform > 0 ? nullptr : seg_offset};
+    SolveParams sp{};
+    sp.pw = pw;
+    sp.vw0 = vw;
+    sp.max_iter = 0;
+    sp.vel = vel;
+    sp.acc = acc;
+    int rc = arena_reserve(h, h->ws, solve_ws_bytes<O>(n_seg, false, false));
+    if (rc) return rc;
+    SolveWs w;
+    carve_solve_ws<O>(h->ws, n_seg, false, coeff_out, w);
+    SolveIO io;
+    io.wp = wp;
+    io.times_in = times;
+    io.coeff_out = coeff_out;
+    io.max_dev_out = max_dev_out;
+    io.best_s_out = best_s_out;
+    io.flags_out = flags_out;
+    return run_solve<O>(h, bi, sp, io, w);
+}
+
+template <int O>
+int generate_dev(msnap_context *h, const msnap_config *cfg, double sd, double v_avg, long long B, int ns_uniform,
+                 const long long *seg_offset, long long n_seg, const double *wp, double *times_out, double *coeff_out,
+                 double *max_dev_out, int *iters_out, double *vw_final_out, int *best_s_out, long long capacity,
+                 long long *sample_offset, double *samples, double *stats, unsigned *flags) {
+    BatchIdx bi{B, n_seg, ns_uniform > 0 ? ns_uniform : 0, ns_uniform > 0 ? nullptr : seg_offset};
+    SolveParams sp{};
+    sp.pw = cfg->path_weight;
+    sp.vw0 = cfg->vel_zero_weight;
+    sp.max_iter = 10;
+    for (int a = 0; a < 3; ++a) {
+        sp.bc[a] = cfg->start_vel[a];
+        sp.bc[3 + a] = cfg->end_vel[a];
+        sp.bc[6 + a] = cfg->start_acc[a];
+        sp.bc[9 + a] = cfg->end_acc[a];
+    }
+    int rc = arena_reserve(h, h->ws, solve_ws_bytes<O>(n_seg, true, coeff_out == nullptr) + sample_ws_bytes(n_seg, B));
+    if (rc) return rc;
+    SolveWs w;
+    carve_solve_ws<O>(h->ws, n_seg, true, coeff_out, w);
+    SampleWs s;
+    carve_sample_ws(h->ws, n_seg, B, s);
+    SolveIO io;
+    io.wp = wp;
+    io.v_avg = v_avg;
+    io.min_time = cfg->min_time_s;
+    io.times_out = times_out;
+    io.coeff_out = coeff_out;
+    io.max_dev_out = max_dev_out;
+    io.iters_out = iters_out;
+    io.vw_final_out = vw_final_out;
+    io.best_s_out = best_s_out;
+    io.flags_out = flags;
+    rc = run_solve<O>(h, bi, sp, io, w);
+    if (rc) return rc;
+    return run_sample<O>(h, bi, w.coeff, w.T, sd, capacity, sample_offset, samples, stats, flags, s);
+}
+
+#define MS_DISPATCH_ORDER(order, CALL)            \
+    switch (order) {                              \
+        case 2: { constexpr int O = 2; CALL; } break; \
+        case 3: { constexpr int O = 3; CALL; } break; \
+        case 4: { constexpr int O = 4; CALL; } break; \
+        case 5: { constexpr int O = 5; CALL; } break; \
+        default: return MSNAP_ERR_INVALID_ARG;    \
+    }
+
+// total segments of a batch whose seg_offset lives on the host
+long long host_total_segments(long long B, int ns_uniform, const long long *seg_offset) {
+    return ns_uniform > 0 ? B * (long long)ns_uniform : seg_offset[B];
+}
+
+// total segments of a batch whose seg_offset lives on the device (one 8-byte read-back for ragged batches)
+int device_total_segments(msnap_context *h, long long B, int ns_uniform, const long long *seg_offset, long long *out) {
+    if (ns_uniform > 0) {
+        *out = B * (long long)ns_uniform;
+        return MSNAP_OK;
+    }
+    MS_CUDA(h, cudaMemcpyAsync(out, seg_offset + B, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    MS_CUDA(h, cudaStreamSynchronize(h->stream));
+    return *out >= B ? MSNAP_OK : MSNAP_ERR_INVALID_ARG;
+}
+
+bool valid_host_offsets(long long B, int ns_uniform, const long long *seg_offset) {
+    if (ns_uniform > 0) return true;
+    if (seg_offset[0] != 0) return false;
+    for (long long b = 0; b < B; ++b)
+        if (seg_offset[b + 1] - seg_offset[b] < 1) return false;
+    return true;
+}
+
+// FP64 peak micro-benchmark: 8 independent DFMA chains per thread.
+__global__ void k_dfma_peak(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 123.456) out[0] = s;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+// extern "C"
+// ------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int msnap_version(void) { return MSNAP_VERSION; }
+
+const char *msnap_status_string(int status) {
+    switch (status) {
+        case MSNAP_OK: return "ok";
+        case MSNAP_ERR_INVALID_ARG: return "invalid argument";
+        case MSNAP_ERR_CUDA: return "CUDA error";
+        case MSNAP_ERR_NO_DEVICE: return "no usable CUDA device";
+        case MSNAP_ERR_CAPACITY: return "sample buffer too small";
+        case MSNAP_ERR_ALLOC: return "allocation failed";
+        case MSNAP_ERR_IO: return "I/O error";
+        default: return "unknown status";
+    }
+}
+
+const char *msnap_last_error(msnap_handle h) { return h ? h->last_error.c_str() : ""; }
+
+int msnap_create(int device, msnap_handle *out) {
+    if (!out) return MSNAP_ERR_INVALID_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+        cudaGetLastError();
+        return MSNAP_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+        cudaGetLastError();
+        return MSNAP_ERR_NO_DEVICE;  // the kernels are built for sm_100a only
+    }
+    msnap_context *h = new (std::nothrow) msnap_context();
+    if (!h) return MSNAP_ERR_ALLOC;
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    DeviceGuard guard(device);
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&h->d_tab, sizeof(h_tab)) != cudaSuccess ||
+        cudaMemcpy(h->d_tab, h_tab, sizeof(h_tab), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGetLastError();
+        if (h->d_tab) cudaFree(h->d_tab);
+        if (h->own_stream) cudaStreamDestroy(h->own_stream);
+        delete h;
+        return MSNAP_ERR_CUDA;
+    }
+    h->stream = h->own_stream;
+    *out = h;
+    return MSNAP_OK;
+}
+
+int msnap_destroy(msnap_handle h) {
+    if (!h) return MSNAP_ERR_INVALID_ARG;
+    DeviceGuard guard(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->ws.base) cudaFree(h->ws.base);
+    if (h->io.base) cudaFree(h->io.base);
+    if (h->d_tab) cudaFree(h->d_tab);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return MSNAP_OK;
+}
+
+int msnap_set_stream(msnap_handle h, void *cuda_stream) {
+    if (!h) return MSNAP_ERR_INVALID_ARG;
+    h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+    return MSNAP_OK;
+}
+
+int msnap_synchronize(msnap_handle h) {
+    if (!h) return MSNAP_ERR_INVALID_ARG;
+    DeviceGuard guard(h->device);
+    MS_CUDA(h, cudaStreamSynchronize(h->stream));
+    return MSNAP_OK;
+}
+
+int msnap_set_reweight_policy(msnap_handle h, int policy) {
+    if (!h || policy < 0 || policy > 2) return MSNAP_ERR_INVALID_ARG;
+    h->policy = policy;
+    return MSNAP_OK;
+}
+
+long long msnap_launch_count(msnap_handle h) { return h ? h->launches : 0; }
+
+void msnap_config_default(msnap_config *cfg) {
+    if (!cfg) return;
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->order = 3;
+    cfg->V_avg = 5.0;
+    cfg->min_time_s = 0.1;
+    cfg->sample_distance = 1.0;
+}
+
+// --- YAML subset: `key: value` lines, optional `minimum_snap:` wrapper, flow or block sequences for the vec3s ---
+static bool parse_double_strict(const std::string &s, double &out) {
+    if (s.empty()) return false;
+    char *end = nullptr;
+    const double v = std::strtod(s.c_str(), &end);
+    while (end && *end == ' ') ++end;
+    if (!end || *end != '\0') return false;
+    out = v;
+    return true;
+}
+static bool parse_int_strict(const std::string &s, int &out) {
+    if (s.empty()) return false;
+    char *end = nullptr;
+    const long v = std::strtol(s.c_str(), &end, 10);
+    while (end && *end == ' ') ++end;
+    if (!end || *end != '\0') return false;  // "2.0" is not an int for yaml-cpp either
+    out = (int)v;
+    return true;
+}
+static std::string trim(const std::string &s) {
+    size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
+    return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
+}
+
+int msnap_config_load_yaml(const char *path, msnap_config *cfg) {
+    if (!path || !cfg) return MSNAP_ERR_INVALID_ARG;
+    std::ifstream f(path);
+    if (!f) return MSNAP_ERR_IO;
+    struct Line { int indent; std::string key, val; std::vector<std::string> items; };
+    std::vector<Line> lines;
+    std::string raw;
+    while (std::getline(f, raw)) {
+        bool in_q = false;
+        size_t cut = std::string::npos;
+        for (size_t i = 0; i < raw.size(); ++i) {
+            if (raw[i] == '"' || raw[i] == '\'') in_q = !in_q;
+            if (raw[i] == '#' && !in_q && (i == 0 || raw[i - 1] == ' ' || raw[i - 1] == '\t')) { cut = i; break; }
+        }
+        if (cut != std::string::npos) raw = raw.substr(0, cut);
+        if (trim(raw).empty()) continue;
+        const int indent = (int)raw.find_first_not_of(" \t");
+        const std::string body = trim(raw);
+        if (body[0] == '-') {  // block sequence item of the previous key
+            if (!lines.empty()) lines.back().items.push_back(trim(body.substr(1)));
+            continue;
+        }
+        const size_t colon = body.find(':');
+        if (colon == std::string::npos) continue;
+        Line L;
+        L.indent = indent;
+        L.key = trim(body.substr(0, colon));
+        L.val = trim(body.substr(colon + 1));
+        if (!L.val.empty() && L.val.front() == '[' && L.val.back() == ']') {
+            std::stringstream ss(L.val.substr(1, L.val.size() - 2));
+            std::string item;
+            while (std::getline(ss, item, ',')) L.items.push_back(trim(item));
+        }
+        lines.push_back(L);
+    }
+    // wrapper style: use the keys nested under a top-level `minimum_snap:`
+    size_t lo = 0, hi = lines.size();
+    int want_indent = lines.empty() ? 0 : lines[0].indent;
+    for (size_t i = 0; i < lines.size(); ++i)
+        if (lines[i].key == "minimum_snap" && lines[i].val.empty() && lines[i].indent == want_indent) {
+            lo = i + 1;
+            hi = lo;
+            while (hi < lines.size() && lines[hi].indent > lines[i].indent) ++hi;
+            want_indent = lo < lines.size() ? lines[lo].indent : 0;
+            break;
+        }
+    auto scalar = [&](const char *key, double &out) {
+        for (size_t i = lo; i < hi; ++i)
+            if (lines[i].indent == want_indent && lines[i].key == key) {
+                double v;
+                if (parse_double_strict(lines[i].val, v)) out = v;
+            }
+    };
+    auto vec3 = [&](const char *key, double *out) {
+        for (size_t i = lo; i < hi; ++i)
+            if (lines[i].indent == want_indent && lines[i].key == key && lines[i].items.size() >= 3) {
+                double v[3];
+                if (parse_double_strict(lines[i].items[0], v[0]) && parse_double_strict(lines[i].items[1], v[1]) &&
+                    parse_double_strict(lines[i].items[2], v[2])) {
+                    out[0] = v[0]; out[1] = v[1]; out[2] = v[2];
+                }
+            }
+    };
+    for (size_t i = lo; i < hi; ++i)
+        if (lines[i].indent == want_indent && lines[i].key == "order") {
+            int v;
+            if (parse_int_strict(lines[i].val, v)) cfg->order = v;
+        }
+    scalar("path_weight", cfg->path_weight);
+    scalar("vel_zero_weight", cfg->vel_zero_weight);
+    scalar("V_avg", cfg->V_avg);
+    scalar("min_time_s", cfg->min_time_s);
+    scalar("sample_distance", cfg->sample_distance);
+    vec3("start_vel", cfg->start_vel);
+    vec3("end_vel", cfg->end_vel);
+    vec3("start_acc", cfg->start_acc);
+    vec3("end_acc", cfg->end_acc);
+    return MSNAP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- solve_qp
+int msnap_solve_qp_batch_dev(msnap_handle h, int order, double path_weight, double vel_zero_weight, long long B,
+                             int ns_uniform, const long long *seg_offset, const double *waypoints, const double *vel,
+                             const double *acc, const double *times, double *coeff_out, double *max_dev_out,
+                             int *best_s_out, unsigned *flags_out) {
+    if (!h) return MSNAP_ERR_INVALID_ARG;
+    int rc = check_batch(B, ns_uniform, seg_offset, waypoints);
+    if (rc) return rc;
+    if (!times || !coeff_out) return MSNAP_ERR_INVALID_ARG;
+    if (B == 0) return MSNAP_OK;
+    DeviceGuard guard(h->device);
+    long long n_seg = 0;
+    rc = device_total_segments(h, B, ns_uniform, seg_offset, &n_seg);
+    if (rc) return rc;
+    MS_DISPATCH_ORDER(order, return solve_qp_dev<O>(h, path_weight, vel_zero_weight, B, ns_uniform, seg_offset, n_seg,
+                                                     waypoints, vel, acc, times, coeff_out, max_dev_out, best_s_out,
+                                                     flags_out));
+    return MSNAP_OK;
+}
+
+int msnap_solve_qp_batch_host(msnap_handle h, int order, double path_weight, double vel_zero_weight, long long B,
+                              int ns_uniform, const long long *seg_offset, const double *waypoints, const double *vel,
+                              const double *acc, const double *times, double *coeff_out, double *max_dev_out,
+                              int *best_s_out, unsigned *flags_out) {
+    if (!h) return MSNAP_ERR_INVALID_ARG;
+    int rc = check_batch(B, ns_uniform, seg_offset, waypoints);
+    if (rc) return rc;
+    if (!times || !coeff_out || order < MSNAP_MIN_ORDER || order > MSNAP_MAX_ORDER) return MSNAP_ERR_INVALID_ARG;
+    if (B == 0) return MSNAP_OK;
+    if (!valid_host_offsets(B, ns_uniform, seg_offset)) return MSNAP_ERR_INVALID_ARG;
+    DeviceGuard guard(h->device);
+    const long long n_seg = host_total_segments(B, ns_uniform, seg_offset);
+    const size_t n_pts = (size_t)(n_seg + B), m3 = (size_t)3 * 2 * order;
+    size_t bytes = padded((B + 1) * sizeof(long long)) + padded(n_pts * 3 * sizeof(double)) +
+                   2 * padded((size_t)B * 6 * sizeof(double)) + padded(n_seg * sizeof(double)) +
+                   padded((size_t)n_seg * m3 * sizeof(double)) + padded(B * sizeof(double)) +
+                   padded(B * sizeof(unsigned)) + padded(n_seg * sizeof(int));
+    rc = arena_reserve(h, h->io, bytes);
+    if (rc) return rc;
+    long long *d_off = arena_take<long long>(h->io, B + 1);
+    double *d_wp = arena_take<double>(h->io, n_pts * 3);
+    double *d_vel = arena_take<double>(h->io, (size_t)B * 6);
+    double *d_acc = arena_take<double>(h->io, (size_t)B * 6);
+    double *d_t = arena_take<double>(h->io, n_seg);
+    double *d_c = arena_take<double>(h->io, (size_t)n_seg * m3);
+    double *d_md = arena_take<double>(h->io, B);
+    unsigned *d_fl = arena_take<unsigned>(h->io, B);
+    int *d_bs = arena_take<int>(h->io, n_seg);
+    cudaStream_t st = h->stream;
+    if (ns_uniform <= 0)
+        MS_CUDA(h, cudaMemcpyAsync(d_off, seg_offset, (B + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    MS_CUDA(h, cudaMemcpyAsync(d_wp, waypoints, n_pts * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (vel) MS_CUDA(h, cudaMemcpyAsync(d_vel, vel, (size_t)B * 6 * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (acc) MS_CUDA(h, cudaMemcpyAsync(d_acc, acc, (size_t)B * 6 * sizeof(double), cudaMemcpyHostToDevice, st));
+    MS_CUDA(h, cudaMemcpyAsync(d_t, times, n_seg * sizeof(double), cudaMemcpyHostToDevice, st));
+    MS_DISPATCH_ORDER(order, rc = solve_qp_dev<O>(h, path_weight, vel_zero_weight, B, ns_uniform,
+                                                  ns_uniform > 0 ? nullptr : d_off, n_seg, d_wp, vel ? d_vel : nullptr,
+                                                  acc ? d_acc : nullptr, d_t, d_c, d_md, best_s_out ? d_bs : nullptr, d_fl));
+    if (rc) return rc;
+    MS_CUDA(h, cudaMemcpyAsync(coeff_out, d_c, (size_t)n_seg * m3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (max_dev_out) MS_CUDA(h, cudaMemcpyAsync(max_dev_out, d_md, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (flags_out) MS_CUDA(h, cudaMemcpyAsync(flags_out, d_fl, B * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    if (best_s_out) MS_CUDA(h, cudaMemcpyAsync(best_s_out, d_bs, n_seg * sizeof(int), cudaMemcpyDeviceToHost, st));
+    MS_CUDA(h, cudaStreamSynchronize(st));
+    return MSNAP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- generate
+int msnap_generate_batch_dev(msnap_handle h, const msnap_config *cfg, double sample_distance_override,
+                             double v_avg_override, long long B, int ns_uniform, const long long *seg_offset,
+                             const double *waypoints, double *times_out, double *coeff_out, double *max_dev_out,
+                             int *iters_out, double *vw_final_out, int *best_s_out, long long sample_capacity,
+                             long long *sample_offset_out, double *samples_out, double *stats_out,
+                             unsigned *flags_out) {
+    if (!h || !cfg) return MSNAP_ERR_INVALID_ARG;
+    int rc = check_batch(B, ns_uniform, seg_offset, waypoints);
+    if (rc) return rc;
+    if (!sample_offset_out || (!samples_out && sample_capacity > 0) || sample_capacity < 0) return MSNAP_ERR_INVALID_ARG;
+    if (B == 0) return MSNAP_OK;
+    DeviceGuard guard(h->device);
+    long long n_seg = 0;
+    rc = device_total_segments(h, B, ns_uniform, seg_offset, &n_seg);
+    if (rc) return rc;
+    const double sd = sample_distance_override > 0.0 ? sample_distance_override : cfg->sample_distance;  // ms.cpp:42-44
+    const double va = v_avg_override > 0.0 ? v_avg_override : cfg->V_avg;                                // ms.cpp:46-48
+    MS_DISPATCH_ORDER(cfg->order,
+                      return generate_dev<O>(h, cfg, sd, va, B, ns_uniform, seg_offset, n_seg, waypoints, times_out,
+                                             coeff_out, max_dev_out, iters_out, vw_final_out, best_s_out, sample_capacity,
+                                             sample_offset_out, samples_out, stats_out, flags_out));
+    return MSNAP_OK;
+}
+
+int msnap_generate_batch_host(msnap_handle h, const msnap_config *cfg, double sample_distance_override,
+                              double v_avg_override, long long B, int ns_uniform, const long long *seg_offset,
+                              const double *waypoints, double *times_out, double *coeff_out, double *max_dev_out,
+                              int *iters_out, double *vw_final_out, int *best_s_out, long long sample_capacity,
+                              long long *sample_offset_out, double *samples_out, double *stats_out,
+                              unsigned *flags_out) {
+    if (!h || !cfg) return MSNAP_ERR_INVALID_ARG;
+    int rc = check_batch(B, ns_uniform, seg_offset, waypoints);
+    if (rc) return rc;
+    if (!sample_offset_out || (!samples_out && sample_capacity > 0) || sample_capacity < 0 ||
+        cfg->order < MSNAP_MIN_ORDER || cfg->order > MSNAP_MAX_ORDER)
+        return MSNAP_ERR_INVALID_ARG;
+    if (B == 0) { sample_offset_out[0] = 0; return MSNAP_OK; }
+    if (!valid_host_offsets(B, ns_uniform, seg_offset)) return MSNAP_ERR_INVALID_ARG;
+    DeviceGuard guard(h->device);
+    const long long n_seg = host_total_segments(B, ns_uniform, seg_offset);
+    const size_t n_pts = (size_t)(n_seg + B), m3 = (size_t)3 * 2 * cfg->order;
+    size_t bytes = padded((B + 1) * sizeof(long long)) + padded(n_pts * 3 * sizeof(double)) +
+                   padded(n_seg * sizeof(double)) + padded((size_t)n_seg * m3 * sizeof(double)) +
+                   2 * padded(B * sizeof(double)) + padded(B * sizeof(int)) + padded((B + 1) * sizeof(long long)) +
+                   padded((size_t)sample_capacity * 3 * sizeof(double)) + padded((size_t)B * 2 * sizeof(double)) +
+                   padded(B * sizeof(unsigned)) + padded(n_seg * sizeof(int));
+    rc = arena_reserve(h, h->io, bytes);
+    if (rc) return rc;
+    long long *d_off = arena_take<long long>(h->io, B + 1);
+    double *d_wp = arena_take<double>(h->io, n_pts * 3);
+    double *d_t = arena_take<double>(h->io, n_seg);
+    double *d_c = arena_take<double>(h->io, (size_t)n_seg * m3);
+    double *d_md = arena_take<double>(h->io, B);
+    double *d_vw = arena_take<double>(h->io, B);
+    int *d_it = arena_take<int>(h->io, B);
+    long long *d_so = arena_take<long long>(h->io, B + 1);
+    double *d_s = arena_take<double>(h->io, (size_t)sample_capacity * 3);
+    double *d_st = arena_take<double>(h->io, (size_t)B * 2);
+    unsigned *d_fl = arena_take<unsigned>(h->io, B);
+    int *d_bs = arena_take<int>(h->io, n_seg);
+    cudaStream_t st = h->stream;
+    if (ns_uniform <= 0)
+        MS_CUDA(h, cudaMemcpyAsync(d_off, seg_offset, (B + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    MS_CUDA(h, cudaMemcpyAsync(d_wp, waypoints, n_pts * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    const double sd = sample_distance_override > 0.0 ? sample_distance_override : cfg->sample_distance;
+    const double va = v_avg_override > 0.0 ? v_avg_override : cfg->V_avg;
+    MS_DISPATCH_ORDER(cfg->order,
+                      rc = generate_dev<O>(h, cfg, sd, va, B, ns_uniform, ns_uniform > 0 ? nullptr : d_off, n_seg, d_wp,
+                                           times_out ? d_t : nullptr, coeff_out ? d_c : nullptr, d_md, d_it, d_vw,
+                                           best_s_out ? d_bs : nullptr, sample_capacity, d_so, d_s, stats_out ? d_st : nullptr, d_fl));
+    if (rc) return rc;
+    MS_CUDA(h, cudaMemcpyAsync(sample_offset_out, d_so, (B + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    if (times_out) MS_CUDA(h, cudaMemcpyAsync(times_out, d_t, n_seg * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (coeff_out)
+        MS_CUDA(h, cudaMemcpyAsync(coeff_out, d_c, (size_t)n_seg * m3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (max_dev_out) MS_CUDA(h, cudaMemcpyAsync(max_dev_out, d_md, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (vw_final_out) MS_CUDA(h, cudaMemcpyAsync(vw_final_out, d_vw, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (iters_out) MS_CUDA(h, cudaMemcpyAsync(iters_out, d_it, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (best_s_out) MS_CUDA(h, cudaMemcpyAsync(best_s_out, d_bs, n_seg * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (stats_out) MS_CUDA(h, cudaMemcpyAsync(stats_out, d_st, (size_t)B * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (flags_out) MS_CUDA(h, cudaMemcpyAsync(flags_out, d_fl, B * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    MS_CUDA(h, cudaStreamSynchronize(st));  // sample_offset_out[B] = exact row count
+    const long long total = sample_offset_out[B];
+    const long long rows = total < sample_capacity ? total : sample_capacity;
+    if (rows > 0) {
+        MS_CUDA(h, cudaMemcpyAsync(samples_out, d_s, (size_t)rows * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        MS_CUDA(h, cudaStreamSynchronize(st));
+    }
+    return total > sample_capacity ? MSNAP_ERR_CAPACITY : MSNAP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- bound
+int msnap_sample_bound_dev(msnap_handle h, const msnap_config *cfg, double v_avg_override, long long B, int ns_uniform,
+                           const long long *seg_offset, const double *waypoints, long long *rows_out_dev) {
+    if (!h || !cfg || !rows_out_dev) return MSNAP_ERR_INVALID_ARG;
+    int rc = check_batch(B, ns_uniform, seg_offset, waypoints);
+    if (rc) return rc;
+    DeviceGuard guard(h->device);
+    MS_CUDA(h, cudaMemsetAsync(rows_out_dev, 0, sizeof(long long), h->stream));
+    if (B == 0) return MSNAP_OK;
+    long long n_seg = 0;
+    rc = device_total_segments(h, B, ns_uniform, seg_offset, &n_seg);
+    if (rc) return rc;
+    BatchIdx bi{B, n_seg, ns_uniform > 0 ? ns_uniform : 0, ns_uniform > 0 ? nullptr : seg_offset};
+    const double va = v_avg_override > 0.0 ? v_avg_override : cfg->V_avg;
+    MS_LAUNCH(h, k_bound, grid_for(n_seg, 256), 256, bi, waypoints, va, cfg->min_time_s,
+              reinterpret_cast<unsigned long long *>(rows_out_dev));
+    return MSNAP_OK;
+}
+
+int msnap_sample_bound_host(msnap_handle h, const msnap_config *cfg, double v_avg_override, long long B,
+                            int ns_uniform, const long long *seg_offset, const double *waypoints, long long *rows_out) {
+    if (!h || !cfg || !rows_out) return MSNAP_ERR_INVALID_ARG;
+    int rc = check_batch(B, ns_uniform, seg_offset, waypoints);
+    if (rc) return rc;
+    *rows_out = 0;
+    if (B == 0) return MSNAP_OK;
+    if (!valid_host_offsets(B, ns_uniform, seg_offset)) return MSNAP_ERR_INVALID_ARG;
+    DeviceGuard guard(h->device);
+    const long long n_seg = host_total_segments(B, ns_uniform, seg_offset);
+    const size_t n_pts = (size_t)(n_seg + B);
+    rc = arena_reserve(h, h->io, padded((B + 1) * sizeof(long long)) + padded(n_pts * 3 * sizeof(double)) + 256);
+    if (rc) return rc;
+    long long *d_off = arena_take<long long>(h->io, B + 1);
+    double *d_wp = arena_take<double>(h->io, n_pts * 3);
+    long long *d_rows = arena_take<long long>(h->io, 1);
+    cudaStream_t st = h->stream;
+    if (ns_uniform <= 0)
+        MS_CUDA(h, cudaMemcpyAsync(d_off, seg_offset, (B + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    MS_CUDA(h, cudaMemcpyAsync(d_wp, waypoints, n_pts * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = msnap_sample_bound_dev(h, cfg, v_avg_override, B, ns_uniform, ns_uniform > 0 ? nullptr : d_off, d_wp, d_rows);
+    if (rc) return rc;
+    MS_CUDA(h, cudaMemcpyAsync(rows_out, d_rows, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    MS_CUDA(h, cudaStreamSynchronize(st));
+    return MSNAP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- single
+int msnap_generate_one_host(msnap_handle h, const msnap_config *cfg, double sample_distance_override,
+                            double v_avg_override, int n_points, const double *waypoints, long long sample_capacity,
+                            double *samples_out, long long *n_samples_out) {
+    if (n_samples_out) *n_samples_out = 0;
+    if (!h || !cfg || !n_samples_out || n_points < 2) return MSNAP_ERR_INVALID_ARG;
+    long long off[2] = {0, 0};
+    int rc = msnap_generate_batch_host(h, cfg, sample_distance_override, v_avg_override, 1, n_points - 1, nullptr,
+                                       waypoints, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, sample_capacity,
+                                       off,
+                                       samples_out, nullptr, nullptr);
+    *n_samples_out = off[1];
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------- fp64 peak
+int msnap_measure_fp64_peak(msnap_handle h, double *tflops_out) {
+    if (!h || !tflops_out) return MSNAP_ERR_INVALID_ARG;
+    DeviceGuard guard(h->device);
+    double *d = nullptr;
+    MS_CUDA(h, cudaMalloc(&d, 64));
+    cudaEvent_t e0, e1;
+    MS_CUDA(h, cudaEventCreate(&e0));
+    MS_CUDA(h, cudaEventCreate(&e1));
+    const int iters = 1 << 14, block = 256, grid = h->sm_count * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        MS_CUDA(h, cudaEventRecord(e0, h->stream));
+        MS_LAUNCH(h, k_dfma_peak, grid, block, d, iters, 1.0000001, 1e-9);
+        MS_CUDA(h, cudaEventRecord(e1, h->stream));
+        MS_CUDA(h, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        MS_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
+        const double tf = 2.0 * 8.0 * (double)iters * block * grid / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *tflops_out = best;
+    return MSNAP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,541 @@
+// msnap_generic.cuh -- the general-shape kernel set: any order 2..5, any segment count >= 1, mixed lengths (CSR).
+//
+// One kernel per phase, intermediates in an HBM workspace laid out per segment.  This path is the reference
+// implementation *inside* the product (it defines what the fused small-trajectory kernels must reproduce bit for
+// bit) and the path long / ragged batches take.  Phases and the reference lines they replace:
+//   k_times       ms.cpp:63-72     segment time allocation
+//   k_rows        ms.cpp:247-330, 441-469, 474-511 (M, Q, A, V, R)  -> block-tridiagonal rows, O(1) per row
+//   k_thomas      ms.cpp:398, 579  (R_PP^-1)  + reweighting loop ms.cpp:76-90 + deviation test ms.cpp:594-624
+//   k_search      ms.cpp:408-439   worst-deviation sample per segment
+//   k_coeff       ms.cpp:402-404, 584-591, 626-646  (M^-1 d, PolyCoeff packing)
+//   k_count/k_traj_count/scan/k_write  ms.cpp:97-161  distance-thresholded sampler, exact CSR output
+//   k_stats       ms.cpp:163-195   climb rate / turn radius
+#ifndef MSNAP_GENERIC_CUH
+#define MSNAP_GENERIC_CUH
+
+#include "msnap_device.cuh"
+
+namespace msnap {
+
+struct BatchIdx {
+    long long B;
+    long long n_seg;              // total segments
+    int ns_uniform;               // > 0: uniform batch, seg_offset unused
+    const long long *seg_offset;  // [B+1] device, or nullptr
+    __device__ __forceinline__ long long seg_begin(long long b) const {
+        return ns_uniform > 0 ? b * ns_uniform : seg_offset[b];
+    }
+    // trajectory b and local segment k of global segment g
+    __device__ __forceinline__ void locate(long long g, long long &b, int &k, int &ns) const {
+        if (ns_uniform > 0) {
+            b = g / ns_uniform;
+            k = (int)(g - b * ns_uniform);
+            ns = ns_uniform;
+            return;
+        }
+        long long lo = 0, hi = B;  // find b with seg_offset[b] <= g < seg_offset[b+1]
+        while (hi - lo > 1) {
+            const long long mid = (lo + hi) >> 1;
+            if (seg_offset[mid] <= g) lo = mid; else hi = mid;
+        }
+        b = lo;
+        k = (int)(g - seg_offset[lo]);
+        ns = (int)(seg_offset[lo + 1] - seg_offset[lo]);
+    }
+};
+
+struct SolveParams {
+    double pw;           // path_weight (penalty active iff > 0)
+    double vw0;          // initial vel_zero_weight
+    int max_iter;        // 10 for GenerateTrajectoryMatrix, 0 for a bare SolveQPClosedForm
+    const double *vel;   // [B][2][3] or nullptr
+    const double *acc;   // [B][2][3] or nullptr
+    double bc[12];       // start_vel, end_vel, start_acc, end_acc used when vel/acc are nullptr
+};
+
+template <int O>
+__device__ __forceinline__ void boundary_of(const SolveParams &sp, long long b, Boundary<O> &bc) {
+    const double *v = sp.vel ? sp.vel + 6 * b : sp.bc;
+    const double *a = sp.acc ? sp.acc + 6 * b : sp.bc + 6;
+    load_boundary<O>(bc, v, a);
+}
+
+// ------------------------------------------------------------------------------------------------ k_times
+// T_k = max(|P_{k+1} - P_k| / V_avg, min_time) -- plain IEEE mul/add (no FMA contraction) so the allocated
+// times, and with them the sampler's candidate grid, are bit-identical to the reference's (ms.cpp:63-72).
+__global__ void k_times(BatchIdx bi, const double *__restrict__ wp, double v_avg, double min_time,
+                        double *__restrict__ T) {
+    const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (g >= bi.n_seg) return;
+    long long b; int k, ns;
+    bi.locate(g, b, k, ns);
+    const double *p = wp + 3 * (g + b);
+    const double dx = __dsub_rn(p[3], p[0]), dy = __dsub_rn(p[4], p[1]), dz = __dsub_rn(p[5], p[2]);
+    const double len = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+    double t = (v_avg > 1e-6) ? __ddiv_rn(len, v_avg) : min_time;
+    if (t < min_time) t = min_time;
+    T[g] = t;
+}
+
+// ------------------------------------------------------------------------------------------------ k_rows
+// Thread per segment g = (b, k).  k >= 1 assembles row j = k (between segments k-1 and k) into base[g];
+// with the path penalty active every thread also writes its segment's deviation probe segx[g].
+template <int O>
+__global__ void k_rows(BatchIdx bi, SolveParams sp, const double *__restrict__ wp, const double *__restrict__ T,
+                       bool use_pw, const int *__restrict__ s_star, const double *__restrict__ ht,
+                       double *__restrict__ base, double *__restrict__ segx) {
+    using D = Dim<O>;
+    const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (g >= bi.n_seg) return;
+    long long b; int k, ns;
+    bi.locate(g, b, k, ns);
+    const double *p = wp + 3 * (g + b);  // waypoint k of trajectory b
+    const double Tc = T[g];
+    if (use_pw) {  // probe of segment k: h, L(t*), 1/len
+        double ip[2 * O], pT[O], h[2 * O];
+        time_powers<O>(Tc, ip, pT);
+        const int s = s_star[g];
+        hermite_at<O>(ht, s, pT, h);
+        double *x = segx + g * D::NSEGX;
+#pragma unroll
+        for (int i = 0; i < 2 * O; ++i) x[i] = h[i];
+        const double tau = (double)s * 0.0625;
+        double l2 = 0.0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double d = p[3 + a] - p[a];
+            x[2 * O + a] = p[a] + tau * d;
+            l2 += d * d;
+        }
+        const double len = sqrt(l2);
+        x[2 * O + 3] = len > 1e-6 ? 1.0 / len : 0.0;
+    }
+    if (k == 0) return;
+    Boundary<O> bc;
+    boundary_of<O>(sp, b, bc);
+    double Pm[3], P0[3], Pp[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        Pm[a] = p[a - 3];
+        P0[a] = p[a];
+        Pp[a] = p[a + 3];
+    }
+    assemble_row<O>(T[g - 1], Tc, Pm, P0, Pp, k == 1, k == ns - 1, bc, use_pw, sp.pw, use_pw ? s_star[g - 1] : 0,
+                    use_pw ? s_star[g] : 0, ht, base + g * D::NBASE, 1);
+}
+
+// ------------------------------------------------------------------------------------------------ k_thomas
+// Thread per trajectory: block-tridiagonal Cholesky for the three axes, and -- when eval_dev -- the reweighting
+// loop of ms.cpp:76-90: solve, measure max deviation at the recorded t*, double vel_zero_weight while
+// max_dev > 0.2 and iter < max_iter.  The final x stays in state[]; per-trajectory results go to the out arrays.
+template <int O>
+__global__ void k_thomas(BatchIdx bi, SolveParams sp, const double *__restrict__ wp, const double *__restrict__ base,
+                         double *__restrict__ state, const double *__restrict__ segx, bool eval_dev, bool use_vw,
+                         double *__restrict__ max_dev_out, int *__restrict__ iters_out,
+                         double *__restrict__ vw_final_out, unsigned *__restrict__ flags) {
+    using D = Dim<O>;
+    constexpr int NR = D::NR;
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= bi.B) return;
+    const long long g0 = bi.seg_begin(b);
+    const int ns = (int)(bi.seg_begin(b + 1) - g0);
+    const int n_rows = ns - 1;
+    Boundary<O> bc;
+    boundary_of<O>(sp, b, bc);
+    auto base_at = [&](int j, int &fs) -> const double * { fs = 1; return base + (g0 + 1 + j) * D::NBASE; };
+    auto state_at = [&](int j, int &fs) -> double * { fs = 1; return state + (g0 + 1 + j) * D::NSTATE; };
+
+    double vw = use_vw ? sp.vw0 : 0.0;
+    int iter = 0;
+    double max_dev = 0.0;
+    bool ok = true;
+    while (true) {
+        const double add00 = vw > 0.0 ? 2.0 * vw : 0.0;
+        ok = thomas_forward<O>(n_rows, add00, base_at, state_at) && ok;
+        // backward sweep; the deviation of segment j+1.. is probed as soon as both its endpoints are known
+        double xn[NR], x[NR];
+#pragma unroll
+        for (int i = 0; i < NR; ++i) xn[i] = 0.0;
+        double yk[3][O], yk1[3][O];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int r = 0; r < O; ++r) yk1[a][r] = bc.yN[a][r];
+        {
+            const double *pN = wp + 3 * (g0 + b + ns);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) yk1[a][0] = pN[a];
+        }
+        max_dev = 0.0;
+        for (int j = n_rows - 1; j >= -1; --j) {
+            // waypoint j+1 (row j) -> yk ; for j == -1 the start waypoint
+            const double *pk = wp + 3 * (g0 + b + j + 1);
+            if (j >= 0) {
+                int bfs, sfs;
+                const double *bb = base_at(j, bfs);
+                double *ss = state_at(j, sfs);
+                thomas_back_step<O>(bb, bfs, ss, sfs, j + 1 < n_rows, xn, x);
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    yk[a][0] = pk[a];
+#pragma unroll
+                    for (int r = 1; r < O; ++r) yk[a][r] = x[(r - 1) * 3 + a];
+                }
+#pragma unroll
+                for (int i = 0; i < NR; ++i) xn[i] = x[i];
+            } else {
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    yk[a][0] = pk[a];
+#pragma unroll
+                    for (int r = 1; r < O; ++r) yk[a][r] = bc.y0[a][r];
+                }
+            }
+            if (eval_dev) {
+                const double ratio = deviation_ratio<O>(segx + (g0 + j + 1) * D::NSEGX, 1, yk, yk1);
+                if (ratio > max_dev) max_dev = ratio;
+            }
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int r = 0; r < O; ++r) yk1[a][r] = yk[a][r];
+        }
+        if (max_dev > 0.2 && iter < sp.max_iter) {
+            vw = (vw < 1e-6) ? 0.01 : vw * 2.0;
+            ++iter;
+        } else {
+            break;
+        }
+    }
+    if (max_dev_out) max_dev_out[b] = max_dev;
+    if (iters_out) iters_out[b] = iter;
+    if (vw_final_out) vw_final_out[b] = vw;
+    if (flags && (!ok || !(max_dev == max_dev))) atomicOr(flags + b, 1u);
+}
+
+// Endpoint derivative vectors of segment g = (b, k) from the boundary data and the solved rows.
+template <int O>
+__device__ __forceinline__ void load_endpoints(const BatchIdx &bi, const SolveParams &sp, const double *wp,
+                                               const double *state, long long g, long long b, int k, int ns,
+                                               double (&yk)[3][O], double (&yk1)[3][O]) {
+    using D = Dim<O>;
+    const double *p = wp + 3 * (g + b);
+    Boundary<O> bc;
+    boundary_of<O>(sp, b, bc);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        yk[a][0] = p[a];
+        yk1[a][0] = p[3 + a];
+#pragma unroll
+        for (int r = 1; r < O; ++r) {
+            yk[a][r] = (k == 0) ? bc.y0[a][r] : state[g * D::NSTATE + D::ND + (r - 1) * 3 + a];
+            yk1[a][r] = (k == ns - 1) ? bc.yN[a][r] : state[(g + 1) * D::NSTATE + D::ND + (r - 1) * 3 + a];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ k_search
+// Thread per segment: the 17-sample arg-max of ms.cpp:408-439 on the pass-1 solution (first strict maximum).
+template <int O>
+__global__ void k_search(BatchIdx bi, SolveParams sp, const double *__restrict__ wp, const double *__restrict__ T,
+                         const double *__restrict__ state, int *__restrict__ s_star) {
+    const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (g >= bi.n_seg) return;
+    long long b; int k, ns;
+    bi.locate(g, b, k, ns);
+    double yk[3][O], yk1[3][O];
+    load_endpoints<O>(bi, sp, wp, state, g, b, k, ns, yk, yk1);
+    double ip[2 * O], pT[O];
+    time_powers<O>(T[g], ip, pT);
+    double dh[3][2 * O];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int i = 0; i < O; ++i) {
+            dh[a][i] = pT[i] * yk[a][i];
+            dh[a][O + i] = pT[i] * yk1[a][i];
+        }
+    double best = -1.0;
+    int best_s = 0;
+#pragma unroll
+    for (int s = 0; s <= 16; ++s) {
+        const double tau = (double)s * 0.0625;
+        double d2 = 0.0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            double p = 0.0;
+#pragma unroll
+            for (int i = 0; i < 2 * O; ++i) p += Tab<O>::HT(s, i) * dh[a][i];
+            const double dd = p - (yk[a][0] + tau * (yk1[a][0] - yk[a][0]));
+            d2 += dd * dd;
+        }
+        if (d2 > best) {
+            best = d2;
+            best_s = s;
+        }
+    }
+    s_star[g] = best_s;
+}
+
+// ------------------------------------------------------------------------------------------------ k_coeff
+// Thread per segment: polynomial coefficients, PolyCoeff row layout [axis][power hi->lo] (ms.cpp:626-646).
+template <int O>
+__global__ void k_coeff(BatchIdx bi, SolveParams sp, const double *__restrict__ wp, const double *__restrict__ T,
+                        const double *__restrict__ state, double *__restrict__ coeff, unsigned *__restrict__ flags) {
+    constexpr int M = 2 * O;
+    const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (g >= bi.n_seg) return;
+    long long b; int k, ns;
+    bi.locate(g, b, k, ns);
+    double yk[3][O], yk1[3][O];
+    load_endpoints<O>(bi, sp, wp, state, g, b, k, ns, yk, yk1);
+    double ip[2 * O], pT[O];
+    time_powers<O>(T[g], ip, pT);
+    bool finite = true;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        double c[M];
+        hermite_coeffs<O>(yk[a], yk1[a], ip, pT, c);
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            coeff[(g * 3 + a) * M + i] = c[i];
+            finite = finite && (fabs(c[i]) <= 1.7976931348623157e308);
+        }
+    }
+    if (flags && !finite) atomicOr(flags + b, 1u);
+}
+
+// ------------------------------------------------------------------------------------------------ sampler
+// Candidate times of a segment follow ms.cpp:124-141 exactly: dt = min(0.1, T/10), t accumulated by repeated
+// addition (NOT i*dt), loop while t <= T + 1e-12, evaluated at min(t, T).
+__device__ __forceinline__ double sample_dt(double T) {
+    double dt = 0.1;
+    const double t10 = __ddiv_rn(T, 10.0);
+    if (dt > t10) dt = t10;
+    return dt;
+}
+
+template <int O>
+__device__ __forceinline__ void load_coeff(const double *__restrict__ coeff, long long g, double (&c)[3][2 * O]) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int i = 0; i < 2 * O; ++i) c[a][i] = coeff[(g * 3 + a) * 2 * O + i];
+}
+
+// Thread per segment.  WRITE == false: count accepted candidates, remember the last accepted point.
+// WRITE == true : store accepted candidates at rows sample_offset[b] + seg_start[g] + i (plus the trajectory's
+// first point / appended end point), dropping rows >= capacity.
+template <int O, bool WRITE>
+__global__ void k_sample(BatchIdx bi, const double *__restrict__ coeff, const double *__restrict__ T,
+                         double sample_distance, int *__restrict__ seg_count, double *__restrict__ seg_last,
+                         const long long *__restrict__ seg_start, const long long *__restrict__ sample_offset,
+                         const int *__restrict__ append_end, long long capacity, double *__restrict__ samples,
+                         unsigned *__restrict__ flags) {
+    const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (g >= bi.n_seg) return;
+    long long b = 0; int k = 0, ns = 0;
+    if (WRITE) bi.locate(g, b, k, ns);
+    double c[3][2 * O];
+    load_coeff<O>(coeff, g, c);
+    const double Tk = T[g];
+    const double dt = sample_dt(Tk);
+    double prev[3], cur[3];
+    eval_xyz<O>(c, 0.0, prev);
+    long long row = 0;
+    bool dropped = false;
+    if (WRITE) {
+        row = sample_offset[b] + seg_start[g];
+        if (k == 0) {  // very first point of the trajectory (ms.cpp:132-137)
+            const long long r0 = sample_offset[b];
+            if (r0 < capacity) {
+                samples[3 * r0] = prev[0]; samples[3 * r0 + 1] = prev[1]; samples[3 * r0 + 2] = prev[2];
+            } else dropped = true;
+        }
+    }
+    int cnt = 0;
+    const double tmax = Tk + 1e-12;
+    for (double t = dt; t <= tmax; t += dt) {
+        const double tt = fmin(t, Tk);
+        eval_xyz<O>(c, tt, cur);
+        if (dist3(cur, prev) >= sample_distance) {
+            prev[0] = cur[0]; prev[1] = cur[1]; prev[2] = cur[2];
+            if (WRITE) {
+                if (row < capacity) {
+                    samples[3 * row] = cur[0]; samples[3 * row + 1] = cur[1]; samples[3 * row + 2] = cur[2];
+                } else dropped = true;
+                ++row;
+            }
+            ++cnt;
+        }
+    }
+    if (!WRITE) {
+        seg_count[g] = cnt;
+        seg_last[3 * g] = prev[0]; seg_last[3 * g + 1] = prev[1]; seg_last[3 * g + 2] = prev[2];
+    } else {
+        if (k == ns - 1 && append_end[b]) {  // end point appended after the last segment (ms.cpp:157-160)
+            eval_xyz<O>(c, Tk, cur);
+            const long long re = sample_offset[b + 1] - 1;
+            if (re < capacity) {
+                samples[3 * re] = cur[0]; samples[3 * re + 1] = cur[1]; samples[3 * re + 2] = cur[2];
+            } else dropped = true;
+        }
+        if (dropped && flags) atomicOr(flags + b, 2u);
+    }
+}
+
+// Thread per trajectory: per-segment start rows (relative to the trajectory), the end-point rule, total count.
+template <int O>
+__global__ void k_traj_count(BatchIdx bi, const double *__restrict__ coeff, const double *__restrict__ T,
+                             const int *__restrict__ seg_count, const double *__restrict__ seg_last,
+                             long long *__restrict__ seg_start, int *__restrict__ append_end,
+                             long long *__restrict__ traj_count) {
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= bi.B) return;
+    const long long g0 = bi.seg_begin(b), g1 = bi.seg_begin(b + 1);
+    long long total = 1;  // first point
+    long long last_g = -1;
+    for (long long g = g0; g < g1; ++g) {
+        seg_start[g] = total;
+        const int c = seg_count[g];
+        total += c;
+        if (c > 0) last_g = g;
+    }
+    double back[3], endp[3], c[3][2 * O];
+    if (last_g >= 0) {
+        back[0] = seg_last[3 * last_g]; back[1] = seg_last[3 * last_g + 1]; back[2] = seg_last[3 * last_g + 2];
+    } else {
+        load_coeff<O>(coeff, g0, c);
+        eval_xyz<O>(c, 0.0, back);
+    }
+    load_coeff<O>(coeff, g1 - 1, c);
+    eval_xyz<O>(c, T[g1 - 1], endp);
+    const int app = dist3(back, endp) > 1e-6 ? 1 : 0;
+    append_end[b] = app;
+    traj_count[b] = total + app;
+}
+
+// Exclusive scan of int64 counts into offsets[n+1], three small kernels (n up to millions; traffic negligible).
+constexpr int SCAN_BLOCK = 1024;
+__global__ void k_scan_reduce(const long long *__restrict__ in, long long n, long long *__restrict__ partial) {
+    __shared__ long long sh[32];
+    const long long i = blockIdx.x * (long long)SCAN_BLOCK + threadIdx.x;
+    long long v = i < n ? in[i] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = sh[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) partial[blockIdx.x] = v;
+    }
+}
+// single block: partial[] -> exclusive prefix in place; total into *total_out
+__global__ void k_scan_partials(long long *__restrict__ partial, int nblk, long long *__restrict__ total_out) {
+    __shared__ long long sh[SCAN_BLOCK];
+    __shared__ long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nblk; base += SCAN_BLOCK) {
+        const int i = base + threadIdx.x;
+        const long long v = i < nblk ? partial[i] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < SCAN_BLOCK; o <<= 1) {
+            long long t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < nblk) partial[i] = carry + sh[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += sh[SCAN_BLOCK - 1];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = carry;
+}
+__global__ void k_scan_apply(const long long *__restrict__ in, long long n, const long long *__restrict__ partial,
+                             long long *__restrict__ offsets) {
+    __shared__ long long sh[SCAN_BLOCK];
+    const long long i = blockIdx.x * (long long)SCAN_BLOCK + threadIdx.x;
+    const long long v = i < n ? in[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < SCAN_BLOCK; o <<= 1) {
+        long long t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += t;
+        __syncthreads();
+    }
+    if (i < n) offsets[i] = partial[blockIdx.x] + sh[threadIdx.x] - v;
+    // offsets[n] is written by k_scan_partials (total_out == offsets + n)
+}
+
+// ------------------------------------------------------------------------------------------------ k_stats
+// Warp per trajectory: max |dz|/dxy over consecutive samples and min circumradius over consecutive triples
+// (ms.cpp:163-195).  Rows beyond the caller's capacity were never written and are skipped.
+__global__ void k_stats(long long B, const long long *__restrict__ sample_offset, const double *__restrict__ samples,
+                        long long capacity, double *__restrict__ stats) {
+    const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= B) return;
+    const long long r0 = sample_offset[w];
+    long long r1 = sample_offset[w + 1];
+    if (r1 > capacity) r1 = capacity;
+    double climb = 0.0, radius = 1.0e12;
+    for (long long i = r0 + lane; i + 1 < r1; i += 32) {
+        const double *p1 = samples + 3 * i, *p2 = p1 + 3;
+        const double dx = p2[0] - p1[0], dy = p2[1] - p1[1], dz = fabs(p2[2] - p1[2]);
+        const double hd = sqrt(dx * dx + dy * dy);
+        if (hd > 1e-6) climb = fmax(climb, dz / hd);
+        if (i > r0) {
+            const double *p0 = p1 - 3;
+            const double ax = p1[0] - p0[0], ay = p1[1] - p0[1], az = p1[2] - p0[2];
+            const double cx = p2[0] - p0[0], cy = p2[1] - p0[1], cz = p2[2] - p0[2];
+            const double a = sqrt(ax * ax + ay * ay + az * az);
+            const double bl = sqrt(dx * dx + dy * dy + (p2[2] - p1[2]) * (p2[2] - p1[2]));
+            const double c = sqrt(cx * cx + cy * cy + cz * cz);
+            const double ux = ay * cz - az * cy, uy = az * cx - ax * cz, uz = ax * cy - ay * cx;
+            const double area = 0.5 * sqrt(ux * ux + uy * uy + uz * uz);
+            if (area > 1e-8) radius = fmin(radius, (a * bl * c) / (4.0 * area));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        climb = fmax(climb, __shfl_down_sync(0xffffffffu, climb, o));
+        radius = fmin(radius, __shfl_down_sync(0xffffffffu, radius, o));
+    }
+    if (lane == 0) {
+        stats[2 * w] = climb;
+        stats[2 * w + 1] = radius;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ k_bound
+// Upper bound of sample rows: candidates per segment (from T alone) + first and last point per trajectory.
+__global__ void k_bound(BatchIdx bi, const double *__restrict__ wp, double v_avg, double min_time,
+                        unsigned long long *__restrict__ total) {
+    const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    unsigned long long n = 0;
+    if (g < bi.n_seg) {
+        long long b; int k, ns;
+        bi.locate(g, b, k, ns);
+        const double *p = wp + 3 * (g + b);
+        const double dx = __dsub_rn(p[3], p[0]), dy = __dsub_rn(p[4], p[1]), dz = __dsub_rn(p[5], p[2]);
+        const double len = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+        double t = (v_avg > 1e-6) ? __ddiv_rn(len, v_avg) : min_time;
+        if (t < min_time) t = min_time;
+        const double dt = sample_dt(t);
+        n = (dt == 0.1) ? (unsigned long long)(t / 0.1) + 2ull : 12ull;
+        if (k == 0) n += 2ull;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_down_sync(0xffffffffu, n, o);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(total, n);
+}
+
+}  // namespace msnap
+
+#endif  // MSNAP_GENERIC_CUH

@@ -1,0 +1,157 @@
+/* include/msnap.h -- C ABI of the B200-native batched minimum-snap trajectory solver.
+ *
+ * This is the drop-in boundary for the reference's TrajectoryGeneratorTool
+ *   /root/reference/math_util/minimum_snap.hpp:36-63   (class)
+ *   /root/reference/math_util/minimum_snap.cpp:22-206   GenerateTrajectoryMatrix
+ *   /root/reference/math_util/minimum_snap.cpp:227-649  SolveQPClosedForm
+ * as called by UavPathPlanner::Minisnap_3D / Minisnap_EN (/root/reference/uavPathPlanning.cpp:4401-4474).
+ * Plain pointers and sizes only; no C++/torch types.  INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *   - A batch holds B independent trajectories.  Trajectory b has ns_b >= 1 segments and ns_b + 1 waypoints.
+ *     Segments are indexed CSR-style by seg_offset[B+1] (seg_offset[0] = 0); the waypoints of trajectory b start at
+ *     point index seg_offset[b] + b.  If every trajectory has the same segment count pass seg_offset = NULL and
+ *     ns_uniform = that count.
+ *   - waypoints : [sum(ns_b) + B][3] row-major (east, north, up) == std::vector<ENUPoint> (uavPathPlanning.hpp:152-156)
+ *   - times     : [sum(ns_b)] segment durations in seconds
+ *   - coeff     : [sum(ns_b)][3][2*order]  = the reference's PolyCoeff rows (ms.cpp:220-225): per segment,
+ *                 x | y | z blocks, highest power first, local time t in [0, T_k] (no time scaling)
+ *   - samples   : [rows][3] row-major; trajectory b owns rows [sample_offset[b], sample_offset[b+1])
+ *   - Functions suffixed _dev take DEVICE pointers for every array argument and only enqueue work on the handle's
+ *     stream (no host synchronisation).  Functions suffixed _host take HOST pointers, stage through pinned memory
+ *     owned by the handle, and return after the results are in the caller's buffers.
+ *   - Every function returns an msnap_status.  There is no CPU fallback: without a usable CUDA device
+ *     msnap_create fails with MSNAP_ERR_NO_DEVICE and nothing else can be called.
+ *   - A handle is bound to one device and one stream and is not thread-safe: one handle per host thread / GPU.
+ */
+#ifndef MSNAP_H
+#define MSNAP_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSNAP_VERSION 100 /* 0.1.0 */
+
+typedef enum msnap_status {
+    MSNAP_OK = 0,
+    MSNAP_ERR_INVALID_ARG = 1, /* NULL where data is required, order outside 2..5, B < 0, ns < 1, ...            */
+    MSNAP_ERR_CUDA = 2,        /* a CUDA call failed; text via msnap_last_error                                  */
+    MSNAP_ERR_NO_DEVICE = 3,   /* no CUDA device / device index out of range / not an sm_100 part                */
+    MSNAP_ERR_CAPACITY = 4,    /* sample buffer too small; sample_offset still holds the exact required layout   */
+    MSNAP_ERR_ALLOC = 5,       /* host or device allocation failed                                               */
+    MSNAP_ERR_IO = 6           /* msnap_config_load_yaml: file unreadable                                        */
+} msnap_status;
+
+/* Field-for-field mirror of struct MinimumSnapConfig (minimum_snap.hpp:9-33). */
+typedef struct msnap_config {
+    int order;              /* derivative order minimised: 2 = acceleration (cubic), 3 = jerk, 4 = snap, 5 = crackle */
+    double path_weight;     /* straight-line deviation penalty (two-pass, ms.cpp:347-469)                        */
+    double vel_zero_weight; /* waypoint velocity penalty (ms.cpp:474-509); start value of the reweighting loop   */
+    double V_avg;           /* cruise speed for time allocation, m/s (ms.cpp:63-72)                              */
+    double min_time_s;      /* lower bound of a segment's duration, s                                            */
+    double sample_distance; /* sampler spacing threshold, m (ms.cpp:145)                                         */
+    double start_vel[3], end_vel[3], start_acc[3], end_acc[3];
+} msnap_config;
+
+/* per-trajectory flag bits written to flags_out */
+#define MSNAP_FLAG_NONFINITE 1u /* a non-finite value or a non-positive pivot appeared in the solve */
+#define MSNAP_FLAG_TRUNCATED 2u /* samples of this trajectory did not fit the caller's buffer       */
+
+typedef struct msnap_context *msnap_handle;
+
+/* ---- library / handle ------------------------------------------------------------------------------------ */
+int msnap_version(void);
+const char *msnap_status_string(int status);
+/* Text of the last CUDA failure seen by this handle ("" if none). */
+const char *msnap_last_error(msnap_handle h);
+
+/* Bind a solver instance to CUDA device `device` (creates a stream, uploads the constant tables). */
+int msnap_create(int device, msnap_handle *out);
+int msnap_destroy(msnap_handle h);
+/* Use the caller's cudaStream_t (passed as void*) for all subsequent _dev work; NULL restores the handle's own. */
+int msnap_set_stream(msnap_handle h, void *cuda_stream);
+/* Block until everything enqueued on the handle's stream has finished. */
+int msnap_synchronize(msnap_handle h);
+/* Execution policy of the reweighting loop (ms.cpp:76-90): 0 = automatic, 1 = sequential per trajectory,
+ * 2 = speculative (all 11 velocity weights solved concurrently, the first admissible one selected). Results are
+ * identical; this is a throughput/latency knob only. */
+int msnap_set_reweight_policy(msnap_handle h, int policy);
+/* Number of kernels this handle has launched since creation (monotonic; used by bench.py's gpu_launches). */
+long long msnap_launch_count(msnap_handle h);
+
+/* ---- configuration (minimum_snap.hpp:9-33, minimum_snap_config.yaml, uavPathPlanning.cpp:851-879) --------- */
+/* Struct defaults: order 3, weights 0, V_avg 5, min_time 0.1, sample_distance 1, zero boundary vel/acc. */
+void msnap_config_default(msnap_config *cfg);
+/* Read the ten min-snap keys from a YAML file, flat or wrapped under `minimum_snap:`; keys that are absent or
+ * malformed keep their current value (yamlAssignIfPresent semantics, uavPathPlanning.cpp:35-59, 859-872). */
+int msnap_config_load_yaml(const char *path, msnap_config *cfg);
+
+/* ---- SolveQPClosedForm, batched (minimum_snap.hpp:45-53; ms.cpp:227-649) ----------------------------------
+ * One closed-form solve per trajectory with caller-supplied segment times: no time allocation, no reweighting.
+ *   vel, acc : [B][2][3] (row 0 = start, row 1 = end) or NULL for zeros
+ *   coeff_out: [sum ns][3][2*order];  max_dev_out: [B] or NULL (ms.cpp:594-624)
+ *   best_s_out: [sum ns] (int) or NULL -- index s in 0..16 of the worst-deviation sample t* = T s/16 chosen per
+ *               segment (ms.cpp:408-439); all zero when path_weight <= 0 */
+int msnap_solve_qp_batch_dev(msnap_handle h, int order, double path_weight, double vel_zero_weight, long long B,
+                             int ns_uniform, const long long *seg_offset, const double *waypoints, const double *vel,
+                             const double *acc, const double *times, double *coeff_out, double *max_dev_out,
+                             int *best_s_out, unsigned *flags_out);
+int msnap_solve_qp_batch_host(msnap_handle h, int order, double path_weight, double vel_zero_weight, long long B,
+                              int ns_uniform, const long long *seg_offset, const double *waypoints, const double *vel,
+                              const double *acc, const double *times, double *coeff_out, double *max_dev_out,
+                              int *best_s_out, unsigned *flags_out);
+
+/* ---- GenerateTrajectoryMatrix, batched (minimum_snap.hpp:60-61; ms.cpp:22-206) -----------------------------
+ * Time allocation (ms.cpp:63-72), the reweighting loop around the closed-form solve (ms.cpp:76-90), the
+ * distance-thresholded sampler (ms.cpp:97-161) and the climb/turn statistics (ms.cpp:163-195), for B trajectories.
+ *   sample_distance_override / v_avg_override: used iff > 0 (ms.cpp:42-48)
+ * Outputs (any optional pointer may be NULL):
+ *   times_out     [sum ns]            optional   allocated segment times
+ *   coeff_out     [sum ns][3][2o]     optional   final polynomial coefficients
+ *   max_dev_out   [B]                 optional   final max deviation ratio
+ *   iters_out     [B] (int)           optional   reweighting iterations performed (0..10)
+ *   vw_final_out  [B]                 optional   final vel_zero_weight
+ *   best_s_out    [sum ns] (int)      optional   worst-deviation sample index per segment (see above)
+ *   sample_offset_out [B+1] (int64)   required   exact CSR layout of the samples (always complete)
+ *   samples_out   [sample_capacity][3] required  rows beyond sample_capacity are dropped (MSNAP_FLAG_TRUNCATED,
+ *                                                 and the _host variant returns MSNAP_ERR_CAPACITY)
+ *   stats_out     [B][2]              optional   max |dz|/dxy and min turn radius (ms.cpp:163-195; 1e12 if none)
+ *   flags_out     [B] (unsigned)      optional   MSNAP_FLAG_* */
+int msnap_generate_batch_dev(msnap_handle h, const msnap_config *cfg, double sample_distance_override,
+                             double v_avg_override, long long B, int ns_uniform, const long long *seg_offset,
+                             const double *waypoints, double *times_out, double *coeff_out, double *max_dev_out,
+                             int *iters_out, double *vw_final_out, int *best_s_out, long long sample_capacity,
+                             long long *sample_offset_out, double *samples_out, double *stats_out,
+                             unsigned *flags_out);
+int msnap_generate_batch_host(msnap_handle h, const msnap_config *cfg, double sample_distance_override,
+                              double v_avg_override, long long B, int ns_uniform, const long long *seg_offset,
+                              const double *waypoints, double *times_out, double *coeff_out, double *max_dev_out,
+                              int *iters_out, double *vw_final_out, int *best_s_out, long long sample_capacity,
+                              long long *sample_offset_out, double *samples_out, double *stats_out,
+                              unsigned *flags_out);
+
+/* Upper bound on the number of sample rows msnap_generate_batch can produce for this input (every candidate of
+ * ms.cpp:140 accepted, plus first and last point), computed on the device from the waypoints alone.
+ * waypoints/seg_offset are DEVICE pointers for _dev (result written to *rows_out_dev, a device int64) and HOST
+ * pointers for _host (result returned in *rows_out). */
+int msnap_sample_bound_dev(msnap_handle h, const msnap_config *cfg, double v_avg_override, long long B, int ns_uniform,
+                           const long long *seg_offset, const double *waypoints, long long *rows_out_dev);
+int msnap_sample_bound_host(msnap_handle h, const msnap_config *cfg, double v_avg_override, long long B,
+                            int ns_uniform, const long long *seg_offset, const double *waypoints, long long *rows_out);
+
+/* ---- single-trajectory convenience (what Minisnap_3D / Minisnap_EN need; batch of one) ---------------------
+ * Returns the sample count in *n_samples_out; writes at most sample_capacity rows.  n_points < 2 is
+ * MSNAP_ERR_INVALID_ARG with *n_samples_out = 0 (the reference returns an empty matrix, ms.cpp:54-57). */
+int msnap_generate_one_host(msnap_handle h, const msnap_config *cfg, double sample_distance_override,
+                            double v_avg_override, int n_points, const double *waypoints, long long sample_capacity,
+                            double *samples_out, long long *n_samples_out);
+
+/* ---- micro-benchmarks used for the roofline denominators (bench.py) --------------------------------------- */
+/* Sustained DFMA rate of this GPU in TFLOP/s (2 flops per DFMA), measured with CUDA events. */
+int msnap_measure_fp64_peak(msnap_handle h, double *tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSNAP_H */

@@ -1,0 +1,119 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI
+(cs_pathplan_b200/libmsnap_b200.so); the oracle is only the checker.
+
+Bars (BASELINE.json north_star): coefficients within 1e-8 relative (position-scaled metric, helpers.scaled_coeff_err;
+the reference's OWN rounding error against 60-digit arithmetic is added where it exceeds the bar, and the GPU result is
+held to 1e-8 against that exact solution unconditionally), every sampled ENU position within 1e-6 m, identical
+discrete decisions: segment times bit-exact, arg-max sample per segment, reweighting iterations, sample counts."""
+import numpy as np
+import pytest
+
+from cs_pathplan_b200 import MinimumSnapConfig, shipped_config, workloads
+from cs_pathplan_b200._lib import MsnapError
+from helpers import COEFF_TOL, SAMPLE_TOL, load_golden, make_cfg, oracle_cfg, scaled_coeff_err
+
+pytestmark = pytest.mark.gpu
+CASES = load_golden()
+
+
+def gpu_cfg(d):
+    return make_cfg(MinimumSnapConfig, d)
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c.name)
+def test_generate_matches_reference_golden(tool, case):
+    res = tool.generate_batch(gpu_cfg(case.cfg), case.path, ns=case.ns, sample_distance_override=case.sdo,
+                              v_avg_override=case.vo)
+    assert res.flags[0] == 0
+    assert np.array_equal(res.times, case.time)                                   # bit-exact time allocation
+    assert res.iters[0] == case.iters and res.vw_final[0] == case.vw_final        # reweighting decisions
+    if case.cfg["path_weight"] > 0 and case.ns > 1:
+        assert np.array_equal(res.best_s, case.best_s)                            # arg-max decisions
+    noise = case.ref_noise()
+    assert scaled_coeff_err(res.coeff, case.truth_coeff, case.time) <= COEFF_TOL  # vs exact arithmetic
+    assert scaled_coeff_err(res.coeff, case.coeff, case.time) <= COEFF_TOL + 4 * noise
+    s = res.trajectory(0)
+    assert s.shape == case.samples.shape                                           # sample count
+    assert np.max(np.abs(s - case.samples)) <= SAMPLE_TOL
+    assert abs(res.max_dev[0] - case.max_dev) <= 1e-8 + 4 * noise
+
+
+def test_reference_method_signatures(tool):
+    """The two reference methods, called the way Minisnap_3D / a SolveQPClosedForm user would."""
+    c1 = next(c for c in CASES if c.name == "uav31_0_v30")
+    s = tool.GenerateTrajectoryMatrix(c1.path, shipped_config(), 300.0, 30.0)
+    assert s.shape == (168, 3) and np.max(np.abs(s - c1.samples)) <= SAMPLE_TOL
+    c = next(c for c in CASES if c.name == "rw_o4_ns8_plain")
+    Vel = np.array([c.cfg.get("start_vel", (0, 0, 0)), c.cfg.get("end_vel", (0, 0, 0))], dtype=float)
+    Acc = np.array([c.cfg.get("start_acc", (0, 0, 0)), c.cfg.get("end_acc", (0, 0, 0))], dtype=float)
+    poly, md = tool.SolveQPClosedForm(4, c.path, Vel, Acc, c.time, 0.0, 0.0, return_max_deviation=True)
+    assert poly.shape == (8, 24) and md == 0.0
+    assert scaled_coeff_err(poly.reshape(8, 3, 8), c.coeff, c.time) <= COEFF_TOL + 4 * c.ref_noise()
+
+
+def test_error_behaviour_like_the_reference(tool):
+    # fewer than 2 waypoints / fewer than 3 columns: empty matrix (ms.cpp:54-57)
+    assert tool.GenerateTrajectoryMatrix(np.zeros((1, 3)), MinimumSnapConfig()).shape == (0, 0)
+    assert tool.GenerateTrajectoryMatrix(np.zeros((5, 2)), MinimumSnapConfig()).shape == (0, 0)
+    # orders the reference cannot represent (int overflow at >= 6) or that have no free derivative (1) are rejected
+    for order in (0, 1, 6):
+        with pytest.raises(MsnapError):
+            tool.generate_batch(MinimumSnapConfig(order=order), np.random.rand(3, 3), ns=2)
+    with pytest.raises(ValueError):
+        tool.generate_batch(MinimumSnapConfig(), np.random.rand(7, 3), ns=3)      # 7 rows is not a multiple of 4
+
+
+def test_capacity_overflow_is_reported_with_exact_layout(tool):
+    wp, ns = workloads.cfg2(B=8, ns=4)
+    cfg = workloads.synthetic_config(4, "plain")
+    full = tool.generate_batch(cfg, wp, ns=ns)
+    with pytest.raises(MsnapError) as e:
+        tool.generate_batch(cfg, wp, ns=ns, capacity=int(full.sample_offset[3]) + 2)
+    part = e.value.partial
+    assert np.array_equal(part.sample_offset, full.sample_offset)                 # layout is still exact
+    assert np.array_equal(part.samples, full.samples[: part.samples.shape[0]])    # rows that fit are right
+    assert (part.flags[:3] & 2).max() == 0 and (part.flags[4:] & 2).min() == 2
+
+
+@pytest.mark.parametrize("order", [2, 3, 4, 5])
+@pytest.mark.parametrize("weights", ["plain", "shipped"])
+def test_batch_vs_oracle_port_seeded(tool, order, weights):
+    """A seeded mixed-length batch through the CSR entry point against the line-by-line port."""
+    from oracle import msnap_oracle as mo
+
+    rng = np.random.default_rng(100 * order + len(weights))
+    lens = [1, 2, 3, 5, 8, 13, 4] if order < 5 else [1, 2, 3, 4]
+    paths = []
+    for n in lens:
+        p0 = rng.uniform(-100, 100, 3)
+        paths.append(np.vstack([p0, p0 + np.cumsum(rng.normal(0, 10, (n, 3)), 0)]))
+    so = np.concatenate([[0], np.cumsum(lens)])
+    cfg = workloads.synthetic_config(order, weights)
+    cfg.start_vel, cfg.end_acc = (0.5, -0.25, 0.1), (0.0, 0.3, -0.1)
+    res = tool.generate_batch(cfg, np.vstack(paths), seg_offset=so)
+    ocfg = oracle_cfg({k: getattr(cfg, k) for k in ("order", "path_weight", "vel_zero_weight", "V_avg", "min_time_s",
+                                                     "sample_distance", "start_vel", "end_vel", "start_acc", "end_acc")})
+    tol = COEFF_TOL if order < 5 else 1e-6      # the dense reference arithmetic itself degrades at order 5
+    for b, p in enumerate(paths):
+        s_o, info = mo.generate_trajectory_matrix(p, ocfg)
+        sl = res.segment_slice(b)
+        assert np.array_equal(res.times[sl], info.Time)
+        assert res.iters[b] == info.iters
+        assert scaled_coeff_err(res.coeff[sl], info.PolyCoeff.reshape(-1, 3, 2 * order), info.Time) <= tol
+        s_g = res.trajectory(b)
+        assert s_g.shape == s_o.shape and np.max(np.abs(s_g - s_o)) <= SAMPLE_TOL
+        assert abs(res.stats[b, 0] - info.max_climb_rate) <= 1e-6 * max(1.0, info.max_climb_rate)
+        assert abs(res.stats[b, 1] - info.min_turn_radius) <= 1e-6 * max(1.0, info.min_turn_radius)
+
+
+def test_batch_equals_singles_bitwise(tool):
+    """Batching must not change any bit: trajectory b of a batch == the same trajectory solved alone."""
+    wp, so = workloads.cfg5(B=24, seed=5, ns_min=2, ns_max=40)
+    cfg = workloads.synthetic_config(4, "shipped")
+    res = tool.generate_batch(cfg, wp, seg_offset=so)
+    for b in (0, 7, 23):
+        p = wp[so[b] + b: so[b + 1] + b + 1]
+        one = tool.generate_batch(cfg, p, ns=p.shape[0] - 1)
+        sl = res.segment_slice(b)
+        assert np.array_equal(one.coeff, res.coeff[sl]) and np.array_equal(one.samples, res.trajectory(b))
+        assert one.iters[0] == res.iters[b] and one.max_dev[0] == res.max_dev[b]

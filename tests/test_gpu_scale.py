@@ -1,0 +1,125 @@
+"""Full-size GPU checks at BASELINE.json's configuration sizes, through size-independent properties: waypoint
+interpolation, C^(o-1) continuity, boundary conditions, sampler invariants, determinism, and spot parity against the
+oracle port on a seeded subsample.  (pytest -m gpu)"""
+import numpy as np
+import pytest
+
+from cs_pathplan_b200 import workloads
+from helpers import COEFF_TOL, SAMPLE_TOL, scaled_coeff_err
+
+pytestmark = pytest.mark.gpu
+
+
+def polyval_hi(c, t):
+    """c [..., m] highest power first, t [...] -> values."""
+    v = np.zeros(c.shape[:-1])
+    for i in range(c.shape[-1]):
+        v = v * t + c[..., i]
+    return v
+
+
+def polyder_hi(c, r):
+    m = c.shape[-1]
+    for _ in range(r):
+        p = np.arange(c.shape[-1] - 1, 0, -1)
+        c = c[..., :-1] * p
+    return c
+
+
+def check_properties(res, wp, seg_offset, order, cfg, pos_tol=2e-8):
+    B = seg_offset.shape[0] - 1
+    ns = np.diff(seg_offset)
+    first_pt = seg_offset[:-1] + np.arange(B)
+    seg_traj = np.repeat(np.arange(B), ns)
+    seg_pt = np.arange(seg_offset[-1]) + seg_traj                  # waypoint index of each segment's start
+    T = res.times
+    assert np.all(res.flags == 0)
+    assert np.all(T >= cfg.min_time_s)
+    c = res.coeff
+    # interpolation: p_k(0) = P_k, p_k(T_k) = P_{k+1}
+    assert np.max(np.abs(c[:, :, -1] - wp[seg_pt])) == 0.0        # constant term IS the waypoint
+    endv = polyval_hi(c, T[:, None])
+    assert np.max(np.abs(endv - wp[seg_pt + 1])) <= pos_tol
+    # C^(o-1) continuity at interior waypoints
+    interior = np.nonzero(np.arange(seg_offset[-1]) + 1 < seg_offset[seg_traj + 1])[0]
+    for r in range(1, order):
+        left = polyval_hi(polyder_hi(c[interior], r), T[interior, None])
+        right = polyder_hi(c[interior + 1], r)[..., -1]
+        scale = np.maximum(1.0, np.abs(right))
+        assert np.max(np.abs(left - right) / scale) <= 1e-7
+    # boundary derivatives (zero in the synthetic configs)
+    last_seg = seg_offset[1:] - 1
+    for r in range(1, min(order, 3)):
+        assert np.max(np.abs(polyder_hi(c[seg_offset[:-1]], r)[..., -1])) <= 1e-9
+        assert np.max(np.abs(polyval_hi(polyder_hi(c[last_seg], r), T[last_seg, None]))) <= 1e-6
+    # sampler: first row = first waypoint, last row = last waypoint, spacing >= sample_distance except at seams
+    so = res.sample_offset
+    assert np.all(np.diff(so) >= 2) and so[-1] == res.samples.shape[0]
+    assert np.max(np.abs(res.samples[so[:-1]] - wp[first_pt])) <= pos_tol
+    assert np.max(np.abs(res.samples[so[1:] - 1] - wp[first_pt + ns])) <= pos_tol
+    assert np.all(res.iters >= 0) and np.all(res.iters <= 10)
+    assert np.all((res.max_dev <= 0.2) | (res.iters == 10))        # the loop's exit condition (ms.cpp:82)
+
+
+def spot_check_vs_port(res, wp, seg_offset, cfg, picks):
+    from oracle import msnap_oracle as mo
+
+    ocfg = mo.MinimumSnapConfig(order=cfg.order, path_weight=cfg.path_weight, vel_zero_weight=cfg.vel_zero_weight,
+                                V_avg=cfg.V_avg, min_time_s=cfg.min_time_s, sample_distance=cfg.sample_distance)
+    for b in picks:
+        p = wp[seg_offset[b] + b: seg_offset[b + 1] + b + 1]
+        s_o, info = mo.generate_trajectory_matrix(p, ocfg)
+        sl = res.segment_slice(b)
+        assert np.array_equal(res.times[sl], info.Time) and res.iters[b] == info.iters
+        assert scaled_coeff_err(res.coeff[sl], info.PolyCoeff.reshape(-1, 3, 2 * cfg.order), info.Time) <= COEFF_TOL
+        s_g = res.trajectory(b)
+        assert s_g.shape == s_o.shape and np.max(np.abs(s_g - s_o)) <= SAMPLE_TOL
+
+
+@pytest.mark.parametrize("weights", ["plain", "shipped"])
+def test_cfg2_full_size(tool, weights):
+    wp, ns = workloads.cfg2()
+    cfg = workloads.synthetic_config(4, weights)
+    res = tool.generate_batch(cfg, wp, ns=ns)
+    so = np.arange(4097, dtype=np.int64) * ns
+    check_properties(res, wp, so, 4, cfg)
+    spot_check_vs_port(res, wp, so, cfg, [0, 1, 2047, 4095])
+    again = tool.generate_batch(cfg, wp, ns=ns)                     # bitwise deterministic
+    assert np.array_equal(again.coeff, res.coeff) and np.array_equal(again.samples, res.samples)
+
+
+def test_cfg3_shard_size(tool):
+    """cfg3 is 2^20 x 8; one eighth of it (a single GPU's shard at 8 GPUs) is checked here in full, and the shard
+    results must equal the same rows of a differently-split batch (sharding is invisible in the results)."""
+    wp, ns = workloads.cfg3(B=1 << 17)
+    cfg = workloads.synthetic_config(4, "shipped")
+    res = tool.generate_batch(cfg, wp, ns=ns)
+    so = np.arange((1 << 17) + 1, dtype=np.int64) * ns
+    check_properties(res, wp, so, 4, cfg)
+    spot_check_vs_port(res, wp, so, cfg, [0, 65535, 131071])
+    half = tool.generate_batch(cfg, wp[(1 << 16) * (ns + 1):], ns=ns)
+    assert np.array_equal(half.coeff, res.coeff[(1 << 16) * ns:])
+    assert np.array_equal(half.samples, res.samples[res.sample_offset[1 << 16]:])
+
+
+def test_cfg4_long_chains(tool):
+    wp, ns = workloads.cfg4(B=64)
+    cfg = workloads.synthetic_config(4, "shipped")
+    res = tool.generate_batch(cfg, wp, ns=ns)
+    check_properties(res, wp, np.arange(65, dtype=np.int64) * ns, 4, cfg, pos_tol=1e-7)
+
+
+def test_cfg5_mixed_lengths_dense_sampling(tool):
+    wp, so = workloads.cfg5(B=2048)
+    cfg = workloads.synthetic_config(4, "plain", sample_distance=0.0)
+    res = tool.generate_batch(cfg, wp, seg_offset=so)
+    check_properties(res, wp, so, 4, cfg)
+    # sample_distance 0 accepts every 10 Hz candidate: count = 1 + sum_k n_cand(T_k) (+1 end point unless the last
+    # candidate already sits on it)
+    T = res.times
+    dt = np.minimum(0.1, T / 10.0)
+    approx = np.floor((T + 1e-12) / dt + 1e-9)
+    per_traj = np.add.reduceat(approx, so[:-1])
+    counts = np.diff(res.sample_offset)
+    assert np.all(np.abs(counts - (per_traj + 1)) <= np.diff(so) + 1)
+    spot_check_vs_port(res, wp, so, cfg, [0, 1000, 2047])

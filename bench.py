@@ -1,0 +1,370 @@
+#!/usr/bin/env python3
+"""bench.py -- min-snap trajectories/sec (16-segment, xyz, fp64) on N B200s vs the host CPU.
+
+Workload (BASELINE.json configs[1]): 4 096 trajectories x 16 segments, derivative order 4
+(degree-7 polynomials), fp64, random-walk waypoints (rng 1234), V_avg 5 m/s, sample spacing 1 m, the reference's
+shipped penalty weights (path_weight 1e-7, vel_zero_weight 0.01) so that every row of the hot path runs: time
+allocation, pass-1 solve, worst-deviation search, penalised solve, the 10-step reweighting loop, coefficient
+recovery and the distance-thresholded sampler.  A "step" is one full GenerateTrajectoryMatrix pass over one batch.
+The plain-weights variant (path_weight = vel_zero_weight = 0: one solve, HBM-bound) is measured as well and reported
+under "variants".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]      # the reference's own CPU code (oracle/_ref)
+
+Prints ONE JSON line (rank 0).  See the task contract for the keys; numbers are never taken under a profiler.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "min-snap trajectories/sec (16-seg, xyz, fp64)"
+UNIT = "trajectories/s"
+B_DEFAULT, NS, ORDER = 4096, 16, 4
+ROTATE = 8  # distinct input/output buffer sets cycled through so a step never finds its data in L2
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--weights", default="shipped", choices=["shipped", "plain"])
+    ap.add_argument("--batch", type=int, default=B_DEFAULT)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(weights, B):
+    w = "shipped penalty weights pw=1e-7 vw=0.01 (1 + up to 11 solves/trajectory)" if weights == "shipped" else \
+        "plain weights pw=vw=0 (1 solve/trajectory)"
+    return f"cfg2: {B} trajectories x {NS} segments, order {ORDER} (degree 7), fp64, V_avg 5, sample 1 m, {w}"
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock / throttle reasons through NVML (falls back to nvidia-smi) while the GPU is under load."""
+
+    def __init__(self, index):
+        self.index, self.samples, self._stop = index, [], threading.Event()
+        self.max_mhz = None
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self._stop.is_set():
+                try:
+                    util = nv.nvmlDeviceGetUtilizationRates(h).gpu
+                except Exception:
+                    util = -1
+                self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), int(get_reasons(h)), util))
+                time.sleep(0.02)
+        except Exception as e:  # pragma: no cover - depends on the box
+            self.error = repr(e)
+
+    def start(self):
+        self._t.start()
+        return self
+
+    def stop(self):
+        self._stop.set()
+        self._t.join(timeout=2)
+        names = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+                 0x80: "hw_power_brake_slowdown"}
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": getattr(self, "error", "no samples")}
+        busy = [s for s in self.samples if s[2] > 0] or self.samples
+        reasons = sorted({n for s in busy for bit, n in names.items() if s[1] & bit})
+        return {"sm_mhz": statistics.median(s[0] for s in busy), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(busy)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def ref_config(weights):
+    from oracle import ref
+
+    pw, vw = (1e-7, 0.01) if weights == "shipped" else (0.0, 0.0)
+    return ref.RefConfig(order=ORDER, path_weight=pw, vel_zero_weight=vw, V_avg=5.0, min_time_s=0.1, sample_distance=1.0)
+
+
+def cpu_rate(weights, wp, n_traj, threads):
+    """Trajectories/s of the reference CPU code on `n_traj` trajectories with `threads` OpenMP threads."""
+    from oracle import ref
+
+    off = np.arange(n_traj + 1, dtype=np.int64) * NS
+    t0 = time.perf_counter()
+    counts, used, _ = ref.generate_batch(off, wp[: n_traj * (NS + 1)], ref_config(weights), nthreads=threads, kind="fast")
+    dt = time.perf_counter() - t0
+    return n_traj / dt, used, int(counts.sum())
+
+
+def cpu_baseline(weights, wp, budget_s=12.0):
+    """Bounded sample of the same workload on all host cores (+ the single-threaded as-shipped call sequence)."""
+    cores = os.cpu_count() or 1
+    r1, _, _ = cpu_rate(weights, wp, 8, 1)                       # single thread, as shipped: one call per trajectory
+    n = int(min(wp.shape[0] // (NS + 1), max(cores * 2, r1 * cores * budget_s * 0.6)))
+    rN, used, _ = cpu_rate(weights, wp, n, cores)
+    return {"value": rN, "unit": UNIT, "cores": used, "kind": "reference",
+            "sample": f"first {n} of the {wp.shape[0] // (NS + 1)} trajectories, one GenerateTrajectoryMatrix call each, "
+                      f"OpenMP over trajectories on {used} threads; unmodified reference minimum_snap.cpp built against "
+                      f"the oracle's Eigen shim (real Eigen is not installable here), -O3 -march=x86-64-v3/v4",
+            "single_thread_value": r1}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from cs_pathplan_b200 import workloads
+    from oracle import ref
+
+    if not ref.available("fast"):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (make -C oracle needs /root/reference)"}))
+        return
+    wp, _ = workloads.cfg2(B=args.batch)
+    cores = os.cpu_count() or 1
+    r1, _, _ = cpu_rate(args.weights, wp, 8, 1)
+    # bounded sample per step: about one second of all-core work, less if K is large (whole run within ~2 minutes)
+    step_s = min(1.0, 120.0 / max(1, args.steps + args.warmup))
+    n = int(min(args.batch, max(cores, r1 * cores * step_s * 0.6)))
+    for _ in range(args.warmup):
+        cpu_rate(args.weights, wp, n, cores)
+    t0 = time.perf_counter()
+    used = cores
+    for _ in range(args.steps):
+        _, used, _ = cpu_rate(args.weights, wp, n, cores)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    sample = (f"each step = first {n} trajectories of the batch, one GenerateTrajectoryMatrix call each, OpenMP over "
+              f"trajectories on {used} threads; unmodified reference minimum_snap.cpp + oracle Eigen shim")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.weights, args.batch), "sample_per_step": n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from cs_pathplan_b200 import TrajectoryGeneratorTool, roofline, workloads
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    tool = TrajectoryGeneratorTool(local)
+    tool.set_stream(torch.cuda.current_stream().cuda_stream)
+    B, m = args.batch, 2 * ORDER
+    n_seg = B * NS
+
+    class Bufs:
+        pass
+
+    def make_set(seed, cfg):
+        s = Bufs()
+        wp_h, _ = workloads.cfg2(B=B, seed=seed)
+        s.wp_h = torch.from_numpy(wp_h).pin_memory()
+        s.wp = s.wp_h.to(dev)
+        s.cap = tool.sample_bound(cfg, wp_h, ns=NS)
+        s.times = torch.empty(n_seg, dtype=torch.float64, device=dev)
+        s.coeff = torch.empty(n_seg * 3 * m, dtype=torch.float64, device=dev)
+        s.max_dev = torch.empty(B, dtype=torch.float64, device=dev)
+        s.vw = torch.empty(B, dtype=torch.float64, device=dev)
+        s.iters = torch.empty(B, dtype=torch.int32, device=dev)
+        s.off = torch.empty(B + 1, dtype=torch.int64, device=dev)
+        s.samples = torch.empty((s.cap, 3), dtype=torch.float64, device=dev)
+        s.flags = torch.empty(B, dtype=torch.int32, device=dev)
+        return s
+
+    def step(cfg, s):
+        tool.generate_batch_dev(cfg, s.wp, s.off, s.samples, ns=NS, times=s.times, coeff=s.coeff, max_dev=s.max_dev,
+                                iters=s.iters, vw_final=s.vw, flags=s.flags)
+
+    def timed_run(cfg, sets, steps, warmup):
+        for i in range(warmup):
+            step(cfg, sets[i % ROTATE])
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = tool.launch_count
+        e0.record()
+        for i in range(steps):
+            step(cfg, sets[i % ROTATE])
+        e1.record()
+        torch.cuda.synchronize()
+        launches = tool.launch_count - l0
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        barrier()
+        return ms, launches
+
+    results = {}
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    fp64_peak = tool.measure_fp64_peak()
+    for weights in ([args.weights] + [w for w in ("shipped", "plain") if w != args.weights]):
+        cfg = workloads.synthetic_config(ORDER, weights)
+        sets = [make_set(1234 + 1000 * rank + r, cfg) for r in range(ROTATE)]
+        headline = weights == args.weights
+        steps = args.steps if headline else min(args.steps, 500)
+        ms, launches = timed_run(cfg, sets, steps, max(args.warmup, 3))
+        tot_samples = int(sets[0].off[-1].item())
+        iters0 = sets[0].iters.to(torch.int64)
+        total_solves = int((iters0 + 1).sum().item())
+        flags_bad = int((sets[0].flags != 0).sum().item())
+        # roofline pass: per-kernel CUDA-event timing on the launching stream (separate from the headline timing)
+        tool.profile_begin()
+        prof_steps = 20
+        for i in range(prof_steps):
+            step(cfg, sets[i % ROTATE])
+        prof = tool.profile_end()
+        dom = max(prof, key=lambda k: prof[k]["total_ms"])
+        dom_ms = prof[dom]["total_ms"] / prof_steps        # per step (a kernel may launch more than once per step)
+        all_ms = sum(v["total_ms"] for v in prof.values()) / prof_steps
+        t_np = sets[0].times.cpu().numpy()
+        cand = int(np.sum(np.floor((t_np + 1e-12) / np.minimum(0.1, t_np / 10.0) + 1e-9)))
+        abytes = roofline.algorithmic_bytes(B, n_seg, ORDER, tot_samples)
+        aflops = roofline.algorithmic_flops(B, n_seg, ORDER, cfg.path_weight > 0, total_solves, cand)
+        footprint = ROTATE * (abytes + 24 * (sets[0].cap - tot_samples))
+        # end to end through the host-pointer C ABI: pinned host inputs -> H2D, solve, D2H of every result
+        out = {k: torch.empty(shape, dtype=dt).pin_memory().numpy() for k, shape, dt in (
+            ("times", (n_seg,), torch.float64), ("coeff", (n_seg, 3, m), torch.float64), ("max_dev", (B,), torch.float64),
+            ("iters", (B,), torch.int32), ("vw_final", (B,), torch.float64), ("sample_offset", (B + 1,), torch.int64),
+            ("samples", (sets[0].cap, 3), torch.float64), ("stats", (B, 2), torch.float64))}
+        out["flags"] = torch.zeros(B, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+        out["best_s"] = torch.zeros(n_seg, dtype=torch.int32).pin_memory().numpy()
+        wp_np = [s.wp_h.numpy() for s in sets]
+        e2e_steps = max(3, min(steps, 30))
+        for i in range(3):
+            tool.generate_batch(cfg, wp_np[i % ROTATE], ns=NS, capacity=sets[0].cap, out=out)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            r = tool.generate_batch(cfg, wp_np[i % ROTATE], ns=NS, capacity=sets[0].cap, out=out)
+        torch.cuda.synchronize()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        h2d = wp_np[0].nbytes
+        d2h = int(r.samples.nbytes + out["times"].nbytes + out["coeff"].nbytes + out["max_dev"].nbytes +
+                  out["iters"].nbytes + out["vw_final"].nbytes + out["sample_offset"].nbytes + out["stats"].nbytes +
+                  out["flags"].nbytes + out["best_s"].nbytes)
+        results[weights] = dict(
+            ms=ms, steps=steps, launches=launches, value=world * B * steps / (ms * 1e-3),
+            e2e=dict(value=world * B * e2e_steps / e2e_s, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                     steps=e2e_steps, ms_per_step=e2e_s / e2e_steps * 1e3),
+            prof=prof, dom=dom, dom_ms=dom_ms, all_kernels_ms=all_ms, abytes=abytes, aflops=aflops,
+            samples=tot_samples, candidates=cand, mean_iters=float(iters0.double().mean().item()), flags_bad=flags_bad,
+            footprint=footprint)
+        del sets
+        torch.cuda.empty_cache()
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak, peak_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured)") if "hbm_gbs" in peaks else \
+            (6650.0, "B200_PROFILING.md fallback")
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))
+        except Exception:
+            pass
+
+        def roof(r, weights):
+            t = r["dom_ms"] * 1e-3
+            gbs = r["abytes"] / t / 1e9
+            tf = r["aflops"] / t / 1e12
+            tr = traffic.get(weights, {}).get(r["dom"]) if isinstance(traffic, dict) else None
+            return {"bound": "hbm", "kernel": r["dom"], "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": gbs / hbm_peak, "traffic": tr, "peak_source": peak_src,
+                    "kernel_ms_per_step": r["dom_ms"], "all_kernels_ms_per_step": r["all_kernels_ms"],
+                    "algorithmic_bytes_per_step": r["abytes"], "algorithmic_flops_per_step": r["aflops"],
+                    "fp64": {"achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+                             "peak_source": "msnap_measure_fp64_peak (own DFMA micro-benchmark, measured this run)"},
+                    "limiter": "fp64" if tf / fp64_peak > gbs / hbm_peak else "hbm",
+                    "kernels_ms_per_step": {k: v["total_ms"] / 20 for k, v in r["prof"].items()}}
+
+        h = results[args.weights]
+        line = {
+            "metric": METRIC, "value": h["value"], "unit": UNIT, "n_gpus": world, "steps": h["steps"],
+            "warmup": max(args.warmup, 3), "ms_per_step": h["ms"] / h["steps"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.weights, B), "trajectories_per_gpu_per_step": B,
+                       "l2_policy": f"inputs and outputs rotate over {ROTATE} distinct buffer sets "
+                                    f"({h['footprint'] / 1e6:.0f} MB > 126 MB L2); workspace is reused",
+                       "samples_per_step": h["samples"], "mean_reweight_iters": h["mean_iters"],
+                       "flagged_trajectories": h["flags_bad"], "parallelism": f"trajectory-sharded x{world}, no collective"},
+            "e2e": h["e2e"], "gpu_launches": h["launches"], "clocks": clocks, "roofline": roof(h, args.weights),
+            "variants": {w: {"value": r["value"], "ms_per_step": r["ms"] / r["steps"], "e2e": r["e2e"],
+                             "roofline": roof(r, w), "workload": workload_name(w, B)}
+                         for w, r in results.items() if w != args.weights},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                from oracle import ref
+
+                wp, _ = workloads.cfg2(B=B)
+                if ref.available("fast"):
+                    line["cpu_baseline"] = cpu_baseline(args.weights, wp)
+                else:
+                    line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                                            "sample": "oracle/_ref not built on this box"}
+            except Exception as e:  # the baseline must never take the GPU number down with it
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": repr(e)}
+        print(json.dumps(line))
+    tool.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -59,6 +59,8 @@ SIGNATURES = {
     "msnap_sample_bound_dev": (_i, [_vp, _cfgp, _d, _ll, _i, _vp, _vp, _vp]),
     "msnap_sample_bound_host": (_i, [_vp, _cfgp, _d, _ll, _i, _vp, _vp, C.POINTER(_ll)]),
     "msnap_generate_one_host": (_i, [_vp, _cfgp, _d, _d, _i, _vp, _ll, _vp, C.POINTER(_ll)]),
+    "msnap_profile_begin": (_i, [_vp]),
+    "msnap_profile_end": (_i, [_vp, C.c_char_p, _ll]),
     "msnap_measure_fp64_peak": (_i, [_vp, C.POINTER(_d)]),
 }
 

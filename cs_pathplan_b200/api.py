@@ -177,6 +177,17 @@ class TrajectoryGeneratorTool:
     def launch_count(self) -> int:
         return int(self._L.msnap_launch_count(self._h))
 
+    def profile_begin(self):
+        self._check(self._L.msnap_profile_begin(self._h))
+
+    def profile_end(self) -> dict:
+        """Per-kernel {name: {"launches", "total_ms"}} since profile_begin (CUDA events on the launching stream)."""
+        import json
+
+        buf = C.create_string_buffer(1 << 16)
+        self._check(self._L.msnap_profile_end(self._h, buf, len(buf)))
+        return json.loads(buf.value.decode())
+
     def measure_fp64_peak(self) -> float:
         out = C.c_double(0.0)
         self._check(self._L.msnap_measure_fp64_peak(self._h, C.byref(out)))

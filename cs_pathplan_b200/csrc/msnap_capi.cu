@@ -36,6 +36,10 @@ struct msnap_context {
     Arena io;                        // device mirrors of host buffers (_host entry points)
     long long launches = 0;
     int policy = 0;
+    // optional per-kernel timing (msnap_profile_begin/end): one event pair per launch on the launching stream
+    bool profiling = false;
+    struct Timed { const char *name; cudaEvent_t e0, e1; };
+    std::vector<Timed> timed;
     int sm_count = 0;
     std::string last_error;
 };
@@ -94,9 +98,23 @@ inline size_t padded(size_t bytes) { return (bytes + 255) & ~size_t(255); }
 
 inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
 
+inline void prof_before(msnap_context *h, const char *name) {
+    if (!h->profiling) return;
+    msnap_context::Timed t{name, nullptr, nullptr};
+    cudaEventCreate(&t.e0);
+    cudaEventCreate(&t.e1);
+    cudaEventRecord(t.e0, h->stream);
+    h->timed.push_back(t);
+}
+inline void prof_after(msnap_context *h) {
+    if (h->profiling) cudaEventRecord(h->timed.back().e1, h->stream);
+}
+
 #define MS_LAUNCH(h, kernel, grid, block, ...)                                                   \
     do {                                                                                         \
+        prof_before((h), #kernel);                                                               \
         kernel<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);                                \
+        prof_after((h));                                                                         \
         ++(h)->launches;                                                                         \
         cudaError_t e__ = cudaPeekAtLastError();                                                 \
         if (e__ != cudaSuccess) {                                                                \
@@ -756,6 +774,52 @@ int msnap_generate_one_host(msnap_handle h, const msnap_config *cfg, double samp
                                        samples_out, nullptr, nullptr);
     *n_samples_out = off[1];
     return rc;
+}
+
+// ---------------------------------------------------------------------------------------------- profiling
+int msnap_profile_begin(msnap_handle h) {
+    if (!h) return MSNAP_ERR_INVALID_ARG;
+    DeviceGuard guard(h->device);
+    for (auto &t : h->timed) {
+        cudaEventDestroy(t.e0);
+        cudaEventDestroy(t.e1);
+    }
+    h->timed.clear();
+    h->profiling = true;
+    return MSNAP_OK;
+}
+
+int msnap_profile_end(msnap_handle h, char *json_out, long long capacity) {
+    if (!h || !json_out || capacity < 3) return MSNAP_ERR_INVALID_ARG;
+    DeviceGuard guard(h->device);
+    h->profiling = false;
+    MS_CUDA(h, cudaStreamSynchronize(h->stream));
+    struct Acc { std::string name; long long n; double ms; };
+    std::vector<Acc> acc;
+    for (auto &t : h->timed) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t.e0, t.e1);
+        cudaEventDestroy(t.e0);
+        cudaEventDestroy(t.e1);
+        std::string nm(t.name);
+        for (char &c : nm)
+            if (c == '"' || c == '\\') c = '_';
+        bool found = false;
+        for (auto &a : acc)
+            if (a.name == nm) { a.n++; a.ms += ms; found = true; break; }
+        if (!found) acc.push_back({nm, 1, (double)ms});
+    }
+    h->timed.clear();
+    std::string js = "{";
+    for (size_t i = 0; i < acc.size(); ++i) {
+        char buf[96];
+        std::snprintf(buf, sizeof buf, "\": {\"launches\": %lld, \"total_ms\": %.6f}", acc[i].n, acc[i].ms);
+        js += (i ? ", \"" : "\"") + acc[i].name + buf;
+    }
+    js += "}";
+    if ((long long)js.size() + 1 > capacity) return MSNAP_ERR_CAPACITY;
+    std::memcpy(json_out, js.c_str(), js.size() + 1);
+    return MSNAP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------- fp64 peak

@@ -147,6 +147,12 @@ int msnap_generate_one_host(msnap_handle h, const msnap_config *cfg, double samp
                             double v_avg_override, int n_points, const double *waypoints, long long sample_capacity,
                             double *samples_out, long long *n_samples_out);
 
+/* ---- per-kernel timing (bench.py's roofline pass) ------------------------------------------------------------
+ * Between begin and end every kernel the handle launches is bracketed by a CUDA event pair on the launching stream.
+ * msnap_profile_end synchronises and writes a JSON object {"<kernel>": {"launches": n, "total_ms": t}, ...}. */
+int msnap_profile_begin(msnap_handle h);
+int msnap_profile_end(msnap_handle h, char *json_out, long long capacity);
+
 /* ---- micro-benchmarks used for the roofline denominators (bench.py) --------------------------------------- */
 /* Sustained DFMA rate of this GPU in TFLOP/s (2 flops per DFMA), measured with CUDA events. */
 int msnap_measure_fp64_peak(msnap_handle h, double *tflops_out);

@@ -15,6 +15,7 @@
 
 #include "msnap_device.cuh"
 #include "msnap_generic.cuh"
+#include "msnap_fused.cuh"
 
 static const MsnapOrderTab h_tab[MSNAP_MAX_ORDER - MSNAP_MIN_ORDER + 1] = MSNAP_ORDER_TABLES;
 
@@ -136,16 +137,64 @@ struct SolveIO {
     unsigned *flags_out = nullptr;
 };
 
-struct SolveWs {
-    double *T, *base, *state, *segx, *coeff;
-    int *s_star;
+// Launch plan of the fused kernel for a uniform batch, or tpc == 0 if the batch does not qualify.
+struct FusedPlan {
+    int tpc = 0, nit = 1, lane_stride = 32, traj_stride = 0, grid = 0;
+    long long n_tiles = 0;
+    size_t smem = 0, state_bytes = 0;
 };
 
 template <int O>
-size_t solve_ws_bytes(long long n_seg, bool need_T, bool need_coeff) {
+FusedPlan plan_fused(msnap_context *h, const BatchIdx &bi, const SolveParams &sp) {
+    using D = Dim<O>;
+    FusedPlan f;
+    if (bi.ns_uniform <= 0 || h->policy == 1) return f;
+    const int ns = bi.ns_uniform;
+    const FusedSmem<O> L(ns);
+    f.nit = sp.pw > 0.0 ? sp.max_iter + 1 : 1;
+    if (f.nit > FUSED_THREADS) return f;
+    const size_t blk = (size_t)L.size * sizeof(double);
+    auto smem_for = [&](int tpc) { return tpc * blk + (size_t)tpc * f.nit * 12 + (size_t)tpc * 8 + 16; };
+    const size_t soft = 72 * 1024, hard = 220 * 1024;  // 3 CTAs per SM when the tile fits in 72 KB
+    int tpc = FUSED_THREADS / f.nit;
+    if ((long long)tpc > bi.B) tpc = (int)bi.B;
+    while (tpc > 1 && smem_for(tpc) > soft) --tpc;
+    if (smem_for(tpc) > hard) return f;  // a single trajectory does not fit: generic path
+    f.tpc = tpc;
+    f.traj_stride = L.size;
+    f.smem = smem_for(tpc);
+    f.lane_stride = ((tpc * f.nit + 31) / 32) * 32;
+    f.n_tiles = (bi.B + tpc - 1) / tpc;
+    int occ = 0;
+    cudaFuncSetAttribute(k_fused_solve<O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f.smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fused_solve<O>, FUSED_THREADS, f.smem) != cudaSuccess ||
+        occ < 1) {
+        cudaGetLastError();
+        f.tpc = 0;
+        return f;
+    }
+    const long long resident = (long long)occ * h->sm_count;
+    f.grid = (int)(f.n_tiles < resident ? f.n_tiles : resident);
+    f.state_bytes = (size_t)f.grid * (ns - 1) * D::NSTATE * f.lane_stride * sizeof(double);
+    return f;
+}
+
+struct SolveWs {
+    double *T, *base, *state, *segx, *coeff;
+    int *s_star;
+    FusedPlan fused;
+};
+
+template <int O>
+size_t solve_ws_bytes(long long n_seg, bool need_T, bool need_coeff, const FusedPlan &f) {
     using D = Dim<O>;
     size_t b = 0;
     if (need_T) b += padded(n_seg * sizeof(double));
+    if (f.tpc > 0) {  // fused path: only the per-CTA state slots (+ coefficients if the caller keeps none)
+        b += padded(f.state_bytes + 256);
+        if (need_coeff) b += padded((size_t)n_seg * 3 * D::M * sizeof(double));
+        return b;
+    }
     b += padded((size_t)n_seg * D::NBASE * sizeof(double));
     b += padded((size_t)(n_seg + 1) * D::NSTATE * sizeof(double));
     b += padded((size_t)n_seg * D::NSEGX * sizeof(double));
@@ -161,6 +210,44 @@ int run_solve(msnap_context *h, const BatchIdx &bi, const SolveParams &sp, const
     const int blk = 128;
     const unsigned gs = grid_for(bi.n_seg, blk), gb = grid_for(bi.B, blk);
     const double *ht = &h->d_tab[O - MSNAP_MIN_ORDER].HT[0][0];
+    if (w.fused.tpc > 0) {  // uniform batch: one persistent launch for the whole closed-form solve
+        const FusedPlan &f = w.fused;
+        FusedParams fp{};
+        fp.B = bi.B;
+        fp.ns = bi.ns_uniform;
+        fp.tpc = f.tpc;
+        fp.nit = f.nit;
+        fp.lane_stride = f.lane_stride;
+        fp.traj_stride = f.traj_stride;
+        fp.n_tiles = f.n_tiles;
+        fp.wp = io.wp;
+        fp.times_in = io.times_in;
+        fp.v_avg = io.v_avg;
+        fp.min_time = io.min_time;
+        fp.sp = sp;
+        fp.ht = ht;
+        fp.times_out = io.times_in ? nullptr : w.T;  // allocated times go to the workspace (the sampler reads them)
+        fp.coeff_out = w.coeff;
+        fp.max_dev_out = io.max_dev_out;
+        fp.vw_final_out = io.vw_final_out;
+        fp.iters_out = io.iters_out;
+        fp.best_s_out = io.best_s_out;
+        fp.flags = io.flags_out;
+        fp.state_ws = w.state;
+        prof_before(h, "k_fused_solve");
+        k_fused_solve<O><<<f.grid, FUSED_THREADS, f.smem, h->stream>>>(fp);
+        prof_after(h);
+        ++h->launches;
+        cudaError_t e = cudaPeekAtLastError();
+        if (e != cudaSuccess) {
+            h->last_error = std::string("k_fused_solve: ") + cudaGetErrorString(e);
+            cudaGetLastError();
+            return MSNAP_ERR_CUDA;
+        }
+        if (!io.times_in && io.times_out)
+            MS_CUDA(h, cudaMemcpyAsync(io.times_out, w.T, bi.n_seg * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        return MSNAP_OK;
+    }
     const double *T = io.times_in;
     if (!T) {
         MS_LAUNCH(h, k_times, gs, blk, bi, io.wp, io.v_avg, io.min_time, w.T);
@@ -192,9 +279,17 @@ int run_solve(msnap_context *h, const BatchIdx &bi, const SolveParams &sp, const
 }
 
 template <int O>
-void carve_solve_ws(Arena &a, long long n_seg, bool need_T, double *coeff_out, SolveWs &w) {
+void carve_solve_ws(Arena &a, long long n_seg, bool need_T, double *coeff_out, const FusedPlan &f, SolveWs &w) {
     using D = Dim<O>;
+    w.fused = f;
     w.T = need_T ? arena_take<double>(a, n_seg) : nullptr;
+    if (f.tpc > 0) {
+        w.base = w.segx = nullptr;
+        w.s_star = nullptr;
+        w.state = arena_take<double>(a, f.state_bytes / sizeof(double) + 32);
+        w.coeff = coeff_out ? coeff_out : arena_take<double>(a, (size_t)n_seg * 3 * D::M);
+        return;
+    }
     w.base = arena_take<double>(a, (size_t)n_seg * D::NBASE);
     w.state = arena_take<double>(a, (size_t)(n_seg + 1) * D::NSTATE);
     w.segx = arena_take<double>(a, (size_t)n_seg * D::NSEGX);
@@ -258,10 +353,11 @@ int solve_qp_dev(msnap_context *h, double pw, double vw, long long B, int ns_uni
     sp.max_iter = 0;
     sp.vel = vel;
     sp.acc = acc;
-    int rc = arena_reserve(h, h->ws, solve_ws_bytes<O>(n_seg, false, false));
+    const FusedPlan f = plan_fused<O>(h, bi, sp);
+    int rc = arena_reserve(h, h->ws, solve_ws_bytes<O>(n_seg, false, false, f));
     if (rc) return rc;
     SolveWs w;
-    carve_solve_ws<O>(h->ws, n_seg, false, coeff_out, w);
+    carve_solve_ws<O>(h->ws, n_seg, false, coeff_out, f, w);
     SolveIO io;
     io.wp = wp;
     io.times_in = times;
@@ -288,10 +384,11 @@ int generate_dev(msnap_context *h, const msnap_config *cfg, double sd, double v_
         sp.bc[6 + a] = cfg->start_acc[a];
         sp.bc[9 + a] = cfg->end_acc[a];
     }
-    int rc = arena_reserve(h, h->ws, solve_ws_bytes<O>(n_seg, true, coeff_out == nullptr) + sample_ws_bytes(n_seg, B));
+    const FusedPlan f = plan_fused<O>(h, bi, sp);
+    int rc = arena_reserve(h, h->ws, solve_ws_bytes<O>(n_seg, true, coeff_out == nullptr, f) + sample_ws_bytes(n_seg, B));
     if (rc) return rc;
     SolveWs w;
-    carve_solve_ws<O>(h->ws, n_seg, true, coeff_out, w);
+    carve_solve_ws<O>(h->ws, n_seg, true, coeff_out, f, w);
     SampleWs s;
     carve_sample_ws(h->ws, n_seg, B, s);
     SolveIO io;

@@ -11,6 +11,10 @@
 //     g = -2 pw L(t*) h  (entering the stationarity condition un-halved, exactly as ms.cpp:579 does)
 //   row j (interior waypoint j):  U_{j-1}' x_{j-1} + D_j x_j + U_j x_{j+1} = r_j,   x_j = y_j[1..o)
 //
+// Arithmetic is written with explicit fma() and the library is compiled with --fmad=false, so the sequence of
+// roundings is fixed by the source and identical wherever these functions are inlined: the fused kernel and the
+// per-phase kernels produce the same bits, and batching or sharding never changes a result.
+//
 // None of this code is derived from the reference's dense formulation (M, C_T, Q as n_coef^2 matrices and
 // 19 dense inverses per solve); it computes the same minimiser in O(ns) work.
 #ifndef MSNAP_DEVICE_CUH
@@ -121,50 +125,50 @@ __device__ __forceinline__ void assemble_row(double Ta, double Tc, const double 
         const double ta = (double)s_a * 0.0625, tc = (double)s_c * 0.0625;
 #pragma unroll
         for (int x = 0; x < 3; ++x) {
-            const double La = Pm[x] + ta * (P0[x] - Pm[x]);
-            const double Lc = P0[x] + tc * (Pp[x] - P0[x]);
-            double sa = ha[0] * Pm[x] + ha[O] * P0[x];
-            double sc = hc[0] * P0[x] + hc[O] * Pp[x];
+            const double La = fma(ta, P0[x] - Pm[x], Pm[x]);
+            const double Lc = fma(tc, Pp[x] - P0[x], P0[x]);
+            double sa = fma(ha[O], P0[x], ha[0] * Pm[x]);
+            double sc = fma(hc[O], Pp[x], hc[0] * P0[x]);
             if (first) {
 #pragma unroll
-                for (int q = 1; q < O; ++q) sa += ha[q] * bc.y0[x][q];
+                for (int q = 1; q < O; ++q) sa = fma(ha[q], bc.y0[x][q], sa);
             }
             if (last) {
 #pragma unroll
-                for (int q = 1; q < O; ++q) sc += hc[O + q] * bc.yN[x][q];
+                for (int q = 1; q < O; ++q) sc = fma(hc[O + q], bc.yN[x][q], sc);
             }
-            wa[x] = pw * (sa - 2.0 * La);
-            wc[x] = pw * (sc - 2.0 * Lc);
+            wa[x] = pw * fma(-2.0, La, sa);
+            wc[x] = pw * fma(-2.0, Lc, sc);
         }
     }
 #pragma unroll
     for (int r = 1; r <= B; ++r) {
 #pragma unroll
         for (int q = 1; q <= r; ++q) {  // packed lower triangle of D_j
-            double v = Tab<O>::S(O + r, O + q) * ipa[NP - r - q] + Tab<O>::S(r, q) * ipc[NP - r - q];
-            if (use_pw) v += pw * (ha[O + r] * ha[O + q] + hc[r] * hc[q]);
+            double v = fma(Tab<O>::S(r, q), ipc[NP - r - q], Tab<O>::S(O + r, O + q) * ipa[NP - r - q]);
+            if (use_pw) v = fma(pw, fma(hc[r], hc[q], ha[O + r] * ha[O + q]), v);
             row[(D::F_D + sym(r - 1, q - 1)) * fs] = v;
         }
 #pragma unroll
         for (int q = 1; q <= B; ++q) {
             double v = Tab<O>::S(r, O + q) * ipc[NP - r - q];
-            if (use_pw) v += pw * hc[r] * hc[O + q];
+            if (use_pw) v = fma(pw * hc[r], hc[O + q], v);
             row[(D::F_U + (r - 1) * B + (q - 1)) * fs] = v;
         }
         const double ca = Tab<O>::S(O + r, O) * ipa[NP - r];  // S_a[o+r][o] = -S_a[o+r][0]
         const double cc = Tab<O>::S(r, O) * ipc[NP - r];      // S_c[r][o]   = -S_c[r][0]
 #pragma unroll
         for (int x = 0; x < 3; ++x) {
-            double acc = ca * (P0[x] - Pm[x]) + cc * (Pp[x] - P0[x]);
+            double acc = fma(cc, Pp[x] - P0[x], ca * (P0[x] - Pm[x]));
             if (first) {
 #pragma unroll
-                for (int q = 1; q < O; ++q) acc += Tab<O>::S(O + r, q) * ipa[NP - r - q] * bc.y0[x][q];
+                for (int q = 1; q < O; ++q) acc = fma(Tab<O>::S(O + r, q) * ipa[NP - r - q], bc.y0[x][q], acc);
             }
             if (last) {
 #pragma unroll
-                for (int q = 1; q < O; ++q) acc += Tab<O>::S(r, O + q) * ipc[NP - r - q] * bc.yN[x][q];
+                for (int q = 1; q < O; ++q) acc = fma(Tab<O>::S(r, O + q) * ipc[NP - r - q], bc.yN[x][q], acc);
             }
-            if (use_pw) acc += ha[O + r] * wa[x] + hc[r] * wc[x];
+            if (use_pw) acc = fma(hc[r], wc[x], fma(ha[O + r], wa[x], acc));
             row[(D::F_R + (r - 1) * 3 + x) * fs] = -acc;
         }
     }
@@ -184,7 +188,7 @@ __device__ __forceinline__ bool chol_packed(double (&g)[B * (B + 1) / 2]) {
         for (int j = 0; j <= i; ++j) {
             double s = g[sym(i, j)];
 #pragma unroll
-            for (int k = 0; k < j; ++k) s -= g[sym(i, k)] * g[sym(j, k)];
+            for (int k = 0; k < j; ++k) s = fma(-g[sym(i, k)], g[sym(j, k)], s);
             if (i == j) {
                 ok = ok && (s > 0.0);
                 g[sym(i, i)] = rsqrt(s);  // 1 / G_ii
@@ -203,7 +207,7 @@ __device__ __forceinline__ void fwd_solve(const double (&g)[B * (B + 1) / 2], do
     for (int i = 0; i < B; ++i) {
         double s = v[i * st];
 #pragma unroll
-        for (int k = 0; k < i; ++k) s -= g[sym(i, k)] * v[k * st];
+        for (int k = 0; k < i; ++k) s = fma(-g[sym(i, k)], v[k * st], s);
         v[i * st] = s * g[sym(i, i)];
     }
 }
@@ -215,7 +219,7 @@ __device__ __forceinline__ void bwd_solve(const double (&g)[B * (B + 1) / 2], do
     for (int i = B - 1; i >= 0; --i) {
         double s = v[i * st];
 #pragma unroll
-        for (int k = i + 1; k < B; ++k) s -= g[sym(k, i)] * v[k * st];
+        for (int k = i + 1; k < B; ++k) s = fma(-g[sym(k, i)], v[k * st], s);
         v[i * st] = s * g[sym(i, i)];
     }
 }
@@ -253,14 +257,14 @@ __device__ __forceinline__ bool thomas_forward(int n_rows, double add00, BaseAt 
                 for (int q = 0; q <= p; ++q) {
                     double acc = g[sym(p, q)];
 #pragma unroll
-                    for (int t = 0; t < B; ++t) acc -= Y[t * B + p] * Y[t * B + q];
+                    for (int t = 0; t < B; ++t) acc = fma(-Y[t * B + p], Y[t * B + q], acc);
                     g[sym(p, q)] = acc;
                 }
 #pragma unroll
                 for (int x = 0; x < 3; ++x) {
                     double acc = r[p * 3 + x];
 #pragma unroll
-                    for (int t = 0; t < B; ++t) acc -= Y[t * B + p] * w[t * 3 + x];
+                    for (int t = 0; t < B; ++t) acc = fma(-Y[t * B + p], w[t * 3 + x], acc);
                     r[p * 3 + x] = acc;
                 }
             }
@@ -305,7 +309,7 @@ __device__ __forceinline__ void thomas_back_step(const double *b, int bfs, doubl
             for (int a = 0; a < 3; ++a) {
                 double acc = 0.0;
 #pragma unroll
-                for (int q = 0; q < B; ++q) acc += b[(D::F_U + p * B + q) * bfs] * xn[q * 3 + a];
+                for (int q = 0; q < B; ++q) acc = fma(b[(D::F_U + p * B + q) * bfs], xn[q * 3 + a], acc);
                 t[p * 3 + a] = acc;
             }
         }
@@ -331,11 +335,11 @@ __device__ __forceinline__ double deviation_ratio(const double *segx, int xs, co
     for (int a = 0; a < 3; ++a) {
         double p = 0.0;
 #pragma unroll
-        for (int i = 0; i < O; ++i) p += segx[i * xs] * yk[a][i];
+        for (int i = 0; i < O; ++i) p = fma(segx[i * xs], yk[a][i], p);
 #pragma unroll
-        for (int i = 0; i < O; ++i) p += segx[(O + i) * xs] * yk1[a][i];
+        for (int i = 0; i < O; ++i) p = fma(segx[(O + i) * xs], yk1[a][i], p);
         const double dd = p - segx[(M + a) * xs];
-        d2 += dd * dd;
+        d2 = fma(dd, dd, d2);
     }
     return sqrt(d2) * segx[(M + 3) * xs];
 }
@@ -356,7 +360,7 @@ __device__ __forceinline__ void hermite_coeffs(const double (&yk)[O], const doub
     for (int k = 0; k < M; ++k) {
         double acc = 0.0;
 #pragma unroll
-        for (int i = 0; i < M; ++i) acc += Tab<O>::H(k, i) * dh[i];
+        for (int i = 0; i < M; ++i) acc = fma(Tab<O>::H(k, i), dh[i], acc);
         out[M - 1 - k] = acc * ip[k];
     }
 }
@@ -376,7 +380,7 @@ __device__ __forceinline__ void eval_xyz(const double (&c)[3][2 * O], double t, 
 
 __device__ __forceinline__ double dist3(const double (&a)[3], const double (&b)[3]) {
     const double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
-    return sqrt(dx * dx + dy * dy + dz * dz);
+    return sqrt(fma(dz, dz, fma(dy, dy, dx * dx)));
 }
 
 }  // namespace msnap

@@ -104,8 +104,8 @@ __global__ void k_rows(BatchIdx bi, SolveParams sp, const double *__restrict__ w
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             const double d = p[3 + a] - p[a];
-            x[2 * O + a] = p[a] + tau * d;
-            l2 += d * d;
+            x[2 * O + a] = fma(tau, d, p[a]);
+            l2 = fma(d, d, l2);
         }
         const double len = sqrt(l2);
         x[2 * O + 3] = len > 1e-6 ? 1.0 / len : 0.0;
@@ -265,9 +265,9 @@ __global__ void k_search(BatchIdx bi, SolveParams sp, const double *__restrict__
         for (int a = 0; a < 3; ++a) {
             double p = 0.0;
 #pragma unroll
-            for (int i = 0; i < 2 * O; ++i) p += Tab<O>::HT(s, i) * dh[a][i];
-            const double dd = p - (yk[a][0] + tau * (yk1[a][0] - yk[a][0]));
-            d2 += dd * dd;
+            for (int i = 0; i < 2 * O; ++i) p = fma(Tab<O>::HT(s, i), dh[a][i], p);
+            const double dd = p - fma(tau, yk1[a][0] - yk[a][0], yk[a][0]);
+            d2 = fma(dd, dd, d2);
         }
         if (d2 > best) {
             best = d2;

@@ -117,3 +117,21 @@ def test_batch_equals_singles_bitwise(tool):
         sl = res.segment_slice(b)
         assert np.array_equal(one.coeff, res.coeff[sl]) and np.array_equal(one.samples, res.trajectory(b))
         assert one.iters[0] == res.iters[b] and one.max_dev[0] == res.max_dev[b]
+
+
+@pytest.mark.parametrize("order,ns,weights", [(4, 16, "shipped"), (4, 16, "plain"), (2, 6, "shipped"), (3, 9, "shipped"),
+                                               (5, 4, "shipped"), (4, 1, "shipped"), (4, 2, "plain"), (4, 40, "shipped")])
+def test_fused_kernel_equals_generic_path(tool, order, ns, weights):
+    """The fused persistent kernel (uniform batches, speculative reweighting) and the per-phase generic kernels
+    (sequential reweighting) are the same arithmetic: every output must agree bit for bit."""
+    wp = workloads.random_walks(37, ns, seed=order * 100 + ns)
+    cfg = workloads.synthetic_config(order, weights)
+    cfg.start_vel, cfg.end_acc = (0.5, -0.25, 0.1), (0.0, 0.3, -0.1)
+    tool.set_reweight_policy(1)          # generic: one thread per trajectory walks the reweighting loop
+    try:
+        gen = tool.generate_batch(cfg, wp, ns=ns)
+    finally:
+        tool.set_reweight_policy(0)      # automatic: fused kernel for uniform batches
+    fus = tool.generate_batch(cfg, wp, ns=ns)
+    for name in ("times", "coeff", "max_dev", "iters", "vw_final", "best_s", "sample_offset", "samples", "stats", "flags"):
+        assert np.array_equal(getattr(gen, name), getattr(fus, name)), name

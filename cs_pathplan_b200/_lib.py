@@ -61,6 +61,7 @@ SIGNATURES = {
     "msnap_generate_one_host": (_i, [_vp, _cfgp, _d, _d, _i, _vp, _ll, _vp, C.POINTER(_ll)]),
     "msnap_profile_begin": (_i, [_vp]),
     "msnap_profile_end": (_i, [_vp, C.c_char_p, _ll]),
+    "msnap_debug_phase_clocks": (_i, [_vp, _i, _vp]),
     "msnap_measure_fp64_peak": (_i, [_vp, C.POINTER(_d)]),
 }
 

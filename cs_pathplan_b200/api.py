@@ -188,6 +188,12 @@ class TrajectoryGeneratorTool:
         self._check(self._L.msnap_profile_end(self._h, buf, len(buf)))
         return json.loads(buf.value.decode())
 
+    def debug_phase_clocks(self, enable: bool, read: bool = False):
+        """Developer instrumentation: arm / read the fused kernel's per-phase clock stamps ([4096,16] int64)."""
+        out = np.zeros((4096, 16), dtype=np.int64) if read else None
+        self._check(self._L.msnap_debug_phase_clocks(self._h, int(enable), _ptr(out)))
+        return out
+
     def measure_fp64_peak(self) -> float:
         out = C.c_double(0.0)
         self._check(self._L.msnap_measure_fp64_peak(self._h, C.byref(out)))

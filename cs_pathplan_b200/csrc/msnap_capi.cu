@@ -29,6 +29,16 @@ struct Arena {  // grow-only device buffer with bump allocation, reset per call
     size_t cap = 0, used = 0;
 };
 
+// Launch plan of the fused kernel for a uniform batch, or tpc == 0 if the batch does not qualify.
+struct FusedPlan {
+    int tpc = 0, nit = 1, chunk = 1, lane_stride = 32, traj_stride = 0, grid = 0;
+    long long n_tiles = 0;
+    size_t smem = 0, state_bytes = 0;
+    // cache key
+    int order = 0, ns = 0, policy = 0;
+    long long B = 0;
+};
+
 struct msnap_context {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -37,7 +47,10 @@ struct msnap_context {
     Arena io;                        // device mirrors of host buffers (_host entry points)
     long long launches = 0;
     int policy = 0;
+    int spec_chunk = 0;               // reweighting iterations per speculative pass (0 = all at once)
+    std::vector<FusedPlan> plans;     // cached launch plans
     // optional per-kernel timing (msnap_profile_begin/end): one event pair per launch on the launching stream
+    long long *phase_clocks = nullptr;  // dev instrumentation (msnap_debug_phase_clocks)
     bool profiling = false;
     struct Timed { const char *name; cudaEvent_t e0, e1; };
     std::vector<Timed> timed;
@@ -137,12 +150,6 @@ struct SolveIO {
     unsigned *flags_out = nullptr;
 };
 
-// Launch plan of the fused kernel for a uniform batch, or tpc == 0 if the batch does not qualify.
-struct FusedPlan {
-    int tpc = 0, nit = 1, lane_stride = 32, traj_stride = 0, grid = 0;
-    long long n_tiles = 0;
-    size_t smem = 0, state_bytes = 0;
-};
 
 template <int O>
 FusedPlan plan_fused(msnap_context *h, const BatchIdx &bi, const SolveParams &sp) {
@@ -150,32 +157,60 @@ FusedPlan plan_fused(msnap_context *h, const BatchIdx &bi, const SolveParams &sp
     FusedPlan f;
     if (bi.ns_uniform <= 0 || h->policy == 1) return f;
     const int ns = bi.ns_uniform;
+    const int nit = sp.pw > 0.0 ? sp.max_iter + 1 : 1;
+    for (const FusedPlan &c : h->plans)
+        if (c.order == O && c.ns == ns && c.nit == nit && c.B == bi.B && c.policy == h->spec_chunk) return c;
+    f.order = O;
+    f.ns = ns;
+    f.nit = nit;
+    f.B = bi.B;
+    f.policy = h->spec_chunk;
+    if (nit > FUSED_THREADS) return f;
+    f.chunk = (h->spec_chunk > 0 && h->spec_chunk < nit) ? h->spec_chunk : nit;
     const FusedSmem<O> L(ns);
-    f.nit = sp.pw > 0.0 ? sp.max_iter + 1 : 1;
-    if (f.nit > FUSED_THREADS) return f;
     const size_t blk = (size_t)L.size * sizeof(double);
-    auto smem_for = [&](int tpc) { return tpc * blk + (size_t)tpc * f.nit * 12 + (size_t)tpc * 8 + 16; };
-    const size_t soft = 72 * 1024, hard = 220 * 1024;  // 3 CTAs per SM when the tile fits in 72 KB
-    int tpc = FUSED_THREADS / f.nit;
-    if ((long long)tpc > bi.B) tpc = (int)bi.B;
-    while (tpc > 1 && smem_for(tpc) > soft) --tpc;
-    if (smem_for(tpc) > hard) return f;  // a single trajectory does not fit: generic path
-    f.tpc = tpc;
-    f.traj_stride = L.size;
-    f.smem = smem_for(tpc);
-    f.lane_stride = ((tpc * f.nit + 31) / 32) * 32;
-    f.n_tiles = (bi.B + tpc - 1) / tpc;
-    int occ = 0;
-    cudaFuncSetAttribute(k_fused_solve<O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f.smem);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fused_solve<O>, FUSED_THREADS, f.smem) != cudaSuccess ||
-        occ < 1) {
-        cudaGetLastError();
-        f.tpc = 0;
-        return f;
+    const size_t st1 = (size_t)(ns - 1) * D::NSTATE * FUSED_SMEM_LANES * sizeof(double);  // shared-memory state rows
+    auto smem_for = [&](int tpc) { return tpc * blk + st1 + (size_t)tpc * nit * 12 + (size_t)tpc * 8 + 16; };
+    const size_t hard = 220 * 1024;
+    int tmax = FUSED_THREADS / f.chunk;
+    if (tmax > FUSED_SMEM_LANES) tmax = FUSED_SMEM_LANES;
+    if ((long long)tmax > bi.B) tmax = (int)bi.B;
+    // Pick the tile size that needs the fewest waves of resident CTAs (the kernel is latency-bound per tile, so a
+    // partial second wave costs a whole tile latency); among those, the largest tile (best lane utilisation).
+    long long best_waves = -1;
+    int best_occ = 0;
+    for (int tpc = tmax; tpc >= 1; --tpc) {
+        const size_t sm = smem_for(tpc);
+        if (sm > hard) continue;
+        int occ = 0;
+        cudaFuncSetAttribute(k_fused_solve<O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fused_solve<O>, FUSED_THREADS, sm) != cudaSuccess ||
+            occ < 1) {
+            cudaGetLastError();
+            continue;
+        }
+        const long long tiles = (bi.B + tpc - 1) / tpc, resident = (long long)occ * h->sm_count;
+        const long long waves = (tiles + resident - 1) / resident;
+        // beyond a few waves the persistent loop amortises everything: prefer big tiles then
+        const long long score = waves > 4 ? 4 : waves;
+        // single wave: the smallest such tile (more CTAs per SM overlap each other's phases)
+        if (best_waves < 0 || score < best_waves || (score == 1 && best_waves == 1)) {
+            best_waves = score;
+            best_occ = occ;
+            f.tpc = tpc;
+        }
     }
-    const long long resident = (long long)occ * h->sm_count;
+    if (f.tpc == 0) return f;  // a single trajectory does not fit: generic path
+    f.traj_stride = L.size;
+    f.smem = smem_for(f.tpc);
+    cudaFuncSetAttribute(k_fused_solve<O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hard);
+    f.lane_stride = FUSED_SLOT_LANES;
+    f.n_tiles = (bi.B + f.tpc - 1) / f.tpc;
+    const long long resident = (long long)best_occ * h->sm_count;
     f.grid = (int)(f.n_tiles < resident ? f.n_tiles : resident);
-    f.state_bytes = (size_t)f.grid * (ns - 1) * D::NSTATE * f.lane_stride * sizeof(double);
+    f.state_bytes = nit > 1 ? (size_t)f.grid * (ns - 1) * D::NSTATE * f.lane_stride * sizeof(double) : 0;
+    if (h->plans.size() > 64) h->plans.clear();
+    h->plans.push_back(f);
     return f;
 }
 
@@ -217,7 +252,7 @@ int run_solve(msnap_context *h, const BatchIdx &bi, const SolveParams &sp, const
         fp.ns = bi.ns_uniform;
         fp.tpc = f.tpc;
         fp.nit = f.nit;
-        fp.lane_stride = f.lane_stride;
+        fp.chunk = f.chunk;
         fp.traj_stride = f.traj_stride;
         fp.n_tiles = f.n_tiles;
         fp.wp = io.wp;
@@ -234,6 +269,7 @@ int run_solve(msnap_context *h, const BatchIdx &bi, const SolveParams &sp, const
         fp.best_s_out = io.best_s_out;
         fp.flags = io.flags_out;
         fp.state_ws = w.state;
+        fp.phase_clocks = h->phase_clocks;
         prof_before(h, "k_fused_solve");
         k_fused_solve<O><<<f.grid, FUSED_THREADS, f.smem, h->stream>>>(fp);
         prof_after(h);
@@ -503,6 +539,7 @@ int msnap_create(int device, msnap_handle *out) {
         return MSNAP_ERR_CUDA;
     }
     h->stream = h->own_stream;
+    if (const char *e = std::getenv("MSNAP_SPEC_CHUNK")) h->spec_chunk = std::atoi(e);
     *out = h;
     return MSNAP_OK;
 }
@@ -514,6 +551,7 @@ int msnap_destroy(msnap_handle h) {
     if (h->ws.base) cudaFree(h->ws.base);
     if (h->io.base) cudaFree(h->io.base);
     if (h->d_tab) cudaFree(h->d_tab);
+    if (h->phase_clocks) cudaFree(h->phase_clocks);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return MSNAP_OK;
@@ -916,6 +954,29 @@ int msnap_profile_end(msnap_handle h, char *json_out, long long capacity) {
     js += "}";
     if ((long long)js.size() + 1 > capacity) return MSNAP_ERR_CAPACITY;
     std::memcpy(json_out, js.c_str(), js.size() + 1);
+    return MSNAP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- dev instrumentation
+// Not part of the drop-in boundary: lets the developer see where a fused-kernel CTA spends its cycles.
+// enable != 0 allocates a [4096][16] clock buffer that the next fused launches fill; out (host, 4096*16 int64) reads it.
+int msnap_debug_phase_clocks(msnap_handle h, int enable, long long *out) {
+    if (!h) return MSNAP_ERR_INVALID_ARG;
+    DeviceGuard guard(h->device);
+    const size_t bytes = 4096 * 16 * sizeof(long long);
+    if (out && h->phase_clocks) {
+        MS_CUDA(h, cudaStreamSynchronize(h->stream));
+        MS_CUDA(h, cudaMemcpy(out, h->phase_clocks, bytes, cudaMemcpyDeviceToHost));
+    }
+    if (enable && !h->phase_clocks) {
+        MS_CUDA(h, cudaMalloc(&h->phase_clocks, bytes));
+    }
+    if (enable) MS_CUDA(h, cudaMemset(h->phase_clocks, 0, bytes));
+    if (!enable && h->phase_clocks) {
+        MS_CUDA(h, cudaStreamSynchronize(h->stream));
+        cudaFree(h->phase_clocks);
+        h->phase_clocks = nullptr;
+    }
     return MSNAP_OK;
 }
 

@@ -36,7 +36,8 @@ struct Dim {
     static constexpr int NR = 3 * B;            // right-hand sides, [r][axis]
     static constexpr int F_D = 0, F_U = ND, F_R = ND + NU;
     static constexpr int NBASE = ND + NU + NR;  // per-row constant data (order 4: 24 doubles)
-    static constexpr int NSTATE = ND + NR;      // per-row factor + solution (order 4: 15 doubles)
+    static constexpr int NSTATE = NR + NU;      // per-row sweep state: z_j / x_j and W_j (order 4: 18 doubles)
+    static constexpr int SX = 0, SW = NR;       // field offsets of x (z) and W inside a state row
     static constexpr int NSEGX = M + 4;         // per-segment deviation probe: h[M], L(t*)[3], 1/|P_{k+1}-P_k|
     static constexpr int NP = 2 * O - 1;        // inverse powers of T used by S: T^-1 .. T^-(2o-1)
 };
@@ -108,15 +109,13 @@ __device__ __forceinline__ void hermite_at(const double *__restrict__ ht, int s,
 //   out: row[F_D..], row[F_U..], row[F_R..] written with stride `fs` between fields
 // ---------------------------------------------------------------------------------------------------------
 template <int O>
-__device__ __forceinline__ void assemble_row(double Ta, double Tc, const double (&Pm)[3], const double (&P0)[3],
-                                             const double (&Pp)[3], bool first, bool last, const Boundary<O> &bc,
-                                             bool use_pw, double pw, int s_a, int s_c,
-                                             const double *__restrict__ ht, double *row, int fs) {
+__device__ __forceinline__ void assemble_row_p(const double (&ipa)[2 * O], const double (&pTa)[O],
+                                               const double (&ipc)[2 * O], const double (&pTc)[O],
+                                               const double (&Pm)[3], const double (&P0)[3], const double (&Pp)[3],
+                                               bool first, bool last, const Boundary<O> &bc, bool use_pw, double pw,
+                                               int s_a, int s_c, const double *__restrict__ ht, double *row, int fs) {
     using D = Dim<O>;
     constexpr int B = D::B, NP = D::NP;
-    double ipa[2 * O], ipc[2 * O], pTa[O], pTc[O];
-    time_powers<O>(Ta, ipa, pTa);
-    time_powers<O>(Tc, ipc, pTc);
     double ha[2 * O], hc[2 * O];
     double wa[3], wc[3];  // pw * (h . d_fixed - 2 L(t*)) per axis, for segments a and c
     if (use_pw) {
@@ -174,174 +173,280 @@ __device__ __forceinline__ void assemble_row(double Ta, double Tc, const double 
     }
 }
 
+// Same, computing the powers of the two segment times on the spot (generic path).
+template <int O>
+__device__ __forceinline__ void assemble_row(double Ta, double Tc, const double (&Pm)[3], const double (&P0)[3],
+                                             const double (&Pp)[3], bool first, bool last, const Boundary<O> &bc,
+                                             bool use_pw, double pw, int s_a, int s_c,
+                                             const double *__restrict__ ht, double *row, int fs) {
+    double ipa[2 * O], ipc[2 * O], pTa[O], pTc[O];
+    time_powers<O>(Ta, ipa, pTa);
+    time_powers<O>(Tc, ipc, pTc);
+    assemble_row_p<O>(ipa, pTa, ipc, pTc, Pm, P0, Pp, first, last, bc, use_pw, pw, s_a, s_c, ht, row, fs);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Small dense kernels on (order-1) x (order-1) SPD blocks, everything in registers.
 // ---------------------------------------------------------------------------------------------------------
-// In-place Cholesky of a packed symmetric block: G lower, diagonal stored as RECIPROCAL (one division per pivot).
-// Returns false if a pivot is not positive (or not finite).
+// Inverse of a packed symmetric positive-definite block, written for LATENCY: the block-tridiagonal sweep is one
+// long dependency chain per trajectory, so the pivot path is what the kernel waits on.  B <= 3 use the adjugate
+// (all cofactors in parallel, ONE reciprocal); every term of a cofactor carries the same powers of the segment
+// times, so the formula is as scale-invariant as a Cholesky factorisation of the same block.  B >= 4 falls back to
+// Cholesky.  Returns false if the block is not positive definite (or not finite).
 template <int B>
-__device__ __forceinline__ bool chol_packed(double (&g)[B * (B + 1) / 2]) {
-    bool ok = true;
+__device__ __forceinline__ bool sym_inverse(const double (&a)[B * (B + 1) / 2], double (&p)[B * (B + 1) / 2]) {
+    if constexpr (B == 1) {
+        p[0] = 1.0 / a[0];
+        return a[0] > 0.0;
+    } else if constexpr (B == 2) {
+        const double det = fma(a[0], a[2], -(a[1] * a[1]));
+        const double r = 1.0 / det;
+        p[0] = a[2] * r;
+        p[1] = -a[1] * r;
+        p[2] = a[0] * r;
+        return a[0] > 0.0 && det > 0.0;
+    } else if constexpr (B == 3) {
+        // a = [a00, a10, a11, a20, a21, a22]
+        const double c00 = fma(a[2], a[5], -(a[4] * a[4]));
+        const double c10 = fma(a[4], a[3], -(a[1] * a[5]));
+        const double c20 = fma(a[1], a[4], -(a[2] * a[3]));
+        const double c11 = fma(a[0], a[5], -(a[3] * a[3]));
+        const double c21 = fma(a[1], a[3], -(a[0] * a[4]));
+        const double c22 = fma(a[0], a[2], -(a[1] * a[1]));
+        const double det = fma(a[3], c20, fma(a[1], c10, a[0] * c00));
+        const double r = 1.0 / det;
+        p[0] = c00 * r;
+        p[1] = c10 * r;
+        p[2] = c11 * r;
+        p[3] = c20 * r;
+        p[4] = c21 * r;
+        p[5] = c22 * r;
+        return a[0] > 0.0 && c22 > 0.0 && det > 0.0;
+    } else {
+        // Cholesky a = G G', then p = G^-T G^-1
+        double g[B * (B + 1) / 2];
+        bool ok = true;
 #pragma unroll
-    for (int i = 0; i < B; ++i) {
+        for (int i = 0; i < B; ++i) {
 #pragma unroll
-        for (int j = 0; j <= i; ++j) {
-            double s = g[sym(i, j)];
+            for (int j = 0; j <= i; ++j) {
+                double s = a[sym(i, j)];
 #pragma unroll
-            for (int k = 0; k < j; ++k) s = fma(-g[sym(i, k)], g[sym(j, k)], s);
-            if (i == j) {
-                ok = ok && (s > 0.0);
-                g[sym(i, i)] = rsqrt(s);  // 1 / G_ii
-            } else {
-                g[sym(i, j)] = s * g[sym(j, j)];
+                for (int k = 0; k < j; ++k) s = fma(-g[sym(i, k)], g[sym(j, k)], s);
+                if (i == j) {
+                    ok = ok && (s > 0.0);
+                    g[sym(i, i)] = rsqrt(s);  // reciprocal diagonal
+                } else {
+                    g[sym(i, j)] = s * g[sym(j, j)];
+                }
             }
         }
-    }
-    return ok;
-}
-
-// v <- G^-1 v  (forward substitution), v has stride `st`
-template <int B>
-__device__ __forceinline__ void fwd_solve(const double (&g)[B * (B + 1) / 2], double *v, int st) {
+        double gi[B][B];  // G^-1 (lower)
 #pragma unroll
-    for (int i = 0; i < B; ++i) {
-        double s = v[i * st];
+        for (int c = 0; c < B; ++c) {
 #pragma unroll
-        for (int k = 0; k < i; ++k) s = fma(-g[sym(i, k)], v[k * st], s);
-        v[i * st] = s * g[sym(i, i)];
-    }
-}
-
-// v <- G^-T v  (backward substitution)
-template <int B>
-__device__ __forceinline__ void bwd_solve(const double (&g)[B * (B + 1) / 2], double *v, int st) {
+            for (int i = 0; i < B; ++i) {
+                if (i < c) { gi[i][c] = 0.0; continue; }
+                double s = (i == c) ? 1.0 : 0.0;
 #pragma unroll
-    for (int i = B - 1; i >= 0; --i) {
-        double s = v[i * st];
+                for (int k = c; k < i; ++k) s = fma(-g[sym(i, k)], gi[k][c], s);
+                gi[i][c] = s * g[sym(i, i)];
+            }
+        }
 #pragma unroll
-        for (int k = i + 1; k < B; ++k) s = fma(-g[sym(k, i)], v[k * st], s);
-        v[i * st] = s * g[sym(i, i)];
+        for (int i = 0; i < B; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = i; k < B; ++k) s = fma(gi[k][i], gi[k][j], s);
+                p[sym(i, j)] = s;
+            }
+        return ok;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Block-tridiagonal Cholesky solve of one trajectory for the three axes at once ("block Thomas").
-//   base(j)  : read-only rows  (D, U, r),   state(j): per-row factor G (packed, reciprocal diagonal) and, after the
-//   backward sweep, the solution x_j[r][axis] in the slot that held the forward-substituted right-hand side.
-//   add00    : value added to D_j[0][0] of every row (2 * vel_zero_weight: one vw from each adjacent segment)
-//   Storage is abstracted by two functors returning (pointer to field 0, field stride) for a row index.
-// Returns false if any pivot failed.
+// Block-tridiagonal solve of one trajectory for the three axes at once ("block Thomas"), SPD system
+//     U_{j-1}' x_{j-1} + D_j x_j + U_j x_{j+1} = r_j .
+// Forward sweep:   D'_j = D_j - U_{j-1}' W_{j-1},   r'_j = r_j - U_{j-1}' z_{j-1},
+//                  P_j = D'_j^-1,   z_j = P_j r'_j,   W_j = P_j U_j
+// Backward sweep:  x_j = z_j - W_j x_{j+1}
+//   base(j)  : read-only rows (D, U, r);  state(j): z_j [r][axis] (overwritten by x_j on the way back) and W_j.
+//   add00    : added to D_j[0][0] of every row (2 * vel_zero_weight: one vw from each adjacent segment).
+// Storage is abstracted by accessor types:  `const double* operator()(int j)` = field 0 of row j, and a
+// COMPILE-TIME field stride `FS` -- the sweep is issue-bound, so every address must be base + immediate.
 // ---------------------------------------------------------------------------------------------------------
 template <int O, class BaseAt, class StateAt>
-__device__ __forceinline__ bool thomas_forward(int n_rows, double add00, BaseAt base_at, StateAt state_at) {
+__device__ __forceinline__ bool thomas_forward(int n_rows, double add00, const BaseAt base_at, const StateAt state_at) {
     using D = Dim<O>;
-    constexpr int B = D::B, ND = D::ND, NR = D::NR;
+    constexpr int B = D::B, ND = D::ND, NR = D::NR, NU = D::NU;
+    constexpr int bfs = BaseAt::FS, sfs = StateAt::FS;
     bool ok = true;
-    double Y[B * B];  // Y = G_{j-1}^-1 U_{j-1}   (column q at Y[.*B + q])
-    double w[NR];     // w = G_{j-1}^-1 r'_{j-1}, [r][axis]
+    double W[NU];  // W_{j-1} = P U_{j-1}
+    double z[NR];  // z_{j-1}, [r][axis]
     for (int j = 0; j < n_rows; ++j) {
-        int bfs, sfs;
-        const double *b = base_at(j, bfs);
-        double *s = state_at(j, sfs);
-        double g[ND], r[NR];
+        const double *b = base_at(j);
+        double *s = state_at(j);
+        double d[ND], r[NR];
 #pragma unroll
-        for (int i = 0; i < ND; ++i) g[i] = b[(D::F_D + i) * bfs];
+        for (int i = 0; i < ND; ++i) d[i] = b[(D::F_D + i) * bfs];
 #pragma unroll
         for (int i = 0; i < NR; ++i) r[i] = b[(D::F_R + i) * bfs];
-        g[0] += add00;
+        d[0] += add00;
         if (j > 0) {
-            // D'_j = D_j - Y'Y ;  r'_j = r_j - Y'w
+            const double *bp = base_at(j - 1);  // U_{j-1} is re-read (a broadcast LDS) rather than carried
+            double U[NU];
+#pragma unroll
+            for (int i = 0; i < NU; ++i) U[i] = bp[(D::F_U + i) * bfs];
 #pragma unroll
             for (int p = 0; p < B; ++p) {
 #pragma unroll
                 for (int q = 0; q <= p; ++q) {
-                    double acc = g[sym(p, q)];
+                    double acc = d[sym(p, q)];
 #pragma unroll
-                    for (int t = 0; t < B; ++t) acc = fma(-Y[t * B + p], Y[t * B + q], acc);
-                    g[sym(p, q)] = acc;
+                    for (int t = 0; t < B; ++t) acc = fma(-U[t * B + p], W[t * B + q], acc);
+                    d[sym(p, q)] = acc;
                 }
 #pragma unroll
                 for (int x = 0; x < 3; ++x) {
                     double acc = r[p * 3 + x];
 #pragma unroll
-                    for (int t = 0; t < B; ++t) acc = fma(-Y[t * B + p], w[t * 3 + x], acc);
+                    for (int t = 0; t < B; ++t) acc = fma(-U[t * B + p], z[t * 3 + x], acc);
                     r[p * 3 + x] = acc;
                 }
             }
         }
-        ok = chol_packed<B>(g) && ok;
+        double P[ND];
+        ok = sym_inverse<B>(d, P) && ok;
 #pragma unroll
-        for (int x = 0; x < 3; ++x) fwd_solve<B>(g, r + x, 3);
+        for (int p = 0; p < B; ++p)
 #pragma unroll
-        for (int i = 0; i < ND; ++i) s[i * sfs] = g[i];
+            for (int x = 0; x < 3; ++x) {
+                double acc = P[sym(p, 0)] * r[x];
 #pragma unroll
-        for (int i = 0; i < NR; ++i) {
-            s[(ND + i) * sfs] = r[i];
-            w[i] = r[i];
-        }
+                for (int t = 1; t < B; ++t) acc = fma(P[sym(p, t)], r[t * 3 + x], acc);
+                z[p * 3 + x] = acc;
+            }
+#pragma unroll
+        for (int i = 0; i < NR; ++i) s[(D::SX + i) * sfs] = z[i];
         if (j + 1 < n_rows) {
+            double U[NU];
 #pragma unroll
-            for (int i = 0; i < B * B; ++i) Y[i] = b[(D::F_U + i) * bfs];
+            for (int i = 0; i < NU; ++i) U[i] = b[(D::F_U + i) * bfs];
 #pragma unroll
-            for (int q = 0; q < B; ++q) fwd_solve<B>(g, Y + q, B);
+            for (int p = 0; p < B; ++p)
+#pragma unroll
+                for (int q = 0; q < B; ++q) {
+                    double acc = P[sym(p, 0)] * U[q];
+#pragma unroll
+                    for (int t = 1; t < B; ++t) acc = fma(P[sym(p, t)], U[t * B + q], acc);
+                    W[p * B + q] = acc;
+                }
+#pragma unroll
+            for (int i = 0; i < NU; ++i) s[(D::SW + i) * sfs] = W[i];
         }
     }
     return ok;
 }
 
-// One backward step: given x_{j+1} (xn, [r][axis]; ignored when `has_next` is false) produce x_j in place in
-// state(j) and in x.
-template <int O>
-__device__ __forceinline__ void thomas_back_step(const double *b, int bfs, double *s, int sfs, bool has_next,
-                                                 const double (&xn)[3 * (O - 1)], double (&x)[3 * (O - 1)]) {
+// One backward step: x_j = z_j - W_j x_{j+1} (xn; ignored when !has_next).  Writes x_j over z_j in the state row
+// and returns it in x.  FS = compile-time field stride of the state row `s`.
+template <int O, int FS>
+__device__ __forceinline__ void thomas_back_step(double *s, bool has_next, const double (&xn)[3 * (O - 1)],
+                                                 double (&x)[3 * (O - 1)]) {
     using D = Dim<O>;
-    constexpr int B = D::B, ND = D::ND, NR = D::NR;
-    double g[ND];
+    constexpr int B = D::B, NR = D::NR;
 #pragma unroll
-    for (int i = 0; i < ND; ++i) g[i] = s[i * sfs];
-#pragma unroll
-    for (int i = 0; i < NR; ++i) x[i] = s[(ND + i) * sfs];
+    for (int i = 0; i < NR; ++i) x[i] = s[(D::SX + i) * FS];
     if (has_next) {
-        double t[NR];
+        double W[D::NU];
 #pragma unroll
-        for (int p = 0; p < B; ++p) {
+        for (int i = 0; i < D::NU; ++i) W[i] = s[(D::SW + i) * FS];
+#pragma unroll
+        for (int p = 0; p < B; ++p)
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                double acc = 0.0;
+                double acc = x[p * 3 + a];
 #pragma unroll
-                for (int q = 0; q < B; ++q) acc = fma(b[(D::F_U + p * B + q) * bfs], xn[q * 3 + a], acc);
-                t[p * 3 + a] = acc;
+                for (int q = 0; q < B; ++q) acc = fma(-W[p * B + q], xn[q * 3 + a], acc);
+                x[p * 3 + a] = acc;
             }
-        }
 #pragma unroll
-        for (int a = 0; a < 3; ++a) fwd_solve<B>(g, t + a, 3);
-#pragma unroll
-        for (int i = 0; i < NR; ++i) x[i] -= t[i];
+        for (int i = 0; i < NR; ++i) s[(D::SX + i) * FS] = x[i];
     }
-#pragma unroll
-    for (int a = 0; a < 3; ++a) bwd_solve<B>(g, x + a, 3);
-#pragma unroll
-    for (int i = 0; i < NR; ++i) s[(ND + i) * sfs] = x[i];
 }
 
-// Deviation probe of one segment (ms.cpp:594-617): || p(t*) - L(t*) || / |P_{k+1} - P_k| from the endpoint
-// derivatives.  segx = { h[M], L[3], rlen } with stride xs.  yk/yk1: [axis][o] endpoint derivative vectors.
-template <int O>
-__device__ __forceinline__ double deviation_ratio(const double *segx, int xs, const double (&yk)[3][O],
-                                                  const double (&yk1)[3][O]) {
+// Squared deviation ratio of one segment (ms.cpp:594-617):  || p(t*) - L(t*) ||^2 / |P_{k+1} - P_k|^2  from the
+// endpoint positions pk, pk1 and derivative vectors dk, dk1 ([r-1][axis], r = 1..o-1).
+// segx = { h[M], L[3], 1/len^2 } with compile-time stride XS.  The caller takes the square root of the maximum.
+template <int O, int XS>
+__device__ __forceinline__ double deviation_sq(const double *segx, const double (&pk)[3], const double *dk,
+                                               const double (&pk1)[3], const double *dk1) {
     constexpr int M = 2 * O;
     double d2 = 0.0;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        double p = 0.0;
+        double p = segx[0] * pk[a];
 #pragma unroll
-        for (int i = 0; i < O; ++i) p = fma(segx[i * xs], yk[a][i], p);
+        for (int r = 1; r < O; ++r) p = fma(segx[r * XS], dk[(r - 1) * 3 + a], p);
+        p = fma(segx[O * XS], pk1[a], p);
 #pragma unroll
-        for (int i = 0; i < O; ++i) p = fma(segx[(O + i) * xs], yk1[a][i], p);
-        const double dd = p - segx[(M + a) * xs];
+        for (int r = 1; r < O; ++r) p = fma(segx[(O + r) * XS], dk1[(r - 1) * 3 + a], p);
+        const double dd = p - segx[(M + a) * XS];
         d2 = fma(dd, dd, d2);
     }
-    return sqrt(d2) * segx[(M + 3) * xs];
+    return d2 * segx[(M + 3) * XS];
+}
+
+// Backward sweep of one trajectory with the deviation probe of every segment folded in (when EVAL).  The row loop
+// is unrolled by two with the roles of the two solution vectors swapped, so nothing is copied between iterations.
+//   pos(w, out[3])  : position of waypoint w = 0..ns
+//   state_at(j)     : state row of interior waypoint j+1
+//   d0 / dN         : fixed derivative vectors of the first / last waypoint, [r-1][axis]
+//   segx_at(k)      : deviation probe of segment k
+// Returns max_k deviation ratio (0 when !EVAL); the solution is left in the state rows.
+template <int O, bool EVAL, class StateAt, class SegxAt, class PosAt>
+__device__ __forceinline__ double thomas_backward(int n_rows, const StateAt state_at, const SegxAt segx_at,
+                                                  const PosAt pos, const double *d0, const double *dN) {
+    using D = Dim<O>;
+    constexpr int NR = D::NR;
+    const int ns = n_rows + 1;
+    double xa[NR], xb[NR], pa[3], pb[3];
+    double m2 = 0.0;
+    // segment k = ns-1 .. 0 has endpoints (waypoint k, waypoint k+1); walk k downwards
+    pos(ns, pb);
+#pragma unroll
+    for (int i = 0; i < NR; ++i) xb[i] = dN[i];  // derivatives of the last waypoint (fixed)
+    int j = n_rows - 1;                           // row of waypoint j+1
+    bool first = true;                            // xb still holds the fixed end derivatives (no W coupling)
+    // step: compute x of waypoint j+1 into `xo` from `xi` (= x of waypoint j+2), probe segment j+1
+    auto step = [&](double (&xo)[NR], double (&po)[3], const double (&xi)[NR], const double (&pi)[3]) {
+        thomas_back_step<O, StateAt::FS>(state_at(j), !first, xi, xo);
+        pos(j + 1, po);
+        if (EVAL) m2 = fmax(m2, deviation_sq<O, SegxAt::FS>(segx_at(j + 1), po, xo, pi, xi));
+        first = false;
+        --j;
+    };
+    // NOTE on `first`: for the last row x_{n-1} = z_{n-1} (no coupling), and the segment above it ends at the fixed
+    // last waypoint whose derivatives are in xb.
+    while (j >= 1) {
+        step(xa, pa, xb, pb);
+        step(xb, pb, xa, pa);
+    }
+    if (j == 0) {
+        step(xa, pa, xb, pb);
+        if (EVAL) {
+            double p0[3];
+            pos(0, p0);
+            m2 = fmax(m2, deviation_sq<O, SegxAt::FS>(segx_at(0), p0, d0, pa, xa));
+        }
+    } else if (EVAL) {  // j == -1: the first segment's far end is in (pb, xb)
+        double p0[3];
+        pos(0, p0);
+        m2 = fmax(m2, deviation_sq<O, SegxAt::FS>(segx_at(0), p0, d0, pb, xb));
+    }
+    return EVAL ? sqrt(m2) : 0.0;
 }
 
 // Polynomial coefficients of one segment and axis from its endpoint derivatives (c = M_k^-1 d, ms.cpp:584-591):

@@ -1,14 +1,14 @@
 // msnap_fused.cuh -- fused, persistent solve kernel for uniform batches (every trajectory has `ns` segments).
 //
 // One launch replaces k_times .. k_coeff of the generic path.  A CTA of FUSED_THREADS threads owns a tile of `tpc`
-// consecutive trajectories whose waypoints, block rows and deviation probes live in shared memory; it walks the
-// phases below with __syncthreads() between them and loops over tiles (persistent grid, one wave).
+// consecutive trajectories whose waypoints, time powers, block rows and deviation probes live in shared memory; it
+// walks the phases below with __syncthreads() between them and loops over tiles (persistent grid).
 //
 //   phase          parallel over            work                                                   reference lines
-//   load           elements (coalesced)     waypoints -> smem (axis-major)
-//   times          (traj, seg)              T_k                                                      ms.cpp:63-72
+//   load           elements (coalesced)     waypoints + boundary derivatives -> smem
+//   times          (traj, seg)              T_k, T_k^-e, T_k^r                                       ms.cpp:63-72
 //   rows (pass 1)  (traj, row)              D_j, U_j, r_j without penalties                          ms.cpp:247-330, 350
-//   thomas pass 1  traj                     block-tridiagonal Cholesky, 3 axes                       ms.cpp:357-405
+//   thomas pass 1  traj                     block-tridiagonal solve, 3 axes (state in smem)          ms.cpp:357-405
 //   search         (traj, seg)              17-sample arg-max of the deviation -> s*                 ms.cpp:408-439
 //   rows (pass 2)  (traj, row) / (traj,seg) rows with pw*h h' and g; deviation probes                ms.cpp:441-469, 511-522
 //   thomas spec    (traj, reweight iter)    ALL velocity weights of the reweighting loop at once     ms.cpp:76-90, 474-509, 524-592
@@ -17,14 +17,14 @@
 //   coeff          (traj, seg, axis)        c = M^-1 d, PolyCoeff layout, straight to HBM            ms.cpp:584-591, 626-646
 //
 // Why speculate on the reweighting loop: its velocity weights are a fixed sequence (vw0, then 0.01 or 2x, ...) and
-// only the *decision* to continue is data dependent, so the <= 11 factorisations of a trajectory are independent
-// problems.  At the headline size (4 096 x 16) one Thomas chain per trajectory would leave 4 096 threads on a
-// 148-SM GPU; 11 chains per trajectory give 45 056, which is what fills the FP64 pipes.  Results are bitwise
-// identical to the sequential loop (same arithmetic per iteration, same selection rule).
+// only the *decision* to continue is data dependent, so the <= 11 solves of a trajectory are independent problems.
+// At the headline size (4 096 x 16) one Thomas chain per trajectory would leave 4 096 threads on a 148-SM GPU;
+// 11 chains per trajectory give 45 056.  Results are bitwise identical to the sequential loop (same arithmetic per
+// iteration, same selection rule).
 //
-// Per-lane factor/solution state (15 doubles per row at order 4) does not fit in shared memory for that many
-// chains; it lives in an L2-resident global scratch slot per CTA, lane-major so every access is a coalesced 256 B
-// warp transaction.
+// The sweeps are issue-bound, so every array in the hot loops has COMPILE-TIME strides (addresses are base +
+// immediate): shared-memory rows are [row][fields] with an odd row pitch, sweep state is [row][field][lanes] with
+// a fixed lane count (16 in shared memory, 128 in the per-CTA L2-resident scratch slot of the speculative lanes).
 #ifndef MSNAP_FUSED_CUH
 #define MSNAP_FUSED_CUH
 
@@ -32,15 +32,17 @@
 
 namespace msnap {
 
-constexpr int FUSED_THREADS = 128;
+constexpr int FUSED_THREADS = 192;     // 2 CTAs per SM at <= 170 registers per thread
+constexpr int FUSED_SLOT_LANES = FUSED_THREADS;  // lanes per state row of the global scratch slot
+constexpr int FUSED_SMEM_LANES = 14;   // lanes per state row in shared memory (= max trajectories per tile)
 
 struct FusedParams {
     long long B;
     int ns;
-    int tpc;           // trajectories per tile
-    int nit;           // lanes per trajectory in the speculative phase: max_iter + 1 if pw > 0 else 1
-    int lane_stride;   // lanes per state row in the scratch slot (multiple of 32, >= tpc * nit)
-    int traj_stride;   // doubles per trajectory block in shared memory (== 1 mod 16: bank-conflict-free broadcast)
+    int tpc;           // trajectories per tile (<= FUSED_SMEM_LANES)
+    int nit;           // solves per trajectory in the speculative phase: max_iter + 1 if pw > 0 else 1
+    int chunk;         // reweighting iterations solved concurrently per speculative pass (tpc * chunk <= threads)
+    int traj_stride;   // doubles per trajectory block in shared memory (odd: conflict-free broadcast)
     long long n_tiles;
     const double *wp;
     const double *times_in;  // nullptr => allocate from v_avg / min_time
@@ -50,134 +52,140 @@ struct FusedParams {
     double *times_out, *coeff_out, *max_dev_out, *vw_final_out;
     int *iters_out, *best_s_out;
     unsigned *flags;
-    double *state_ws;        // [gridDim.x][ns-1][NSTATE][lane_stride]
+    double *state_ws;        // [gridDim.x][ns-1][NSTATE][FUSED_SLOT_LANES]
+    long long *phase_clocks; // optional [gridDim.x][16]: clock64() of thread 0 after each phase of the CTA's first tile
 };
 
+// Shared-memory layout of one trajectory block (offsets in doubles).  Row pitches are odd so that the
+// (traj, row)-parallel writers hit distinct banks; readers in the sweeps broadcast.
 template <int O>
 struct FusedSmem {
-    // offsets in doubles inside one trajectory block
-    int oT, oP, oBase, oSegx, oS, size;
+    using D = Dim<O>;
+    static constexpr int ST = 3;                 // per segment: T, 1/T (powers are re-multiplied, not stored)
+    static constexpr int BS = D::NBASE | 1;      // per row: D, U, r
+    static constexpr int XS = D::NSEGX | 1;      // per segment: deviation probe
+    int oSeg, oP, oBC, oBase, oSegx, oS, size;
     __host__ __device__ FusedSmem(int ns) {
-        using D = Dim<O>;
         const int nr = ns - 1;
-        oT = 0;
-        oP = oT + ns;
-        oBase = oP + 3 * (ns + 1);
-        oSegx = oBase + D::NBASE * nr;
-        oS = oSegx + D::NSEGX * ns;       // ns ints
+        oSeg = 0;
+        oP = oSeg + ST * ns;              // [w][3]
+        oBC = oP + 3 * (ns + 1);          // d0[NR], dN[NR]: fixed boundary derivatives, [r-1][axis]
+        oBase = oBC + 2 * D::NR;
+        oSegx = oBase + BS * nr;
+        oS = oSegx + XS * ns;             // ns ints
         size = oS + (ns + 1) / 2;
-        size += (17 - (size % 16)) % 16;  // size == 1 (mod 16)
+        size |= 1;                        // odd pitch: t * size (mod 16) is distinct for 16 consecutive t
     }
 };
 
-// Row storage accessors handed to thomas_forward / thomas_back_step (pointer to field 0 of row j + field stride).
-struct SmemRows {
-    const double *ptr;  // field 0 of row 0; rows are consecutive doubles, fields `fs` apart
-    int fs;
-    __device__ __forceinline__ const double *operator()(int j, int &f) const { f = fs; return ptr + j; }
+template <int O>
+struct FBaseRows {
+    const double *p;
+    static constexpr int FS = 1;
+    __device__ __forceinline__ const double *operator()(int j) const { return p + j * FusedSmem<O>::BS; }
 };
-struct SlotRows {
-    double *ptr;  // this lane's column of the CTA's scratch slot
-    int fs;       // lane stride
-    int row;      // doubles per row = NSTATE * lane stride
-    __device__ __forceinline__ double *operator()(int j, int &f) const { f = fs; return ptr + (size_t)j * row; }
+template <int O>
+struct FSegxRows {
+    const double *p;
+    static constexpr int FS = 1;
+    __device__ __forceinline__ const double *operator()(int k) const { return p + k * FusedSmem<O>::XS; }
+};
+struct FPos {
+    const double *p;
+    __device__ __forceinline__ void operator()(int w, double (&out)[3]) const {
+        out[0] = p[3 * w];
+        out[1] = p[3 * w + 1];
+        out[2] = p[3 * w + 2];
+    }
+};
+template <int O, int LANES>
+struct FStateRows {
+    double *p;  // this lane's column
+    static constexpr int FS = LANES;
+    __device__ __forceinline__ double *operator()(int j) const { return p + (size_t)j * (Dim<O>::NSTATE * LANES); }
 };
 
-// Per-tile context shared by the phase functions.
+// segment time powers from smem: ip[e] = T^-e (e = 0..2o-1), pT[r] = T^r (r = 0..o-1)
 template <int O>
-struct FusedCtx {
-    double *smem;
-    double *slot;
-    FusedSmem<O> L;
-    int ns, nr, nit, tstride, lstride;
-    long long b0, g0;
-    __device__ FusedCtx(int ns_) : L(ns_) {}
-    __device__ __forceinline__ double *block(int t) const { return smem + t * tstride; }
-};
+__device__ __forceinline__ void fused_powers(const double *seg, double (&ip)[2 * O], double (&pT)[O]) {
+    const double T = seg[0], inv = seg[1];  // same multiplication sequence as time_powers(): bitwise identical
+    ip[0] = 1.0;
+#pragma unroll
+    for (int e = 1; e < 2 * O; ++e) ip[e] = ip[e - 1] * inv;
+    pT[0] = 1.0;
+#pragma unroll
+    for (int r = 1; r < O; ++r) pT[r] = pT[r - 1] * T;
+}
 
-// Endpoint derivatives of waypoint w: position from smem, derivatives from the boundary data or a lane's solution.
+// Endpoint derivative vector ([r-1][axis]) of waypoint w from the fixed boundary data or the solved state rows.
 template <int O>
-__device__ __forceinline__ void fused_endpoint(const double *P, int ns, const double *slot_lane, int lane_stride, int w,
-                                               const Boundary<O> &bc, double (&y)[3][O]) {
+__device__ __forceinline__ void fused_derivs(const double *bcs, const double *state_lane, int ns, int w,
+                                             double (&d)[3 * (O - 1)]) {
     using D = Dim<O>;
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        y[a][0] = P[a * (ns + 1) + w];
-#pragma unroll
-        for (int r = 1; r < O; ++r) {
-            if (w == 0) y[a][r] = bc.y0[a][r];
-            else if (w == ns) y[a][r] = bc.yN[a][r];
-            else y[a][r] = slot_lane[((size_t)(w - 1) * D::NSTATE + D::ND + (r - 1) * 3 + a) * lane_stride];
-        }
+    for (int i = 0; i < D::NR; ++i) {
+        if (w == 0) d[i] = bcs[i];
+        else if (w == ns) d[i] = bcs[D::NR + i];
+        else d[i] = state_lane[((w - 1) * D::NSTATE + D::SX + i) * FUSED_SMEM_LANES];
     }
 }
 
-// The phase bodies are deliberately NOT inlined into the persistent tile loop: inside a loop the compiler hoists the
-// constant-table reads (c_tab) into registers, which costs ~100 registers and spills; as straight-line functions the
-// table entries fold into the DFMA/DMUL instructions as constant-bank operands.
+// The table-heavy phase bodies are deliberately NOT inlined into the persistent tile loop: inside a loop the
+// compiler hoists the constant-table reads (c_tab) into registers, which costs ~100 registers and spills; as
+// straight-line functions the table entries fold into the DFMA/DMUL instructions as constant-bank operands.
 
 // rows: item (t, j), j = 1..ns-1
 template <int O>
-__device__ __noinline__ void fused_row_item(const FusedParams &p, const FusedCtx<O> &c, int t, int j, bool with_pw) {
-    const int ns = c.ns;
-    double *blk = c.block(t);
-    const double *P = blk + c.L.oP;
-    const int *ss = reinterpret_cast<const int *>(blk + c.L.oS);
+__device__ __noinline__ void fused_row_item(const FusedParams &p, double *blk, int ns, int j, bool with_pw) {
+    using D = Dim<O>;
+    const FusedSmem<O> L(ns);
+    const double *P = blk + L.oP + 3 * j;
+    const int *ss = reinterpret_cast<const int *>(blk + L.oS);
     Boundary<O> bc;
-    boundary_of<O>(p.sp, c.b0 + t, bc);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        bc.y0[a][0] = bc.yN[a][0] = 0.0;
+#pragma unroll
+        for (int r = 1; r < O; ++r) {
+            bc.y0[a][r] = blk[L.oBC + (r - 1) * 3 + a];
+            bc.yN[a][r] = blk[L.oBC + D::NR + (r - 1) * 3 + a];
+        }
+    }
     double Pm[3], P0[3], Pp[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        Pm[a] = P[a * (ns + 1) + j - 1];
-        P0[a] = P[a * (ns + 1) + j];
-        Pp[a] = P[a * (ns + 1) + j + 1];
+        Pm[a] = P[a - 3];
+        P0[a] = P[a];
+        Pp[a] = P[a + 3];
     }
-    assemble_row<O>(blk[c.L.oT + j - 1], blk[c.L.oT + j], Pm, P0, Pp, j == 1, j == ns - 1, bc, with_pw, p.sp.pw,
-                    with_pw ? ss[j - 1] : 0, with_pw ? ss[j] : 0, p.ht, blk + c.L.oBase + (j - 1), c.nr);
-}
-
-// pass-1 Thomas of trajectory t (one lane); returns pivot status
-template <int O>
-__device__ __noinline__ bool fused_pass1_lane(const FusedCtx<O> &c, int t) {
-    using D = Dim<O>;
-    constexpr int NR = D::NR;
-    const SmemRows base_at{c.block(t) + c.L.oBase, c.nr};
-    const SlotRows state_at{c.slot + t, c.lstride, D::NSTATE * c.lstride};
-    const bool ok = thomas_forward<O>(c.nr, 0.0, base_at, state_at);
-    double xn[NR], x[NR];
-#pragma unroll
-    for (int i = 0; i < NR; ++i) xn[i] = 0.0;
-    for (int j = c.nr - 1; j >= 0; --j) {
-        int bfs, sfs;
-        const double *bb = base_at(j, bfs);
-        double *st = state_at(j, sfs);
-        thomas_back_step<O>(bb, bfs, st, sfs, j + 1 < c.nr, xn, x);
-#pragma unroll
-        for (int i = 0; i < NR; ++i) xn[i] = x[i];
-    }
-    return ok;
+    double ipa[2 * O], ipc[2 * O], pTa[O], pTc[O];
+    fused_powers<O>(blk + L.oSeg + (j - 1) * L.ST, ipa, pTa);
+    fused_powers<O>(blk + L.oSeg + j * L.ST, ipc, pTc);
+    assemble_row_p<O>(ipa, pTa, ipc, pTc, Pm, P0, Pp, j == 1, j == ns - 1, bc, with_pw, p.sp.pw,
+                      with_pw ? ss[j - 1] : 0, with_pw ? ss[j] : 0, p.ht, blk + L.oBase + (j - 1) * L.BS, 1);
 }
 
 // search: item (t, k) -> index of the worst-deviation sample (first strict maximum, ms.cpp:435)
 template <int O>
-__device__ __noinline__ int fused_search_item(const FusedParams &p, const FusedCtx<O> &c, int t, int k) {
-    const int ns = c.ns;
-    const double *blk = c.block(t);
-    Boundary<O> bc;
-    boundary_of<O>(p.sp, c.b0 + t, bc);
-    double yk[3][O], yk1[3][O];
-    fused_endpoint<O>(blk + c.L.oP, ns, c.slot + t, c.lstride, k, bc, yk);
-    fused_endpoint<O>(blk + c.L.oP, ns, c.slot + t, c.lstride, k + 1, bc, yk1);
+__device__ __noinline__ int fused_search_item(const double *blk, const double *state_lane, int ns, int k) {
+    const FusedSmem<O> L(ns);
+    double dk[3 * (O - 1)], dk1[3 * (O - 1)];
+    fused_derivs<O>(blk + L.oBC, state_lane, ns, k, dk);
+    fused_derivs<O>(blk + L.oBC, state_lane, ns, k + 1, dk1);
+    const double *P = blk + L.oP + 3 * k;
     double ip[2 * O], pT[O];
-    time_powers<O>(blk[c.L.oT + k], ip, pT);
+    fused_powers<O>(blk + L.oSeg + k * L.ST, ip, pT);
     double dh[3][2 * O];
 #pragma unroll
-    for (int a = 0; a < 3; ++a)
+    for (int a = 0; a < 3; ++a) {
+        dh[a][0] = P[a];
+        dh[a][O] = P[3 + a];
 #pragma unroll
-        for (int q = 0; q < O; ++q) {
-            dh[a][q] = pT[q] * yk[a][q];
-            dh[a][O + q] = pT[q] * yk1[a][q];
+        for (int q = 1; q < O; ++q) {
+            dh[a][q] = pT[q] * dk[(q - 1) * 3 + a];
+            dh[a][O + q] = pT[q] * dk1[(q - 1) * 3 + a];
         }
+    }
     double best = -1.0;
     int best_s = 0;
 #pragma unroll
@@ -189,7 +197,7 @@ __device__ __noinline__ int fused_search_item(const FusedParams &p, const FusedC
             double v = 0.0;
 #pragma unroll
             for (int q = 0; q < 2 * O; ++q) v = fma(Tab<O>::HT(s, q), dh[a][q], v);
-            const double dd = v - fma(tau, yk1[a][0] - yk[a][0], yk[a][0]);
+            const double dd = v - fma(tau, P[3 + a] - P[a], P[a]);
             d2 = fma(dd, dd, d2);
         }
         if (d2 > best) {
@@ -200,119 +208,66 @@ __device__ __noinline__ int fused_search_item(const FusedParams &p, const FusedC
     return best_s;
 }
 
-// deviation probe of segment (t, k): h, L(t*), 1/len, field-major in smem
+// deviation probe of segment (t, k): h, L(t*), 1/len^2
 template <int O>
-__device__ __noinline__ void fused_probe_item(const FusedParams &p, const FusedCtx<O> &c, int t, int k) {
-    const int ns = c.ns;
-    double *blk = c.block(t);
-    const double *P = blk + c.L.oP;
+__device__ __noinline__ void fused_probe_item(const FusedParams &p, double *blk, int ns, int k) {
+    const FusedSmem<O> L(ns);
+    const double *P = blk + L.oP + 3 * k;
     double ip[2 * O], pT[O], h[2 * O];
-    time_powers<O>(blk[c.L.oT + k], ip, pT);
-    const int s = reinterpret_cast<const int *>(blk + c.L.oS)[k];
+    fused_powers<O>(blk + L.oSeg + k * L.ST, ip, pT);
+    const int s = reinterpret_cast<const int *>(blk + L.oS)[k];
     hermite_at<O>(p.ht, s, pT, h);
-    double *x = blk + c.L.oSegx + k;
+    double *x = blk + L.oSegx + k * L.XS;
 #pragma unroll
-    for (int q = 0; q < 2 * O; ++q) x[q * ns] = h[q];
+    for (int q = 0; q < 2 * O; ++q) x[q] = h[q];
     const double tau = (double)s * 0.0625;
     double l2 = 0.0;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        const double d = P[a * (ns + 1) + k + 1] - P[a * (ns + 1) + k];
-        x[(2 * O + a) * ns] = fma(tau, d, P[a * (ns + 1) + k]);
+        const double d = P[3 + a] - P[a];
+        x[2 * O + a] = fma(tau, d, P[a]);
         l2 = fma(d, d, l2);
     }
     const double len = sqrt(l2);
-    x[(2 * O + 3) * ns] = len > 1e-6 ? 1.0 / len : 0.0;
+    x[2 * O + 3] = len > 1e-6 ? 1.0 / l2 : 0.0;
 }
 
-// speculative Thomas: lane (t, q) solves with the q-th velocity weight of the reweighting sequence and measures
-// the max deviation at the recorded t* (ms.cpp:594-624).  Returns pivot status.
-template <int O>
-__device__ __noinline__ bool fused_spec_lane(const FusedParams &p, const FusedCtx<O> &c, int lane, int t, int q,
-                                             bool use_pw, double *max_dev_out) {
+// One Thomas chain of trajectory block `blk` with diagonal shift add00; state rows given by `state_at`.
+template <int O, bool EVAL, class StateAt>
+__device__ __forceinline__ bool fused_chain(const double *blk, int ns, double add00, const StateAt state_at,
+                                            double *max_dev_out) {
     using D = Dim<O>;
-    constexpr int NR = D::NR;
-    const int ns = c.ns, nr = c.nr;
-    double vw = p.sp.vw0;
-    for (int i = 0; i < q; ++i) vw = (vw < 1e-6) ? 0.01 : vw * 2.0;
-    const double add00 = vw > 0.0 ? 2.0 * vw : 0.0;
-    const double *blk = c.block(t);
-    const SmemRows base_at{blk + c.L.oBase, nr};
-    const SlotRows state_at{c.slot + lane, c.lstride, D::NSTATE * c.lstride};
-    const bool ok = thomas_forward<O>(nr, add00, base_at, state_at);
-    Boundary<O> bc;
-    boundary_of<O>(p.sp, c.b0 + t, bc);
-    const double *P = blk + c.L.oP;
-    double xn[NR], x[NR];
-#pragma unroll
-    for (int i = 0; i < NR; ++i) xn[i] = 0.0;
-    double yk[3][O], yk1[3][O];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        yk1[a][0] = P[a * (ns + 1) + ns];
-#pragma unroll
-        for (int r = 1; r < O; ++r) yk1[a][r] = bc.yN[a][r];
-    }
-    double max_dev = 0.0;
-    for (int j = nr - 1; j >= -1; --j) {
-        if (j >= 0) {
-            int bfs, sfs;
-            const double *bb = base_at(j, bfs);
-            double *st = state_at(j, sfs);
-            thomas_back_step<O>(bb, bfs, st, sfs, j + 1 < nr, xn, x);
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                yk[a][0] = P[a * (ns + 1) + j + 1];
-#pragma unroll
-                for (int r = 1; r < O; ++r) yk[a][r] = x[(r - 1) * 3 + a];
-            }
-#pragma unroll
-            for (int i = 0; i < NR; ++i) xn[i] = x[i];
-        } else {
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                yk[a][0] = P[a * (ns + 1)];
-#pragma unroll
-                for (int r = 1; r < O; ++r) yk[a][r] = bc.y0[a][r];
-            }
-        }
-        if (use_pw) {
-            const double ratio = deviation_ratio<O>(blk + c.L.oSegx + (j + 1), ns, yk, yk1);
-            if (ratio > max_dev) max_dev = ratio;
-        }
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-            for (int r = 0; r < O; ++r) yk1[a][r] = yk[a][r];
-    }
-    *max_dev_out = max_dev;
+    const FusedSmem<O> L(ns);
+    const FBaseRows<O> base_at{blk + L.oBase};
+    const bool ok = thomas_forward<O>(ns - 1, add00, base_at, state_at);
+    const FSegxRows<O> segx_at{blk + L.oSegx};
+    const FPos pos{blk + L.oP};
+    *max_dev_out = thomas_backward<O, EVAL>(ns - 1, state_at, segx_at, pos, blk + L.oBC, blk + L.oBC + D::NR);
     return ok;
 }
 
-// coefficients of (t, k, axis) from the selected lane's solution, 64-byte rows straight to HBM; returns finiteness
+// coefficients of (t, k, axis) from the final solution in the shared-memory state rows; returns finiteness
 template <int O>
-__device__ __noinline__ bool fused_coeff_item(const FusedParams &p, const FusedCtx<O> &c, int t, int k, int a, int lane) {
+__device__ __noinline__ bool fused_coeff_item(const double *blk, const double *state_lane, int ns, int k, int a,
+                                              double *dst_row) {
     using D = Dim<O>;
     constexpr int M = D::M;
-    const int ns = c.ns;
-    const double *blk = c.block(t);
-    const double *P = blk + c.L.oP;
-    Boundary<O> bc;
-    boundary_of<O>(p.sp, c.b0 + t, bc);
+    const FusedSmem<O> L(ns);
+    const double *P = blk + L.oP + 3 * k;
+    const double *bcs = blk + L.oBC;
     double yk[O], yk1[O];
-    yk[0] = P[a * (ns + 1) + k];
-    yk1[0] = P[a * (ns + 1) + k + 1];
+    yk[0] = P[a];
+    yk1[0] = P[3 + a];
 #pragma unroll
     for (int d = 1; d < O; ++d) {
-        yk[d] = (k == 0) ? bc.y0[a][d]
-                         : c.slot[((size_t)(k - 1) * D::NSTATE + D::ND + (d - 1) * 3 + a) * c.lstride + lane];
-        yk1[d] = (k == ns - 1) ? bc.yN[a][d]
-                               : c.slot[((size_t)k * D::NSTATE + D::ND + (d - 1) * 3 + a) * c.lstride + lane];
+        const int f = (d - 1) * 3 + a;
+        yk[d] = (k == 0) ? bcs[f] : state_lane[((k - 1) * D::NSTATE + D::SX + f) * FUSED_SMEM_LANES];
+        yk1[d] = (k == ns - 1) ? bcs[D::NR + f] : state_lane[(k * D::NSTATE + D::SX + f) * FUSED_SMEM_LANES];
     }
     double ip[2 * O], pT[O], co[M];
-    time_powers<O>(blk[c.L.oT + k], ip, pT);
+    fused_powers<O>(blk + L.oSeg + k * L.ST, ip, pT);
     hermite_coeffs<O>(yk, yk1, ip, pT, co);
-    double2 *dst = reinterpret_cast<double2 *>(p.coeff_out + ((c.g0 + (long long)t * ns + k) * 3 + a) * M);
+    double2 *dst = reinterpret_cast<double2 *>(dst_row);
     bool finite = true;
 #pragma unroll
     for (int q = 0; q < M / 2; ++q) {
@@ -323,104 +278,162 @@ __device__ __noinline__ bool fused_coeff_item(const FusedParams &p, const FusedC
 }
 
 template <int O>
-__global__ void __launch_bounds__(FUSED_THREADS, 3) k_fused_solve(const __grid_constant__ FusedParams p) {
+__global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_constant__ FusedParams p) {
     using D = Dim<O>;
+    constexpr int SL = FUSED_SMEM_LANES, GL = FUSED_SLOT_LANES;
     extern __shared__ double smem[];
     const int tid = threadIdx.x;
-    const int ns = p.ns, nr = ns - 1, tpc = p.tpc, nit = p.nit;
-    FusedCtx<O> c(ns);
-    c.smem = smem;
-    c.ns = ns;
-    c.nr = nr;
-    c.nit = nit;
-    c.tstride = p.traj_stride;
-    c.lstride = p.lane_stride;
-    c.slot = p.state_ws + (size_t)blockIdx.x * nr * D::NSTATE * p.lane_stride;
-    double *md = smem + (size_t)tpc * p.traj_stride;     // [tpc][nit] max deviation of every speculative solve
-    int *okf = reinterpret_cast<int *>(md + tpc * nit);  // [tpc][nit] pivot status
-    int *sel = okf + tpc * nit;                          // [tpc] selected iteration
-    int *ok1 = sel + tpc;                                // [tpc] pass-1 pivot status
+    const int ns = p.ns, nr = ns - 1, tpc = p.tpc, nit = p.nit, tstride = p.traj_stride;
+    const FusedSmem<O> L(ns);
+    double *state1 = smem + (size_t)tpc * tstride;            // [nr][NSTATE][SL]: pass-1 sweep, then the final x
+    double *md = state1 + (size_t)nr * D::NSTATE * SL;        // [tpc][nit] max deviation of every speculative solve
+    int *okf = reinterpret_cast<int *>(md + tpc * nit);       // [tpc][nit] pivot status
+    int *sel = okf + tpc * nit;                               // [tpc] selected iteration
+    int *ok1 = sel + tpc;                                     // [tpc] pass-1 pivot status
+    double *slot = p.state_ws + (size_t)blockIdx.x * nr * D::NSTATE * GL;
     const bool use_pw = p.sp.pw > 0.0;
+    int stamp = 0;
+#define MSNAP_STAMP()                                                                              \
+    do {                                                                                           \
+        if (p.phase_clocks && tid == 0 && tile == blockIdx.x && stamp < 16)                        \
+            p.phase_clocks[blockIdx.x * 16 + stamp++] = clock64();                                 \
+    } while (0)
 
     for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const long long b0 = tile * tpc;
         const int nt = (int)min((long long)tpc, p.B - b0);  // trajectories in this tile
         const long long g0 = b0 * ns;                       // first global segment of the tile
-        c.b0 = b0;
-        c.g0 = g0;
-
-        // ---- load: waypoints of the tile, contiguous in HBM -> axis-major rows in smem
+        MSNAP_STAMP();
+        // ---- load: waypoints of the tile (contiguous in HBM, [w][3] per trajectory) and boundary derivatives
         {
             const double *src = p.wp + 3 * (g0 + b0);
-            const int n = nt * (ns + 1) * 3;
+            const int per = 3 * (ns + 1), n = nt * per;
             for (int i = tid; i < n; i += FUSED_THREADS) {
-                const int t = i / (3 * (ns + 1)), r = i - t * 3 * (ns + 1);
-                const int k = r / 3, a = r - 3 * k;
-                smem[t * c.tstride + c.L.oP + a * (ns + 1) + k] = src[i];
+                const int t = i / per;
+                smem[t * tstride + L.oP + (i - t * per)] = src[i];
+            }
+            // fixed boundary derivatives (velocity, acceleration; higher ones zero -- ms.cpp:526-555), [r-1][axis]
+            for (int i = tid; i < nt * 2 * D::NR; i += FUSED_THREADS) {
+                const int t = i / (2 * D::NR), r = i - t * 2 * D::NR;
+                const int end = r / D::NR, d = (r % D::NR) / 3 + 1, a = r % 3;  // derivative order d
+                double v = 0.0;
+                if (d == 1) v = p.sp.vel ? p.sp.vel[6 * (b0 + t) + 3 * end + a] : p.sp.bc[3 * end + a];
+                if (d == 2) v = p.sp.acc ? p.sp.acc[6 * (b0 + t) + 3 * end + a] : p.sp.bc[6 + 3 * end + a];
+                smem[t * tstride + L.oBC + r] = v;
             }
         }
         __syncthreads();
-        // ---- times (plain IEEE mul/add: bit-identical to the reference's allocation, ms.cpp:63-72)
+        MSNAP_STAMP();
+        // ---- times (plain IEEE mul/add: bit-identical to the reference's allocation, ms.cpp:63-72) and powers
         for (int i = tid; i < nt * ns; i += FUSED_THREADS) {
             const int t = i / ns, k = i - t * ns;
-            double *blk = c.block(t);
+            double *blk = smem + t * tstride;
             double Tk;
             if (p.times_in) {
                 Tk = p.times_in[g0 + i];
             } else {
-                const double *P = blk + c.L.oP;
-                const double dx = __dsub_rn(P[k + 1], P[k]);
-                const double dy = __dsub_rn(P[(ns + 1) + k + 1], P[(ns + 1) + k]);
-                const double dz = __dsub_rn(P[2 * (ns + 1) + k + 1], P[2 * (ns + 1) + k]);
+                const double *P = blk + L.oP + 3 * k;
+                const double dx = __dsub_rn(P[3], P[0]), dy = __dsub_rn(P[4], P[1]), dz = __dsub_rn(P[5], P[2]);
                 const double len =
                     __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
                 Tk = (p.v_avg > 1e-6) ? __ddiv_rn(len, p.v_avg) : p.min_time;
                 if (Tk < p.min_time) Tk = p.min_time;
                 if (p.times_out) p.times_out[g0 + i] = Tk;
             }
-            blk[c.L.oT + k] = Tk;
+            double *seg = blk + L.oSeg + k * L.ST;
+            seg[0] = Tk;
+            seg[1] = 1.0 / Tk;
             if (!use_pw) {
-                reinterpret_cast<int *>(blk + c.L.oS)[k] = 0;
+                reinterpret_cast<int *>(blk + L.oS)[k] = 0;
                 if (p.best_s_out) p.best_s_out[g0 + i] = 0;
             }
         }
         __syncthreads();
+        MSNAP_STAMP();
 
         if (use_pw) {
             // ---- pass 1: snap cost only -> worst-deviation sample per segment
-            for (int i = tid; i < nt * nr; i += FUSED_THREADS) fused_row_item<O>(p, c, i / nr, i % nr + 1, false);
+            for (int i = tid; i < nt * nr; i += FUSED_THREADS)
+                fused_row_item<O>(p, smem + (i / nr) * tstride, ns, i % nr + 1, false);
             __syncthreads();
-            if (tid < nt) ok1[tid] = fused_pass1_lane<O>(c, tid) ? 1 : 0;
+            MSNAP_STAMP();
+            if (tid < nt) {
+                double unused;
+                const FStateRows<O, SL> st{state1 + tid};
+                ok1[tid] = fused_chain<O, false>(smem + tid * tstride, ns, 0.0, st, &unused) ? 1 : 0;
+            }
             __syncthreads();
+            MSNAP_STAMP();
             for (int i = tid; i < nt * ns; i += FUSED_THREADS) {
                 const int t = i / ns, k = i - t * ns;
-                const int s = fused_search_item<O>(p, c, t, k);
-                reinterpret_cast<int *>(c.block(t) + c.L.oS)[k] = s;
+                const int s = fused_search_item<O>(smem + t * tstride, state1 + t, ns, k);
+                reinterpret_cast<int *>(smem + t * tstride + L.oS)[k] = s;
                 if (p.best_s_out) p.best_s_out[g0 + i] = s;
             }
             __syncthreads();
-            for (int i = tid; i < nt * ns; i += FUSED_THREADS) fused_probe_item<O>(p, c, i / ns, i % ns);
+            MSNAP_STAMP();
+            for (int i = tid; i < nt * ns; i += FUSED_THREADS) fused_probe_item<O>(p, smem + (i / ns) * tstride, ns, i % ns);
         }
         // ---- rows of the final system
-        for (int i = tid; i < nt * nr; i += FUSED_THREADS) fused_row_item<O>(p, c, i / nr, i % nr + 1, use_pw);
+        for (int i = tid; i < nt * nr; i += FUSED_THREADS)
+            fused_row_item<O>(p, smem + (i / nr) * tstride, ns, i % nr + 1, use_pw);
+        if (tid < nt) sel[tid] = -1;
         __syncthreads();
-        // ---- speculative Thomas over (trajectory, reweighting iteration)
-        if (tid < nt * nit) {
-            double mdv;
-            const bool ok = fused_spec_lane<O>(p, c, tid, tid / nit, tid % nit, use_pw, &mdv);
-            md[tid] = mdv;
-            okf[tid] = ok ? 1 : 0;
-        }
-        __syncthreads();
-        // ---- select the iteration the sequential loop would have stopped at (ms.cpp:82)
-        if (tid < nt) {
-            int q = 0;
-            double vw = p.sp.vw0;
-            while (md[tid * nit + q] > 0.2 && q < nit - 1) {
-                vw = (vw < 1e-6) ? 0.01 : vw * 2.0;
-                ++q;
+        MSNAP_STAMP();
+        // ---- speculative Thomas over (trajectory, reweighting iteration), `chunk` iterations per pass.
+        // The final x of every trajectory ends up in the shared-memory state rows (state1); with a single solve per
+        // trajectory (nit == 1: no penalty, or a bare SolveQPClosedForm) the sweep runs there directly.
+        for (int c0 = 0; c0 < nit; c0 += p.chunk) {
+            const int cw = min(p.chunk, nit - c0);
+            if (tid < nt * cw) {
+                const int t = tid / cw, q = c0 + tid % cw;
+                if (sel[t] < 0) {
+                    double vw = p.sp.vw0;
+                    for (int i = 0; i < q; ++i) vw = (vw < 1e-6) ? 0.01 : vw * 2.0;
+                    const double add00 = vw > 0.0 ? 2.0 * vw : 0.0;
+                    const double *blk = smem + t * tstride;
+                    double mdv;
+                    bool ok;
+                    if (nit == 1) {
+                        const FStateRows<O, SL> st{state1 + t};
+                        ok = use_pw ? fused_chain<O, true>(blk, ns, add00, st, &mdv)
+                                    : fused_chain<O, false>(blk, ns, add00, st, &mdv);
+                    } else {
+                        const FStateRows<O, GL> st{slot + tid};
+                        ok = fused_chain<O, true>(blk, ns, add00, st, &mdv);
+                    }
+                    md[t * nit + q] = mdv;
+                    okf[t * nit + q] = ok ? 1 : 0;
+                }
             }
-            sel[tid] = q;
+            __syncthreads();
+            // the iteration the sequential loop would have stopped at (ms.cpp:82), if it lies in this chunk
+            if (tid < nt && sel[tid] < 0) {
+                for (int q = c0; q < c0 + cw; ++q)
+                    if (!(md[tid * nit + q] > 0.2) || q == nit - 1) {
+                        sel[tid] = q;
+                        break;
+                    }
+            }
+            __syncthreads();
+            if (nit > 1) {  // keep the selected solution: scratch slot -> shared-memory state rows
+                for (int i = tid; i < nt * nr * D::NR; i += FUSED_THREADS) {
+                    const int t = i / (nr * D::NR), r = i - t * nr * D::NR;
+                    const int q = sel[t];
+                    if (q >= c0 && q < c0 + cw) {
+                        const int j = r / D::NR, f = D::SX + r % D::NR;
+                        state1[(j * D::NSTATE + f) * SL + t] =
+                            slot[((size_t)j * D::NSTATE + f) * GL + t * cw + (q - c0)];
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        MSNAP_STAMP();
+        if (tid < nt) {
+            const int q = sel[tid];
+            double vw = p.sp.vw0;
+            for (int i = 0; i < q; ++i) vw = (vw < 1e-6) ? 0.01 : vw * 2.0;
             const double mdv = md[tid * nit + q];
             const long long b = b0 + tid;
             if (p.max_dev_out) p.max_dev_out[b] = mdv;
@@ -431,16 +444,19 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) k_fused_solve(const __grid_c
                 p.flags[b] = bad ? 1u : 0u;
             }
         }
-        __syncthreads();
-        // ---- coefficients: items (t, k, axis)
+        __syncthreads();  // flags[b] is OR-ed below
+        // ---- coefficients: items (t, k, axis), 64-byte rows straight to HBM
         for (int i = tid; i < nt * ns * 3; i += FUSED_THREADS) {
             const int t = i / (ns * 3), r = i - t * ns * 3;
             const int k = r / 3, a = r - 3 * k;
-            const bool finite = fused_coeff_item<O>(p, c, t, k, a, t * nit + sel[t]);
+            double *dst = p.coeff_out + ((g0 + (long long)t * ns + k) * 3 + a) * D::M;
+            const bool finite = fused_coeff_item<O>(smem + t * tstride, state1 + t, ns, k, a, dst);
             if (!finite && p.flags) atomicOr(p.flags + b0 + t, 1u);
         }
         __syncthreads();  // the tile's smem and state slot are reused by the next tile
+        MSNAP_STAMP();
     }
+#undef MSNAP_STAMP
 }
 
 }  // namespace msnap

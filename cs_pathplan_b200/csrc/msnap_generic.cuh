@@ -108,7 +108,7 @@ __global__ void k_rows(BatchIdx bi, SolveParams sp, const double *__restrict__ w
             l2 = fma(d, d, l2);
         }
         const double len = sqrt(l2);
-        x[2 * O + 3] = len > 1e-6 ? 1.0 / len : 0.0;
+        x[2 * O + 3] = len > 1e-6 ? 1.0 / l2 : 0.0;  // 1/len^2: deviations are compared squared
     }
     if (k == 0) return;
     Boundary<O> bc;
@@ -128,9 +128,25 @@ __global__ void k_rows(BatchIdx bi, SolveParams sp, const double *__restrict__ w
 // Thread per trajectory: block-tridiagonal Cholesky for the three axes, and -- when eval_dev -- the reweighting
 // loop of ms.cpp:76-90: solve, measure max deviation at the recorded t*, double vel_zero_weight while
 // max_dev > 0.2 and iter < max_iter.  The final x stays in state[]; per-trajectory results go to the out arrays.
+// Row accessors of the generic path: contiguous rows in the HBM workspace, field stride 1.
+template <int NF>
+struct GlobalRows {
+    double *p;
+    static constexpr int FS = 1;
+    __device__ __forceinline__ double *operator()(int j) const { return p + (size_t)j * NF; }
+};
+struct GlobalPos {  // waypoint positions of one trajectory, [w][3]
+    const double *p;
+    __device__ __forceinline__ void operator()(int w, double (&out)[3]) const {
+        out[0] = p[3 * w];
+        out[1] = p[3 * w + 1];
+        out[2] = p[3 * w + 2];
+    }
+};
+
 template <int O>
-__global__ void k_thomas(BatchIdx bi, SolveParams sp, const double *__restrict__ wp, const double *__restrict__ base,
-                         double *__restrict__ state, const double *__restrict__ segx, bool eval_dev, bool use_vw,
+__global__ void k_thomas(BatchIdx bi, SolveParams sp, const double *__restrict__ wp, double *base,
+                         double *state, double *segx, bool eval_dev, bool use_vw,
                          double *__restrict__ max_dev_out, int *__restrict__ iters_out,
                          double *__restrict__ vw_final_out, unsigned *__restrict__ flags) {
     using D = Dim<O>;
@@ -142,8 +158,18 @@ __global__ void k_thomas(BatchIdx bi, SolveParams sp, const double *__restrict__
     const int n_rows = ns - 1;
     Boundary<O> bc;
     boundary_of<O>(sp, b, bc);
-    auto base_at = [&](int j, int &fs) -> const double * { fs = 1; return base + (g0 + 1 + j) * D::NBASE; };
-    auto state_at = [&](int j, int &fs) -> double * { fs = 1; return state + (g0 + 1 + j) * D::NSTATE; };
+    double d0[NR], dN[NR];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int r = 1; r < O; ++r) {
+            d0[(r - 1) * 3 + a] = bc.y0[a][r];
+            dN[(r - 1) * 3 + a] = bc.yN[a][r];
+        }
+    const GlobalRows<D::NBASE> base_at{base + (g0 + 1) * D::NBASE};
+    const GlobalRows<D::NSTATE> state_at{state + (g0 + 1) * D::NSTATE};
+    const GlobalRows<D::NSEGX> segx_at{segx + g0 * D::NSEGX};
+    const GlobalPos pos{wp + 3 * (g0 + b)};
 
     double vw = use_vw ? sp.vw0 : 0.0;
     int iter = 0;
@@ -152,54 +178,8 @@ __global__ void k_thomas(BatchIdx bi, SolveParams sp, const double *__restrict__
     while (true) {
         const double add00 = vw > 0.0 ? 2.0 * vw : 0.0;
         ok = thomas_forward<O>(n_rows, add00, base_at, state_at) && ok;
-        // backward sweep; the deviation of segment j+1.. is probed as soon as both its endpoints are known
-        double xn[NR], x[NR];
-#pragma unroll
-        for (int i = 0; i < NR; ++i) xn[i] = 0.0;
-        double yk[3][O], yk1[3][O];
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-            for (int r = 0; r < O; ++r) yk1[a][r] = bc.yN[a][r];
-        {
-            const double *pN = wp + 3 * (g0 + b + ns);
-#pragma unroll
-            for (int a = 0; a < 3; ++a) yk1[a][0] = pN[a];
-        }
-        max_dev = 0.0;
-        for (int j = n_rows - 1; j >= -1; --j) {
-            // waypoint j+1 (row j) -> yk ; for j == -1 the start waypoint
-            const double *pk = wp + 3 * (g0 + b + j + 1);
-            if (j >= 0) {
-                int bfs, sfs;
-                const double *bb = base_at(j, bfs);
-                double *ss = state_at(j, sfs);
-                thomas_back_step<O>(bb, bfs, ss, sfs, j + 1 < n_rows, xn, x);
-#pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    yk[a][0] = pk[a];
-#pragma unroll
-                    for (int r = 1; r < O; ++r) yk[a][r] = x[(r - 1) * 3 + a];
-                }
-#pragma unroll
-                for (int i = 0; i < NR; ++i) xn[i] = x[i];
-            } else {
-#pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    yk[a][0] = pk[a];
-#pragma unroll
-                    for (int r = 1; r < O; ++r) yk[a][r] = bc.y0[a][r];
-                }
-            }
-            if (eval_dev) {
-                const double ratio = deviation_ratio<O>(segx + (g0 + j + 1) * D::NSEGX, 1, yk, yk1);
-                if (ratio > max_dev) max_dev = ratio;
-            }
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-                for (int r = 0; r < O; ++r) yk1[a][r] = yk[a][r];
-        }
+        max_dev = eval_dev ? thomas_backward<O, true>(n_rows, state_at, segx_at, pos, d0, dN)
+                           : thomas_backward<O, false>(n_rows, state_at, segx_at, pos, d0, dN);
         if (max_dev > 0.2 && iter < sp.max_iter) {
             vw = (vw < 1e-6) ? 0.01 : vw * 2.0;
             ++iter;
@@ -228,8 +208,8 @@ __device__ __forceinline__ void load_endpoints(const BatchIdx &bi, const SolvePa
         yk1[a][0] = p[3 + a];
 #pragma unroll
         for (int r = 1; r < O; ++r) {
-            yk[a][r] = (k == 0) ? bc.y0[a][r] : state[g * D::NSTATE + D::ND + (r - 1) * 3 + a];
-            yk1[a][r] = (k == ns - 1) ? bc.yN[a][r] : state[(g + 1) * D::NSTATE + D::ND + (r - 1) * 3 + a];
+            yk[a][r] = (k == 0) ? bc.y0[a][r] : state[g * D::NSTATE + D::SX + (r - 1) * 3 + a];
+            yk1[a][r] = (k == ns - 1) ? bc.yN[a][r] : state[(g + 1) * D::NSTATE + D::SX + (r - 1) * 3 + a];
         }
     }
 }

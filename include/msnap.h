@@ -153,6 +153,10 @@ int msnap_generate_one_host(msnap_handle h, const msnap_config *cfg, double samp
 int msnap_profile_begin(msnap_handle h);
 int msnap_profile_end(msnap_handle h, char *json_out, long long capacity);
 
+/* Developer instrumentation (not needed by an integrator): per-CTA clock64() stamps after each phase of the fused
+ * kernel's first tile.  enable != 0 arms a device buffer [4096][16]; out != NULL copies the last stamps to the host. */
+int msnap_debug_phase_clocks(msnap_handle h, int enable, long long *out);
+
 /* ---- micro-benchmarks used for the roofline denominators (bench.py) --------------------------------------- */
 /* Sustained DFMA rate of this GPU in TFLOP/s (2 flops per DFMA), measured with CUDA events. */
 int msnap_measure_fp64_peak(msnap_handle h, double *tflops_out);

@@ -1,0 +1,25 @@
+"""Developer tool: where does a fused-kernel CTA spend its time?  (clock64 stamps after every phase barrier)"""
+import sys; sys.path.insert(0, ".")
+import numpy as np, torch
+from cs_pathplan_b200 import TrajectoryGeneratorTool, workloads
+names_pw = ["load", "times", "rows1", "thomas1", "search", "probes+rows2", "selinit"]
+names_plain = ["load", "times", "rows", "selinit"]
+tool = TrajectoryGeneratorTool(0)
+for weights in ("shipped", "plain"):
+    for B, ns in ((4096, 16), (1 << 15, 8)):
+        cfg = workloads.synthetic_config(4, weights)
+        wp = workloads.random_walks(B, ns, 1234)
+        cap = tool.sample_bound(cfg, wp, ns=ns)
+        for _ in range(2): tool.generate_batch(cfg, wp, ns=ns, capacity=cap)
+        tool.debug_phase_clocks(True)
+        tool.generate_batch(cfg, wp, ns=ns, capacity=cap)
+        c = tool.debug_phase_clocks(True, read=True)
+        c = c[c[:, 0] > 0]
+        names = names_pw if weights == "shipped" else names_plain
+        d = np.diff(c[:, : len(names) + 1], axis=1) / 1.9e3   # us at ~1.9 GHz
+        print(f"{weights} B={B} ns={ns}: CTAs {len(c)}  span of first tiles {(c[:, len(names)].max() - c[:, 0].min()) / 1.9e3:.1f} us")
+        print("   spec lane0: forward %.1f us, backward %.1f us" % (((c[:,13]-c[:,12])/1.9e3).mean(), ((c[:,14]-c[:,13])/1.9e3).mean()))
+        rest = np.diff(c, axis=1)[:, len(names):] / 1.9e3
+        rest = np.where(rest > 0, rest, 0)
+        print("   " + "  ".join(f"{n} {m:.1f}" for n, m in zip(names, d.mean(0))), " | then", np.round(rest.mean(0)[:8], 1))
+tool.debug_phase_clocks(False)

@@ -194,7 +194,12 @@ def run_b200(args):
         return float(t.item())
 
     tool = TrajectoryGeneratorTool(local)
-    tool.set_stream(torch.cuda.current_stream().cuda_stream)
+    # All kernels run on ONE explicit stream and the timing events are recorded on that same stream.  (Passing torch's
+    # legacy default stream would hand the library a NULL stream, which it replaces by its own: events recorded on the
+    # default stream would then not see the kernels at all.)
+    stream = torch.cuda.Stream(device=dev)
+    tool.set_stream(stream.cuda_stream)
+    assert stream.cuda_stream != 0
     B, m = args.batch, 2 * ORDER
     n_seg = B * NS
 
@@ -227,10 +232,11 @@ def run_b200(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = tool.launch_count
-        e0.record()
+        e0.record(stream)
         for i in range(steps):
             step(cfg, sets[i % ROTATE])
-        e1.record()
+        e1.record(stream)
+        e1.synchronize()
         torch.cuda.synchronize()
         launches = tool.launch_count - l0
         ms = max_over_ranks(e0.elapsed_time(e1))

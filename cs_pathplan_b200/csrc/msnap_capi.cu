@@ -166,14 +166,16 @@ FusedPlan plan_fused(msnap_context *h, const BatchIdx &bi, const SolveParams &sp
     f.B = bi.B;
     f.policy = h->spec_chunk;
     if (nit > FUSED_THREADS) return f;
-    f.chunk = (h->spec_chunk > 0 && h->spec_chunk < nit) ? h->spec_chunk : nit;
+    f.chunk = nit;
     const FusedSmem<O> L(ns);
     const size_t blk = (size_t)L.size * sizeof(double);
     const size_t st1 = (size_t)(ns - 1) * D::NSTATE * FUSED_SMEM_LANES * sizeof(double);  // shared-memory state rows
     auto smem_for = [&](int tpc) { return tpc * blk + st1 + (size_t)tpc * nit * 12 + (size_t)tpc * 8 + 16; };
     const size_t hard = 220 * 1024;
-    int tmax = FUSED_THREADS / f.chunk;
-    if (tmax > FUSED_SMEM_LANES) tmax = FUSED_SMEM_LANES;
+    // lanes: tpc * (nit - 1) speculative lanes, then (warp-aligned) tpc lanes for the last iteration
+    int tmax = FUSED_SMEM_LANES;
+    while (tmax > 1 && ((tmax * (nit - 1) + 31) & ~31) + tmax > FUSED_THREADS) --tmax;
+    if (((tmax * (nit - 1) + 31) & ~31) + tmax > FUSED_THREADS) return f;
     if ((long long)tmax > bi.B) tmax = (int)bi.B;
     // Pick the tile size that needs the fewest waves of resident CTAs (the kernel is latency-bound per tile, so a
     // partial second wave costs a whole tile latency); among those, the largest tile (best lane utilisation).
@@ -252,7 +254,6 @@ int run_solve(msnap_context *h, const BatchIdx &bi, const SolveParams &sp, const
         fp.ns = bi.ns_uniform;
         fp.tpc = f.tpc;
         fp.nit = f.nit;
-        fp.chunk = f.chunk;
         fp.traj_stride = f.traj_stride;
         fp.n_tiles = f.n_tiles;
         fp.wp = io.wp;
@@ -337,13 +338,32 @@ struct SampleWs {
     int *seg_count, *append_end;
     double *seg_last;
     long long *seg_start, *traj_count, *partial;
+    // single-launch sampler (uniform batches)
+    unsigned long long *status = nullptr;
+    unsigned int *ticket = nullptr;
+    long long n_tiles = 0;
+    int tpt = 0;
 };
-size_t sample_ws_bytes(long long n_seg, long long B) {
+// tile size of the single-launch sampler: about one CTA's worth of segments
+int scan_tpt(int ns) { return ns >= SCAN_THREADS ? 1 : SCAN_THREADS / ns; }
+
+size_t sample_ws_bytes(long long n_seg, long long B, int ns_uniform, int policy) {
+    if (ns_uniform > 0 && policy != 1) {
+        const long long n_tiles = (B + scan_tpt(ns_uniform) - 1) / scan_tpt(ns_uniform);
+        return padded((size_t)(n_tiles + 1) * sizeof(unsigned long long)) + 256;
+    }
     return padded(n_seg * sizeof(int)) + padded(B * sizeof(int)) + padded((size_t)n_seg * 3 * sizeof(double)) +
            padded(n_seg * sizeof(long long)) + padded(B * sizeof(long long)) +
            padded((size_t)(B / SCAN_BLOCK + 2) * sizeof(long long));
 }
-void carve_sample_ws(Arena &a, long long n_seg, long long B, SampleWs &s) {
+void carve_sample_ws(Arena &a, long long n_seg, long long B, int ns_uniform, int policy, SampleWs &s) {
+    if (ns_uniform > 0 && policy != 1) {
+        s.tpt = scan_tpt(ns_uniform);
+        s.n_tiles = (B + s.tpt - 1) / s.tpt;
+        s.status = arena_take<unsigned long long>(a, s.n_tiles + 1);  // + the ticket counter right behind it
+        s.ticket = reinterpret_cast<unsigned int *>(s.status + s.n_tiles);
+        return;
+    }
     s.seg_count = arena_take<int>(a, n_seg);
     s.append_end = arena_take<int>(a, B);
     s.seg_last = arena_take<double>(a, (size_t)n_seg * 3);
@@ -356,6 +376,30 @@ template <int O>
 int run_sample(msnap_context *h, const BatchIdx &bi, const double *coeff, const double *T, double sd,
                long long capacity, long long *sample_offset, double *samples, double *stats, unsigned *flags,
                SampleWs &s) {
+    if (s.status) {  // uniform batch: count + scan + write in one launch
+        const int ns = bi.ns_uniform, seg_cap = s.tpt * ns;
+        const size_t smem = (size_t)((seg_cap + 1) & ~1) * sizeof(int) + (size_t)seg_cap * sizeof(long long) +
+                            (size_t)seg_cap * 3 * sizeof(double) + (size_t)(s.tpt + 1) * sizeof(long long) +
+                            (size_t)s.tpt * sizeof(int) + 16;
+        MS_CUDA(h, cudaMemsetAsync(s.status, 0, (size_t)(s.n_tiles + 1) * sizeof(unsigned long long), h->stream));
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(k_sample_scan<O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const long long resident = (long long)h->sm_count * 8;
+        const unsigned grid = (unsigned)(s.n_tiles < resident ? s.n_tiles : resident);
+        prof_before(h, "k_sample_scan");
+        k_sample_scan<O><<<grid, SCAN_THREADS, smem, h->stream>>>(bi.B, ns, s.tpt, s.n_tiles, coeff, T, sd, s.status,
+                                                                   s.ticket, capacity, sample_offset, samples, flags);
+        prof_after(h);
+        ++h->launches;
+        cudaError_t e = cudaPeekAtLastError();
+        if (e != cudaSuccess) {
+            h->last_error = std::string("k_sample_scan: ") + cudaGetErrorString(e);
+            cudaGetLastError();
+            return MSNAP_ERR_CUDA;
+        }
+        if (stats) MS_LAUNCH(h, k_stats, grid_for(bi.B * 32, 256), 256, bi.B, sample_offset, samples, capacity, stats);
+        return MSNAP_OK;
+    }
     const int blk = 128;
     const unsigned gs = grid_for(bi.n_seg, blk), gb = grid_for(bi.B, blk);
     MS_LAUNCH(h, (k_sample<O, false>), gs, blk, bi, coeff, T, sd, s.seg_count, s.seg_last, (const long long *)nullptr,
@@ -421,12 +465,13 @@ int generate_dev(msnap_context *h, const msnap_config *cfg, double sd, double v_
         sp.bc[9 + a] = cfg->end_acc[a];
     }
     const FusedPlan f = plan_fused<O>(h, bi, sp);
-    int rc = arena_reserve(h, h->ws, solve_ws_bytes<O>(n_seg, true, coeff_out == nullptr, f) + sample_ws_bytes(n_seg, B));
+    int rc = arena_reserve(h, h->ws, solve_ws_bytes<O>(n_seg, true, coeff_out == nullptr, f) +
+                                        sample_ws_bytes(n_seg, B, bi.ns_uniform, h->policy));
     if (rc) return rc;
     SolveWs w;
     carve_solve_ws<O>(h->ws, n_seg, true, coeff_out, f, w);
     SampleWs s;
-    carve_sample_ws(h->ws, n_seg, B, s);
+    carve_sample_ws(h->ws, n_seg, B, bi.ns_uniform, h->policy, s);
     SolveIO io;
     io.wp = wp;
     io.v_avg = v_avg;

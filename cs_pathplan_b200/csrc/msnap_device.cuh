@@ -22,8 +22,6 @@
 
 #include "msnap_tables.h"
 
-// The library is a single translation unit (msnap_capi.cu), so the constant-bank copy of the tables is defined here.
-__constant__ MsnapOrderTab c_tab[MSNAP_MAX_ORDER - MSNAP_MIN_ORDER + 1] = MSNAP_ORDER_TABLES;
 
 namespace msnap {
 
@@ -36,20 +34,23 @@ struct Dim {
     static constexpr int NR = 3 * B;            // right-hand sides, [r][axis]
     static constexpr int F_D = 0, F_U = ND, F_R = ND + NU;
     static constexpr int NBASE = ND + NU + NR;  // per-row constant data (order 4: 24 doubles)
-    static constexpr int NSTATE = NR + NU;      // per-row sweep state: z_j / x_j and W_j (order 4: 18 doubles)
-    static constexpr int SX = 0, SW = NR;       // field offsets of x (z) and W inside a state row
+    static constexpr int NSTATE = NR + ND;      // per-row sweep state: z_j (or x_j) and P_j (order 4: 15 doubles)
+    static constexpr int SX = 0, SP = NR;       // field offsets of z/x and of the packed inverse P inside a state row
     static constexpr int NSEGX = M + 4;         // per-segment deviation probe: h[M], L(t*)[3], 1/|P_{k+1}-P_k|
     static constexpr int NP = 2 * O - 1;        // inverse powers of T used by S: T^-1 .. T^-(2o-1)
 };
 
 __host__ __device__ constexpr int sym(int r, int q) { return r >= q ? r * (r + 1) / 2 + q : q * (q + 1) / 2 + r; }
 
-// Tables of one order: compile-time indices -> constant-bank operands.
+// Tables of one order as compile-time constants.  Every use has constant indices after unrolling, so an entry
+// becomes a literal operand of the DFMA/DMUL that consumes it -- there is no load for the optimiser to hoist out of
+// the persistent loops (a __constant__ array would be hoisted into ~100 live registers).  Lane-divergent lookups
+// (HT[s*]) go through a global-memory copy instead (hermite_at).
 template <int O>
 struct Tab {
-    __device__ static __forceinline__ double S(int i, int j) { return c_tab[O - MSNAP_MIN_ORDER].S[i][j]; }
-    __device__ static __forceinline__ double H(int k, int i) { return c_tab[O - MSNAP_MIN_ORDER].H[k][i]; }
-    __device__ static __forceinline__ double HT(int s, int i) { return c_tab[O - MSNAP_MIN_ORDER].HT[s][i]; }
+    __host__ __device__ static constexpr double S(int i, int j) { return MsnapConstTab<O>::S(i, j); }
+    __host__ __device__ static constexpr double H(int k, int i) { return MsnapConstTab<O>::H(k, i); }
+    __host__ __device__ static constexpr double HT(int s, int i) { return MsnapConstTab<O>::HT(s, i); }
 };
 
 // Boundary conditions of one trajectory: fixed derivatives 1..o-1 at the first and the last waypoint
@@ -270,13 +271,39 @@ __device__ __forceinline__ bool sym_inverse(const double (&a)[B * (B + 1) / 2], 
 // Block-tridiagonal solve of one trajectory for the three axes at once ("block Thomas"), SPD system
 //     U_{j-1}' x_{j-1} + D_j x_j + U_j x_{j+1} = r_j .
 // Forward sweep:   D'_j = D_j - U_{j-1}' W_{j-1},   r'_j = r_j - U_{j-1}' z_{j-1},
-//                  P_j = D'_j^-1,   z_j = P_j r'_j,   W_j = P_j U_j
-// Backward sweep:  x_j = z_j - W_j x_{j+1}
-//   base(j)  : read-only rows (D, U, r);  state(j): z_j [r][axis] (overwritten by x_j on the way back) and W_j.
+//                  P_j = D'_j^-1,   z_j = P_j r'_j,   W_j = P_j U_j  (W_j lives in registers for one row only)
+// Backward sweep:  x_j = z_j - P_j (U_j x_{j+1})
+//   base(j)  : read-only rows (D, U, r);  state(j): z_j [r][axis] and the packed symmetric P_j -- the sweep state
+//              is what the speculative lanes stream through L2, so it is kept to NR + ND doubles per row and the
+//              solution is written only where the caller asks for it (XOut).
 //   add00    : added to D_j[0][0] of every row (2 * vel_zero_weight: one vw from each adjacent segment).
 // Storage is abstracted by accessor types:  `const double* operator()(int j)` = field 0 of row j, and a
 // COMPILE-TIME field stride `FS` -- the sweep is issue-bound, so every address must be base + immediate.
 // ---------------------------------------------------------------------------------------------------------
+// How sweep state is read and written.  PlainMem: ordinary loads/stores (shared memory, or the generic path's HBM
+// workspace).  L2KeepMem: global-memory state that is written once and read back once a few microseconds later by
+// the same thread -- stores and loads carry an L2 evict_last policy so that the streaming inputs/outputs of the batch
+// do not push it out to DRAM in between.
+struct PlainMem {
+    __device__ static __forceinline__ double ld(const double *p) { return *p; }
+    __device__ static __forceinline__ void st(double *p, double v) { *p = v; }
+};
+struct L2KeepMem {
+    __device__ static __forceinline__ unsigned long long policy() {
+        unsigned long long pol;
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+        return pol;
+    }
+    __device__ static __forceinline__ double ld(const double *p) {
+        double v;
+        asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy()));
+        return v;
+    }
+    __device__ static __forceinline__ void st(double *p, double v) {
+        asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(policy()) : "memory");
+    }
+};
+
 template <int O, class BaseAt, class StateAt>
 __device__ __forceinline__ bool thomas_forward(int n_rows, double add00, const BaseAt base_at, const StateAt state_at) {
     using D = Dim<O>;
@@ -329,7 +356,7 @@ __device__ __forceinline__ bool thomas_forward(int n_rows, double add00, const B
                 z[p * 3 + x] = acc;
             }
 #pragma unroll
-        for (int i = 0; i < NR; ++i) s[(D::SX + i) * sfs] = z[i];
+        for (int i = 0; i < NR; ++i) StateAt::Mem::st(s + (D::SX + i) * sfs, z[i]);
         if (j + 1 < n_rows) {
             double U[NU];
 #pragma unroll
@@ -344,36 +371,56 @@ __device__ __forceinline__ bool thomas_forward(int n_rows, double add00, const B
                     W[p * B + q] = acc;
                 }
 #pragma unroll
-            for (int i = 0; i < NU; ++i) s[(D::SW + i) * sfs] = W[i];
+            for (int i = 0; i < ND; ++i) StateAt::Mem::st(s + (D::SP + i) * sfs, P[i]);
         }
     }
     return ok;
 }
 
-// One backward step: x_j = z_j - W_j x_{j+1} (xn; ignored when !has_next).  Writes x_j over z_j in the state row
-// and returns it in x.  FS = compile-time field stride of the state row `s`.
-template <int O, int FS>
-__device__ __forceinline__ void thomas_back_step(double *s, bool has_next, const double (&xn)[3 * (O - 1)],
-                                                 double (&x)[3 * (O - 1)]) {
+// Where the backward sweep leaves the solution.  NoOut: nowhere (a speculative lane only needs its max deviation).
+struct NoOut {
+    static constexpr bool ENABLED = false;
+    static constexpr int FS = 1;
+    using Mem = PlainMem;
+    __device__ __forceinline__ double *operator()(int) const { return nullptr; }
+};
+
+// One backward step: x_j = z_j - P_j (U_j x_{j+1})  (xn = x_{j+1}; no coupling when !has_next).
+//   s: state row j (z, P) with field stride SFS;  b: base row j (for U_j) with field stride BFS;
+//   xo: where x_j is stored ([r][axis], field stride XOut::FS) if XOut::ENABLED.
+template <int O, int SFS, class SMem, int BFS, class XOut>
+__device__ __forceinline__ void thomas_back_step(const double *s, const double *b, double *xo, bool has_next,
+                                                 const double (&xn)[3 * (O - 1)], double (&x)[3 * (O - 1)]) {
     using D = Dim<O>;
     constexpr int B = D::B, NR = D::NR;
 #pragma unroll
-    for (int i = 0; i < NR; ++i) x[i] = s[(D::SX + i) * FS];
+    for (int i = 0; i < NR; ++i) x[i] = SMem::ld(s + (D::SX + i) * SFS);
     if (has_next) {
-        double W[D::NU];
+        double P[D::ND], t[NR];
 #pragma unroll
-        for (int i = 0; i < D::NU; ++i) W[i] = s[(D::SW + i) * FS];
+        for (int i = 0; i < D::ND; ++i) P[i] = SMem::ld(s + (D::SP + i) * SFS);
+#pragma unroll
+        for (int p = 0; p < B; ++p)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                double acc = b[(D::F_U + p * B) * BFS] * xn[a];
+#pragma unroll
+                for (int q = 1; q < B; ++q) acc = fma(b[(D::F_U + p * B + q) * BFS], xn[q * 3 + a], acc);
+                t[p * 3 + a] = acc;
+            }
 #pragma unroll
         for (int p = 0; p < B; ++p)
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 double acc = x[p * 3 + a];
 #pragma unroll
-                for (int q = 0; q < B; ++q) acc = fma(-W[p * B + q], xn[q * 3 + a], acc);
+                for (int q = 0; q < B; ++q) acc = fma(-P[sym(p, q)], t[q * 3 + a], acc);
                 x[p * 3 + a] = acc;
             }
+    }
+    if (XOut::ENABLED) {
 #pragma unroll
-        for (int i = 0; i < NR; ++i) s[(D::SX + i) * FS] = x[i];
+        for (int i = 0; i < NR; ++i) XOut::Mem::st(xo + (D::SX + i) * XOut::FS, x[i]);
     }
 }
 
@@ -402,13 +449,15 @@ __device__ __forceinline__ double deviation_sq(const double *segx, const double 
 // Backward sweep of one trajectory with the deviation probe of every segment folded in (when EVAL).  The row loop
 // is unrolled by two with the roles of the two solution vectors swapped, so nothing is copied between iterations.
 //   pos(w, out[3])  : position of waypoint w = 0..ns
-//   state_at(j)     : state row of interior waypoint j+1
+//   base_at(j) / state_at(j) : base / state row of interior waypoint j+1
+//   xout(j)         : row that receives x_{j} (field SX..), or NoOut
 //   d0 / dN         : fixed derivative vectors of the first / last waypoint, [r-1][axis]
 //   segx_at(k)      : deviation probe of segment k
-// Returns max_k deviation ratio (0 when !EVAL); the solution is left in the state rows.
-template <int O, bool EVAL, class StateAt, class SegxAt, class PosAt>
-__device__ __forceinline__ double thomas_backward(int n_rows, const StateAt state_at, const SegxAt segx_at,
-                                                  const PosAt pos, const double *d0, const double *dN) {
+// Returns max_k deviation ratio (0 when !EVAL).
+template <int O, bool EVAL, class BaseAt, class StateAt, class XOut, class SegxAt, class PosAt>
+__device__ __forceinline__ double thomas_backward(int n_rows, const BaseAt base_at, const StateAt state_at,
+                                                  const XOut xout, const SegxAt segx_at, const PosAt pos,
+                                                  const double *d0, const double *dN) {
     using D = Dim<O>;
     constexpr int NR = D::NR;
     const int ns = n_rows + 1;
@@ -422,7 +471,8 @@ __device__ __forceinline__ double thomas_backward(int n_rows, const StateAt stat
     bool first = true;                            // xb still holds the fixed end derivatives (no W coupling)
     // step: compute x of waypoint j+1 into `xo` from `xi` (= x of waypoint j+2), probe segment j+1
     auto step = [&](double (&xo)[NR], double (&po)[3], const double (&xi)[NR], const double (&pi)[3]) {
-        thomas_back_step<O, StateAt::FS>(state_at(j), !first, xi, xo);
+        thomas_back_step<O, StateAt::FS, typename StateAt::Mem, BaseAt::FS, XOut>(state_at(j), base_at(j), xout(j), !first,
+                                                                                  xi, xo);
         pos(j + 1, po);
         if (EVAL) m2 = fmax(m2, deviation_sq<O, SegxAt::FS>(segx_at(j + 1), po, xo, pi, xi));
         first = false;

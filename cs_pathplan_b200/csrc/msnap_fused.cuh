@@ -41,7 +41,6 @@ struct FusedParams {
     int ns;
     int tpc;           // trajectories per tile (<= FUSED_SMEM_LANES)
     int nit;           // solves per trajectory in the speculative phase: max_iter + 1 if pw > 0 else 1
-    int chunk;         // reweighting iterations solved concurrently per speculative pass (tpc * chunk <= threads)
     int traj_stride;   // doubles per trajectory block in shared memory (odd: conflict-free broadcast)
     long long n_tiles;
     const double *wp;
@@ -98,10 +97,12 @@ struct FPos {
         out[2] = p[3 * w + 2];
     }
 };
-template <int O, int LANES>
+template <int O, int LANES, class MemT = PlainMem>
 struct FStateRows {
     double *p;  // this lane's column
     static constexpr int FS = LANES;
+    static constexpr bool ENABLED = true;  // usable as the solution sink of thomas_backward
+    using Mem = MemT;
     __device__ __forceinline__ double *operator()(int j) const { return p + (size_t)j * (Dim<O>::NSTATE * LANES); }
 };
 
@@ -130,13 +131,13 @@ __device__ __forceinline__ void fused_derivs(const double *bcs, const double *st
     }
 }
 
-// The table-heavy phase bodies are deliberately NOT inlined into the persistent tile loop: inside a loop the
-// compiler hoists the constant-table reads (c_tab) into registers, which costs ~100 registers and spills; as
-// straight-line functions the table entries fold into the DFMA/DMUL instructions as constant-bank operands.
+// All phase bodies are inlined: the order tables are constexpr (literal operands), so nothing is hoisted out of
+// the persistent loop, and there is no call ABI (callee-saved spills go to local memory, and with two ~110 KB CTAs
+// per SM there is almost no L1 left to catch them).
 
 // rows: item (t, j), j = 1..ns-1
 template <int O>
-__device__ __noinline__ void fused_row_item(const FusedParams &p, double *blk, int ns, int j, bool with_pw) {
+__device__ __forceinline__ void fused_row_item(const FusedParams &p, double *blk, int ns, int j, bool with_pw) {
     using D = Dim<O>;
     const FusedSmem<O> L(ns);
     const double *P = blk + L.oP + 3 * j;
@@ -167,7 +168,7 @@ __device__ __noinline__ void fused_row_item(const FusedParams &p, double *blk, i
 
 // search: item (t, k) -> index of the worst-deviation sample (first strict maximum, ms.cpp:435)
 template <int O>
-__device__ __noinline__ int fused_search_item(const double *blk, const double *state_lane, int ns, int k) {
+__device__ __forceinline__ int fused_search_item(const double *blk, const double *state_lane, int ns, int k) {
     const FusedSmem<O> L(ns);
     double dk[3 * (O - 1)], dk1[3 * (O - 1)];
     fused_derivs<O>(blk + L.oBC, state_lane, ns, k, dk);
@@ -210,7 +211,7 @@ __device__ __noinline__ int fused_search_item(const double *blk, const double *s
 
 // deviation probe of segment (t, k): h, L(t*), 1/len^2
 template <int O>
-__device__ __noinline__ void fused_probe_item(const FusedParams &p, double *blk, int ns, int k) {
+__device__ __forceinline__ void fused_probe_item(const FusedParams &p, double *blk, int ns, int k) {
     const FusedSmem<O> L(ns);
     const double *P = blk + L.oP + 3 * k;
     double ip[2 * O], pT[O], h[2 * O];
@@ -233,22 +234,43 @@ __device__ __noinline__ void fused_probe_item(const FusedParams &p, double *blk,
 }
 
 // One Thomas chain of trajectory block `blk` with diagonal shift add00; state rows given by `state_at`.
-template <int O, bool EVAL, class StateAt>
-__device__ __forceinline__ bool fused_chain(const double *blk, int ns, double add00, const StateAt state_at,
-                                            double *max_dev_out) {
+// NOT inlined on purpose: as separate functions the 15-row sweeps get the whole register budget to themselves
+// (inlined next to the other phases they spill into local memory inside the row loop); a call is made once per
+// chain, so its ABI cost is noise.
+//
+// One Thomas chain of trajectory block `blk` with diagonal shift add00: forward sweep into `state_at`, backward
+// sweep with the deviation probes (EVAL) leaving x in `xout` (or nowhere).
+template <int O, bool EVAL, class StateAt, class XOut>
+__device__ __noinline__ bool fused_chain(const double *blk, int ns, double add00, const StateAt state_at,
+                                         const XOut xout, double *max_dev_out, long long *clk = nullptr) {
     using D = Dim<O>;
     const FusedSmem<O> L(ns);
     const FBaseRows<O> base_at{blk + L.oBase};
+    if (clk) clk[0] = clock64();
     const bool ok = thomas_forward<O>(ns - 1, add00, base_at, state_at);
+    if (clk) clk[1] = clock64();
     const FSegxRows<O> segx_at{blk + L.oSegx};
     const FPos pos{blk + L.oP};
-    *max_dev_out = thomas_backward<O, EVAL>(ns - 1, state_at, segx_at, pos, blk + L.oBC, blk + L.oBC + D::NR);
+    *max_dev_out = thomas_backward<O, EVAL>(ns - 1, base_at, state_at, xout, segx_at, pos, blk + L.oBC,
+                                            blk + L.oBC + D::NR);
+    if (clk) clk[2] = clock64();
     return ok;
+}
+
+// Backward sweep only: replay a finished forward sweep (`state_at`) and leave the solution in `xout`.
+template <int O, class StateAt, class XOut>
+__device__ __noinline__ void fused_replay(const double *blk, int ns, const StateAt state_at, const XOut xout) {
+    using D = Dim<O>;
+    const FusedSmem<O> L(ns);
+    const FBaseRows<O> base_at{blk + L.oBase};
+    const FSegxRows<O> segx_at{blk + L.oSegx};
+    const FPos pos{blk + L.oP};
+    thomas_backward<O, false>(ns - 1, base_at, state_at, xout, segx_at, pos, blk + L.oBC, blk + L.oBC + D::NR);
 }
 
 // coefficients of (t, k, axis) from the final solution in the shared-memory state rows; returns finiteness
 template <int O>
-__device__ __noinline__ bool fused_coeff_item(const double *blk, const double *state_lane, int ns, int k, int a,
+__device__ __forceinline__ bool fused_coeff_item(const double *blk, const double *state_lane, int ns, int k, int a,
                                               double *dst_row) {
     using D = Dim<O>;
     constexpr int M = D::M;
@@ -295,7 +317,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_c
     int stamp = 0;
 #define MSNAP_STAMP()                                                                              \
     do {                                                                                           \
-        if (p.phase_clocks && tid == 0 && tile == blockIdx.x && stamp < 16)                        \
+        if (p.phase_clocks && tid == 0 && tile == blockIdx.x && stamp < 7)                        \
             p.phase_clocks[blockIdx.x * 16 + stamp++] = clock64();                                 \
     } while (0)
 
@@ -360,7 +382,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_c
             if (tid < nt) {
                 double unused;
                 const FStateRows<O, SL> st{state1 + tid};
-                ok1[tid] = fused_chain<O, false>(smem + tid * tstride, ns, 0.0, st, &unused) ? 1 : 0;
+                ok1[tid] = fused_chain<O, false>(smem + tid * tstride, ns, 0.0, st, st, &unused) ? 1 : 0;
             }
             __syncthreads();
             MSNAP_STAMP();
@@ -377,57 +399,62 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_c
         // ---- rows of the final system
         for (int i = tid; i < nt * nr; i += FUSED_THREADS)
             fused_row_item<O>(p, smem + (i / nr) * tstride, ns, i % nr + 1, use_pw);
-        if (tid < nt) sel[tid] = -1;
         __syncthreads();
         MSNAP_STAMP();
-        // ---- speculative Thomas over (trajectory, reweighting iteration), `chunk` iterations per pass.
-        // The final x of every trajectory ends up in the shared-memory state rows (state1); with a single solve per
-        // trajectory (nit == 1: no penalty, or a bare SolveQPClosedForm) the sweep runs there directly.
-        for (int c0 = 0; c0 < nit; c0 += p.chunk) {
-            const int cw = min(p.chunk, nit - c0);
-            if (tid < nt * cw) {
-                const int t = tid / cw, q = c0 + tid % cw;
-                if (sel[t] < 0) {
-                    double vw = p.sp.vw0;
-                    for (int i = 0; i < q; ++i) vw = (vw < 1e-6) ? 0.01 : vw * 2.0;
-                    const double add00 = vw > 0.0 ? 2.0 * vw : 0.0;
-                    const double *blk = smem + t * tstride;
-                    double mdv;
-                    bool ok;
-                    if (nit == 1) {
-                        const FStateRows<O, SL> st{state1 + t};
-                        ok = use_pw ? fused_chain<O, true>(blk, ns, add00, st, &mdv)
-                                    : fused_chain<O, false>(blk, ns, add00, st, &mdv);
-                    } else {
-                        const FStateRows<O, GL> st{slot + tid};
-                        ok = fused_chain<O, true>(blk, ns, add00, st, &mdv);
-                    }
-                    md[t * nit + q] = mdv;
-                    okf[t * nit + q] = ok ? 1 : 0;
+        // ---- speculative Thomas over (trajectory, reweighting iteration).
+        // Lanes [0, nt*(nit-1)) solve iterations 0..nit-2 with their sweep state in the CTA's global scratch slot and
+        // keep only the max deviation.  The LAST iteration -- the one most trajectories end on -- is solved by a
+        // separate warp-aligned group of nt lanes in the shared-memory state rows (idle since the search) and leaves
+        // its x there, ready for the coefficient phase.  With a single solve per trajectory (nit == 1: no penalty, or
+        // a bare SolveQPClosedForm) only that group runs.  Keeping the two groups in different warps avoids
+        // executing both code paths in every warp.
+        {
+            const int n_glob = nt * (nit - 1);
+            const int sl0 = (tpc * (nit - 1) + 31) & ~31;  // first lane of the shared-memory group
+            if (tid < n_glob) {
+                const int t = tid / (nit - 1), q = tid - t * (nit - 1);
+                double vw = p.sp.vw0;
+                for (int i = 0; i < q; ++i) vw = (vw < 1e-6) ? 0.01 : vw * 2.0;
+                const double add00 = vw > 0.0 ? 2.0 * vw : 0.0;
+                const FStateRows<O, GL, L2KeepMem> st{slot + tid};
+                long long *clk = nullptr;  // dev instrumentation: lanes 0, 64 and 128 of the CTA's first tile
+                if (p.phase_clocks && tile == blockIdx.x && (tid & 63) == 0)
+                    clk = p.phase_clocks + blockIdx.x * 16 + 7 + 3 * (tid >> 6);
+                double mdv;
+                const bool ok = fused_chain<O, true>(smem + t * tstride, ns, add00, st, NoOut{}, &mdv, clk);
+                md[t * nit + q] = mdv;
+                okf[t * nit + q] = ok ? 1 : 0;
+            } else if (tid >= sl0 && tid < sl0 + nt) {
+                const int t = tid - sl0, q = nit - 1;
+                double vw = p.sp.vw0;
+                for (int i = 0; i < q; ++i) vw = (vw < 1e-6) ? 0.01 : vw * 2.0;
+                const double add00 = vw > 0.0 ? 2.0 * vw : 0.0;
+                const FStateRows<O, SL> st{state1 + t};
+                double mdv;
+                const bool ok = use_pw ? fused_chain<O, true>(smem + t * tstride, ns, add00, st, st, &mdv)
+                                       : fused_chain<O, false>(smem + t * tstride, ns, add00, st, st, &mdv);
+                md[t * nit + q] = mdv;
+                okf[t * nit + q] = ok ? 1 : 0;
+            }
+            __syncthreads();
+            // the iteration the sequential loop would have stopped at (ms.cpp:82)
+            if (tid < nt) {
+                int q = 0;
+                while (md[tid * nit + q] > 0.2 && q < nit - 1) ++q;
+                sel[tid] = q;
+            }
+            __syncthreads();
+            // a trajectory that stopped early: the lane that solved that iteration replays its backward sweep, this
+            // time leaving the solution in the shared-memory state rows
+            if (tid < n_glob) {
+                const int t = tid / (nit - 1), q = tid - t * (nit - 1);
+                if (sel[t] == q) {
+                    const FStateRows<O, GL, L2KeepMem> st{slot + tid};
+                    const FStateRows<O, SL> xo{state1 + t};
+                    fused_replay<O>(smem + t * tstride, ns, st, xo);
                 }
             }
             __syncthreads();
-            // the iteration the sequential loop would have stopped at (ms.cpp:82), if it lies in this chunk
-            if (tid < nt && sel[tid] < 0) {
-                for (int q = c0; q < c0 + cw; ++q)
-                    if (!(md[tid * nit + q] > 0.2) || q == nit - 1) {
-                        sel[tid] = q;
-                        break;
-                    }
-            }
-            __syncthreads();
-            if (nit > 1) {  // keep the selected solution: scratch slot -> shared-memory state rows
-                for (int i = tid; i < nt * nr * D::NR; i += FUSED_THREADS) {
-                    const int t = i / (nr * D::NR), r = i - t * nr * D::NR;
-                    const int q = sel[t];
-                    if (q >= c0 && q < c0 + cw) {
-                        const int j = r / D::NR, f = D::SX + r % D::NR;
-                        state1[(j * D::NSTATE + f) * SL + t] =
-                            slot[((size_t)j * D::NSTATE + f) * GL + t * cw + (q - c0)];
-                    }
-                }
-                __syncthreads();
-            }
         }
         MSNAP_STAMP();
         if (tid < nt) {

@@ -133,6 +133,8 @@ template <int NF>
 struct GlobalRows {
     double *p;
     static constexpr int FS = 1;
+    static constexpr bool ENABLED = true;  // usable as the solution sink of thomas_backward
+    using Mem = PlainMem;
     __device__ __forceinline__ double *operator()(int j) const { return p + (size_t)j * NF; }
 };
 struct GlobalPos {  // waypoint positions of one trajectory, [w][3]
@@ -178,8 +180,9 @@ __global__ void k_thomas(BatchIdx bi, SolveParams sp, const double *__restrict__
     while (true) {
         const double add00 = vw > 0.0 ? 2.0 * vw : 0.0;
         ok = thomas_forward<O>(n_rows, add00, base_at, state_at) && ok;
-        max_dev = eval_dev ? thomas_backward<O, true>(n_rows, state_at, segx_at, pos, d0, dN)
-                           : thomas_backward<O, false>(n_rows, state_at, segx_at, pos, d0, dN);
+        // x_j overwrites z_j in the state row (z_j is read before it is replaced)
+        max_dev = eval_dev ? thomas_backward<O, true>(n_rows, base_at, state_at, state_at, segx_at, pos, d0, dN)
+                           : thomas_backward<O, false>(n_rows, base_at, state_at, state_at, segx_at, pos, d0, dN);
         if (max_dev > 0.2 && iter < sp.max_iter) {
             vw = (vw < 1e-6) ? 0.01 : vw * 2.0;
             ++iter;
@@ -451,6 +454,185 @@ __global__ void k_scan_apply(const long long *__restrict__ in, long long n, cons
     }
     if (i < n) offsets[i] = partial[blockIdx.x] + sh[threadIdx.x] - v;
     // offsets[n] is written by k_scan_partials (total_out == offsets + n)
+}
+
+// ------------------------------------------------------------------------------------------------ k_sample_scan
+// Single-launch sampler for uniform batches: count, exclusive scan across the whole batch and write, in one kernel.
+// A CTA takes tiles of `tpt` consecutive trajectories in ticket order (atomic counter), so that a tile's
+// predecessors have always started; the cross-tile exclusive prefix uses decoupled look-back on one 64-bit status
+// word per tile (2 flag bits + 62 value bits), read 128 predecessors at a time by the whole CTA.
+//   status[i]: 0 = nothing yet, (v << 2) | 1 = tile aggregate v, (v << 2) | 2 = inclusive prefix v
+// Candidate evaluation and acceptance are the same device code as k_sample, so the rows are bitwise identical.
+constexpr int SCAN_THREADS = 128;
+
+template <int O>
+__global__ void __launch_bounds__(SCAN_THREADS) k_sample_scan(
+    long long B, int ns, int tpt, long long n_tiles, const double *__restrict__ coeff, const double *__restrict__ T,
+    double sample_distance, unsigned long long *status, unsigned int *ticket, long long capacity,
+    long long *__restrict__ sample_offset, double *__restrict__ samples, unsigned *__restrict__ flags) {
+    extern __shared__ unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int seg_cap = tpt * ns;
+    int *cnt = reinterpret_cast<int *>(smem_raw);                                   // [seg_cap]
+    long long *seg_start = reinterpret_cast<long long *>(cnt + ((seg_cap + 1) & ~1));  // [seg_cap]
+    double *last = reinterpret_cast<double *>(seg_start + seg_cap);                // [seg_cap][3]
+    long long *traj_base = reinterpret_cast<long long *>(last + 3 * seg_cap);      // [tpt + 1]
+    int *append = reinterpret_cast<int *>(traj_base + tpt + 1);                     // [tpt]
+    __shared__ long long sh_tile;
+    __shared__ long long sh_base;
+    __shared__ long long sh_part[SCAN_THREADS / 32];
+
+    while (true) {
+        if (tid == 0) sh_tile = (long long)atomicAdd(ticket, 1u);
+        __syncthreads();
+        const long long tile = sh_tile;
+        if (tile >= n_tiles) break;
+        const long long b0 = tile * tpt;
+        const int nt = (int)min((long long)tpt, B - b0);
+        const long long g0 = b0 * ns;
+        const int nseg = nt * ns;
+        const double tmax_eps = 1e-12;
+        // ---- A: count accepted candidates per segment, remember the last accepted point
+        for (int i = tid; i < nseg; i += SCAN_THREADS) {
+            double c[3][2 * O];
+            load_coeff<O>(coeff, g0 + i, c);
+            const double Tk = T[g0 + i];
+            const double dt = sample_dt(Tk);
+            double prev[3], cur[3];
+            eval_xyz<O>(c, 0.0, prev);
+            int n = 0;
+            for (double t = dt; t <= Tk + tmax_eps; t += dt) {
+                eval_xyz<O>(c, fmin(t, Tk), cur);
+                if (dist3(cur, prev) >= sample_distance) {
+                    prev[0] = cur[0]; prev[1] = cur[1]; prev[2] = cur[2];
+                    ++n;
+                }
+            }
+            cnt[i] = n;
+            last[3 * i] = prev[0]; last[3 * i + 1] = prev[1]; last[3 * i + 2] = prev[2];
+        }
+        __syncthreads();
+        // ---- B: per trajectory: segment start rows, end-point rule (ms.cpp:157-160), row count
+        if (tid < nt) {
+            long long total = 1;  // the first point
+            int last_seg = -1;
+            for (int k = 0; k < ns; ++k) {
+                const int i = tid * ns + k;
+                seg_start[i] = total;
+                total += cnt[i];
+                if (cnt[i] > 0) last_seg = i;
+            }
+            double back[3], endp[3], c[3][2 * O];
+            if (last_seg >= 0) {
+                back[0] = last[3 * last_seg]; back[1] = last[3 * last_seg + 1]; back[2] = last[3 * last_seg + 2];
+            } else {
+                load_coeff<O>(coeff, g0 + (long long)tid * ns, c);
+                eval_xyz<O>(c, 0.0, back);
+            }
+            const long long gl = g0 + (long long)tid * ns + ns - 1;
+            load_coeff<O>(coeff, gl, c);
+            eval_xyz<O>(c, T[gl], endp);
+            const int app = dist3(back, endp) > 1e-6 ? 1 : 0;
+            append[tid] = app;
+            traj_base[tid + 1] = total + app;  // row count, scanned below
+        }
+        __syncthreads();
+        // ---- C: scan inside the tile, publish the aggregate, look back for the exclusive prefix of the tile
+        if (tid == 0) {
+            long long run = 0;
+            traj_base[0] = 0;
+            for (int t = 0; t < nt; ++t) {
+                const long long c = traj_base[t + 1];
+                traj_base[t] = run;
+                run += c;
+            }
+            traj_base[nt] = run;  // tile total
+            const unsigned long long word = ((unsigned long long)run << 2) | (tile == 0 ? 2ull : 1ull);
+            __threadfence();
+            atomicExch(status + tile, word);
+            if (tile == 0) sh_base = 0;
+        }
+        __syncthreads();
+        if (tile > 0) {
+            long long base = 0;
+            long long hi = tile;  // predecessors [lo, hi) are examined per step, newest first
+            bool done = false;
+            while (!done) {
+                const long long idx = hi - 1 - tid;
+                unsigned long long w = 2ull;  // lanes beyond the start of the array count as "prefix 0"
+                if (idx >= 0) {
+                    const volatile unsigned long long *sp = status + idx;
+                    do {
+                        w = *sp;  // volatile: re-read from L2 every time
+                    } while ((w & 3ull) == 0ull);
+                }
+                // nearest predecessor (smallest tid) that already has an inclusive prefix
+                const unsigned ball = __ballot_sync(0xffffffffu, (w & 3ull) == 2ull);
+                __shared__ int sh_first[SCAN_THREADS / 32];
+                if ((tid & 31) == 0) sh_first[tid >> 5] = ball ? (tid & ~31) + __ffs(ball) - 1 : -1;
+                __syncthreads();
+                int first = -1;
+                for (int wi = 0; wi < SCAN_THREADS / 32; ++wi)
+                    if (sh_first[wi] >= 0) { first = sh_first[wi]; break; }
+                // sum the values of lanes [0, first] (all lanes if no prefix in this window)
+                long long v = (first < 0 || tid <= first) ? (long long)(w >> 2) : 0;
+                if (idx < 0) v = 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                if ((tid & 31) == 0) sh_part[tid >> 5] = v;
+                __syncthreads();
+                for (int wi = 0; wi < SCAN_THREADS / 32; ++wi) base += sh_part[wi];
+                done = first >= 0 || hi - SCAN_THREADS <= 0;
+                hi -= SCAN_THREADS;
+                __syncthreads();
+            }
+            if (tid == 0) {
+                sh_base = base;
+                __threadfence();
+                atomicExch(status + tile, ((unsigned long long)(base + traj_base[nt]) << 2) | 2ull);
+            }
+            __syncthreads();
+        }
+        const long long tile_base = sh_base;
+        if (tid < nt) sample_offset[b0 + tid] = tile_base + traj_base[tid];
+        if (tile == n_tiles - 1 && tid == 0) sample_offset[B] = tile_base + traj_base[nt];
+        // ---- D: write (re-evaluates the accepted candidates; same arithmetic as the count pass)
+        for (int i = tid; i < nseg; i += SCAN_THREADS) {
+            const int t = i / ns, k = i - t * ns;
+            double c[3][2 * O];
+            load_coeff<O>(coeff, g0 + i, c);
+            const double Tk = T[g0 + i];
+            const double dt = sample_dt(Tk);
+            double prev[3], cur[3];
+            eval_xyz<O>(c, 0.0, prev);
+            const long long row0 = tile_base + traj_base[t];
+            long long row = row0 + seg_start[i];
+            bool dropped = false;
+            if (k == 0) {
+                if (row0 < capacity) {
+                    samples[3 * row0] = prev[0]; samples[3 * row0 + 1] = prev[1]; samples[3 * row0 + 2] = prev[2];
+                } else dropped = true;
+            }
+            for (double tt = dt; tt <= Tk + tmax_eps; tt += dt) {
+                eval_xyz<O>(c, fmin(tt, Tk), cur);
+                if (dist3(cur, prev) >= sample_distance) {
+                    prev[0] = cur[0]; prev[1] = cur[1]; prev[2] = cur[2];
+                    if (row < capacity) {
+                        samples[3 * row] = cur[0]; samples[3 * row + 1] = cur[1]; samples[3 * row + 2] = cur[2];
+                    } else dropped = true;
+                    ++row;
+                }
+            }
+            if (k == ns - 1 && append[t]) {
+                eval_xyz<O>(c, Tk, cur);
+                if (row < capacity) {
+                    samples[3 * row] = cur[0]; samples[3 * row + 1] = cur[1]; samples[3 * row + 2] = cur[2];
+                } else dropped = true;
+            }
+            if (dropped && flags) atomicOr(flags + b0 + t, 2u);
+        }
+        __syncthreads();  // smem is reused by the next tile
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ k_stats

@@ -18,7 +18,11 @@ for weights in ("shipped", "plain"):
         names = names_pw if weights == "shipped" else names_plain
         d = np.diff(c[:, : len(names) + 1], axis=1) / 1.9e3   # us at ~1.9 GHz
         print(f"{weights} B={B} ns={ns}: CTAs {len(c)}  span of first tiles {(c[:, len(names)].max() - c[:, 0].min()) / 1.9e3:.1f} us")
-        print("   spec lane0: forward %.1f us, backward %.1f us" % (((c[:,13]-c[:,12])/1.9e3).mean(), ((c[:,14]-c[:,13])/1.9e3).mean()))
+        if weights == "shipped":
+            for w in range(3):
+                f = (c[:, 8 + 3 * w] - c[:, 7 + 3 * w]) / 1.9e3; b = (c[:, 9 + 3 * w] - c[:, 8 + 3 * w]) / 1.9e3
+                s0 = (c[:, 7 + 3 * w] - c[:, 6]) / 1.9e3
+                print("   spec lane %3d: starts %.1f us after rows2 barrier, forward %.1f us, backward %.1f us" % (64 * w, s0.mean(), f.mean(), b.mean()))
         rest = np.diff(c, axis=1)[:, len(names):] / 1.9e3
         rest = np.where(rest > 0, rest, 0)
         print("   " + "  ".join(f"{n} {m:.1f}" for n, m in zip(names, d.mean(0))), " | then", np.round(rest.mean(0)[:8], 1))

@@ -13,7 +13,8 @@ ap.add_argument("--iters", type=int, default=6)
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 tool = TrajectoryGeneratorTool(0)
-tool.set_stream(torch.cuda.current_stream().cuda_stream)
+stream = torch.cuda.Stream(device=dev)
+tool.set_stream(stream.cuda_stream)
 cfg = workloads.synthetic_config(a.order, a.weights)
 B, ns, m = a.batch, a.ns, 2 * a.order
 wp_h = workloads.random_walks(B, ns, 1234)

@@ -21,6 +21,8 @@ static const MsnapOrderTab h_tab[MSNAP_MAX_ORDER - MSNAP_MIN_ORDER + 1] = MSNAP_
 
 using namespace msnap;
 
+static constexpr int T_TABLE_N = 4096;  // candidate-time table of the single-launch sampler (covers 64*SCAN_MASK_WORDS)
+
 // ------------------------------------------------------------------------------------------------------------
 // handle
 // ------------------------------------------------------------------------------------------------------------
@@ -43,6 +45,7 @@ struct msnap_context {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     MsnapOrderTab *d_tab = nullptr;  // global-memory copy of the tables (lane-divergent lookups)
+    double *d_ttab = nullptr;        // t_table[i] = the i-th candidate time of the sampler's `t += 0.1` accumulation
     Arena ws;                        // solver workspace
     Arena io;                        // device mirrors of host buffers (_host entry points)
     long long launches = 0;
@@ -345,20 +348,27 @@ struct SampleWs {
     int tpt = 0;
 };
 // tile size of the single-launch sampler: about one CTA's worth of segments
-int scan_tpt(int ns) { return ns >= SCAN_THREADS ? 1 : SCAN_THREADS / ns; }
+// Two segments per lane (snake-balanced) when the batch is large enough to keep every CTA slot busy with such
+// tiles; one segment per lane otherwise, so that a small batch still spreads over the whole GPU.
+int scan_tpt(int ns, long long B, int sm_count) {
+    const int one = ns >= SCAN_THREADS ? 1 : SCAN_THREADS / ns;
+    const int two = ns >= 2 * SCAN_THREADS ? 1 : 2 * SCAN_THREADS / ns;
+    const long long tiles_two = (B + two - 1) / two;
+    return tiles_two >= 2LL * 5 * sm_count ? two : one;
+}
 
 size_t sample_ws_bytes(long long n_seg, long long B, int ns_uniform, int policy) {
     if (ns_uniform > 0 && policy != 1) {
-        const long long n_tiles = (B + scan_tpt(ns_uniform) - 1) / scan_tpt(ns_uniform);
+        const long long n_tiles = B;  // upper bound on the tile count (tpt >= 1)
         return padded((size_t)(n_tiles + 1) * sizeof(unsigned long long)) + 256;
     }
     return padded(n_seg * sizeof(int)) + padded(B * sizeof(int)) + padded((size_t)n_seg * 3 * sizeof(double)) +
            padded(n_seg * sizeof(long long)) + padded(B * sizeof(long long)) +
            padded((size_t)(B / SCAN_BLOCK + 2) * sizeof(long long));
 }
-void carve_sample_ws(Arena &a, long long n_seg, long long B, int ns_uniform, int policy, SampleWs &s) {
+void carve_sample_ws(Arena &a, long long n_seg, long long B, int ns_uniform, int policy, int sm_count, SampleWs &s) {
     if (ns_uniform > 0 && policy != 1) {
-        s.tpt = scan_tpt(ns_uniform);
+        s.tpt = scan_tpt(ns_uniform, B, sm_count);
         s.n_tiles = (B + s.tpt - 1) / s.tpt;
         s.status = arena_take<unsigned long long>(a, s.n_tiles + 1);  // + the ticket counter right behind it
         s.ticket = reinterpret_cast<unsigned int *>(s.status + s.n_tiles);
@@ -378,8 +388,9 @@ int run_sample(msnap_context *h, const BatchIdx &bi, const double *coeff, const 
                SampleWs &s) {
     if (s.status) {  // uniform batch: count + scan + write in one launch
         const int ns = bi.ns_uniform, seg_cap = s.tpt * ns;
-        const size_t smem = (size_t)((seg_cap + 1) & ~1) * sizeof(int) + (size_t)seg_cap * sizeof(long long) +
-                            (size_t)seg_cap * 3 * sizeof(double) + (size_t)(s.tpt + 1) * sizeof(long long) +
+        const size_t smem = (size_t)seg_cap * SCAN_MASK_WORDS * sizeof(unsigned long long) +
+                            (size_t)seg_cap * sizeof(long long) + (size_t)seg_cap * 3 * sizeof(double) +
+                            (size_t)(s.tpt + 1) * sizeof(long long) + (size_t)3 * seg_cap * sizeof(int) +
                             (size_t)s.tpt * sizeof(int) + 16;
         MS_CUDA(h, cudaMemsetAsync(s.status, 0, (size_t)(s.n_tiles + 1) * sizeof(unsigned long long), h->stream));
         if (smem > 48 * 1024)
@@ -387,8 +398,10 @@ int run_sample(msnap_context *h, const BatchIdx &bi, const double *coeff, const 
         const long long resident = (long long)h->sm_count * 8;
         const unsigned grid = (unsigned)(s.n_tiles < resident ? s.n_tiles : resident);
         prof_before(h, "k_sample_scan");
-        k_sample_scan<O><<<grid, SCAN_THREADS, smem, h->stream>>>(bi.B, ns, s.tpt, s.n_tiles, coeff, T, sd, s.status,
-                                                                   s.ticket, capacity, sample_offset, samples, flags);
+        k_sample_scan<O><<<grid, SCAN_THREADS, smem, h->stream>>>(bi.B, ns, s.tpt, s.n_tiles, coeff, T, sd, h->d_ttab,
+                                                                   T_TABLE_N, s.status,
+                                                                   s.ticket, capacity, sample_offset, samples, flags,
+                                                                   h->phase_clocks);
         prof_after(h);
         ++h->launches;
         cudaError_t e = cudaPeekAtLastError();
@@ -471,7 +484,7 @@ int generate_dev(msnap_context *h, const msnap_config *cfg, double sd, double v_
     SolveWs w;
     carve_solve_ws<O>(h->ws, n_seg, true, coeff_out, f, w);
     SampleWs s;
-    carve_sample_ws(h->ws, n_seg, B, bi.ns_uniform, h->policy, s);
+    carve_sample_ws(h->ws, n_seg, B, bi.ns_uniform, h->policy, h->sm_count, s);
     SolveIO io;
     io.wp = wp;
     io.v_avg = v_avg;
@@ -574,11 +587,24 @@ int msnap_create(int device, msnap_handle *out) {
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
     DeviceGuard guard(device);
+    // candidate times exactly as ms.cpp:140 accumulates them: t_1 = 0.1, t_{i+1} = fl(t_i + 0.1)
+    std::vector<double> ttab(T_TABLE_N);
+    ttab[0] = 0.0;
+    {
+        volatile double t = 0.1;
+        for (int i = 1; i < T_TABLE_N; ++i) {
+            ttab[i] = t;
+            t = t + 0.1;
+        }
+    }
     if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&h->d_ttab, T_TABLE_N * sizeof(double)) != cudaSuccess ||
+        cudaMemcpy(h->d_ttab, ttab.data(), T_TABLE_N * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMalloc(&h->d_tab, sizeof(h_tab)) != cudaSuccess ||
         cudaMemcpy(h->d_tab, h_tab, sizeof(h_tab), cudaMemcpyHostToDevice) != cudaSuccess) {
         cudaGetLastError();
         if (h->d_tab) cudaFree(h->d_tab);
+        if (h->d_ttab) cudaFree(h->d_ttab);
         if (h->own_stream) cudaStreamDestroy(h->own_stream);
         delete h;
         return MSNAP_ERR_CUDA;
@@ -596,6 +622,7 @@ int msnap_destroy(msnap_handle h) {
     if (h->ws.base) cudaFree(h->ws.base);
     if (h->io.base) cudaFree(h->io.base);
     if (h->d_tab) cudaFree(h->d_tab);
+    if (h->d_ttab) cudaFree(h->d_ttab);
     if (h->phase_clocks) cudaFree(h->phase_clocks);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;

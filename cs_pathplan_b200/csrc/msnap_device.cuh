@@ -538,6 +538,27 @@ __device__ __forceinline__ double dist3(const double (&a)[3], const double (&b)[
     return sqrt(fma(dz, dz, fma(dy, dy, dx * dx)));
 }
 
+// Acceptance test of the sampler (ms.cpp:143-145): || cur - prev || >= sample_distance.  The square root is only
+// taken when the squared distance lies within 1e-14 (relative) of the squared threshold, where its rounding could
+// matter; everywhere else comparing squares gives the same answer as the reference's sqrt-then-compare.
+struct AcceptTest {
+    double sd, lo, hi;
+    __device__ __forceinline__ explicit AcceptTest(double sample_distance) : sd(sample_distance) {
+        const double s2 = sample_distance > 0.0 ? sample_distance * sample_distance : 0.0;
+        lo = s2 * (1.0 - 1e-14);
+        hi = s2 * (1.0 + 1e-14);
+    }
+    // kept out of line so that the compiler cannot speculate the square root into the common path
+    __device__ __noinline__ static bool tie_band(double d2, double sd_) { return sqrt(d2) >= sd_; }
+    __device__ __forceinline__ bool operator()(const double (&a)[3], const double (&b)[3]) const {
+        const double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+        const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+        if (d2 >= hi) return true;
+        if (d2 < lo) return false;
+        return tie_band(d2, sd);  // also reached for NaN (false) and for a non-positive threshold (true)
+    }
+};
+
 }  // namespace msnap
 
 #endif  // MSNAP_DEVICE_CUH

@@ -338,10 +338,11 @@ __global__ void k_sample(BatchIdx bi, const double *__restrict__ coeff, const do
     }
     int cnt = 0;
     const double tmax = Tk + 1e-12;
+    const AcceptTest accept(sample_distance);
     for (double t = dt; t <= tmax; t += dt) {
         const double tt = fmin(t, Tk);
         eval_xyz<O>(c, tt, cur);
-        if (dist3(cur, prev) >= sample_distance) {
+        if (accept(cur, prev)) {
             prev[0] = cur[0]; prev[1] = cur[1]; prev[2] = cur[2];
             if (WRITE) {
                 if (row < capacity) {
@@ -462,65 +463,121 @@ __global__ void k_scan_apply(const long long *__restrict__ in, long long n, cons
 // predecessors have always started; the cross-tile exclusive prefix uses decoupled look-back on one 64-bit status
 // word per tile (2 flag bits + 62 value bits), read 128 predecessors at a time by the whole CTA.
 //   status[i]: 0 = nothing yet, (v << 2) | 1 = tile aggregate v, (v << 2) | 2 = inclusive prefix v
-// Candidate evaluation and acceptance are the same device code as k_sample, so the rows are bitwise identical.
+//
+// Work balance.  A segment's candidate count is proportional to its duration, which varies several-fold inside a
+// tile.  The tile's segments are ranked by candidate count and dealt to the lanes in snake order (lane l takes ranks
+// l, 2N-1-l, 2N+l, ...), so every lane -- and every warp -- gets about the same number of candidates.
+//
+// The count pass records WHICH candidates were accepted (a bitmask, up to 64*SCAN_MASK_WORDS candidates per
+// segment), so the write pass evaluates only those, at the tabulated times t_i (the reference accumulates t += 0.1;
+// t_table[i] holds exactly that sequence).  Segments outside the mask/table range, or with dt = T/10 (T < 1 s), take
+// the plain re-evaluation loop.  Candidate evaluation and acceptance are the same device code as k_sample, so the rows
+// are bitwise identical.
 constexpr int SCAN_THREADS = 128;
+constexpr int SCAN_MASK_WORDS = 2;
 
 template <int O>
-__global__ void __launch_bounds__(SCAN_THREADS) k_sample_scan(
+__global__ void __launch_bounds__(SCAN_THREADS, 5) k_sample_scan(
     long long B, int ns, int tpt, long long n_tiles, const double *__restrict__ coeff, const double *__restrict__ T,
-    double sample_distance, unsigned long long *status, unsigned int *ticket, long long capacity,
-    long long *__restrict__ sample_offset, double *__restrict__ samples, unsigned *__restrict__ flags) {
+    double sample_distance, const double *__restrict__ t_table, int t_table_n, unsigned long long *status,
+    unsigned int *ticket, long long capacity, long long *__restrict__ sample_offset, double *__restrict__ samples,
+    unsigned *__restrict__ flags, long long *phase_clocks) {
     extern __shared__ unsigned char smem_raw[];
     const int tid = threadIdx.x;
     const int seg_cap = tpt * ns;
-    int *cnt = reinterpret_cast<int *>(smem_raw);                                   // [seg_cap]
-    long long *seg_start = reinterpret_cast<long long *>(cnt + ((seg_cap + 1) & ~1));  // [seg_cap]
-    double *last = reinterpret_cast<double *>(seg_start + seg_cap);                // [seg_cap][3]
-    long long *traj_base = reinterpret_cast<long long *>(last + 3 * seg_cap);      // [tpt + 1]
-    int *append = reinterpret_cast<int *>(traj_base + tpt + 1);                     // [tpt]
+    unsigned long long *mask = reinterpret_cast<unsigned long long *>(smem_raw);       // [seg_cap][SCAN_MASK_WORDS]
+    long long *seg_start = reinterpret_cast<long long *>(mask + (size_t)seg_cap * SCAN_MASK_WORDS);  // [seg_cap]
+    double *last = reinterpret_cast<double *>(seg_start + seg_cap);                     // [seg_cap][3]
+    long long *traj_base = reinterpret_cast<long long *>(last + 3 * seg_cap);           // [tpt + 1]
+    int *cnt = reinterpret_cast<int *>(traj_base + tpt + 1);                            // [seg_cap]
+    int *append = cnt + seg_cap;                                                        // [tpt]
+    int *key = append + tpt;                                                            // [seg_cap] candidate-count estimate
+    int *perm = key + seg_cap;                                                          // [seg_cap] segments, longest first
+    const AcceptTest accept(sample_distance);
     __shared__ long long sh_tile;
     __shared__ long long sh_base;
     __shared__ long long sh_part[SCAN_THREADS / 32];
+    __shared__ int sh_first[SCAN_THREADS / 32];
 
     while (true) {
         if (tid == 0) sh_tile = (long long)atomicAdd(ticket, 1u);
         __syncthreads();
         const long long tile = sh_tile;
         if (tile >= n_tiles) break;
+        int stamp = 0;
+#define SCAN_STAMP()                                                                   \
+    do {                                                                               \
+        if (phase_clocks && tid == 0 && tile < 4096 && stamp < 8)                      \
+            phase_clocks[tile * 16 + 8 + stamp++] = clock64();                         \
+    } while (0)
+        SCAN_STAMP();
         const long long b0 = tile * tpt;
         const int nt = (int)min((long long)tpt, B - b0);
         const long long g0 = b0 * ns;
         const int nseg = nt * ns;
-        const double tmax_eps = 1e-12;
-        // ---- A: count accepted candidates per segment, remember the last accepted point
+        // ---- rank the tile's segments by candidate count, longest first
         for (int i = tid; i < nseg; i += SCAN_THREADS) {
+            const double Tk = T[g0 + i];
+            key[i] = (int)fmin(Tk / sample_dt(Tk), 1.0e9);
+        }
+        __syncthreads();
+        for (int i = tid; i < nseg; i += SCAN_THREADS) {
+            const int ki = key[i];
+            int rank = 0;
+            for (int j = 0; j < nseg; ++j) {
+                const int kj = key[j];
+                rank += (kj > ki || (kj == ki && j < i)) ? 1 : 0;
+            }
+            perm[rank] = i;
+        }
+        __syncthreads();
+        SCAN_STAMP();
+        // ---- A: count accepted candidates per segment, remember which and the last accepted point
+        auto count_segment = [&](int i) {
             double c[3][2 * O];
             load_coeff<O>(coeff, g0 + i, c);
             const double Tk = T[g0 + i];
             const double dt = sample_dt(Tk);
             double prev[3], cur[3];
             eval_xyz<O>(c, 0.0, prev);
-            int n = 0;
-            for (double t = dt; t <= Tk + tmax_eps; t += dt) {
+            int n = 0, idx = 0;
+            unsigned long long m[SCAN_MASK_WORDS];
+#pragma unroll
+            for (int w = 0; w < SCAN_MASK_WORDS; ++w) m[w] = 0ull;
+            for (double t = dt; t <= Tk + 1e-12; t += dt, ++idx) {
                 eval_xyz<O>(c, fmin(t, Tk), cur);
-                if (dist3(cur, prev) >= sample_distance) {
+                if (accept(cur, prev)) {
                     prev[0] = cur[0]; prev[1] = cur[1]; prev[2] = cur[2];
                     ++n;
+#pragma unroll
+                    for (int w = 0; w < SCAN_MASK_WORDS; ++w)
+                        if ((idx >> 6) == w) m[w] |= 1ull << (idx & 63);
                 }
             }
-            cnt[i] = n;
+            // the mask is usable by the write pass iff every candidate has a bit and a tabulated time
+            const bool usable = dt == 0.1 && idx <= 64 * SCAN_MASK_WORDS && idx < t_table_n;
+            cnt[i] = usable ? n : -n - 1;  // negative: "re-evaluate in the write pass"
+#pragma unroll
+            for (int w = 0; w < SCAN_MASK_WORDS; ++w) mask[i * SCAN_MASK_WORDS + w] = m[w];
             last[3 * i] = prev[0]; last[3 * i + 1] = prev[1]; last[3 * i + 2] = prev[2];
+        };
+        for (int r0 = 0; r0 < nseg; r0 += 2 * SCAN_THREADS) {  // snake order over the ranking
+            const int ra = r0 + tid, rb = r0 + 2 * SCAN_THREADS - 1 - tid;
+            if (ra < nseg) count_segment(perm[ra]);
+            if (rb < nseg) count_segment(perm[rb]);
         }
         __syncthreads();
+        SCAN_STAMP();
         // ---- B: per trajectory: segment start rows, end-point rule (ms.cpp:157-160), row count
         if (tid < nt) {
             long long total = 1;  // the first point
             int last_seg = -1;
             for (int k = 0; k < ns; ++k) {
                 const int i = tid * ns + k;
+                const int n = cnt[i] >= 0 ? cnt[i] : -cnt[i] - 1;
                 seg_start[i] = total;
-                total += cnt[i];
-                if (cnt[i] > 0) last_seg = i;
+                total += n;
+                if (n > 0) last_seg = i;
             }
             double back[3], endp[3], c[3][2 * O];
             if (last_seg >= 0) {
@@ -537,6 +594,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_sample_scan(
             traj_base[tid + 1] = total + app;  // row count, scanned below
         }
         __syncthreads();
+        SCAN_STAMP();
         // ---- C: scan inside the tile, publish the aggregate, look back for the exclusive prefix of the tile
         if (tid == 0) {
             long long run = 0;
@@ -555,7 +613,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_sample_scan(
         __syncthreads();
         if (tile > 0) {
             long long base = 0;
-            long long hi = tile;  // predecessors [lo, hi) are examined per step, newest first
+            long long hi = tile;  // predecessors [hi - 128, hi) are examined per step, newest first
             bool done = false;
             while (!done) {
                 const long long idx = hi - 1 - tid;
@@ -568,7 +626,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_sample_scan(
                 }
                 // nearest predecessor (smallest tid) that already has an inclusive prefix
                 const unsigned ball = __ballot_sync(0xffffffffu, (w & 3ull) == 2ull);
-                __shared__ int sh_first[SCAN_THREADS / 32];
                 if ((tid & 31) == 0) sh_first[tid >> 5] = ball ? (tid & ~31) + __ffs(ball) - 1 : -1;
                 __syncthreads();
                 int first = -1;
@@ -582,7 +639,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_sample_scan(
                 if ((tid & 31) == 0) sh_part[tid >> 5] = v;
                 __syncthreads();
                 for (int wi = 0; wi < SCAN_THREADS / 32; ++wi) base += sh_part[wi];
-                done = first >= 0 || hi - SCAN_THREADS <= 0;
+                done = first >= 0;
                 hi -= SCAN_THREADS;
                 __syncthreads();
             }
@@ -593,46 +650,67 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_sample_scan(
             }
             __syncthreads();
         }
+        SCAN_STAMP();
         const long long tile_base = sh_base;
         if (tid < nt) sample_offset[b0 + tid] = tile_base + traj_base[tid];
         if (tile == n_tiles - 1 && tid == 0) sample_offset[B] = tile_base + traj_base[nt];
-        // ---- D: write (re-evaluates the accepted candidates; same arithmetic as the count pass)
-        for (int i = tid; i < nseg; i += SCAN_THREADS) {
+        // ---- D: write the accepted candidates (same arithmetic as the count pass)
+        auto write_segment = [&](int i) {
             const int t = i / ns, k = i - t * ns;
             double c[3][2 * O];
             load_coeff<O>(coeff, g0 + i, c);
             const double Tk = T[g0 + i];
-            const double dt = sample_dt(Tk);
-            double prev[3], cur[3];
-            eval_xyz<O>(c, 0.0, prev);
+            double cur[3];
             const long long row0 = tile_base + traj_base[t];
             long long row = row0 + seg_start[i];
             bool dropped = false;
-            if (k == 0) {
-                if (row0 < capacity) {
-                    samples[3 * row0] = prev[0]; samples[3 * row0 + 1] = prev[1]; samples[3 * row0 + 2] = prev[2];
+            auto put = [&](long long r, const double (&v)[3]) {
+                if (r < capacity) {
+                    samples[3 * r] = v[0]; samples[3 * r + 1] = v[1]; samples[3 * r + 2] = v[2];
                 } else dropped = true;
+            };
+            if (k == 0) {  // the trajectory's first point (ms.cpp:132-137)
+                eval_xyz<O>(c, 0.0, cur);
+                put(row0, cur);
             }
-            for (double tt = dt; tt <= Tk + tmax_eps; tt += dt) {
-                eval_xyz<O>(c, fmin(tt, Tk), cur);
-                if (dist3(cur, prev) >= sample_distance) {
-                    prev[0] = cur[0]; prev[1] = cur[1]; prev[2] = cur[2];
-                    if (row < capacity) {
-                        samples[3 * row] = cur[0]; samples[3 * row + 1] = cur[1]; samples[3 * row + 2] = cur[2];
-                    } else dropped = true;
-                    ++row;
+            if (cnt[i] >= 0) {
+#pragma unroll
+                for (int w = 0; w < SCAN_MASK_WORDS; ++w) {
+                    unsigned long long m = mask[i * SCAN_MASK_WORDS + w];
+                    while (m) {
+                        const int bit = __ffsll((long long)m) - 1;
+                        m &= m - 1;
+                        eval_xyz<O>(c, fmin(__ldg(t_table + w * 64 + bit + 1), Tk), cur);
+                        put(row++, cur);
+                    }
+                }
+            } else {
+                const double dt = sample_dt(Tk);
+                double prev[3];
+                eval_xyz<O>(c, 0.0, prev);
+                for (double tt = dt; tt <= Tk + 1e-12; tt += dt) {
+                    eval_xyz<O>(c, fmin(tt, Tk), cur);
+                    if (accept(cur, prev)) {
+                        prev[0] = cur[0]; prev[1] = cur[1]; prev[2] = cur[2];
+                        put(row++, cur);
+                    }
                 }
             }
-            if (k == ns - 1 && append[t]) {
+            if (k == ns - 1 && append[t]) {  // the end point (ms.cpp:157-160)
                 eval_xyz<O>(c, Tk, cur);
-                if (row < capacity) {
-                    samples[3 * row] = cur[0]; samples[3 * row + 1] = cur[1]; samples[3 * row + 2] = cur[2];
-                } else dropped = true;
+                put(row, cur);
             }
             if (dropped && flags) atomicOr(flags + b0 + t, 2u);
+        };
+        for (int r0 = 0; r0 < nseg; r0 += 2 * SCAN_THREADS) {
+            const int ra = r0 + tid, rb = r0 + 2 * SCAN_THREADS - 1 - tid;
+            if (ra < nseg) write_segment(perm[ra]);
+            if (rb < nseg) write_segment(perm[rb]);
         }
         __syncthreads();  // smem is reused by the next tile
+        SCAN_STAMP();
     }
+#undef SCAN_STAMP
 }
 
 // ------------------------------------------------------------------------------------------------ k_stats

@@ -23,7 +23,15 @@ for weights in ("shipped", "plain"):
                 f = (c[:, 8 + 3 * w] - c[:, 7 + 3 * w]) / 1.9e3; b = (c[:, 9 + 3 * w] - c[:, 8 + 3 * w]) / 1.9e3
                 s0 = (c[:, 7 + 3 * w] - c[:, 6]) / 1.9e3
                 print("   spec lane %3d: starts %.1f us after rows2 barrier, forward %.1f us, backward %.1f us" % (64 * w, s0.mean(), f.mean(), b.mean()))
+        sc = tool.debug_phase_clocks(True, read=True) if False else c
+        full = sc
         rest = np.diff(c, axis=1)[:, len(names):] / 1.9e3
         rest = np.where(rest > 0, rest, 0)
         print("   " + "  ".join(f"{n} {m:.1f}" for n, m in zip(names, d.mean(0))), " | then", np.round(rest.mean(0)[:8], 1))
+# sampler kernel phases (stamps in columns 8..13 of rows indexed by tile)
+cfg = workloads.synthetic_config(4, "plain"); wp = workloads.random_walks(4096, 16, 1234); cap = tool.sample_bound(cfg, wp, ns=16)
+tool.debug_phase_clocks(True); tool.generate_batch(cfg, wp, ns=16, capacity=cap); c = tool.debug_phase_clocks(True, read=True)
+c = c[:512, 8:14]; d = np.diff(c, axis=1) / 1.9e3
+print("sampler tiles:", len(c), " phases [sort, A count, B traj, C lookback, D write] us mean:", np.round(d.mean(0), 1), " max:", np.round(d.max(0), 1),
+      " span:", round((c[:, -1].max() - c[:, 0].min()) / 1.9e3, 1))
 tool.debug_phase_clocks(False)

@@ -21,7 +21,7 @@ static const MsnapOrderTab h_tab[MSNAP_MAX_ORDER - MSNAP_MIN_ORDER + 1] = MSNAP_
 
 using namespace msnap;
 
-static constexpr int T_TABLE_N = 4096;  // candidate-time table of the single-launch sampler (covers 64*SCAN_MASK_WORDS)
+static constexpr int T_TABLE_N = 256;  // candidate-time table of the sampler's write pass (>= SAMPLE_TTAB_N)
 
 // ------------------------------------------------------------------------------------------------------------
 // handle
@@ -51,6 +51,7 @@ struct msnap_context {
     long long launches = 0;
     int policy = 0;
     int spec_chunk = 0;               // reweighting iterations per speculative pass (0 = all at once)
+    bool scan_coef_smem = false;      // sampler: stage the tile's coefficients in shared memory (MSNAP_SCAN_COEF_SMEM=1)
     std::vector<FusedPlan> plans;     // cached launch plans
     // optional per-kernel timing (msnap_profile_begin/end): one event pair per launch on the launching stream
     long long *phase_clocks = nullptr;  // dev instrumentation (msnap_debug_phase_clocks)
@@ -339,43 +340,46 @@ void carve_solve_ws(Arena &a, long long n_seg, bool need_T, double *coeff_out, c
 
 struct SampleWs {
     int *seg_count, *append_end;
+    unsigned long long *seg_mask;
     double *seg_last;
     long long *seg_start, *traj_count, *partial;
     // single-launch sampler (uniform batches)
     unsigned long long *status = nullptr;
     unsigned int *ticket = nullptr;
+    int *sm_ctr = nullptr;  // [512] arrival order of the CTAs on each SM
     long long n_tiles = 0;
     int tpt = 0;
 };
-// tile size of the single-launch sampler: about one CTA's worth of segments
-// Two segments per lane (snake-balanced) when the batch is large enough to keep every CTA slot busy with such
-// tiles; one segment per lane otherwise, so that a small batch still spreads over the whole GPU.
+// Tile size of the single-launch sampler.  One segment per thread while that still gives every CTA slot of the GPU a
+// tile; two segments per thread for big batches (half as many tiles to look back over).
 int scan_tpt(int ns, long long B, int sm_count) {
     const int one = ns >= SCAN_THREADS ? 1 : SCAN_THREADS / ns;
     const int two = ns >= 2 * SCAN_THREADS ? 1 : 2 * SCAN_THREADS / ns;
     const long long tiles_two = (B + two - 1) / two;
-    return tiles_two >= 2LL * 5 * sm_count ? two : one;
+    return tiles_two >= 2LL * 4 * sm_count ? two : one;
 }
 
 size_t sample_ws_bytes(long long n_seg, long long B, int ns_uniform, int policy) {
     if (ns_uniform > 0 && policy != 1) {
         const long long n_tiles = B;  // upper bound on the tile count (tpt >= 1)
-        return padded((size_t)(n_tiles + 1) * sizeof(unsigned long long)) + 256;
+        return padded((size_t)(n_tiles + 1 + 256) * sizeof(unsigned long long)) + 256;  // + ticket + per-SM counters
     }
-    return padded(n_seg * sizeof(int)) + padded(B * sizeof(int)) + padded((size_t)n_seg * 3 * sizeof(double)) +
-           padded(n_seg * sizeof(long long)) + padded(B * sizeof(long long)) +
-           padded((size_t)(B / SCAN_BLOCK + 2) * sizeof(long long));
+    return padded(n_seg * sizeof(int)) + padded(B * sizeof(int)) + padded((size_t)n_seg * 2 * sizeof(unsigned long long)) +
+           padded((size_t)n_seg * 3 * sizeof(double)) + padded(n_seg * sizeof(long long)) +
+           padded(B * sizeof(long long)) + padded((size_t)(B / SCAN_BLOCK + 2) * sizeof(long long));
 }
 void carve_sample_ws(Arena &a, long long n_seg, long long B, int ns_uniform, int policy, int sm_count, SampleWs &s) {
     if (ns_uniform > 0 && policy != 1) {
         s.tpt = scan_tpt(ns_uniform, B, sm_count);
         s.n_tiles = (B + s.tpt - 1) / s.tpt;
-        s.status = arena_take<unsigned long long>(a, s.n_tiles + 1);  // + the ticket counter right behind it
+        s.status = arena_take<unsigned long long>(a, s.n_tiles + 1 + 256);  // + ticket + per-SM arrival counters
         s.ticket = reinterpret_cast<unsigned int *>(s.status + s.n_tiles);
+        s.sm_ctr = reinterpret_cast<int *>(s.status + s.n_tiles + 1);
         return;
     }
     s.seg_count = arena_take<int>(a, n_seg);
     s.append_end = arena_take<int>(a, B);
+    s.seg_mask = arena_take<unsigned long long>(a, (size_t)n_seg * 2);
     s.seg_last = arena_take<double>(a, (size_t)n_seg * 3);
     s.seg_start = arena_take<long long>(a, n_seg);
     s.traj_count = arena_take<long long>(a, B);
@@ -387,21 +391,19 @@ int run_sample(msnap_context *h, const BatchIdx &bi, const double *coeff, const 
                long long capacity, long long *sample_offset, double *samples, double *stats, unsigned *flags,
                SampleWs &s) {
     if (s.status) {  // uniform batch: count + scan + write in one launch
-        const int ns = bi.ns_uniform, seg_cap = s.tpt * ns;
-        const size_t smem = (size_t)seg_cap * SCAN_MASK_WORDS * sizeof(unsigned long long) +
-                            (size_t)seg_cap * sizeof(long long) + (size_t)seg_cap * 3 * sizeof(double) +
-                            (size_t)(s.tpt + 1) * sizeof(long long) + (size_t)3 * seg_cap * sizeof(int) +
-                            (size_t)s.tpt * sizeof(int) + 16;
-        MS_CUDA(h, cudaMemsetAsync(s.status, 0, (size_t)(s.n_tiles + 1) * sizeof(unsigned long long), h->stream));
-        if (smem > 48 * 1024)
+        const int ns = bi.ns_uniform;
+        // stage the tile's coefficients in shared memory while four CTAs still fit an SM
+        const bool coef_smem = h->scan_coef_smem && scan_smem_bytes(s.tpt, ns, O, true) <= 52 * 1024;
+        const size_t smem = scan_smem_bytes(s.tpt, ns, O, coef_smem);
+        MS_CUDA(h, cudaMemsetAsync(s.status, 0, (size_t)(s.n_tiles + 1 + 256) * sizeof(unsigned long long), h->stream));
+        if (smem > 40 * 1024)  // the kernel also has ~4 KB of static shared memory
             cudaFuncSetAttribute(k_sample_scan<O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        const long long resident = (long long)h->sm_count * 8;
+        const long long resident = (long long)h->sm_count * 4;
         const unsigned grid = (unsigned)(s.n_tiles < resident ? s.n_tiles : resident);
         prof_before(h, "k_sample_scan");
         k_sample_scan<O><<<grid, SCAN_THREADS, smem, h->stream>>>(bi.B, ns, s.tpt, s.n_tiles, coeff, T, sd, h->d_ttab,
-                                                                   T_TABLE_N, s.status,
-                                                                   s.ticket, capacity, sample_offset, samples, flags,
-                                                                   h->phase_clocks);
+                                                                   s.status, s.ticket, capacity, sample_offset, samples,
+                                                                   flags, coef_smem ? 1 : 0, s.sm_ctr, h->phase_clocks);
         prof_after(h);
         ++h->launches;
         cudaError_t e = cudaPeekAtLastError();
@@ -415,15 +417,14 @@ int run_sample(msnap_context *h, const BatchIdx &bi, const double *coeff, const 
     }
     const int blk = 128;
     const unsigned gs = grid_for(bi.n_seg, blk), gb = grid_for(bi.B, blk);
-    MS_LAUNCH(h, (k_sample<O, false>), gs, blk, bi, coeff, T, sd, s.seg_count, s.seg_last, (const long long *)nullptr,
-              (const long long *)nullptr, (const int *)nullptr, 0LL, (double *)nullptr, (unsigned *)nullptr);
+    MS_LAUNCH(h, (k_count<O>), gs, blk, bi, coeff, T, sd, s.seg_count, s.seg_mask, s.seg_last);
     MS_LAUNCH(h, (k_traj_count<O>), gb, blk, bi, coeff, T, s.seg_count, s.seg_last, s.seg_start, s.append_end,
               s.traj_count);
     const int nblk = (int)grid_for(bi.B, SCAN_BLOCK);
     MS_LAUNCH(h, k_scan_reduce, nblk, SCAN_BLOCK, s.traj_count, bi.B, s.partial);
     MS_LAUNCH(h, k_scan_partials, 1, SCAN_BLOCK, s.partial, nblk, sample_offset + bi.B);
     MS_LAUNCH(h, k_scan_apply, nblk, SCAN_BLOCK, s.traj_count, bi.B, s.partial, sample_offset);
-    MS_LAUNCH(h, (k_sample<O, true>), gs, blk, bi, coeff, T, sd, (int *)nullptr, (double *)nullptr, s.seg_start,
+    MS_LAUNCH(h, (k_write<O>), gs, blk, bi, coeff, T, sd, h->d_ttab, s.seg_count, s.seg_mask, s.seg_start,
               sample_offset, s.append_end, capacity, samples, flags);
     if (stats) MS_LAUNCH(h, k_stats, grid_for(bi.B * 32, 256), 256, bi.B, sample_offset, samples, capacity, stats);
     return MSNAP_OK;
@@ -611,6 +612,7 @@ int msnap_create(int device, msnap_handle *out) {
     }
     h->stream = h->own_stream;
     if (const char *e = std::getenv("MSNAP_SPEC_CHUNK")) h->spec_chunk = std::atoi(e);
+    if (const char *e = std::getenv("MSNAP_SCAN_COEF_SMEM")) h->scan_coef_smem = std::atoi(e) != 0;
     *out = h;
     return MSNAP_OK;
 }

@@ -34,8 +34,8 @@ struct Dim {
     static constexpr int NR = 3 * B;            // right-hand sides, [r][axis]
     static constexpr int F_D = 0, F_U = ND, F_R = ND + NU;
     static constexpr int NBASE = ND + NU + NR;  // per-row constant data (order 4: 24 doubles)
-    static constexpr int NSTATE = NR + ND;      // per-row sweep state: z_j (or x_j) and P_j (order 4: 15 doubles)
-    static constexpr int SX = 0, SP = NR;       // field offsets of z/x and of the packed inverse P inside a state row
+    static constexpr int NSTATE = NR + NU;      // per-row sweep state: z_j (or x_j) and W_j = P_j U_j (order 4: 18 doubles)
+    static constexpr int SX = 0, SW = NR;       // field offsets of z/x and of W inside a state row
     static constexpr int NSEGX = M + 4;         // per-segment deviation probe: h[M], L(t*)[3], 1/|P_{k+1}-P_k|
     static constexpr int NP = 2 * O - 1;        // inverse powers of T used by S: T^-1 .. T^-(2o-1)
 };
@@ -271,11 +271,11 @@ __device__ __forceinline__ bool sym_inverse(const double (&a)[B * (B + 1) / 2], 
 // Block-tridiagonal solve of one trajectory for the three axes at once ("block Thomas"), SPD system
 //     U_{j-1}' x_{j-1} + D_j x_j + U_j x_{j+1} = r_j .
 // Forward sweep:   D'_j = D_j - U_{j-1}' W_{j-1},   r'_j = r_j - U_{j-1}' z_{j-1},
-//                  P_j = D'_j^-1,   z_j = P_j r'_j,   W_j = P_j U_j  (W_j lives in registers for one row only)
-// Backward sweep:  x_j = z_j - P_j (U_j x_{j+1})
-//   base(j)  : read-only rows (D, U, r);  state(j): z_j [r][axis] and the packed symmetric P_j -- the sweep state
-//              is what the speculative lanes stream through L2, so it is kept to NR + ND doubles per row and the
-//              solution is written only where the caller asks for it (XOut).
+//                  P_j = D'_j^-1 (registers only),   z_j = P_j r'_j,   W_j = P_j U_j
+// Backward sweep:  x_j = z_j - W_j x_{j+1}
+//   base(j)  : read-only rows (D, U, r);  state(j): z_j [r][axis] and W_j -- the sweep state is what the
+//              speculative lanes stream through L2; the solution is written only where the caller asks for it
+//              (XOut).
 //   add00    : added to D_j[0][0] of every row (2 * vel_zero_weight: one vw from each adjacent segment).
 // Storage is abstracted by accessor types:  `const double* operator()(int j)` = field 0 of row j, and a
 // COMPILE-TIME field stride `FS` -- the sweep is issue-bound, so every address must be base + immediate.
@@ -371,7 +371,7 @@ __device__ __forceinline__ bool thomas_forward(int n_rows, double add00, const B
                     W[p * B + q] = acc;
                 }
 #pragma unroll
-            for (int i = 0; i < ND; ++i) StateAt::Mem::st(s + (D::SP + i) * sfs, P[i]);
+            for (int i = 0; i < NU; ++i) StateAt::Mem::st(s + (D::SW + i) * sfs, W[i]);
         }
     }
     return ok;
@@ -385,36 +385,27 @@ struct NoOut {
     __device__ __forceinline__ double *operator()(int) const { return nullptr; }
 };
 
-// One backward step: x_j = z_j - P_j (U_j x_{j+1})  (xn = x_{j+1}; no coupling when !has_next).
-//   s: state row j (z, P) with field stride SFS;  b: base row j (for U_j) with field stride BFS;
+// One backward step: x_j = z_j - W_j x_{j+1}  (xn = x_{j+1}; no coupling when !has_next).
+//   s: state row j (z, W) with field stride SFS;
 //   xo: where x_j is stored ([r][axis], field stride XOut::FS) if XOut::ENABLED.
-template <int O, int SFS, class SMem, int BFS, class XOut>
-__device__ __forceinline__ void thomas_back_step(const double *s, const double *b, double *xo, bool has_next,
+template <int O, int SFS, class SMem, class XOut>
+__device__ __forceinline__ void thomas_back_step(const double *s, double *xo, bool has_next,
                                                  const double (&xn)[3 * (O - 1)], double (&x)[3 * (O - 1)]) {
     using D = Dim<O>;
     constexpr int B = D::B, NR = D::NR;
 #pragma unroll
     for (int i = 0; i < NR; ++i) x[i] = SMem::ld(s + (D::SX + i) * SFS);
     if (has_next) {
-        double P[D::ND], t[NR];
+        double W[D::NU];
 #pragma unroll
-        for (int i = 0; i < D::ND; ++i) P[i] = SMem::ld(s + (D::SP + i) * SFS);
-#pragma unroll
-        for (int p = 0; p < B; ++p)
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                double acc = b[(D::F_U + p * B) * BFS] * xn[a];
-#pragma unroll
-                for (int q = 1; q < B; ++q) acc = fma(b[(D::F_U + p * B + q) * BFS], xn[q * 3 + a], acc);
-                t[p * 3 + a] = acc;
-            }
+        for (int i = 0; i < D::NU; ++i) W[i] = SMem::ld(s + (D::SW + i) * SFS);
 #pragma unroll
         for (int p = 0; p < B; ++p)
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 double acc = x[p * 3 + a];
 #pragma unroll
-                for (int q = 0; q < B; ++q) acc = fma(-P[sym(p, q)], t[q * 3 + a], acc);
+                for (int q = 0; q < B; ++q) acc = fma(-W[p * B + q], xn[q * 3 + a], acc);
                 x[p * 3 + a] = acc;
             }
     }
@@ -454,8 +445,13 @@ __device__ __forceinline__ double deviation_sq(const double *segx, const double 
 //   d0 / dN         : fixed derivative vectors of the first / last waypoint, [r-1][axis]
 //   segx_at(k)      : deviation probe of segment k
 // Returns max_k deviation ratio (0 when !EVAL).
-template <int O, bool EVAL, class BaseAt, class StateAt, class XOut, class SegxAt, class PosAt>
-__device__ __forceinline__ double thomas_backward(int n_rows, const BaseAt base_at, const StateAt state_at,
+// EARLY: the caller only needs to know WHETHER the ratio exceeds the reweighting threshold 0.2 (ms.cpp:82), so the
+// sweep stops at the first segment whose squared ratio is safely above 0.04 and returns that (partial) maximum --
+// still > 0.2.  A sweep that runs to the end returns the exact maximum, so a trajectory that passes the test always
+// has its exact max_dev.
+constexpr double EARLY_DEV2 = 0.04 * (1.0 + 1e-9);
+template <int O, bool EVAL, bool EARLY, class StateAt, class XOut, class SegxAt, class PosAt>
+__device__ __forceinline__ double thomas_backward(int n_rows, const StateAt state_at,
                                                   const XOut xout, const SegxAt segx_at, const PosAt pos,
                                                   const double *d0, const double *dN) {
     using D = Dim<O>;
@@ -471,8 +467,7 @@ __device__ __forceinline__ double thomas_backward(int n_rows, const BaseAt base_
     bool first = true;                            // xb still holds the fixed end derivatives (no W coupling)
     // step: compute x of waypoint j+1 into `xo` from `xi` (= x of waypoint j+2), probe segment j+1
     auto step = [&](double (&xo)[NR], double (&po)[3], const double (&xi)[NR], const double (&pi)[3]) {
-        thomas_back_step<O, StateAt::FS, typename StateAt::Mem, BaseAt::FS, XOut>(state_at(j), base_at(j), xout(j), !first,
-                                                                                  xi, xo);
+        thomas_back_step<O, StateAt::FS, typename StateAt::Mem, XOut>(state_at(j), xout(j), !first, xi, xo);
         pos(j + 1, po);
         if (EVAL) m2 = fmax(m2, deviation_sq<O, SegxAt::FS>(segx_at(j + 1), po, xo, pi, xi));
         first = false;
@@ -483,6 +478,7 @@ __device__ __forceinline__ double thomas_backward(int n_rows, const BaseAt base_
     while (j >= 1) {
         step(xa, pa, xb, pb);
         step(xb, pb, xa, pa);
+        if (EVAL && EARLY && m2 > EARLY_DEV2) return sqrt(m2);
     }
     if (j == 0) {
         step(xa, pa, xb, pb);

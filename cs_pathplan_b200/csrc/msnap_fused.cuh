@@ -240,7 +240,7 @@ __device__ __forceinline__ void fused_probe_item(const FusedParams &p, double *b
 //
 // One Thomas chain of trajectory block `blk` with diagonal shift add00: forward sweep into `state_at`, backward
 // sweep with the deviation probes (EVAL) leaving x in `xout` (or nowhere).
-template <int O, bool EVAL, class StateAt, class XOut>
+template <int O, bool EVAL, bool EARLY, class StateAt, class XOut>
 __device__ __noinline__ bool fused_chain(const double *blk, int ns, double add00, const StateAt state_at,
                                          const XOut xout, double *max_dev_out, long long *clk = nullptr) {
     using D = Dim<O>;
@@ -251,8 +251,8 @@ __device__ __noinline__ bool fused_chain(const double *blk, int ns, double add00
     if (clk) clk[1] = clock64();
     const FSegxRows<O> segx_at{blk + L.oSegx};
     const FPos pos{blk + L.oP};
-    *max_dev_out = thomas_backward<O, EVAL>(ns - 1, base_at, state_at, xout, segx_at, pos, blk + L.oBC,
-                                            blk + L.oBC + D::NR);
+    *max_dev_out = thomas_backward<O, EVAL, EARLY>(ns - 1, state_at, xout, segx_at, pos, blk + L.oBC,
+                                                   blk + L.oBC + D::NR);
     if (clk) clk[2] = clock64();
     return ok;
 }
@@ -262,10 +262,9 @@ template <int O, class StateAt, class XOut>
 __device__ __noinline__ void fused_replay(const double *blk, int ns, const StateAt state_at, const XOut xout) {
     using D = Dim<O>;
     const FusedSmem<O> L(ns);
-    const FBaseRows<O> base_at{blk + L.oBase};
     const FSegxRows<O> segx_at{blk + L.oSegx};
     const FPos pos{blk + L.oP};
-    thomas_backward<O, false>(ns - 1, base_at, state_at, xout, segx_at, pos, blk + L.oBC, blk + L.oBC + D::NR);
+    thomas_backward<O, false, false>(ns - 1, state_at, xout, segx_at, pos, blk + L.oBC, blk + L.oBC + D::NR);
 }
 
 // coefficients of (t, k, axis) from the final solution in the shared-memory state rows; returns finiteness
@@ -382,7 +381,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_c
             if (tid < nt) {
                 double unused;
                 const FStateRows<O, SL> st{state1 + tid};
-                ok1[tid] = fused_chain<O, false>(smem + tid * tstride, ns, 0.0, st, st, &unused) ? 1 : 0;
+                ok1[tid] = fused_chain<O, false, false>(smem + tid * tstride, ns, 0.0, st, st, &unused) ? 1 : 0;
             }
             __syncthreads();
             MSNAP_STAMP();
@@ -421,7 +420,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_c
                 if (p.phase_clocks && tile == blockIdx.x && (tid & 63) == 0)
                     clk = p.phase_clocks + blockIdx.x * 16 + 7 + 3 * (tid >> 6);
                 double mdv;
-                const bool ok = fused_chain<O, true>(smem + t * tstride, ns, add00, st, NoOut{}, &mdv, clk);
+                const bool ok = fused_chain<O, true, true>(smem + t * tstride, ns, add00, st, NoOut{}, &mdv, clk);
                 md[t * nit + q] = mdv;
                 okf[t * nit + q] = ok ? 1 : 0;
             } else if (tid >= sl0 && tid < sl0 + nt) {
@@ -431,8 +430,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_c
                 const double add00 = vw > 0.0 ? 2.0 * vw : 0.0;
                 const FStateRows<O, SL> st{state1 + t};
                 double mdv;
-                const bool ok = use_pw ? fused_chain<O, true>(smem + t * tstride, ns, add00, st, st, &mdv)
-                                       : fused_chain<O, false>(smem + t * tstride, ns, add00, st, st, &mdv);
+                const bool ok = use_pw ? fused_chain<O, true, false>(smem + t * tstride, ns, add00, st, st, &mdv)
+                                       : fused_chain<O, false, false>(smem + t * tstride, ns, add00, st, st, &mdv);
                 md[t * nit + q] = mdv;
                 okf[t * nit + q] = ok ? 1 : 0;
             }

@@ -181,8 +181,8 @@ __global__ void k_thomas(BatchIdx bi, SolveParams sp, const double *__restrict__
         const double add00 = vw > 0.0 ? 2.0 * vw : 0.0;
         ok = thomas_forward<O>(n_rows, add00, base_at, state_at) && ok;
         // x_j overwrites z_j in the state row (z_j is read before it is replaced)
-        max_dev = eval_dev ? thomas_backward<O, true>(n_rows, base_at, state_at, state_at, segx_at, pos, d0, dN)
-                           : thomas_backward<O, false>(n_rows, base_at, state_at, state_at, segx_at, pos, d0, dN);
+        max_dev = eval_dev ? thomas_backward<O, true, false>(n_rows, state_at, state_at, segx_at, pos, d0, dN)
+                           : thomas_backward<O, false, false>(n_rows, state_at, state_at, segx_at, pos, d0, dN);
         if (max_dev > 0.2 && iter < sp.max_iter) {
             vw = (vw < 1e-6) ? 0.01 : vw * 2.0;
             ++iter;
@@ -291,12 +291,23 @@ __global__ void k_coeff(BatchIdx bi, SolveParams sp, const double *__restrict__ 
 // ------------------------------------------------------------------------------------------------ sampler
 // Candidate times of a segment follow ms.cpp:124-141 exactly: dt = min(0.1, T/10), t accumulated by repeated
 // addition (NOT i*dt), loop while t <= T + 1e-12, evaluated at min(t, T).
+//
+// The sampler is split into a COUNT pass and a WRITE pass around an exclusive scan of the per-trajectory row counts.
+// The count pass walks the candidates of a segment in order (the acceptance test depends on the last accepted point,
+// ms.cpp:143-151) and records WHICH candidates were accepted in a 128-bit mask, so the write pass evaluates only those
+// -- at the tabulated times t_i (t_table[i] holds the reference's accumulated `t += 0.1` sequence bit for bit) or, for
+// segments shorter than 1 s (dt = T/10), by redoing the <= 11 additions.  Segments with more than 128 candidates
+// (T > 12.8 s) fall back to re-running the acceptance loop in the write pass.  Both passes evaluate with the same
+// device code, so the rows are identical whichever path wrote them.
 __device__ __forceinline__ double sample_dt(double T) {
     double dt = 0.1;
     const double t10 = __ddiv_rn(T, 10.0);
     if (dt > t10) dt = t10;
     return dt;
 }
+
+constexpr int SAMPLE_MASK_BITS = 128;            // candidates per segment the acceptance mask can describe
+constexpr int SAMPLE_TTAB_N = SAMPLE_MASK_BITS + 2;  // entries of t_table a write pass needs
 
 template <int O>
 __device__ __forceinline__ void load_coeff(const double *__restrict__ coeff, long long g, double (&c)[3][2 * O]) {
@@ -306,66 +317,124 @@ __device__ __forceinline__ void load_coeff(const double *__restrict__ coeff, lon
         for (int i = 0; i < 2 * O; ++i) c[a][i] = coeff[(g * 3 + a) * 2 * O + i];
 }
 
-// Thread per segment.  WRITE == false: count accepted candidates, remember the last accepted point.
-// WRITE == true : store accepted candidates at rows sample_offset[b] + seg_start[g] + i (plus the trajectory's
-// first point / appended end point), dropping rows >= capacity.
-template <int O, bool WRITE>
-__global__ void k_sample(BatchIdx bi, const double *__restrict__ coeff, const double *__restrict__ T,
-                         double sample_distance, int *__restrict__ seg_count, double *__restrict__ seg_last,
-                         const long long *__restrict__ seg_start, const long long *__restrict__ sample_offset,
-                         const int *__restrict__ append_end, long long capacity, double *__restrict__ samples,
-                         unsigned *__restrict__ flags) {
+// Count pass of one segment.  n: accepted candidates; (m0, m1): acceptance mask of candidates 0..127; usable: every
+// candidate has a mask bit; last: the last accepted point (the segment's start point if none was accepted).
+// Two candidates are evaluated per trip (their positions do not depend on the acceptance decisions), which doubles the
+// instruction-level parallelism of the Horner chains; the decisions are still taken strictly in order.
+template <int O>
+__device__ __forceinline__ void count_candidates(const double (&c)[3][2 * O], double Tk, const AcceptTest &accept,
+                                                 int &n_out, bool &usable, unsigned long long &m0,
+                                                 unsigned long long &m1, double (&last)[3]) {
+    const double dt = sample_dt(Tk);
+    const double tmax = Tk + 1e-12;
+    double prev[3], ca[3], cb[3];
+    eval_xyz<O>(c, 0.0, prev);
+    int n = 0, idx = 0;
+    unsigned long long w0 = 0ull, w1 = 0ull;
+    double t = dt;
+    while (t <= tmax) {
+        const double t2 = t + dt;
+        eval_xyz<O>(c, fmin(t, Tk), ca);
+        eval_xyz<O>(c, fmin(t2, Tk), cb);
+        if (accept(ca, prev)) {
+            prev[0] = ca[0]; prev[1] = ca[1]; prev[2] = ca[2];
+            ++n;
+            if (idx < 64) w0 |= 1ull << idx; else if (idx < 128) w1 |= 1ull << (idx - 64);
+        }
+        ++idx;
+        if (t2 <= tmax) {
+            if (accept(cb, prev)) {
+                prev[0] = cb[0]; prev[1] = cb[1]; prev[2] = cb[2];
+                ++n;
+                if (idx < 64) w0 |= 1ull << idx; else if (idx < 128) w1 |= 1ull << (idx - 64);
+            }
+            ++idx;
+        }
+        t = t2 + dt;
+    }
+    n_out = n;
+    usable = idx <= SAMPLE_MASK_BITS;
+    m0 = w0;
+    m1 = w1;
+    last[0] = prev[0]; last[1] = prev[1]; last[2] = prev[2];
+}
+
+// Write pass of one segment: put(row, point) for every accepted candidate, rows counted from `row`.
+//   ttab: t_table[0 .. SAMPLE_TTAB_N) (shared memory in the callers)
+template <int O, class Put>
+__device__ __forceinline__ void write_candidates(const double (&c)[3][2 * O], double Tk, bool usable,
+                                                 unsigned long long m0, unsigned long long m1,
+                                                 const AcceptTest &accept, const double *ttab, long long row,
+                                                 const Put &put) {
+    const double dt = sample_dt(Tk);
+    double cur[3];
+    if (usable) {
+        const bool tabulated = dt == 0.1;
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            unsigned long long m = w == 0 ? m0 : m1;
+            while (m) {
+                const int bit = __ffsll((long long)m) - 1 + 64 * w;
+                m &= m - 1;
+                double t;
+                if (tabulated) {
+                    t = ttab[bit + 1];
+                } else {
+                    t = dt;
+                    for (int i = 0; i < bit; ++i) t += dt;
+                }
+                eval_xyz<O>(c, fmin(t, Tk), cur);
+                put(row++, cur);
+            }
+        }
+    } else {
+        double prev[3];
+        eval_xyz<O>(c, 0.0, prev);
+        for (double t = dt; t <= Tk + 1e-12; t += dt) {
+            eval_xyz<O>(c, fmin(t, Tk), cur);
+            if (accept(cur, prev)) {
+                prev[0] = cur[0]; prev[1] = cur[1]; prev[2] = cur[2];
+                put(row++, cur);
+            }
+        }
+    }
+}
+
+// Stores one sample row unless it lies beyond the caller's capacity.
+struct RowSink {
+    double *__restrict__ samples;
+    long long capacity;
+    bool *dropped;
+    __device__ __forceinline__ void operator()(long long r, const double (&v)[3]) const {
+        if (r < capacity) {
+            samples[3 * r] = v[0]; samples[3 * r + 1] = v[1]; samples[3 * r + 2] = v[2];
+        } else {
+            *dropped = true;
+        }
+    }
+};
+
+// ---- generic (CSR) path: one kernel per pass, intermediates in the HBM workspace ----------------------------------
+// k_count: thread per segment.  seg_count[g] = n (usable mask) or -n-1 (write pass must re-run the acceptance loop).
+template <int O>
+__global__ void __launch_bounds__(128) k_count(BatchIdx bi, const double *__restrict__ coeff,
+                                               const double *__restrict__ T, double sample_distance,
+                                               int *__restrict__ seg_count, unsigned long long *__restrict__ seg_mask,
+                                               double *__restrict__ seg_last) {
     const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (g >= bi.n_seg) return;
-    long long b = 0; int k = 0, ns = 0;
-    if (WRITE) bi.locate(g, b, k, ns);
     double c[3][2 * O];
     load_coeff<O>(coeff, g, c);
-    const double Tk = T[g];
-    const double dt = sample_dt(Tk);
-    double prev[3], cur[3];
-    eval_xyz<O>(c, 0.0, prev);
-    long long row = 0;
-    bool dropped = false;
-    if (WRITE) {
-        row = sample_offset[b] + seg_start[g];
-        if (k == 0) {  // very first point of the trajectory (ms.cpp:132-137)
-            const long long r0 = sample_offset[b];
-            if (r0 < capacity) {
-                samples[3 * r0] = prev[0]; samples[3 * r0 + 1] = prev[1]; samples[3 * r0 + 2] = prev[2];
-            } else dropped = true;
-        }
-    }
-    int cnt = 0;
-    const double tmax = Tk + 1e-12;
     const AcceptTest accept(sample_distance);
-    for (double t = dt; t <= tmax; t += dt) {
-        const double tt = fmin(t, Tk);
-        eval_xyz<O>(c, tt, cur);
-        if (accept(cur, prev)) {
-            prev[0] = cur[0]; prev[1] = cur[1]; prev[2] = cur[2];
-            if (WRITE) {
-                if (row < capacity) {
-                    samples[3 * row] = cur[0]; samples[3 * row + 1] = cur[1]; samples[3 * row + 2] = cur[2];
-                } else dropped = true;
-                ++row;
-            }
-            ++cnt;
-        }
-    }
-    if (!WRITE) {
-        seg_count[g] = cnt;
-        seg_last[3 * g] = prev[0]; seg_last[3 * g + 1] = prev[1]; seg_last[3 * g + 2] = prev[2];
-    } else {
-        if (k == ns - 1 && append_end[b]) {  // end point appended after the last segment (ms.cpp:157-160)
-            eval_xyz<O>(c, Tk, cur);
-            const long long re = sample_offset[b + 1] - 1;
-            if (re < capacity) {
-                samples[3 * re] = cur[0]; samples[3 * re + 1] = cur[1]; samples[3 * re + 2] = cur[2];
-            } else dropped = true;
-        }
-        if (dropped && flags) atomicOr(flags + b, 2u);
-    }
+    int n;
+    bool usable;
+    unsigned long long m0, m1;
+    double last[3];
+    count_candidates<O>(c, T[g], accept, n, usable, m0, m1, last);
+    seg_count[g] = usable ? n : -n - 1;
+    seg_mask[2 * g] = m0;
+    seg_mask[2 * g + 1] = m1;
+    seg_last[3 * g] = last[0]; seg_last[3 * g + 1] = last[1]; seg_last[3 * g + 2] = last[2];
 }
 
 // Thread per trajectory: per-segment start rows (relative to the trajectory), the end-point rule, total count.
@@ -381,7 +450,8 @@ __global__ void k_traj_count(BatchIdx bi, const double *__restrict__ coeff, cons
     long long last_g = -1;
     for (long long g = g0; g < g1; ++g) {
         seg_start[g] = total;
-        const int c = seg_count[g];
+        const int sc = seg_count[g];
+        const int c = sc >= 0 ? sc : -sc - 1;
         total += c;
         if (c > 0) last_g = g;
     }
@@ -397,6 +467,44 @@ __global__ void k_traj_count(BatchIdx bi, const double *__restrict__ coeff, cons
     const int app = dist3(back, endp) > 1e-6 ? 1 : 0;
     append_end[b] = app;
     traj_count[b] = total + app;
+}
+
+// k_write: thread per segment.  Rows sample_offset[b] + seg_start[g] + i, plus the trajectory's first point (k == 0)
+// and the appended end point (k == ns-1); rows >= capacity are dropped and flagged.
+template <int O>
+__global__ void __launch_bounds__(128) k_write(BatchIdx bi, const double *__restrict__ coeff,
+                                               const double *__restrict__ T, double sample_distance,
+                                               const double *__restrict__ t_table, const int *__restrict__ seg_count,
+                                               const unsigned long long *__restrict__ seg_mask,
+                                               const long long *__restrict__ seg_start,
+                                               const long long *__restrict__ sample_offset,
+                                               const int *__restrict__ append_end, long long capacity,
+                                               double *__restrict__ samples, unsigned *__restrict__ flags) {
+    __shared__ double ttab[SAMPLE_TTAB_N];
+    for (int i = threadIdx.x; i < SAMPLE_TTAB_N; i += blockDim.x) ttab[i] = t_table[i];
+    __syncthreads();
+    const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (g >= bi.n_seg) return;
+    long long b; int k, ns;
+    bi.locate(g, b, k, ns);
+    double c[3][2 * O], cur[3];
+    load_coeff<O>(coeff, g, c);
+    const double Tk = T[g];
+    const AcceptTest accept(sample_distance);
+    bool dropped = false;
+    const RowSink put{samples, capacity, &dropped};
+    const long long row0 = sample_offset[b];
+    if (k == 0) {  // very first point of the trajectory (ms.cpp:132-137)
+        eval_xyz<O>(c, 0.0, cur);
+        put(row0, cur);
+    }
+    const int sc = seg_count[g];
+    write_candidates<O>(c, Tk, sc >= 0, seg_mask[2 * g], seg_mask[2 * g + 1], accept, ttab, row0 + seg_start[g], put);
+    if (k == ns - 1 && append_end[b]) {  // end point appended after the last segment (ms.cpp:157-160)
+        eval_xyz<O>(c, Tk, cur);
+        put(sample_offset[b + 1] - 1, cur);
+    }
+    if (dropped && flags) atomicOr(flags + b, 2u);
 }
 
 // Exclusive scan of int64 counts into offsets[n+1], three small kernels (n up to millions; traffic negligible).
@@ -461,46 +569,103 @@ __global__ void k_scan_apply(const long long *__restrict__ in, long long n, cons
 // Single-launch sampler for uniform batches: count, exclusive scan across the whole batch and write, in one kernel.
 // A CTA takes tiles of `tpt` consecutive trajectories in ticket order (atomic counter), so that a tile's
 // predecessors have always started; the cross-tile exclusive prefix uses decoupled look-back on one 64-bit status
-// word per tile (2 flag bits + 62 value bits), read 128 predecessors at a time by the whole CTA.
+// word per tile (2 flag bits + 62 value bits), read SCAN_THREADS predecessors at a time by the whole CTA.
 //   status[i]: 0 = nothing yet, (v << 2) | 1 = tile aggregate v, (v << 2) | 2 = inclusive prefix v
 //
-// Work balance.  A segment's candidate count is proportional to its duration, which varies several-fold inside a
-// tile.  The tile's segments are ranked by candidate count and dealt to the lanes in snake order (lane l takes ranks
-// l, 2N-1-l, 2N+l, ...), so every lane -- and every warp -- gets about the same number of candidates.
+//   A  count   thread per segment, segments dealt to the lanes in order of decreasing candidate count (a counting
+//              sort on the candidate-count estimate), so that the lanes of a warp run loops of similar length
+//   B  rows    thread per trajectory: start row of every segment, end-point rule, row count
+//   C  scan    tile-local scan, publish the aggregate, EXPAND (below), then look back for the tile's first row
+//   D  write   one row per lane, 32 consecutive rows per warp step = 768 contiguous bytes, three coalesced stores
 //
-// The count pass records WHICH candidates were accepted (a bitmask, up to 64*SCAN_MASK_WORDS candidates per
-// segment), so the write pass evaluates only those, at the tabulated times t_i (the reference accumulates t += 0.1;
-// t_table[i] holds exactly that sequence).  Segments outside the mask/table range, or with dt = T/10 (T < 1 s), take
-// the plain re-evaluation loop.  Candidate evaluation and acceptance are the same device code as k_sample, so the rows
-// are bitwise identical.
+// EXPAND turns the acceptance masks into one 32-bit descriptor per output row (segment << 8 | code), written by
+// the segment's own lane at the row's tile-local position, so that the write pass needs no search: a lane reads
+// its descriptor, takes the candidate time from the table and evaluates.  It runs while the CTA would otherwise only
+// wait for its predecessors in the look-back.
 constexpr int SCAN_THREADS = 128;
-constexpr int SCAN_MASK_WORDS = 2;
+constexpr int SCAN_DESC_CAP = 4096;        // descriptors (rows) expanded per chunk
+constexpr unsigned DESC_END = 253u;        // code: the appended end point p(T) of the trajectory's last segment
+constexpr unsigned DESC_FIRST = 254u;      // code: the trajectory's first point p(0)
+constexpr unsigned DESC_SLOW = 252u;       // code: first row of a segment without a usable mask (lane redoes the segment)
+constexpr unsigned DESC_SKIP = 251u;       // code: further rows of such a segment (written by the DESC_SLOW lane)
+constexpr unsigned DESC_ACCUM = 1u << 31;  // flag: candidate times are accumulated from dt = T/10 (T < 1 s), not tabulated
+
+// bytes of dynamic shared memory for a tile of `tpt` trajectories of `ns` segments; coef_smem: the tile's
+// coefficients are staged in shared memory too (row pitch 6*order + 1 doubles, conflict-free for the count pass)
+__host__ __device__ inline size_t scan_smem_bytes(int tpt, int ns, int order, bool coef_smem) {
+    const size_t seg_cap = (size_t)tpt * ns;
+    return SAMPLE_TTAB_N * sizeof(double) + seg_cap * 2 * sizeof(unsigned long long) + seg_cap * 3 * sizeof(double) +
+           seg_cap * sizeof(double) + (coef_smem ? seg_cap * (6 * order + 1) * sizeof(double) : 0) +
+           (size_t)(tpt + 1) * sizeof(long long) + seg_cap * 3 * sizeof(int) +
+           (size_t)tpt * sizeof(int) + SCAN_DESC_CAP * sizeof(unsigned) + 16;
+}
 
 template <int O>
-__global__ void __launch_bounds__(SCAN_THREADS, 5) k_sample_scan(
+__global__ void __launch_bounds__(SCAN_THREADS, 4) k_sample_scan(
     long long B, int ns, int tpt, long long n_tiles, const double *__restrict__ coeff, const double *__restrict__ T,
-    double sample_distance, const double *__restrict__ t_table, int t_table_n, unsigned long long *status,
-    unsigned int *ticket, long long capacity, long long *__restrict__ sample_offset, double *__restrict__ samples,
-    unsigned *__restrict__ flags, long long *phase_clocks) {
+    double sample_distance, const double *__restrict__ t_table, unsigned long long *status, unsigned int *ticket,
+    long long capacity, long long *__restrict__ sample_offset, double *__restrict__ samples,
+    unsigned *__restrict__ flags, int coef_smem, int *sm_ctr, long long *phase_clocks) {
     extern __shared__ unsigned char smem_raw[];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int seg_cap = tpt * ns;
-    unsigned long long *mask = reinterpret_cast<unsigned long long *>(smem_raw);       // [seg_cap][SCAN_MASK_WORDS]
-    long long *seg_start = reinterpret_cast<long long *>(mask + (size_t)seg_cap * SCAN_MASK_WORDS);  // [seg_cap]
-    double *last = reinterpret_cast<double *>(seg_start + seg_cap);                     // [seg_cap][3]
-    long long *traj_base = reinterpret_cast<long long *>(last + 3 * seg_cap);           // [tpt + 1]
-    int *cnt = reinterpret_cast<int *>(traj_base + tpt + 1);                            // [seg_cap]
-    int *append = cnt + seg_cap;                                                        // [tpt]
-    int *key = append + tpt;                                                            // [seg_cap] candidate-count estimate
-    int *perm = key + seg_cap;                                                          // [seg_cap] segments, longest first
+    constexpr int CP = 6 * O + 1;  // row pitch of the staged coefficients
+    double *ttab = reinterpret_cast<double *>(smem_raw);                                  // [SAMPLE_TTAB_N]
+    unsigned long long *mask = reinterpret_cast<unsigned long long *>(ttab + SAMPLE_TTAB_N);  // [seg_cap][2]
+    double *last = reinterpret_cast<double *>(mask + 2 * (size_t)seg_cap);                // [seg_cap][3]
+    double *segT = last + 3 * (size_t)seg_cap;                                            // [seg_cap] segment times
+    double *csm = segT + seg_cap;                                                         // [seg_cap][CP] if coef_smem
+    long long *traj_base = reinterpret_cast<long long *>(csm + (coef_smem ? (size_t)seg_cap * CP : 0));  // [tpt + 1]
+    int *cnt = reinterpret_cast<int *>(traj_base + tpt + 1);                              // [seg_cap] signed count
+    int *seg_start = cnt + seg_cap;                                                       // [seg_cap] row in trajectory
+    int *perm = seg_start + seg_cap;                                                      // [seg_cap] longest first
+    int *append = perm + seg_cap;                                                         // [tpt]
+    unsigned *desc = reinterpret_cast<unsigned *>(append + tpt);                          // [SCAN_DESC_CAP]
     const AcceptTest accept(sample_distance);
+    __shared__ double wstage[(SCAN_THREADS / 32) * 96];  // per warp: 32 rows x 3 doubles staged for coalesced stores
+    __shared__ int hist[SAMPLE_MASK_BITS + 1];
     __shared__ long long sh_tile;
     __shared__ long long sh_base;
     __shared__ long long sh_part[SCAN_THREADS / 32];
     __shared__ int sh_first[SCAN_THREADS / 32];
+    __shared__ int sh_slot, sh_sched[SCAN_THREADS / 32];
+    for (int i = tid; i < SAMPLE_TTAB_N; i += SCAN_THREADS) ttab[i] = t_table[i];
+    // Which chunk of the ranking a warp takes in phase A: (its scheduler + the CTA's arrival order on this SM) mod 4,
+    // a Latin square over (scheduler, co-resident CTA), so that every scheduler of the SM gets one chunk of each rank.
+    // The scheduler of a warp is its hardware warp slot mod 4; if the CTA's warps do not sit on four distinct
+    // schedulers the plain order (warp w takes chunk w) is used.
+    if (tid == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        sh_slot = atomicAdd(sm_ctr + smid, 1);
+    }
+    if (lane == 0) {
+        unsigned wslot;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wslot));
+        sh_sched[wid] = (int)(wslot & 3u);
+    }
+    __syncthreads();
+    int chunk = wid;
+    {
+        unsigned seen = 0;
+        for (int w = 0; w < SCAN_THREADS / 32; ++w) seen |= 1u << sh_sched[w];
+        if (seen == (1u << (SCAN_THREADS / 32)) - 1u) chunk = (sh_sched[wid] + sh_slot) & (SCAN_THREADS / 32 - 1);
+    }
+    // coefficients of tile-local segment i: from the staged copy once phase A has filled it
+    auto staged_coeff = [&](long long g0_, int i, double (&c)[3][2 * O]) {
+        if (coef_smem) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int j = 0; j < 2 * O; ++j) c[a][j] = csm[i * CP + a * 2 * O + j];
+        } else {
+            load_coeff<O>(coeff, g0_ + i, c);
+        }
+    };
 
     while (true) {
         if (tid == 0) sh_tile = (long long)atomicAdd(ticket, 1u);
+        for (int i = tid; i <= SAMPLE_MASK_BITS; i += SCAN_THREADS) hist[i] = 0;
         __syncthreads();
         const long long tile = sh_tile;
         if (tile >= n_tiles) break;
@@ -515,62 +680,67 @@ __global__ void __launch_bounds__(SCAN_THREADS, 5) k_sample_scan(
         const int nt = (int)min((long long)tpt, B - b0);
         const long long g0 = b0 * ns;
         const int nseg = nt * ns;
-        // ---- rank the tile's segments by candidate count, longest first
+        // ---- counting sort of the tile's segments by candidate-count estimate, longest first
         for (int i = tid; i < nseg; i += SCAN_THREADS) {
             const double Tk = T[g0 + i];
-            key[i] = (int)fmin(Tk / sample_dt(Tk), 1.0e9);
+            segT[i] = Tk;
+            const int key = (int)fmax(0.0, fmin(Tk * 10.0, (double)SAMPLE_MASK_BITS));  // ~ candidates when dt = 0.1
+            seg_start[i] = key;                          // (scratch until phase B)
+            cnt[i] = atomicAdd(&hist[key], 1);           // rank inside the bin (scratch until phase A)
         }
         __syncthreads();
-        for (int i = tid; i < nseg; i += SCAN_THREADS) {
-            const int ki = key[i];
-            int rank = 0;
-            for (int j = 0; j < nseg; ++j) {
-                const int kj = key[j];
-                rank += (kj > ki || (kj == ki && j < i)) ? 1 : 0;
-            }
-            perm[rank] = i;
-        }
-        __syncthreads();
-        SCAN_STAMP();
-        // ---- A: count accepted candidates per segment, remember which and the last accepted point
-        auto count_segment = [&](int i) {
-            double c[3][2 * O];
-            load_coeff<O>(coeff, g0 + i, c);
-            const double Tk = T[g0 + i];
-            const double dt = sample_dt(Tk);
-            double prev[3], cur[3];
-            eval_xyz<O>(c, 0.0, prev);
-            int n = 0, idx = 0;
-            unsigned long long m[SCAN_MASK_WORDS];
+        if (tid < 32) {  // hist[k] := number of segments with a larger key (one warp, 129 bins)
+            int run = 0;
+            for (int base = SAMPLE_MASK_BITS - (SAMPLE_MASK_BITS % 32); base >= 0; base -= 32) {
+                const int k = base + lane;
+                const int h = k <= SAMPLE_MASK_BITS ? hist[k] : 0;
+                int v = h;  // inclusive suffix sum inside the 32 bins, highest lane first
 #pragma unroll
-            for (int w = 0; w < SCAN_MASK_WORDS; ++w) m[w] = 0ull;
-            for (double t = dt; t <= Tk + 1e-12; t += dt, ++idx) {
-                eval_xyz<O>(c, fmin(t, Tk), cur);
-                if (accept(cur, prev)) {
-                    prev[0] = cur[0]; prev[1] = cur[1]; prev[2] = cur[2];
-                    ++n;
-#pragma unroll
-                    for (int w = 0; w < SCAN_MASK_WORDS; ++w)
-                        if ((idx >> 6) == w) m[w] |= 1ull << (idx & 63);
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_down_sync(0xffffffffu, v, o);
+                    if (lane + o < 32) v += u;
                 }
+                if (k <= SAMPLE_MASK_BITS) hist[k] = run + v - h;
+                run += __shfl_sync(0xffffffffu, v, 0);
             }
-            // the mask is usable by the write pass iff every candidate has a bit and a tabulated time
-            const bool usable = dt == 0.1 && idx <= 64 * SCAN_MASK_WORDS && idx < t_table_n;
-            cnt[i] = usable ? n : -n - 1;  // negative: "re-evaluate in the write pass"
-#pragma unroll
-            for (int w = 0; w < SCAN_MASK_WORDS; ++w) mask[i * SCAN_MASK_WORDS + w] = m[w];
-            last[3 * i] = prev[0]; last[3 * i + 1] = prev[1]; last[3 * i + 2] = prev[2];
-        };
+        }
+        __syncthreads();
+        for (int i = tid; i < nseg; i += SCAN_THREADS) perm[hist[seg_start[i]] + cnt[i]] = i;
+        __syncthreads();
+        // ---- A: count accepted candidates per segment, remember which and the last accepted point
+        // Warps take the ranking in chunks of 32 (homogeneous loop lengths inside a warp); which chunk a warp takes is
+        // `chunk` (see above), so that the long chunks of the CTAs sharing an SM land on different schedulers.
+        const int rot_tid = (chunk << 5) | lane;
         for (int r0 = 0; r0 < nseg; r0 += 2 * SCAN_THREADS) {  // snake order over the ranking
-            const int ra = r0 + tid, rb = r0 + 2 * SCAN_THREADS - 1 - tid;
-            if (ra < nseg) count_segment(perm[ra]);
-            if (rb < nseg) count_segment(perm[rb]);
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const int rk = half == 0 ? r0 + rot_tid : r0 + 2 * SCAN_THREADS - 1 - rot_tid;
+                if (rk >= nseg) continue;
+                const int i = perm[rk];
+                double c[3][2 * O];
+                load_coeff<O>(coeff, g0 + i, c);
+                if (coef_smem) {
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+#pragma unroll
+                        for (int j = 0; j < 2 * O; ++j) csm[i * CP + a * 2 * O + j] = c[a][j];
+                }
+                int n;
+                bool usable;
+                unsigned long long m0, m1;
+                double lp[3];
+                count_candidates<O>(c, segT[i], accept, n, usable, m0, m1, lp);
+                cnt[i] = usable ? n : -n - 1;
+                mask[2 * i] = m0;
+                mask[2 * i + 1] = m1;
+                last[3 * i] = lp[0]; last[3 * i + 1] = lp[1]; last[3 * i + 2] = lp[2];
+            }
         }
         __syncthreads();
         SCAN_STAMP();
         // ---- B: per trajectory: segment start rows, end-point rule (ms.cpp:157-160), row count
         if (tid < nt) {
-            long long total = 1;  // the first point
+            int total = 1;  // the first point
             int last_seg = -1;
             for (int k = 0; k < ns; ++k) {
                 const int i = tid * ns + k;
@@ -583,19 +753,19 @@ __global__ void __launch_bounds__(SCAN_THREADS, 5) k_sample_scan(
             if (last_seg >= 0) {
                 back[0] = last[3 * last_seg]; back[1] = last[3 * last_seg + 1]; back[2] = last[3 * last_seg + 2];
             } else {
-                load_coeff<O>(coeff, g0 + (long long)tid * ns, c);
+                staged_coeff(g0, tid * ns, c);
                 eval_xyz<O>(c, 0.0, back);
             }
-            const long long gl = g0 + (long long)tid * ns + ns - 1;
-            load_coeff<O>(coeff, gl, c);
-            eval_xyz<O>(c, T[gl], endp);
+            const int il = tid * ns + ns - 1;
+            staged_coeff(g0, il, c);
+            eval_xyz<O>(c, segT[il], endp);
             const int app = dist3(back, endp) > 1e-6 ? 1 : 0;
             append[tid] = app;
             traj_base[tid + 1] = total + app;  // row count, scanned below
         }
         __syncthreads();
         SCAN_STAMP();
-        // ---- C: scan inside the tile, publish the aggregate, look back for the exclusive prefix of the tile
+        // ---- C: scan inside the tile and publish the aggregate
         if (tid == 0) {
             long long run = 0;
             traj_base[0] = 0;
@@ -611,9 +781,45 @@ __global__ void __launch_bounds__(SCAN_THREADS, 5) k_sample_scan(
             if (tile == 0) sh_base = 0;
         }
         __syncthreads();
+        const int total = (int)traj_base[nt];
+        // ---- EXPAND rows [c0, c0 + SCAN_DESC_CAP) of the tile into descriptors (first chunk before the look-back)
+        auto expand = [&](int c0) {
+            for (int i = tid; i < nseg; i += SCAN_THREADS) {
+                const int t = i / ns, k = i - t * ns;
+                const int tb = (int)traj_base[t] - c0;
+                if (k == 0 && tb >= 0 && tb < SCAN_DESC_CAP) desc[tb] = ((unsigned)i << 8) | DESC_FIRST;
+                if (k == ns - 1 && append[t]) {
+                    const int re = (int)traj_base[t + 1] - 1 - c0;
+                    if (re >= 0 && re < SCAN_DESC_CAP) desc[re] = ((unsigned)i << 8) | DESC_END;
+                }
+                int row = tb + seg_start[i];
+                const int sc = cnt[i];
+                const int n = sc >= 0 ? sc : -sc - 1;
+                if (row >= SCAN_DESC_CAP || row + n <= 0) continue;
+                if (sc >= 0) {
+                    const unsigned head = ((unsigned)i << 8) | (segT[i] < 1.0 ? DESC_ACCUM : 0u);
+#pragma unroll
+                    for (int w = 0; w < 2; ++w) {
+                        unsigned long long m = mask[2 * i + w];
+                        while (m) {
+                            const int bit = __ffsll((long long)m) - 1 + 64 * w;
+                            m &= m - 1;
+                            if (row >= 0 && row < SCAN_DESC_CAP) desc[row] = head | (unsigned)bit;
+                            ++row;
+                        }
+                    }
+                } else {
+                    for (int j = 0; j < n; ++j, ++row)
+                        if (row >= 0 && row < SCAN_DESC_CAP)
+                            desc[row] = ((unsigned)i << 8) | (j == 0 ? DESC_SLOW : DESC_SKIP);
+                }
+            }
+        };
+        expand(0);
+        // ---- look back for the exclusive prefix of the tile
         if (tile > 0) {
             long long base = 0;
-            long long hi = tile;  // predecessors [hi - 128, hi) are examined per step, newest first
+            long long hi = tile;  // predecessors [hi - SCAN_THREADS, hi) are examined per step, newest first
             bool done = false;
             while (!done) {
                 const long long idx = hi - 1 - tid;
@@ -626,7 +832,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 5) k_sample_scan(
                 }
                 // nearest predecessor (smallest tid) that already has an inclusive prefix
                 const unsigned ball = __ballot_sync(0xffffffffu, (w & 3ull) == 2ull);
-                if ((tid & 31) == 0) sh_first[tid >> 5] = ball ? (tid & ~31) + __ffs(ball) - 1 : -1;
+                if (lane == 0) sh_first[wid] = ball ? (tid & ~31) + __ffs(ball) - 1 : -1;
                 __syncthreads();
                 int first = -1;
                 for (int wi = 0; wi < SCAN_THREADS / 32; ++wi)
@@ -636,7 +842,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 5) k_sample_scan(
                 if (idx < 0) v = 0;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-                if ((tid & 31) == 0) sh_part[tid >> 5] = v;
+                if (lane == 0) sh_part[wid] = v;
                 __syncthreads();
                 for (int wi = 0; wi < SCAN_THREADS / 32; ++wi) base += sh_part[wi];
                 done = first >= 0;
@@ -648,64 +854,72 @@ __global__ void __launch_bounds__(SCAN_THREADS, 5) k_sample_scan(
                 __threadfence();
                 atomicExch(status + tile, ((unsigned long long)(base + traj_base[nt]) << 2) | 2ull);
             }
-            __syncthreads();
         }
+        __syncthreads();
         SCAN_STAMP();
         const long long tile_base = sh_base;
         if (tid < nt) sample_offset[b0 + tid] = tile_base + traj_base[tid];
         if (tile == n_tiles - 1 && tid == 0) sample_offset[B] = tile_base + traj_base[nt];
-        // ---- D: write the accepted candidates (same arithmetic as the count pass)
-        auto write_segment = [&](int i) {
-            const int t = i / ns, k = i - t * ns;
-            double c[3][2 * O];
-            load_coeff<O>(coeff, g0 + i, c);
-            const double Tk = T[g0 + i];
-            double cur[3];
-            const long long row0 = tile_base + traj_base[t];
-            long long row = row0 + seg_start[i];
-            bool dropped = false;
-            auto put = [&](long long r, const double (&v)[3]) {
-                if (r < capacity) {
-                    samples[3 * r] = v[0]; samples[3 * r + 1] = v[1]; samples[3 * r + 2] = v[2];
-                } else dropped = true;
-            };
-            if (k == 0) {  // the trajectory's first point (ms.cpp:132-137)
-                eval_xyz<O>(c, 0.0, cur);
-                put(row0, cur);
+        // ---- D: write the rows of the tile (same arithmetic as the count pass)
+        double *stage = wstage + wid * 96;
+        for (int c0 = 0; c0 < total; c0 += SCAN_DESC_CAP) {
+            if (c0 > 0) {
+                __syncthreads();
+                expand(c0);
+                __syncthreads();
             }
-            if (cnt[i] >= 0) {
+            const int c1 = min(total, c0 + SCAN_DESC_CAP);
+            for (int r0 = c0 + wid * 32; r0 < c1; r0 += SCAN_THREADS) {
+                const int r = r0 + lane;
+                double cur[3] = {0.0, 0.0, 0.0};
+                bool hole = false;  // row written by another lane (DESC_SLOW / DESC_SKIP)
+                if (r < c1) {
+                    const unsigned d = desc[r - c0];
+                    const int i = (int)((d & ~DESC_ACCUM) >> 8);
+                    const unsigned code = d & 255u;
+                    if (code != DESC_SKIP) {
+                        double c[3][2 * O];
+                        staged_coeff(g0, i, c);
+                        const double Tk = segT[i];
+                        if (code == DESC_SLOW) {  // > SAMPLE_MASK_BITS candidates: this lane redoes the segment
+                            bool dropped = false;
+                            const RowSink put{samples, capacity, &dropped};
+                            write_candidates<O>(c, Tk, false, 0ull, 0ull, accept, ttab, tile_base + r, put);
+                            if (dropped && flags) atomicOr(flags + b0 + i / ns, 2u);
+                            hole = true;
+                        } else {
+                            double tt;
+                            if (code == DESC_FIRST) tt = 0.0;
+                            else if (code == DESC_END) tt = Tk;
+                            else if (d & DESC_ACCUM) {
+                                const double dt = sample_dt(Tk);
+                                tt = dt;
+                                for (unsigned n = 0; n < code; ++n) tt += dt;
+                                tt = fmin(tt, Tk);
+                            } else {
+                                tt = fmin(ttab[code + 1], Tk);
+                            }
+                            eval_xyz<O>(c, tt, cur);
+                            if (tile_base + r >= capacity && flags) atomicOr(flags + b0 + i / ns, 2u);
+                        }
+                    } else {
+                        hole = true;
+                    }
+                }
+                stage[3 * lane] = cur[0]; stage[3 * lane + 1] = cur[1]; stage[3 * lane + 2] = cur[2];
+                const unsigned holes = __ballot_sync(0xffffffffu, hole);
+                __syncwarp();
+                const long long e0 = 3 * (tile_base + r0);
+                long long room = capacity - (tile_base + r0);  // rows of this step that fit the caller's buffer
+                if (room > 32) room = 32;
+                const int n_el = 3 * min((int)(room > 0 ? room : 0), c1 - r0);
 #pragma unroll
-                for (int w = 0; w < SCAN_MASK_WORDS; ++w) {
-                    unsigned long long m = mask[i * SCAN_MASK_WORDS + w];
-                    while (m) {
-                        const int bit = __ffsll((long long)m) - 1;
-                        m &= m - 1;
-                        eval_xyz<O>(c, fmin(__ldg(t_table + w * 64 + bit + 1), Tk), cur);
-                        put(row++, cur);
-                    }
+                for (int j = 0; j < 3; ++j) {
+                    const int e = lane + 32 * j;
+                    if (e < n_el && !(holes && ((holes >> (e / 3)) & 1u))) samples[e0 + e] = stage[e];
                 }
-            } else {
-                const double dt = sample_dt(Tk);
-                double prev[3];
-                eval_xyz<O>(c, 0.0, prev);
-                for (double tt = dt; tt <= Tk + 1e-12; tt += dt) {
-                    eval_xyz<O>(c, fmin(tt, Tk), cur);
-                    if (accept(cur, prev)) {
-                        prev[0] = cur[0]; prev[1] = cur[1]; prev[2] = cur[2];
-                        put(row++, cur);
-                    }
-                }
+                __syncwarp();
             }
-            if (k == ns - 1 && append[t]) {  // the end point (ms.cpp:157-160)
-                eval_xyz<O>(c, Tk, cur);
-                put(row, cur);
-            }
-            if (dropped && flags) atomicOr(flags + b0 + t, 2u);
-        };
-        for (int r0 = 0; r0 < nseg; r0 += 2 * SCAN_THREADS) {
-            const int ra = r0 + tid, rb = r0 + 2 * SCAN_THREADS - 1 - tid;
-            if (ra < nseg) write_segment(perm[ra]);
-            if (rb < nseg) write_segment(perm[rb]);
         }
         __syncthreads();  // smem is reused by the next tile
         SCAN_STAMP();

@@ -189,8 +189,9 @@ class TrajectoryGeneratorTool:
         return json.loads(buf.value.decode())
 
     def debug_phase_clocks(self, enable: bool, read: bool = False):
-        """Developer instrumentation: arm / read the fused kernel's per-phase clock stamps ([4096,16] int64)."""
-        out = np.zeros((4096, 16), dtype=np.int64) if read else None
+        """Developer instrumentation: arm / read the per-phase clock stamps ([8192,16] int64: rows 0..4095 fused-solve
+        CTAs, rows 4096.. sampler tiles)."""
+        out = np.zeros((8192, 16), dtype=np.int64) if read else None
         self._check(self._L.msnap_debug_phase_clocks(self._h, int(enable), _ptr(out)))
         return out
 

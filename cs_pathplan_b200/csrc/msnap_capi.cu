@@ -1033,11 +1033,11 @@ int msnap_profile_end(msnap_handle h, char *json_out, long long capacity) {
 
 // ---------------------------------------------------------------------------------------------- dev instrumentation
 // Not part of the drop-in boundary: lets the developer see where a fused-kernel CTA spends its cycles.
-// enable != 0 allocates a [4096][16] clock buffer that the next fused launches fill; out (host, 4096*16 int64) reads it.
+// enable != 0 allocates a [8192][16] clock buffer that the next launches fill; out (host, 8192*16 int64) reads it.
 int msnap_debug_phase_clocks(msnap_handle h, int enable, long long *out) {
     if (!h) return MSNAP_ERR_INVALID_ARG;
     DeviceGuard guard(h->device);
-    const size_t bytes = 4096 * 16 * sizeof(long long);
+    const size_t bytes = 8192 * 16 * sizeof(long long);  // rows 0..4095: fused-solve CTAs, 4096..8191: sampler tiles
     if (out && h->phase_clocks) {
         MS_CUDA(h, cudaStreamSynchronize(h->stream));
         MS_CUDA(h, cudaMemcpy(out, h->phase_clocks, bytes, cudaMemcpyDeviceToHost));

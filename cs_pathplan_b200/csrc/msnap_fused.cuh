@@ -53,6 +53,7 @@ struct FusedParams {
     unsigned *flags;
     double *state_ws;        // [gridDim.x][ns-1][NSTATE][FUSED_SLOT_LANES]
     long long *phase_clocks; // optional [gridDim.x][16]: clock64() of thread 0 after each phase of the CTA's first tile
+                             // (columns 0..9) and (forward end, backward end) of speculative lanes 0, 64, 128 (10..15)
 };
 
 // Shared-memory layout of one trajectory block (offsets in doubles).  Row pitches are odd so that the
@@ -246,14 +247,13 @@ __device__ __noinline__ bool fused_chain(const double *blk, int ns, double add00
     using D = Dim<O>;
     const FusedSmem<O> L(ns);
     const FBaseRows<O> base_at{blk + L.oBase};
-    if (clk) clk[0] = clock64();
     const bool ok = thomas_forward<O>(ns - 1, add00, base_at, state_at);
-    if (clk) clk[1] = clock64();
+    if (clk) clk[0] = clock64();
     const FSegxRows<O> segx_at{blk + L.oSegx};
     const FPos pos{blk + L.oP};
     *max_dev_out = thomas_backward<O, EVAL, EARLY>(ns - 1, state_at, xout, segx_at, pos, blk + L.oBC,
                                                    blk + L.oBC + D::NR);
-    if (clk) clk[2] = clock64();
+    if (clk) clk[1] = clock64();
     return ok;
 }
 
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_c
     int stamp = 0;
 #define MSNAP_STAMP()                                                                              \
     do {                                                                                           \
-        if (p.phase_clocks && tid == 0 && tile == blockIdx.x && stamp < 7)                        \
+        if (p.phase_clocks && tid == 0 && tile == blockIdx.x && stamp < 10)                        \
             p.phase_clocks[blockIdx.x * 16 + stamp++] = clock64();                                 \
     } while (0)
 
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_c
                 const FStateRows<O, GL, L2KeepMem> st{slot + tid};
                 long long *clk = nullptr;  // dev instrumentation: lanes 0, 64 and 128 of the CTA's first tile
                 if (p.phase_clocks && tile == blockIdx.x && (tid & 63) == 0)
-                    clk = p.phase_clocks + blockIdx.x * 16 + 7 + 3 * (tid >> 6);
+                    clk = p.phase_clocks + blockIdx.x * 16 + 10 + 2 * (tid >> 6);
                 double mdv;
                 const bool ok = fused_chain<O, true, true>(smem + t * tstride, ns, add00, st, NoOut{}, &mdv, clk);
                 md[t * nit + q] = mdv;

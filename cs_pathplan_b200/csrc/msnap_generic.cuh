@@ -673,7 +673,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_sample_scan(
 #define SCAN_STAMP()                                                                   \
     do {                                                                               \
         if (phase_clocks && tid == 0 && tile < 4096 && stamp < 8)                      \
-            phase_clocks[tile * 16 + 8 + stamp++] = clock64();                         \
+            phase_clocks[(4096 + tile) * 16 + stamp++] = clock64();                         \
     } while (0)
         SCAN_STAMP();
         const long long b0 = tile * tpt;

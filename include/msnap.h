@@ -154,7 +154,8 @@ int msnap_profile_begin(msnap_handle h);
 int msnap_profile_end(msnap_handle h, char *json_out, long long capacity);
 
 /* Developer instrumentation (not needed by an integrator): per-CTA clock64() stamps after each phase of the fused
- * kernel's first tile.  enable != 0 arms a device buffer [4096][16]; out != NULL copies the last stamps to the host. */
+ * kernel's first tile (rows 0..4095) and of the sampler's tiles (rows 4096..8191).  enable != 0 arms a device buffer
+ * [8192][16]; out != NULL copies the last stamps to the host. */
 int msnap_debug_phase_clocks(msnap_handle h, int enable, long long *out);
 
 /* ---- micro-benchmarks used for the roofline denominators (bench.py) --------------------------------------- */

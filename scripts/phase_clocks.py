@@ -1,12 +1,15 @@
-"""Developer tool: where does a fused-kernel CTA spend its time?  (clock64 stamps after every phase barrier)"""
+"""Developer tool: where do the fused solve kernel and the sampler kernel spend their time?  (clock64 stamps)"""
 import sys; sys.path.insert(0, ".")
 import numpy as np, torch
 from cs_pathplan_b200 import TrajectoryGeneratorTool, workloads
-names_pw = ["load", "times", "rows1", "thomas1", "search", "probes+rows2", "selinit"]
-names_plain = ["load", "times", "rows", "selinit"]
+GHZ = 1.9e3  # cycles per microsecond at the clock the stamps were taken (approximate)
+names_pw = ["load", "times", "rows1", "thomas1", "search", "probes+rows2", "spec+select", "outputs+coeff"]
+names_plain = ["load", "times", "rows", "solve+select", "outputs+coeff"]
+scan_names = ["sort+count", "rows", "scan+expand+lookback", "write"]
 tool = TrajectoryGeneratorTool(0)
+cases = [(4096, 16), (1 << 15, 8)] if len(sys.argv) < 2 else [(int(sys.argv[1]), int(sys.argv[2]))]
 for weights in ("shipped", "plain"):
-    for B, ns in ((4096, 16), (1 << 15, 8)):
+    for B, ns in cases:
         cfg = workloads.synthetic_config(4, weights)
         wp = workloads.random_walks(B, ns, 1234)
         cap = tool.sample_bound(cfg, wp, ns=ns)
@@ -14,24 +17,21 @@ for weights in ("shipped", "plain"):
         tool.debug_phase_clocks(True)
         tool.generate_batch(cfg, wp, ns=ns, capacity=cap)
         c = tool.debug_phase_clocks(True, read=True)
-        c = c[c[:, 0] > 0]
+        f = c[:4096]; f = f[f[:, 0] > 0]
         names = names_pw if weights == "shipped" else names_plain
-        d = np.diff(c[:, : len(names) + 1], axis=1) / 1.9e3   # us at ~1.9 GHz
-        print(f"{weights} B={B} ns={ns}: CTAs {len(c)}  span of first tiles {(c[:, len(names)].max() - c[:, 0].min()) / 1.9e3:.1f} us")
+        d = np.diff(f[:, : len(names) + 1], axis=1) / GHZ
+        print(f"{weights} B={B} ns={ns}: fused CTAs {len(f)}, first tile {((f[:, len(names)] - f[:, 0]) / GHZ).mean():.1f} us mean, "
+              f"span {(f[:, len(names)].max() - f[:, 0].min()) / GHZ:.1f} us")
+        print("   " + "  ".join(f"{n} {m:.1f}" for n, m in zip(names, d.mean(0))))
         if weights == "shipped":
             for w in range(3):
-                f = (c[:, 8 + 3 * w] - c[:, 7 + 3 * w]) / 1.9e3; b = (c[:, 9 + 3 * w] - c[:, 8 + 3 * w]) / 1.9e3
-                s0 = (c[:, 7 + 3 * w] - c[:, 6]) / 1.9e3
-                print("   spec lane %3d: starts %.1f us after rows2 barrier, forward %.1f us, backward %.1f us" % (64 * w, s0.mean(), f.mean(), b.mean()))
-        sc = tool.debug_phase_clocks(True, read=True) if False else c
-        full = sc
-        rest = np.diff(c, axis=1)[:, len(names):] / 1.9e3
-        rest = np.where(rest > 0, rest, 0)
-        print("   " + "  ".join(f"{n} {m:.1f}" for n, m in zip(names, d.mean(0))), " | then", np.round(rest.mean(0)[:8], 1))
-# sampler kernel phases (stamps in columns 8..13 of rows indexed by tile)
-cfg = workloads.synthetic_config(4, "plain"); wp = workloads.random_walks(4096, 16, 1234); cap = tool.sample_bound(cfg, wp, ns=16)
-tool.debug_phase_clocks(True); tool.generate_batch(cfg, wp, ns=16, capacity=cap); c = tool.debug_phase_clocks(True, read=True)
-c = c[:512, 8:14]; d = np.diff(c, axis=1) / 1.9e3
-print("sampler tiles:", len(c), " phases [sort, A count, B traj, C lookback, D write] us mean:", np.round(d.mean(0), 1), " max:", np.round(d.max(0), 1),
-      " span:", round((c[:, -1].max() - c[:, 0].min()) / 1.9e3, 1))
+                fe, be = f[:, 10 + 2 * w], f[:, 11 + 2 * w]
+                ok = fe > 0
+                if ok.any():
+                    print("   spec lane %3d: forward ends %.1f us after the rows2 barrier, backward takes %.1f us" %
+                          (64 * w, ((fe - f[:, 6])[ok] / GHZ).mean(), ((be - fe)[ok] / GHZ).mean()))
+        s = c[4096:]; s = s[s[:, 0] > 0][:, :5]
+        ds = np.diff(s, axis=1) / GHZ
+        print(f"   sampler tiles {len(s)}: " + "  ".join(f"{n} {m:.1f} (max {x:.1f})" for n, m, x in zip(scan_names, ds.mean(0), ds.max(0))) +
+              f"  span {(s[:, -1].max() - s[:, 0].min()) / GHZ:.1f} us")
 tool.debug_phase_clocks(False)

@@ -224,12 +224,28 @@ struct SolveWs {
     double *T, *base, *state, *segx, *coeff;
     int *s_star;
     FusedPlan fused;
+    // speculative reweighting loop of the generic path (nullptr: sequential loop)
+    double *spec_state = nullptr, *md_ws = nullptr, *md_last = nullptr;
+    int *ok_ws = nullptr;
+    unsigned *flag_last = nullptr;
 };
+constexpr int SPEC_NIT1 = 10;                         // speculative iterations of the generic path (max_iter = 10)
+constexpr size_t SPEC_WS_LIMIT = (size_t)24 << 30;    // beyond this the generic path falls back to the sequential loop
 
 template <int O>
-size_t solve_ws_bytes(long long n_seg, bool need_T, bool need_coeff, const FusedPlan &f) {
+bool use_generic_spec(const msnap_context *h, long long n_seg, const SolveParams &sp) {
+    return h->policy != 1 && sp.pw > 0.0 && sp.max_iter == SPEC_NIT1 &&
+           (size_t)(n_seg + 1) * Dim<O>::NSTATE * SPEC_NIT1 * sizeof(double) <= SPEC_WS_LIMIT;
+}
+
+template <int O>
+size_t solve_ws_bytes(long long n_seg, long long B, bool need_T, bool need_coeff, const FusedPlan &f, bool spec) {
     using D = Dim<O>;
     size_t b = 0;
+    if (f.tpc == 0 && spec)
+        b += padded((size_t)(n_seg + 1) * D::NSTATE * SPEC_NIT1 * sizeof(double)) +
+             padded((size_t)B * SPEC_NIT1 * sizeof(double)) + padded((size_t)B * SPEC_NIT1 * sizeof(int)) +
+             padded(B * sizeof(double)) + padded(B * sizeof(unsigned));
     if (need_T) b += padded(n_seg * sizeof(double));
     if (f.tpc > 0) {  // fused path: only the per-CTA state slots (+ coefficients if the caller keeps none)
         b += padded(f.state_bytes + 256);
@@ -249,7 +265,10 @@ template <int O>
 int run_solve(msnap_context *h, const BatchIdx &bi, const SolveParams &sp, const SolveIO &io, SolveWs &w) {
     using D = Dim<O>;
     const int blk = 128;
-    const unsigned gs = grid_for(bi.n_seg, blk), gb = grid_for(bi.B, blk);
+    // Thread-per-trajectory sweeps touch 32 different cache lines per warp access, so they are bound by the L1 of the
+    // SMs they run on: small batches use one warp per CTA to spread over as many SMs as possible.
+    const int blk_b = bi.B >= 128LL * h->sm_count ? 128 : 32;
+    const unsigned gs = grid_for(bi.n_seg, blk), gb = grid_for(bi.B, blk_b);
     const double *ht = &h->d_tab[O - MSNAP_MIN_ORDER].HT[0][0];
     if (w.fused.tpc > 0) {  // uniform batch: one persistent launch for the whole closed-form solve
         const FusedPlan &f = w.fused;
@@ -305,13 +324,27 @@ int run_solve(msnap_context *h, const BatchIdx &bi, const SolveParams &sp, const
         MS_LAUNCH(h, (k_rows<O>), gs, blk, bi, sp, io.wp, T, false, (const int *)nullptr, ht, w.base, w.segx);
         SolveParams sp1 = sp;
         sp1.max_iter = 0;
-        MS_LAUNCH(h, (k_thomas<O>), gb, blk, bi, sp1, io.wp, w.base, w.state, w.segx, false, false,
+        MS_LAUNCH(h, (k_thomas<O>), gb, blk_b, bi, sp1, io.wp, w.base, w.state, w.segx, false, false,
                   (double *)nullptr, (int *)nullptr, (double *)nullptr, io.flags_out);
         MS_LAUNCH(h, (k_search<O>), gs, blk, bi, sp, io.wp, T, w.state, w.s_star);
     }
     MS_LAUNCH(h, (k_rows<O>), gs, blk, bi, sp, io.wp, T, use_pw, w.s_star, ht, w.base, w.segx);
-    MS_LAUNCH(h, (k_thomas<O>), gb, blk, bi, sp, io.wp, w.base, w.state, w.segx, use_pw, true, io.max_dev_out,
-              io.iters_out, io.vw_final_out, io.flags_out);
+    if (w.spec_state) {
+        // all reweighting iterations at once: iterations 0..9 as speculative lanes, the last one into the final state
+        MS_LAUNCH(h, (k_thomas_spec<O, SPEC_NIT1>), grid_for(bi.B * SPEC_NIT1, blk), blk, bi, sp, io.wp, w.base,
+                  w.spec_state, w.segx, w.md_ws, w.ok_ws);
+        MS_CUDA(h, cudaMemsetAsync(w.flag_last, 0, bi.B * sizeof(unsigned), h->stream));
+        SolveParams spl = sp;
+        spl.vw0 = reweighted_vw(sp.vw0, SPEC_NIT1);
+        spl.max_iter = 0;
+        MS_LAUNCH(h, (k_thomas<O>), gb, blk_b, bi, spl, io.wp, w.base, w.state, w.segx, true, true, w.md_last,
+                  (int *)nullptr, (double *)nullptr, w.flag_last);
+        MS_LAUNCH(h, (k_spec_select<O, SPEC_NIT1>), gb, blk_b, bi, sp, io.wp, w.spec_state, w.state, w.segx, w.md_ws,
+                  w.ok_ws, w.md_last, w.flag_last, io.max_dev_out, io.iters_out, io.vw_final_out, io.flags_out);
+    } else {
+        MS_LAUNCH(h, (k_thomas<O>), gb, blk_b, bi, sp, io.wp, w.base, w.state, w.segx, use_pw, true, io.max_dev_out,
+                  io.iters_out, io.vw_final_out, io.flags_out);
+    }
     MS_LAUNCH(h, (k_coeff<O>), gs, blk, bi, sp, io.wp, T, w.state, w.coeff, io.flags_out);
     if (io.times_out && io.times_out != T)
         MS_CUDA(h, cudaMemcpyAsync(io.times_out, T, bi.n_seg * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
@@ -320,9 +353,17 @@ int run_solve(msnap_context *h, const BatchIdx &bi, const SolveParams &sp, const
 }
 
 template <int O>
-void carve_solve_ws(Arena &a, long long n_seg, bool need_T, double *coeff_out, const FusedPlan &f, SolveWs &w) {
+void carve_solve_ws(Arena &a, long long n_seg, long long B, bool need_T, double *coeff_out, const FusedPlan &f, bool spec,
+                    SolveWs &w) {
     using D = Dim<O>;
     w.fused = f;
+    if (f.tpc == 0 && spec) {
+        w.spec_state = arena_take<double>(a, (size_t)(n_seg + 1) * D::NSTATE * SPEC_NIT1);
+        w.md_ws = arena_take<double>(a, (size_t)B * SPEC_NIT1);
+        w.ok_ws = arena_take<int>(a, (size_t)B * SPEC_NIT1);
+        w.md_last = arena_take<double>(a, B);
+        w.flag_last = arena_take<unsigned>(a, B);
+    }
     w.T = need_T ? arena_take<double>(a, n_seg) : nullptr;
     if (f.tpc > 0) {
         w.base = w.segx = nullptr;
@@ -448,10 +489,10 @@ int solve_qp_dev(msnap_context *h, double pw, double vw, long long B, int ns_uni
     sp.vel = vel;
     sp.acc = acc;
     const FusedPlan f = plan_fused<O>(h, bi, sp);
-    int rc = arena_reserve(h, h->ws, solve_ws_bytes<O>(n_seg, false, false, f));
+    int rc = arena_reserve(h, h->ws, solve_ws_bytes<O>(n_seg, B, false, false, f, false));
     if (rc) return rc;
     SolveWs w;
-    carve_solve_ws<O>(h->ws, n_seg, false, coeff_out, f, w);
+    carve_solve_ws<O>(h->ws, n_seg, B, false, coeff_out, f, false, w);
     SolveIO io;
     io.wp = wp;
     io.times_in = times;
@@ -479,11 +520,12 @@ int generate_dev(msnap_context *h, const msnap_config *cfg, double sd, double v_
         sp.bc[9 + a] = cfg->end_acc[a];
     }
     const FusedPlan f = plan_fused<O>(h, bi, sp);
-    int rc = arena_reserve(h, h->ws, solve_ws_bytes<O>(n_seg, true, coeff_out == nullptr, f) +
+    const bool spec = use_generic_spec<O>(h, n_seg, sp);
+    int rc = arena_reserve(h, h->ws, solve_ws_bytes<O>(n_seg, B, true, coeff_out == nullptr, f, spec) +
                                         sample_ws_bytes(n_seg, B, bi.ns_uniform, h->policy));
     if (rc) return rc;
     SolveWs w;
-    carve_solve_ws<O>(h->ws, n_seg, true, coeff_out, f, w);
+    carve_solve_ws<O>(h->ws, n_seg, B, true, coeff_out, f, spec, w);
     SampleWs s;
     carve_sample_ws(h->ws, n_seg, B, bi.ns_uniform, h->policy, h->sm_count, s);
     SolveIO io;

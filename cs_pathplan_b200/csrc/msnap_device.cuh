@@ -313,6 +313,7 @@ __device__ __forceinline__ bool thomas_forward(int n_rows, double add00, const B
     double W[NU];  // W_{j-1} = P U_{j-1}
     double z[NR];  // z_{j-1}, [r][axis]
     for (int j = 0; j < n_rows; ++j) {
+        if (j + 1 < n_rows) base_at.prefetch(j + 1);
         const double *b = base_at(j);
         double *s = state_at(j);
         double d[ND], r[NR];
@@ -383,6 +384,7 @@ struct NoOut {
     static constexpr int FS = 1;
     using Mem = PlainMem;
     __device__ __forceinline__ double *operator()(int) const { return nullptr; }
+    __device__ __forceinline__ void prefetch(int) const {}
 };
 
 // One backward step: x_j = z_j - W_j x_{j+1}  (xn = x_{j+1}; no coupling when !has_next).
@@ -467,6 +469,8 @@ __device__ __forceinline__ double thomas_backward(int n_rows, const StateAt stat
     bool first = true;                            // xb still holds the fixed end derivatives (no W coupling)
     // step: compute x of waypoint j+1 into `xo` from `xi` (= x of waypoint j+2), probe segment j+1
     auto step = [&](double (&xo)[NR], double (&po)[3], const double (&xi)[NR], const double (&pi)[3]) {
+        if (j >= 1) state_at.prefetch(j - 1);
+        if (EVAL) segx_at.prefetch(j);
         thomas_back_step<O, StateAt::FS, typename StateAt::Mem, XOut>(state_at(j), xout(j), !first, xi, xo);
         pos(j + 1, po);
         if (EVAL) m2 = fmax(m2, deviation_sq<O, SegxAt::FS>(segx_at(j + 1), po, xo, pi, xi));

@@ -83,12 +83,14 @@ struct FBaseRows {
     const double *p;
     static constexpr int FS = 1;
     __device__ __forceinline__ const double *operator()(int j) const { return p + j * FusedSmem<O>::BS; }
+    __device__ __forceinline__ void prefetch(int) const {}
 };
 template <int O>
 struct FSegxRows {
     const double *p;
     static constexpr int FS = 1;
     __device__ __forceinline__ const double *operator()(int k) const { return p + k * FusedSmem<O>::XS; }
+    __device__ __forceinline__ void prefetch(int) const {}
 };
 struct FPos {
     const double *p;
@@ -105,6 +107,7 @@ struct FStateRows {
     static constexpr bool ENABLED = true;  // usable as the solution sink of thomas_backward
     using Mem = MemT;
     __device__ __forceinline__ double *operator()(int j) const { return p + (size_t)j * (Dim<O>::NSTATE * LANES); }
+    __device__ __forceinline__ void prefetch(int) const {}
 };
 
 // segment time powers from smem: ip[e] = T^-e (e = 0..2o-1), pT[r] = T^r (r = 0..o-1)

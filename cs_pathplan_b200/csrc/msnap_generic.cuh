@@ -136,6 +136,13 @@ struct GlobalRows {
     static constexpr bool ENABLED = true;  // usable as the solution sink of thomas_backward
     using Mem = PlainMem;
     __device__ __forceinline__ double *operator()(int j) const { return p + (size_t)j * NF; }
+    // The sweeps are one dependent chain per thread, so a row's loads would otherwise pay the full L2/HBM latency:
+    // pull row j into L1 while the previous row is being computed.
+    __device__ __forceinline__ void prefetch(int j) const {
+        const char *q = reinterpret_cast<const char *>(p + (size_t)j * NF);
+#pragma unroll
+        for (int o = 0; o < NF * 8 + 127; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(q + o));
+    }
 };
 struct GlobalPos {  // waypoint positions of one trajectory, [w][3]
     const double *p;
@@ -194,6 +201,108 @@ __global__ void k_thomas(BatchIdx bi, SolveParams sp, const double *__restrict__
     if (iters_out) iters_out[b] = iter;
     if (vw_final_out) vw_final_out[b] = vw;
     if (flags && (!ok || !(max_dev == max_dev))) atomicOr(flags + b, 1u);
+}
+
+// ------------------------------------------------------------------------------------------------ speculative loop
+// The reweighting loop of ms.cpp:76-90 for CSR batches, all iterations at once (same idea as the fused kernel): the
+// velocity weights are a fixed sequence, so iteration q of trajectory b is an independent solve.
+//   k_thomas_spec : thread per (b, q), q = 0..NIT1-1 (all but the last iteration).  Sweep state in a workspace laid out
+//                   [row][field][q], so the NIT1 lanes of a trajectory read the same base row (one broadcast load)
+//                   and store NIT1 consecutive doubles.  Only the max deviation is kept, and the backward sweep stops at
+//                   the first segment safely above the 0.2 threshold (EARLY).
+//   k_thomas      : (above) solves the LAST iteration into the final state rows -- where almost every trajectory ends.
+//   k_spec_select : thread per trajectory: first iteration whose max_dev <= 0.2, or the last (ms.cpp:82); a trajectory that
+//                   stopped early replays that lane's backward sweep into the final state rows.
+template <int O, int NIT1>
+struct SpecRows {
+    double *p;  // this lane's column of the first row
+    static constexpr int FS = NIT1;
+    static constexpr bool ENABLED = true;
+    using Mem = PlainMem;
+    __device__ __forceinline__ double *operator()(int j) const { return p + (size_t)j * (Dim<O>::NSTATE * NIT1); }
+    __device__ __forceinline__ void prefetch(int) const {}
+};
+
+__host__ __device__ inline double reweighted_vw(double vw0, int q) {  // vel_zero_weight of iteration q (ms.cpp:83-87)
+    double vw = vw0;
+    for (int i = 0; i < q; ++i) vw = (vw < 1e-6) ? 0.01 : vw * 2.0;
+    return vw;
+}
+
+template <int O, int NIT1>
+__global__ void __launch_bounds__(128) k_thomas_spec(BatchIdx bi, SolveParams sp, const double *__restrict__ wp,
+                                                     double *base, double *spec_state, double *segx,
+                                                     double *__restrict__ md_ws, int *__restrict__ ok_ws) {
+    using D = Dim<O>;
+    constexpr int NR = D::NR;
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= bi.B * NIT1) return;
+    const long long b = idx / NIT1;
+    const int q = (int)(idx - b * NIT1);
+    const long long g0 = bi.seg_begin(b);
+    const int ns = (int)(bi.seg_begin(b + 1) - g0);
+    const int n_rows = ns - 1;
+    Boundary<O> bc;
+    boundary_of<O>(sp, b, bc);
+    double d0[NR], dN[NR];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int r = 1; r < O; ++r) {
+            d0[(r - 1) * 3 + a] = bc.y0[a][r];
+            dN[(r - 1) * 3 + a] = bc.yN[a][r];
+        }
+    const GlobalRows<D::NBASE> base_at{base + (g0 + 1) * D::NBASE};
+    const SpecRows<O, NIT1> state_at{spec_state + (size_t)(g0 + 1) * D::NSTATE * NIT1 + q};
+    const GlobalRows<D::NSEGX> segx_at{segx + g0 * D::NSEGX};
+    const GlobalPos pos{wp + 3 * (g0 + b)};
+    const double vw = reweighted_vw(sp.vw0, q);
+    const double add00 = vw > 0.0 ? 2.0 * vw : 0.0;
+    const bool ok = thomas_forward<O>(n_rows, add00, base_at, state_at);
+    const double md = thomas_backward<O, true, true>(n_rows, state_at, NoOut{}, segx_at, pos, d0, dN);
+    md_ws[idx] = md;
+    ok_ws[idx] = ok ? 1 : 0;
+}
+
+template <int O, int NIT1>
+__global__ void k_spec_select(BatchIdx bi, SolveParams sp, const double *__restrict__ wp, double *spec_state,
+                              double *state, double *segx, const double *__restrict__ md_ws,
+                              const int *__restrict__ ok_ws, const double *__restrict__ md_last,
+                              const unsigned *__restrict__ flag_last, double *__restrict__ max_dev_out, int *__restrict__ iters_out,
+                              double *__restrict__ vw_final_out, unsigned *__restrict__ flags) {
+    using D = Dim<O>;
+    constexpr int NR = D::NR;
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= bi.B) return;
+    int q = 0;
+    while (q < NIT1 && md_ws[b * NIT1 + q] > 0.2) ++q;  // q == NIT1: the last iteration (already in `state`)
+    double md = md_last[b];
+    bool ok = flag_last[b] == 0u;
+    if (q < NIT1) {
+        md = md_ws[b * NIT1 + q];  // exact: a sweep that passes the test never left early
+        ok = ok_ws[b * NIT1 + q] != 0;
+        const long long g0 = bi.seg_begin(b);
+        const int n_rows = (int)(bi.seg_begin(b + 1) - g0) - 1;
+        Boundary<O> bc;
+        boundary_of<O>(sp, b, bc);
+        double d0[NR], dN[NR];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int r = 1; r < O; ++r) {
+                d0[(r - 1) * 3 + a] = bc.y0[a][r];
+                dN[(r - 1) * 3 + a] = bc.yN[a][r];
+            }
+        const SpecRows<O, NIT1> from{spec_state + (size_t)(g0 + 1) * D::NSTATE * NIT1 + q};
+        const GlobalRows<D::NSTATE> to{state + (g0 + 1) * D::NSTATE};
+        const GlobalRows<D::NSEGX> segx_at{segx + g0 * D::NSEGX};
+        const GlobalPos pos{wp + 3 * (g0 + b)};
+        thomas_backward<O, false, false>(n_rows, from, to, segx_at, pos, d0, dN);
+    }
+    if (max_dev_out) max_dev_out[b] = md;
+    if (iters_out) iters_out[b] = q;
+    if (vw_final_out) vw_final_out[b] = reweighted_vw(sp.vw0, q);
+    if (flags && (!ok || !(md == md))) atomicOr(flags + b, 1u);  // status of the selected iteration only
 }
 
 // Endpoint derivative vectors of segment g = (b, k) from the boundary data and the solved rows.

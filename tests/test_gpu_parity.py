@@ -135,3 +135,24 @@ def test_fused_kernel_equals_generic_path(tool, order, ns, weights):
     fus = tool.generate_batch(cfg, wp, ns=ns)
     for name in ("times", "coeff", "max_dev", "iters", "vw_final", "best_s", "sample_offset", "samples", "stats", "flags"):
         assert np.array_equal(getattr(gen, name), getattr(fus, name)), name
+
+
+@pytest.mark.parametrize("order", [2, 3, 4, 5])
+def test_speculative_generic_path_equals_sequential_loop(tool, order):
+    """CSR batches solve all reweighting iterations at once (k_thomas_spec + k_spec_select); the sequential loop of
+    policy 1 is the same arithmetic, so every output must agree bit for bit -- including trajectories that stop early."""
+    wp, so = workloads.cfg5(B=96, seed=40 + order, ns_min=1, ns_max=48)
+    for weights, pw in (("shipped", None), ("shipped", 3e-4)):       # the larger path weight makes some stop early
+        cfg = workloads.synthetic_config(order, weights)
+        if pw is not None:
+            cfg.path_weight = pw
+        tool.set_reweight_policy(1)
+        try:
+            seq = tool.generate_batch(cfg, wp, seg_offset=so)
+        finally:
+            tool.set_reweight_policy(0)
+        spec = tool.generate_batch(cfg, wp, seg_offset=so)
+        for name in ("times", "coeff", "max_dev", "iters", "vw_final", "best_s", "sample_offset", "samples", "stats", "flags"):
+            assert np.array_equal(getattr(seq, name), getattr(spec, name)), (name, pw)
+        if pw is not None and order <= 4:
+            assert len(set(seq.iters.tolist())) > 1                   # the early-stop branch is really exercised

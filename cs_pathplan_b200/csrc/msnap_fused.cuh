@@ -404,30 +404,33 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_c
         __syncthreads();
         MSNAP_STAMP();
         // ---- speculative Thomas over (trajectory, reweighting iteration).
-        // Lanes [0, nt*(nit-1)) solve iterations 0..nit-2 with their sweep state in the CTA's global scratch slot and
-        // keep only the max deviation.  The LAST iteration -- the one most trajectories end on -- is solved by a
+        // nt*(nit-1) speculative lanes solve iterations 0..nit-2 with their sweep state in the CTA's global scratch slot
+        // and keep only the max deviation.  The LAST iteration -- the one most trajectories end on -- is solved by a
         // separate warp-aligned group of nt lanes in the shared-memory state rows (idle since the search) and leaves
         // its x there, ready for the coefficient phase.  With a single solve per trajectory (nit == 1: no penalty, or
         // a bare SolveQPClosedForm) only that group runs.  Keeping the two groups in different warps avoids
         // executing both code paths in every warp.
         {
+            // The last-iteration group sits in warp 0 .. (the CTA's oldest warps, which the scheduler favours): its
+            // full backward sweep is the longest chain of this phase.  Speculative lanes start at the next warp boundary.
             const int n_glob = nt * (nit - 1);
-            const int sl0 = (tpc * (nit - 1) + 31) & ~31;  // first lane of the shared-memory group
-            if (tid < n_glob) {
-                const int t = tid / (nit - 1), q = tid - t * (nit - 1);
+            const int g0l = (tpc + 31) & ~31;  // first speculative lane
+            if (tid >= g0l && tid < g0l + n_glob) {
+                const int l = tid - g0l;
+                const int t = l / (nit - 1), q = l - t * (nit - 1);
                 double vw = p.sp.vw0;
                 for (int i = 0; i < q; ++i) vw = (vw < 1e-6) ? 0.01 : vw * 2.0;
                 const double add00 = vw > 0.0 ? 2.0 * vw : 0.0;
-                const FStateRows<O, GL, L2KeepMem> st{slot + tid};
-                long long *clk = nullptr;  // dev instrumentation: lanes 0, 64 and 128 of the CTA's first tile
-                if (p.phase_clocks && tile == blockIdx.x && (tid & 63) == 0)
-                    clk = p.phase_clocks + blockIdx.x * 16 + 10 + 2 * (tid >> 6);
+                const FStateRows<O, GL, L2KeepMem> st{slot + l};
+                long long *clk = nullptr;  // dev instrumentation: speculative lanes 0, 64 and 128 of the CTA's first tile
+                if (p.phase_clocks && tile == blockIdx.x && (l & 63) == 0)
+                    clk = p.phase_clocks + blockIdx.x * 16 + 10 + 2 * (l >> 6);
                 double mdv;
                 const bool ok = fused_chain<O, true, true>(smem + t * tstride, ns, add00, st, NoOut{}, &mdv, clk);
                 md[t * nit + q] = mdv;
                 okf[t * nit + q] = ok ? 1 : 0;
-            } else if (tid >= sl0 && tid < sl0 + nt) {
-                const int t = tid - sl0, q = nit - 1;
+            } else if (tid < nt) {
+                const int t = tid, q = nit - 1;
                 double vw = p.sp.vw0;
                 for (int i = 0; i < q; ++i) vw = (vw < 1e-6) ? 0.01 : vw * 2.0;
                 const double add00 = vw > 0.0 ? 2.0 * vw : 0.0;
@@ -448,10 +451,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_c
             __syncthreads();
             // a trajectory that stopped early: the lane that solved that iteration replays its backward sweep, this
             // time leaving the solution in the shared-memory state rows
-            if (tid < n_glob) {
-                const int t = tid / (nit - 1), q = tid - t * (nit - 1);
+            if (tid >= g0l && tid < g0l + n_glob) {
+                const int l = tid - g0l;
+                const int t = l / (nit - 1), q = l - t * (nit - 1);
                 if (sel[t] == q) {
-                    const FStateRows<O, GL, L2KeepMem> st{slot + tid};
+                    const FStateRows<O, GL, L2KeepMem> st{slot + l};
                     const FStateRows<O, SL> xo{state1 + t};
                     fused_replay<O>(smem + t * tstride, ns, st, xo);
                 }

@@ -176,10 +176,11 @@ FusedPlan plan_fused(msnap_context *h, const BatchIdx &bi, const SolveParams &sp
     const size_t st1 = (size_t)(ns - 1) * D::NSTATE * FUSED_SMEM_LANES * sizeof(double);  // shared-memory state rows
     auto smem_for = [&](int tpc) { return tpc * blk + st1 + (size_t)tpc * nit * 12 + (size_t)tpc * 8 + 16; };
     const size_t hard = 220 * 1024;
-    // lanes: tpc lanes for the last iteration in the first warp(s), then tpc * (nit - 1) speculative lanes
-    int tmax = FUSED_SMEM_LANES;
-    while (tmax > 1 && ((tmax + 31) & ~31) + tmax * (nit - 1) > FUSED_THREADS) --tmax;
-    if (((tmax + 31) & ~31) + tmax * (nit - 1) > FUSED_THREADS) return f;
+    // lanes: 2 * tpc lanes (one pair per trajectory, within ONE warp) for the last iteration, then, from the next warp
+    // boundary, tpc * (nit - 1) speculative lanes
+    int tmax = FUSED_SMEM_LANES < 16 ? FUSED_SMEM_LANES : 16;
+    while (tmax > 1 && 32 + tmax * (nit - 1) > FUSED_THREADS) --tmax;
+    if (32 + tmax * (nit - 1) > FUSED_THREADS) return f;
     if ((long long)tmax > bi.B) tmax = (int)bi.B;
     // Pick the tile size that needs the fewest waves of resident CTAs (the kernel is latency-bound per tile, so a
     // partial second wave costs a whole tile latency); among those, the largest tile (best lane utilisation).

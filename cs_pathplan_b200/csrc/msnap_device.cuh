@@ -304,43 +304,75 @@ struct L2KeepMem {
     }
 };
 
+// ---- twisted (two-sided) elimination ---------------------------------------------------------------------------
+// The chain of n block rows is split at a row m and eliminated from BOTH ends towards it:
+//   top half     rows 0 .. m-1      D'_j = D_j - U_{j-1}' W_{j-1},  z_j = P_j (r_j - U_{j-1}' z_{j-1}),  W_j = P_j U_j
+//   bottom half  rows n-1 .. m+1    D'_j = D_j - U_j W_{j+1},       z_j = P_j (r_j - U_j z_{j+1}),       W_j = P_j U_{j-1}'
+//   split row m                     D*  = D_m - U_{m-1}' W_{m-1} - U_m W_{m+1},  x_m = D*^-1 (r_m - U_{m-1}' z_{m-1} - U_m z_{m+1})
+// and substituted back outwards:  x_j = z_j - W_j x_{j+1} (j < m),  x_j = z_j - W_j x_{j-1} (j > m).
+// Every pivot block is a Schur complement of the SPD matrix, hence SPD.  The bottom half is the top-half recurrence
+// applied to the MIRRORED chain (row i of the mirrored chain = row n-1-i, coupling blocks transposed), so one routine
+// with a `mirror` flag that only enters address computations serves both.  The two halves are independent until the
+// split row: two lanes can each take one (the latency-critical chains of the fused kernel do, with m = n/2), or one lane
+// runs them in turn -- the operations, and therefore the bits, are the same.
+//   m = n/2 : the balanced split (pass 1, a bare solve, the last reweighting iteration)
+//   m = n-1 : everything in the top half = plain downward block Thomas; the back-substitution then starts at the LAST
+//             segment, whose deviation usually decides the reweighting test at once (speculative iterations).
+__host__ __device__ constexpr int split_row(int n_rows, bool balanced) { return balanced ? n_rows / 2 : n_rows - 1; }
+
+// coupling block of a base row in the orientation the recurrences use: C[t][p] = U[t][p], or U[p][t] when transposed
+template <int O, int BFS>
+__device__ __forceinline__ void load_coupling(const double *b, bool transposed, double (&C)[(O - 1) * (O - 1)]) {
+    using D = Dim<O>;
+    constexpr int B = D::B;
+#pragma unroll
+    for (int t = 0; t < B; ++t)
+#pragma unroll
+        for (int p = 0; p < B; ++p) C[t * B + p] = b[(D::F_U + (transposed ? p * B + t : t * B + p)) * BFS];
+}
+
+// Elimination of one half: local rows i = 0 .. cnt-1, outermost first; row index j = mirror ? n_rows-1-i : i.
+// Returns false if a pivot block was not positive definite.
 template <int O, class BaseAt, class StateAt>
-__device__ __forceinline__ bool thomas_forward(int n_rows, double add00, const BaseAt base_at, const StateAt state_at) {
+__device__ __forceinline__ bool elim_half(int n_rows, int cnt, bool mirror, double add00, const BaseAt base_at,
+                                          const StateAt state_at) {
     using D = Dim<O>;
     constexpr int B = D::B, ND = D::ND, NR = D::NR, NU = D::NU;
     constexpr int bfs = BaseAt::FS, sfs = StateAt::FS;
     bool ok = true;
-    double W[NU];  // W_{j-1} = P U_{j-1}
-    double z[NR];  // z_{j-1}, [r][axis]
-    for (int j = 0; j < n_rows; ++j) {
-        if (j + 1 < n_rows) base_at.prefetch(j + 1);
+    double W[NU];  // W of the previously eliminated row
+    double z[NR];  // z of the previously eliminated row, [r][axis]
+    const int step = mirror ? -1 : 1;
+    int j = mirror ? n_rows - 1 : 0;
+    for (int i = 0; i < cnt; ++i, j += step) {
+        base_at.prefetch(j + step);  // the next row towards the split row (which always exists)
         const double *b = base_at(j);
         double *s = state_at(j);
         double d[ND], r[NR];
 #pragma unroll
-        for (int i = 0; i < ND; ++i) d[i] = b[(D::F_D + i) * bfs];
+        for (int k = 0; k < ND; ++k) d[k] = b[(D::F_D + k) * bfs];
 #pragma unroll
-        for (int i = 0; i < NR; ++i) r[i] = b[(D::F_R + i) * bfs];
+        for (int k = 0; k < NR; ++k) r[k] = b[(D::F_R + k) * bfs];
         d[0] += add00;
-        if (j > 0) {
-            const double *bp = base_at(j - 1);  // U_{j-1} is re-read (a broadcast LDS) rather than carried
-            double U[NU];
-#pragma unroll
-            for (int i = 0; i < NU; ++i) U[i] = bp[(D::F_U + i) * bfs];
+        if (i > 0) {
+            // coupling to the previously eliminated row: U_{j-1} (stored in row j-1), or U_j' (row j) when mirrored;
+            // re-read (a broadcast LDS) rather than carried in registers
+            double C[NU];
+            load_coupling<O, bfs>(mirror ? b : base_at(j - 1), mirror, C);
 #pragma unroll
             for (int p = 0; p < B; ++p) {
 #pragma unroll
                 for (int q = 0; q <= p; ++q) {
                     double acc = d[sym(p, q)];
 #pragma unroll
-                    for (int t = 0; t < B; ++t) acc = fma(-U[t * B + p], W[t * B + q], acc);
+                    for (int t = 0; t < B; ++t) acc = fma(-C[t * B + p], W[t * B + q], acc);
                     d[sym(p, q)] = acc;
                 }
 #pragma unroll
                 for (int x = 0; x < 3; ++x) {
                     double acc = r[p * 3 + x];
 #pragma unroll
-                    for (int t = 0; t < B; ++t) acc = fma(-U[t * B + p], z[t * 3 + x], acc);
+                    for (int t = 0; t < B; ++t) acc = fma(-C[t * B + p], z[t * 3 + x], acc);
                     r[p * 3 + x] = acc;
                 }
             }
@@ -357,28 +389,97 @@ __device__ __forceinline__ bool thomas_forward(int n_rows, double add00, const B
                 z[p * 3 + x] = acc;
             }
 #pragma unroll
-        for (int i = 0; i < NR; ++i) StateAt::Mem::st(s + (D::SX + i) * sfs, z[i]);
-        if (j + 1 < n_rows) {
-            double U[NU];
-#pragma unroll
-            for (int i = 0; i < NU; ++i) U[i] = b[(D::F_U + i) * bfs];
+        for (int k = 0; k < NR; ++k) StateAt::Mem::st(s + (D::SX + k) * sfs, z[k]);
+        {
+            // coupling to the next row towards the split row: U_j (row j), or U_{j-1}' (row j-1) when mirrored
+            double N[NU];
+            load_coupling<O, bfs>(mirror ? base_at(j - 1) : b, mirror, N);
 #pragma unroll
             for (int p = 0; p < B; ++p)
 #pragma unroll
                 for (int q = 0; q < B; ++q) {
-                    double acc = P[sym(p, 0)] * U[q];
+                    double acc = P[sym(p, 0)] * N[q];
 #pragma unroll
-                    for (int t = 1; t < B; ++t) acc = fma(P[sym(p, t)], U[t * B + q], acc);
+                    for (int t = 1; t < B; ++t) acc = fma(P[sym(p, t)], N[t * B + q], acc);
                     W[p * B + q] = acc;
                 }
 #pragma unroll
-            for (int i = 0; i < NU; ++i) StateAt::Mem::st(s + (D::SW + i) * sfs, W[i]);
+            for (int k = 0; k < NU; ++k) StateAt::Mem::st(s + (D::SW + k) * sfs, W[k]);
         }
     }
     return ok;
 }
 
-// Where the backward sweep leaves the solution.  NoOut: nowhere (a speculative lane only needs its max deviation).
+// The split row m receives both halves (from the state rows m-1 and m+1) and is solved for x_m, which is left in the SX
+// field of state row m.
+template <int O, class BaseAt, class StateAt>
+__device__ __forceinline__ bool elim_middle(int n_rows, int m, double add00, const BaseAt base_at,
+                                            const StateAt state_at) {
+    using D = Dim<O>;
+    constexpr int B = D::B, ND = D::ND, NR = D::NR, NU = D::NU;
+    constexpr int bfs = BaseAt::FS, sfs = StateAt::FS;
+    const double *b = base_at(m);
+    double d[ND], r[NR];
+#pragma unroll
+    for (int k = 0; k < ND; ++k) d[k] = b[(D::F_D + k) * bfs];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) r[k] = b[(D::F_R + k) * bfs];
+    d[0] += add00;
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {  // 0: last row of the top half (m-1), 1: last row of the bottom half (m+1)
+        if (side == 0 ? m > 0 : m < n_rows - 1) {
+            const double *sn = state_at(side == 0 ? m - 1 : m + 1);
+            double C[NU], W[NU], z[NR];
+            load_coupling<O, bfs>(side == 0 ? base_at(m - 1) : b, side != 0, C);
+#pragma unroll
+            for (int k = 0; k < NU; ++k) W[k] = StateAt::Mem::ld(sn + (D::SW + k) * sfs);
+#pragma unroll
+            for (int k = 0; k < NR; ++k) z[k] = StateAt::Mem::ld(sn + (D::SX + k) * sfs);
+#pragma unroll
+            for (int p = 0; p < B; ++p) {
+#pragma unroll
+                for (int q = 0; q <= p; ++q) {
+                    double acc = d[sym(p, q)];
+#pragma unroll
+                    for (int t = 0; t < B; ++t) acc = fma(-C[t * B + p], W[t * B + q], acc);
+                    d[sym(p, q)] = acc;
+                }
+#pragma unroll
+                for (int x = 0; x < 3; ++x) {
+                    double acc = r[p * 3 + x];
+#pragma unroll
+                    for (int t = 0; t < B; ++t) acc = fma(-C[t * B + p], z[t * 3 + x], acc);
+                    r[p * 3 + x] = acc;
+                }
+            }
+        }
+    }
+    double P[ND];
+    const bool ok = sym_inverse<B>(d, P);
+    double *s = state_at(m);
+#pragma unroll
+    for (int p = 0; p < B; ++p)
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            double acc = P[sym(p, 0)] * r[x];
+#pragma unroll
+            for (int t = 1; t < B; ++t) acc = fma(P[sym(p, t)], r[t * 3 + x], acc);
+            StateAt::Mem::st(s + (D::SX + p * 3 + x) * sfs, acc);
+        }
+    return ok;
+}
+
+// One lane doing the whole elimination: top half, bottom half, split row.
+template <int O, class BaseAt, class StateAt>
+__device__ __forceinline__ bool thomas_forward(int n_rows, int m, double add00, const BaseAt base_at,
+                                               const StateAt state_at) {
+    if (n_rows <= 0) return true;
+    bool ok = elim_half<O>(n_rows, m, false, add00, base_at, state_at);
+    ok = elim_half<O>(n_rows, n_rows - 1 - m, true, add00, base_at, state_at) && ok;
+    return elim_middle<O>(n_rows, m, add00, base_at, state_at) && ok;
+}
+
+// Where the back-substitution leaves the solution.  NoOut: nowhere (a speculative lane only needs its max deviation).
 struct NoOut {
     static constexpr bool ENABLED = false;
     static constexpr int FS = 1;
@@ -387,115 +488,135 @@ struct NoOut {
     __device__ __forceinline__ void prefetch(int) const {}
 };
 
-// One backward step: x_j = z_j - W_j x_{j+1}  (xn = x_{j+1}; no coupling when !has_next).
+// One back-substitution step: x_j = z_j - W_j x_n  (x_n = the solution of the neighbouring row nearer to the split row).
 //   s: state row j (z, W) with field stride SFS;
 //   xo: where x_j is stored ([r][axis], field stride XOut::FS) if XOut::ENABLED.
 template <int O, int SFS, class SMem, class XOut>
-__device__ __forceinline__ void thomas_back_step(const double *s, double *xo, bool has_next,
-                                                 const double (&xn)[3 * (O - 1)], double (&x)[3 * (O - 1)]) {
+__device__ __forceinline__ void thomas_back_step(const double *s, double *xo, const double (&xn)[3 * (O - 1)],
+                                                 double (&x)[3 * (O - 1)]) {
     using D = Dim<O>;
     constexpr int B = D::B, NR = D::NR;
+    double W[D::NU];
 #pragma unroll
     for (int i = 0; i < NR; ++i) x[i] = SMem::ld(s + (D::SX + i) * SFS);
-    if (has_next) {
-        double W[D::NU];
 #pragma unroll
-        for (int i = 0; i < D::NU; ++i) W[i] = SMem::ld(s + (D::SW + i) * SFS);
+    for (int i = 0; i < D::NU; ++i) W[i] = SMem::ld(s + (D::SW + i) * SFS);
 #pragma unroll
-        for (int p = 0; p < B; ++p)
+    for (int p = 0; p < B; ++p)
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                double acc = x[p * 3 + a];
+        for (int a = 0; a < 3; ++a) {
+            double acc = x[p * 3 + a];
 #pragma unroll
-                for (int q = 0; q < B; ++q) acc = fma(-W[p * B + q], xn[q * 3 + a], acc);
-                x[p * 3 + a] = acc;
-            }
-    }
+            for (int q = 0; q < B; ++q) acc = fma(-W[p * B + q], xn[q * 3 + a], acc);
+            x[p * 3 + a] = acc;
+        }
     if (XOut::ENABLED) {
 #pragma unroll
         for (int i = 0; i < NR; ++i) XOut::Mem::st(xo + (D::SX + i) * XOut::FS, x[i]);
     }
 }
 
-// Squared deviation ratio of one segment (ms.cpp:594-617):  || p(t*) - L(t*) ||^2 / |P_{k+1} - P_k|^2  from the
-// endpoint positions pk, pk1 and derivative vectors dk, dk1 ([r-1][axis], r = 1..o-1).
+// Squared deviation ratio of one segment (ms.cpp:594-617):  || p(t*) - L(t*) ||^2 / |P_{k+1} - P_k|^2.
+// The segment is seen from one of its ends: the OUTER waypoint (position po, derivatives dout, [r-1][axis]) is the one
+// farther from the split row, the INNER one (pi, din) the nearer.  outer_is_k1: the outer waypoint is the segment's
+// second waypoint (bottom half), so its Hermite weights are the second half of h.  Terms are accumulated outer first.
 // segx = { h[M], L[3], 1/len^2 } with compile-time stride XS.  The caller takes the square root of the maximum.
 template <int O, int XS>
-__device__ __forceinline__ double deviation_sq(const double *segx, const double (&pk)[3], const double *dk,
-                                               const double (&pk1)[3], const double *dk1) {
+__device__ __forceinline__ double deviation_sq(const double *segx, bool outer_is_k1, const double (&po)[3],
+                                               const double *dout, const double (&pi)[3], const double *din) {
     constexpr int M = 2 * O;
+    const double *ho = segx + (outer_is_k1 ? O * XS : 0), *hi = segx + (outer_is_k1 ? 0 : O * XS);
     double d2 = 0.0;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        double p = segx[0] * pk[a];
+        double p = ho[0] * po[a];
 #pragma unroll
-        for (int r = 1; r < O; ++r) p = fma(segx[r * XS], dk[(r - 1) * 3 + a], p);
-        p = fma(segx[O * XS], pk1[a], p);
+        for (int r = 1; r < O; ++r) p = fma(ho[r * XS], dout[(r - 1) * 3 + a], p);
+        p = fma(hi[0], pi[a], p);
 #pragma unroll
-        for (int r = 1; r < O; ++r) p = fma(segx[(O + r) * XS], dk1[(r - 1) * 3 + a], p);
+        for (int r = 1; r < O; ++r) p = fma(hi[r * XS], din[(r - 1) * 3 + a], p);
         const double dd = p - segx[(M + a) * XS];
         d2 = fma(dd, dd, d2);
     }
     return d2 * segx[(M + 3) * XS];
 }
 
-// Backward sweep of one trajectory with the deviation probe of every segment folded in (when EVAL).  The row loop
-// is unrolled by two with the roles of the two solution vectors swapped, so nothing is copied between iterations.
-//   pos(w, out[3])  : position of waypoint w = 0..ns
-//   base_at(j) / state_at(j) : base / state row of interior waypoint j+1
-//   xout(j)         : row that receives x_{j} (field SX..), or NoOut
-//   d0 / dN         : fixed derivative vectors of the first / last waypoint, [r-1][axis]
+// Back-substitution of one half of a trajectory, outwards from the split row m, with the deviation probe of every
+// segment it passes folded in (when EVAL).
+//   mirror == false: rows m-1 .. 0, then segment 0 (its outer end is the fixed first waypoint, derivatives dfix = d0)
+//   mirror == true : rows m+1 .. n-1, then the last segment (outer end: the fixed last waypoint, dfix = dN)
+//   pos(w, out[3])  : position of waypoint w = 0..ns        (row j belongs to waypoint j+1)
+//   state_at(j)     : state row j (z, W; SX of row m holds x_m);  xout(j): row that receives x_j, or NoOut
 //   segx_at(k)      : deviation probe of segment k
-// Returns max_k deviation ratio (0 when !EVAL).
+// Returns the larger of m2_in and the squared deviation ratios seen (m2_in when !EVAL).
 // EARLY: the caller only needs to know WHETHER the ratio exceeds the reweighting threshold 0.2 (ms.cpp:82), so the
 // sweep stops at the first segment whose squared ratio is safely above 0.04 and returns that (partial) maximum --
 // still > 0.2.  A sweep that runs to the end returns the exact maximum, so a trajectory that passes the test always
 // has its exact max_dev.
 constexpr double EARLY_DEV2 = 0.04 * (1.0 + 1e-9);
 template <int O, bool EVAL, bool EARLY, class StateAt, class XOut, class SegxAt, class PosAt>
-__device__ __forceinline__ double thomas_backward(int n_rows, const StateAt state_at,
-                                                  const XOut xout, const SegxAt segx_at, const PosAt pos,
-                                                  const double *d0, const double *dN) {
+__device__ __forceinline__ double back_half(int n_rows, int m, bool mirror, const StateAt state_at, const XOut xout,
+                                            const SegxAt segx_at, const PosAt pos, const double *dfix, double m2_in) {
     using D = Dim<O>;
     constexpr int NR = D::NR;
-    const int ns = n_rows + 1;
-    double xa[NR], xb[NR], pa[3], pb[3];
-    double m2 = 0.0;
-    // segment k = ns-1 .. 0 has endpoints (waypoint k, waypoint k+1); walk k downwards
-    pos(ns, pb);
+    double m2 = m2_in;
+    double xn[NR], pn[3];  // solution and position of the row nearer to the split row
+    {
+        const double *sm = state_at(m);
 #pragma unroll
-    for (int i = 0; i < NR; ++i) xb[i] = dN[i];  // derivatives of the last waypoint (fixed)
-    int j = n_rows - 1;                           // row of waypoint j+1
-    bool first = true;                            // xb still holds the fixed end derivatives (no W coupling)
-    // step: compute x of waypoint j+1 into `xo` from `xi` (= x of waypoint j+2), probe segment j+1
-    auto step = [&](double (&xo)[NR], double (&po)[3], const double (&xi)[NR], const double (&pi)[3]) {
-        if (j >= 1) state_at.prefetch(j - 1);
-        if (EVAL) segx_at.prefetch(j);
-        thomas_back_step<O, StateAt::FS, typename StateAt::Mem, XOut>(state_at(j), xout(j), !first, xi, xo);
-        pos(j + 1, po);
-        if (EVAL) m2 = fmax(m2, deviation_sq<O, SegxAt::FS>(segx_at(j + 1), po, xo, pi, xi));
-        first = false;
-        --j;
-    };
-    // NOTE on `first`: for the last row x_{n-1} = z_{n-1} (no coupling), and the segment above it ends at the fixed
-    // last waypoint whose derivatives are in xb.
-    while (j >= 1) {
-        step(xa, pa, xb, pb);
-        step(xb, pb, xa, pa);
-        if (EVAL && EARLY && m2 > EARLY_DEV2) return sqrt(m2);
-    }
-    if (j == 0) {
-        step(xa, pa, xb, pb);
-        if (EVAL) {
-            double p0[3];
-            pos(0, p0);
-            m2 = fmax(m2, deviation_sq<O, SegxAt::FS>(segx_at(0), p0, d0, pa, xa));
+        for (int i = 0; i < NR; ++i) xn[i] = StateAt::Mem::ld(sm + (D::SX + i) * StateAt::FS);
+        if (XOut::ENABLED && !mirror) {  // x_m itself (written once, by the top half)
+            double *xo = xout(m);
+#pragma unroll
+            for (int i = 0; i < NR; ++i) XOut::Mem::st(xo + (D::SX + i) * XOut::FS, xn[i]);
         }
-    } else if (EVAL) {  // j == -1: the first segment's far end is in (pb, xb)
-        double p0[3];
-        pos(0, p0);
-        m2 = fmax(m2, deviation_sq<O, SegxAt::FS>(segx_at(0), p0, d0, pb, xb));
+        pos(m + 1, pn);
     }
+    const int cnt = mirror ? n_rows - 1 - m : m;
+    const int step = mirror ? 1 : -1;
+    int j = m + step;
+    for (int i = 0; i < cnt; ++i, j += step) {
+        if (i + 1 < cnt) state_at.prefetch(j + step);
+        double x[NR], po[3];
+        thomas_back_step<O, StateAt::FS, typename StateAt::Mem, XOut>(state_at(j), xout(j), xn, x);
+        pos(j + 1, po);
+        if (EVAL) {  // the segment between rows j and j -+ 1: segment j+1 (top half) or j (bottom half)
+            if (EVAL) segx_at.prefetch(mirror ? j + 1 : j);
+            m2 = fmax(m2, deviation_sq<O, SegxAt::FS>(segx_at(mirror ? j : j + 1), mirror, po, x, pn, xn));
+        }
+#pragma unroll
+        for (int k = 0; k < NR; ++k) xn[k] = x[k];
+        pn[0] = po[0]; pn[1] = po[1]; pn[2] = po[2];
+        if (EVAL && EARLY && m2 > EARLY_DEV2) return m2;
+    }
+    if (EVAL) {  // the end segment: its outer waypoint has fixed derivatives
+        double pe[3];
+        pos(mirror ? n_rows + 1 : 0, pe);
+        m2 = fmax(m2, deviation_sq<O, SegxAt::FS>(segx_at(mirror ? n_rows : 0), mirror, pe, dfix, pn, xn));
+    }
+    return m2;
+}
+
+// Squared deviation ratio of a single-segment trajectory (both ends fixed).
+template <int O, class SegxAt, class PosAt>
+__device__ __forceinline__ double single_segment_dev2(const SegxAt segx_at, const PosAt pos, const double *d0,
+                                                      const double *dN) {
+    double p0[3], p1[3];
+    pos(0, p0);
+    pos(1, p1);
+    return deviation_sq<O, SegxAt::FS>(segx_at(0), false, p0, d0, p1, dN);
+}
+
+// One lane doing both halves: the bottom half first (for m = n-1 that is just the last segment, the likeliest to decide
+// an EARLY test).  Returns max_k deviation ratio (0 when !EVAL).
+template <int O, bool EVAL, bool EARLY, class StateAt, class XOut, class SegxAt, class PosAt>
+__device__ __forceinline__ double thomas_backward(int n_rows, int m, const StateAt state_at, const XOut xout,
+                                                  const SegxAt segx_at, const PosAt pos, const double *d0,
+                                                  const double *dN) {
+    if (n_rows <= 0) return EVAL ? sqrt(single_segment_dev2<O>(segx_at, pos, d0, dN)) : 0.0;
+    double m2 = back_half<O, EVAL, EARLY>(n_rows, m, true, state_at, xout, segx_at, pos, dN, 0.0);
+    if (EVAL && EARLY && m2 > EARLY_DEV2) return sqrt(m2);
+    m2 = back_half<O, EVAL, EARLY>(n_rows, m, false, state_at, xout, segx_at, pos, d0, m2);
     return EVAL ? sqrt(m2) : 0.0;
 }
 

@@ -237,37 +237,69 @@ __device__ __forceinline__ void fused_probe_item(const FusedParams &p, double *b
     x[2 * O + 3] = len > 1e-6 ? 1.0 / l2 : 0.0;
 }
 
-// One Thomas chain of trajectory block `blk` with diagonal shift add00; state rows given by `state_at`.
-// NOT inlined on purpose: as separate functions the 15-row sweeps get the whole register budget to themselves
-// (inlined next to the other phases they spill into local memory inside the row loop); a call is made once per
-// chain, so its ABI cost is noise.
+// The chains below are NOT inlined on purpose: as separate functions the row sweeps get the whole register budget to
+// themselves (inlined next to the other phases they spill into local memory inside the row loop); a call is made once
+// per chain, so its ABI cost is noise.
 //
-// One Thomas chain of trajectory block `blk` with diagonal shift add00: forward sweep into `state_at`, backward
-// sweep with the deviation probes (EVAL) leaving x in `xout` (or nowhere).
-template <int O, bool EVAL, bool EARLY, class StateAt, class XOut>
-__device__ __noinline__ bool fused_chain(const double *blk, int ns, double add00, const StateAt state_at,
-                                         const XOut xout, double *max_dev_out, long long *clk = nullptr) {
+// One speculative chain of trajectory block `blk` with diagonal shift add00 by ONE lane (split row n-1): elimination
+// into `state_at`, back-substitution with the deviation probes, leaving x nowhere.  Returns the pivot status.
+template <int O, class StateAt>
+__device__ __noinline__ bool fused_chain_spec(const double *blk, int ns, double add00, const StateAt state_at,
+                                              double *max_dev_out, long long *clk = nullptr) {
     using D = Dim<O>;
     const FusedSmem<O> L(ns);
     const FBaseRows<O> base_at{blk + L.oBase};
-    const bool ok = thomas_forward<O>(ns - 1, add00, base_at, state_at);
+    const int n = ns - 1, m = split_row(n, false);
+    const bool ok = thomas_forward<O>(n, m, add00, base_at, state_at);
     if (clk) clk[0] = clock64();
     const FSegxRows<O> segx_at{blk + L.oSegx};
     const FPos pos{blk + L.oP};
-    *max_dev_out = thomas_backward<O, EVAL, EARLY>(ns - 1, state_at, xout, segx_at, pos, blk + L.oBC,
-                                                   blk + L.oBC + D::NR);
+    *max_dev_out = thomas_backward<O, true, true>(n, m, state_at, NoOut{}, segx_at, pos, blk + L.oBC, blk + L.oBC + D::NR);
     if (clk) clk[1] = clock64();
     return ok;
 }
 
-// Backward sweep only: replay a finished forward sweep (`state_at`) and leave the solution in `xout`.
+// One latency-critical chain (pass 1, the last reweighting iteration, a bare solve) by TWO adjacent lanes of a warp
+// (balanced split): side 0 eliminates the top half, solves the split row and substitutes back upwards; side 1 takes the
+// bottom half.  `pair_mask` = the lanes of the warp that call this function (all of them must).  The solution is left
+// in `state_at` (shared memory).  Both lanes return the combined pivot status and the max deviation (0 when !EVAL).
+template <int O, bool EVAL, class StateAt>
+__device__ __noinline__ bool fused_chain_pair(const double *blk, int ns, double add00, const StateAt state_at, int side,
+                                              unsigned pair_mask, double *max_dev_out) {
+    using D = Dim<O>;
+    const FusedSmem<O> L(ns);
+    const FBaseRows<O> base_at{blk + L.oBase};
+    const FSegxRows<O> segx_at{blk + L.oSegx};
+    const FPos pos{blk + L.oP};
+    const double *d0 = blk + L.oBC, *dN = blk + L.oBC + D::NR;
+    const int n = ns - 1;
+    bool ok = true;
+    double m2 = 0.0;
+    if (n <= 0) {
+        if (EVAL && side == 0) m2 = single_segment_dev2<O>(segx_at, pos, d0, dN);
+    } else {
+        const int m = split_row(n, true);
+        ok = elim_half<O>(n, side ? n - 1 - m : m, side != 0, add00, base_at, state_at);
+        __syncwarp(pair_mask);
+        if (side == 0) ok = elim_middle<O>(n, m, add00, base_at, state_at) && ok;
+        __syncwarp(pair_mask);
+        m2 = back_half<O, EVAL, false>(n, m, side != 0, state_at, state_at, segx_at, pos, side ? dN : d0, 0.0);
+    }
+    m2 = fmax(m2, __shfl_xor_sync(pair_mask, m2, 1));
+    ok = __shfl_xor_sync(pair_mask, ok ? 1 : 0, 1) != 0 && ok;
+    *max_dev_out = EVAL ? sqrt(m2) : 0.0;
+    return ok;
+}
+
+// Back-substitution only: replay a finished speculative elimination (`state_at`) and leave the solution in `xout`.
 template <int O, class StateAt, class XOut>
 __device__ __noinline__ void fused_replay(const double *blk, int ns, const StateAt state_at, const XOut xout) {
     using D = Dim<O>;
     const FusedSmem<O> L(ns);
     const FSegxRows<O> segx_at{blk + L.oSegx};
     const FPos pos{blk + L.oP};
-    thomas_backward<O, false, false>(ns - 1, state_at, xout, segx_at, pos, blk + L.oBC, blk + L.oBC + D::NR);
+    thomas_backward<O, false, false>(ns - 1, split_row(ns - 1, false), state_at, xout, segx_at, pos, blk + L.oBC,
+                                     blk + L.oBC + D::NR);
 }
 
 // coefficients of (t, k, axis) from the final solution in the shared-memory state rows; returns finiteness
@@ -381,10 +413,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_c
                 fused_row_item<O>(p, smem + (i / nr) * tstride, ns, i % nr + 1, false);
             __syncthreads();
             MSNAP_STAMP();
-            if (tid < nt) {
+            if (tid < 2 * nt) {  // two lanes per trajectory (fused_chain_pair)
                 double unused;
-                const FStateRows<O, SL> st{state1 + tid};
-                ok1[tid] = fused_chain<O, false, false>(smem + tid * tstride, ns, 0.0, st, st, &unused) ? 1 : 0;
+                const int t = tid >> 1;
+                const FStateRows<O, SL> st{state1 + t};
+                const unsigned pm = 2 * nt >= 32 ? 0xffffffffu : (1u << (2 * nt)) - 1u;
+                const bool ok = fused_chain_pair<O, false>(smem + t * tstride, ns, 0.0, st, tid & 1, pm, &unused);
+                if ((tid & 1) == 0) ok1[t] = ok ? 1 : 0;
             }
             __syncthreads();
             MSNAP_STAMP();
@@ -414,7 +449,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_c
             // The last-iteration group sits in warp 0 .. (the CTA's oldest warps, which the scheduler favours): its
             // full backward sweep is the longest chain of this phase.  Speculative lanes start at the next warp boundary.
             const int n_glob = nt * (nit - 1);
-            const int g0l = (tpc + 31) & ~31;  // first speculative lane
+            const int g0l = (2 * tpc + 31) & ~31;  // first speculative lane
             if (tid >= g0l && tid < g0l + n_glob) {
                 const int l = tid - g0l;
                 const int t = l / (nit - 1), q = l - t * (nit - 1);
@@ -426,20 +461,23 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_c
                 if (p.phase_clocks && tile == blockIdx.x && (l & 63) == 0)
                     clk = p.phase_clocks + blockIdx.x * 16 + 10 + 2 * (l >> 6);
                 double mdv;
-                const bool ok = fused_chain<O, true, true>(smem + t * tstride, ns, add00, st, NoOut{}, &mdv, clk);
+                const bool ok = fused_chain_spec<O>(smem + t * tstride, ns, add00, st, &mdv, clk);
                 md[t * nit + q] = mdv;
                 okf[t * nit + q] = ok ? 1 : 0;
-            } else if (tid < nt) {
-                const int t = tid, q = nit - 1;
+            } else if (tid < 2 * nt) {  // two lanes per trajectory (fused_chain_pair)
+                const int t = tid >> 1, q = nit - 1;
                 double vw = p.sp.vw0;
                 for (int i = 0; i < q; ++i) vw = (vw < 1e-6) ? 0.01 : vw * 2.0;
                 const double add00 = vw > 0.0 ? 2.0 * vw : 0.0;
                 const FStateRows<O, SL> st{state1 + t};
+                const unsigned pm = 2 * nt >= 32 ? 0xffffffffu : (1u << (2 * nt)) - 1u;
                 double mdv;
-                const bool ok = use_pw ? fused_chain<O, true, false>(smem + t * tstride, ns, add00, st, st, &mdv)
-                                       : fused_chain<O, false, false>(smem + t * tstride, ns, add00, st, st, &mdv);
-                md[t * nit + q] = mdv;
-                okf[t * nit + q] = ok ? 1 : 0;
+                const bool ok = use_pw ? fused_chain_pair<O, true>(smem + t * tstride, ns, add00, st, tid & 1, pm, &mdv)
+                                       : fused_chain_pair<O, false>(smem + t * tstride, ns, add00, st, tid & 1, pm, &mdv);
+                if ((tid & 1) == 0) {
+                    md[t * nit + q] = mdv;
+                    okf[t * nit + q] = ok ? 1 : 0;
+                }
             }
             __syncthreads();
             // the iteration the sequential loop would have stopped at (ms.cpp:82)

@@ -186,10 +186,13 @@ __global__ void k_thomas(BatchIdx bi, SolveParams sp, const double *__restrict__
     bool ok = true;
     while (true) {
         const double add00 = vw > 0.0 ? 2.0 * vw : 0.0;
-        ok = thomas_forward<O>(n_rows, add00, base_at, state_at) && ok;
+        // the last possible iteration (and a bare solve, max_iter == 0) uses the balanced split, like the two-lane
+        // chains of the fused kernel; earlier iterations the one-sided split of the speculative lanes (split_row)
+        const int m = split_row(n_rows, iter == sp.max_iter || !eval_dev);  // !eval_dev: the loop ends after this solve
+        ok = thomas_forward<O>(n_rows, m, add00, base_at, state_at) && ok;
         // x_j overwrites z_j in the state row (z_j is read before it is replaced)
-        max_dev = eval_dev ? thomas_backward<O, true, false>(n_rows, state_at, state_at, segx_at, pos, d0, dN)
-                           : thomas_backward<O, false, false>(n_rows, state_at, state_at, segx_at, pos, d0, dN);
+        max_dev = eval_dev ? thomas_backward<O, true, false>(n_rows, m, state_at, state_at, segx_at, pos, d0, dN)
+                           : thomas_backward<O, false, false>(n_rows, m, state_at, state_at, segx_at, pos, d0, dN);
         if (max_dev > 0.2 && iter < sp.max_iter) {
             vw = (vw < 1e-6) ? 0.01 : vw * 2.0;
             ++iter;
@@ -258,8 +261,9 @@ __global__ void __launch_bounds__(128) k_thomas_spec(BatchIdx bi, SolveParams sp
     const GlobalPos pos{wp + 3 * (g0 + b)};
     const double vw = reweighted_vw(sp.vw0, q);
     const double add00 = vw > 0.0 ? 2.0 * vw : 0.0;
-    const bool ok = thomas_forward<O>(n_rows, add00, base_at, state_at);
-    const double md = thomas_backward<O, true, true>(n_rows, state_at, NoOut{}, segx_at, pos, d0, dN);
+    const int m = split_row(n_rows, false);
+    const bool ok = thomas_forward<O>(n_rows, m, add00, base_at, state_at);
+    const double md = thomas_backward<O, true, true>(n_rows, m, state_at, NoOut{}, segx_at, pos, d0, dN);
     md_ws[idx] = md;
     ok_ws[idx] = ok ? 1 : 0;
 }
@@ -297,7 +301,7 @@ __global__ void k_spec_select(BatchIdx bi, SolveParams sp, const double *__restr
         const GlobalRows<D::NSTATE> to{state + (g0 + 1) * D::NSTATE};
         const GlobalRows<D::NSEGX> segx_at{segx + g0 * D::NSEGX};
         const GlobalPos pos{wp + 3 * (g0 + b)};
-        thomas_backward<O, false, false>(n_rows, from, to, segx_at, pos, d0, dN);
+        thomas_backward<O, false, false>(n_rows, split_row(n_rows, false), from, to, segx_at, pos, d0, dN);
     }
     if (max_dev_out) max_dev_out[b] = md;
     if (iters_out) iters_out[b] = q;

@@ -173,6 +173,10 @@ class TrajectoryGeneratorTool:
     def set_reweight_policy(self, policy: int):
         self._check(self._L.msnap_set_reweight_policy(self._h, int(policy)))
 
+    def set_host_chunks(self, n_chunks: int):
+        """0 = automatic pipelining of the host-pointer path, 1 = one chunk (no overlap of copies and kernels)."""
+        self._check(self._L.msnap_set_host_chunks(self._h, int(n_chunks)))
+
     @property
     def launch_count(self) -> int:
         return int(self._L.msnap_launch_count(self._h))

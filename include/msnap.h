@@ -18,8 +18,9 @@
  *                 x | y | z blocks, highest power first, local time t in [0, T_k] (no time scaling)
  *   - samples   : [rows][3] row-major; trajectory b owns rows [sample_offset[b], sample_offset[b+1])
  *   - Functions suffixed _dev take DEVICE pointers for every array argument and only enqueue work on the handle's
- *     stream (no host synchronisation).  Functions suffixed _host take HOST pointers, stage through pinned memory
- *     owned by the handle, and return after the results are in the caller's buffers.
+ *     stream (no host synchronisation).  Functions suffixed _host take HOST pointers (pinned memory makes the copies
+ *     asynchronous and lets them overlap the kernels), use device mirrors owned by the handle, and return after the
+ *     results are in the caller's buffers.
  *   - Every function returns an msnap_status.  There is no CPU fallback: without a usable CUDA device
  *     msnap_create fails with MSNAP_ERR_NO_DEVICE and nothing else can be called.
  *   - A handle is bound to one device and one stream and is not thread-safe: one handle per host thread / GPU.
@@ -77,6 +78,10 @@ int msnap_synchronize(msnap_handle h);
  * 2 = speculative (all 11 velocity weights solved concurrently, the first admissible one selected). Results are
  * identical; this is a throughput/latency knob only. */
 int msnap_set_reweight_policy(msnap_handle h, int policy);
+/* Host-pointer entry points cut big batches into chunks whose kernels overlap the previous chunk's device-to-host
+ * copies (two internal streams).  n_chunks = 0: automatic (one chunk per 8 192 trajectories, at most 8); 1: no
+ * pipelining.  Results do not depend on the chunking. */
+int msnap_set_host_chunks(msnap_handle h, int n_chunks);
 /* Number of kernels this handle has launched since creation (monotonic; used by bench.py's gpu_launches). */
 long long msnap_launch_count(msnap_handle h);
 

@@ -156,3 +156,32 @@ def test_speculative_generic_path_equals_sequential_loop(tool, order):
             assert np.array_equal(getattr(seq, name), getattr(spec, name)), (name, pw)
         if pw is not None and order <= 4:
             assert len(set(seq.iters.tolist())) > 1                   # the early-stop branch is really exercised
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_pipelined_host_path_equals_single_chunk(tool, ragged):
+    """The host-pointer entry point cuts big batches into chunks on two streams; the chunking must not change a bit
+    and the CSR sample layout must come out identical (offsets rebased on the host)."""
+    if ragged:
+        wp, so = workloads.cfg5(B=3000, seed=77, ns_min=1, ns_max=24)
+        kw = dict(seg_offset=so)
+    else:
+        wp, ns = workloads.cfg2(B=3000, ns=8, seed=78)
+        kw = dict(ns=ns)
+    cfg = workloads.synthetic_config(4, "shipped")
+    tool.set_host_chunks(1)
+    try:
+        one = tool.generate_batch(cfg, wp, **kw)
+        tool.set_host_chunks(5)
+        five = tool.generate_batch(cfg, wp, **kw)
+        cap = int(one.sample_offset[1700]) + 3                         # overflow inside the third chunk
+        with pytest.raises(MsnapError) as e:
+            tool.generate_batch(cfg, wp, capacity=cap, **kw)
+    finally:
+        tool.set_host_chunks(0)
+    for name in ("times", "coeff", "max_dev", "iters", "vw_final", "best_s", "sample_offset", "samples", "stats", "flags"):
+        assert np.array_equal(getattr(one, name), getattr(five, name)), name
+    part = e.value.partial
+    assert np.array_equal(part.sample_offset, one.sample_offset)
+    assert np.array_equal(part.samples, one.samples[:cap])
+    assert (part.flags[:1700] & 2).max() == 0 and (part.flags[1701:] & 2).min() == 2

@@ -275,6 +275,7 @@ int run_solve(msnap_context *h, const BatchIdx &bi, const SolveParams &sp, const
     // Thread-per-trajectory sweeps touch 32 different cache lines per warp access, so they are bound by the L1 of the
     // SMs they run on: small batches use one warp per CTA to spread over as many SMs as possible.
     const int blk_b = bi.B >= 128LL * h->sm_count ? 128 : 32;
+    const int blk_p = 2 * bi.B >= 64LL * h->sm_count ? 64 : 32;  // k_thomas_pair: two lanes per trajectory
     const unsigned gs = grid_for(bi.n_seg, blk), gb = grid_for(bi.B, blk_b);
     const double *ht = &h->d_tab[O - MSNAP_MIN_ORDER].HT[0][0];
     if (w.fused.tpc > 0) {  // uniform batch: one persistent launch for the whole closed-form solve
@@ -331,8 +332,13 @@ int run_solve(msnap_context *h, const BatchIdx &bi, const SolveParams &sp, const
         MS_LAUNCH(h, (k_rows<O>), gs, blk, bi, sp, io.wp, T, false, (const int *)nullptr, ht, w.base, w.segx);
         SolveParams sp1 = sp;
         sp1.max_iter = 0;
-        MS_LAUNCH(h, (k_thomas<O>), gb, blk_b, bi, sp1, io.wp, w.base, w.state, w.segx, false, false,
-                  (double *)nullptr, (int *)nullptr, (double *)nullptr, io.flags_out);
+        if (h->policy != 1) {
+            MS_LAUNCH(h, (k_thomas_pair<O>), grid_for(2 * bi.B, blk_p), blk_p, bi, sp1, io.wp, w.base, w.state, w.segx,
+                      false, 0.0, (double *)nullptr, io.flags_out);
+        } else {
+            MS_LAUNCH(h, (k_thomas<O>), gb, blk_b, bi, sp1, io.wp, w.base, w.state, w.segx, false, false,
+                      (double *)nullptr, (int *)nullptr, (double *)nullptr, io.flags_out);
+        }
         MS_LAUNCH(h, (k_search<O>), gs, blk, bi, sp, io.wp, T, w.state, w.s_star);
     }
     MS_LAUNCH(h, (k_rows<O>), gs, blk, bi, sp, io.wp, T, use_pw, w.s_star, ht, w.base, w.segx);
@@ -341,11 +347,8 @@ int run_solve(msnap_context *h, const BatchIdx &bi, const SolveParams &sp, const
         MS_LAUNCH(h, (k_thomas_spec<O, SPEC_NIT1>), grid_for(bi.B * SPEC_NIT1, blk), blk, bi, sp, io.wp, w.base,
                   w.spec_state, w.segx, w.md_ws, w.ok_ws);
         MS_CUDA(h, cudaMemsetAsync(w.flag_last, 0, bi.B * sizeof(unsigned), h->stream));
-        SolveParams spl = sp;
-        spl.vw0 = reweighted_vw(sp.vw0, SPEC_NIT1);
-        spl.max_iter = 0;
-        MS_LAUNCH(h, (k_thomas<O>), gb, blk_b, bi, spl, io.wp, w.base, w.state, w.segx, true, true, w.md_last,
-                  (int *)nullptr, (double *)nullptr, w.flag_last);
+        MS_LAUNCH(h, (k_thomas_pair<O>), grid_for(2 * bi.B, blk_p), blk_p, bi, sp, io.wp, w.base, w.state, w.segx, true,
+                  reweighted_vw(sp.vw0, SPEC_NIT1), w.md_last, w.flag_last);
         MS_LAUNCH(h, (k_spec_select<O, SPEC_NIT1>), gb, blk_b, bi, sp, io.wp, w.spec_state, w.state, w.segx, w.md_ws,
                   w.ok_ws, w.md_last, w.flag_last, io.max_dev_out, io.iters_out, io.vw_final_out, io.flags_out);
     } else {

@@ -206,6 +206,67 @@ __global__ void k_thomas(BatchIdx bi, SolveParams sp, const double *__restrict__
     if (flags && (!ok || !(max_dev == max_dev))) atomicOr(flags + b, 1u);
 }
 
+// ------------------------------------------------------------------------------------------------ k_thomas_pair
+// ONE solve per trajectory (pass 1, the last reweighting iteration, a bare solve) by a PAIR of adjacent lanes:
+// balanced split, lane 0 takes the top half and the split row, lane 1 the bottom half (same arithmetic as k_thomas with
+// the balanced split, half the chain latency -- these sweeps are pure latency on CSR / long batches).
+template <int O>
+__global__ void __launch_bounds__(64) k_thomas_pair(BatchIdx bi, SolveParams sp, const double *__restrict__ wp,
+                                                    double *base, double *state, double *segx, bool eval_dev,
+                                                    double vw, double *__restrict__ max_dev_out,
+                                                    unsigned *__restrict__ flags) {
+    using D = Dim<O>;
+    constexpr int NR = D::NR;
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long b = idx >> 1;
+    const int side = (int)(idx & 1);
+    if (b >= bi.B) return;
+    // lanes of this warp that have a trajectory (pairs are never split: 2B is even and warps start at even indices)
+    const long long valid = 2 * bi.B - (idx - (threadIdx.x & 31));
+    const unsigned pair_mask = valid >= 32 ? 0xffffffffu : (1u << (int)valid) - 1u;
+    const long long g0 = bi.seg_begin(b);
+    const int ns = (int)(bi.seg_begin(b + 1) - g0);
+    const int n = ns - 1;
+    Boundary<O> bc;
+    boundary_of<O>(sp, b, bc);
+    double d0[NR], dN[NR];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int r = 1; r < O; ++r) {
+            d0[(r - 1) * 3 + a] = bc.y0[a][r];
+            dN[(r - 1) * 3 + a] = bc.yN[a][r];
+        }
+    const GlobalRows<D::NBASE> base_at{base + (g0 + 1) * D::NBASE};
+    const GlobalRows<D::NSTATE> state_at{state + (g0 + 1) * D::NSTATE};
+    const GlobalRows<D::NSEGX> segx_at{segx + g0 * D::NSEGX};
+    const GlobalPos pos{wp + 3 * (g0 + b)};
+    const double add00 = vw > 0.0 ? 2.0 * vw : 0.0;
+    bool ok = true;
+    double m2 = 0.0;
+    // segment counts differ between the trajectories of a warp: every lane passes both warp barriers
+    const int m = n > 0 ? split_row(n, true) : 0;
+    if (n > 0) ok = elim_half<O>(n, side ? n - 1 - m : m, side != 0, add00, base_at, state_at);
+    __threadfence_block();
+    __syncwarp(pair_mask);
+    if (n > 0 && side == 0) ok = elim_middle<O>(n, m, add00, base_at, state_at) && ok;
+    __threadfence_block();
+    __syncwarp(pair_mask);
+    if (n > 0) {
+        m2 = eval_dev ? back_half<O, true, false>(n, m, side != 0, state_at, state_at, segx_at, pos, side ? dN : d0, 0.0)
+                      : back_half<O, false, false>(n, m, side != 0, state_at, state_at, segx_at, pos, side ? dN : d0, 0.0);
+    } else if (eval_dev && side == 0) {
+        m2 = single_segment_dev2<O>(segx_at, pos, d0, dN);
+    }
+    m2 = fmax(m2, __shfl_xor_sync(pair_mask, m2, 1));
+    ok = __shfl_xor_sync(pair_mask, ok ? 1 : 0, 1) != 0 && ok;
+    if (side == 0) {
+        const double md = eval_dev ? sqrt(m2) : 0.0;
+        if (max_dev_out) max_dev_out[b] = md;
+        if (flags && (!ok || !(md == md))) atomicOr(flags + b, 1u);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ speculative loop
 // The reweighting loop of ms.cpp:76-90 for CSR batches, all iterations at once (same idea as the fused kernel): the
 // velocity weights are a fixed sequence, so iteration q of trajectory b is an independent solve.

@@ -269,6 +269,10 @@ def run_b200(args):
         cand = int(np.sum(np.floor((t_np + 1e-12) / np.minimum(0.1, t_np / 10.0) + 1e-9)))
         abytes = roofline.algorithmic_bytes(B, n_seg, ORDER, tot_samples)
         aflops = roofline.algorithmic_flops(B, n_seg, ORDER, cfg.path_weight > 0, total_solves, cand)
+        use_pw = cfg.path_weight > 0
+        kbytes = {k: roofline.kernel_bytes(k, B, n_seg, ORDER, tot_samples) for k in ("k_fused_solve", "k_sample_scan")}
+        kflops = {k: roofline.kernel_flops(k, B, n_seg, ORDER, use_pw, total_solves, cand)
+                  for k in ("k_fused_solve", "k_sample_scan")}
         footprint = ROTATE * (abytes + 24 * (sets[0].cap - tot_samples))
         # end to end through the host-pointer C ABI: pinned host inputs -> H2D, solve, D2H of every result
         out = {k: torch.empty(shape, dtype=dt).pin_memory().numpy() for k, shape, dt in (
@@ -296,7 +300,8 @@ def run_b200(args):
             ms=ms, steps=steps, launches=launches, value=world * B * steps / (ms * 1e-3),
             e2e=dict(value=world * B * e2e_steps / e2e_s, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                      steps=e2e_steps, ms_per_step=e2e_s / e2e_steps * 1e3),
-            prof=prof, dom=dom, dom_ms=dom_ms, all_kernels_ms=all_ms, abytes=abytes, aflops=aflops,
+            prof=prof, dom=dom, dom_ms=dom_ms, all_kernels_ms=all_ms, abytes=abytes, aflops=aflops, kbytes=kbytes,
+            kflops=kflops,
             samples=tot_samples, candidates=cand, mean_iters=float(iters0.double().mean().item()), flags_bad=flags_bad,
             footprint=footprint)
         del sets
@@ -318,17 +323,29 @@ def run_b200(args):
             pass
 
         def roof(r, weights):
+            # the dominant kernel against ITS OWN algorithmic bytes / flops per launch (one launch per step)
             t = r["dom_ms"] * 1e-3
-            gbs = r["abytes"] / t / 1e9
-            tf = r["aflops"] / t / 1e12
+            kb, kf = r["kbytes"][r["dom"]], r["kflops"][r["dom"]]
+            gbs = kb / t / 1e9
+            tf = kf / t / 1e12
             tr = traffic.get(weights, {}).get(r["dom"]) if isinstance(traffic, dict) else None
+            t_all = r["all_kernels_ms"] * 1e-3
             return {"bound": "hbm", "kernel": r["dom"], "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                     "frac": gbs / hbm_peak, "traffic": tr, "peak_source": peak_src,
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
+                                      "(profiles/dominant_kernel_traffic.json)" if tr else None,
                     "kernel_ms_per_step": r["dom_ms"], "all_kernels_ms_per_step": r["all_kernels_ms"],
-                    "algorithmic_bytes_per_step": r["abytes"], "algorithmic_flops_per_step": r["aflops"],
+                    "algorithmic_bytes_per_launch": kb, "algorithmic_flops_per_launch": kf,
                     "fp64": {"achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
                              "peak_source": "msnap_measure_fp64_peak (own DFMA micro-benchmark, measured this run)"},
-                    "limiter": "fp64" if tf / fp64_peak > gbs / hbm_peak else "hbm",
+                    "limiter": "fp64 issue/latency" if tf / fp64_peak > gbs / hbm_peak else "hbm",
+                    "whole_step": {"algorithmic_bytes": r["abytes"], "algorithmic_flops": r["aflops"],
+                                   "hbm_frac": r["abytes"] / t_all / 1e9 / hbm_peak,
+                                   "fp64_frac": r["aflops"] / t_all / 1e12 / fp64_peak},
+                    "kernels": {k: {"ms_per_step": v["total_ms"] / 20,
+                                    "hbm_frac": r["kbytes"][k] / (v["total_ms"] / 20 * 1e-3) / 1e9 / hbm_peak,
+                                    "fp64_frac": r["kflops"][k] / (v["total_ms"] / 20 * 1e-3) / 1e12 / fp64_peak}
+                                for k, v in r["prof"].items() if k in r["kbytes"]},
                     "kernels_ms_per_step": {k: v["total_ms"] / 20 for k, v in r["prof"].items()}}
 
         h = results[args.weights]

@@ -21,6 +21,32 @@ def algorithmic_bytes(B: int, n_seg: int, order: int, total_samples: int) -> int
     return wp_in + times_out + coeff_out + samples_out + per_traj
 
 
+def kernel_bytes(kernel: str, B: int, n_seg: int, order: int, total_samples: int) -> int:
+    """Algorithmic bytes of ONE kernel of the uniform-batch pipeline per launch: what that kernel must read and write
+    whatever its implementation.  The coefficients and segment times cross HBM twice in the two-kernel pipeline (written
+    by the solve kernel, read by the sampler), which is why the per-kernel figures add up to more than
+    ``algorithmic_bytes`` (the bytes of the whole path)."""
+    wp_in = 24 * (n_seg + B)
+    times = 8 * n_seg
+    coeff = 48 * order * n_seg
+    if kernel == "k_fused_solve":
+        return wp_in + times + coeff + (8 + 4 + 8 + 4) * B       # + max_dev, iters, vw_final, flags
+    if kernel == "k_sample_scan":
+        return coeff + times + 24 * total_samples + 8 * (B + 1)  # + sample_offset
+    raise KeyError(kernel)
+
+
+def kernel_flops(kernel: str, B: int, n_seg: int, order: int, use_pw: bool, total_solves: int,
+                 total_candidates: int) -> float:
+    """Share of ``algorithmic_flops`` that belongs to one kernel of the uniform-batch pipeline."""
+    sampler = total_candidates * sample_candidate_flops(order)
+    if kernel == "k_sample_scan":
+        return sampler
+    if kernel == "k_fused_solve":
+        return algorithmic_flops(B, n_seg, order, use_pw, total_solves, total_candidates) - sampler
+    raise KeyError(kernel)
+
+
 def thomas_row_flops(order: int) -> float:
     """One block row of the block-tridiagonal Cholesky for three right-hand sides: forward + backward."""
     b = order - 1

@@ -185,8 +185,8 @@ FusedPlan plan_fused(msnap_context *h, const BatchIdx &bi, const SolveParams &sp
     // lanes: 2 * tpc lanes (one pair per trajectory, within ONE warp) for the last iteration, then, from the next warp
     // boundary, tpc * (nit - 1) speculative lanes
     int tmax = FUSED_SMEM_LANES < 16 ? FUSED_SMEM_LANES : 16;
-    while (tmax > 1 && 32 + tmax * (nit - 1) > FUSED_THREADS) --tmax;
-    if (32 + tmax * (nit - 1) > FUSED_THREADS) return f;
+    while (tmax > 1 && (32 + tmax * (nit - 1) > FUSED_THREADS || tmax * (nit - 1) > FUSED_SLOT_LANES)) --tmax;
+    if (32 + tmax * (nit - 1) > FUSED_THREADS || tmax * (nit - 1) > FUSED_SLOT_LANES) return f;
     if ((long long)tmax > bi.B) tmax = (int)bi.B;
     // Pick the tile size that needs the fewest waves of resident CTAs (the kernel is latency-bound per tile, so a
     // partial second wave costs a whole tile latency); among those, the largest tile (best lane utilisation).

@@ -33,7 +33,7 @@
 namespace msnap {
 
 constexpr int FUSED_THREADS = 192;     // 2 CTAs per SM at <= 170 registers per thread
-constexpr int FUSED_SLOT_LANES = FUSED_THREADS;  // lanes per state row of the global scratch slot
+constexpr int FUSED_SLOT_LANES = 160;  // lanes per state row of the global scratch slot (>= 16 trajectories x 10 speculative iterations)
 constexpr int FUSED_SMEM_LANES = 14;   // lanes per state row in shared memory (= max trajectories per tile)
 
 struct FusedParams {
@@ -516,6 +516,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_c
             }
         }
         __syncthreads();  // flags[b] is OR-ed below
+        // The speculative sweep state in this CTA's scratch slot is dead from here on: tell L2 to drop the lines instead
+        // of writing them back to HBM when they are evicted (the slot is rewritten before it is read again).
+        if (nit > 1) {
+            char *sb = reinterpret_cast<char *>(slot);
+            const int n_lines = (int)(((size_t)nr * D::NSTATE * GL * sizeof(double)) / 128);
+            for (int i = tid; i < n_lines; i += FUSED_THREADS)
+                asm volatile("discard.global.L2 [%0], 128;" ::"l"(sb + (size_t)i * 128) : "memory");
+        }
         // ---- coefficients: items (t, k, axis), 64-byte rows straight to HBM
         for (int i = tid; i < nt * ns * 3; i += FUSED_THREADS) {
             const int t = i / (ns * 3), r = i - t * ns * 3;

@@ -7,6 +7,7 @@ names_pw = ["load", "times", "rows1", "thomas1", "search", "probes+rows2", "spec
 names_plain = ["load", "times", "rows", "solve+select", "outputs+coeff"]
 scan_names = ["sort+count", "rows", "scan+expand+lookback", "write"]
 tool = TrajectoryGeneratorTool(0)
+tool.set_host_chunks(1)  # the stamps are taken on this handle's own launches
 cases = [(4096, 16), (1 << 15, 8)] if len(sys.argv) < 2 else [(int(sys.argv[1]), int(sys.argv[2]))]
 for weights in ("shipped", "plain"):
     for B, ns in cases:

@@ -410,8 +410,15 @@ int scan_tpt(int ns, long long B, int sm_count) {
     return tiles_two >= 2LL * 4 * sm_count ? two : one;
 }
 
-size_t sample_ws_bytes(long long n_seg, long long B, int ns_uniform, int policy) {
-    if (ns_uniform > 0 && policy != 1) {
+// The single-launch sampler keeps a tile's per-segment bookkeeping in shared memory: uniform batches only, and only
+// while a one-trajectory tile fits (very long trajectories take the per-pass kernels).
+bool use_scan_sampler(int ns_uniform, long long B, int policy, int sm_count) {
+    if (ns_uniform <= 0 || policy == 1) return false;
+    return scan_smem_bytes(scan_tpt(ns_uniform, B, sm_count), ns_uniform, 4, false) <= 96 * 1024;
+}
+
+size_t sample_ws_bytes(long long n_seg, long long B, int ns_uniform, int policy, int sm_count) {
+    if (use_scan_sampler(ns_uniform, B, policy, sm_count)) {
         const long long n_tiles = B;  // upper bound on the tile count (tpt >= 1)
         return padded((size_t)(n_tiles + 1 + 256) * sizeof(unsigned long long)) + 256;  // + ticket + per-SM counters
     }
@@ -420,7 +427,7 @@ size_t sample_ws_bytes(long long n_seg, long long B, int ns_uniform, int policy)
            padded(B * sizeof(long long)) + padded((size_t)(B / SCAN_BLOCK + 2) * sizeof(long long));
 }
 void carve_sample_ws(Arena &a, long long n_seg, long long B, int ns_uniform, int policy, int sm_count, SampleWs &s) {
-    if (ns_uniform > 0 && policy != 1) {
+    if (use_scan_sampler(ns_uniform, B, policy, sm_count)) {
         s.tpt = scan_tpt(ns_uniform, B, sm_count);
         s.n_tiles = (B + s.tpt - 1) / s.tpt;
         s.status = arena_take<unsigned long long>(a, s.n_tiles + 1 + 256);  // + ticket + per-SM arrival counters
@@ -532,7 +539,7 @@ int generate_dev(msnap_context *h, const msnap_config *cfg, double sd, double v_
     const FusedPlan f = plan_fused<O>(h, bi, sp);
     const bool spec = use_generic_spec<O>(h, n_seg, sp);
     int rc = arena_reserve(h, h->ws, solve_ws_bytes<O>(n_seg, B, true, coeff_out == nullptr, f, spec) +
-                                        sample_ws_bytes(n_seg, B, bi.ns_uniform, h->policy));
+                                        sample_ws_bytes(n_seg, B, bi.ns_uniform, h->policy, h->sm_count));
     if (rc) return rc;
     SolveWs w;
     carve_solve_ws<O>(h->ws, n_seg, B, true, coeff_out, f, spec, w);

@@ -115,6 +115,20 @@ def test_cfg4_long_chains(tool):
     check_properties(res, wp, np.arange(65, dtype=np.int64) * ns, 4, cfg, pos_tol=1e-7)
 
 
+def test_very_long_uniform_trajectories(tool):
+    """3 000 segments per trajectory: too long for the fused kernel's and the single-launch sampler's shared-memory tiles,
+    so the per-pass kernels with the speculative reweighting lanes and the lane-pair solves run; a ragged batch holding
+    the same trajectories must give the same bits."""
+    wp, ns = workloads.cfg4(B=3, ns=3000, seed=9)
+    cfg = workloads.synthetic_config(4, "shipped")
+    res = tool.generate_batch(cfg, wp, ns=ns)
+    so = np.arange(4, dtype=np.int64) * ns
+    check_properties(res, wp, so, 4, cfg, pos_tol=1e-7)
+    rag = tool.generate_batch(cfg, wp, seg_offset=so)
+    assert np.array_equal(rag.coeff, res.coeff) and np.array_equal(rag.samples, res.samples)
+    assert np.array_equal(rag.iters, res.iters) and np.array_equal(rag.max_dev, res.max_dev)
+
+
 def test_cfg5_mixed_lengths_dense_sampling(tool):
     wp, so = workloads.cfg5(B=2048)
     cfg = workloads.synthetic_config(4, "plain", sample_distance=0.0)

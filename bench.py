@@ -278,23 +278,23 @@ def run_b200(args):
         out = {k: torch.empty(shape, dtype=dt).pin_memory().numpy() for k, shape, dt in (
             ("times", (n_seg,), torch.float64), ("coeff", (n_seg, 3, m), torch.float64), ("max_dev", (B,), torch.float64),
             ("iters", (B,), torch.int32), ("vw_final", (B,), torch.float64), ("sample_offset", (B + 1,), torch.int64),
-            ("samples", (sets[0].cap, 3), torch.float64), ("stats", (B, 2), torch.float64))}
+            ("samples", (sets[0].cap, 3), torch.float64))}
         out["flags"] = torch.zeros(B, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
         out["best_s"] = torch.zeros(n_seg, dtype=torch.int32).pin_memory().numpy()
         wp_np = [s.wp_h.numpy() for s in sets]
         e2e_steps = max(3, min(steps, 30))
         for i in range(3):
-            tool.generate_batch(cfg, wp_np[i % ROTATE], ns=NS, capacity=sets[0].cap, out=out)
+            tool.generate_batch(cfg, wp_np[i % ROTATE], ns=NS, capacity=sets[0].cap, out=out, stats=False)
         barrier()
         t0 = time.perf_counter()
         for i in range(e2e_steps):
-            r = tool.generate_batch(cfg, wp_np[i % ROTATE], ns=NS, capacity=sets[0].cap, out=out)
+            r = tool.generate_batch(cfg, wp_np[i % ROTATE], ns=NS, capacity=sets[0].cap, out=out, stats=False)
         torch.cuda.synchronize()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         barrier()
         h2d = wp_np[0].nbytes
         d2h = int(r.samples.nbytes + out["times"].nbytes + out["coeff"].nbytes + out["max_dev"].nbytes +
-                  out["iters"].nbytes + out["vw_final"].nbytes + out["sample_offset"].nbytes + out["stats"].nbytes +
+                  out["iters"].nbytes + out["vw_final"].nbytes + out["sample_offset"].nbytes +
                   out["flags"].nbytes + out["best_s"].nbytes)
         results[weights] = dict(
             ms=ms, steps=steps, launches=launches, value=world * B * steps / (ms * 1e-3),

@@ -177,6 +177,11 @@ class TrajectoryGeneratorTool:
         """0 = automatic pipelining of the host-pointer path, 1 = one chunk (no overlap of copies and kernels)."""
         self._check(self._L.msnap_set_host_chunks(self._h, int(n_chunks)))
 
+    def set_zero_copy(self, enable: bool):
+        """Let the kernels store coefficients / samples straight into pinned host buffers (default off: slower than
+        the copy engine on B200 / PCIe 5)."""
+        self._check(self._L.msnap_set_zero_copy(self._h, int(bool(enable))))
+
     @property
     def launch_count(self) -> int:
         return int(self._L.msnap_launch_count(self._h))
@@ -269,7 +274,7 @@ class TrajectoryGeneratorTool:
 
     def generate_batch(self, cfg: MinimumSnapConfig, waypoints, ns=None, seg_offset=None,
                        sample_distance_override=-1.0, v_avg_override=-1.0, capacity: Optional[int] = None,
-                       out: Optional[dict] = None) -> BatchResult:
+                       out: Optional[dict] = None, stats: bool = True) -> BatchResult:
         """B independent GenerateTrajectoryMatrix calls in one launch sequence; host arrays in, host arrays out.
         ``capacity`` rows are reserved for the samples (default: the exact-safe upper bound from
         ``msnap_sample_bound``); if it is too small MsnapError(ERR_CAPACITY) is raised with the exact layout
@@ -289,7 +294,7 @@ class TrajectoryGeneratorTool:
         best_s = o.get("best_s", np.zeros(n_seg, dtype=np.int32))
         sample_offset = o.get("sample_offset", np.empty(B + 1, dtype=np.int64))
         samples = o.get("samples", np.empty((max(int(capacity), 1), 3)))
-        stats = o.get("stats", np.empty((B, 2)))
+        stats = o.get("stats", np.empty((B, 2))) if stats else None   # (the reference only prints them, ms.cpp:194)
         flags = o.get("flags", np.zeros(B, dtype=np.uint32))
         rc = self._L.msnap_generate_batch_host(
             self._h, C.byref(c), float(sample_distance_override), float(v_avg_override), B, nsu, _ptr(so), _ptr(wp),

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -64,6 +65,8 @@ struct msnap_context {
     // stream, own arenas), so that a chunk's kernels overlap the previous chunk's device-to-host copies
     std::vector<msnap_context *> kids;
     int host_chunks = 0;              // 0 = automatic (MSNAP_HOST_CHUNKS)
+    bool zero_copy = false;           // host path: store big results straight into pinned caller buffers (MSNAP_ZERO_COPY);
+                                      // measured on B200/PCIe 5: SM stores reach ~24 GB/s, the copy engine ~53 GB/s => off
     long long *h_off = nullptr;       // pinned staging for a chunk's sample offsets
     size_t h_off_cap = 0;
 };
@@ -158,6 +161,9 @@ struct SolveIO {
     double *times_out = nullptr, *coeff_out = nullptr, *max_dev_out = nullptr, *vw_final_out = nullptr;
     int *iters_out = nullptr, *best_s_out = nullptr;
     unsigned *flags_out = nullptr;
+    // zero-copy outputs of the host-pointer path: device-visible addresses of the caller's PINNED host buffers
+    double *coeff_mirror = nullptr;   // the fused kernel stores the coefficients there as well (honoured: mirror_done)
+    bool *mirror_done = nullptr;
 };
 
 
@@ -295,6 +301,8 @@ int run_solve(msnap_context *h, const BatchIdx &bi, const SolveParams &sp, const
         fp.ht = ht;
         fp.times_out = io.times_in ? nullptr : w.T;  // allocated times go to the workspace (the sampler reads them)
         fp.coeff_out = w.coeff;
+        fp.coeff_mirror = io.coeff_mirror;
+        if (io.coeff_mirror && io.mirror_done) *io.mirror_done = true;
         fp.max_dev_out = io.max_dev_out;
         fp.vw_final_out = io.vw_final_out;
         fp.iters_out = io.iters_out;
@@ -524,7 +532,8 @@ template <int O>
 int generate_dev(msnap_context *h, const msnap_config *cfg, double sd, double v_avg, long long B, int ns_uniform,
                  const long long *seg_offset, long long n_seg, const double *wp, double *times_out, double *coeff_out,
                  double *max_dev_out, int *iters_out, double *vw_final_out, int *best_s_out, long long capacity,
-                 long long *sample_offset, double *samples, double *stats, unsigned *flags) {
+                 long long *sample_offset, double *samples, double *stats, unsigned *flags,
+                 double *coeff_mirror = nullptr, bool *mirror_done = nullptr) {
     BatchIdx bi{B, n_seg, ns_uniform > 0 ? ns_uniform : 0, ns_uniform > 0 ? nullptr : seg_offset};
     SolveParams sp{};
     sp.pw = cfg->path_weight;
@@ -556,6 +565,8 @@ int generate_dev(msnap_context *h, const msnap_config *cfg, double sd, double v_
     io.vw_final_out = vw_final_out;
     io.best_s_out = best_s_out;
     io.flags_out = flags;
+    io.coeff_mirror = coeff_mirror;
+    io.mirror_done = mirror_done;
     rc = run_solve<O>(h, bi, sp, io, w);
     if (rc) return rc;
     return run_sample<O>(h, bi, w.coeff, w.T, sd, capacity, sample_offset, samples, stats, flags, s);
@@ -673,6 +684,7 @@ int msnap_create(int device, msnap_handle *out) {
     if (const char *e = std::getenv("MSNAP_SPEC_CHUNK")) h->spec_chunk = std::atoi(e);
     if (const char *e = std::getenv("MSNAP_SCAN_COEF_SMEM")) h->scan_coef_smem = std::atoi(e) != 0;
     if (const char *e = std::getenv("MSNAP_HOST_CHUNKS")) h->host_chunks = std::atoi(e);
+    if (const char *e = std::getenv("MSNAP_ZERO_COPY")) h->zero_copy = std::atoi(e) != 0;
     *out = h;
     return MSNAP_OK;
 }
@@ -709,6 +721,12 @@ int msnap_synchronize(msnap_handle h) {
 int msnap_set_reweight_policy(msnap_handle h, int policy) {
     if (!h || policy < 0 || policy > 2) return MSNAP_ERR_INVALID_ARG;
     h->policy = policy;
+    return MSNAP_OK;
+}
+
+int msnap_set_zero_copy(msnap_handle h, int enable) {
+    if (!h) return MSNAP_ERR_INVALID_ARG;
+    h->zero_copy = enable != 0;
     return MSNAP_OK;
 }
 
@@ -936,13 +954,25 @@ struct HostChunk {
     std::vector<long long> off_local;                       // ragged batches: seg_offset of the chunk, rebased to 0
     long long *d_so = nullptr;
     double *d_s = nullptr;
+    bool single = false;               // the only chunk of the call
+    double *samples_direct = nullptr;  // zero-copy: the kernels wrote the rows straight into the caller's pinned buffer
 };
 
 // Enqueue H2D, the kernels and the D2H of everything but the samples on k's stream; no host synchronisation.
+// Device-visible address of a pinned (page-locked, mapped) host allocation, or nullptr for anything else.
+static void *device_view_of_pinned(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
 static int host_chunk_enqueue(msnap_context *k, const msnap_config *cfg, double sd, double va, HostChunk &j,
                               int ns_uniform, const double *waypoints, double *times_out, double *coeff_out,
                               double *max_dev_out, int *iters_out, double *vw_final_out, int *best_s_out,
-                              long long sample_capacity, double *stats_out, unsigned *flags_out) {
+                              long long sample_capacity, double *samples_out, double *stats_out, unsigned *flags_out) {
     const long long B = j.B, n_seg = j.n_seg;
     const size_t n_pts = (size_t)(n_seg + B), m3 = (size_t)3 * 2 * cfg->order;
     size_t bytes = padded((B + 1) * sizeof(long long)) + padded(n_pts * 3 * sizeof(double)) +
@@ -978,16 +1008,28 @@ static int host_chunk_enqueue(msnap_context *k, const msnap_config *cfg, double 
     if (ns_uniform <= 0)
         MS_CUDA(k, cudaMemcpyAsync(d_off, j.off_local.data(), (B + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
     MS_CUDA(k, cudaMemcpyAsync(d_wp, waypoints + 3 * j.p0, n_pts * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    // Zero-copy outputs: when the caller's big result buffers are pinned (device-visible) host memory the kernels store
+    // straight into them over PCIe -- coalesced 64-byte coefficient rows and 768-byte sample row groups -- so the
+    // transfer overlaps the computation and no separate device-to-host copy (nor a round trip for the row count) is
+    // needed.  Samples only without statistics (k_stats would read them back over PCIe) and for a single chunk.
+    double *coeff_zc = nullptr;
+    bool coeff_direct = false;
+    if (k->zero_copy && coeff_out && (reinterpret_cast<uintptr_t>(coeff_out) & 15) == 0)
+        coeff_zc = static_cast<double *>(device_view_of_pinned(coeff_out));
+    j.samples_direct = nullptr;
+    if (k->zero_copy && j.single && !stats_out && samples_out)
+        j.samples_direct = static_cast<double *>(device_view_of_pinned(samples_out));
     MS_DISPATCH_ORDER(cfg->order,
                       rc = generate_dev<O>(k, cfg, sd, va, B, ns_uniform, ns_uniform > 0 ? nullptr : d_off, n_seg, d_wp,
                                            times_out ? d_t : nullptr, coeff_out ? d_c : nullptr, d_md, d_it, d_vw,
-                                           best_s_out ? d_bs : nullptr, sample_capacity, j.d_so, j.d_s,
-                                           stats_out ? d_st : nullptr, d_fl));
+                                           best_s_out ? d_bs : nullptr, sample_capacity, j.d_so,
+                                           j.samples_direct ? j.samples_direct : j.d_s, stats_out ? d_st : nullptr, d_fl,
+                                           coeff_zc ? coeff_zc + j.g0 * m3 : nullptr, &coeff_direct));
     if (rc) return rc;
     MS_CUDA(k, cudaMemcpyAsync(k->h_off, j.d_so, (B + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
     if (times_out)
         MS_CUDA(k, cudaMemcpyAsync(times_out + j.g0, d_t, n_seg * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (coeff_out)
+    if (coeff_out && !coeff_direct)
         MS_CUDA(k, cudaMemcpyAsync(coeff_out + j.g0 * m3, d_c, (size_t)n_seg * m3 * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (max_dev_out) MS_CUDA(k, cudaMemcpyAsync(max_dev_out + j.b0, d_md, B * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (vw_final_out) MS_CUDA(k, cudaMemcpyAsync(vw_final_out + j.b0, d_vw, B * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1007,7 +1049,7 @@ static int host_chunk_finish(msnap_context *k, HostChunk &j, long long &rows_bas
     long long room = sample_capacity - rows_base;
     if (room < 0) room = 0;
     const long long rows = total < room ? total : room;
-    if (rows > 0)
+    if (rows > 0 && !j.samples_direct)
         MS_CUDA(k, cudaMemcpyAsync(samples_out + 3 * rows_base, j.d_s, (size_t)rows * 3 * sizeof(double),
                                    cudaMemcpyDeviceToHost, k->stream));
     for (long long b = 0; b < j.B; ++b) sample_offset_out[j.b0 + b] = rows_base + k->h_off[b];
@@ -1056,6 +1098,7 @@ int msnap_generate_batch_host(msnap_handle h, const msnap_config *cfg, double sa
             k->policy = h->policy;
             k->spec_chunk = h->spec_chunk;
             k->scan_coef_smem = h->scan_coef_smem;
+            k->zero_copy = h->zero_copy;
         }
         ctx = h->kids;
     }
@@ -1077,9 +1120,10 @@ int msnap_generate_batch_host(msnap_handle h, const msnap_config *cfg, double sa
         j.p0 = j.g0 + b0;
     }
     auto enqueue = [&](long long c) {
+        jobs[(size_t)c].single = n_chunks == 1;
         return host_chunk_enqueue(ctx[(size_t)c % ctx.size()], cfg, sd, va, jobs[(size_t)c], ns_uniform, waypoints,
                                   times_out, coeff_out, max_dev_out, iters_out, vw_final_out, best_s_out,
-                                  sample_capacity, stats_out, flags_out);
+                                  sample_capacity, samples_out, stats_out, flags_out);
     };
     auto fail = [&](int code, msnap_context *k) {
         if (k != h) h->last_error = k->last_error;

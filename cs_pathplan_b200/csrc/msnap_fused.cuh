@@ -49,6 +49,7 @@ struct FusedParams {
     SolveParams sp;
     const double *ht;        // HT table of this order in global memory
     double *times_out, *coeff_out, *max_dev_out, *vw_final_out;
+    double *coeff_mirror;    // optional second destination of the coefficients (the caller's pinned host buffer)
     int *iters_out, *best_s_out;
     unsigned *flags;
     double *state_ws;        // [gridDim.x][ns-1][NSTATE][FUSED_SLOT_LANES]
@@ -305,7 +306,7 @@ __device__ __noinline__ void fused_replay(const double *blk, int ns, const State
 // coefficients of (t, k, axis) from the final solution in the shared-memory state rows; returns finiteness
 template <int O>
 __device__ __forceinline__ bool fused_coeff_item(const double *blk, const double *state_lane, int ns, int k, int a,
-                                              double *dst_row) {
+                                              double *dst_row, double *mirror_row) {
     using D = Dim<O>;
     constexpr int M = D::M;
     const FusedSmem<O> L(ns);
@@ -328,6 +329,7 @@ __device__ __forceinline__ bool fused_coeff_item(const double *blk, const double
 #pragma unroll
     for (int q = 0; q < M / 2; ++q) {
         dst[q] = make_double2(co[2 * q], co[2 * q + 1]);
+        if (mirror_row) reinterpret_cast<double2 *>(mirror_row)[q] = make_double2(co[2 * q], co[2 * q + 1]);
         finite = finite && (fabs(co[2 * q]) <= 1.7976931348623157e308) && (fabs(co[2 * q + 1]) <= 1.7976931348623157e308);
     }
     return finite;
@@ -528,8 +530,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_c
         for (int i = tid; i < nt * ns * 3; i += FUSED_THREADS) {
             const int t = i / (ns * 3), r = i - t * ns * 3;
             const int k = r / 3, a = r - 3 * k;
-            double *dst = p.coeff_out + ((g0 + (long long)t * ns + k) * 3 + a) * D::M;
-            const bool finite = fused_coeff_item<O>(smem + t * tstride, state1 + t, ns, k, a, dst);
+            const long long row = ((g0 + (long long)t * ns + k) * 3 + a) * D::M;
+            const bool finite = fused_coeff_item<O>(smem + t * tstride, state1 + t, ns, k, a, p.coeff_out + row,
+                                                    p.coeff_mirror ? p.coeff_mirror + row : nullptr);
             if (!finite && p.flags) atomicOr(p.flags + b0 + t, 1u);
         }
         __syncthreads();  // the tile's smem and state slot are reused by the next tile

@@ -82,6 +82,12 @@ int msnap_set_reweight_policy(msnap_handle h, int policy);
  * copies (two internal streams).  n_chunks = 0: automatic (one chunk per 8 192 trajectories, at most 8); 1: no
  * pipelining.  Results do not depend on the chunking. */
 int msnap_set_host_chunks(msnap_handle h, int n_chunks);
+/* Host-pointer entry points: when the caller's coefficient / sample buffers are PINNED host memory (cudaHostAlloc,
+ * cudaHostRegister, torch pin_memory) the kernels store the results straight into them over PCIe, overlapping transfer
+ * and computation (samples: only when no statistics are requested and the batch is a single chunk).  enable = 0 uses
+ * device buffers + cudaMemcpyAsync.  Default: DISABLED -- on B200 / PCIe 5 the SMs' stores to host memory reach about
+ * 24 GB/s while the copy engine moves the same bytes at about 53 GB/s (scripts/e2e_chunks.py).  Results are identical. */
+int msnap_set_zero_copy(msnap_handle h, int enable);
 /* Number of kernels this handle has launched since creation (monotonic; used by bench.py's gpu_launches). */
 long long msnap_launch_count(msnap_handle h);
 

@@ -11,14 +11,15 @@ n_seg = B * NS
 out = {k: torch.empty(shape, dtype=dt).pin_memory().numpy() for k, shape, dt in (
     ("times", (n_seg,), torch.float64), ("coeff", (n_seg, 3, 8), torch.float64), ("max_dev", (B,), torch.float64),
     ("iters", (B,), torch.int32), ("vw_final", (B,), torch.float64), ("sample_offset", (B + 1,), torch.int64),
-    ("samples", (cap, 3), torch.float64), ("stats", (B, 2), torch.float64))}
+    ("samples", (cap, 3), torch.float64))}
 out["flags"] = torch.zeros(B, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
 out["best_s"] = torch.zeros(n_seg, dtype=torch.int32).pin_memory().numpy()
-for chunks in (1, 2, 3, 4, 6, 8):
+for chunks, zc in ((1, True), (1, False), (2, True), (4, True), (8, True)):
     tool.set_host_chunks(chunks)
-    for i in range(5): tool.generate_batch(cfg, wps[i % 4], ns=NS, capacity=cap, out=out)
+    tool.set_zero_copy(zc)
+    for i in range(5): tool.generate_batch(cfg, wps[i % 4], ns=NS, capacity=cap, out=out, stats=False)
     t0 = time.perf_counter()
     n = 40
-    for i in range(n): tool.generate_batch(cfg, wps[i % 4], ns=NS, capacity=cap, out=out)
+    for i in range(n): tool.generate_batch(cfg, wps[i % 4], ns=NS, capacity=cap, out=out, stats=False)
     dt = (time.perf_counter() - t0) / n
-    print(f"B={B} chunks={chunks}: {dt*1e6:.0f} us/step  {B/dt/1e6:.2f} M traj/s", flush=True)
+    print(f"B={B} chunks={chunks} zero_copy={zc}: {dt*1e6:.0f} us/step  {B/dt/1e6:.2f} M traj/s", flush=True)

@@ -185,3 +185,30 @@ def test_pipelined_host_path_equals_single_chunk(tool, ragged):
     assert np.array_equal(part.sample_offset, one.sample_offset)
     assert np.array_equal(part.samples, one.samples[:cap])
     assert (part.flags[:1700] & 2).max() == 0 and (part.flags[1701:] & 2).min() == 2
+
+
+def test_zero_copy_outputs_equal_copied_outputs(tool):
+    """With pinned host buffers the kernels store coefficients and samples straight into them; the bytes must equal
+    those of the copy path, also when the sample buffer is too small."""
+    import torch
+
+    wp, ns = workloads.cfg2(B=600, ns=16, seed=91)
+    cfg = workloads.synthetic_config(4, "shipped")
+    ref = tool.generate_batch(cfg, wp, ns=ns, stats=False)
+    tool.set_zero_copy(True)
+    n_seg, cap = 600 * ns, ref.samples.shape[0] + 5
+    out = {"coeff": torch.empty((n_seg, 3, 8), dtype=torch.float64).pin_memory().numpy(),
+           "samples": torch.full((cap, 3), -7.0, dtype=torch.float64).pin_memory().numpy()}
+    try:
+        zc = tool.generate_batch(cfg, wp, ns=ns, capacity=cap, out=out, stats=False)
+        small = int(ref.sample_offset[300]) + 1
+        sm = {"coeff": out["coeff"], "samples": torch.full((cap, 3), -7.0, dtype=torch.float64).pin_memory().numpy()}
+        with pytest.raises(MsnapError) as e:
+            tool.generate_batch(cfg, wp, ns=ns, capacity=small, out={**sm, "samples": sm["samples"][:small]}, stats=False)
+    finally:
+        tool.set_zero_copy(False)
+    for name in ("times", "coeff", "max_dev", "iters", "vw_final", "best_s", "sample_offset", "samples", "flags"):
+        assert np.array_equal(getattr(ref, name), getattr(zc, name)), name
+    assert np.all(out["samples"][ref.samples.shape[0]:] == -7.0)               # nothing written past the last row
+    assert np.array_equal(e.value.partial.samples, ref.samples[:small])
+    assert np.all(sm["samples"][small:] == -7.0)

@@ -69,6 +69,9 @@ struct msnap_context {
                                       // measured on B200/PCIe 5: SM stores reach ~24 GB/s, the copy engine ~53 GB/s => off
     long long *h_off = nullptr;       // pinned staging for a chunk's sample offsets
     size_t h_off_cap = 0;
+    cudaStream_t aux = nullptr;       // host path: copies the solve's results out while the sampler is still running
+    cudaEvent_t ev_solved = nullptr;  // recorded on `stream` between the solve and the sampler (host path only)
+    bool mark_solved = false;
 };
 
 namespace {
@@ -569,6 +572,7 @@ int generate_dev(msnap_context *h, const msnap_config *cfg, double sd, double v_
     io.mirror_done = mirror_done;
     rc = run_solve<O>(h, bi, sp, io, w);
     if (rc) return rc;
+    if (h->mark_solved) MS_CUDA(h, cudaEventRecord(h->ev_solved, h->stream));
     return run_sample<O>(h, bi, w.coeff, w.T, sd, capacity, sample_offset, samples, stats, flags, s);
 }
 
@@ -681,6 +685,12 @@ int msnap_create(int device, msnap_handle *out) {
         return MSNAP_ERR_CUDA;
     }
     h->stream = h->own_stream;
+    if (cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_solved, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        msnap_destroy(h);
+        return MSNAP_ERR_CUDA;
+    }
     if (const char *e = std::getenv("MSNAP_SPEC_CHUNK")) h->spec_chunk = std::atoi(e);
     if (const char *e = std::getenv("MSNAP_SCAN_COEF_SMEM")) h->scan_coef_smem = std::atoi(e) != 0;
     if (const char *e = std::getenv("MSNAP_HOST_CHUNKS")) h->host_chunks = std::atoi(e);
@@ -699,6 +709,11 @@ int msnap_destroy(msnap_handle h) {
     if (h->d_ttab) cudaFree(h->d_ttab);
     if (h->phase_clocks) cudaFree(h->phase_clocks);
     if (h->h_off) cudaFreeHost(h->h_off);
+    if (h->aux) {
+        cudaStreamSynchronize(h->aux);
+        cudaStreamDestroy(h->aux);
+    }
+    if (h->ev_solved) cudaEventDestroy(h->ev_solved);
     for (msnap_context *k : h->kids) msnap_destroy(k);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -980,6 +995,7 @@ static int host_chunk_enqueue(msnap_context *k, const msnap_config *cfg, double 
                    2 * padded(B * sizeof(double)) + padded(B * sizeof(int)) + padded((B + 1) * sizeof(long long)) +
                    padded((size_t)sample_capacity * 3 * sizeof(double)) + padded((size_t)B * 2 * sizeof(double)) +
                    padded(B * sizeof(unsigned)) + padded(n_seg * sizeof(int));
+    MS_CUDA(k, cudaStreamSynchronize(k->aux));  // copies of this context's previous chunk still read its device buffers
     int rc = arena_reserve(k, k->io, bytes);
     if (rc) return rc;
     if (k->h_off_cap < (size_t)(B + 1)) {
@@ -1019,22 +1035,27 @@ static int host_chunk_enqueue(msnap_context *k, const msnap_config *cfg, double 
     j.samples_direct = nullptr;
     if (k->zero_copy && j.single && !stats_out && samples_out)
         j.samples_direct = static_cast<double *>(device_view_of_pinned(samples_out));
+    k->mark_solved = true;  // ev_solved: the solve's outputs are final, the sampler has not started yet
     MS_DISPATCH_ORDER(cfg->order,
                       rc = generate_dev<O>(k, cfg, sd, va, B, ns_uniform, ns_uniform > 0 ? nullptr : d_off, n_seg, d_wp,
                                            times_out ? d_t : nullptr, coeff_out ? d_c : nullptr, d_md, d_it, d_vw,
                                            best_s_out ? d_bs : nullptr, sample_capacity, j.d_so,
                                            j.samples_direct ? j.samples_direct : j.d_s, stats_out ? d_st : nullptr, d_fl,
                                            coeff_zc ? coeff_zc + j.g0 * m3 : nullptr, &coeff_direct));
+    k->mark_solved = false;
     if (rc) return rc;
-    MS_CUDA(k, cudaMemcpyAsync(k->h_off, j.d_so, (B + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
-    if (times_out)
-        MS_CUDA(k, cudaMemcpyAsync(times_out + j.g0, d_t, n_seg * sizeof(double), cudaMemcpyDeviceToHost, st));
+    // the solve's results leave on the auxiliary stream while the sampler is still running on the main one
+    cudaStream_t ax = k->aux;
+    MS_CUDA(k, cudaStreamWaitEvent(ax, k->ev_solved, 0));
     if (coeff_out && !coeff_direct)
-        MS_CUDA(k, cudaMemcpyAsync(coeff_out + j.g0 * m3, d_c, (size_t)n_seg * m3 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (max_dev_out) MS_CUDA(k, cudaMemcpyAsync(max_dev_out + j.b0, d_md, B * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (vw_final_out) MS_CUDA(k, cudaMemcpyAsync(vw_final_out + j.b0, d_vw, B * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (iters_out) MS_CUDA(k, cudaMemcpyAsync(iters_out + j.b0, d_it, B * sizeof(int), cudaMemcpyDeviceToHost, st));
-    if (best_s_out) MS_CUDA(k, cudaMemcpyAsync(best_s_out + j.g0, d_bs, n_seg * sizeof(int), cudaMemcpyDeviceToHost, st));
+        MS_CUDA(k, cudaMemcpyAsync(coeff_out + j.g0 * m3, d_c, (size_t)n_seg * m3 * sizeof(double), cudaMemcpyDeviceToHost, ax));
+    if (times_out)
+        MS_CUDA(k, cudaMemcpyAsync(times_out + j.g0, d_t, n_seg * sizeof(double), cudaMemcpyDeviceToHost, ax));
+    if (max_dev_out) MS_CUDA(k, cudaMemcpyAsync(max_dev_out + j.b0, d_md, B * sizeof(double), cudaMemcpyDeviceToHost, ax));
+    if (vw_final_out) MS_CUDA(k, cudaMemcpyAsync(vw_final_out + j.b0, d_vw, B * sizeof(double), cudaMemcpyDeviceToHost, ax));
+    if (iters_out) MS_CUDA(k, cudaMemcpyAsync(iters_out + j.b0, d_it, B * sizeof(int), cudaMemcpyDeviceToHost, ax));
+    if (best_s_out) MS_CUDA(k, cudaMemcpyAsync(best_s_out + j.g0, d_bs, n_seg * sizeof(int), cudaMemcpyDeviceToHost, ax));
+    MS_CUDA(k, cudaMemcpyAsync(k->h_off, j.d_so, (B + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
     if (stats_out)
         MS_CUDA(k, cudaMemcpyAsync(stats_out + 2 * j.b0, d_st, (size_t)B * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (flags_out) MS_CUDA(k, cudaMemcpyAsync(flags_out + j.b0, d_fl, B * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
@@ -1127,7 +1148,10 @@ int msnap_generate_batch_host(msnap_handle h, const msnap_config *cfg, double sa
     };
     auto fail = [&](int code, msnap_context *k) {
         if (k != h) h->last_error = k->last_error;
-        for (msnap_context *q : ctx) cudaStreamSynchronize(q->stream);
+        for (msnap_context *q : ctx) {
+            cudaStreamSynchronize(q->aux);
+            cudaStreamSynchronize(q->stream);
+        }
         return code;
     };
     long long rows_base = 0;
@@ -1146,7 +1170,7 @@ int msnap_generate_batch_host(msnap_handle h, const msnap_config *cfg, double sa
     }
     sample_offset_out[B] = rows_base;
     for (msnap_context *q : ctx) {
-        if (cudaStreamSynchronize(q->stream) != cudaSuccess) {
+        if (cudaStreamSynchronize(q->aux) != cudaSuccess || cudaStreamSynchronize(q->stream) != cudaSuccess) {
             h->last_error = "cudaStreamSynchronize(host chunk)";
             cudaGetLastError();
             return MSNAP_ERR_CUDA;

@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--weights", default="shipped", choices=["shipped", "plain"])
     ap.add_argument("--batch", type=int, default=B_DEFAULT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=2,
+                    help="solver handles (each with its own CUDA stream) per GPU that consecutive steps alternate between")
     return ap.parse_args()
 
 
@@ -193,13 +195,20 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    tool = TrajectoryGeneratorTool(local)
-    # All kernels run on ONE explicit stream and the timing events are recorded on that same stream.  (Passing torch's
-    # legacy default stream would hand the library a NULL stream, which it replaces by its own: events recorded on the
-    # default stream would then not see the kernels at all.)
-    stream = torch.cuda.Stream(device=dev)
-    tool.set_stream(stream.cuda_stream)
-    assert stream.cuda_stream != 0
+    # Consecutive steps (independent batches) alternate between S solver handles, each on its own explicit CUDA stream,
+    # so that the solve kernel of one step overlaps the sampler kernel of the previous one -- the way a service that
+    # has several batches in flight would drive the library.  The timing events are recorded on stream 0, which waits
+    # for the other streams' last step before the end event.  (Passing torch's legacy default stream would hand the
+    # library a NULL stream, which it replaces by its own: events recorded there would not see the kernels at all.)
+    S = max(1, args.streams)
+    if ROTATE % S:
+        S = 2  # a buffer set must always be used by the same stream
+    tools = [TrajectoryGeneratorTool(local) for _ in range(S)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
+    for t_, s_ in zip(tools, streams):
+        t_.set_stream(s_.cuda_stream)
+        assert s_.cuda_stream != 0
+    tool, stream = tools[0], streams[0]
     B, m = args.batch, 2 * ORDER
     n_seg = B * NS
 
@@ -222,23 +231,29 @@ def run_b200(args):
         s.flags = torch.empty(B, dtype=torch.int32, device=dev)
         return s
 
-    def step(cfg, s):
-        tool.generate_batch_dev(cfg, s.wp, s.off, s.samples, ns=NS, times=s.times, coeff=s.coeff, max_dev=s.max_dev,
-                                iters=s.iters, vw_final=s.vw, flags=s.flags)
+    def step(cfg, s, which=0):
+        tools[which].generate_batch_dev(cfg, s.wp, s.off, s.samples, ns=NS, times=s.times, coeff=s.coeff,
+                                        max_dev=s.max_dev, iters=s.iters, vw_final=s.vw, flags=s.flags)
 
-    def timed_run(cfg, sets, steps, warmup):
+    def timed_run(cfg, sets, steps, warmup, n_streams):
         for i in range(warmup):
-            step(cfg, sets[i % ROTATE])
+            step(cfg, sets[i % ROTATE], i % n_streams)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = tool.launch_count
+        done = [torch.cuda.Event() for _ in range(n_streams)]
+        l0 = sum(t_.launch_count for t_ in tools)
         e0.record(stream)
+        for k in range(1, n_streams):
+            streams[k].wait_event(e0)                      # nothing of the timed region starts before e0
         for i in range(steps):
-            step(cfg, sets[i % ROTATE])
+            step(cfg, sets[i % ROTATE], i % n_streams)     # buffer set i % 8 is only ever used by stream i % n_streams
+        for k in range(1, n_streams):
+            done[k].record(streams[k])
+            stream.wait_event(done[k])                     # e1 fires after the last step of every stream
         e1.record(stream)
         e1.synchronize()
         torch.cuda.synchronize()
-        launches = tool.launch_count - l0
+        launches = sum(t_.launch_count for t_ in tools) - l0
         ms = max_over_ranks(e0.elapsed_time(e1))
         barrier()
         return ms, launches
@@ -251,7 +266,9 @@ def run_b200(args):
         sets = [make_set(1234 + 1000 * rank + r, cfg) for r in range(ROTATE)]
         headline = weights == args.weights
         steps = args.steps if headline else min(args.steps, 500)
-        ms, launches = timed_run(cfg, sets, steps, max(args.warmup, 3))
+        ms, launches = timed_run(cfg, sets, steps, max(args.warmup, 3), S)
+        ms_1, _ = timed_run(cfg, sets, min(steps, 300), 3, 1) if S > 1 else (ms / steps * min(steps, 300), 0)
+        latency_ms = ms_1 / min(steps, 300)                # one step at a time on one stream
         tot_samples = int(sets[0].off[-1].item())
         iters0 = sets[0].iters.to(torch.int64)
         total_solves = int((iters0 + 1).sum().item())
@@ -297,7 +314,7 @@ def run_b200(args):
                   out["iters"].nbytes + out["vw_final"].nbytes + out["sample_offset"].nbytes +
                   out["flags"].nbytes + out["best_s"].nbytes)
         results[weights] = dict(
-            ms=ms, steps=steps, launches=launches, value=world * B * steps / (ms * 1e-3),
+            ms=ms, steps=steps, launches=launches, value=world * B * steps / (ms * 1e-3), latency_ms=latency_ms,
             e2e=dict(value=world * B * e2e_steps / e2e_s, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                      steps=e2e_steps, ms_per_step=e2e_s / e2e_steps * 1e3),
             prof=prof, dom=dom, dom_ms=dom_ms, all_kernels_ms=all_ms, abytes=abytes, aflops=aflops, kbytes=kbytes,
@@ -356,10 +373,14 @@ def run_b200(args):
             "config": {"workload": workload_name(args.weights, B), "trajectories_per_gpu_per_step": B,
                        "l2_policy": f"inputs and outputs rotate over {ROTATE} distinct buffer sets "
                                     f"({h['footprint'] / 1e6:.0f} MB > 126 MB L2); workspace is reused",
+                       "streams_per_gpu": S, "single_stream_ms_per_step": h["latency_ms"],
+                       "pipelining": f"consecutive steps (independent batches) alternate between {S} solver handles / CUDA "
+                                     f"streams per GPU; ms_per_step = timed region / steps",
                        "samples_per_step": h["samples"], "mean_reweight_iters": h["mean_iters"],
                        "flagged_trajectories": h["flags_bad"], "parallelism": f"trajectory-sharded x{world}, no collective"},
             "e2e": h["e2e"], "gpu_launches": h["launches"], "clocks": clocks, "roofline": roof(h, args.weights),
-            "variants": {w: {"value": r["value"], "ms_per_step": r["ms"] / r["steps"], "e2e": r["e2e"],
+            "variants": {w: {"value": r["value"], "ms_per_step": r["ms"] / r["steps"],
+                             "single_stream_ms_per_step": r["latency_ms"], "e2e": r["e2e"],
                              "roofline": roof(r, w), "workload": workload_name(w, B)}
                          for w, r in results.items() if w != args.weights},
         }
@@ -376,7 +397,8 @@ def run_b200(args):
             except Exception as e:  # the baseline must never take the GPU number down with it
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": repr(e)}
         print(json.dumps(line))
-    tool.close()
+    for t_ in tools:
+        t_.close()
     if world > 1:
         dist.destroy_process_group()
 

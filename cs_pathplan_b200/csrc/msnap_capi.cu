@@ -65,6 +65,7 @@ struct msnap_context {
     // stream, own arenas), so that a chunk's kernels overlap the previous chunk's device-to-host copies
     std::vector<msnap_context *> kids;
     int host_chunks = 0;              // 0 = automatic (MSNAP_HOST_CHUNKS)
+    bool discard_state = true;        // fused solve: discard dead sweep state from L2 (MSNAP_DISCARD_STATE)
     bool zero_copy = false;           // host path: store big results straight into pinned caller buffers (MSNAP_ZERO_COPY);
                                       // measured on B200/PCIe 5: SM stores reach ~24 GB/s, the copy engine ~53 GB/s => off
     long long *h_off = nullptr;       // pinned staging for a chunk's sample offsets
@@ -304,6 +305,7 @@ int run_solve(msnap_context *h, const BatchIdx &bi, const SolveParams &sp, const
         fp.ht = ht;
         fp.times_out = io.times_in ? nullptr : w.T;  // allocated times go to the workspace (the sampler reads them)
         fp.coeff_out = w.coeff;
+        fp.discard_state = h->discard_state ? 1 : 0;
         fp.coeff_mirror = io.coeff_mirror;
         if (io.coeff_mirror && io.mirror_done) *io.mirror_done = true;
         fp.max_dev_out = io.max_dev_out;
@@ -695,6 +697,7 @@ int msnap_create(int device, msnap_handle *out) {
     if (const char *e = std::getenv("MSNAP_SCAN_COEF_SMEM")) h->scan_coef_smem = std::atoi(e) != 0;
     if (const char *e = std::getenv("MSNAP_HOST_CHUNKS")) h->host_chunks = std::atoi(e);
     if (const char *e = std::getenv("MSNAP_ZERO_COPY")) h->zero_copy = std::atoi(e) != 0;
+    if (const char *e = std::getenv("MSNAP_DISCARD_STATE")) h->discard_state = std::atoi(e) != 0;
     *out = h;
     return MSNAP_OK;
 }

@@ -49,6 +49,7 @@ struct FusedParams {
     SolveParams sp;
     const double *ht;        // HT table of this order in global memory
     double *times_out, *coeff_out, *max_dev_out, *vw_final_out;
+    int discard_state;       // drop the dead scratch lines from L2 at tile end (less write-back, a few discards per thread)
     double *coeff_mirror;    // optional second destination of the coefficients (the caller's pinned host buffer)
     int *iters_out, *best_s_out;
     unsigned *flags;
@@ -520,7 +521,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_c
         __syncthreads();  // flags[b] is OR-ed below
         // The speculative sweep state in this CTA's scratch slot is dead from here on: tell L2 to drop the lines instead
         // of writing them back to HBM when they are evicted (the slot is rewritten before it is read again).
-        if (nit > 1) {
+        if (nit > 1 && p.discard_state) {
             char *sb = reinterpret_cast<char *>(slot);
             const int n_lines = (int)(((size_t)nr * D::NSTATE * GL * sizeof(double)) / 128);
             for (int i = tid; i < n_lines; i += FUSED_THREADS)

@@ -552,9 +552,16 @@ int generate_dev(msnap_context *h, const msnap_config *cfg, double sd, double v_
     }
     const FusedPlan f = plan_fused<O>(h, bi, sp);
     const bool spec = use_generic_spec<O>(h, n_seg, sp);
+    const bool ragged = bi.ns_uniform <= 0 && B < 2000000000LL;
     int rc = arena_reserve(h, h->ws, solve_ws_bytes<O>(n_seg, B, true, coeff_out == nullptr, f, spec) +
-                                        sample_ws_bytes(n_seg, B, bi.ns_uniform, h->policy, h->sm_count));
+                                        sample_ws_bytes(n_seg, B, bi.ns_uniform, h->policy, h->sm_count) +
+                                        (ragged ? padded(n_seg * sizeof(int)) : 0));
     if (rc) return rc;
+    if (ragged) {  // segment -> trajectory map, so that the per-segment kernels need no binary search
+        int *st = arena_take<int>(h->ws, n_seg);
+        MS_LAUNCH(h, k_seg_traj, grid_for(B * 32, 256), 256, B, seg_offset, st);
+        bi.seg_traj = st;
+    }
     SolveWs w;
     carve_solve_ws<O>(h->ws, n_seg, B, true, coeff_out, f, spec, w);
     SampleWs s;

@@ -22,6 +22,7 @@ struct BatchIdx {
     long long n_seg;              // total segments
     int ns_uniform;               // > 0: uniform batch, seg_offset unused
     const long long *seg_offset;  // [B+1] device, or nullptr
+    const int *seg_traj = nullptr;  // optional [n_seg] trajectory of every segment (k_seg_traj): replaces the search
     __device__ __forceinline__ long long seg_begin(long long b) const {
         return ns_uniform > 0 ? b * ns_uniform : seg_offset[b];
     }
@@ -31,6 +32,12 @@ struct BatchIdx {
             b = g / ns_uniform;
             k = (int)(g - b * ns_uniform);
             ns = ns_uniform;
+            return;
+        }
+        if (seg_traj) {
+            b = seg_traj[g];
+            k = (int)(g - seg_offset[b]);
+            ns = (int)(seg_offset[b + 1] - seg_offset[b]);
             return;
         }
         long long lo = 0, hi = B;  // find b with seg_offset[b] <= g < seg_offset[b+1]
@@ -43,6 +50,14 @@ struct BatchIdx {
         ns = (int)(seg_offset[lo + 1] - seg_offset[lo]);
     }
 };
+
+// Warp per trajectory: seg_traj[g] = b for every segment of trajectory b (ragged batches; one pass per call).
+__global__ void k_seg_traj(long long B, const long long *__restrict__ seg_offset, int *__restrict__ seg_traj) {
+    const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    if (w >= B) return;
+    const long long g1 = seg_offset[w + 1];
+    for (long long g = seg_offset[w] + (threadIdx.x & 31); g < g1; g += 32) seg_traj[g] = (int)w;
+}
 
 struct SolveParams {
     double pw;           // path_weight (penalty active iff > 0)

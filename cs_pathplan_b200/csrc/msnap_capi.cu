@@ -890,6 +890,7 @@ int msnap_solve_qp_batch_dev(msnap_handle h, int order, double path_weight, doub
     int rc = check_batch(B, ns_uniform, seg_offset, waypoints);
     if (rc) return rc;
     if (!times || !coeff_out) return MSNAP_ERR_INVALID_ARG;
+    if (reinterpret_cast<uintptr_t>(coeff_out) & 15) return MSNAP_ERR_INVALID_ARG;  // 128-bit stores
     if (B == 0) return MSNAP_OK;
     DeviceGuard guard(h->device);
     long long n_seg = 0;
@@ -959,6 +960,7 @@ int msnap_generate_batch_dev(msnap_handle h, const msnap_config *cfg, double sam
     int rc = check_batch(B, ns_uniform, seg_offset, waypoints);
     if (rc) return rc;
     if (!sample_offset_out || (!samples_out && sample_capacity > 0) || sample_capacity < 0) return MSNAP_ERR_INVALID_ARG;
+    if (reinterpret_cast<uintptr_t>(coeff_out) & 15) return MSNAP_ERR_INVALID_ARG;  // 128-bit stores
     if (B == 0) return MSNAP_OK;
     DeviceGuard guard(h->device);
     long long n_seg = 0;

@@ -15,7 +15,8 @@
  *   - waypoints : [sum(ns_b) + B][3] row-major (east, north, up) == std::vector<ENUPoint> (uavPathPlanning.hpp:152-156)
  *   - times     : [sum(ns_b)] segment durations in seconds
  *   - coeff     : [sum(ns_b)][3][2*order]  = the reference's PolyCoeff rows (ms.cpp:220-225): per segment,
- *                 x | y | z blocks, highest power first, local time t in [0, T_k] (no time scaling)
+ *                 x | y | z blocks, highest power first, local time t in [0, T_k] (no time scaling).  DEVICE coefficient
+ *                 buffers must be 16-byte aligned (128-bit stores); cudaMalloc / torch allocations are.
  *   - samples   : [rows][3] row-major; trajectory b owns rows [sample_offset[b], sample_offset[b+1])
  *   - Functions suffixed _dev take DEVICE pointers for every array argument and only enqueue work on the handle's
  *     stream (no host synchronisation).  Functions suffixed _host take HOST pointers (pinned memory makes the copies

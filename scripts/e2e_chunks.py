@@ -14,7 +14,7 @@ out = {k: torch.empty(shape, dtype=dt).pin_memory().numpy() for k, shape, dt in 
     ("samples", (cap, 3), torch.float64))}
 out["flags"] = torch.zeros(B, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
 out["best_s"] = torch.zeros(n_seg, dtype=torch.int32).pin_memory().numpy()
-for chunks, zc in ((1, True), (1, False), (2, True), (4, True), (8, True)):
+for chunks, zc in ((1, False), (2, False), (3, False), (4, False), (1, True)):
     tool.set_host_chunks(chunks)
     tool.set_zero_copy(zc)
     for i in range(5): tool.generate_batch(cfg, wps[i % 4], ns=NS, capacity=cap, out=out, stats=False)

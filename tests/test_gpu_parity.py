@@ -212,3 +212,20 @@ def test_zero_copy_outputs_equal_copied_outputs(tool):
     assert np.all(out["samples"][ref.samples.shape[0]:] == -7.0)               # nothing written past the last row
     assert np.array_equal(e.value.partial.samples, ref.samples[:small])
     assert np.all(sm["samples"][small:] == -7.0)
+
+
+def test_misaligned_device_coefficient_buffer_is_rejected(tool):
+    import torch
+
+    wp, ns = workloads.cfg2(B=4, ns=4)
+    cfg = workloads.synthetic_config(4, "plain")
+    dev = torch.device("cuda", 0)
+    d_wp = torch.from_numpy(wp).to(dev)
+    off = torch.empty(5, dtype=torch.int64, device=dev)
+    samples = torch.empty((4000, 3), dtype=torch.float64, device=dev)
+    raw = torch.empty(4 * ns * 24 + 1, dtype=torch.float64, device=dev)
+    with pytest.raises(MsnapError):
+        tool.generate_batch_dev(cfg, d_wp, off, samples, ns=ns, coeff=raw[1:])     # 8-byte aligned only
+    tool.generate_batch_dev(cfg, d_wp, off, samples, ns=ns, coeff=raw[:-1])
+    tool.synchronize()
+    assert int(off[-1]) > 8

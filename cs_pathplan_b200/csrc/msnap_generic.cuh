@@ -603,6 +603,50 @@ struct RowSink {
     }
 };
 
+// Row sink of the thread-per-segment write kernel.  A thread's rows are consecutive, so an even row is held back until
+// its successor arrives and the two leave as three 128-bit stores (48 bytes from a 16-byte aligned address): the kernel
+// is bound by the number of store transactions, not by bytes.  flush() must be called after the last row.
+struct PairRowSink {
+    double *__restrict__ samples;
+    long long capacity;
+    bool *dropped;
+    bool vec;          // the sample buffer is 16-byte aligned
+    bool *have;        // a row is held back
+    long long *r0;
+    double *v0;        // [3]
+    __device__ __forceinline__ void scalar(long long r, const double *v) const {
+        samples[3 * r] = v[0]; samples[3 * r + 1] = v[1]; samples[3 * r + 2] = v[2];
+    }
+    __device__ __forceinline__ void flush() const {
+        if (*have) scalar(*r0, v0);
+        *have = false;
+    }
+    __device__ __forceinline__ void operator()(long long r, const double (&v)[3]) const {
+        if (r >= capacity) {
+            *dropped = true;
+            return;
+        }
+        if (*have) {
+            if (r == *r0 + 1) {
+                double2 *dst = reinterpret_cast<double2 *>(samples + 3 * *r0);
+                dst[0] = make_double2(v0[0], v0[1]);
+                dst[1] = make_double2(v0[2], v[0]);
+                dst[2] = make_double2(v[1], v[2]);
+                *have = false;
+                return;
+            }
+            flush();
+        }
+        if (vec && (r & 1) == 0) {
+            *r0 = r;
+            v0[0] = v[0]; v0[1] = v[1]; v0[2] = v[2];
+            *have = true;
+        } else {
+            scalar(r, v);
+        }
+    }
+};
+
 // ---- generic (CSR) path: one kernel per pass, intermediates in the HBM workspace ----------------------------------
 // k_count: thread per segment.  seg_count[g] = n (usable mask) or -n-1 (write pass must re-run the acceptance loop).
 template <int O>
@@ -680,8 +724,11 @@ __global__ void __launch_bounds__(128) k_write(BatchIdx bi, const double *__rest
     load_coeff<O>(coeff, g, c);
     const double Tk = T[g];
     const AcceptTest accept(sample_distance);
-    bool dropped = false;
-    const RowSink put{samples, capacity, &dropped};
+    bool dropped = false, have = false;
+    long long held_row = 0;
+    double held[3];
+    const PairRowSink put{samples, capacity, &dropped, (reinterpret_cast<unsigned long long>(samples) & 15ull) == 0,
+                          &have, &held_row, held};
     const long long row0 = sample_offset[b];
     if (k == 0) {  // very first point of the trajectory (ms.cpp:132-137)
         eval_xyz<O>(c, 0.0, cur);
@@ -693,6 +740,7 @@ __global__ void __launch_bounds__(128) k_write(BatchIdx bi, const double *__rest
         eval_xyz<O>(c, Tk, cur);
         put(sample_offset[b + 1] - 1, cur);
     }
+    put.flush();
     if (dropped && flags) atomicOr(flags + b, 2u);
 }
 

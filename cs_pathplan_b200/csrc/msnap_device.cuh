@@ -304,6 +304,40 @@ struct L2KeepMem {
     }
 };
 
+// Consecutive fields F0 .. F0+N-1 of a row.  Accessors whose rows are contiguous and 16-byte aligned (Rows::VEC: the
+// per-trajectory rows of the generic path in HBM) move them as 128-bit words: those sweeps touch 32 different cache lines
+// per warp access and are bound by the number of load/store transactions.  All other accessors go field by field.
+template <class Rows, int F0, int N>
+__device__ __forceinline__ void row_load(const double *row, double (&out)[N]) {
+    if constexpr (Rows::VEC) {
+        constexpr int H = F0 & 1;
+        if (H) out[0] = row[F0];
+#pragma unroll
+        for (int k = H; k + 1 < N; k += 2) {
+            const double2 v = *reinterpret_cast<const double2 *>(row + F0 + k);
+            out[k] = v.x;
+            out[k + 1] = v.y;
+        }
+        if ((N - H) & 1) out[N - 1] = row[F0 + N - 1];
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) out[k] = Rows::Mem::ld(row + (F0 + k) * Rows::FS);
+    }
+}
+template <class Rows, int F0, int N>
+__device__ __forceinline__ void row_store(double *row, const double (&in)[N]) {
+    if constexpr (Rows::VEC) {
+        constexpr int H = F0 & 1;
+        if (H) row[F0] = in[0];
+#pragma unroll
+        for (int k = H; k + 1 < N; k += 2) *reinterpret_cast<double2 *>(row + F0 + k) = make_double2(in[k], in[k + 1]);
+        if ((N - H) & 1) row[F0 + N - 1] = in[N - 1];
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) Rows::Mem::st(row + (F0 + k) * Rows::FS, in[k]);
+    }
+}
+
 // ---- twisted (two-sided) elimination ---------------------------------------------------------------------------
 // The chain of n block rows is split at a row m and eliminated from BOTH ends towards it:
 //   top half     rows 0 .. m-1      D'_j = D_j - U_{j-1}' W_{j-1},  z_j = P_j (r_j - U_{j-1}' z_{j-1}),  W_j = P_j U_j
@@ -321,14 +355,24 @@ struct L2KeepMem {
 __host__ __device__ constexpr int split_row(int n_rows, bool balanced) { return balanced ? n_rows / 2 : n_rows - 1; }
 
 // coupling block of a base row in the orientation the recurrences use: C[t][p] = U[t][p], or U[p][t] when transposed
-template <int O, int BFS>
+template <int O, class BaseAt>
 __device__ __forceinline__ void load_coupling(const double *b, bool transposed, double (&C)[(O - 1) * (O - 1)]) {
     using D = Dim<O>;
     constexpr int B = D::B;
+    if constexpr (BaseAt::VEC) {
+        double U[B * B];
+        row_load<BaseAt, D::F_U, B * B>(b, U);
 #pragma unroll
-    for (int t = 0; t < B; ++t)
+        for (int t = 0; t < B; ++t)
 #pragma unroll
-        for (int p = 0; p < B; ++p) C[t * B + p] = b[(D::F_U + (transposed ? p * B + t : t * B + p)) * BFS];
+            for (int p = 0; p < B; ++p) C[t * B + p] = transposed ? U[p * B + t] : U[t * B + p];
+    } else {
+#pragma unroll
+        for (int t = 0; t < B; ++t)
+#pragma unroll
+            for (int p = 0; p < B; ++p)
+                C[t * B + p] = b[(D::F_U + (transposed ? p * B + t : t * B + p)) * BaseAt::FS];
+    }
 }
 
 // Elimination of one half: local rows i = 0 .. cnt-1, outermost first; row index j = mirror ? n_rows-1-i : i.
@@ -338,7 +382,6 @@ __device__ __forceinline__ bool elim_half(int n_rows, int cnt, bool mirror, doub
                                           const StateAt state_at) {
     using D = Dim<O>;
     constexpr int B = D::B, ND = D::ND, NR = D::NR, NU = D::NU;
-    constexpr int bfs = BaseAt::FS, sfs = StateAt::FS;
     bool ok = true;
     double W[NU];  // W of the previously eliminated row
     double z[NR];  // z of the previously eliminated row, [r][axis]
@@ -349,16 +392,14 @@ __device__ __forceinline__ bool elim_half(int n_rows, int cnt, bool mirror, doub
         const double *b = base_at(j);
         double *s = state_at(j);
         double d[ND], r[NR];
-#pragma unroll
-        for (int k = 0; k < ND; ++k) d[k] = b[(D::F_D + k) * bfs];
-#pragma unroll
-        for (int k = 0; k < NR; ++k) r[k] = b[(D::F_R + k) * bfs];
+        row_load<BaseAt, D::F_D, ND>(b, d);
+        row_load<BaseAt, D::F_R, NR>(b, r);
         d[0] += add00;
         if (i > 0) {
             // coupling to the previously eliminated row: U_{j-1} (stored in row j-1), or U_j' (row j) when mirrored;
             // re-read (a broadcast LDS) rather than carried in registers
             double C[NU];
-            load_coupling<O, bfs>(mirror ? b : base_at(j - 1), mirror, C);
+            load_coupling<O, BaseAt>(mirror ? b : base_at(j - 1), mirror, C);
 #pragma unroll
             for (int p = 0; p < B; ++p) {
 #pragma unroll
@@ -388,12 +429,11 @@ __device__ __forceinline__ bool elim_half(int n_rows, int cnt, bool mirror, doub
                 for (int t = 1; t < B; ++t) acc = fma(P[sym(p, t)], r[t * 3 + x], acc);
                 z[p * 3 + x] = acc;
             }
-#pragma unroll
-        for (int k = 0; k < NR; ++k) StateAt::Mem::st(s + (D::SX + k) * sfs, z[k]);
+        row_store<StateAt, D::SX, NR>(s, z);
         {
             // coupling to the next row towards the split row: U_j (row j), or U_{j-1}' (row j-1) when mirrored
             double N[NU];
-            load_coupling<O, bfs>(mirror ? base_at(j - 1) : b, mirror, N);
+            load_coupling<O, BaseAt>(mirror ? base_at(j - 1) : b, mirror, N);
 #pragma unroll
             for (int p = 0; p < B; ++p)
 #pragma unroll
@@ -403,8 +443,7 @@ __device__ __forceinline__ bool elim_half(int n_rows, int cnt, bool mirror, doub
                     for (int t = 1; t < B; ++t) acc = fma(P[sym(p, t)], N[t * B + q], acc);
                     W[p * B + q] = acc;
                 }
-#pragma unroll
-            for (int k = 0; k < NU; ++k) StateAt::Mem::st(s + (D::SW + k) * sfs, W[k]);
+            row_store<StateAt, D::SW, NU>(s, W);
         }
     }
     return ok;
@@ -417,24 +456,19 @@ __device__ __forceinline__ bool elim_middle(int n_rows, int m, double add00, con
                                             const StateAt state_at) {
     using D = Dim<O>;
     constexpr int B = D::B, ND = D::ND, NR = D::NR, NU = D::NU;
-    constexpr int bfs = BaseAt::FS, sfs = StateAt::FS;
     const double *b = base_at(m);
     double d[ND], r[NR];
-#pragma unroll
-    for (int k = 0; k < ND; ++k) d[k] = b[(D::F_D + k) * bfs];
-#pragma unroll
-    for (int k = 0; k < NR; ++k) r[k] = b[(D::F_R + k) * bfs];
+    row_load<BaseAt, D::F_D, ND>(b, d);
+    row_load<BaseAt, D::F_R, NR>(b, r);
     d[0] += add00;
 #pragma unroll
     for (int side = 0; side < 2; ++side) {  // 0: last row of the top half (m-1), 1: last row of the bottom half (m+1)
         if (side == 0 ? m > 0 : m < n_rows - 1) {
             const double *sn = state_at(side == 0 ? m - 1 : m + 1);
             double C[NU], W[NU], z[NR];
-            load_coupling<O, bfs>(side == 0 ? base_at(m - 1) : b, side != 0, C);
-#pragma unroll
-            for (int k = 0; k < NU; ++k) W[k] = StateAt::Mem::ld(sn + (D::SW + k) * sfs);
-#pragma unroll
-            for (int k = 0; k < NR; ++k) z[k] = StateAt::Mem::ld(sn + (D::SX + k) * sfs);
+            load_coupling<O, BaseAt>(side == 0 ? base_at(m - 1) : b, side != 0, C);
+            row_load<StateAt, D::SW, NU>(sn, W);
+            row_load<StateAt, D::SX, NR>(sn, z);
 #pragma unroll
             for (int p = 0; p < B; ++p) {
 #pragma unroll
@@ -456,7 +490,7 @@ __device__ __forceinline__ bool elim_middle(int n_rows, int m, double add00, con
     }
     double P[ND];
     const bool ok = sym_inverse<B>(d, P);
-    double *s = state_at(m);
+    double xm[NR];
 #pragma unroll
     for (int p = 0; p < B; ++p)
 #pragma unroll
@@ -464,8 +498,9 @@ __device__ __forceinline__ bool elim_middle(int n_rows, int m, double add00, con
             double acc = P[sym(p, 0)] * r[x];
 #pragma unroll
             for (int t = 1; t < B; ++t) acc = fma(P[sym(p, t)], r[t * 3 + x], acc);
-            StateAt::Mem::st(s + (D::SX + p * 3 + x) * sfs, acc);
+            xm[p * 3 + x] = acc;
         }
+    row_store<StateAt, D::SX, NR>(state_at(m), xm);
     return ok;
 }
 
@@ -482,6 +517,7 @@ __device__ __forceinline__ bool thomas_forward(int n_rows, int m, double add00, 
 // Where the back-substitution leaves the solution.  NoOut: nowhere (a speculative lane only needs its max deviation).
 struct NoOut {
     static constexpr bool ENABLED = false;
+    static constexpr bool VEC = false;
     static constexpr int FS = 1;
     using Mem = PlainMem;
     __device__ __forceinline__ double *operator()(int) const { return nullptr; }
@@ -491,16 +527,14 @@ struct NoOut {
 // One back-substitution step: x_j = z_j - W_j x_n  (x_n = the solution of the neighbouring row nearer to the split row).
 //   s: state row j (z, W) with field stride SFS;
 //   xo: where x_j is stored ([r][axis], field stride XOut::FS) if XOut::ENABLED.
-template <int O, int SFS, class SMem, class XOut>
+template <int O, class StateAt, class XOut>
 __device__ __forceinline__ void thomas_back_step(const double *s, double *xo, const double (&xn)[3 * (O - 1)],
                                                  double (&x)[3 * (O - 1)]) {
     using D = Dim<O>;
     constexpr int B = D::B, NR = D::NR;
     double W[D::NU];
-#pragma unroll
-    for (int i = 0; i < NR; ++i) x[i] = SMem::ld(s + (D::SX + i) * SFS);
-#pragma unroll
-    for (int i = 0; i < D::NU; ++i) W[i] = SMem::ld(s + (D::SW + i) * SFS);
+    row_load<StateAt, D::SX, NR>(s, x);
+    row_load<StateAt, D::SW, D::NU>(s, W);
 #pragma unroll
     for (int p = 0; p < B; ++p)
 #pragma unroll
@@ -510,10 +544,7 @@ __device__ __forceinline__ void thomas_back_step(const double *s, double *xo, co
             for (int q = 0; q < B; ++q) acc = fma(-W[p * B + q], xn[q * 3 + a], acc);
             x[p * 3 + a] = acc;
         }
-    if (XOut::ENABLED) {
-#pragma unroll
-        for (int i = 0; i < NR; ++i) XOut::Mem::st(xo + (D::SX + i) * XOut::FS, x[i]);
-    }
+    if constexpr (XOut::ENABLED) row_store<XOut, D::SX, NR>(xo, x);
 }
 
 // Squared deviation ratio of one segment (ms.cpp:594-617):  || p(t*) - L(t*) ||^2 / |P_{k+1} - P_k|^2.
@@ -562,13 +593,9 @@ __device__ __forceinline__ double back_half(int n_rows, int m, bool mirror, cons
     double m2 = m2_in;
     double xn[NR], pn[3];  // solution and position of the row nearer to the split row
     {
-        const double *sm = state_at(m);
-#pragma unroll
-        for (int i = 0; i < NR; ++i) xn[i] = StateAt::Mem::ld(sm + (D::SX + i) * StateAt::FS);
-        if (XOut::ENABLED && !mirror) {  // x_m itself (written once, by the top half)
-            double *xo = xout(m);
-#pragma unroll
-            for (int i = 0; i < NR; ++i) XOut::Mem::st(xo + (D::SX + i) * XOut::FS, xn[i]);
+        row_load<StateAt, D::SX, NR>(state_at(m), xn);
+        if constexpr (XOut::ENABLED) {
+            if (!mirror) row_store<XOut, D::SX, NR>(xout(m), xn);  // x_m itself (written once, by the top half)
         }
         pos(m + 1, pn);
     }
@@ -578,7 +605,7 @@ __device__ __forceinline__ double back_half(int n_rows, int m, bool mirror, cons
     for (int i = 0; i < cnt; ++i, j += step) {
         if (i + 1 < cnt) state_at.prefetch(j + step);
         double x[NR], po[3];
-        thomas_back_step<O, StateAt::FS, typename StateAt::Mem, XOut>(state_at(j), xout(j), xn, x);
+        thomas_back_step<O, StateAt, XOut>(state_at(j), xout(j), xn, x);
         pos(j + 1, po);
         if (EVAL) {  // the segment between rows j and j -+ 1: segment j+1 (top half) or j (bottom half)
             if (EVAL) segx_at.prefetch(mirror ? j + 1 : j);

@@ -84,6 +84,8 @@ template <int O>
 struct FBaseRows {
     const double *p;
     static constexpr int FS = 1;
+    static constexpr bool VEC = false;  // odd row pitch
+    using Mem = PlainMem;
     __device__ __forceinline__ const double *operator()(int j) const { return p + j * FusedSmem<O>::BS; }
     __device__ __forceinline__ void prefetch(int) const {}
 };
@@ -91,6 +93,8 @@ template <int O>
 struct FSegxRows {
     const double *p;
     static constexpr int FS = 1;
+    static constexpr bool VEC = false;
+    using Mem = PlainMem;
     __device__ __forceinline__ const double *operator()(int k) const { return p + k * FusedSmem<O>::XS; }
     __device__ __forceinline__ void prefetch(int) const {}
 };
@@ -106,6 +110,7 @@ template <int O, int LANES, class MemT = PlainMem>
 struct FStateRows {
     double *p;  // this lane's column
     static constexpr int FS = LANES;
+    static constexpr bool VEC = false;
     static constexpr bool ENABLED = true;  // usable as the solution sink of thomas_backward
     using Mem = MemT;
     __device__ __forceinline__ double *operator()(int j) const { return p + (size_t)j * (Dim<O>::NSTATE * LANES); }

@@ -149,6 +149,7 @@ struct GlobalRows {
     double *p;
     static constexpr int FS = 1;
     static constexpr bool ENABLED = true;  // usable as the solution sink of thomas_backward
+    static constexpr bool VEC = NF % 2 == 0;  // rows are 16-byte aligned (workspace arrays are 256-byte aligned): row_load
     using Mem = PlainMem;
     __device__ __forceinline__ double *operator()(int j) const { return p + (size_t)j * NF; }
     // The sweeps are one dependent chain per thread, so a row's loads would otherwise pay the full L2/HBM latency:
@@ -297,6 +298,7 @@ struct SpecRows {
     double *p;  // this lane's column of the first row
     static constexpr int FS = NIT1;
     static constexpr bool ENABLED = true;
+    static constexpr bool VEC = false;
     using Mem = PlainMem;
     __device__ __forceinline__ double *operator()(int j) const { return p + (size_t)j * (Dim<O>::NSTATE * NIT1); }
     __device__ __forceinline__ void prefetch(int) const {}

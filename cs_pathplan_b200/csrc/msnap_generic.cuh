@@ -75,6 +75,32 @@ __device__ __forceinline__ void boundary_of(const SolveParams &sp, long long b, 
     load_boundary<O>(bc, v, a);
 }
 
+// Row accessors of the generic path: contiguous rows in the HBM workspace, field stride 1.
+template <int NF>
+struct GlobalRows {
+    double *p;
+    static constexpr int FS = 1;
+    static constexpr bool ENABLED = true;  // usable as the solution sink of thomas_backward
+    static constexpr bool VEC = NF % 2 == 0;  // rows are 16-byte aligned (workspace arrays are 256-byte aligned): row_load
+    using Mem = PlainMem;
+    __device__ __forceinline__ double *operator()(int j) const { return p + (size_t)j * NF; }
+    // The sweeps are one dependent chain per thread, so a row's loads would otherwise pay the full L2/HBM latency:
+    // pull row j into L1 while the previous row is being computed.
+    __device__ __forceinline__ void prefetch(int j) const {
+        const char *q = reinterpret_cast<const char *>(p + (size_t)j * NF);
+#pragma unroll
+        for (int o = 0; o < NF * 8 + 127; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(q + o));
+    }
+};
+struct GlobalPos {  // waypoint positions of one trajectory, [w][3]
+    const double *p;
+    __device__ __forceinline__ void operator()(int w, double (&out)[3]) const {
+        out[0] = p[3 * w];
+        out[1] = p[3 * w + 1];
+        out[2] = p[3 * w + 2];
+    }
+};
+
 // ------------------------------------------------------------------------------------------------ k_times
 // T_k = max(|P_{k+1} - P_k| / V_avg, min_time) -- plain IEEE mul/add (no FMA contraction) so the allocated
 // times, and with them the sampler's candidate grid, are bit-identical to the reference's (ms.cpp:63-72).
@@ -111,7 +137,7 @@ __global__ void k_rows(BatchIdx bi, SolveParams sp, const double *__restrict__ w
         time_powers<O>(Tc, ip, pT);
         const int s = s_star[g];
         hermite_at<O>(ht, s, pT, h);
-        double *x = segx + g * D::NSEGX;
+        double x[D::NSEGX];
 #pragma unroll
         for (int i = 0; i < 2 * O; ++i) x[i] = h[i];
         const double tau = (double)s * 0.0625;
@@ -124,6 +150,7 @@ __global__ void k_rows(BatchIdx bi, SolveParams sp, const double *__restrict__ w
         }
         const double len = sqrt(l2);
         x[2 * O + 3] = len > 1e-6 ? 1.0 / l2 : 0.0;  // 1/len^2: deviations are compared squared
+        row_store<GlobalRows<D::NSEGX>, 0, D::NSEGX>(segx + g * D::NSEGX, x);
     }
     if (k == 0) return;
     Boundary<O> bc;
@@ -135,8 +162,10 @@ __global__ void k_rows(BatchIdx bi, SolveParams sp, const double *__restrict__ w
         P0[a] = p[a];
         Pp[a] = p[a + 3];
     }
+    double row[D::NBASE];
     assemble_row<O>(T[g - 1], Tc, Pm, P0, Pp, k == 1, k == ns - 1, bc, use_pw, sp.pw, use_pw ? s_star[g - 1] : 0,
-                    use_pw ? s_star[g] : 0, ht, base + g * D::NBASE, 1);
+                    use_pw ? s_star[g] : 0, ht, row, 1);
+    row_store<GlobalRows<D::NBASE>, 0, D::NBASE>(base + g * D::NBASE, row);
 }
 
 // ------------------------------------------------------------------------------------------------ k_thomas
@@ -144,31 +173,6 @@ __global__ void k_rows(BatchIdx bi, SolveParams sp, const double *__restrict__ w
 // loop of ms.cpp:76-90: solve, measure max deviation at the recorded t*, double vel_zero_weight while
 // max_dev > 0.2 and iter < max_iter.  The final x stays in state[]; per-trajectory results go to the out arrays.
 // Row accessors of the generic path: contiguous rows in the HBM workspace, field stride 1.
-template <int NF>
-struct GlobalRows {
-    double *p;
-    static constexpr int FS = 1;
-    static constexpr bool ENABLED = true;  // usable as the solution sink of thomas_backward
-    static constexpr bool VEC = NF % 2 == 0;  // rows are 16-byte aligned (workspace arrays are 256-byte aligned): row_load
-    using Mem = PlainMem;
-    __device__ __forceinline__ double *operator()(int j) const { return p + (size_t)j * NF; }
-    // The sweeps are one dependent chain per thread, so a row's loads would otherwise pay the full L2/HBM latency:
-    // pull row j into L1 while the previous row is being computed.
-    __device__ __forceinline__ void prefetch(int j) const {
-        const char *q = reinterpret_cast<const char *>(p + (size_t)j * NF);
-#pragma unroll
-        for (int o = 0; o < NF * 8 + 127; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(q + o));
-    }
-};
-struct GlobalPos {  // waypoint positions of one trajectory, [w][3]
-    const double *p;
-    __device__ __forceinline__ void operator()(int w, double (&out)[3]) const {
-        out[0] = p[3 * w];
-        out[1] = p[3 * w + 1];
-        out[2] = p[3 * w + 2];
-    }
-};
-
 template <int O>
 __global__ void k_thomas(BatchIdx bi, SolveParams sp, const double *__restrict__ wp, double *base,
                          double *state, double *segx, bool eval_dev, bool use_vw,
@@ -470,10 +474,11 @@ __global__ void k_coeff(BatchIdx bi, SolveParams sp, const double *__restrict__ 
     for (int a = 0; a < 3; ++a) {
         double c[M];
         hermite_coeffs<O>(yk[a], yk1[a], ip, pT, c);
+        double2 *dst = reinterpret_cast<double2 *>(coeff + (g * 3 + a) * M);
 #pragma unroll
-        for (int i = 0; i < M; ++i) {
-            coeff[(g * 3 + a) * M + i] = c[i];
-            finite = finite && (fabs(c[i]) <= 1.7976931348623157e308);
+        for (int i = 0; i < M; i += 2) {
+            dst[i / 2] = make_double2(c[i], c[i + 1]);
+            finite = finite && (fabs(c[i]) <= 1.7976931348623157e308) && (fabs(c[i + 1]) <= 1.7976931348623157e308);
         }
     }
     if (flags && !finite) atomicOr(flags + b, 1u);
@@ -502,10 +507,16 @@ constexpr int SAMPLE_TTAB_N = SAMPLE_MASK_BITS + 2;  // entries of t_table a wri
 
 template <int O>
 __device__ __forceinline__ void load_coeff(const double *__restrict__ coeff, long long g, double (&c)[3][2 * O]) {
+    // coefficient rows are 16*O bytes long and the buffer is 16-byte aligned (checked at the C ABI): 128-bit loads
+    const double2 *src = reinterpret_cast<const double2 *>(coeff + g * 3 * 2 * O);
 #pragma unroll
     for (int a = 0; a < 3; ++a)
 #pragma unroll
-        for (int i = 0; i < 2 * O; ++i) c[a][i] = coeff[(g * 3 + a) * 2 * O + i];
+        for (int i = 0; i < O; ++i) {
+            const double2 v = src[a * O + i];
+            c[a][2 * i] = v.x;
+            c[a][2 * i + 1] = v.y;
+        }
 }
 
 // Count pass of one segment.  n: accepted candidates; (m0, m1): acceptance mask of candidates 0..127; usable: every

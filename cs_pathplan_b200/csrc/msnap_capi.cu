@@ -285,7 +285,10 @@ int run_solve(msnap_context *h, const BatchIdx &bi, const SolveParams &sp, const
     // Thread-per-trajectory sweeps touch 32 different cache lines per warp access, so they are bound by the L1 of the
     // SMs they run on: small batches use one warp per CTA to spread over as many SMs as possible.
     const int blk_b = bi.B >= 128LL * h->sm_count ? 128 : 32;
-    const int blk_p = 2 * bi.B >= 64LL * h->sm_count ? 64 : 32;  // k_thomas_pair: two lanes per trajectory
+    // k_thomas_pair: two lanes per trajectory.  Every access of a warp touches as many cache lines as it has lanes, so
+    // small batches run with FEWER lanes per warp (down to 4) to get ~4 warps per SM instead of a few full ones.
+    int blk_p = 64;
+    while (blk_p > 4 && 2 * bi.B < (long long)blk_p * 4 * h->sm_count) blk_p >>= 1;
     const unsigned gs = grid_for(bi.n_seg, blk), gb = grid_for(bi.B, blk_b);
     const double *ht = &h->d_tab[O - MSNAP_MIN_ORDER].HT[0][0];
     if (w.fused.tpc > 0) {  // uniform batch: one persistent launch for the whole closed-form solve
@@ -364,6 +367,11 @@ int run_solve(msnap_context *h, const BatchIdx &bi, const SolveParams &sp, const
                   reweighted_vw(sp.vw0, SPEC_NIT1), w.md_last, w.flag_last);
         MS_LAUNCH(h, (k_spec_select<O, SPEC_NIT1>), gb, blk_b, bi, sp, io.wp, w.spec_state, w.state, w.segx, w.md_ws,
                   w.ok_ws, w.md_last, w.flag_last, io.max_dev_out, io.iters_out, io.vw_final_out, io.flags_out);
+    } else if ((!use_pw || sp.max_iter == 0) && h->policy != 1) {
+        // no path penalty (the reweighting loop ends after its first solve, max_dev = 0) or a bare SolveQPClosedForm:
+        // exactly one solve -- one lane pair per trajectory
+        MS_LAUNCH(h, (k_thomas_pair<O>), grid_for(2 * bi.B, blk_p), blk_p, bi, sp, io.wp, w.base, w.state, w.segx, use_pw,
+                  sp.vw0, io.max_dev_out, io.flags_out, io.iters_out, io.vw_final_out);
     } else {
         MS_LAUNCH(h, (k_thomas<O>), gb, blk_b, bi, sp, io.wp, w.base, w.state, w.segx, use_pw, true, io.max_dev_out,
                   io.iters_out, io.vw_final_out, io.flags_out);

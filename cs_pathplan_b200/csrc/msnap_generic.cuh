@@ -234,7 +234,8 @@ template <int O>
 __global__ void __launch_bounds__(64) k_thomas_pair(BatchIdx bi, SolveParams sp, const double *__restrict__ wp,
                                                     double *base, double *state, double *segx, bool eval_dev,
                                                     double vw, double *__restrict__ max_dev_out,
-                                                    unsigned *__restrict__ flags) {
+                                                    unsigned *__restrict__ flags, int *__restrict__ iters_out = nullptr,
+                                                    double *__restrict__ vw_final_out = nullptr) {
     using D = Dim<O>;
     constexpr int NR = D::NR;
     const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -242,7 +243,8 @@ __global__ void __launch_bounds__(64) k_thomas_pair(BatchIdx bi, SolveParams sp,
     const int side = (int)(idx & 1);
     if (b >= bi.B) return;
     // lanes of this warp that have a trajectory (pairs are never split: 2B is even and warps start at even indices)
-    const long long valid = 2 * bi.B - (idx - (threadIdx.x & 31));
+    long long valid = 2 * bi.B - (idx - (threadIdx.x & 31));
+    if (valid > (long long)blockDim.x) valid = blockDim.x;  // small batches run with fewer than 32 lanes per warp
     const unsigned pair_mask = valid >= 32 ? 0xffffffffu : (1u << (int)valid) - 1u;
     const long long g0 = bi.seg_begin(b);
     const int ns = (int)(bi.seg_begin(b + 1) - g0);
@@ -283,6 +285,8 @@ __global__ void __launch_bounds__(64) k_thomas_pair(BatchIdx bi, SolveParams sp,
     if (side == 0) {
         const double md = eval_dev ? sqrt(m2) : 0.0;
         if (max_dev_out) max_dev_out[b] = md;
+        if (iters_out) iters_out[b] = 0;  // a solve outside the reweighting loop
+        if (vw_final_out) vw_final_out[b] = vw;
         if (flags && (!ok || !(md == md))) atomicOr(flags + b, 1u);
     }
 }

@@ -108,11 +108,45 @@ def test_cfg3_shard_size(tool):
     assert np.array_equal(half.samples, res.samples[res.sample_offset[1 << 16]:])
 
 
+def spot_check_vs_structured(res, wp, seg_offset, cfg, picks):
+    """Parity for chains the dense reference arithmetic cannot reach (512 segments = a 4 096 x 4 096 dense inverse, 19 times
+    per solve): Oracle B (oracle/msnap_structured.py) replays the reference's loop in double for the discrete decisions
+    and in 40-digit arithmetic for the exact coefficients."""
+    import mpmath
+
+    from helpers import decisions_equivalent
+    from oracle import msnap_structured as st
+
+    mpmath.mp.dps = 40
+    Vel = np.array([cfg.start_vel, cfg.end_vel], dtype=float)
+    Acc = np.array([cfg.start_acc, cfg.end_acc], dtype=float)
+    for b in picks:
+        p = wp[seg_offset[b] + b: seg_offset[b + 1] + b + 1]
+        sl = res.segment_slice(b)
+        d = p[1:] - p[:-1]
+        T = np.maximum(np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2]) / cfg.V_avg, cfg.min_time_s)
+        assert np.array_equal(res.times[sl], T)                                     # bit-exact time allocation
+        out = st.reweighted_structured(cfg.order, p, Vel, Acc, T, cfg.path_weight, cfg.vel_zero_weight)
+        assert out["iters"] == res.iters[b] and out["vw_final"] == res.vw_final[b]
+        assert decisions_equivalent(res.best_s[sl], out["best_s"], np.array(out["dist2"], dtype=float))
+        truth = st.solve_structured(cfg.order, p, Vel, Acc, T, cfg.path_weight, float(res.vw_final[b]), ctx=mpmath.mp,
+                                    best_s=[int(v) for v in res.best_s[sl]])
+        tc = np.array([[[float(v) for v in ax] for ax in seg] for seg in truth["coeff"]])
+        assert scaled_coeff_err(res.coeff[sl], tc, T) <= COEFF_TOL
+        assert abs(res.max_dev[b] - float(truth["max_dev"])) <= 1e-8
+
+
 def test_cfg4_long_chains(tool):
-    wp, ns = workloads.cfg4(B=64)
+    """cfg4 at full size: 1 024 boustrophedon patrols x 512 segments."""
+    wp, ns = workloads.cfg4()
     cfg = workloads.synthetic_config(4, "shipped")
     res = tool.generate_batch(cfg, wp, ns=ns)
-    check_properties(res, wp, np.arange(65, dtype=np.int64) * ns, 4, cfg, pos_tol=1e-7)
+    so = np.arange(1025, dtype=np.int64) * ns
+    check_properties(res, wp, so, 4, cfg, pos_tol=1e-7)
+    spot_check_vs_structured(res, wp, so, cfg, [0, 1023])
+    sub = tool.generate_batch(cfg, wp[700 * (ns + 1): 703 * (ns + 1)], ns=ns)        # batch shape does not matter
+    assert np.array_equal(sub.coeff, res.coeff[700 * ns: 703 * ns])
+    assert np.array_equal(sub.samples, res.samples[res.sample_offset[700]: res.sample_offset[703]])
 
 
 def test_very_long_uniform_trajectories(tool):
@@ -130,7 +164,7 @@ def test_very_long_uniform_trajectories(tool):
 
 
 def test_cfg5_mixed_lengths_dense_sampling(tool):
-    wp, so = workloads.cfg5(B=2048)
+    wp, so = workloads.cfg5(B=8192)
     cfg = workloads.synthetic_config(4, "plain", sample_distance=0.0)
     res = tool.generate_batch(cfg, wp, seg_offset=so)
     check_properties(res, wp, so, 4, cfg)
@@ -142,4 +176,4 @@ def test_cfg5_mixed_lengths_dense_sampling(tool):
     per_traj = np.add.reduceat(approx, so[:-1])
     counts = np.diff(res.sample_offset)
     assert np.all(np.abs(counts - (per_traj + 1)) <= np.diff(so) + 1)
-    spot_check_vs_port(res, wp, so, cfg, [0, 1000, 2047])
+    spot_check_vs_port(res, wp, so, cfg, [0, 1000, 2047, 8191])

@@ -293,24 +293,54 @@ def run_b200(args):
         kflops = {k: roofline.kernel_flops(k, B, n_seg, ORDER, use_pw, total_solves, cand)
                   for k in ("k_fused_solve", "k_sample_scan")}
         footprint = ROTATE * (abytes + 24 * (sets[0].cap - tot_samples))
-        # end to end through the host-pointer C ABI: pinned host inputs -> H2D, solve, D2H of every result
-        out = {k: torch.empty(shape, dtype=dt).pin_memory().numpy() for k, shape, dt in (
-            ("times", (n_seg,), torch.float64), ("coeff", (n_seg, 3, m), torch.float64), ("max_dev", (B,), torch.float64),
-            ("iters", (B,), torch.int32), ("vw_final", (B,), torch.float64), ("sample_offset", (B + 1,), torch.int64),
-            ("samples", (sets[0].cap, 3), torch.float64))}
-        out["flags"] = torch.zeros(B, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
-        out["best_s"] = torch.zeros(n_seg, dtype=torch.int32).pin_memory().numpy()
+        # end to end through the host-pointer C ABI: pinned host inputs -> H2D, solve, D2H of every result.  As in the
+        # device-resident run, consecutive steps alternate between the S handles -- here each handle is driven by its own
+        # host thread (the call is synchronous and releases the GIL), so one step's upload and kernels overlap the
+        # previous step's download; every step still moves all of its bytes inside the timed region.
+        def make_out():
+            o = {k: torch.empty(shape, dtype=dt).pin_memory().numpy() for k, shape, dt in (
+                ("times", (n_seg,), torch.float64), ("coeff", (n_seg, 3, m), torch.float64),
+                ("max_dev", (B,), torch.float64), ("iters", (B,), torch.int32), ("vw_final", (B,), torch.float64),
+                ("sample_offset", (B + 1,), torch.int64), ("samples", (sets[0].cap, 3), torch.float64))}
+            o["flags"] = torch.zeros(B, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+            o["best_s"] = torch.zeros(n_seg, dtype=torch.int32).pin_memory().numpy()
+            return o
+
+        outs = [make_out() for _ in range(S)]
+        out = outs[0]
         wp_np = [s.wp_h.numpy() for s in sets]
-        e2e_steps = max(3, min(steps, 30))
-        for i in range(3):
-            tool.generate_batch(cfg, wp_np[i % ROTATE], ns=NS, capacity=sets[0].cap, out=out, stats=False)
+        e2e_steps = max(3 * S, min(steps, 30 * S))
+        e2e_steps -= e2e_steps % S
+
+        def e2e_worker(which, n):
+            res = None
+            for i in range(which, n, S):
+                res = tools[which].generate_batch(cfg, wp_np[i % ROTATE], ns=NS, capacity=sets[0].cap, out=outs[which],
+                                                  stats=False)
+            return res
+
+        def e2e_run(n):
+            if S == 1:
+                return e2e_worker(0, n)
+            th = [threading.Thread(target=e2e_worker, args=(k, n)) for k in range(1, S)]
+            for t_ in th:
+                t_.start()
+            res = e2e_worker(0, n)
+            for t_ in th:
+                t_.join()
+            return res
+
+        e2e_run(3 * S)
         barrier()
         t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            r = tool.generate_batch(cfg, wp_np[i % ROTATE], ns=NS, capacity=sets[0].cap, out=out, stats=False)
+        r = e2e_run(e2e_steps)
         torch.cuda.synchronize()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         barrier()
+        t0 = time.perf_counter()
+        for i in range(6):
+            tool.generate_batch(cfg, wp_np[i % ROTATE], ns=NS, capacity=sets[0].cap, out=out, stats=False)
+        e2e_single_ms = (time.perf_counter() - t0) / 6 * 1e3   # one call at a time on one handle
         h2d = wp_np[0].nbytes
         d2h = int(r.samples.nbytes + out["times"].nbytes + out["coeff"].nbytes + out["max_dev"].nbytes +
                   out["iters"].nbytes + out["vw_final"].nbytes + out["sample_offset"].nbytes +
@@ -318,7 +348,8 @@ def run_b200(args):
         results[weights] = dict(
             ms=ms, steps=steps, launches=launches, value=world * B * steps / (ms * 1e-3), latency_ms=latency_ms,
             e2e=dict(value=world * B * e2e_steps / e2e_s, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                     steps=e2e_steps, ms_per_step=e2e_s / e2e_steps * 1e3),
+                     steps=e2e_steps, ms_per_step=e2e_s / e2e_steps * 1e3, host_threads=S,
+                     single_call_ms=e2e_single_ms),
             prof=prof, dom=dom, dom_ms=dom_ms, all_kernels_ms=all_ms, abytes=abytes, aflops=aflops, kbytes=kbytes,
             kflops=kflops,
             samples=tot_samples, candidates=cand, mean_iters=float(iters0.double().mean().item()), flags_bad=flags_bad,

@@ -34,11 +34,11 @@ struct Arena {  // grow-only device buffer with bump allocation, reset per call
 
 // Launch plan of the fused kernel for a uniform batch, or tpc == 0 if the batch does not qualify.
 struct FusedPlan {
-    int tpc = 0, nit = 1, chunk = 1, lane_stride = 32, traj_stride = 0, grid = 0;
+    int tpc = 0, nit = 1, lane_stride = 32, traj_stride = 0, grid = 0;
     long long n_tiles = 0;
     size_t smem = 0, state_bytes = 0;
     // cache key
-    int order = 0, ns = 0, policy = 0;
+    int order = 0, ns = 0;
     long long B = 0;
 };
 
@@ -51,7 +51,6 @@ struct msnap_context {
     Arena io;                        // device mirrors of host buffers (_host entry points)
     long long launches = 0;
     int policy = 0;
-    int spec_chunk = 0;               // reweighting iterations per speculative pass (0 = all at once)
     bool scan_coef_smem = false;      // sampler: stage the tile's coefficients in shared memory (MSNAP_SCAN_COEF_SMEM=1)
     std::vector<FusedPlan> plans;     // cached launch plans
     // optional per-kernel timing (msnap_profile_begin/end): one event pair per launch on the launching stream
@@ -179,14 +178,12 @@ FusedPlan plan_fused(msnap_context *h, const BatchIdx &bi, const SolveParams &sp
     const int ns = bi.ns_uniform;
     const int nit = sp.pw > 0.0 ? sp.max_iter + 1 : 1;
     for (const FusedPlan &c : h->plans)
-        if (c.order == O && c.ns == ns && c.nit == nit && c.B == bi.B && c.policy == h->spec_chunk) return c;
+        if (c.order == O && c.ns == ns && c.nit == nit && c.B == bi.B) return c;
     f.order = O;
     f.ns = ns;
     f.nit = nit;
     f.B = bi.B;
-    f.policy = h->spec_chunk;
     if (nit > FUSED_THREADS) return f;
-    f.chunk = nit;
     const FusedSmem<O> L(ns);
     const size_t blk = (size_t)L.size * sizeof(double);
     const size_t st1 = (size_t)(ns - 1) * D::NSTATE * FUSED_SMEM_LANES * sizeof(double);  // shared-memory state rows
@@ -708,7 +705,6 @@ int msnap_create(int device, msnap_handle *out) {
         msnap_destroy(h);
         return MSNAP_ERR_CUDA;
     }
-    if (const char *e = std::getenv("MSNAP_SPEC_CHUNK")) h->spec_chunk = std::atoi(e);
     if (const char *e = std::getenv("MSNAP_SCAN_COEF_SMEM")) h->scan_coef_smem = std::atoi(e) != 0;
     if (const char *e = std::getenv("MSNAP_HOST_CHUNKS")) h->host_chunks = std::atoi(e);
     if (const char *e = std::getenv("MSNAP_ZERO_COPY")) h->zero_copy = std::atoi(e) != 0;
@@ -1137,7 +1133,6 @@ int msnap_generate_batch_host(msnap_handle h, const msnap_config *cfg, double sa
         }
         for (msnap_context *k : h->kids) {
             k->policy = h->policy;
-            k->spec_chunk = h->spec_chunk;
             k->scan_coef_smem = h->scan_coef_smem;
             k->zero_copy = h->zero_copy;
         }

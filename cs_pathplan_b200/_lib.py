@@ -61,6 +61,12 @@ SIGNATURES = {
     "msnap_sample_bound_dev": (_i, [_vp, _cfgp, _d, _ll, _i, _vp, _vp, _vp]),
     "msnap_sample_bound_host": (_i, [_vp, _cfgp, _d, _ll, _i, _vp, _vp, C.POINTER(_ll)]),
     "msnap_generate_one_host": (_i, [_vp, _cfgp, _d, _d, _i, _vp, _ll, _vp, C.POINTER(_ll)]),
+    "msnap_wgs84_to_enu_dev": (_i, [_vp, _vp, _ll, _vp, _vp]),
+    "msnap_wgs84_to_enu_host": (_i, [_vp, _vp, _ll, _vp, _vp]),
+    "msnap_enu_to_wgs84_dev": (_i, [_vp, _vp, _ll, _vp, _vp]),
+    "msnap_enu_to_wgs84_host": (_i, [_vp, _vp, _ll, _vp, _vp]),
+    "msnap_set_sample_frame": (_i, [_vp, _i, _vp]),
+    "msnap_debug_geo_steps_dev": (_i, [_vp, _vp, _ll, _vp, _vp, _vp]),
     "msnap_profile_begin": (_i, [_vp]),
     "msnap_profile_end": (_i, [_vp, C.c_char_p, _ll]),
     "msnap_debug_phase_clocks": (_i, [_vp, _i, _vp]),

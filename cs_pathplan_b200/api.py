@@ -242,6 +242,63 @@ class TrajectoryGeneratorTool:
                                                     _ptr(wp), out.shape[0], _ptr(out), C.byref(cnt)))
         return out[:cnt.value].copy()
 
+    # ------------------------------------------------------------------ WGS84 <-> ENU (UavPathPlanner's transforms)
+    @staticmethod
+    def _geo_args(rows, reference):
+        rows = _f64(rows)
+        if rows.ndim != 2 or rows.shape[1] != 3:
+            raise ValueError("expected [n, 3] rows")
+        ref = _f64(reference).reshape(-1)
+        if ref.shape[0] != 3:
+            raise ValueError("reference must be (lon_deg, lat_deg, alt_m)")
+        return rows, ref
+
+    def wgs84ToENU_Batch(self, targets, reference) -> np.ndarray:
+        """UavPathPlanner::wgs84ToENU_Batch (uavPathPlanning.cpp:1085-1095): rows [lon, lat, alt] (degrees, metres) ->
+        rows [east, north, up] about ``reference`` = (lon, lat, alt)."""
+        t, ref = self._geo_args(targets, reference)
+        out = np.empty_like(t)
+        self._check(self._L.msnap_wgs84_to_enu_host(self._h, _ptr(ref), t.shape[0], _ptr(t), _ptr(out)))
+        return out
+
+    def enuToWGS84_Batch(self, targets, reference) -> np.ndarray:
+        """UavPathPlanner::enuToWGS84_Batch (uavPathPlanning.cpp:1098-1108): rows [east, north, up] -> [lon, lat, alt]."""
+        t, ref = self._geo_args(targets, reference)
+        out = np.empty_like(t)
+        self._check(self._L.msnap_enu_to_wgs84_host(self._h, _ptr(ref), t.shape[0], _ptr(t), _ptr(out)))
+        return out
+
+    def wgs84ToENU(self, target, reference) -> np.ndarray:
+        """UavPathPlanner::wgs84ToENU (cpp:1047-1063), one point."""
+        return self.wgs84ToENU_Batch(np.asarray(target, dtype=np.float64).reshape(1, 3), reference)[0]
+
+    def enuToWGS84(self, enu, reference) -> np.ndarray:
+        """UavPathPlanner::enuToWGS84 (cpp:1066-1083), one point."""
+        return self.enuToWGS84_Batch(np.asarray(enu, dtype=np.float64).reshape(1, 3), reference)[0]
+
+    def wgs84_to_enu_dev(self, reference, lla, enu_out):
+        """Device rows (CUDA fp64 torch tensors [n,3]); enqueued on the handle's stream; in place allowed."""
+        ref = _f64(reference).reshape(3)
+        self._check(self._L.msnap_wgs84_to_enu_dev(self._h, _ptr(ref), int(lla.shape[0]), int(lla.data_ptr()),
+                                                   int(enu_out.data_ptr())))
+
+    def enu_to_wgs84_dev(self, reference, enu, lla_out, steps_out=None):
+        ref = _f64(reference).reshape(3)
+        if steps_out is None:
+            self._check(self._L.msnap_enu_to_wgs84_dev(self._h, _ptr(ref), int(enu.shape[0]), int(enu.data_ptr()),
+                                                       int(lla_out.data_ptr())))
+        else:
+            self._check(self._L.msnap_debug_geo_steps_dev(self._h, _ptr(ref), int(enu.shape[0]), int(enu.data_ptr()),
+                                                          int(lla_out.data_ptr()), int(steps_out.data_ptr())))
+
+    def set_sample_frame(self, frame: str = "enu", reference=None):
+        """Frame of the sampled rows the generate calls return: "enu" (the reference's GenerateTrajectoryMatrix) or
+        "wgs84" = getPlan's enuToWGS84_Batch(Trajectory_ENU, origin_) (cpp:3699) applied on the device."""
+        if frame not in ("enu", "wgs84"):
+            raise ValueError("frame must be 'enu' or 'wgs84'")
+        ref = None if reference is None else _f64(reference).reshape(3)
+        self._check(self._L.msnap_set_sample_frame(self._h, 1 if frame == "wgs84" else 0, _ptr(ref)))
+
     # ------------------------------------------------------------------ batched, host buffers
     def solve_qp_batch(self, order, waypoints, times, ns=None, seg_offset=None, vel=None, acc=None,
                        path_weight=0.0, vel_zero_weight=0.0):

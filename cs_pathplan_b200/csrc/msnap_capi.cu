@@ -17,6 +17,7 @@
 #include "msnap_device.cuh"
 #include "msnap_generic.cuh"
 #include "msnap_fused.cuh"
+#include "msnap_geo.cuh"
 
 static const MsnapOrderTab h_tab[MSNAP_MAX_ORDER - MSNAP_MIN_ORDER + 1] = MSNAP_ORDER_TABLES;
 
@@ -72,6 +73,10 @@ struct msnap_context {
     cudaStream_t aux = nullptr;       // host path: copies the solve's results out while the sampler is still running
     cudaEvent_t ev_solved = nullptr;  // recorded on `stream` between the solve and the sampler (host path only)
     bool mark_solved = false;
+    // sampler output frame (msnap_set_sample_frame): 0 = ENU rows as the reference's sampler returns them, 1 = the rows
+    // leave as [lon, lat, alt] = enuToWGS84_Batch of the sampled trajectory (uavPathPlanning.cpp:3699)
+    int frame = 0;
+    GeoFrame geo{};
 };
 
 namespace {
@@ -538,6 +543,11 @@ int solve_qp_dev(msnap_context *h, double pw, double vw, long long B, int ns_uni
     return run_solve<O>(h, bi, sp, io, w);
 }
 
+inline unsigned geo_grid(const msnap_context *h, long long n) {  // grid-stride over warps of 32 rows
+    const long long want = (n + GEO_BLOCK - 1) / GEO_BLOCK, cap = (long long)h->sm_count * 8;
+    return (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
 template <int O>
 int generate_dev(msnap_context *h, const msnap_config *cfg, double sd, double v_avg, long long B, int ns_uniform,
                  const long long *seg_offset, long long n_seg, const double *wp, double *times_out, double *coeff_out,
@@ -587,7 +597,13 @@ int generate_dev(msnap_context *h, const msnap_config *cfg, double sd, double v_
     rc = run_solve<O>(h, bi, sp, io, w);
     if (rc) return rc;
     if (h->mark_solved) MS_CUDA(h, cudaEventRecord(h->ev_solved, h->stream));
-    return run_sample<O>(h, bi, w.coeff, w.T, sd, capacity, sample_offset, samples, stats, flags, s);
+    rc = run_sample<O>(h, bi, w.coeff, w.T, sd, capacity, sample_offset, samples, stats, flags, s);
+    if (rc || h->frame == 0 || capacity <= 0) return rc;
+    // the rows leave as WGS84: in place, after the statistics (which are defined on the ENU rows, ms.cpp:163-195); the
+    // row count stays on the device (sample_offset[B])
+    MS_LAUNCH(h, k_enu_to_wgs84, geo_grid(h, capacity), GEO_BLOCK, h->geo, capacity, sample_offset + B, samples, samples,
+              (int *)nullptr);
+    return MSNAP_OK;
 }
 
 #define MS_DISPATCH_ORDER(order, CALL)            \
@@ -1049,7 +1065,7 @@ static int host_chunk_enqueue(msnap_context *k, const msnap_config *cfg, double 
     if (k->zero_copy && coeff_out && (reinterpret_cast<uintptr_t>(coeff_out) & 15) == 0)
         coeff_zc = static_cast<double *>(device_view_of_pinned(coeff_out));
     j.samples_direct = nullptr;
-    if (k->zero_copy && j.single && !stats_out && samples_out)
+    if (k->zero_copy && j.single && !stats_out && samples_out && k->frame == 0)
         j.samples_direct = static_cast<double *>(device_view_of_pinned(samples_out));
     k->mark_solved = true;  // ev_solved: the solve's outputs are final, the sampler has not started yet
     MS_DISPATCH_ORDER(cfg->order,
@@ -1135,6 +1151,8 @@ int msnap_generate_batch_host(msnap_handle h, const msnap_config *cfg, double sa
             k->policy = h->policy;
             k->scan_coef_smem = h->scan_coef_smem;
             k->zero_copy = h->zero_copy;
+            k->frame = h->frame;
+            k->geo = h->geo;
         }
         ctx = h->kids;
     }
@@ -1192,6 +1210,98 @@ int msnap_generate_batch_host(msnap_handle h, const msnap_config *cfg, double sa
         }
     }
     return rows_base > sample_capacity ? MSNAP_ERR_CAPACITY : MSNAP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- WGS84 <-> ENU
+static bool geo_reference_ok(const double *r) {
+    return r && std::isfinite(r[0]) && std::isfinite(r[1]) && std::isfinite(r[2]);
+}
+
+int msnap_set_sample_frame(msnap_handle h, int frame, const double *reference_lla) {
+    if (!h || frame < 0 || frame > 1 || (frame == 1 && !geo_reference_ok(reference_lla))) return MSNAP_ERR_INVALID_ARG;
+    h->frame = frame;
+    if (frame == 1) geo_make_frame(reference_lla, h->geo);
+    return MSNAP_OK;
+}
+
+int msnap_enu_to_wgs84_dev(msnap_handle h, const double *reference_lla, long long n, const double *enu, double *lla_out) {
+    if (!h || !geo_reference_ok(reference_lla) || n < 0 || (n > 0 && (!enu || !lla_out))) return MSNAP_ERR_INVALID_ARG;
+    if (n == 0) return MSNAP_OK;
+    DeviceGuard guard(h->device);
+    GeoFrame f;
+    geo_make_frame(reference_lla, f);
+    MS_LAUNCH(h, k_enu_to_wgs84, geo_grid(h, n), GEO_BLOCK, f, n, (const long long *)nullptr, enu, lla_out, (int *)nullptr);
+    return MSNAP_OK;
+}
+
+int msnap_wgs84_to_enu_dev(msnap_handle h, const double *reference_lla, long long n, const double *lla, double *enu_out) {
+    if (!h || !geo_reference_ok(reference_lla) || n < 0 || (n > 0 && (!lla || !enu_out))) return MSNAP_ERR_INVALID_ARG;
+    if (n == 0) return MSNAP_OK;
+    DeviceGuard guard(h->device);
+    GeoFrame f;
+    geo_make_frame(reference_lla, f);
+    MS_LAUNCH(h, k_wgs84_to_enu, geo_grid(h, n), GEO_BLOCK, f, n, lla, enu_out);
+    return MSNAP_OK;
+}
+
+// Host rows in, host rows out: the batch is cut into pieces that alternate between the handle's two streams, so that a
+// piece's kernel and download overlap the next piece's upload (PCIe is full duplex).
+static int geo_host(msnap_handle h, const double *reference_lla, long long n, const double *in, double *out, bool to_wgs) {
+    if (!h || !geo_reference_ok(reference_lla) || n < 0 || (n > 0 && (!in || !out))) return MSNAP_ERR_INVALID_ARG;
+    if (n == 0) return MSNAP_OK;
+    DeviceGuard guard(h->device);
+    GeoFrame f;
+    geo_make_frame(reference_lla, f);
+    MS_CUDA(h, cudaStreamSynchronize(h->aux));
+    int rc = arena_reserve(h, h->io, padded((size_t)n * 3 * sizeof(double)));
+    if (rc) return rc;
+    double *d = arena_take<double>(h->io, (size_t)n * 3);
+    const long long piece = 1 << 18;  // 262 144 rows = 6.3 MB per copy
+    const long long n_pieces = (n + piece - 1) / piece;
+    cudaStream_t own = h->stream, lanes[2] = {h->stream, n_pieces > 1 ? h->aux : h->stream};
+    int err = MSNAP_OK;
+    for (long long c = 0; c < n_pieces && !err; ++c) {
+        const long long r0 = c * piece, m = (n - r0) < piece ? (n - r0) : piece;
+        h->stream = lanes[c & 1];
+        err = [&]() -> int {
+            MS_CUDA(h, cudaMemcpyAsync(d + 3 * r0, in + 3 * r0, (size_t)m * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            if (to_wgs)
+                MS_LAUNCH(h, k_enu_to_wgs84, geo_grid(h, m), GEO_BLOCK, f, m, (const long long *)nullptr, d + 3 * r0, d + 3 * r0,
+                          (int *)nullptr);
+            else
+                MS_LAUNCH(h, k_wgs84_to_enu, geo_grid(h, m), GEO_BLOCK, f, m, d + 3 * r0, d + 3 * r0);
+            MS_CUDA(h, cudaMemcpyAsync(out + 3 * r0, d + 3 * r0, (size_t)m * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            return MSNAP_OK;
+        }();
+    }
+    h->stream = own;
+    cudaError_t e1 = cudaStreamSynchronize(h->aux), e2 = cudaStreamSynchronize(h->stream);
+    if (err) return err;
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+        h->last_error = std::string("geo_host: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2);
+        cudaGetLastError();
+        return MSNAP_ERR_CUDA;
+    }
+    return MSNAP_OK;
+}
+
+int msnap_enu_to_wgs84_host(msnap_handle h, const double *reference_lla, long long n, const double *enu, double *lla_out) {
+    return geo_host(h, reference_lla, n, enu, lla_out, true);
+}
+int msnap_wgs84_to_enu_host(msnap_handle h, const double *reference_lla, long long n, const double *lla, double *enu_out) {
+    return geo_host(h, reference_lla, n, lla, enu_out, false);
+}
+
+// Developer/test hook: ENU -> WGS84 on device rows, also returning the number of fixed-point steps per point (cpp:939-949).
+int msnap_debug_geo_steps_dev(msnap_handle h, const double *reference_lla, long long n, const double *enu, double *lla_out,
+                              int *steps_out) {
+    if (!h || !geo_reference_ok(reference_lla) || n < 0 || (n > 0 && (!enu || !lla_out || !steps_out))) return MSNAP_ERR_INVALID_ARG;
+    if (n == 0) return MSNAP_OK;
+    DeviceGuard guard(h->device);
+    GeoFrame f;
+    geo_make_frame(reference_lla, f);
+    MS_LAUNCH(h, k_enu_to_wgs84, geo_grid(h, n), GEO_BLOCK, f, n, (const long long *)nullptr, enu, lla_out, steps_out);
+    return MSNAP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------- bound

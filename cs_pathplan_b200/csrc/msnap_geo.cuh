@@ -1,0 +1,192 @@
+// msnap_geo.cuh -- batched WGS84 <-> ENU maps (sm_100a, fp64): the step every sampled point takes right after the
+// minimum-snap sampler in the reference (enuToWGS84_Batch at uavPathPlanning.cpp:3699, 3806, 4909-4913) and every
+// waypoint takes right before it (wgs84ToENU_Batch at cpp:2640, 3217).
+//
+// Mathematical contract, in the reference's operation order (the library is compiled with --fmad=false, so
+// a*b + c*d + e*f rounds exactly as the reference's unfused x86-64 code does):
+//   calcN, deg2rad, rad2deg, WGS84_A, WGS84_E2                /root/reference/uavPathPlanning.hpp:134-173
+//   wgs84ToECEF                                               /root/reference/uavPathPlanning.cpp:894-910
+//   ecefToWGS84: start value + <= 10 fixed-point steps,
+//                stop when |lat_new - lat| < 1e-12            /root/reference/uavPathPlanning.cpp:926-968
+//   ecefToENU / enuToECEF (rotation by the reference point)   /root/reference/uavPathPlanning.cpp:971-1044
+//   wgs84ToENU / enuToWGS84                                   /root/reference/uavPathPlanning.cpp:1047-1083
+// The only arithmetic that differs from the reference's is inside sin/cos/atan2 (CUDA's fp64 libm, <= 2 ulp, against
+// glibc's) -- a few 1e-16 rad, i.e. below 1e-8 m; sqrt and division are IEEE-exact on both sides; pow(x, 3) is
+// replaced by an fma-compensated cube that is correctly rounded except in ~1e-16 of the cases, as glibc's pow is.
+// The quantities that depend on the reference point only (its ECEF position and the two rotation matrices, which
+// the reference recomputes for every point) are computed ONCE per call on the host with the host's libm
+// (geo_make_frame), i.e. bit-identically to the reference, and passed to the kernels by value.
+//
+// Work decomposition: one point per lane; a warp moves 32 consecutive rows (768 contiguous bytes) per trip through
+// shared memory, so global loads and stores are fully coalesced although a row is 24 bytes; in place is allowed
+// (out == in).  Both kernels are bound by the FP64 pipe, not by HBM: ~1.3 k fp64 instructions per ENU->WGS84 point
+// (7 atan2, 6 sincos, 6 sqrt, ~13 divisions at the usual 4 fixed-point steps) against 48 bytes of traffic.
+#ifndef MSNAP_GEO_CUH
+#define MSNAP_GEO_CUH
+
+#include <cmath>
+
+namespace msnap {
+
+constexpr double GEO_A = 6378137.0;           // WGS84_A,  hpp:134
+constexpr double GEO_E2 = 0.006694379990141;  // WGS84_E2, hpp:135
+constexpr double GEO_PI = 3.14159265358979323846;
+constexpr int GEO_BLOCK = 256;
+constexpr int GEO_MAX_STEPS = 10;             // cpp:936
+constexpr double GEO_TOL = 1e-12;             // cpp:937
+
+// Everything that depends only on the reference point (lon, lat, alt).
+struct GeoFrame {
+    double ref_ecef[3];
+    double R[9];     // ECEF delta -> ENU   (computeENURotationMatrix, cpp:971-994), row-major
+    double Rinv[9];  // ENU -> ECEF delta   (computeENURotationMatrixInverse, cpp:998-1020), row-major
+};
+
+// Host side, host libm: the same statements the reference executes per point for its reference argument.
+inline void geo_make_frame(const double ref_lla[3], GeoFrame &f) {
+    const double lat_rad = ref_lla[1] * GEO_PI / 180.0, lon_rad = ref_lla[0] * GEO_PI / 180.0;  // deg2rad, hpp:166-168
+    {                                                                                           // wgs84ToECEF, cpp:894-910
+        const double sl = std::sin(lat_rad);
+        const double N = GEO_A / std::sqrt(1.0 - GEO_E2 * sl * sl);
+        const double cos_lat = std::cos(lat_rad), sin_lat = std::sin(lat_rad);
+        const double cos_lon = std::cos(lon_rad), sin_lon = std::sin(lon_rad);
+        f.ref_ecef[0] = (N + ref_lla[2]) * cos_lat * cos_lon;
+        f.ref_ecef[1] = (N + ref_lla[2]) * cos_lat * sin_lon;
+        f.ref_ecef[2] = (N * (1 - GEO_E2) + ref_lla[2]) * sin_lat;
+    }
+    const double cos_lat = std::cos(lat_rad), sin_lat = std::sin(lat_rad);
+    const double cos_lon = std::cos(lon_rad), sin_lon = std::sin(lon_rad);
+    const double R[9] = {-sin_lon,           cos_lon,            0.0,
+                         -sin_lat * cos_lon, -sin_lat * sin_lon, cos_lat,
+                         cos_lat * cos_lon,  cos_lat * sin_lon,  sin_lat};
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            f.R[3 * i + j] = R[3 * i + j];
+            f.Rinv[3 * j + i] = R[3 * i + j];  // the reference writes the transpose out entry by entry: same values
+        }
+}
+
+// x^3 rounded like a correctly-rounded pow(x, 3): the two products' rounding errors are recovered with fma.
+__device__ __forceinline__ double geo_cube(double x) {
+    const double s = x * x, es = fma(x, x, -s);
+    const double t = s * x, et = fma(s, x, -t);
+    return t + (et + es * x);
+}
+
+__device__ __forceinline__ double geo_calcN(double sin_lat) {  // hpp:139-142
+    return GEO_A / sqrt(1.0 - GEO_E2 * sin_lat * sin_lat);
+}
+
+// ecefToWGS84, cpp:926-968.  Returns the number of fixed-point steps taken.
+__device__ __forceinline__ int geo_ecef_to_wgs84(double x, double y, double z, double &lon_deg, double &lat_deg,
+                                                  double &alt_out) {
+    const double p = sqrt(x * x + y * y);
+    const double theta = atan2(z * GEO_A, p * GEO_A * (1 - GEO_E2));
+    double st, ct;
+    sincos(theta, &st, &ct);
+    double lat = atan2(z + GEO_E2 * GEO_A * (1 - GEO_E2) * geo_cube(st) / (1 - GEO_E2), p - GEO_E2 * GEO_A * geo_cube(ct));
+    int steps = 0;
+    double sl, cl;
+    sincos(lat, &sl, &cl);
+#pragma unroll 1
+    for (int i = 0; i < GEO_MAX_STEPS; ++i) {
+        const double N = geo_calcN(sl);
+        const double alt = p / cl - N;
+        const double lat_new = atan2(z, p * (1 - GEO_E2 * N / (N + alt)));
+        const bool done = fabs(lat_new - lat) < GEO_TOL;
+        lat = lat_new;
+        sincos(lat, &sl, &cl);  // needed by the next step, or by the final N / alt below
+        ++steps;
+        if (done) break;
+    }
+    const double lon = atan2(y, x);
+    const double N = geo_calcN(sl);
+    const double alt = p < 1e-12 ? fabs(z) - GEO_A * sqrt(1 - GEO_E2) : p / cl - N;  // cpp:956-960
+    lat_deg = lat * 180.0 / GEO_PI;  // rad2deg, hpp:171-173
+    lon_deg = lon * 180.0 / GEO_PI;
+    alt_out = alt;
+    return steps;
+}
+
+// Warp-cooperative move of 32 rows x 3 doubles between global and shared memory (three coalesced 256-byte accesses).
+__device__ __forceinline__ void geo_rows_in(const double *__restrict__ g, long long row0, long long n, double *sm, int lane) {
+    const long long base = 3 * row0, end = 3 * n;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const long long i = base + 32 * k + lane;
+        sm[32 * k + lane] = i < end ? g[i] : 0.0;
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void geo_rows_out(double *__restrict__ g, long long row0, long long n, const double *sm, int lane) {
+    __syncwarp();
+    const long long base = 3 * row0, end = 3 * n;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const long long i = base + 32 * k + lane;
+        if (i < end) g[i] = sm[32 * k + lane];
+    }
+    __syncwarp();
+}
+
+// enuToWGS84_Batch (cpp:1098-1108): rows [east, north, up] -> rows [lon_deg, lat_deg, alt_m].
+// n_dev != nullptr: the row count is read from device memory (the sampler's sample_offset[B]) and clamped to n_cap.
+__global__ void __launch_bounds__(GEO_BLOCK) k_enu_to_wgs84(GeoFrame f, long long n_cap, const long long *__restrict__ n_dev,
+                                                            const double *enu, double *lla, int *__restrict__ steps_out) {
+    __shared__ double sm_all[GEO_BLOCK / 32][96];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double *sm = sm_all[w];
+    long long n = n_cap;
+    if (n_dev) {
+        const long long m = *n_dev;
+        n = m < n_cap ? m : n_cap;
+    }
+    const long long warps = (long long)gridDim.x * (GEO_BLOCK / 32);
+    for (long long row0 = ((long long)blockIdx.x * (GEO_BLOCK / 32) + w) * 32; row0 < n; row0 += warps * 32) {
+        geo_rows_in(enu, row0, n, sm, lane);
+        const double e = sm[3 * lane], no = sm[3 * lane + 1], u = sm[3 * lane + 2];
+        // enuToECEF (cpp:1035-1044) and the shift by the reference point (cpp:1076-1079)
+        const double dx = f.Rinv[0] * e + f.Rinv[1] * no + f.Rinv[2] * u;
+        const double dy = f.Rinv[3] * e + f.Rinv[4] * no + f.Rinv[5] * u;
+        const double dz = f.Rinv[6] * e + f.Rinv[7] * no + f.Rinv[8] * u;
+        double lon, lat, alt;
+        const int steps = geo_ecef_to_wgs84(f.ref_ecef[0] + dx, f.ref_ecef[1] + dy, f.ref_ecef[2] + dz, lon, lat, alt);
+        __syncwarp();
+        sm[3 * lane] = lon;
+        sm[3 * lane + 1] = lat;
+        sm[3 * lane + 2] = alt;
+        if (steps_out && row0 + lane < n) steps_out[row0 + lane] = steps;
+        geo_rows_out(lla, row0, n, sm, lane);
+    }
+}
+
+// wgs84ToENU_Batch (cpp:1085-1095): rows [lon_deg, lat_deg, alt_m] -> rows [east, north, up].
+__global__ void __launch_bounds__(GEO_BLOCK) k_wgs84_to_enu(GeoFrame f, long long n, const double *lla, double *enu) {
+    __shared__ double sm_all[GEO_BLOCK / 32][96];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double *sm = sm_all[w];
+    const long long warps = (long long)gridDim.x * (GEO_BLOCK / 32);
+    for (long long row0 = ((long long)blockIdx.x * (GEO_BLOCK / 32) + w) * 32; row0 < n; row0 += warps * 32) {
+        geo_rows_in(lla, row0, n, sm, lane);
+        const double lon_deg = sm[3 * lane], lat_deg = sm[3 * lane + 1], h = sm[3 * lane + 2];
+        // wgs84ToECEF (cpp:894-910)
+        const double lat_rad = lat_deg * GEO_PI / 180.0, lon_rad = lon_deg * GEO_PI / 180.0;
+        double sin_lat, cos_lat, sin_lon, cos_lon;
+        sincos(lat_rad, &sin_lat, &cos_lat);
+        sincos(lon_rad, &sin_lon, &cos_lon);
+        const double N = geo_calcN(sin_lat);
+        const double x = (N + h) * cos_lat * cos_lon;
+        const double y = (N + h) * cos_lat * sin_lon;
+        const double z = (N * (1 - GEO_E2) + h) * sin_lat;
+        // delta (cpp:1053-1056) and ecefToENU (cpp:1023-1032)
+        const double dx = x - f.ref_ecef[0], dy = y - f.ref_ecef[1], dz = z - f.ref_ecef[2];
+        __syncwarp();
+        sm[3 * lane] = f.R[0] * dx + f.R[1] * dy + f.R[2] * dz;
+        sm[3 * lane + 1] = f.R[3] * dx + f.R[4] * dy + f.R[5] * dz;
+        sm[3 * lane + 2] = f.R[6] * dx + f.R[7] * dy + f.R[8] * dz;
+        geo_rows_out(enu, row0, n, sm, lane);
+    }
+}
+
+}  // namespace msnap
+#endif  // MSNAP_GEO_CUH

@@ -159,6 +159,32 @@ int msnap_generate_one_host(msnap_handle h, const msnap_config *cfg, double samp
                             double v_avg_override, int n_points, const double *waypoints, long long sample_capacity,
                             double *samples_out, long long *n_samples_out);
 
+/* ---- WGS84 <-> ENU, batched -----------------------------------------------------
+ * Drop-in for UavPathPlanner::wgs84ToENU_Batch / enuToWGS84_Batch (/root/reference/uavPathPlanning.cpp:1085-1108;
+ * per point wgs84ToENU cpp:1047-1063 and enuToWGS84 cpp:1066-1083 over wgs84ToECEF cpp:894-910, ecefToWGS84
+ * cpp:926-968, ecefToENU / enuToECEF cpp:1023-1044; constants uavPathPlanning.hpp:134-173): the map every waypoint
+ * takes right before the minimum-snap path (cpp:2640, 3217) and every sampled point right after it (cpp:3699, 3806,
+ * 4909-4913).
+ *   reference_lla : HOST pointer to {lon_deg, lat_deg, alt_m} == struct WGS84Point (hpp:145-149), the ENU origin
+ *   lla rows      : [n][3] {lon_deg, lat_deg, alt_m}  == std::vector<WGS84Point>
+ *   enu rows      : [n][3] {east, north, up} metres    == std::vector<ENUPoint> (hpp:152-156)
+ * _dev: device rows, enqueued on the handle's stream; _host: host rows, returns when the output is complete.
+ * In place (output == input) is allowed.  Same formulas in the same operation order as the reference, including the
+ * <= 10-step fixed-point iteration with its 1e-12 rad stopping rule; results agree with the reference's to ~1e-9 m
+ * (tests: 1e-6 m), the difference being CUDA's sin/cos/atan2 against the host libm's. */
+int msnap_wgs84_to_enu_dev(msnap_handle h, const double *reference_lla, long long n, const double *lla, double *enu_out);
+int msnap_wgs84_to_enu_host(msnap_handle h, const double *reference_lla, long long n, const double *lla, double *enu_out);
+int msnap_enu_to_wgs84_dev(msnap_handle h, const double *reference_lla, long long n, const double *enu, double *lla_out);
+int msnap_enu_to_wgs84_host(msnap_handle h, const double *reference_lla, long long n, const double *enu, double *lla_out);
+/* Frame of the rows msnap_generate_batch_* / msnap_generate_one_host write to samples_out: 0 (default) = ENU, as
+ * GenerateTrajectoryMatrix returns them; 1 = WGS84 {lon, lat, alt} about reference_lla, i.e. getPlan's
+ * `enuToWGS84_Batch(Trajectory_ENU, origin_)` (cpp:3699) applied on the device before the rows leave it.  The
+ * statistics in stats_out are those of the ENU rows either way.  reference_lla may be NULL for frame 0. */
+int msnap_set_sample_frame(msnap_handle h, int frame, const double *reference_lla);
+/* Test hook: msnap_enu_to_wgs84_dev that also writes the number of fixed-point steps taken per point (cpp:939-949). */
+int msnap_debug_geo_steps_dev(msnap_handle h, const double *reference_lla, long long n, const double *enu, double *lla_out,
+                              int *steps_out);
+
 /* ---- per-kernel timing (bench.py's roofline pass) ------------------------------------------------------------
  * Between begin and end every kernel the handle launches is bracketed by a CUDA event pair on the launching stream.
  * msnap_profile_end synchronises and writes a JSON object {"<kernel>": {"launches": n, "total_ms": t}, ...}. */

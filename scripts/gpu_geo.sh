@@ -1,0 +1,18 @@
+#!/bin/bash
+# GPU-box pass for the WGS84 <-> ENU row: all GPU tests, the geo micro-benchmark, then an ncu launch list and one full
+# capture of k_enu_to_wgs84.  Usage (under gpurun): bash scripts/gpu_geo.sh <tag>
+set -u
+TAG=${1:-geo}
+OUT=gpurun_out
+mkdir -p $OUT
+python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/${TAG}_pytest.log
+tail -15 $OUT/${TAG}_pytest.log
+python scripts/geo_bench.py > $OUT/${TAG}_geo_bench.jsonl 2> $OUT/${TAG}_geo_bench.err; echo "geo bench rc=$?"
+cat $OUT/${TAG}_geo_bench.jsonl; tail -3 $OUT/${TAG}_geo_bench.err
+if [ "${NCU:-1}" = "1" ]; then
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/${TAG}_geo_launches.csv \
+    python scripts/geo_bench.py --iters 2 --no-cpu > $OUT/${TAG}_geo_ncu1.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_enu_to_wgs84 -s 2 -c 1 -o $OUT/${TAG}_enu_to_wgs84 -f \
+    python scripts/geo_bench.py --iters 2 --no-cpu > $OUT/${TAG}_geo_ncu2.log 2>&1
+fi
+ls -la $OUT | tail -12

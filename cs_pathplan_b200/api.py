@@ -291,6 +291,11 @@ class TrajectoryGeneratorTool:
             self._check(self._L.msnap_debug_geo_steps_dev(self._h, _ptr(ref), int(enu.shape[0]), int(enu.data_ptr()),
                                                           int(lla_out.data_ptr()), int(steps_out.data_ptr())))
 
+    def set_geo_exact_trig(self, enable: bool):
+        """ENU -> WGS84: run ecefToWGS84's iteration statement by statement with per-step sin/cos/atan2 (True) or on
+        direction vectors (False, default; same iteration, ~4x faster, rounding-level differences)."""
+        self._check(self._L.msnap_set_geo_exact_trig(self._h, int(bool(enable))))
+
     def set_sample_frame(self, frame: str = "enu", reference=None):
         """Frame of the sampled rows the generate calls return: "enu" (the reference's GenerateTrajectoryMatrix) or
         "wgs84" = getPlan's enuToWGS84_Batch(Trajectory_ENU, origin_) (cpp:3699) applied on the device."""

@@ -77,6 +77,7 @@ struct msnap_context {
     // leave as [lon, lat, alt] = enuToWGS84_Batch of the sampled trajectory (uavPathPlanning.cpp:3699)
     int frame = 0;
     GeoFrame geo{};
+    bool geo_trig = false;  // msnap_set_geo_exact_trig: ENU -> WGS84 with the reference's per-step sin/cos/atan2
 };
 
 namespace {
@@ -548,6 +549,15 @@ inline unsigned geo_grid(const msnap_context *h, long long n) {  // grid-stride 
     return (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
 }
 
+int launch_enu_to_wgs84(msnap_context *h, const GeoFrame &f, long long n_cap, const long long *n_dev, const double *enu,
+                        double *lla, int *steps) {
+    if (h->geo_trig)
+        MS_LAUNCH(h, k_enu_to_wgs84<true>, geo_grid(h, n_cap), GEO_BLOCK, f, n_cap, n_dev, enu, lla, steps);
+    else
+        MS_LAUNCH(h, k_enu_to_wgs84<false>, geo_grid(h, n_cap), GEO_BLOCK, f, n_cap, n_dev, enu, lla, steps);
+    return MSNAP_OK;
+}
+
 template <int O>
 int generate_dev(msnap_context *h, const msnap_config *cfg, double sd, double v_avg, long long B, int ns_uniform,
                  const long long *seg_offset, long long n_seg, const double *wp, double *times_out, double *coeff_out,
@@ -601,9 +611,7 @@ int generate_dev(msnap_context *h, const msnap_config *cfg, double sd, double v_
     if (rc || h->frame == 0 || capacity <= 0) return rc;
     // the rows leave as WGS84: in place, after the statistics (which are defined on the ENU rows, ms.cpp:163-195); the
     // row count stays on the device (sample_offset[B])
-    MS_LAUNCH(h, k_enu_to_wgs84, geo_grid(h, capacity), GEO_BLOCK, h->geo, capacity, sample_offset + B, samples, samples,
-              (int *)nullptr);
-    return MSNAP_OK;
+    return launch_enu_to_wgs84(h, h->geo, capacity, sample_offset + B, samples, samples, nullptr);
 }
 
 #define MS_DISPATCH_ORDER(order, CALL)            \
@@ -1153,6 +1161,7 @@ int msnap_generate_batch_host(msnap_handle h, const msnap_config *cfg, double sa
             k->zero_copy = h->zero_copy;
             k->frame = h->frame;
             k->geo = h->geo;
+            k->geo_trig = h->geo_trig;
         }
         ctx = h->kids;
     }
@@ -1224,14 +1233,19 @@ int msnap_set_sample_frame(msnap_handle h, int frame, const double *reference_ll
     return MSNAP_OK;
 }
 
+int msnap_set_geo_exact_trig(msnap_handle h, int enable) {
+    if (!h) return MSNAP_ERR_INVALID_ARG;
+    h->geo_trig = enable != 0;
+    return MSNAP_OK;
+}
+
 int msnap_enu_to_wgs84_dev(msnap_handle h, const double *reference_lla, long long n, const double *enu, double *lla_out) {
     if (!h || !geo_reference_ok(reference_lla) || n < 0 || (n > 0 && (!enu || !lla_out))) return MSNAP_ERR_INVALID_ARG;
     if (n == 0) return MSNAP_OK;
     DeviceGuard guard(h->device);
     GeoFrame f;
     geo_make_frame(reference_lla, f);
-    MS_LAUNCH(h, k_enu_to_wgs84, geo_grid(h, n), GEO_BLOCK, f, n, (const long long *)nullptr, enu, lla_out, (int *)nullptr);
-    return MSNAP_OK;
+    return launch_enu_to_wgs84(h, f, n, nullptr, enu, lla_out, nullptr);
 }
 
 int msnap_wgs84_to_enu_dev(msnap_handle h, const double *reference_lla, long long n, const double *lla, double *enu_out) {
@@ -1265,10 +1279,10 @@ static int geo_host(msnap_handle h, const double *reference_lla, long long n, co
         h->stream = lanes[c & 1];
         err = [&]() -> int {
             MS_CUDA(h, cudaMemcpyAsync(d + 3 * r0, in + 3 * r0, (size_t)m * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-            if (to_wgs)
-                MS_LAUNCH(h, k_enu_to_wgs84, geo_grid(h, m), GEO_BLOCK, f, m, (const long long *)nullptr, d + 3 * r0, d + 3 * r0,
-                          (int *)nullptr);
-            else
+            if (to_wgs) {
+                const int rc2 = launch_enu_to_wgs84(h, f, m, nullptr, d + 3 * r0, d + 3 * r0, nullptr);
+                if (rc2) return rc2;
+            } else
                 MS_LAUNCH(h, k_wgs84_to_enu, geo_grid(h, m), GEO_BLOCK, f, m, d + 3 * r0, d + 3 * r0);
             MS_CUDA(h, cudaMemcpyAsync(out + 3 * r0, d + 3 * r0, (size_t)m * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
             return MSNAP_OK;
@@ -1300,8 +1314,7 @@ int msnap_debug_geo_steps_dev(msnap_handle h, const double *reference_lla, long 
     DeviceGuard guard(h->device);
     GeoFrame f;
     geo_make_frame(reference_lla, f);
-    MS_LAUNCH(h, k_enu_to_wgs84, geo_grid(h, n), GEO_BLOCK, f, n, (const long long *)nullptr, enu, lla_out, steps_out);
-    return MSNAP_OK;
+    return launch_enu_to_wgs84(h, f, n, nullptr, enu, lla_out, steps_out);
 }
 
 // ---------------------------------------------------------------------------------------------- bound

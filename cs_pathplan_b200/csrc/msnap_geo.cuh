@@ -13,6 +13,9 @@
 // The only arithmetic that differs from the reference's is inside sin/cos/atan2 (CUDA's fp64 libm, <= 2 ulp, against
 // glibc's) -- a few 1e-16 rad, i.e. below 1e-8 m; sqrt and division are IEEE-exact on both sides; pow(x, 3) is
 // replaced by an fma-compensated cube that is correctly rounded except in ~1e-16 of the cases, as glibc's pow is.
+// That statement-by-statement form is k_enu_to_wgs84<true> (msnap_set_geo_exact_trig); the default,
+// k_enu_to_wgs84<false>, runs the same iteration on direction vectors instead of angles (geo_ecef_to_wgs84_fast: same
+// start value, same step, same stopping rule, ~4x fewer instructions).
 // The quantities that depend on the reference point only (its ECEF position and the two rotation matrices, which
 // the reference recomputes for every point) are computed ONCE per call on the host with the host's libm
 // (geo_make_frame), i.e. bit-identically to the reference, and passed to the kernels by value.
@@ -25,6 +28,8 @@
 #define MSNAP_GEO_CUH
 
 #include <cmath>
+
+#include "msnap_geo_atan.h"
 
 namespace msnap {
 
@@ -108,14 +113,118 @@ __device__ __forceinline__ int geo_ecef_to_wgs84(double x, double y, double z, d
     return steps;
 }
 
+// The same map without trigonometry inside the loop (default).  A latitude is carried as an unnormalised direction
+// d = (S, C), lat = atan2(S, C).  With R = |d| and W = sqrt(C^2 + (1 - e2) S^2) one has cos(lat)/sqrt(1 - e2 sin^2(lat))
+// = C / W, and the reference's step  lat_new = atan2(z, p (1 - e2 N / (N + alt)))  with  N + alt = p / cos(lat)
+// (cpp:940-944) is  lat_new = atan2(z, p - e2 a C / W) = atan2(z W, p W - e2 a C):  one sqrt and five multiply-adds per
+// step, no division, no sin/cos/atan2.  The stopping rule |lat_new - lat| < 1e-12 (cpp:946) is evaluated on the angle
+// between the two directions, cross / dot; start value, step limit and final formulas are the reference's.  The angle
+// is formed once, at the end.  Directions are rescaled by 2^-23 per step (exact) so that ten steps cannot overflow.
+// Differences to geo_ecef_to_wgs84: rounding only (a few 1e-16 rad), plus the stopping decision where |d lat| falls
+// within ~1e-4 relative of the threshold (the reference's own subtraction is that noisy there); one step more or less
+// moves the result by < 1e-14 rad.
+// ---- lean fp64 primitives for the direction form (device only) ------------------------------------------------
+// CUDA's sqrt / division / atan2 are IEEE-exact resp. <= 2 ulp but carry slow paths and cost 23 / 20 / 128 issued
+// instructions each (ncu, this kernel); these cost 7-11 / 6-8 / ~45 and are accurate to ~1 ulp on the ranges used.
+__device__ __forceinline__ double geo_rcp(double x) {  // 1/x, |x| normal: MUFU.RCP64H seed + two Newton steps
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+__device__ __forceinline__ double geo_div(double n, double d) {  // n/d with one residual correction
+    const double r = geo_rcp(d), q = n * r;
+    return fma(fma(-q, d, n), r, q);
+}
+__device__ __forceinline__ double geo_rsqrt(double q) {  // 1/sqrt(q), q > 0 normal: MUFU.RSQ64H seed + one cubic step
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(q));
+    const double e = fma(-(q * y), y, 1.0);
+    return fma(y * e, fma(0.375, e, 0.5), y);
+}
+__device__ __forceinline__ double geo_sqrt_pos(double q, double y) {  // sqrt(q) from y = geo_rsqrt(q)
+    const double s = q * y;
+    return fma(fma(-s, s, q), 0.5 * y, s);
+}
+// atan2 for finite arguments: t = min/max in [0, 1], atan(t) = t + t^3 P(t^2) (GEO_ATAN_N = 21 coefficients from gen_geo_atan.py:
+// Chebyshev interpolation in 60-digit arithmetic, approximation error 3e-17), quadrant fix-up with pi split into two doubles.  atan2(0, 0) = 0.
+__device__ __forceinline__ double geo_atan2(double y, double x) {
+    const double ax = fabs(x), ay = fabs(y);
+    const double mx = fmax(ax, ay), mn = fmin(ax, ay);
+    const double t = geo_div(mn, mx), u = t * t;
+    constexpr double c[GEO_ATAN_N] = GEO_ATAN_COEFFS;
+    double pl = c[GEO_ATAN_N - 1];
+#pragma unroll
+    for (int i = GEO_ATAN_N - 2; i >= 0; --i) pl = fma(pl, u, c[i]);
+    double a = fma(t * u, pl, t);
+    if (ay > ax) a = (1.57079632679489655800e+00 - a) + 6.12323399573676603587e-17;
+    if (x < 0.0) a = (3.14159265358979311600e+00 - a) + 1.22464679914735320717e-16;
+    if (mx == 0.0) a = 0.0;
+    return copysign(a, y);
+}
+__device__ __forceinline__ double geo_rad2deg(double rad) {  // (rad * 180) / pi, hpp:171-173, division by residual fix-up
+    constexpr double INV_PI = 0.318309886183790671538;
+    const double n = rad * 180.0, q = n * INV_PI;
+    return fma(fma(-q, GEO_PI, n), INV_PI, q);
+}
+
+__device__ __forceinline__ int geo_ecef_to_wgs84_fast(double x, double y, double z, double &lon_deg, double &lat_deg,
+                                                       double &alt_out) {
+    constexpr double E2A = GEO_E2 * GEO_A, OME2 = 1.0 - GEO_E2, SCALE = 1.1920928955078125e-07;  // 2^-23
+    const double p2 = fma(x, x, y * y);
+    const double p = p2 > 0.0 ? geo_sqrt_pos(p2, geo_rsqrt(p2)) : 0.0;
+    // theta = atan2(z a, p a (1 - e2)): only sin(theta), cos(theta) are used (cpp:929-932)
+    const double u = z * GEO_A, v = p * GEO_A * OME2;
+    const double ih = geo_rsqrt(fma(u, u, v * v));
+    const double st = u * ih, ct = v * ih;
+    double S = z + E2A * (st * st * st);            // z + e2 a (1-e2) sin^3 / (1-e2), cpp:931
+    double C = fma(-E2A, ct * ct * ct, p);          // p - e2 a cos^3,                  cpp:932
+    int steps = 0;
+#pragma unroll 1
+    for (int i = 0; i < GEO_MAX_STEPS; ++i) {
+        const double q = fma(C, C, OME2 * S * S);
+        const double W = q * geo_rsqrt(q);
+        const double Sn = z * W * SCALE, Cn = fma(p, W, -E2A * C) * SCALE;
+        const double cross = fma(Sn, C, -(Cn * S)), dot = fma(Sn, S, Cn * C);
+        const bool done = fabs(cross) < GEO_TOL * dot;
+        S = Sn;
+        C = Cn;
+        ++steps;
+        if (done) break;
+    }
+    const double ir = geo_rsqrt(fma(S, S, C * C));
+    const double sl = S * ir, cl = C * ir;
+    const double N = GEO_A * geo_rsqrt(fma(-GEO_E2 * sl, sl, 1.0));
+    const double alt = p < 1e-12 ? fabs(z) - GEO_A * sqrt(OME2) : geo_div(p, cl) - N;  // cpp:956-960
+    double lat = geo_atan2(S, C);
+    if (p == 0.0) lat = NAN;  // the reference's step evaluates 0 * inf there (cpp:944)
+    lat_deg = geo_rad2deg(lat);
+    lon_deg = geo_rad2deg(geo_atan2(y, x));
+    alt_out = alt;
+    return steps;
+}
+
 // Warp-cooperative move of 32 rows x 3 doubles between global and shared memory (three coalesced 256-byte accesses).
-__device__ __forceinline__ void geo_rows_in(const double *__restrict__ g, long long row0, long long n, double *sm, int lane) {
+// The loads of the NEXT trip are issued into registers before the current trip's arithmetic (geo_rows_fetch) and
+// only parked in shared memory when the trip starts (geo_rows_park), so no warp waits on HBM.
+struct GeoRows {
+    double v[3];
+};
+__device__ __forceinline__ GeoRows geo_rows_fetch(const double *g, long long row0, long long n, int lane) {
+    GeoRows r;
     const long long base = 3 * row0, end = 3 * n;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const long long i = base + 32 * k + lane;
-        sm[32 * k + lane] = i < end ? g[i] : 0.0;
+        r.v[k] = i < end ? g[i] : 0.0;
     }
+    return r;
+}
+__device__ __forceinline__ void geo_rows_park(const GeoRows &r, double *sm, int lane) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sm[32 * k + lane] = r.v[k];
     __syncwarp();
 }
 __device__ __forceinline__ void geo_rows_out(double *__restrict__ g, long long row0, long long n, const double *sm, int lane) {
@@ -131,6 +240,7 @@ __device__ __forceinline__ void geo_rows_out(double *__restrict__ g, long long r
 
 // enuToWGS84_Batch (cpp:1098-1108): rows [east, north, up] -> rows [lon_deg, lat_deg, alt_m].
 // n_dev != nullptr: the row count is read from device memory (the sampler's sample_offset[B]) and clamped to n_cap.
+template <bool TRIG>
 __global__ void __launch_bounds__(GEO_BLOCK) k_enu_to_wgs84(GeoFrame f, long long n_cap, const long long *__restrict__ n_dev,
                                                             const double *enu, double *lla, int *__restrict__ steps_out) {
     __shared__ double sm_all[GEO_BLOCK / 32][96];
@@ -142,15 +252,20 @@ __global__ void __launch_bounds__(GEO_BLOCK) k_enu_to_wgs84(GeoFrame f, long lon
         n = m < n_cap ? m : n_cap;
     }
     const long long warps = (long long)gridDim.x * (GEO_BLOCK / 32);
-    for (long long row0 = ((long long)blockIdx.x * (GEO_BLOCK / 32) + w) * 32; row0 < n; row0 += warps * 32) {
-        geo_rows_in(enu, row0, n, sm, lane);
+    long long row0 = ((long long)blockIdx.x * (GEO_BLOCK / 32) + w) * 32;
+    GeoRows next = geo_rows_fetch(enu, row0, n, lane);
+    for (; row0 < n; row0 += warps * 32) {
+        geo_rows_park(next, sm, lane);
+        // in place: the next trip's rows belong to this warp alone, nobody has written them yet
+        next = geo_rows_fetch(enu, row0 + warps * 32, n, lane);
         const double e = sm[3 * lane], no = sm[3 * lane + 1], u = sm[3 * lane + 2];
         // enuToECEF (cpp:1035-1044) and the shift by the reference point (cpp:1076-1079)
         const double dx = f.Rinv[0] * e + f.Rinv[1] * no + f.Rinv[2] * u;
         const double dy = f.Rinv[3] * e + f.Rinv[4] * no + f.Rinv[5] * u;
         const double dz = f.Rinv[6] * e + f.Rinv[7] * no + f.Rinv[8] * u;
         double lon, lat, alt;
-        const int steps = geo_ecef_to_wgs84(f.ref_ecef[0] + dx, f.ref_ecef[1] + dy, f.ref_ecef[2] + dz, lon, lat, alt);
+        const double X = f.ref_ecef[0] + dx, Y = f.ref_ecef[1] + dy, Z = f.ref_ecef[2] + dz;
+        const int steps = TRIG ? geo_ecef_to_wgs84(X, Y, Z, lon, lat, alt) : geo_ecef_to_wgs84_fast(X, Y, Z, lon, lat, alt);
         __syncwarp();
         sm[3 * lane] = lon;
         sm[3 * lane + 1] = lat;
@@ -166,8 +281,11 @@ __global__ void __launch_bounds__(GEO_BLOCK) k_wgs84_to_enu(GeoFrame f, long lon
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     double *sm = sm_all[w];
     const long long warps = (long long)gridDim.x * (GEO_BLOCK / 32);
-    for (long long row0 = ((long long)blockIdx.x * (GEO_BLOCK / 32) + w) * 32; row0 < n; row0 += warps * 32) {
-        geo_rows_in(lla, row0, n, sm, lane);
+    long long row0 = ((long long)blockIdx.x * (GEO_BLOCK / 32) + w) * 32;
+    GeoRows next = geo_rows_fetch(lla, row0, n, lane);
+    for (; row0 < n; row0 += warps * 32) {
+        geo_rows_park(next, sm, lane);
+        next = geo_rows_fetch(lla, row0 + warps * 32, n, lane);
         const double lon_deg = sm[3 * lane], lat_deg = sm[3 * lane + 1], h = sm[3 * lane + 2];
         // wgs84ToECEF (cpp:894-910)
         const double lat_rad = lat_deg * GEO_PI / 180.0, lon_rad = lon_deg * GEO_PI / 180.0;

@@ -47,7 +47,9 @@ def main():
         mean_steps = float(steps.float().mean())
         out = []
         for name, fn in (("enu_to_wgs84", lambda: tool.enu_to_wgs84_dev(ref, enu, lla)),
-                         ("wgs84_to_enu", lambda: tool.wgs84_to_enu_dev(ref, lla, back))):
+                         ("wgs84_to_enu", lambda: tool.wgs84_to_enu_dev(ref, lla, back)),
+                         ("enu_to_wgs84<exact_trig>", lambda: tool.enu_to_wgs84_dev(ref, enu, lla))):
+            tool.set_geo_exact_trig(name.endswith("<exact_trig>"))
             for _ in range(3):
                 fn()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -63,8 +65,9 @@ def main():
             out.append({"kernel": "k_" + name, "rows": n, "ms": ms, "rows_per_s": n / (ms * 1e-3),
                         "algorithmic_bytes_per_row": 48, "achieved_GBps": gbs, "hbm_peak_GBps": hbm_peak,
                         "hbm_frac": gbs / hbm_peak, "fp64_dfma_peak_TFLOPs": fp64_peak,
-                        "mean_fixed_point_steps": mean_steps if name == "enu_to_wgs84" else None,
+                        "mean_fixed_point_steps": mean_steps if name.startswith("enu_to_wgs84") else None,
                         "input": "rows 402 MB >> L2 (126 MB)"})
+        tool.set_geo_exact_trig(False)
         tool.set_stream(None)
     if not a.no_cpu:
         from oracle import geo

@@ -12,7 +12,7 @@ cat $OUT/${TAG}_geo_bench.jsonl; tail -3 $OUT/${TAG}_geo_bench.err
 if [ "${NCU:-1}" = "1" ]; then
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/${TAG}_geo_launches.csv \
     python scripts/geo_bench.py --iters 2 --no-cpu > $OUT/${TAG}_geo_ncu1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_enu_to_wgs84 -s 2 -c 1 -o $OUT/${TAG}_enu_to_wgs84 -f \
+ncu --set full --clock-control none --import-source on -k regex:k_enu_to_wgs84 -s 4 -c 1 -o $OUT/${TAG}_enu_to_wgs84 -f \
     python scripts/geo_bench.py --iters 2 --no-cpu > $OUT/${TAG}_geo_ncu2.log 2>&1
 fi
 ls -la $OUT | tail -12

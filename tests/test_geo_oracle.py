@@ -73,3 +73,26 @@ def test_up_axis_is_the_ellipsoid_normal():
 def test_shape_errors(bad):
     with pytest.raises(ValueError):
         geo.wgs84_to_enu_batch(bad, [0, 0, 0])
+
+
+def test_device_atan2_polynomial_on_the_host(tmp_path):
+    """geo_atan2 (msnap_geo.cuh) restated on the host with the same generated coefficients and the same fma sequence
+    (tests/cpp/geo_atan_host.cpp): at most ~1 ulp of pi away from libm's atan2l over 2 M directions and 12 decades."""
+    import subprocess
+
+    root = os.path.dirname(HERE)
+    exe = str(tmp_path / "geo_atan_host")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-mfma", "-I", os.path.join(root, "cs_pathplan_b200", "csrc"),
+                           os.path.join(HERE, "cpp", "geo_atan_host.cpp"), "-o", exe])
+    worst = float(subprocess.run([exe], capture_output=True, text=True, check=True).stdout)
+    assert worst <= 6.0          # units of 2^-53 rad; ulp(pi) = 4 units
+
+
+def test_generated_atan_header_is_current():
+    import subprocess
+    import sys
+
+    root = os.path.dirname(HERE)
+    out = subprocess.run([sys.executable, os.path.join(root, "cs_pathplan_b200", "csrc", "gen_geo_atan.py")],
+                         capture_output=True, text=True, check=True).stdout
+    assert out == open(os.path.join(root, "cs_pathplan_b200", "csrc", "msnap_geo_atan.h")).read()

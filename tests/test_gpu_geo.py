@@ -25,12 +25,21 @@ POS_TOL = 1e-7    # metres
 ANG_TOL = 1e-12   # degrees
 
 
+@pytest.fixture(params=["directions", "exact_trig"])
+def geo_tool(tool, request):
+    """Both execution forms of ecefToWGS84's iteration (msnap_set_geo_exact_trig) must meet the same bars."""
+    tool.set_geo_exact_trig(request.param == "exact_trig")
+    yield tool
+    tool.set_geo_exact_trig(False)
+
+
 def lla_close(a, b):
     d = np.abs(np.asarray(a) - np.asarray(b))
     return d[:, 0].max() <= ANG_TOL and d[:, 1].max() <= ANG_TOL and d[:, 2].max() <= POS_TOL
 
 
-def test_readme_waypoints_both_ways(tool):
+def test_readme_waypoints_both_ways(geo_tool):
+    tool = geo_tool
     """The reference's only recorded numbers for this path (readme.md:11-28)."""
     enu = tool.wgs84ToENU_Batch(geo.README_WGS84, geo.README_ORIGIN)
     assert np.abs(enu - geo.README_ENU).max() <= POS_TOL
@@ -41,7 +50,8 @@ def test_readme_waypoints_both_ways(tool):
     assert np.array_equal(tool.enuToWGS84(geo.README_ENU[3], geo.README_ORIGIN), lla[3])
 
 
-def test_committed_fixture(tool):
+def test_committed_fixture(geo_tool):
+    tool = geo_tool
     z = np.load(os.path.join(HERE, "golden", "geo_golden.npz"))
     same_steps = total = 0
     for r, ref in enumerate(z["refs"]):
@@ -61,7 +71,8 @@ def test_committed_fixture(tool):
     assert same_steps >= 0.99 * total                                         # the stopping decision itself agrees
 
 
-def test_seeded_points_against_the_port(tool):
+def test_seeded_points_against_the_port(geo_tool):
+    tool = geo_tool
     rng = np.random.default_rng(99)
     ref = np.array([116.39, 39.91, 43.5])
     n = 200_003                                                               # ragged: not a multiple of 32 or 256
@@ -83,7 +94,8 @@ def test_seeded_points_against_the_port(tool):
     assert np.array_equal(d.cpu().numpy(), back)
 
 
-def test_empty_and_invalid(tool):
+def test_empty_and_invalid(geo_tool):
+    tool = geo_tool
     assert tool.enuToWGS84_Batch(np.zeros((0, 3)), [0, 0, 0]).shape == (0, 3)
     assert tool.wgs84ToENU_Batch(np.zeros((0, 3)), [0, 0, 0]).shape == (0, 3)
     with pytest.raises(MsnapError):
@@ -99,6 +111,37 @@ def test_empty_and_invalid(tool):
     out = tool.enuToWGS84_Batch(np.array([[0.0, x, 25.0]]), ref)[0]
     exp = geo.enu_to_wgs84_batch(np.array([[0.0, x, 25.0]]), ref)[0]
     assert np.isnan(out[1]) == np.isnan(exp[1]) and abs(out[2] - exp[2]) <= POS_TOL
+
+
+def test_direction_form_equals_trig_form(tool):
+    """The default (direction-vector) iteration against the statement-by-statement one: same steps, rounding-level
+    differences in the results."""
+    rng = np.random.default_rng(3)
+    n = 1 << 20
+    for ref in ([109.56, 40.87, 0.0], [10.0, -89.2, 2800.0], [-45.0, 0.01, 0.0]):
+        ref = np.array(ref)
+        enu = np.column_stack([rng.normal(0, 1e5, n), rng.normal(0, 1e5, n), rng.uniform(-1000, 20000, n)])
+        d = torch.from_numpy(enu).cuda()
+        out = {}
+        for trig in (False, True):
+            tool.set_geo_exact_trig(trig)
+            lla = torch.empty_like(d)
+            st = torch.zeros(n, dtype=torch.int32, device="cuda")
+            tool.enu_to_wgs84_dev(ref, d, lla, steps_out=st)
+            tool.synchronize()
+            out[trig] = (lla.cpu().numpy(), st.cpu().numpy())
+        tool.set_geo_exact_trig(False)
+        fin = np.isfinite(out[True][0]).all(axis=1)
+        assert fin.mean() > 0.999999 and np.array_equal(fin, np.isfinite(out[False][0]).all(axis=1))
+        dl = np.abs(out[False][0][fin] - out[True][0][fin])
+        # near a pole a metre on the ground is many degrees of longitude: compare longitudes as ground distance
+        coslat = np.cos(np.radians(out[True][0][fin, 1]))
+        assert (dl[:, 0] * coslat).max() <= ANG_TOL and dl[:, 1].max() <= ANG_TOL
+        # alt = p / cos(lat) - N (cpp:959) amplifies a rounding error d in lat to R d / cos(lat): 2e-9 m at mid latitudes,
+        # 1e-6 m at 10 km from a pole -- in the reference's own arithmetic as much as here
+        assert (dl[:, 2] - 5e-9 / coslat).max() <= POS_TOL
+        assert np.abs(out[False][1] - out[True][1]).max() <= 1
+        assert np.mean(out[False][1] == out[True][1]) >= 0.99
 
 
 def test_sampler_rows_leave_as_wgs84(tool):

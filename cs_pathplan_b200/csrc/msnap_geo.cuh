@@ -123,6 +123,8 @@ __device__ __forceinline__ int geo_ecef_to_wgs84(double x, double y, double z, d
 // Differences to geo_ecef_to_wgs84: rounding only (a few 1e-16 rad), plus the stopping decision where |d lat| falls
 // within ~1e-4 relative of the threshold (the reference's own subtraction is that noisy there); one step more or less
 // moves the result by < 1e-14 rad.
+__constant__ double GEO_ATAN_C[GEO_ATAN_N] = GEO_ATAN_COEFFS;
+
 // ---- lean fp64 primitives for the direction form (device only) ------------------------------------------------
 // CUDA's sqrt / division / atan2 are IEEE-exact resp. <= 2 ulp but carry slow paths and cost 23 / 20 / 128 issued
 // instructions each (ncu, this kernel); these cost 7-11 / 6-8 / ~45 and are accurate to ~1 ulp on the ranges used.
@@ -152,15 +154,17 @@ __device__ __forceinline__ double geo_sqrt_pos(double q, double y) {  // sqrt(q)
 // Chebyshev interpolation in 60-digit arithmetic, approximation error 3e-17), quadrant fix-up with pi split into two doubles.  atan2(0, 0) = 0.
 __device__ __forceinline__ double geo_atan2(double y, double x) {
     const double ax = fabs(x), ay = fabs(y);
-    const double mx = fmax(ax, ay), mn = fmin(ax, ay);
+    const bool sw = ay > ax, xneg = x < 0.0;
+    const double mx = sw ? ay : ax, mn = sw ? ax : ay;
     const double t = geo_div(mn, mx), u = t * t;
-    constexpr double c[GEO_ATAN_N] = GEO_ATAN_COEFFS;
-    double pl = c[GEO_ATAN_N - 1];
+    double pl = GEO_ATAN_C[GEO_ATAN_N - 1];
 #pragma unroll
-    for (int i = GEO_ATAN_N - 2; i >= 0; --i) pl = fma(pl, u, c[i]);
+    for (int i = GEO_ATAN_N - 2; i >= 0; --i) pl = fma(pl, u, GEO_ATAN_C[i]);  // DFMA with a constant-bank operand
     double a = fma(t * u, pl, t);
-    if (ay > ax) a = (1.57079632679489655800e+00 - a) + 6.12323399573676603587e-17;
-    if (x < 0.0) a = (3.14159265358979311600e+00 - a) + 1.22464679914735320717e-16;
+    // octant fix-up  a | pi/2 - a | pi/2 + a | pi - a  as  (off_hi + (+-a)) + off_lo
+    const double off_hi = sw ? 1.57079632679489655800e+00 : (xneg ? 3.14159265358979311600e+00 : 0.0);
+    const double off_lo = sw ? 6.12323399573676603587e-17 : (xneg ? 1.22464679914735320717e-16 : 0.0);
+    a = (off_hi + (sw != xneg ? -a : a)) + off_lo;
     if (mx == 0.0) a = 0.0;
     return copysign(a, y);
 }
@@ -182,7 +186,7 @@ __device__ __forceinline__ int geo_ecef_to_wgs84_fast(double x, double y, double
     double S = z + E2A * (st * st * st);            // z + e2 a (1-e2) sin^3 / (1-e2), cpp:931
     double C = fma(-E2A, ct * ct * ct, p);          // p - e2 a cos^3,                  cpp:932
     int steps = 0;
-#pragma unroll 1
+#pragma unroll
     for (int i = 0; i < GEO_MAX_STEPS; ++i) {
         const double q = fma(C, C, OME2 * S * S);
         const double W = q * geo_rsqrt(q);
@@ -191,7 +195,7 @@ __device__ __forceinline__ int geo_ecef_to_wgs84_fast(double x, double y, double
         const bool done = fabs(cross) < GEO_TOL * dot;
         S = Sn;
         C = Cn;
-        ++steps;
+        steps = i + 1;
         if (done) break;
     }
     const double ir = geo_rsqrt(fma(S, S, C * C));

@@ -8,15 +8,15 @@
 #include "msnap_geo_atan.h"
 
 static double geo_atan2_host(double y, double x) {
-    static const double c[GEO_ATAN_N] = GEO_ATAN_COEFFS;
     const double ax = std::fabs(x), ay = std::fabs(y);
-    const double mx = ax > ay ? ax : ay, mn = ax > ay ? ay : ax;
+    const bool sw = ay > ax, xneg = x < 0.0;
+    const double mx = sw ? ay : ax, mn = sw ? ax : ay;
     const double t = mn / mx, u = t * t;
-    double pl = c[GEO_ATAN_N - 1];
-    for (int i = GEO_ATAN_N - 2; i >= 0; --i) pl = std::fma(pl, u, c[i]);
+    const double pl = GEO_ATAN_POLY(std::fma, u);
     double a = std::fma(t * u, pl, t);
-    if (ay > ax) a = (1.57079632679489655800e+00 - a) + 6.12323399573676603587e-17;
-    if (x < 0.0) a = (3.14159265358979311600e+00 - a) + 1.22464679914735320717e-16;
+    const double off_hi = sw ? 1.57079632679489655800e+00 : (xneg ? 3.14159265358979311600e+00 : 0.0);
+    const double off_lo = sw ? 6.12323399573676603587e-17 : (xneg ? 1.22464679914735320717e-16 : 0.0);
+    a = (off_hi + (sw != xneg ? -a : a)) + off_lo;
     if (mx == 0.0) a = 0.0;
     return std::copysign(a, y);
 }

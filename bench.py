@@ -345,8 +345,28 @@ def run_b200(args):
         d2h = int(r.samples.nbytes + out["times"].nbytes + out["coeff"].nbytes + out["max_dev"].nbytes +
                   out["iters"].nbytes + out["vw_final"].nbytes + out["sample_offset"].nbytes +
                   out["flags"].nbytes + out["best_s"].nbytes)
+        # the same step with the sampled rows leaving as WGS84 [lon, lat, alt] (getPlan's
+        # enuToWGS84_Batch, uavPathPlanning.cpp:3699, applied on the device by k_enu_to_wgs84 after the sampler)
+        geo = None
+        if headline:
+            origin = np.array([109.56059880227296, 40.86719901015758, 0.0])   # readme.md:11, the uav31_0 origin
+            for t_ in tools:
+                t_.set_sample_frame("wgs84", origin)
+            g_steps = min(steps, 500)
+            g_ms, g_launches = timed_run(cfg, sets, g_steps, 3, S)
+            tool.profile_begin()
+            for i in range(prof_steps):
+                step(cfg, sets[i % ROTATE])
+            gprof = tool.profile_end()
+            for t_ in tools:
+                t_.set_sample_frame("enu")
+            kname = next(k for k in gprof if k.startswith("k_enu_to_wgs84"))
+            geo = dict(value=world * B * g_steps / (g_ms * 1e-3), unit=UNIT, ms_per_step=g_ms / g_steps,
+                       launches_per_step=g_launches / g_steps, kernel=kname,
+                       kernel_ms_per_step=gprof[kname]["total_ms"] / prof_steps, rows_per_step=tot_samples,
+                       algorithmic_bytes_per_launch=48 * tot_samples)
         results[weights] = dict(
-            ms=ms, steps=steps, launches=launches, value=world * B * steps / (ms * 1e-3), latency_ms=latency_ms,
+            geo=geo, ms=ms, steps=steps, launches=launches, value=world * B * steps / (ms * 1e-3), latency_ms=latency_ms,
             e2e=dict(value=world * B * e2e_steps / e2e_s, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                      steps=e2e_steps, ms_per_step=e2e_s / e2e_steps * 1e3, host_threads=S,
                      single_call_ms=e2e_single_ms),
@@ -417,6 +437,14 @@ def run_b200(args):
                              "roofline": roof(r, w), "workload": workload_name(w, B)}
                          for w, r in results.items() if w != args.weights},
         }
+        if h.get("geo"):
+            g = dict(h["geo"])
+            gbs = g["algorithmic_bytes_per_launch"] / (g["kernel_ms_per_step"] * 1e-3) / 1e9
+            g.update(note="same workload and driver as `value`, sampled rows converted to WGS84 lon/lat/alt on the device "
+                          "(msnap_set_sample_frame); SURVEY.md section 8f rank 1",
+                     kernel_hbm_GBps=gbs, kernel_hbm_frac=gbs / hbm_peak,
+                     kernel_rows_per_s=g["rows_per_step"] / (g["kernel_ms_per_step"] * 1e-3))
+            line["wgs84_frame"] = g
         if world == 1 and not args.no_cpu_baseline:
             try:
                 from oracle import ref

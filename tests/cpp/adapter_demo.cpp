@@ -6,7 +6,16 @@
 #include <cstdlib>
 #include <exception>
 
+#include "geo_transform_gpu.hpp"
 #include "minimum_snap_gpu.hpp"
+
+// uavPathPlanning.hpp:145-156
+struct WGS84Point {
+    double lon, lat, alt;
+};
+struct ENUPoint {
+    double east, north, up;
+};
 
 int main(int argc, char **argv) {
     // readme.md:14-20 -- ENU waypoints of the uav31_0 leader route
@@ -50,6 +59,21 @@ int main(int argc, char **argv) {
         // too-short input: empty matrix, as minimum_snap.cpp:54-57
         Eigen::MatrixXd one(1, 3);
         std::printf("short %ld\n", static_cast<long>(generator_.GenerateTrajectoryMatrix(one, cfg).rows()));
+        // the planner's transforms on its own structs (readme.md:11): WGS84 -> ENU -> WGS84 about the leader's start
+        const std::vector<WGS84Point> wgs = {{109.56059880227296, 40.86719901015758, 1669.0},
+                                             {109.2995997466117, 40.86719901015758, 1674.0},
+                                             {109.299698988346, 40.84019989401251, 1674.0},
+                                             {109.38269994693026, 40.84019989401251, 1674.0},
+                                             {109.54869918188973, 40.84019989401251, 1674.0},
+                                             {109.54869918188973, 40.86719901015758, 1674.0},
+                                             {109.54869918188973, 40.868098891288774, 1674.0}};
+        const WGS84Point origin_{109.56059880227296, 40.86719901015758, 0.0};
+        const std::vector<ENUPoint> e = msnap_geo::wgs84ToENU_Batch<ENUPoint>(generator_.handle(), wgs, origin_);
+        const std::vector<WGS84Point> back = msnap_geo::enuToWGS84_Batch<WGS84Point>(generator_.handle(), e, origin_);
+        std::printf("geo %zu\n", e.size());
+        for (size_t i = 0; i < e.size(); ++i)
+            std::printf("%.17g %.17g %.17g %.17g %.17g %.17g\n", e[i].east, e[i].north, e[i].up, back[i].lon, back[i].lat,
+                        back[i].alt);
     } catch (const std::exception &e) {
         std::printf("exception %s\n", e.what());
         return 3;

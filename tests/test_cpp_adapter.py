@@ -54,3 +54,11 @@ def test_adapter_reproduces_golden(golden, speed, name):
     assert scaled_coeff_err(coeff.reshape(6, 3, 4), c_ref.reshape(6, 3, 4), T) <= 1e-8
     assert abs(float(head[4]) - info.max_dev) <= 1e-8
     assert lines[2 + n + 6].split() == ["short", "0"]
+    # the planner's coordinate transforms through include/geo_transform_gpu.hpp against the reference's recorded run
+    from oracle import geo
+
+    assert lines[3 + n + 6].split() == ["geo", "7"]
+    rows = np.array([[float(v) for v in ln.split()] for ln in lines[4 + n + 6:4 + n + 6 + 7]])
+    assert np.abs(rows[:, :3] - geo.README_ENU).max() <= 1e-7
+    assert np.abs(rows[:, 3:5] - geo.README_WGS84_BACK[:, :2]).max() <= 1e-12
+    assert np.abs(rows[:, 5] - geo.README_WGS84_BACK[:, 2]).max() <= 1e-6

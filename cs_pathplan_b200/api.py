@@ -304,6 +304,14 @@ class TrajectoryGeneratorTool:
         ref = None if reference is None else _f64(reference).reshape(3)
         self._check(self._L.msnap_set_sample_frame(self._h, 1 if frame == "wgs84" else 0, _ptr(ref)))
 
+    def set_waypoint_frame(self, frame: str = "enu", reference=None):
+        """Frame of the waypoints the generate / sample_bound calls take: "enu" or "wgs84" rows [lon, lat, alt], converted
+        on the device first = prepareWaypoints' wgs84ToENU_Batch(wgs84_points, origin_) (cpp:2640)."""
+        if frame not in ("enu", "wgs84"):
+            raise ValueError("frame must be 'enu' or 'wgs84'")
+        ref = None if reference is None else _f64(reference).reshape(3)
+        self._check(self._L.msnap_set_waypoint_frame(self._h, 1 if frame == "wgs84" else 0, _ptr(ref)))
+
     # ------------------------------------------------------------------ batched, host buffers
     def solve_qp_batch(self, order, waypoints, times, ns=None, seg_offset=None, vel=None, acc=None,
                        path_weight=0.0, vel_zero_weight=0.0):

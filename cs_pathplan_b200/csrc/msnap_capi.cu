@@ -77,6 +77,8 @@ struct msnap_context {
     // leave as [lon, lat, alt] = enuToWGS84_Batch of the sampled trajectory (uavPathPlanning.cpp:3699)
     int frame = 0;
     GeoFrame geo{};
+    int wp_frame = 0;       // msnap_set_waypoint_frame: 1 = generate / sample_bound take WGS84 waypoints (cpp:2640)
+    GeoFrame wp_geo{};
     bool geo_trig = false;  // msnap_set_geo_exact_trig: ENU -> WGS84 with the reference's per-step sin/cos/atan2
 };
 
@@ -578,10 +580,17 @@ int generate_dev(msnap_context *h, const msnap_config *cfg, double sd, double v_
     const FusedPlan f = plan_fused<O>(h, bi, sp);
     const bool spec = use_generic_spec<O>(h, n_seg, sp);
     const bool ragged = bi.ns_uniform <= 0 && B < 2000000000LL;
+    const size_t n_pts = (size_t)(n_seg + B);
     int rc = arena_reserve(h, h->ws, solve_ws_bytes<O>(n_seg, B, true, coeff_out == nullptr, f, spec) +
                                         sample_ws_bytes(n_seg, B, bi.ns_uniform, h->policy, h->sm_count) +
-                                        (ragged ? padded(n_seg * sizeof(int)) : 0));
+                                        (ragged ? padded(n_seg * sizeof(int)) : 0) +
+                                        (h->wp_frame ? padded(n_pts * 3 * sizeof(double)) : 0));
     if (rc) return rc;
+    if (h->wp_frame) {  // the waypoints arrive as WGS84 rows: wgs84ToENU_Batch (cpp:2640) into the workspace first
+        double *enu = arena_take<double>(h->ws, n_pts * 3);
+        MS_LAUNCH(h, k_wgs84_to_enu, geo_grid(h, (long long)n_pts), GEO_BLOCK, h->wp_geo, (long long)n_pts, wp, enu);
+        wp = enu;
+    }
     if (ragged) {  // segment -> trajectory map, so that the per-segment kernels need no binary search
         int *st = arena_take<int>(h->ws, n_seg);
         MS_LAUNCH(h, k_seg_traj, grid_for(B * 32, 256), 256, B, seg_offset, st);
@@ -1162,6 +1171,8 @@ int msnap_generate_batch_host(msnap_handle h, const msnap_config *cfg, double sa
             k->frame = h->frame;
             k->geo = h->geo;
             k->geo_trig = h->geo_trig;
+            k->wp_frame = h->wp_frame;
+            k->wp_geo = h->wp_geo;
         }
         ctx = h->kids;
     }
@@ -1230,6 +1241,13 @@ int msnap_set_sample_frame(msnap_handle h, int frame, const double *reference_ll
     if (!h || frame < 0 || frame > 1 || (frame == 1 && !geo_reference_ok(reference_lla))) return MSNAP_ERR_INVALID_ARG;
     h->frame = frame;
     if (frame == 1) geo_make_frame(reference_lla, h->geo);
+    return MSNAP_OK;
+}
+
+int msnap_set_waypoint_frame(msnap_handle h, int frame, const double *reference_lla) {
+    if (!h || frame < 0 || frame > 1 || (frame == 1 && !geo_reference_ok(reference_lla))) return MSNAP_ERR_INVALID_ARG;
+    h->wp_frame = frame;
+    if (frame == 1) geo_make_frame(reference_lla, h->wp_geo);
     return MSNAP_OK;
 }
 
@@ -1331,6 +1349,14 @@ int msnap_sample_bound_dev(msnap_handle h, const msnap_config *cfg, double v_avg
     if (rc) return rc;
     BatchIdx bi{B, n_seg, ns_uniform > 0 ? ns_uniform : 0, ns_uniform > 0 ? nullptr : seg_offset};
     const double va = v_avg_override > 0.0 ? v_avg_override : cfg->V_avg;
+    if (h->wp_frame) {
+        const long long n_pts = n_seg + B;
+        rc = arena_reserve(h, h->ws, padded((size_t)n_pts * 3 * sizeof(double)));
+        if (rc) return rc;
+        double *enu = arena_take<double>(h->ws, (size_t)n_pts * 3);
+        MS_LAUNCH(h, k_wgs84_to_enu, geo_grid(h, n_pts), GEO_BLOCK, h->wp_geo, n_pts, waypoints, enu);
+        waypoints = enu;
+    }
     MS_LAUNCH(h, k_bound, grid_for(n_seg, 256), 256, bi, waypoints, va, cfg->min_time_s,
               reinterpret_cast<unsigned long long *>(rows_out_dev));
     return MSNAP_OK;

@@ -181,6 +181,12 @@ int msnap_enu_to_wgs84_host(msnap_handle h, const double *reference_lla, long lo
  * `enuToWGS84_Batch(Trajectory_ENU, origin_)` (cpp:3699) applied on the device before the rows leave it.  The
  * statistics in stats_out are those of the ENU rows either way.  reference_lla may be NULL for frame 0. */
 int msnap_set_sample_frame(msnap_handle h, int frame, const double *reference_lla);
+/* Frame of the waypoints msnap_generate_batch_* / msnap_generate_one_host / msnap_sample_bound_* read: 0 (default) = ENU;
+ * 1 = WGS84 {lon, lat, alt} rows, converted about reference_lla on the device before anything else, i.e. prepareWaypoints'
+ * `Enu_waypoint = wgs84ToENU_Batch(wgs84_points, origin_)` (cpp:2640) in front of Minisnap_3D (cpp:3684).  With both
+ * frames set to 1 a call is getPlan's leader chain WGS84 waypoints -> ENU -> minimum snap -> sampled ENU -> WGS84 rows
+ * (cpp:2640, 3684, 3699) without the ENU data ever leaving the device.  msnap_solve_qp_batch_* is not affected. */
+int msnap_set_waypoint_frame(msnap_handle h, int frame, const double *reference_lla);
 /* Execution form of ecefToWGS84's fixed-point iteration (cpp:926-968) inside every ENU -> WGS84 call of this handle:
  * 0 (default) = the iteration carried on direction vectors (one sqrt per step, the angle formed once at the end);
  * 1 = statement by statement as the reference writes it (sin, cos, sqrt, two divisions and an atan2 per step).  Same start

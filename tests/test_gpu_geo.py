@@ -208,3 +208,40 @@ def test_full_size_round_trip_properties(tool):
     # spot check against the port on a strided subsample
     idx = torch.arange(0, n, 4099, device="cuda")
     assert lla_close(lla[idx].cpu().numpy(), geo.enu_to_wgs84_batch(enu[idx].cpu().numpy(), ref, threads=8))
+
+
+def test_wgs84_waypoints_in_wgs84_rows_out(tool):
+    """getPlan's leader chain on the device (cpp:2640 -> 3684 -> 3699): WGS84 waypoints -> ENU -> minimum snap ->
+    sampled ENU -> WGS84 rows.  (1) the reference's own case against the oracle chain, (2) a batch: bitwise the same as
+    the three calls made one after the other."""
+    from oracle import msnap_oracle as mo
+
+    origin = geo.README_ORIGIN
+    try:
+        tool.set_waypoint_frame("wgs84", origin)
+        tool.set_sample_frame("wgs84", origin)
+        s = tool.GenerateTrajectoryMatrix(geo.README_WGS84, shipped_config(), 300.0, 30.0)
+        enu_wp = geo.wgs84_to_enu_batch(geo.README_WGS84, origin)
+        ocfg = mo.MinimumSnapConfig(order=2, path_weight=1e-7, vel_zero_weight=0.01, V_avg=200.0, min_time_s=1.0,
+                                    sample_distance=300.0)
+        s_o, _ = mo.generate_trajectory_matrix(enu_wp, ocfg, sample_distance_override=300.0, v_avg_override=30.0)
+        assert s.shape == s_o.shape == (168, 3)
+        assert lla_close(s, geo.enu_to_wgs84_batch(s_o, origin))
+        # batch
+        wp_enu, ns = workloads.cfg2(B=700, ns=16)
+        wp_enu = wp_enu * np.array([30.0, 30.0, 1.0]) + np.array([0.0, 0.0, 1500.0])   # a few km apart, 1.5 km up
+        wp_lla = geo.enu_to_wgs84_batch(wp_enu, origin)
+        cfg = workloads.synthetic_config(4, "shipped", sample_distance=25.0)
+        cfg.V_avg = 150.0
+        both = tool.generate_batch(cfg, wp_lla, ns=ns)
+        tool.set_waypoint_frame("enu")
+        tool.set_sample_frame("enu")
+        step1 = tool.wgs84ToENU_Batch(wp_lla, origin)
+        step2 = tool.generate_batch(cfg, step1, ns=ns)
+        step3 = tool.enuToWGS84_Batch(step2.samples, origin)
+        assert np.array_equal(both.sample_offset, step2.sample_offset) and np.array_equal(both.coeff, step2.coeff)
+        assert np.array_equal(both.times, step2.times) and np.array_equal(both.samples, step3)
+        assert np.abs(step1 - wp_enu).max() <= 2e-7
+    finally:
+        tool.set_waypoint_frame("enu")
+        tool.set_sample_frame("enu")

@@ -5,6 +5,8 @@ Drop-in for the reference's ``TrajectoryGeneratorTool`` (math_util/minimum_snap.
 Python host layer used by the tests and the benchmark.
 """
 from .api import (  # noqa: F401
+    AltitudeParams,
+    shipped_altitude_params,
     BatchResult,
     MinimumSnapConfig,
     TrajectoryGeneratorTool,
@@ -14,6 +16,8 @@ from .api import (  # noqa: F401
 from .sharding import shard_bounds, shard_batch  # noqa: F401
 
 __all__ = [
+    "AltitudeParams",
+    "shipped_altitude_params",
     "BatchResult",
     "MinimumSnapConfig",
     "TrajectoryGeneratorTool",

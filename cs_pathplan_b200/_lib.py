@@ -33,6 +33,13 @@ class msnap_config(C.Structure):
     ]
 
 
+class msnap_altitude_params(C.Structure):
+    """struct msnap_altitude_params (include/msnap.h) == AltitudeParams (uavPathPlanning.hpp:415-421)."""
+
+    _fields_ = [("lambda_smooth", C.c_double), ("lambda_follow", C.c_double), ("max_climb_rate", C.c_double),
+                ("uav_R", C.c_double), ("safe_distance", C.c_double)]
+
+
 _vp = C.c_void_p
 _ll = C.c_longlong
 _i = C.c_int
@@ -69,6 +76,10 @@ SIGNATURES = {
     "msnap_set_waypoint_frame": (_i, [_vp, _i, _vp]),
     "msnap_set_geo_exact_trig": (_i, [_vp, _i]),
     "msnap_debug_geo_steps_dev": (_i, [_vp, _vp, _ll, _vp, _vp, _vp]),
+    "msnap_altitude_params_default": (None, [C.POINTER(msnap_altitude_params)]),
+    "msnap_altitude_optimize_batch_dev": (_i, [_vp, C.POINTER(msnap_altitude_params), _ll, _vp, _ll] + [_vp] * 5),
+    "msnap_altitude_optimize_batch_host": (_i, [_vp, C.POINTER(msnap_altitude_params), _ll] + [_vp] * 6),
+    "msnap_cost_map_lookup_dev": (_i, [_vp, _vp, _i, _i, _d, _d, _d, _ll, _vp, _vp, _vp]),
     "msnap_profile_begin": (_i, [_vp]),
     "msnap_profile_end": (_i, [_vp, C.c_char_p, _ll]),
     "msnap_debug_phase_clocks": (_i, [_vp, _i, _vp]),

@@ -15,7 +15,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import MsnapError, msnap_config
+from ._lib import MsnapError, msnap_altitude_params, msnap_config
 
 
 @dataclass
@@ -54,6 +54,26 @@ class MinimumSnapConfig:
             c.order, c.path_weight, c.vel_zero_weight, c.V_avg, c.min_time_s, c.sample_distance,
             tuple(c.start_vel), tuple(c.end_vel), tuple(c.start_acc), tuple(c.end_acc),
         )
+
+
+@dataclass
+class AltitudeParams:
+    """struct AltitudeParams, uavPathPlanning.hpp:415-421 -- same field names, same defaults."""
+
+    lambda_smooth: float = 1.0
+    lambda_follow: float = 0.0
+    max_climb_rate: float = 2.0
+    uav_R: float = 2.0
+    safe_distance: float = 50.0
+
+    def to_c(self) -> msnap_altitude_params:
+        return msnap_altitude_params(float(self.lambda_smooth), float(self.lambda_follow), float(self.max_climb_rate),
+                                     float(self.uav_R), float(self.safe_distance))
+
+
+def shipped_altitude_params() -> AltitudeParams:
+    """The altitude_optimization block the reference ships in config.yaml:1-8."""
+    return AltitudeParams(lambda_smooth=1.0, lambda_follow=1.0, max_climb_rate=0.3, uav_R=2.0, safe_distance=10.0)
 
 
 def shipped_config(**over) -> MinimumSnapConfig:
@@ -303,6 +323,54 @@ class TrajectoryGeneratorTool:
             raise ValueError("frame must be 'enu' or 'wgs84'")
         ref = None if reference is None else _f64(reference).reshape(3)
         self._check(self._L.msnap_set_sample_frame(self._h, 1 if frame == "wgs84" else 0, _ptr(ref)))
+
+    # ------------------------------------------------------------------ altitude optimisation (cpp:1329-1364, 1575-1827)
+    def altitude_optimize_batch(self, rows, row_offset, params: AltitudeParams, elev=None, return_info: bool = False):
+        """B independent optimizeSegmentAltitudeENU calls: rows [n,3] (east, north, up) with CSR row_offset [B+1], elev [n]
+        (terrain elevation per row, NaN = none).  Returns the rows with the optimised ``up`` column (a copy), and with
+        ``return_info`` also (z after pass 1 [n], solves of pass 2 [B], flags [B])."""
+        rows = _f64(rows).copy()
+        off = np.ascontiguousarray(row_offset, dtype=np.int64)
+        B = off.shape[0] - 1
+        if rows.ndim != 2 or rows.shape[1] != 3 or B < 0 or (B >= 0 and (off[0] != 0 or off[-1] != rows.shape[0])):
+            raise ValueError("rows must be [n,3] and row_offset [B+1] with row_offset[0] = 0, row_offset[B] = n")
+        elev = None if elev is None else _f64(elev)
+        if elev is not None and elev.shape != (rows.shape[0],):
+            raise ValueError("elev must have one entry per row")
+        z1 = np.empty(rows.shape[0])
+        solves = np.zeros(max(B, 0), dtype=np.int32)
+        flags = np.zeros(max(B, 0), dtype=np.uint32)
+        c = params.to_c()
+        self._check(self._L.msnap_altitude_optimize_batch_host(self._h, C.byref(c), B, _ptr(off), _ptr(rows), _ptr(elev),
+                                                               _ptr(z1), _ptr(solves), _ptr(flags)))
+        return (rows, z1, solves, flags) if return_info else rows
+
+    def optimizeSegmentAltitudeENU(self, segment_enu, params: AltitudeParams, elev=None) -> np.ndarray:
+        """UavPathPlanner::optimizeSegmentAltitudeENU (cpp:1329-1364) for one trajectory: returns the rows with the new
+        ``up`` values (the reference updates segment_enu in place)."""
+        seg = _f64(segment_enu)
+        return self.altitude_optimize_batch(seg, np.array([0, seg.shape[0]], dtype=np.int64), params, elev)
+
+    def altitude_optimize_batch_dev(self, params: AltitudeParams, row_offset, rows, elev=None, z_pass1=None, solves=None,
+                                    flags=None):
+        """Device rows (CUDA torch tensors: row_offset int64 [B+1], rows fp64 [cap,3], elev fp64 [cap]); enqueued on the
+        handle's stream, ``up`` column updated in place."""
+        c = params.to_c()
+
+        def dp(t):
+            return None if t is None else int(t.data_ptr())
+
+        self._check(self._L.msnap_altitude_optimize_batch_dev(
+            self._h, C.byref(c), int(row_offset.numel()) - 1, dp(row_offset), int(rows.shape[0]), dp(rows), dp(elev),
+            dp(z_pass1), dp(solves), dp(flags)))
+
+    def cost_map_lookup_dev(self, grid, resolution, origin_x, origin_y, rows, elev_out, n_rows=None):
+        """ElevationCostMap::getCostAt (elevation_cost_map.cpp:373-380) for device rows: grid = CUDA float32 tensor
+        [height, width] (row-major, top-left origin); n_rows = optional device int64 scalar bounding the rows."""
+        self._check(self._L.msnap_cost_map_lookup_dev(
+            self._h, int(grid.data_ptr()), int(grid.shape[1]), int(grid.shape[0]), float(resolution), float(origin_x),
+            float(origin_y), int(rows.shape[0]), None if n_rows is None else int(n_rows.data_ptr()), int(rows.data_ptr()),
+            int(elev_out.data_ptr())))
 
     def set_waypoint_frame(self, frame: str = "enu", reference=None):
         """Frame of the waypoints the generate / sample_bound calls take: "enu" or "wgs84" rows [lon, lat, alt], converted

@@ -18,6 +18,7 @@
 #include "msnap_generic.cuh"
 #include "msnap_fused.cuh"
 #include "msnap_geo.cuh"
+#include "msnap_alt.cuh"
 
 static const MsnapOrderTab h_tab[MSNAP_MAX_ORDER - MSNAP_MIN_ORDER + 1] = MSNAP_ORDER_TABLES;
 
@@ -1333,6 +1334,96 @@ int msnap_debug_geo_steps_dev(msnap_handle h, const double *reference_lla, long 
     GeoFrame f;
     geo_make_frame(reference_lla, f);
     return launch_enu_to_wgs84(h, f, n, nullptr, enu, lla_out, steps_out);
+}
+
+// ---------------------------------------------------------------------------------------------- altitude optimisation
+void msnap_altitude_params_default(msnap_altitude_params *p) {  // uavPathPlanning.hpp:415-421
+    if (!p) return;
+    p->lambda_smooth = 1.0;
+    p->lambda_follow = 0.0;
+    p->max_climb_rate = 2.0;
+    p->uav_R = 2.0;
+    p->safe_distance = 50.0;
+}
+
+int msnap_cost_map_lookup_dev(msnap_handle h, const float *grid, int width, int height, double resolution, double origin_x,
+                              double origin_y, long long n_rows_cap, const long long *n_rows_dev, const double *rows,
+                              double *elev_out) {
+    if (!h || !grid || width <= 0 || height <= 0 || !(resolution > 0.0) || n_rows_cap < 0 ||
+        (n_rows_cap > 0 && (!rows || !elev_out)))
+        return MSNAP_ERR_INVALID_ARG;
+    if (n_rows_cap == 0) return MSNAP_OK;
+    DeviceGuard guard(h->device);
+    const long long want = (n_rows_cap + 255) / 256, cap = (long long)h->sm_count * 8;
+    MS_LAUNCH(h, k_cost_lookup, (unsigned)(want < cap ? want : cap), 256, grid, width, height, resolution, origin_x, origin_y,
+              n_rows_cap, n_rows_dev, rows, elev_out);
+    return MSNAP_OK;
+}
+
+int msnap_altitude_optimize_batch_dev(msnap_handle h, const msnap_altitude_params *params, long long B,
+                                      const long long *row_offset, long long n_rows_cap, double *rows_inout,
+                                      const double *elev, double *z_pass1_out, int *solves_out, unsigned *flags_out) {
+    if (!h || !params || B < 0 || n_rows_cap < 0 || (B > 0 && (!row_offset || (n_rows_cap > 0 && !rows_inout))))
+        return MSNAP_ERR_INVALID_ARG;
+    if (B == 0 || n_rows_cap == 0) return MSNAP_OK;
+    DeviceGuard guard(h->device);
+    const size_t n = (size_t)n_rows_cap;
+    int rc = arena_reserve(h, h->ws, 8 * padded(n * sizeof(double)) + padded(n));
+    if (rc) return rc;
+    double *w1 = arena_take<double>(h->ws, n), *w2 = arena_take<double>(h->ws, n), *tgt = arena_take<double>(h->ws, n);
+    double *l1 = arena_take<double>(h->ws, n), *l2 = arena_take<double>(h->ws, n), *yd = arena_take<double>(h->ws, n);
+    double *zin = arena_take<double>(h->ws, n), *cur = arena_take<double>(h->ws, n);
+    unsigned char *act = arena_take<unsigned char>(h->ws, n);
+    const AltParams p{params->lambda_smooth, params->lambda_follow, params->max_climb_rate, params->uav_R,
+                      params->safe_distance};
+    const long long want = (n_rows_cap + 255) / 256, cap = (long long)h->sm_count * 8;
+    MS_LAUNCH(h, k_alt_prep, (unsigned)(want < cap ? want : cap), 256, p, B, row_offset, rows_inout, elev, w1, w2, tgt);
+    MS_LAUNCH(h, k_alt_solve, grid_for(B, 32), 32, p, B, row_offset, rows_inout, elev, w1, w2, tgt, l1, l2, yd, zin, cur, act,
+              z_pass1_out, solves_out, flags_out);
+    return MSNAP_OK;
+}
+
+int msnap_altitude_optimize_batch_host(msnap_handle h, const msnap_altitude_params *params, long long B,
+                                       const long long *row_offset, double *rows_inout, const double *elev,
+                                       double *z_pass1_out, int *solves_out, unsigned *flags_out) {
+    if (!h || !params || B < 0 || (B > 0 && !row_offset)) return MSNAP_ERR_INVALID_ARG;
+    if (B == 0) return MSNAP_OK;
+    if (row_offset[0] != 0) return MSNAP_ERR_INVALID_ARG;
+    for (long long b = 0; b < B; ++b)
+        if (row_offset[b + 1] < row_offset[b]) return MSNAP_ERR_INVALID_ARG;
+    const long long n = row_offset[B];
+    if (n == 0) {
+        for (long long b = 0; b < B; ++b) {
+            if (solves_out) solves_out[b] = 0;
+            if (flags_out) flags_out[b] = 0;
+        }
+        return MSNAP_OK;
+    }
+    if (!rows_inout) return MSNAP_ERR_INVALID_ARG;
+    DeviceGuard guard(h->device);
+    MS_CUDA(h, cudaStreamSynchronize(h->aux));
+    int rc = arena_reserve(h, h->io, padded((B + 1) * sizeof(long long)) + padded((size_t)n * 3 * sizeof(double)) +
+                                         2 * padded((size_t)n * sizeof(double)) + padded(B * sizeof(int)) +
+                                         padded(B * sizeof(unsigned)));
+    if (rc) return rc;
+    long long *d_off = arena_take<long long>(h->io, B + 1);
+    double *d_rows = arena_take<double>(h->io, (size_t)n * 3);
+    double *d_elev = arena_take<double>(h->io, (size_t)n), *d_z1 = arena_take<double>(h->io, (size_t)n);
+    int *d_sol = arena_take<int>(h->io, B);
+    unsigned *d_fl = arena_take<unsigned>(h->io, B);
+    cudaStream_t st = h->stream;
+    MS_CUDA(h, cudaMemcpyAsync(d_off, row_offset, (B + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    MS_CUDA(h, cudaMemcpyAsync(d_rows, rows_inout, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (elev) MS_CUDA(h, cudaMemcpyAsync(d_elev, elev, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = msnap_altitude_optimize_batch_dev(h, params, B, d_off, n, d_rows, elev ? d_elev : nullptr,
+                                           z_pass1_out ? d_z1 : nullptr, d_sol, d_fl);
+    if (rc) return rc;
+    MS_CUDA(h, cudaMemcpyAsync(rows_inout, d_rows, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (z_pass1_out) MS_CUDA(h, cudaMemcpyAsync(z_pass1_out, d_z1, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (solves_out) MS_CUDA(h, cudaMemcpyAsync(solves_out, d_sol, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (flags_out) MS_CUDA(h, cudaMemcpyAsync(flags_out, d_fl, B * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    MS_CUDA(h, cudaStreamSynchronize(st));
+    return MSNAP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------- bound

@@ -196,6 +196,40 @@ int msnap_set_geo_exact_trig(msnap_handle h, int enable);
 int msnap_debug_geo_steps_dev(msnap_handle h, const double *reference_lla, long long n, const double *enu, double *lla_out,
                               int *steps_out);
 
+/* ---- altitude optimisation of sampled trajectories, batched ----------------------
+ * Drop-in for UavPathPlanner::optimizeSegmentAltitudeENU (/root/reference/uavPathPlanning.cpp:1329-1364) = optimizeHeights
+ * (cpp:1575-1712) followed by optimizeHeightsGlobalSmooth with lambda_smooth x 10 and max_climb_rate x 0.5 (cpp:1714-1827):
+ * the step getPlan runs on Minisnap_3D's sampled trajectory before converting it to WGS84 (cpp:3712-3729, 1535-1573).  One
+ * independent problem per trajectory; the reference's Eigen::SimplicialLDLT on the SPD pentadiagonal Hessian is replaced
+ * by a banded LDL' recurrence per trajectory.
+ *   params      : struct AltitudeParams (uavPathPlanning.hpp:415-421; config.yaml:1-8 ships 1.0, 1.0, 0.3, 2.0, 10.0)
+ *   row_offset  : [B+1] (int64) CSR layout of the rows, e.g. the sample_offset_out of msnap_generate_batch_*
+ *   rows_inout  : [rows][3] {east, north, up}; the `up` column is replaced by the optimised heights (cpp:1357-1359)
+ *   elev        : [rows] terrain elevation the cost map returns at each row (getCostAt, elevation_cost_map.cpp:373-380),
+ *                 NaN where it has no value; NULL = no terrain anywhere.  msnap_cost_map_lookup_dev fills it from a grid.
+ *   z_pass1_out : [rows] optional, the heights after optimizeHeights (before the global smoothing pass)
+ *   solves_out  : [B] optional, solves the active-set loop of pass 2 took (1..10, cpp:1733-1814)
+ *   flags_out   : [B] optional, bit 0 = a non-positive pivot appeared (the reference's "decomposition failed")
+ * _dev: device pointers, n_rows_cap = allocated rows (the exact count is read from row_offset[B] on the device), enqueued on
+ * the handle's stream.  _host: host pointers, returns when the outputs are complete. */
+typedef struct msnap_altitude_params {
+    double lambda_smooth, lambda_follow, max_climb_rate, uav_R, safe_distance;
+} msnap_altitude_params;
+void msnap_altitude_params_default(msnap_altitude_params *p);
+int msnap_altitude_optimize_batch_dev(msnap_handle h, const msnap_altitude_params *params, long long B,
+                                      const long long *row_offset, long long n_rows_cap, double *rows_inout,
+                                      const double *elev, double *z_pass1_out, int *solves_out, unsigned *flags_out);
+int msnap_altitude_optimize_batch_host(msnap_handle h, const msnap_altitude_params *params, long long B,
+                                       const long long *row_offset, double *rows_inout, const double *elev,
+                                       double *z_pass1_out, int *solves_out, unsigned *flags_out);
+/* ElevationCostMap::getCostAt (elevation_cost_map.cpp:373-380) for every row: grid is a DEVICE float array
+ * [height][width], row-major, top-left origin at (origin_x, origin_y) in ENU metres, square cells of `resolution` metres;
+ * elev_out[i] = the cell containing (east_i, north_i), NaN outside the grid.  n_rows_dev (device int64, may be NULL)
+ * bounds the rows actually looked up, e.g. sample_offset + B. */
+int msnap_cost_map_lookup_dev(msnap_handle h, const float *grid, int width, int height, double resolution, double origin_x,
+                              double origin_y, long long n_rows_cap, const long long *n_rows_dev, const double *rows,
+                              double *elev_out);
+
 /* ---- per-kernel timing (bench.py's roofline pass) ------------------------------------------------------------
  * Between begin and end every kernel the handle launches is bracketed by a CUDA event pair on the launching stream.
  * msnap_profile_end synchronises and writes a JSON object {"<kernel>": {"launches": n, "total_ms": t}, ...}. */

@@ -1,0 +1,149 @@
+"""GPU parity tests of the batched altitude optimisation through the C ABI
+(msnap_altitude_optimize_batch_* / msnap_cost_map_lookup_dev in include/msnap.h) against oracle/alt_oracle.py.
+
+Bars: optimised heights within 1e-6 m (the north star's position bar) of the port; identical discrete decisions: the
+number of solves the active-set loop takes, and -- through the heights -- which rows it pinned.  The port is itself
+within 1e-6 m of a 50-digit solve of the same systems (tests/test_alt_oracle.py); the reference's own solver
+(Eigen::SimplicialLDLT) is not available in this image, so parity with the reference's bits is unpinned (DESIGN.md
+section 10)."""
+import numpy as np
+import pytest
+import torch
+
+from alt_helpers import lookup, sampled_paths, terrain_grid
+from cs_pathplan_b200 import AltitudeParams, shipped_altitude_params, workloads
+from cs_pathplan_b200._lib import MsnapError
+from oracle import alt_oracle as ao
+from oracle import geo
+
+pytestmark = pytest.mark.gpu
+Z_TOL = 1e-6
+
+
+def oracle_params(p):
+    return ao.AltitudeParams(p.lambda_smooth, p.lambda_follow, p.max_climb_rate, p.uav_R, p.safe_distance)
+
+
+@pytest.mark.parametrize("params", [shipped_altitude_params(), AltitudeParams(),
+                                    AltitudeParams(lambda_smooth=0.0, lambda_follow=2.0, max_climb_rate=0.5, safe_distance=30.0),
+                                    AltitudeParams(lambda_smooth=3.0, lambda_follow=0.5, max_climb_rate=0.0, safe_distance=5.0)],
+                         ids=["shipped", "struct_defaults", "no_smoothing", "no_climb_term"])
+def test_ragged_batch_against_the_port(tool, params):
+    grid, res, ox, oy = terrain_grid()
+    rows, off = sampled_paths(48, seed=21)
+    elev = lookup(grid, res, ox, oy, rows)
+    assert np.isnan(elev).any() and (~np.isnan(elev)).any()          # some rows lie outside the map
+    out, z1, solves, flags = tool.altitude_optimize_batch(rows, off, params, elev, return_info=True)
+    assert not flags.any()
+    assert np.array_equal(out[:, :2], rows[:, :2])                   # only the up column changes (cpp:1357-1359)
+    po = oracle_params(params)
+    for b in range(off.shape[0] - 1):
+        sl = slice(int(off[b]), int(off[b + 1]))
+        z2_o, z1_o, solves_o, _ = ao.optimize_segment_altitude_enu(rows[sl], po, elev[sl], return_info=True)
+        assert np.abs(z1[sl] - z1_o).max() <= Z_TOL, b
+        assert solves[b] == solves_o, b
+        assert np.abs(out[sl, 2] - z2_o).max() <= Z_TOL, b
+
+
+def test_reference_shaped_single_call_and_edge_cases(tool):
+    p = shipped_altitude_params()
+    seg = np.column_stack([np.arange(50) * 30.0, np.zeros(50), np.full(50, 1000.0)])
+    elev = 980.0 + 25.0 * np.sin(np.arange(50) / 5.0)
+    out = tool.optimizeSegmentAltitudeENU(seg, p, elev)
+    exp = ao.optimize_segment_altitude_enu(seg, oracle_params(p), elev)
+    assert np.abs(out[:, 2] - exp).max() <= Z_TOL and np.all(out[:, 2] >= elev + p.safe_distance - 1e-9)
+    # no terrain at all: elev = None and elev = NaN are the same thing
+    a = tool.optimizeSegmentAltitudeENU(seg, p, None)
+    b = tool.optimizeSegmentAltitudeENU(seg, p, np.full(50, np.nan))
+    assert np.array_equal(a, b)
+    assert np.abs(a[:, 2] - ao.optimize_segment_altitude_enu(seg, oracle_params(p), np.full(50, np.nan))).max() <= Z_TOL
+    # n = 1, 2, 3 and an empty trajectory inside a batch
+    rows = np.column_stack([np.arange(6) * 40.0, np.zeros(6), np.full(6, 1000.0)])
+    off = np.array([0, 1, 1, 3, 6], dtype=np.int64)
+    el = np.full(6, 995.0)
+    out, z1, solves, flags = tool.altitude_optimize_batch(rows, off, p, el, return_info=True)
+    assert solves[1] == 0 and not flags.any()
+    for b in (0, 2, 3):
+        sl = slice(int(off[b]), int(off[b + 1]))
+        assert np.abs(out[sl, 2] - ao.optimize_segment_altitude_enu(rows[sl], oracle_params(p), el[sl])).max() <= Z_TOL
+    # empty batch, malformed offsets
+    assert tool.altitude_optimize_batch(np.zeros((0, 3)), np.array([0]), p).shape == (0, 3)
+    with pytest.raises(ValueError):
+        tool.altitude_optimize_batch(rows, np.array([0, 5]), p)
+    with pytest.raises(MsnapError):
+        tool.altitude_optimize_batch(rows, np.array([0, 4, 2, 6]), p)
+
+
+def test_batch_equals_singles_bitwise(tool):
+    grid, res, ox, oy = terrain_grid()
+    rows, off = sampled_paths(40, seed=5)
+    elev = lookup(grid, res, ox, oy, rows)
+    p = shipped_altitude_params()
+    out = tool.altitude_optimize_batch(rows, off, p, elev)
+    for b in (0, 3, 7, 39):
+        sl = slice(int(off[b]), int(off[b + 1]))
+        assert np.array_equal(tool.optimizeSegmentAltitudeENU(rows[sl], p, elev[sl]), out[sl])
+
+
+def test_device_chain_sampler_lookup_altitude_wgs84(tool):
+    """getPlan's leader chain after Minisnap_3D on the device (cpp:3684 -> 3712-3729 -> 1535-1573): sampled ENU rows ->
+    cost-map lookup -> optimizeSegmentAltitudeENU -> enuToWGS84_Batch, against the oracles run step by step on the host."""
+    grid, res, ox, oy = terrain_grid(width=900, height=900, resolution=10.0, origin_x=-4500.0, origin_y=4500.0)
+    B, ns = 64, 16
+    wp, _ = workloads.cfg2(B=B, ns=ns)
+    wp = wp * np.array([8.0, 8.0, 1.0]) + np.array([0.0, 0.0, 1250.0])
+    cfg = workloads.synthetic_config(4, "shipped", sample_distance=20.0)
+    cfg.V_avg = 40.0
+    res_enu = tool.generate_batch(cfg, wp, ns=ns)
+    n = res_enu.samples.shape[0]
+    dev = torch.device("cuda")
+    d_rows = torch.from_numpy(res_enu.samples).to(dev)
+    d_off = torch.from_numpy(res_enu.sample_offset).to(dev)
+    d_grid = torch.from_numpy(grid).to(dev)
+    d_elev = torch.empty(n, dtype=torch.float64, device=dev)
+    d_solves = torch.zeros(B, dtype=torch.int32, device=dev)
+    p = shipped_altitude_params()
+    tool.cost_map_lookup_dev(d_grid, res, ox, oy, d_rows, d_elev, n_rows=d_off[B:])
+    tool.altitude_optimize_batch_dev(p, d_off, d_rows, d_elev, solves=d_solves)
+    d_lla = torch.empty_like(d_rows)
+    tool.enu_to_wgs84_dev(geo.README_ORIGIN, d_rows, d_lla)
+    tool.synchronize()
+    elev_o = lookup(grid, res, ox, oy, res_enu.samples)
+    got_elev = d_elev.cpu().numpy()
+    assert np.array_equal(np.isnan(got_elev), np.isnan(elev_o)) and np.array_equal(got_elev[~np.isnan(elev_o)], elev_o[~np.isnan(elev_o)])
+    rows_o = res_enu.samples.copy()
+    for b in range(B):
+        sl = slice(int(res_enu.sample_offset[b]), int(res_enu.sample_offset[b + 1]))
+        z2, _, solves_o, _ = ao.optimize_segment_altitude_enu(res_enu.samples[sl], oracle_params(p), elev_o[sl], return_info=True)
+        rows_o[sl, 2] = z2
+        assert int(d_solves[b]) == solves_o
+    assert np.abs(d_rows.cpu().numpy() - rows_o).max() <= Z_TOL
+    lla_o = geo.enu_to_wgs84_batch(rows_o, geo.README_ORIGIN)
+    d = np.abs(d_lla.cpu().numpy() - lla_o)
+    assert d[:, :2].max() <= 1e-11 and d[:, 2].max() <= 2e-6
+    # host path == device path, bitwise
+    host = tool.altitude_optimize_batch(res_enu.samples, res_enu.sample_offset, p, elev_o)
+    assert np.array_equal(host, d_rows.cpu().numpy())
+
+
+def test_full_size_properties(tool):
+    """cfg2-sized sampler output (4 096 trajectories, ~0.8 M rows): clearance, monotonicity and fixed end points."""
+    rng = np.random.default_rng(4)
+    B = 4096
+    ns = rng.integers(150, 260, B)
+    off = np.concatenate([[0], np.cumsum(ns)]).astype(np.int64)
+    n = int(off[-1])
+    t = np.arange(n) - np.repeat(off[:-1], ns)
+    rows = np.column_stack([t * 25.0, np.repeat(rng.uniform(-1e3, 1e3, B), ns), 1300.0 + 40.0 * np.sin(t / 9.0)])
+    elev = 1250.0 + 80.0 * np.sin(rows[:, 0] / 400.0 + np.repeat(rng.uniform(0, 6, B), ns))
+    p = shipped_altitude_params()
+    out, z1, solves, flags = tool.altitude_optimize_batch(rows, off, p, elev, return_info=True)
+    assert not flags.any() and solves.min() >= 1 and solves.max() <= 10
+    assert np.all(z1 >= elev + p.safe_distance - 1e-9)
+    assert np.all(out[:, 2] >= z1)
+    first, last = off[:-1], off[1:] - 1
+    assert np.abs(out[first, 2] - z1[first]).max() <= 1e-6 and np.abs(out[last, 2] - z1[last]).max() <= 1e-6
+    for b in (0, 1234, 4095):
+        sl = slice(int(off[b]), int(off[b + 1]))
+        z2 = ao.optimize_segment_altitude_enu(rows[sl], oracle_params(p), elev[sl])
+        assert np.abs(out[sl, 2] - z2).max() <= Z_TOL

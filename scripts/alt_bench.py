@@ -1,0 +1,133 @@
+#!/usr/bin/env python3
+"""Time the batched altitude optimisation (k_alt_prep + k_alt_solve; device-resident rows, per-kernel CUDA events on the
+launching stream through msnap_profile_begin/end) on a cfg2-sized sampler output, and beside it a banded-Cholesky CPU
+stand-in for the reference's per-trajectory SimplicialLDLT loop.  One JSON line.
+
+    python scripts/alt_bench.py [--B 4096] [--iters 20] [--cpu-traj 256]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from cs_pathplan_b200 import TrajectoryGeneratorTool, shipped_altitude_params  # noqa: E402
+
+
+def workload(B, seed=4):
+    rng = np.random.default_rng(seed)
+    ns = rng.integers(150, 260, B)
+    off = np.concatenate([[0], np.cumsum(ns)]).astype(np.int64)
+    n = int(off[-1])
+    t = np.arange(n) - np.repeat(off[:-1], ns)
+    rows = np.column_stack([t * 25.0, np.repeat(rng.uniform(-1e3, 1e3, B), ns), 1300.0 + 40.0 * np.sin(t / 9.0)])
+    elev = 1250.0 + 80.0 * np.sin(rows[:, 0] / 400.0 + np.repeat(rng.uniform(0, 6, B), ns))
+    return rows, off, elev
+
+
+def cpu_banded(rows, off, elev, p, n_traj, check=None):
+    """The same two passes per trajectory with LAPACK's banded Cholesky (scipy solveh_banded): an O(n) CPU stand-in for
+    the reference's Eigen::SimplicialLDLT loop (cpp:1575-1827).  Returns seconds for n_traj trajectories."""
+    from scipy.linalg import solveh_banded
+
+    def band(n, s, w, extra):
+        ab = np.zeros((3, n))                      # lower form: ab[0] diagonal, ab[1] first, ab[2] second sub-diagonal
+        if n >= 3 and s > 0:
+            inner = np.zeros(n + 2)                # inner[i + 1] = 1 if row i is an interior row
+            inner[2:n] = 1.0
+            ab[0] += s * (inner[2:] + 4.0 * inner[1:-1] + inner[:-2])
+            ab[1, :n - 1] += s * -2.0 * (inner[1:n] + inner[2:n + 1])
+            ab[2, :n - 2] += s * inner[2:n]
+        ab[0, :n - 1] += w
+        ab[0, 1:] += w
+        ab[1, :n - 1] -= w
+        ab[0] += extra + 1e-8
+        return ab
+
+    t0 = time.perf_counter()
+    for b in range(n_traj):
+        sl = slice(int(off[b]), int(off[b + 1]))
+        r, el = rows[sl], elev[sl]
+        n = r.shape[0]
+        dist = np.hypot(np.diff(r[:, 0]), np.diff(r[:, 1]))
+        w1 = np.where(dist > 1e-9, 1.0 / np.maximum(dist * p.max_climb_rate, 1e-300) ** 2, 0.0)
+        w2 = np.where(dist > 1e-9, 1.0 / np.maximum(dist * p.max_climb_rate * 0.5, 1e-300) ** 2, 0.0)
+        tgt = np.maximum(r[:, 2], el + p.safe_distance)
+        z1 = solveh_banded(band(n, p.lambda_smooth, w1, np.full(n, p.lambda_follow)), p.lambda_follow * tgt, lower=True)
+        z1 = np.maximum(z1, el + p.safe_distance)
+        act = np.zeros(n, dtype=bool)
+        for _ in range(10):
+            extra = np.where(act, 1e8, 0.0)
+            extra[0] = extra[-1] = 1e10            # end rows: fixed, never "active" (cpp:1779-1790)
+            rhs = extra * z1
+            z = solveh_banded(band(n, p.lambda_smooth * 10.0, w2, extra), rhs, lower=True)
+            new = (z < z1 - 1e-3) & ~act
+            act |= new
+            if not new.any():
+                break
+        if check is not None:
+            check.append(np.maximum(z, z1))
+    return time.perf_counter() - t0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--B", type=int, default=4096)
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--cpu-traj", type=int, default=256)
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    rows, off, elev = workload(a.B)
+    n = rows.shape[0]
+    p = shipped_altitude_params()
+    dev = torch.device("cuda")
+    d_rows0 = torch.from_numpy(rows).to(dev)
+    d_rows = d_rows0.clone()
+    d_off = torch.from_numpy(off).to(dev)
+    d_elev = torch.from_numpy(elev).to(dev)
+    d_solves = torch.zeros(a.B, dtype=torch.int32, device=dev)
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        hbm_peak = 6553.3
+    with TrajectoryGeneratorTool(0) as tool:
+        stream = torch.cuda.Stream()
+        tool.set_stream(stream.cuda_stream)
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                d_rows.copy_(d_rows0)
+                tool.altitude_optimize_batch_dev(p, d_off, d_rows, d_elev, solves=d_solves)
+            stream.synchronize()
+            tool.profile_begin()
+            for _ in range(a.iters):
+                d_rows.copy_(d_rows0)
+                tool.altitude_optimize_batch_dev(p, d_off, d_rows, d_elev, solves=d_solves)
+            prof = tool.profile_end()
+        tool.set_stream(None)
+    ms = {k: v["total_ms"] / a.iters for k, v in prof.items()}
+    total = sum(ms.values())
+    solves = d_solves.cpu().numpy()
+    out = {"workload": f"{a.B} sampled trajectories, 150-259 rows each ({n} rows), shipped altitude parameters "
+                       f"(config.yaml:1-8), analytic terrain", "kernels_ms": ms, "ms_per_batch": total,
+           "trajectories_per_s": a.B / (total * 1e-3), "rows_per_s": n / (total * 1e-3),
+           "mean_pass2_solves": float(solves.mean()), "max_pass2_solves": int(solves.max()),
+           "algorithmic_bytes_per_row": 40, "achieved_GBps": 40.0 * n / (total * 1e-3) / 1e9,
+           "hbm_frac": 40.0 * n / (total * 1e-3) / 1e9 / hbm_peak,
+           "bound": "latency: one dependent chain of n rows per solve and trajectory, (1 + solves) chains per trajectory"}
+    if not a.no_cpu:
+        from oracle import alt_oracle as ao
+
+        m = min(a.cpu_traj, a.B)
+        dt = cpu_banded(rows, off, elev, ao.shipped_params(), m)
+        out["cpu_banded_cholesky_trajectories_per_s_1thread"] = m / dt
+        out["cpu_sample"] = f"first {m} trajectories, scipy.linalg.solveh_banded (LAPACK dpbsv) per solve, one thread"
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

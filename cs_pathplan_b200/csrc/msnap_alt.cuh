@@ -22,9 +22,12 @@
 // Work decomposition: k_alt_prep is row-parallel (edge weights of both passes and the follow target: hypot, two divisions
 // per row, off the recurrences); k_alt_solve runs one trajectory per lane through pass 1 and the whole active-set loop --
 // a dependent chain of n steps per solve (one reciprocal and ~14 multiply-adds per row forward, 2 per row backward), so
-// the kernel is latency-bound and is launched with one warp per CTA to spread the chains over all SMs.
+// the kernel is latency-bound and is launched with one warp per CTA to spread the chains over all SMs; k_alt_finish
+// (row-parallel) writes the heights back into the rows.
 #ifndef MSNAP_ALT_CUH
 #define MSNAP_ALT_CUH
+
+#include <cuda_pipeline.h>
 
 #include <cmath>
 
@@ -63,7 +66,8 @@ __global__ void __launch_bounds__(256) k_cost_lookup(const float *__restrict__ g
 // trajectory and for skipped edges), tgt = follow target of pass 1 (NaN where the map has no value).
 __global__ void __launch_bounds__(256) k_alt_prep(AltParams p, long long B, const long long *__restrict__ row_offset,
                                                   const double *__restrict__ rows, const double *__restrict__ elev,
-                                                  double *__restrict__ w1, double *__restrict__ w2, double *__restrict__ tgt) {
+                                                  double *__restrict__ w1, double *__restrict__ w2, double *__restrict__ tgt,
+                                                  double *__restrict__ act) {
     const long long n = row_offset[B];
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += (long long)gridDim.x * blockDim.x) {
         long long lo = 0, hi = B;  // trajectory of row g: largest b with row_offset[b] <= g
@@ -84,6 +88,7 @@ __global__ void __launch_bounds__(256) k_alt_prep(AltParams p, long long B, cons
         }
         w1[g] = a1;
         w2[g] = a2;
+        act[g] = 0.0;
         const double el = elev ? elev[g] : NAN;
         tgt[g] = el == el ? fmax(rows[3 * g + 2], el + p.safe_distance) : NAN;  // cpp:1637-1638
     }
@@ -98,121 +103,220 @@ __device__ __forceinline__ double alt_rcp(double x) {  // 1/x for a positive nor
     return fma(r, e, r);
 }
 
-// One banded LDL' solve of a trajectory (n rows starting at `base`).  diag_extra(k) / rhs(k) supply what the two passes
-// add to the shared smoothing + climb + regularisation part.  Leaves z in `out` and returns false on a bad pivot.
-template <class Extra, class Rhs, class Sink>
-__device__ __forceinline__ bool alt_solve(long long base, long long n, double s, const double *__restrict__ w,
-                                          double *__restrict__ l1, double *__restrict__ l2, double *__restrict__ yd,
-                                          Extra diag_extra, Rhs rhs, Sink sink) {
-    const bool smooth = n >= 3 && s > 0.0;
-    double a1 = 0.0, a2 = 0.0, c = 0.0, Dm1 = 0.0, Dm2 = 0.0, ym1 = 0.0, ym2 = 0.0, wm1 = 0.0;
-    bool ok = true;
-    for (long long k = 0; k < n; ++k) {
-        const double wk = w[base + k];
-        const int in_m = smooth && k - 1 >= 1 && k - 1 <= n - 2, in_0 = smooth && k >= 1 && k <= n - 2,
-                  in_p = smooth && k + 1 >= 1 && k + 1 <= n - 2;
-        const double d = s * (double)(in_p + 4 * in_0 + in_m) + (wm1 + wk) + diag_extra(k) + ALT_REG;
-        const double e = k + 1 < n ? s * (double)(-2 * (in_0 + in_p)) - wk : 0.0;  // H[k, k+1]
-        const double f = k + 2 < n ? s * (double)in_p : 0.0;                       // H[k, k+2]
-        const double D = fma(-a2 * a2, Dm2, fma(-a1 * a1, Dm1, d));
-        const double y = fma(-a2, ym2, fma(-a1, ym1, rhs(k)));
-        ok = ok && D > 0.0 && D < 1e300;
-        const double inv = alt_rcp(D);
-        const double n1 = fma(-c * Dm1, a1, e) * inv;  // L[k+1, k]
-        const double n2 = f * inv;                     // L[k+2, k]
-        l1[base + k] = a1;
-        l2[base + k] = a2;
-        yd[base + k] = y * inv;
-        a2 = c;
-        a1 = n1;
-        c = n2;
-        Dm2 = Dm1;
-        Dm1 = D;
-        ym2 = ym1;
-        ym1 = y;
-        wm1 = wk;
+// ---- k_alt_solve: one trajectory per lane, 32 trajectories per warp, one warp per CTA -------------------------------
+// All lanes of a warp advance through their chains in lock step, so row k of 32 different trajectories is needed at the
+// same time: 32 addresses n rows apart.  The warp therefore moves its data in CHUNKS of 32 rows: for every trajectory of
+// the warp the 32 rows of a chunk are 256 contiguous bytes, fetched by one coalesced warp-wide cp.async into a shared
+// memory tile [field][trajectory][row] (padded pitch) and written back the same way.  Tiles are double buffered: the
+// copies of the next chunk are issued before the current chunk's 32 recurrence steps and waited for after them, so the
+// chains never wait on memory, and every global access is a full 256-byte line.
+constexpr int ALT_CHUNK = 32;
+constexpr int ALT_PITCH = ALT_CHUNK + 1;  // bank-conflict-free: lane t reads word t * 33 + j
+constexpr int ALT_TILES = 5;              // fields a sweep stages at most (backward sweep of pass 2)
+constexpr int ALT_TILE_WORDS = 32 * ALT_PITCH;
+constexpr size_t ALT_SMEM_BYTES = 2 * ALT_TILES * ALT_TILE_WORDS * sizeof(double);
+
+// One sweep over the chunks of the warp's 32 trajectories, ascending (forward elimination) or descending (back
+// substitution).  in[f] -> tile f; `row(k, j, T)` performs row k of this lane's trajectory on T(f, j) = tile f, this lane,
+// row j of the chunk, and leaves its results in tiles; out[o] is then stored from tile o.  Lanes with active == false
+// neither compute nor store (their trajectory has converged), lanes beyond their own length neither.
+template <int NIN, int NOUT, bool DESC, class Row>
+__device__ __forceinline__ void alt_sweep(double *sm, const double *const (&in)[NIN], double *const (&out)[NOUT], long long base,
+                                          int n, int nmax, bool active, int lane, Row row) {
+    if (nmax <= 0) return;
+    const int n_chunks = (nmax + ALT_CHUNK - 1) / ALT_CHUNK;
+    auto chunk_k0 = [&](int c) { return (long long)(DESC ? n_chunks - 1 - c : c) * ALT_CHUNK; };
+    auto issue = [&](int c, int buf) {
+        const long long k = chunk_k0(c) + lane;
+        double *tiles = sm + (size_t)buf * ALT_TILES * ALT_TILE_WORDS;
+#pragma unroll 4
+        for (int q = 0; q < 32; ++q) {
+            const long long bq = __shfl_sync(0xffffffffu, base, q);
+            const int nq = __shfl_sync(0xffffffffu, n, q);
+            if (k < nq) {
+#pragma unroll
+                for (int f = 0; f < NIN; ++f)
+                    __pipeline_memcpy_async(tiles + f * ALT_TILE_WORDS + q * ALT_PITCH + lane, in[f] + bq + k, sizeof(double));
+            }
+        }
+        __pipeline_commit();
+    };
+    issue(0, 0);
+    for (int c = 0; c < n_chunks; ++c) {
+        const int buf = c & 1;
+        const bool more = c + 1 < n_chunks;
+        if (more) issue(c + 1, buf ^ 1);
+        if (more) __pipeline_wait_prior(1);
+        else __pipeline_wait_prior(0);
+        __syncwarp();
+        double *tiles = sm + (size_t)buf * ALT_TILES * ALT_TILE_WORDS;
+        const long long k0 = chunk_k0(c);
+        if (active) {
+            auto T = [&](int f, int j) -> double & { return tiles[f * ALT_TILE_WORDS + lane * ALT_PITCH + j]; };
+            if (DESC) {
+                for (int j = ALT_CHUNK - 1; j >= 0; --j)
+                    if (k0 + j < n) row(k0 + j, j, T);
+            } else {
+                for (int j = 0; j < ALT_CHUNK; ++j)
+                    if (k0 + j < n) row(k0 + j, j, T);
+            }
+        }
+        __syncwarp();
+        const long long k = k0 + lane;
+#pragma unroll 4
+        for (int q = 0; q < 32; ++q) {
+            const long long bq = __shfl_sync(0xffffffffu, base, q);
+            const int nq = __shfl_sync(0xffffffffu, n, q);
+            const bool aq = __shfl_sync(0xffffffffu, active, q);
+            if (aq && k < nq) {
+#pragma unroll
+                for (int o = 0; o < NOUT; ++o)
+                    if (out[o]) out[o][bq + k] = tiles[o * ALT_TILE_WORDS + q * ALT_PITCH + lane];
+            }
+        }
+        __syncwarp();  // the tiles of `buf` are free again for the copies issued in the next trip
     }
-    double z1 = 0.0, z2 = 0.0, b1 = 0.0, b2 = 0.0, b2n = 0.0;  // z_{k+1}, z_{k+2}; L[k+1,k], L[k+2,k]
-    for (long long k = n - 1; k >= 0; --k) {
-        const double z = fma(-b2, z2, fma(-b1, z1, yd[base + k]));
-        sink(k, z);
-        z2 = z1;
-        z1 = z;
-        b2 = b2n;              // L[(k-1)+2, k-1] = l2[k+1]
-        b2n = l2[base + k];    // becomes L[k, k-2], used two rows further down
-        b1 = l1[base + k];     // L[k, k-1], used by row k-1
-    }
-    return ok;
 }
 
-// One trajectory per lane: optimizeSegmentAltitudeENU (cpp:1329-1364).  The new heights replace the `up` column of rows.
+struct AltFwd {  // state a lane carries from row to row of the forward sweep
+    double a1 = 0.0, a2 = 0.0, c = 0.0, Dm1 = 0.0, Dm2 = 0.0, ym1 = 0.0, ym2 = 0.0, wm1 = 0.0;
+    bool ok = true;
+};
+struct AltBwd {  // ... and of the backward sweep: z_{k+1}, z_{k+2}, L[k+1,k], L[k+2,k], L[k+1,k-1]
+    double z1 = 0.0, z2 = 0.0, b1 = 0.0, b2 = 0.0, b2n = 0.0;
+};
+
+// Row k of the banded LDL' factorisation fused with the forward substitution.  wk = climb weight of edge (k, k+1),
+// extra / rhs = what the pass adds to the diagonal / right-hand side.  Returns (L[k,k-1], L[k,k-2], y_k / D_k).
+__device__ __forceinline__ void alt_fwd_row(AltFwd &f, long long k, long long n, double s, bool smooth, double wk, double extra,
+                                            double rhs, double &o_l1, double &o_l2, double &o_yd) {
+    const int in_m = smooth && k - 1 >= 1 && k - 1 <= n - 2, in_0 = smooth && k >= 1 && k <= n - 2,
+              in_p = smooth && k + 1 >= 1 && k + 1 <= n - 2;
+    const double d = s * (double)(in_p + 4 * in_0 + in_m) + (f.wm1 + wk) + extra + ALT_REG;
+    const double e = k + 1 < n ? s * (double)(-2 * (in_0 + in_p)) - wk : 0.0;  // H[k, k+1]
+    const double h = k + 2 < n ? s * (double)in_p : 0.0;                       // H[k, k+2]
+    const double D = fma(-f.a2 * f.a2, f.Dm2, fma(-f.a1 * f.a1, f.Dm1, d));
+    const double y = fma(-f.a2, f.ym2, fma(-f.a1, f.ym1, rhs));
+    f.ok = f.ok && D > 0.0 && D < 1e300;
+    const double inv = alt_rcp(D);
+    const double n1 = fma(-f.c * f.Dm1, f.a1, e) * inv;  // L[k+1, k]
+    const double n2 = h * inv;                           // L[k+2, k]
+    o_l1 = f.a1;
+    o_l2 = f.a2;
+    o_yd = y * inv;
+    f.a2 = f.c;
+    f.a1 = n1;
+    f.c = n2;
+    f.Dm2 = f.Dm1;
+    f.Dm1 = D;
+    f.ym2 = f.ym1;
+    f.ym1 = y;
+    f.wm1 = wk;
+}
+// Row k of the backward substitution: z_k = y_k/D_k - L[k+1,k] z_{k+1} - L[k+2,k] z_{k+2}.
+__device__ __forceinline__ double alt_bwd_row(AltBwd &r, double l1k, double l2k, double ydk) {
+    const double z = fma(-r.b2, r.z2, fma(-r.b1, r.z1, ydk));
+    r.z2 = r.z1;
+    r.z1 = z;
+    r.b2 = r.b2n;  // L[k+1, k-1] = l2[k+1]
+    r.b2n = l2k;   // L[k, k-2], needed two rows further down
+    r.b1 = l1k;    // L[k, k-1], needed by row k-1
+    return z;
+}
+
+// optimizeSegmentAltitudeENU (cpp:1329-1364) for 32 trajectories per warp.  The heights of both passes stay in the
+// scratch arrays zin (pass 1, clamped) and cur (last solve of pass 2); k_alt_finish writes max(cur, zin) back to the rows.
 __global__ void __launch_bounds__(32) k_alt_solve(AltParams p, long long B, const long long *__restrict__ row_offset,
-                                                  double *rows, const double *__restrict__ elev,
-                                                  const double *__restrict__ w1, const double *__restrict__ w2,
-                                                  const double *__restrict__ tgt, double *__restrict__ l1,
-                                                  double *__restrict__ l2, double *__restrict__ yd, double *__restrict__ zin,
-                                                  double *__restrict__ cur, unsigned char *__restrict__ act,
-                                                  double *__restrict__ z_pass1_out, int *__restrict__ solves_out,
+                                                  const double *elev, const double *w1, const double *w2, const double *tgt,
+                                                  double *l1, double *l2, double *yd, double *zin, double *cur, double *act,
+                                                  double *z_pass1_out, int *__restrict__ solves_out,
                                                   unsigned *__restrict__ flags_out) {
-    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    const long long base = row_offset[b], n = row_offset[b + 1] - base;
-    if (n <= 0) {
-        if (solves_out) solves_out[b] = 0;
-        if (flags_out) flags_out[b] = 0;
-        return;
-    }
-    // ---- pass 1: optimizeHeights
-    bool ok = alt_solve(
-        base, n, p.lambda_smooth, w1, l1, l2, yd,
-        [&](long long k) { const double t = tgt[base + k]; return t == t ? p.lambda_follow : 0.0; },
-        [&](long long k) { const double t = tgt[base + k]; return t == t ? p.lambda_follow * t : 0.0; },
-        [&](long long k, double z) {
-            const double el = elev ? elev[base + k] : NAN;
-            if (el == el && z < el + p.safe_distance) z = el + p.safe_distance;  // cpp:1705-1707
-            zin[base + k] = z;
-            act[base + k] = 0;
-            if (z_pass1_out) z_pass1_out[base + k] = z;
+    extern __shared__ double alt_sm[];
+    const int lane = threadIdx.x;
+    const long long b = (long long)blockIdx.x * 32 + lane;
+    const long long base = b < B ? row_offset[b] : 0;
+    const int n = b < B ? (int)(row_offset[b + 1] - base) : 0;
+    const int nmax = __reduce_max_sync(0xffffffffu, n);
+    bool ok = true;
+
+    // ---- pass 1: optimizeHeights (cpp:1575-1712)
+    {
+        const double s = p.lambda_smooth, lf = p.lambda_follow, safe = p.safe_distance;
+        const bool smooth = n >= 3 && s > 0.0;
+        AltFwd f;
+        const double *const in_f[2] = {w1, tgt};
+        double *const out_f[3] = {l1, l2, yd};
+        alt_sweep<2, 3, false>(alt_sm, in_f, out_f, base, n, nmax, n > 0, lane, [&](long long k, int j, auto &T) {
+            const double wk = T(0, j), t = T(1, j);
+            const bool has = t == t;
+            alt_fwd_row(f, k, n, s, smooth, wk, has ? lf : 0.0, has ? lf * t : 0.0, T(0, j), T(1, j), T(2, j));
         });
-    // ---- pass 2: optimizeHeightsGlobalSmooth with lambda_smooth * 10, max_climb_rate * 0.5 (cpp:1352-1355)
+        ok = f.ok;
+        AltBwd r;
+        const bool have_elev = elev != nullptr;
+        const double *const in_b[4] = {l1, l2, yd, have_elev ? elev : yd};
+        double *const out_b[2] = {zin, z_pass1_out};
+        alt_sweep<4, 2, true>(alt_sm, in_b, out_b, base, n, nmax, n > 0, lane, [&](long long, int j, auto &T) {
+            double z = alt_bwd_row(r, T(0, j), T(1, j), T(2, j));
+            const double el = have_elev ? T(3, j) : NAN;
+            if (el == el && z < el + safe) z = el + safe;  // cpp:1705-1707
+            T(0, j) = z;
+            T(1, j) = z;
+        });
+    }
+    // ---- pass 2: optimizeHeightsGlobalSmooth with lambda_smooth * 10, max_climb_rate * 0.5 (cpp:1352-1355, 1714-1827)
     const double s2 = p.lambda_smooth * 10.0;
+    const bool smooth2 = n >= 3 && s2 > 0.0;
     int solves = 0;
+    bool running = n > 0;  // this lane's trajectory still iterates
     for (int iter = 0; iter < ALT_MAX_ITER; ++iter) {
+        if (!__any_sync(0xffffffffu, running)) break;
+        AltFwd f;
+        const double *const in_f[3] = {w2, zin, act};
+        double *const out_f[3] = {l1, l2, yd};
+        alt_sweep<3, 3, false>(alt_sm, in_f, out_f, base, n, nmax, running, lane, [&](long long k, int j, auto &T) {
+            const double wk = T(0, j), zi = T(1, j);
+            double x = 0.0;
+            if (k == 0) x += ALT_FIX_WEIGHT;                                // cpp:1779-1784
+            if (k == n - 1) x += ALT_FIX_WEIGHT;
+            if (k >= 1 && k < n - 1 && T(2, j) != 0.0) x += ALT_CON_WEIGHT;  // cpp:1787-1793
+            alt_fwd_row(f, k, n, s2, smooth2, wk, x, x * zi, T(0, j), T(1, j), T(2, j));
+        });
+        if (running) ok = ok && f.ok;
+        AltBwd r;
         bool violation = false;
-        ok = alt_solve(
-                 base, n, s2, w2, l1, l2, yd,
-                 [&](long long k) {
-                     double x = 0.0;
-                     if (k == 0) x += ALT_FIX_WEIGHT;
-                     if (k == n - 1) x += ALT_FIX_WEIGHT;
-                     if (k >= 1 && k < n - 1 && act[base + k]) x += ALT_CON_WEIGHT;
-                     return x;
-                 },
-                 [&](long long k) {
-                     const double zi = zin[base + k];
-                     double x = 0.0;
-                     if (k == 0) x += ALT_FIX_WEIGHT * zi;
-                     if (k == n - 1) x += ALT_FIX_WEIGHT * zi;
-                     if (k >= 1 && k < n - 1 && act[base + k]) x += ALT_CON_WEIGHT * zi;
-                     return x;
-                 },
-                 [&](long long k, double z) {
-                     cur[base + k] = z;
-                     if (z < zin[base + k] - ALT_VIOLATION && !act[base + k]) {  // cpp:1805-1810
-                         act[base + k] = 1;
-                         violation = true;
-                     }
-                 }) &&
-             ok;
-        ++solves;
-        if (!violation) break;
+        const double *const in_b[5] = {l1, l2, yd, zin, act};
+        double *const out_b[2] = {cur, act};
+        alt_sweep<5, 2, true>(alt_sm, in_b, out_b, base, n, nmax, running, lane, [&](long long, int j, auto &T) {
+            const double z = alt_bwd_row(r, T(0, j), T(1, j), T(2, j));
+            double a = T(4, j);
+            if (z < T(3, j) - ALT_VIOLATION && a == 0.0) {  // cpp:1805-1810
+                a = 1.0;
+                violation = true;
+            }
+            T(0, j) = z;
+            T(1, j) = a;
+        });
+        if (running) {
+            ++solves;
+            if (!violation) running = false;  // converged (cpp:1814)
+        }
     }
-    for (long long k = 0; k < n; ++k) {  // cpp:1817-1821, written back as segment_enu[i].up (cpp:1357-1359)
-        const double z = cur[base + k], zi = zin[base + k];
-        rows[3 * (base + k) + 2] = z < zi ? zi : z;
+    if (b < B) {
+        if (solves_out) solves_out[b] = solves;
+        if (flags_out) flags_out[b] = ok ? 0u : ALT_FLAG_PIVOT;
     }
-    if (solves_out) solves_out[b] = solves;
-    if (flags_out) flags_out[b] = ok ? 0u : ALT_FLAG_PIVOT;
+}
+
+// cpp:1817-1821 and the write-back of cpp:1357-1359: up_i = max(z_i, z1_i), row-parallel.
+__global__ void __launch_bounds__(256) k_alt_finish(long long B, const long long *__restrict__ row_offset,
+                                                    const double *__restrict__ cur, const double *__restrict__ zin,
+                                                    double *__restrict__ rows) {
+    const long long n = row_offset[B];
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += (long long)gridDim.x * blockDim.x) {
+        const double z = cur[g], zi = zin[g];
+        rows[3 * g + 2] = z < zi ? zi : z;
+    }
 }
 
 }  // namespace msnap

@@ -80,6 +80,7 @@ struct msnap_context {
     GeoFrame geo{};
     int wp_frame = 0;       // msnap_set_waypoint_frame: 1 = generate / sample_bound take WGS84 waypoints (cpp:2640)
     GeoFrame wp_geo{};
+    bool alt_smem_opted = false;
     bool geo_trig = false;  // msnap_set_geo_exact_trig: ENU -> WGS84 with the reference's per-step sin/cos/atan2
 };
 
@@ -1368,18 +1369,27 @@ int msnap_altitude_optimize_batch_dev(msnap_handle h, const msnap_altitude_param
     if (B == 0 || n_rows_cap == 0) return MSNAP_OK;
     DeviceGuard guard(h->device);
     const size_t n = (size_t)n_rows_cap;
-    int rc = arena_reserve(h, h->ws, 8 * padded(n * sizeof(double)) + padded(n));
+    int rc = arena_reserve(h, h->ws, 9 * padded(n * sizeof(double)));
     if (rc) return rc;
     double *w1 = arena_take<double>(h->ws, n), *w2 = arena_take<double>(h->ws, n), *tgt = arena_take<double>(h->ws, n);
     double *l1 = arena_take<double>(h->ws, n), *l2 = arena_take<double>(h->ws, n), *yd = arena_take<double>(h->ws, n);
     double *zin = arena_take<double>(h->ws, n), *cur = arena_take<double>(h->ws, n);
-    unsigned char *act = arena_take<unsigned char>(h->ws, n);
+    double *act = arena_take<double>(h->ws, n);  // active-set marks of pass 2 (0.0 / 1.0: staged like the other fields)
     const AltParams p{params->lambda_smooth, params->lambda_follow, params->max_climb_rate, params->uav_R,
                       params->safe_distance};
     const long long want = (n_rows_cap + 255) / 256, cap = (long long)h->sm_count * 8;
-    MS_LAUNCH(h, k_alt_prep, (unsigned)(want < cap ? want : cap), 256, p, B, row_offset, rows_inout, elev, w1, w2, tgt);
-    MS_LAUNCH(h, k_alt_solve, grid_for(B, 32), 32, p, B, row_offset, rows_inout, elev, w1, w2, tgt, l1, l2, yd, zin, cur, act,
-              z_pass1_out, solves_out, flags_out);
+    MS_LAUNCH(h, k_alt_prep, (unsigned)(want < cap ? want : cap), 256, p, B, row_offset, rows_inout, elev, w1, w2, tgt, act);
+    if (!h->alt_smem_opted) {  // > 48 KB of dynamic shared memory needs the opt-in (per device; once per handle)
+        MS_CUDA(h, cudaFuncSetAttribute(k_alt_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ALT_SMEM_BYTES));
+        h->alt_smem_opted = true;
+    }
+    prof_before(h, "k_alt_solve");
+    k_alt_solve<<<grid_for(B, 32), 32, ALT_SMEM_BYTES, h->stream>>>(p, B, row_offset, elev, w1, w2, tgt, l1, l2, yd, zin, cur,
+                                                                    act, z_pass1_out, solves_out, flags_out);
+    prof_after(h);
+    ++h->launches;
+    MS_CUDA(h, cudaPeekAtLastError());
+    MS_LAUNCH(h, k_alt_finish, (unsigned)(want < cap ? want : cap), 256, B, row_offset, cur, zin, rows_inout);
     return MSNAP_OK;
 }
 

@@ -104,40 +104,38 @@ __device__ __forceinline__ double alt_rcp(double x) {  // 1/x for a positive nor
 }
 
 // ---- k_alt_solve: one trajectory per lane, 32 trajectories per warp, one warp per CTA -------------------------------
-// All lanes of a warp advance through their chains in lock step, so row k of 32 different trajectories is needed at the
-// same time: 32 addresses n rows apart.  The warp therefore moves its data in CHUNKS of 32 rows: for every trajectory of
-// the warp the 32 rows of a chunk are 256 contiguous bytes, fetched by one coalesced warp-wide cp.async into a shared
-// memory tile [field][trajectory][row] (padded pitch) and written back the same way.  Tiles are double buffered: the
-// copies of the next chunk are issued before the current chunk's 32 recurrence steps and waited for after them, so the
-// chains never wait on memory, and every global access is a full 256-byte line.
+// The kernel is a set of dependent chains, so what counts is the latency of one row step and nothing may wait on memory
+// inside it.  Each lane therefore streams the rows of ITS trajectory through shared memory in chunks of 32 rows with
+// cp.async (8 bytes per copy, consecutive addresses: every 32-byte sector is fetched from L2 once and served from L1 three
+// more times), double buffered: the copies of the next chunk are issued before the current chunk's 32 recurrence steps and
+// waited for after them.  A lane's tile row is private to it ([field][lane][row], padded pitch => no bank conflicts), so no
+// cross-lane synchronisation or index exchange is needed; results leave by plain stores, which nothing waits for.
 constexpr int ALT_CHUNK = 32;
-constexpr int ALT_PITCH = ALT_CHUNK + 1;  // bank-conflict-free: lane t reads word t * 33 + j
+constexpr int ALT_PITCH = ALT_CHUNK + 1;  // lane t reads word t * 33 + j: conflict-free
 constexpr int ALT_TILES = 5;              // fields a sweep stages at most (backward sweep of pass 2)
 constexpr int ALT_TILE_WORDS = 32 * ALT_PITCH;
 constexpr size_t ALT_SMEM_BYTES = 2 * ALT_TILES * ALT_TILE_WORDS * sizeof(double);
 
-// One sweep over the chunks of the warp's 32 trajectories, ascending (forward elimination) or descending (back
-// substitution).  in[f] -> tile f; `row(k, j, T)` performs row k of this lane's trajectory on T(f, j) = tile f, this lane,
-// row j of the chunk, and leaves its results in tiles; out[o] is then stored from tile o.  Lanes with active == false
-// neither compute nor store (their trajectory has converged), lanes beyond their own length neither.
-template <int NIN, int NOUT, bool DESC, class Row>
-__device__ __forceinline__ void alt_sweep(double *sm, const double *const (&in)[NIN], double *const (&out)[NOUT], long long base,
-                                          int n, int nmax, bool active, int lane, Row row) {
+// One sweep over this lane's rows, ascending (forward elimination) or descending (back substitution).  in[f] is staged
+// into tile f; `row(k, j, T)` performs row k with T(f, j) = staged value of field f.  Lanes with active == false idle.
+template <int NIN, bool DESC, class Row>
+__device__ __forceinline__ void alt_sweep(double *sm, const double *const (&in)[NIN], long long base, int n, int nmax, bool active,
+                                          int lane, Row row) {
     if (nmax <= 0) return;
     const int n_chunks = (nmax + ALT_CHUNK - 1) / ALT_CHUNK;
-    auto chunk_k0 = [&](int c) { return (long long)(DESC ? n_chunks - 1 - c : c) * ALT_CHUNK; };
+    const int n_eff = active ? n : 0;
+    auto chunk_k0 = [&](int c) { return (DESC ? n_chunks - 1 - c : c) * ALT_CHUNK; };
     auto issue = [&](int c, int buf) {
-        const long long k = chunk_k0(c) + lane;
-        double *tiles = sm + (size_t)buf * ALT_TILES * ALT_TILE_WORDS;
-#pragma unroll 4
-        for (int q = 0; q < 32; ++q) {
-            const long long bq = __shfl_sync(0xffffffffu, base, q);
-            const int nq = __shfl_sync(0xffffffffu, n, q);
-            if (k < nq) {
+        const int k0 = chunk_k0(c);
+        double *mine = sm + (size_t)buf * ALT_TILES * ALT_TILE_WORDS + lane * ALT_PITCH;
+        const int cnt = n_eff - k0 < ALT_CHUNK ? n_eff - k0 : ALT_CHUNK;  // rows of this chunk this lane owns (may be <= 0)
 #pragma unroll
-                for (int f = 0; f < NIN; ++f)
-                    __pipeline_memcpy_async(tiles + f * ALT_TILE_WORDS + q * ALT_PITCH + lane, in[f] + bq + k, sizeof(double));
-            }
+        for (int f = 0; f < NIN; ++f) {
+            const double *src = in[f] + base + k0;
+            double *dst = mine + f * ALT_TILE_WORDS;
+#pragma unroll 8
+            for (int j = 0; j < ALT_CHUNK; ++j)
+                if (j < cnt) __pipeline_memcpy_async(dst + j, src + j, sizeof(double));
         }
         __pipeline_commit();
     };
@@ -148,38 +146,22 @@ __device__ __forceinline__ void alt_sweep(double *sm, const double *const (&in)[
         if (more) issue(c + 1, buf ^ 1);
         if (more) __pipeline_wait_prior(1);
         else __pipeline_wait_prior(0);
-        __syncwarp();
-        double *tiles = sm + (size_t)buf * ALT_TILES * ALT_TILE_WORDS;
-        const long long k0 = chunk_k0(c);
-        if (active) {
-            auto T = [&](int f, int j) -> double & { return tiles[f * ALT_TILE_WORDS + lane * ALT_PITCH + j]; };
-            if (DESC) {
-                for (int j = ALT_CHUNK - 1; j >= 0; --j)
-                    if (k0 + j < n) row(k0 + j, j, T);
-            } else {
-                for (int j = 0; j < ALT_CHUNK; ++j)
-                    if (k0 + j < n) row(k0 + j, j, T);
-            }
+        const double *mine = sm + (size_t)buf * ALT_TILES * ALT_TILE_WORDS + lane * ALT_PITCH;
+        auto T = [&](int f, int j) { return mine[f * ALT_TILE_WORDS + j]; };
+        const int k0 = chunk_k0(c);
+        const int cnt = n_eff - k0 < ALT_CHUNK ? n_eff - k0 : ALT_CHUNK;
+        if (DESC) {
+            for (int j = cnt - 1; j >= 0; --j) row(k0 + j, j, T);
+        } else {
+            for (int j = 0; j < cnt; ++j) row(k0 + j, j, T);
         }
         __syncwarp();
-        const long long k = k0 + lane;
-#pragma unroll 4
-        for (int q = 0; q < 32; ++q) {
-            const long long bq = __shfl_sync(0xffffffffu, base, q);
-            const int nq = __shfl_sync(0xffffffffu, n, q);
-            const bool aq = __shfl_sync(0xffffffffu, active, q);
-            if (aq && k < nq) {
-#pragma unroll
-                for (int o = 0; o < NOUT; ++o)
-                    if (out[o]) out[o][bq + k] = tiles[o * ALT_TILE_WORDS + q * ALT_PITCH + lane];
-            }
-        }
-        __syncwarp();  // the tiles of `buf` are free again for the copies issued in the next trip
     }
 }
 
 struct AltFwd {  // state a lane carries from row to row of the forward sweep
     double a1 = 0.0, a2 = 0.0, c = 0.0, Dm1 = 0.0, Dm2 = 0.0, ym1 = 0.0, ym2 = 0.0, wm1 = 0.0;
+    int in_m = 0, in_0 = 0;  // rows k-1 / k are interior rows of the smoothing stencil (carried, row k+1 is tested anew)
     bool ok = true;
 };
 struct AltBwd {  // ... and of the backward sweep: z_{k+1}, z_{k+2}, L[k+1,k], L[k+2,k], L[k+1,k-1]
@@ -188,13 +170,14 @@ struct AltBwd {  // ... and of the backward sweep: z_{k+1}, z_{k+2}, L[k+1,k], L
 
 // Row k of the banded LDL' factorisation fused with the forward substitution.  wk = climb weight of edge (k, k+1),
 // extra / rhs = what the pass adds to the diagonal / right-hand side.  Returns (L[k,k-1], L[k,k-2], y_k / D_k).
-__device__ __forceinline__ void alt_fwd_row(AltFwd &f, long long k, long long n, double s, bool smooth, double wk, double extra,
+__device__ __forceinline__ void alt_fwd_row(AltFwd &f, int k, int n, double s, bool smooth, double wk, double extra,
                                             double rhs, double &o_l1, double &o_l2, double &o_yd) {
-    const int in_m = smooth && k - 1 >= 1 && k - 1 <= n - 2, in_0 = smooth && k >= 1 && k <= n - 2,
-              in_p = smooth && k + 1 >= 1 && k + 1 <= n - 2;
+    const int in_m = f.in_m, in_0 = f.in_0, in_p = smooth && k + 1 <= n - 2;   // k + 1 >= 1 always
+    f.in_m = in_0;
+    f.in_0 = in_p;
     const double d = s * (double)(in_p + 4 * in_0 + in_m) + (f.wm1 + wk) + extra + ALT_REG;
     const double e = k + 1 < n ? s * (double)(-2 * (in_0 + in_p)) - wk : 0.0;  // H[k, k+1]
-    const double h = k + 2 < n ? s * (double)in_p : 0.0;                       // H[k, k+2]
+    const double h = s * (double)in_p;                                         // H[k, k+2] (in_p implies k + 2 < n)
     const double D = fma(-f.a2 * f.a2, f.Dm2, fma(-f.a1 * f.a1, f.Dm1, d));
     const double y = fma(-f.a2, f.ym2, fma(-f.a1, f.ym1, rhs));
     f.ok = f.ok && D > 0.0 && D < 1e300;
@@ -245,23 +228,25 @@ __global__ void __launch_bounds__(32) k_alt_solve(AltParams p, long long B, cons
         const bool smooth = n >= 3 && s > 0.0;
         AltFwd f;
         const double *const in_f[2] = {w1, tgt};
-        double *const out_f[3] = {l1, l2, yd};
-        alt_sweep<2, 3, false>(alt_sm, in_f, out_f, base, n, nmax, n > 0, lane, [&](long long k, int j, auto &T) {
-            const double wk = T(0, j), t = T(1, j);
+        alt_sweep<2, false>(alt_sm, in_f, base, n, nmax, n > 0, lane, [&](int k, int j, auto &T) {
+            const double t = T(1, j);
             const bool has = t == t;
-            alt_fwd_row(f, k, n, s, smooth, wk, has ? lf : 0.0, has ? lf * t : 0.0, T(0, j), T(1, j), T(2, j));
+            double o1, o2, o3;
+            alt_fwd_row(f, k, n, s, smooth, T(0, j), has ? lf : 0.0, has ? lf * t : 0.0, o1, o2, o3);
+            l1[base + k] = o1;
+            l2[base + k] = o2;
+            yd[base + k] = o3;
         });
         ok = f.ok;
         AltBwd r;
         const bool have_elev = elev != nullptr;
         const double *const in_b[4] = {l1, l2, yd, have_elev ? elev : yd};
-        double *const out_b[2] = {zin, z_pass1_out};
-        alt_sweep<4, 2, true>(alt_sm, in_b, out_b, base, n, nmax, n > 0, lane, [&](long long, int j, auto &T) {
+        alt_sweep<4, true>(alt_sm, in_b, base, n, nmax, n > 0, lane, [&](int k, int j, auto &T) {
             double z = alt_bwd_row(r, T(0, j), T(1, j), T(2, j));
             const double el = have_elev ? T(3, j) : NAN;
             if (el == el && z < el + safe) z = el + safe;  // cpp:1705-1707
-            T(0, j) = z;
-            T(1, j) = z;
+            zin[base + k] = z;
+            if (z_pass1_out) z_pass1_out[base + k] = z;
         });
     }
     // ---- pass 2: optimizeHeightsGlobalSmooth with lambda_smooth * 10, max_climb_rate * 0.5 (cpp:1352-1355, 1714-1827)
@@ -273,29 +258,29 @@ __global__ void __launch_bounds__(32) k_alt_solve(AltParams p, long long B, cons
         if (!__any_sync(0xffffffffu, running)) break;
         AltFwd f;
         const double *const in_f[3] = {w2, zin, act};
-        double *const out_f[3] = {l1, l2, yd};
-        alt_sweep<3, 3, false>(alt_sm, in_f, out_f, base, n, nmax, running, lane, [&](long long k, int j, auto &T) {
-            const double wk = T(0, j), zi = T(1, j);
+        alt_sweep<3, false>(alt_sm, in_f, base, n, nmax, running, lane, [&](int k, int j, auto &T) {
+            const double zi = T(1, j);
             double x = 0.0;
             if (k == 0) x += ALT_FIX_WEIGHT;                                // cpp:1779-1784
             if (k == n - 1) x += ALT_FIX_WEIGHT;
             if (k >= 1 && k < n - 1 && T(2, j) != 0.0) x += ALT_CON_WEIGHT;  // cpp:1787-1793
-            alt_fwd_row(f, k, n, s2, smooth2, wk, x, x * zi, T(0, j), T(1, j), T(2, j));
+            double o1, o2, o3;
+            alt_fwd_row(f, k, n, s2, smooth2, T(0, j), x, x * zi, o1, o2, o3);
+            l1[base + k] = o1;
+            l2[base + k] = o2;
+            yd[base + k] = o3;
         });
         if (running) ok = ok && f.ok;
         AltBwd r;
         bool violation = false;
         const double *const in_b[5] = {l1, l2, yd, zin, act};
-        double *const out_b[2] = {cur, act};
-        alt_sweep<5, 2, true>(alt_sm, in_b, out_b, base, n, nmax, running, lane, [&](long long, int j, auto &T) {
+        alt_sweep<5, true>(alt_sm, in_b, base, n, nmax, running, lane, [&](int k, int j, auto &T) {
             const double z = alt_bwd_row(r, T(0, j), T(1, j), T(2, j));
-            double a = T(4, j);
-            if (z < T(3, j) - ALT_VIOLATION && a == 0.0) {  // cpp:1805-1810
-                a = 1.0;
+            cur[base + k] = z;
+            if (z < T(3, j) - ALT_VIOLATION && T(4, j) == 0.0) {  // cpp:1805-1810
+                act[base + k] = 1.0;
                 violation = true;
             }
-            T(0, j) = z;
-            T(1, j) = a;
         });
         if (running) {
             ++solves;

@@ -161,7 +161,7 @@ __device__ __forceinline__ void alt_sweep(double *sm, const double *const (&in)[
 
 struct AltFwd {  // state a lane carries from row to row of the forward sweep
     double a1 = 0.0, a2 = 0.0, c = 0.0, Dm1 = 0.0, Dm2 = 0.0, ym1 = 0.0, ym2 = 0.0, wm1 = 0.0;
-    int in_m = 0, in_0 = 0;  // rows k-1 / k are interior rows of the smoothing stencil (carried, row k+1 is tested anew)
+    double sm = 0.0, s0 = 0.0;  // lambda * [row k-1 / row k is an interior row of the smoothing stencil] (row k+1 is tested anew)
     bool ok = true;
 };
 struct AltBwd {  // ... and of the backward sweep: z_{k+1}, z_{k+2}, L[k+1,k], L[k+2,k], L[k+1,k-1]
@@ -172,12 +172,14 @@ struct AltBwd {  // ... and of the backward sweep: z_{k+1}, z_{k+2}, L[k+1,k], L
 // extra / rhs = what the pass adds to the diagonal / right-hand side.  Returns (L[k,k-1], L[k,k-2], y_k / D_k).
 __device__ __forceinline__ void alt_fwd_row(AltFwd &f, int k, int n, double s, bool smooth, double wk, double extra,
                                             double rhs, double &o_l1, double &o_l2, double &o_yd) {
-    const int in_m = f.in_m, in_0 = f.in_0, in_p = smooth && k + 1 <= n - 2;   // k + 1 >= 1 always
-    f.in_m = in_0;
-    f.in_0 = in_p;
-    const double d = s * (double)(in_p + 4 * in_0 + in_m) + (f.wm1 + wk) + extra + ALT_REG;
-    const double e = k + 1 < n ? s * (double)(-2 * (in_0 + in_p)) - wk : 0.0;  // H[k, k+1]
-    const double h = s * (double)in_p;                                         // H[k, k+2] (in_p implies k + 2 < n)
+    // smoothing stencil (cpp:1588-1604): H[k,k] = s (in_p + 4 in_0 + in_m), H[k,k+1] = -2 s (in_0 + in_p), H[k,k+2] = s in_p,
+    // in_x = 1 iff row k-1 / k / k+1 is interior (1 <= row <= n-2)
+    const double sm = f.sm, s0 = f.s0, sp = (smooth && k + 1 <= n - 2) ? s : 0.0;
+    f.sm = s0;
+    f.s0 = sp;
+    const double d = fma(4.0, s0, sp + sm) + (f.wm1 + wk) + extra + ALT_REG;
+    const double e = -2.0 * (s0 + sp) - wk;  // H[k, k+1]; the last row has s0 = sp = 0 and wk = 0 (k_alt_prep)
+    const double h = sp;                     // H[k, k+2]; sp != 0 implies k + 2 < n
     const double D = fma(-f.a2 * f.a2, f.Dm2, fma(-f.a1 * f.a1, f.Dm1, d));
     const double y = fma(-f.a2, f.ym2, fma(-f.a1, f.ym1, rhs));
     f.ok = f.ok && D > 0.0 && D < 1e300;

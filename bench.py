@@ -365,8 +365,49 @@ def run_b200(args):
                        launches_per_step=g_launches / g_steps, kernel=kname,
                        kernel_ms_per_step=gprof[kname]["total_ms"] / prof_steps, rows_per_step=tot_samples,
                        algorithmic_bytes_per_launch=48 * tot_samples)
+        # SURVEY 8f ranks 1 + 2 together: getPlan's leader chain on the device (cpp:2640 -> 3684 -> 3712-3729 -> 3699):
+        # WGS84 waypoints -> ENU -> minimum snap -> sampled rows -> cost-map lookup -> altitude optimisation -> WGS84 rows
+        chain = None
+        if headline:
+            from cs_pathplan_b200 import shipped_altitude_params
+
+            alt_p = shipped_altitude_params()
+            gx = torch.arange(128, dtype=torch.float64, device=dev)
+            grid = (-60.0 + 25.0 * torch.sin(gx[None, :] / 9.0) * torch.cos(gx[:, None] / 7.0)).to(torch.float32).contiguous()
+            g_res, g_ox, g_oy = 8.0, -512.0, 512.0            # 128 x 128 cells of 8 m around the origin, terrain -85..-35 m
+            for s_ in sets:
+                s_.lla_wp = torch.from_numpy(tool.enuToWGS84_Batch(s_.wp_h.numpy(), origin)).to(dev)
+                s_.elev = torch.empty(s_.cap, dtype=torch.float64, device=dev)
+                s_.lla = torch.empty((s_.cap, 3), dtype=torch.float64, device=dev)
+                s_.solves = torch.empty(B, dtype=torch.int32, device=dev)
+
+            def chain_step(cfg_, s_, which=0):
+                t_ = tools[which]
+                t_.generate_batch_dev(cfg_, s_.lla_wp, s_.off, s_.samples, ns=NS, times=s_.times, coeff=s_.coeff,
+                                      max_dev=s_.max_dev, iters=s_.iters, vw_final=s_.vw, flags=s_.flags)
+                t_.cost_map_lookup_dev(grid, g_res, g_ox, g_oy, s_.samples, s_.elev, n_rows=s_.off[B:])
+                t_.altitude_optimize_batch_dev(alt_p, s_.off, s_.samples, s_.elev, solves=s_.solves)
+                t_.enu_to_wgs84_dev(origin, s_.samples, s_.lla, n_rows=s_.off[B:])
+
+            for t_ in tools:
+                t_.set_waypoint_frame("wgs84", origin)
+            step_main = step
+            step = chain_step
+            c_steps = min(steps, 300)
+            c_ms, c_launches = timed_run(cfg, sets, c_steps, 3, S)
+            tool.profile_begin()
+            for i in range(prof_steps):
+                chain_step(cfg, sets[i % ROTATE])
+            cprof = tool.profile_end()
+            step = step_main
+            for t_ in tools:
+                t_.set_waypoint_frame("enu")
+            chain = dict(value=world * B * c_steps / (c_ms * 1e-3), unit=UNIT, ms_per_step=c_ms / c_steps,
+                         launches_per_step=c_launches / c_steps, rows_per_step=int(sets[0].off[-1].item()),
+                         mean_altitude_solves=float(sets[0].solves.double().mean().item()),
+                         kernels_ms_per_step={k: v["total_ms"] / prof_steps for k, v in cprof.items()})
         results[weights] = dict(
-            geo=geo, ms=ms, steps=steps, launches=launches, value=world * B * steps / (ms * 1e-3), latency_ms=latency_ms,
+            geo=geo, chain=chain, ms=ms, steps=steps, launches=launches, value=world * B * steps / (ms * 1e-3), latency_ms=latency_ms,
             e2e=dict(value=world * B * e2e_steps / e2e_s, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                      steps=e2e_steps, ms_per_step=e2e_s / e2e_steps * 1e3, host_threads=S,
                      single_call_ms=e2e_single_ms),
@@ -445,6 +486,12 @@ def run_b200(args):
                      kernel_hbm_GBps=gbs, kernel_hbm_frac=gbs / hbm_peak,
                      kernel_rows_per_s=g["rows_per_step"] / (g["kernel_ms_per_step"] * 1e-3))
             line["wgs84_frame"] = g
+        if h.get("chain"):
+            c = dict(h["chain"])
+            c["note"] = ("getPlan's leader chain per batch, device resident, same two-stream driver as `value`: WGS84 waypoints -> "
+                         "ENU (k_wgs84_to_enu) -> minimum snap + sampler -> cost-map lookup -> altitude optimisation (shipped "
+                         "config.yaml parameters, synthetic 128 x 128 terrain grid) -> WGS84 rows; SURVEY.md section 8f ranks 1-2")
+            line["leader_chain"] = c
         if world == 1 and not args.no_cpu_baseline:
             try:
                 from oracle import ref

@@ -72,6 +72,7 @@ SIGNATURES = {
     "msnap_wgs84_to_enu_host": (_i, [_vp, _vp, _ll, _vp, _vp]),
     "msnap_enu_to_wgs84_dev": (_i, [_vp, _vp, _ll, _vp, _vp]),
     "msnap_enu_to_wgs84_host": (_i, [_vp, _vp, _ll, _vp, _vp]),
+    "msnap_enu_to_wgs84_counted_dev": (_i, [_vp, _vp, _ll, _vp, _vp, _vp]),
     "msnap_set_sample_frame": (_i, [_vp, _i, _vp]),
     "msnap_set_waypoint_frame": (_i, [_vp, _i, _vp]),
     "msnap_set_geo_exact_trig": (_i, [_vp, _i]),

@@ -302,9 +302,13 @@ class TrajectoryGeneratorTool:
         self._check(self._L.msnap_wgs84_to_enu_dev(self._h, _ptr(ref), int(lla.shape[0]), int(lla.data_ptr()),
                                                    int(enu_out.data_ptr())))
 
-    def enu_to_wgs84_dev(self, reference, enu, lla_out, steps_out=None):
+    def enu_to_wgs84_dev(self, reference, enu, lla_out, steps_out=None, n_rows=None):
+        """n_rows: optional device int64 scalar (e.g. sample_offset[B:]) bounding the rows that are converted."""
         ref = _f64(reference).reshape(3)
-        if steps_out is None:
+        if n_rows is not None:
+            self._check(self._L.msnap_enu_to_wgs84_counted_dev(self._h, _ptr(ref), int(enu.shape[0]), int(n_rows.data_ptr()),
+                                                               int(enu.data_ptr()), int(lla_out.data_ptr())))
+        elif steps_out is None:
             self._check(self._L.msnap_enu_to_wgs84_dev(self._h, _ptr(ref), int(enu.shape[0]), int(enu.data_ptr()),
                                                        int(lla_out.data_ptr())))
         else:

@@ -1268,6 +1268,17 @@ int msnap_enu_to_wgs84_dev(msnap_handle h, const double *reference_lla, long lon
     return launch_enu_to_wgs84(h, f, n, nullptr, enu, lla_out, nullptr);
 }
 
+int msnap_enu_to_wgs84_counted_dev(msnap_handle h, const double *reference_lla, long long n_rows_cap,
+                                   const long long *n_rows_dev, const double *enu, double *lla_out) {
+    if (!h || !geo_reference_ok(reference_lla) || n_rows_cap < 0 || !n_rows_dev || (n_rows_cap > 0 && (!enu || !lla_out)))
+        return MSNAP_ERR_INVALID_ARG;
+    if (n_rows_cap == 0) return MSNAP_OK;
+    DeviceGuard guard(h->device);
+    GeoFrame f;
+    geo_make_frame(reference_lla, f);
+    return launch_enu_to_wgs84(h, f, n_rows_cap, n_rows_dev, enu, lla_out, nullptr);
+}
+
 int msnap_wgs84_to_enu_dev(msnap_handle h, const double *reference_lla, long long n, const double *lla, double *enu_out) {
     if (!h || !geo_reference_ok(reference_lla) || n < 0 || (n > 0 && (!lla || !enu_out))) return MSNAP_ERR_INVALID_ARG;
     if (n == 0) return MSNAP_OK;

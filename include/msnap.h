@@ -176,6 +176,10 @@ int msnap_wgs84_to_enu_dev(msnap_handle h, const double *reference_lla, long lon
 int msnap_wgs84_to_enu_host(msnap_handle h, const double *reference_lla, long long n, const double *lla, double *enu_out);
 int msnap_enu_to_wgs84_dev(msnap_handle h, const double *reference_lla, long long n, const double *enu, double *lla_out);
 int msnap_enu_to_wgs84_host(msnap_handle h, const double *reference_lla, long long n, const double *enu, double *lla_out);
+/* msnap_enu_to_wgs84_dev for a buffer whose fill level is only known on the device: converts the first
+ * min(*n_rows_dev, n_rows_cap) rows (n_rows_dev = e.g. sample_offset_out + B of msnap_generate_batch_dev). */
+int msnap_enu_to_wgs84_counted_dev(msnap_handle h, const double *reference_lla, long long n_rows_cap,
+                                   const long long *n_rows_dev, const double *enu, double *lla_out);
 /* Frame of the rows msnap_generate_batch_* / msnap_generate_one_host write to samples_out: 0 (default) = ENU, as
  * GenerateTrajectoryMatrix returns them; 1 = WGS84 {lon, lat, alt} about reference_lla, i.e. getPlan's
  * `enuToWGS84_Batch(Trajectory_ENU, origin_)` (cpp:3699) applied on the device before the rows leave it.  The

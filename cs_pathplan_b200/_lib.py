@@ -80,6 +80,7 @@ SIGNATURES = {
     "msnap_altitude_params_default": (None, [C.POINTER(msnap_altitude_params)]),
     "msnap_altitude_optimize_batch_dev": (_i, [_vp, C.POINTER(msnap_altitude_params), _ll, _vp, _ll] + [_vp] * 5),
     "msnap_altitude_optimize_batch_host": (_i, [_vp, C.POINTER(msnap_altitude_params), _ll] + [_vp] * 6),
+    "msnap_set_altitude_policy": (_i, [_vp, _i]),
     "msnap_cost_map_lookup_dev": (_i, [_vp, _vp, _i, _i, _d, _d, _d, _ll, _vp, _vp, _vp]),
     "msnap_profile_begin": (_i, [_vp]),
     "msnap_profile_end": (_i, [_vp, C.c_char_p, _ll]),

@@ -368,6 +368,10 @@ class TrajectoryGeneratorTool:
             self._h, C.byref(c), int(row_offset.numel()) - 1, dp(row_offset), int(rows.shape[0]), dp(rows), dp(elev),
             dp(z_pass1), dp(solves), dp(flags)))
 
+    def set_altitude_policy(self, policy: int):
+        """0 = lane pairs (two-sided elimination, default), 1 = one lane per trajectory."""
+        self._check(self._L.msnap_set_altitude_policy(self._h, int(policy)))
+
     def cost_map_lookup_dev(self, grid, resolution, origin_x, origin_y, rows, elev_out, n_rows=None):
         """ElevationCostMap::getCostAt (elevation_cost_map.cpp:373-380) for device rows: grid = CUDA float32 tensor
         [height, width] (row-major, top-left origin); n_rows = optional device int64 scalar bounding the rows."""

@@ -30,6 +30,7 @@
 #include <cuda_pipeline.h>
 
 #include <cmath>
+#include <type_traits>
 
 namespace msnap {
 
@@ -158,6 +159,17 @@ __device__ __forceinline__ void alt_sweep(double *sm, const double *const (&in)[
         __syncwarp();
     }
 }
+
+template <int NN>
+struct AltPtrs {
+    static constexpr int N = NN;
+    const double *p[NN];
+};
+template <int NN>
+struct AltInts {
+    static constexpr int N = NN;
+    int p[NN];
+};
 
 struct AltFwd {  // state a lane carries from row to row of the forward sweep
     double a1 = 0.0, a2 = 0.0, c = 0.0, Dm1 = 0.0, Dm2 = 0.0, ym1 = 0.0, ym2 = 0.0, wm1 = 0.0;
@@ -290,6 +302,211 @@ __global__ void __launch_bounds__(32) k_alt_solve(AltParams p, long long B, cons
         }
     }
     if (b < B) {
+        if (solves_out) solves_out[b] = solves;
+        if (flags_out) flags_out[b] = ok ? 0u : ALT_FLAG_PIVOT;
+    }
+}
+
+// ---- k_alt_solve_pair: two lanes per trajectory (two-sided / twisted elimination) ----------------------------------
+// The chain of a solve is cut in two: lane 0 of a pair eliminates rows 0 .. m-1 downwards, lane 1 rows n-1 .. m+2 upwards
+// (the same recurrence on the mirrored system: the smoothing stencil and the penalties are symmetric, the climb weight of
+// the edge towards the NEXT row is w[k] going down and w[k-1] going up).  Both stop in front of the two middle rows m, m+1,
+// whose 2 x 2 Schur complement collects the contributions of both sides; the pair exchanges six numbers by shuffle, both
+// lanes solve the 2 x 2 system (symmetric expressions: bit-identical on both lanes) and substitute back outwards.  Half
+// the dependent steps per solve, twice the warps.  Trajectories shorter than ALT_TWIST_MIN rows run on lane 0 alone.
+constexpr int ALT_TWIST_MIN = 8;
+
+struct AltSpan {
+    long long base;
+    int n, side, cnt;  // cnt = local rows this lane walks (its side's rows + its middle row)
+    bool twisted;
+    __device__ __forceinline__ int row(int i) const { return side ? n - 1 - i : i; }
+};
+
+// alt_sweep for a lane of a pair: local indices 0 .. S.cnt-1 (ascending, or descending for the back substitution) map to
+// rows S.row(i); field f is read at row + shift[f] on the upward side (the climb weights).
+template <int NIN, bool DESC, class Row>
+__device__ __forceinline__ void alt_sweep_pair(double *sm, const double *const (&in)[NIN], const int (&shift)[NIN], const AltSpan &S,
+                                               int cmax, bool active, int lane, Row row) {
+    if (cmax <= 0) return;
+    const int n_chunks = (cmax + ALT_CHUNK - 1) / ALT_CHUNK;
+    const int len = active ? S.cnt : 0;
+    auto chunk_i0 = [&](int c) { return (DESC ? n_chunks - 1 - c : c) * ALT_CHUNK; };
+    auto issue = [&](int c, int buf) {
+        const int i0 = chunk_i0(c);
+        double *mine = sm + (size_t)buf * ALT_TILES * ALT_TILE_WORDS + lane * ALT_PITCH;
+        const int cnt = len - i0 < ALT_CHUNK ? len - i0 : ALT_CHUNK;
+        const int step = S.side ? -1 : 1;
+#pragma unroll
+        for (int f = 0; f < NIN; ++f) {
+            const double *src = in[f] + S.base + S.row(i0) + (S.side ? shift[f] : 0);
+            double *dst = mine + f * ALT_TILE_WORDS;
+#pragma unroll 8
+            for (int j = 0; j < ALT_CHUNK; ++j)
+                if (j < cnt) __pipeline_memcpy_async(dst + j, src + step * j, sizeof(double));
+        }
+        __pipeline_commit();
+    };
+    issue(0, 0);
+    for (int c = 0; c < n_chunks; ++c) {
+        const int buf = c & 1;
+        const bool more = c + 1 < n_chunks;
+        if (more) issue(c + 1, buf ^ 1);
+        if (more) __pipeline_wait_prior(1);
+        else __pipeline_wait_prior(0);
+        const double *mine = sm + (size_t)buf * ALT_TILES * ALT_TILE_WORDS + lane * ALT_PITCH;
+        auto T = [&](int f, int j) { return mine[f * ALT_TILE_WORDS + j]; };
+        const int i0 = chunk_i0(c);
+        const int cnt = len - i0 < ALT_CHUNK ? len - i0 : ALT_CHUNK;
+        if (DESC) {
+            for (int j = cnt - 1; j >= 0; --j) row(i0 + j, S.row(i0 + j), j, T);
+        } else {
+            for (int j = 0; j < cnt; ++j) row(i0 + j, S.row(i0 + j), j, T);
+        }
+        __syncwarp();
+    }
+}
+
+// The middle row of a side: its diagonal and right-hand side with this side's eliminations applied, the side's coupling
+// term K = L[m+1,m-1] D_{m-1} L[m,m-1] of the off-diagonal entry, and the entry H[m,m+1] itself.  The state is not advanced.
+__device__ __forceinline__ void alt_twist_row(const AltFwd &f, int i, int n, double s, bool smooth, double wk, double extra,
+                                              double rhs, double &tD, double &tY, double &tK, double &tE) {
+    const double sp = (smooth && i + 1 <= n - 2) ? s : 0.0;
+    const double d = fma(4.0, f.s0, sp + f.sm) + (f.wm1 + wk) + extra + ALT_REG;
+    tE = -2.0 * (f.s0 + sp) - wk;
+    tD = fma(-f.a2 * f.a2, f.Dm2, fma(-f.a1 * f.a1, f.Dm1, d));
+    tY = fma(-f.a2, f.ym2, fma(-f.a1, f.ym1, rhs));
+    tK = f.c * f.Dm1 * f.a1;
+}
+
+__global__ void __launch_bounds__(32) k_alt_solve_pair(AltParams p, long long B, const long long *__restrict__ row_offset,
+                                                       const double *elev, const double *w1, const double *w2,
+                                                       const double *tgt, double *l1, double *l2, double *yd, double *zin,
+                                                       double *cur, double *act, double *z_pass1_out,
+                                                       int *__restrict__ solves_out, unsigned *__restrict__ flags_out) {
+    extern __shared__ double alt_sm[];
+    const int lane = threadIdx.x;
+    const unsigned FULL = 0xffffffffu;
+    const long long b = (long long)blockIdx.x * 16 + (lane >> 1);
+    AltSpan S;
+    S.side = lane & 1;
+    S.base = b < B ? row_offset[b] : 0;
+    S.n = b < B ? (int)(row_offset[b + 1] - S.base) : 0;
+    S.twisted = S.n >= ALT_TWIST_MIN;
+    const int n = S.n, m = (n - 2) / 2;  // middle rows m, m + 1
+    S.cnt = S.twisted ? (S.side ? n - m - 1 : m + 1) : (S.side ? 0 : n);
+    const int cmax = __reduce_max_sync(FULL, S.cnt);
+    const long long base = S.base;
+    const int cnt = S.cnt;
+    const bool twist = S.twisted;
+    bool ok = true;
+    auto X = [&](double v) { return __shfl_xor_sync(FULL, v, 1); };
+
+    // one solve: forward sweeps of both sides, the middle 2 x 2 system, back substitution outwards.
+    //   coef(k, j, T, extra, rhs): what the pass adds to row k's diagonal and right-hand side (T(f, j) = staged field f)
+    //   sink(k, j, T, z): what the pass does with z_k (T = the fields staged for the backward sweep)
+    auto solve = [&](double s, auto &in_f, auto &sh_f, auto &in_b, auto &sh_b, bool active, auto coef, auto sink) {
+        const bool smooth = n >= 3 && s > 0.0;
+        AltFwd f;
+        double tD = 1.0, tY = 0.0, tK = 0.0, tE = 0.0;
+        alt_sweep_pair<std::remove_reference_t<decltype(in_f)>::N, false>(
+            alt_sm, in_f.p, sh_f.p, S, cmax, active, lane, [&](int i, int k, int j, auto &T) {
+                double extra, rhs;
+                coef(k, j, T, extra, rhs);
+                if (twist && i == cnt - 1) {
+                    alt_twist_row(f, i, n, s, smooth, T(0, j), extra, rhs, tD, tY, tK, tE);
+                } else {
+                    double o1, o2, o3;
+                    alt_fwd_row(f, i, n, s, smooth, T(0, j), extra, rhs, o1, o2, o3);
+                    l1[base + k] = o1;
+                    l2[base + k] = o2;
+                    yd[base + k] = o3;
+                }
+            });
+        AltBwd r;
+        double z_mid = 0.0;
+        // the partner's middle row and last eliminated row (all lanes take part in the shuffles)
+        const double pD = X(tD), pY = X(tY), pK = X(tK), pc = X(f.c), pDm1 = X(f.Dm1), pym1 = X(f.ym1);
+        bool good = f.ok;
+        if (twist) {
+            const double A_self = fma(-pc * pc, pDm1, tD), A_oth = fma(-f.c * f.c, f.Dm1, pD);
+            const double A12 = tE - (tK + pK);
+            const double g_self = fma(-pc, pym1, tY), g_oth = fma(-f.c, f.ym1, pY);
+            const double det = fma(A_self, A_oth, -(A12 * A12));
+            good = good && A_self > 0.0 && det > 0.0 && det < 1e300;
+            const double idet = alt_rcp(det);
+            z_mid = fma(g_self, A_oth, -(g_oth * A12)) * idet;
+            r.z1 = z_mid;
+            r.z2 = fma(g_oth, A_self, -(g_self * A12)) * idet;
+            r.b1 = f.a1;   // L[m, m-1]   (mirrored on the upward side)
+            r.b2 = f.c;    // L[m+1, m-1]
+            r.b2n = f.a2;  // L[m, m-2]
+        }
+        alt_sweep_pair<std::remove_reference_t<decltype(in_b)>::N, true>(
+            alt_sm, in_b.p, sh_b.p, S, cmax, active, lane, [&](int i, int k, int j, auto &T) {
+                const double z = (twist && i == cnt - 1) ? z_mid : alt_bwd_row(r, T(0, j), T(1, j), T(2, j));
+                sink(k, j, T, z);
+            });
+        return good;
+    };
+
+    // ---- pass 1: optimizeHeights (cpp:1575-1712)
+    {
+        const double lf = p.lambda_follow, safe = p.safe_distance;
+        const bool have_elev = elev != nullptr;
+        const AltPtrs<2> in_f{{w1, tgt}};
+        const AltInts<2> sh_f{{-1, 0}};
+        const AltPtrs<4> in_b{{l1, l2, yd, have_elev ? elev : yd}};
+        const AltInts<4> sh_b{{0, 0, 0, 0}};
+        ok = solve(p.lambda_smooth, in_f, sh_f, in_b, sh_b, cnt > 0,
+                   [&](int, int j, auto &T, double &extra, double &rhs) {
+                       const double t = T(1, j);
+                       const bool has = t == t;
+                       extra = has ? lf : 0.0;
+                       rhs = has ? lf * t : 0.0;
+                   },
+                   [&](int k, int j, auto &T, double z) {
+                       const double el = have_elev ? T(3, j) : NAN;
+                       if (el == el && z < el + safe) z = el + safe;  // cpp:1705-1707
+                       zin[base + k] = z;
+                       if (z_pass1_out) z_pass1_out[base + k] = z;
+                   });
+    }
+    // ---- pass 2: optimizeHeightsGlobalSmooth with lambda_smooth * 10, max_climb_rate * 0.5 (cpp:1352-1355, 1714-1827)
+    int solves = 0;
+    bool running = n > 0;  // the pair's trajectory still iterates (identical on both lanes)
+    for (int iter = 0; iter < ALT_MAX_ITER; ++iter) {
+        if (!__any_sync(FULL, running)) break;
+        bool violation = false;
+        const AltPtrs<3> in_f{{w2, zin, act}};
+        const AltInts<3> sh_f{{-1, 0, 0}};
+        const AltPtrs<5> in_b{{l1, l2, yd, zin, act}};
+        const AltInts<5> sh_b{{0, 0, 0, 0, 0}};
+        const bool good = solve(p.lambda_smooth * 10.0, in_f, sh_f, in_b, sh_b, running && cnt > 0,
+                                [&](int k, int j, auto &T, double &extra, double &rhs) {
+                                    double x = 0.0;
+                                    if (k == 0) x += ALT_FIX_WEIGHT;                                // cpp:1779-1784
+                                    if (k == n - 1) x += ALT_FIX_WEIGHT;
+                                    if (k >= 1 && k < n - 1 && T(2, j) != 0.0) x += ALT_CON_WEIGHT;  // cpp:1787-1793
+                                    extra = x;
+                                    rhs = x * T(1, j);
+                                },
+                                [&](int k, int j, auto &T, double z) {
+                                    cur[base + k] = z;
+                                    if (z < T(3, j) - ALT_VIOLATION && T(4, j) == 0.0) {  // cpp:1805-1810
+                                        act[base + k] = 1.0;
+                                        violation = true;
+                                    }
+                                });
+        violation = violation || __shfl_xor_sync(FULL, violation, 1);
+        if (running) {
+            ok = ok && good;
+            ++solves;
+            if (!violation) running = false;  // converged (cpp:1814)
+        }
+    }
+    ok = ok && __shfl_xor_sync(FULL, ok, 1);
+    if (b < B && S.side == 0) {
         if (solves_out) solves_out[b] = solves;
         if (flags_out) flags_out[b] = ok ? 0u : ALT_FLAG_PIVOT;
     }

@@ -81,6 +81,7 @@ struct msnap_context {
     int wp_frame = 0;       // msnap_set_waypoint_frame: 1 = generate / sample_bound take WGS84 waypoints (cpp:2640)
     GeoFrame wp_geo{};
     bool alt_smem_opted = false;
+    int alt_policy = 0;     // msnap_set_altitude_policy: 0 = lane pairs (two-sided elimination), 1 = one lane per trajectory
     bool geo_trig = false;  // msnap_set_geo_exact_trig: ENU -> WGS84 with the reference's per-step sin/cos/atan2
 };
 
@@ -1358,6 +1359,12 @@ void msnap_altitude_params_default(msnap_altitude_params *p) {  // uavPathPlanni
     p->safe_distance = 50.0;
 }
 
+int msnap_set_altitude_policy(msnap_handle h, int policy) {
+    if (!h || policy < 0 || policy > 1) return MSNAP_ERR_INVALID_ARG;
+    h->alt_policy = policy;
+    return MSNAP_OK;
+}
+
 int msnap_cost_map_lookup_dev(msnap_handle h, const float *grid, int width, int height, double resolution, double origin_x,
                               double origin_y, long long n_rows_cap, const long long *n_rows_dev, const double *rows,
                               double *elev_out) {
@@ -1392,11 +1399,18 @@ int msnap_altitude_optimize_batch_dev(msnap_handle h, const msnap_altitude_param
     MS_LAUNCH(h, k_alt_prep, (unsigned)(want < cap ? want : cap), 256, p, B, row_offset, rows_inout, elev, w1, w2, tgt, act);
     if (!h->alt_smem_opted) {  // > 48 KB of dynamic shared memory needs the opt-in (per device; once per handle)
         MS_CUDA(h, cudaFuncSetAttribute(k_alt_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ALT_SMEM_BYTES));
+        MS_CUDA(h, cudaFuncSetAttribute(k_alt_solve_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ALT_SMEM_BYTES));
         h->alt_smem_opted = true;
     }
-    prof_before(h, "k_alt_solve");
-    k_alt_solve<<<grid_for(B, 32), 32, ALT_SMEM_BYTES, h->stream>>>(p, B, row_offset, elev, w1, w2, tgt, l1, l2, yd, zin, cur,
-                                                                    act, z_pass1_out, solves_out, flags_out);
+    if (h->alt_policy == 1) {  // one lane per trajectory
+        prof_before(h, "k_alt_solve");
+        k_alt_solve<<<grid_for(B, 32), 32, ALT_SMEM_BYTES, h->stream>>>(p, B, row_offset, elev, w1, w2, tgt, l1, l2, yd, zin,
+                                                                        cur, act, z_pass1_out, solves_out, flags_out);
+    } else {  // lane pairs (two-sided elimination)
+        prof_before(h, "k_alt_solve_pair");
+        k_alt_solve_pair<<<grid_for(B, 16), 32, ALT_SMEM_BYTES, h->stream>>>(p, B, row_offset, elev, w1, w2, tgt, l1, l2, yd,
+                                                                             zin, cur, act, z_pass1_out, solves_out, flags_out);
+    }
     prof_after(h);
     ++h->launches;
     MS_CUDA(h, cudaPeekAtLastError());

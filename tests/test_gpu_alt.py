@@ -20,6 +20,14 @@ pytestmark = pytest.mark.gpu
 Z_TOL = 1e-6
 
 
+@pytest.fixture(params=["lane_pairs", "one_lane"])
+def alt_tool(tool, request):
+    """Both execution forms of the banded solves (msnap_set_altitude_policy) must meet the same bars."""
+    tool.set_altitude_policy(0 if request.param == "lane_pairs" else 1)
+    yield tool
+    tool.set_altitude_policy(0)
+
+
 def oracle_params(p):
     return ao.AltitudeParams(p.lambda_smooth, p.lambda_follow, p.max_climb_rate, p.uav_R, p.safe_distance)
 
@@ -28,7 +36,8 @@ def oracle_params(p):
                                     AltitudeParams(lambda_smooth=0.0, lambda_follow=2.0, max_climb_rate=0.5, safe_distance=30.0),
                                     AltitudeParams(lambda_smooth=3.0, lambda_follow=0.5, max_climb_rate=0.0, safe_distance=5.0)],
                          ids=["shipped", "struct_defaults", "no_smoothing", "no_climb_term"])
-def test_ragged_batch_against_the_port(tool, params):
+def test_ragged_batch_against_the_port(alt_tool, params):
+    tool = alt_tool
     grid, res, ox, oy = terrain_grid()
     rows, off = sampled_paths(48, seed=21)
     elev = lookup(grid, res, ox, oy, rows)
@@ -52,7 +61,8 @@ def test_ragged_batch_against_the_port(tool, params):
         assert np.abs(out[sl, 2] - z2_o).max() <= tol2, b
 
 
-def test_reference_shaped_single_call_and_edge_cases(tool):
+def test_reference_shaped_single_call_and_edge_cases(alt_tool):
+    tool = alt_tool
     p = shipped_altitude_params()
     seg = np.column_stack([np.arange(50) * 30.0, np.zeros(50), np.full(50, 1000.0)])
     elev = 980.0 + 25.0 * np.sin(np.arange(50) / 5.0)
@@ -81,7 +91,8 @@ def test_reference_shaped_single_call_and_edge_cases(tool):
         tool.altitude_optimize_batch(rows, np.array([0, 4, 2, 6]), p)
 
 
-def test_batch_equals_singles_bitwise(tool):
+def test_batch_equals_singles_bitwise(alt_tool):
+    tool = alt_tool
     grid, res, ox, oy = terrain_grid()
     rows, off = sampled_paths(40, seed=5)
     elev = lookup(grid, res, ox, oy, rows)
@@ -92,7 +103,8 @@ def test_batch_equals_singles_bitwise(tool):
         assert np.array_equal(tool.optimizeSegmentAltitudeENU(rows[sl], p, elev[sl]), out[sl])
 
 
-def test_device_chain_sampler_lookup_altitude_wgs84(tool):
+def test_device_chain_sampler_lookup_altitude_wgs84(alt_tool):
+    tool = alt_tool
     """getPlan's leader chain after Minisnap_3D on the device (cpp:3684 -> 3712-3729 -> 1535-1573): sampled ENU rows ->
     cost-map lookup -> optimizeSegmentAltitudeENU -> enuToWGS84_Batch, against the oracles run step by step on the host."""
     grid, res, ox, oy = terrain_grid(width=900, height=900, resolution=10.0, origin_x=-4500.0, origin_y=4500.0)
@@ -133,7 +145,8 @@ def test_device_chain_sampler_lookup_altitude_wgs84(tool):
     assert np.array_equal(host, d_rows.cpu().numpy())
 
 
-def test_full_size_properties(tool):
+def test_full_size_properties(alt_tool):
+    tool = alt_tool
     """cfg2-sized sampler output (4 096 trajectories, ~0.8 M rows): clearance, monotonicity and fixed end points."""
     rng = np.random.default_rng(4)
     B = 4096
@@ -154,3 +167,26 @@ def test_full_size_properties(tool):
         sl = slice(int(off[b]), int(off[b + 1]))
         z2 = ao.optimize_segment_altitude_enu(rows[sl], oracle_params(p), elev[sl])
         assert np.abs(out[sl, 2] - z2).max() <= Z_TOL
+
+
+def test_lane_pairs_equal_one_lane(tool):
+    """Two-sided elimination against the plain downward recurrence: same active-set decisions, heights equal to rounding;
+    lengths around the pairing threshold (8 rows) and odd / even lengths included."""
+    grid, res, ox, oy = terrain_grid()
+    rows, off = sampled_paths(200, seed=77, n_min=1, n_max=40)
+    rows2, off2 = sampled_paths(60, seed=78, n_min=100, n_max=400)
+    rows = np.vstack([rows, rows2])
+    off = np.concatenate([off, off[-1] + off2[1:]])
+    elev = lookup(grid, res, ox, oy, rows)
+    p = shipped_altitude_params()
+    out = {}
+    try:
+        for pol in (0, 1):
+            tool.set_altitude_policy(pol)
+            out[pol] = tool.altitude_optimize_batch(rows, off, p, elev, return_info=True)
+    finally:
+        tool.set_altitude_policy(0)
+    assert np.array_equal(out[0][2], out[1][2])                       # solves of the active-set loop
+    assert not out[0][3].any() and not out[1][3].any()
+    assert np.abs(out[0][1] - out[1][1]).max() <= 1e-8                # pass 1
+    assert np.abs(out[0][0][:, 2] - out[1][0][:, 2]).max() <= 1e-7   # final heights

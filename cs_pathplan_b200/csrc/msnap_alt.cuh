@@ -498,14 +498,16 @@ __global__ void __launch_bounds__(32) k_alt_solve_pair(AltParams p, long long B,
                                         violation = true;
                                     }
                                 });
-        violation = violation || __shfl_xor_sync(FULL, violation, 1);
+        const bool partner_violation = __shfl_xor_sync(FULL, violation, 1);  // (no short circuit around a warp collective)
+        violation = violation || partner_violation;
         if (running) {
             ok = ok && good;
             ++solves;
             if (!violation) running = false;  // converged (cpp:1814)
         }
     }
-    ok = ok && __shfl_xor_sync(FULL, ok, 1);
+    const bool partner_ok = __shfl_xor_sync(FULL, ok, 1);
+    ok = ok && partner_ok;
     if (b < B && S.side == 0) {
         if (solves_out) solves_out[b] = solves;
         if (flags_out) flags_out[b] = ok ? 0u : ALT_FLAG_PIVOT;

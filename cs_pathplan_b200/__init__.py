@@ -13,7 +13,7 @@ from .api import (  # noqa: F401
     load_minimum_snap_config,
     shipped_config,
 )
-from .sharding import shard_bounds, shard_batch  # noqa: F401
+from .sharding import shard_bounds, shard_batch, shard_rows  # noqa: F401
 
 __all__ = [
     "AltitudeParams",
@@ -25,4 +25,5 @@ __all__ = [
     "shipped_config",
     "shard_bounds",
     "shard_batch",
+    "shard_rows",
 ]

@@ -53,6 +53,16 @@ def shard_batch(waypoints: np.ndarray, rank: int, world: int, ns: Optional[int] 
     return wp[p0:p1], None, so[b0: b1 + 1] - so[b0], (b0, b1)
 
 
+def shard_rows(rows: np.ndarray, row_offset: np.ndarray, rank: int, world: int):
+    """This rank's slice of a batch of sampled trajectories (rows [n, 3] with CSR row_offset [B+1]) -- the layout the
+    WGS84 <-> ENU and altitude-optimisation stages work on.  Balanced on the number of rows.  Returns
+    (rows_local, row_offset_local, (b0, b1)); rows_local is a view of the caller's array."""
+    off = np.asarray(row_offset, dtype=np.int64)
+    B = off.shape[0] - 1
+    b0, b1 = shard_bounds(B, world, off)[rank]
+    return np.asarray(rows)[int(off[b0]): int(off[b1])], off[b0: b1 + 1] - off[b0], (b0, b1)
+
+
 def global_sample_base(local_rows: int, group=None) -> Tuple[int, int]:
     """Exclusive scan of per-rank sample-row counts over the process group (host-side, off the timed path).
     Returns (first global row of this rank, total rows).  Works with the gloo and nccl backends."""

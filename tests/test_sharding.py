@@ -88,3 +88,67 @@ def test_world2_gloo_shards_and_sample_scan():
     assert n0 == 4 * 4 and n1 == 5 * 4
     assert (base0, base1) == (0, 1234) and tot0 == tot1 == 1333
 
+
+
+def _rows_worker(rank, world, port, out):
+    """Each rank runs the post-sampler stages (altitude optimisation, ENU -> WGS84) on its shard of a ragged batch of
+    sampled trajectories -- here with the CPU oracles standing in for the GPU -- and places its rows in the global
+    layout by the off-path exclusive scan; no other communication."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from alt_helpers import sampled_paths
+        from cs_pathplan_b200 import shard_rows
+        from oracle import alt_oracle as ao
+        from oracle import geo
+
+        rows, off = sampled_paths(13, seed=9, n_min=2, n_max=30)
+        local, loff, (b0, b1) = shard_rows(rows, off, rank, world)
+        z = local.copy()
+        for b in range(b1 - b0):
+            sl = slice(int(loff[b]), int(loff[b + 1]))
+            z[sl, 2] = ao.optimize_segment_altitude_enu(local[sl], ao.shipped_params(), np.full(sl.stop - sl.start, 1000.0))
+        lla = geo.enu_to_wgs84_batch(z, geo.README_ORIGIN)
+        base, total = global_sample_base(local.shape[0])
+        out.put((rank, b0, b1, base, total, lla))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_gloo_row_stages_reassemble():
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from alt_helpers import sampled_paths
+    from oracle import alt_oracle as ao
+    from oracle import geo
+
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rows_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=180) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    rows, off = sampled_paths(13, seed=9, n_min=2, n_max=30)
+    full = rows.copy()
+    for b in range(13):
+        sl = slice(int(off[b]), int(off[b + 1]))
+        full[sl, 2] = ao.optimize_segment_altitude_enu(rows[sl], ao.shipped_params(), np.full(sl.stop - sl.start, 1000.0))
+    exp = geo.enu_to_wgs84_batch(full, geo.README_ORIGIN)
+    assert got[0][1] == 0 and got[0][2] == got[1][1] and got[1][2] == 13          # contiguous trajectory ranges
+    assert got[0][3] == 0 and got[1][3] == got[0][5].shape[0] and got[0][4] == got[1][4] == rows.shape[0]
+    glued = np.empty_like(exp)
+    for _, _, _, base, _, lla in got:
+        glued[base: base + lla.shape[0]] = lla
+    assert np.array_equal(glued, exp)                                             # sharding never changes a result
+    n0, n1 = got[0][5].shape[0], got[1][5].shape[0]
+    assert abs(n0 - n1) <= 2 * 30                                                 # balanced on rows (within one longest trajectory per cut)

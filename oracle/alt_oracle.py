@@ -176,3 +176,64 @@ def optimize_segment_altitude_enu(segment_enu, p: AltitudeParams, elev, return_i
     p2 = replace(p, lambda_smooth=p.lambda_smooth * 10.0, max_climb_rate=p.max_climb_rate * 0.5)
     z2, solves, active = optimize_heights_global_smooth(out_z, seg, p2, return_info=True)
     return (z2, out_z, solves, active) if return_info else z2
+
+
+# ---- O(n) variant for long trajectories ---------------------------------------------------------------------------
+def _band(n, s, w, extra):
+    """Lower banded storage (scipy solveh_banded) of the pass Hessian: smoothing (cpp:1588-1604), climb weights w[i] of
+    the edges (i, i+1) (cpp:1649-1665), `extra` on the diagonal, 1e-8 regularisation."""
+    ab = np.zeros((3, n))
+    if n >= 3 and s > 0:
+        inner = np.zeros(n + 2)                # inner[i + 1] = 1 if row i is an interior row
+        inner[2:n] = 1.0
+        ab[0] += s * (inner[2:] + 4.0 * inner[1:-1] + inner[:-2])
+        ab[1, :n - 1] += s * -2.0 * (inner[1:n] + inner[2:n + 1])
+        ab[2, :n - 2] += s * inner[2:n]
+    ab[0, :n - 1] += w
+    ab[0, 1:] += w
+    ab[1, :n - 1] -= w
+    ab[0] += extra + 1e-8
+    return ab
+
+
+def _climb_weights(seg, max_climb_rate):
+    dist = np.hypot(np.diff(seg[:, 0]), np.diff(seg[:, 1]))
+    denom = dist * max_climb_rate
+    ok = (dist > 1e-9) & (denom > 1e-12) & (max_climb_rate > 0.0)
+    return np.where(ok, 1.0 / np.where(ok, denom, 1.0) ** 2, 0.0)
+
+
+def optimize_segment_altitude_enu_banded(segment_enu, p: AltitudeParams, elev, return_info: bool = False):
+    """optimize_segment_altitude_enu with vectorised assembly and LAPACK's banded Cholesky (O(n) per solve): the same
+    systems and the same active-set loop, entries summed in a different order (last-bit differences).  Checked against
+    the statement-by-statement version in tests/test_alt_oracle.py; used where n is in the thousands."""
+    from scipy.linalg import solveh_banded
+
+    seg = np.asarray(segment_enu, dtype=np.float64)
+    elev = np.asarray(elev, dtype=np.float64)
+    n = seg.shape[0]
+    if n == 0:
+        return None
+    has = ~np.isnan(elev)
+    w1 = _climb_weights(seg, p.max_climb_rate) if n > 1 else np.zeros(0)
+    tgt = np.where(has, np.maximum(seg[:, 2], elev + p.safe_distance), 0.0)
+    z1 = solveh_banded(_band(n, p.lambda_smooth, w1, np.where(has, p.lambda_follow, 0.0)),
+                       np.where(has, p.lambda_follow * tgt, 0.0), lower=True)
+    z1 = np.where(has, np.maximum(z1, elev + p.safe_distance), z1)
+    w2 = _climb_weights(seg, p.max_climb_rate * 0.5) if n > 1 else np.zeros(0)
+    act = np.zeros(n, dtype=bool)
+    cur = z1.copy()
+    solves = 0
+    for _ in range(10):
+        extra = np.zeros(n)
+        extra[1:n - 1] = np.where(act[1:n - 1], 1e8, 0.0)
+        extra[0] += 1e10
+        extra[n - 1] += 1e10
+        cur = solveh_banded(_band(n, p.lambda_smooth * 10.0, w2, extra), extra * z1, lower=True)
+        solves += 1
+        new = (cur < z1 - 1e-3) & ~act
+        act |= new
+        if not new.any():
+            break
+    z2 = np.maximum(cur, z1)
+    return (z2, z1, solves, act) if return_info else z2

@@ -30,48 +30,16 @@ def workload(B, seed=4):
     return rows, off, elev
 
 
-def cpu_banded(rows, off, elev, p, n_traj, check=None):
-    """The same two passes per trajectory with LAPACK's banded Cholesky (scipy solveh_banded): an O(n) CPU stand-in for
-    the reference's Eigen::SimplicialLDLT loop (cpp:1575-1827).  Returns seconds for n_traj trajectories."""
-    from scipy.linalg import solveh_banded
-
-    def band(n, s, w, extra):
-        ab = np.zeros((3, n))                      # lower form: ab[0] diagonal, ab[1] first, ab[2] second sub-diagonal
-        if n >= 3 and s > 0:
-            inner = np.zeros(n + 2)                # inner[i + 1] = 1 if row i is an interior row
-            inner[2:n] = 1.0
-            ab[0] += s * (inner[2:] + 4.0 * inner[1:-1] + inner[:-2])
-            ab[1, :n - 1] += s * -2.0 * (inner[1:n] + inner[2:n + 1])
-            ab[2, :n - 2] += s * inner[2:n]
-        ab[0, :n - 1] += w
-        ab[0, 1:] += w
-        ab[1, :n - 1] -= w
-        ab[0] += extra + 1e-8
-        return ab
+def cpu_banded(rows, off, elev, p, n_traj):
+    """The same two passes per trajectory with LAPACK's banded Cholesky (oracle/alt_oracle.py,
+    optimize_segment_altitude_enu_banded): an O(n) CPU stand-in for the reference's Eigen::SimplicialLDLT loop
+    (cpp:1575-1827).  Returns seconds for n_traj trajectories."""
+    from oracle import alt_oracle as ao
 
     t0 = time.perf_counter()
     for b in range(n_traj):
         sl = slice(int(off[b]), int(off[b + 1]))
-        r, el = rows[sl], elev[sl]
-        n = r.shape[0]
-        dist = np.hypot(np.diff(r[:, 0]), np.diff(r[:, 1]))
-        w1 = np.where(dist > 1e-9, 1.0 / np.maximum(dist * p.max_climb_rate, 1e-300) ** 2, 0.0)
-        w2 = np.where(dist > 1e-9, 1.0 / np.maximum(dist * p.max_climb_rate * 0.5, 1e-300) ** 2, 0.0)
-        tgt = np.maximum(r[:, 2], el + p.safe_distance)
-        z1 = solveh_banded(band(n, p.lambda_smooth, w1, np.full(n, p.lambda_follow)), p.lambda_follow * tgt, lower=True)
-        z1 = np.maximum(z1, el + p.safe_distance)
-        act = np.zeros(n, dtype=bool)
-        for _ in range(10):
-            extra = np.where(act, 1e8, 0.0)
-            extra[0] = extra[-1] = 1e10            # end rows: fixed, never "active" (cpp:1779-1790)
-            rhs = extra * z1
-            z = solveh_banded(band(n, p.lambda_smooth * 10.0, w2, extra), rhs, lower=True)
-            new = (z < z1 - 1e-3) & ~act
-            act |= new
-            if not new.any():
-                break
-        if check is not None:
-            check.append(np.maximum(z, z1))
+        ao.optimize_segment_altitude_enu_banded(rows[sl], p, elev[sl])
     return time.perf_counter() - t0
 
 

@@ -94,3 +94,16 @@ def test_no_terrain_keeps_a_straight_profile():
     seg = np.column_stack([np.arange(40) * 25.0, np.zeros(40), np.linspace(1000.0, 1100.0, 40)])
     z = ao.optimize_segment_altitude_enu(seg, ao.shipped_params(), np.full(40, np.nan))
     assert np.all(np.isfinite(z))
+
+
+def test_banded_variant_equals_the_statement_by_statement_port():
+    grid, res, ox, oy = terrain_grid()
+    rows, off = sampled_paths(24, seed=12, n_min=1, n_max=120)
+    for p in (ao.shipped_params(), ao.AltitudeParams()):
+        for b in range(24):
+            seg = rows[off[b]:off[b + 1]]
+            elev = lookup(grid, res, ox, oy, seg)
+            a = ao.optimize_segment_altitude_enu(seg, p, elev, return_info=True)
+            c = ao.optimize_segment_altitude_enu_banded(seg, p, elev, return_info=True)
+            assert a[2] == c[2] and np.array_equal(a[3], c[3])           # solves, active set
+            assert np.abs(a[1] - c[1]).max() <= 1e-7 and np.abs(a[0] - c[0]).max() <= 1e-7

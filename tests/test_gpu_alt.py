@@ -190,3 +190,26 @@ def test_lane_pairs_equal_one_lane(tool):
     assert not out[0][3].any() and not out[1][3].any()
     assert np.abs(out[0][1] - out[1][1]).max() <= 1e-6                # pass 1 (rows outside the map are weakly held)
     assert np.abs(out[0][0][:, 2] - out[1][0][:, 2]).max() <= 1e-6   # final heights
+
+
+def test_long_trajectories_many_chunks(alt_tool):
+    """Thousands of rows per trajectory (dozens of 32-row chunks per sweep, both sides of a pair), lengths chosen around
+    chunk boundaries; checker: the O(n) banded-Cholesky variant of the port."""
+    tool = alt_tool
+    rng = np.random.default_rng(31)
+    ns = np.array([3000, 1537, 64, 65, 63, 33, 32, 31, 2049, 1000])
+    off = np.concatenate([[0], np.cumsum(ns)]).astype(np.int64)
+    n = int(off[-1])
+    t = np.arange(n) - np.repeat(off[:-1], ns)
+    rows = np.column_stack([t * 25.0 + rng.normal(0, 2.0, n), np.repeat(rng.uniform(-500, 500, len(ns)), ns) + rng.normal(0, 2.0, n),
+                            1300.0 + 60.0 * np.sin(t / 37.0)])
+    elev = 1260.0 + 70.0 * np.sin(rows[:, 0] / 900.0) + 25.0 * np.sin(rows[:, 0] / 130.0)
+    p = shipped_altitude_params()
+    out, z1, solves, flags = tool.altitude_optimize_batch(rows, off, p, elev, return_info=True)
+    assert not flags.any()
+    for b in range(len(ns)):
+        sl = slice(int(off[b]), int(off[b + 1]))
+        z2_o, z1_o, solves_o, _ = ao.optimize_segment_altitude_enu_banded(rows[sl], oracle_params(p), elev[sl], return_info=True)
+        assert np.abs(z1[sl] - z1_o).max() <= Z_TOL, b
+        assert solves[b] == solves_o, b
+        assert np.abs(out[sl, 2] - z2_o).max() <= Z_TOL, b

@@ -554,6 +554,14 @@ inline unsigned geo_grid(const msnap_context *h, long long n) {  // grid-stride 
     return (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
 }
 
+int launch_wgs84_to_enu(msnap_context *h, const GeoFrame &f, long long n, const double *lla, double *enu) {
+    if (h->geo_trig)
+        MS_LAUNCH(h, k_wgs84_to_enu<true>, geo_grid(h, n), GEO_BLOCK, f, n, lla, enu);
+    else
+        MS_LAUNCH(h, k_wgs84_to_enu<false>, geo_grid(h, n), GEO_BLOCK, f, n, lla, enu);
+    return MSNAP_OK;
+}
+
 int launch_enu_to_wgs84(msnap_context *h, const GeoFrame &f, long long n_cap, const long long *n_dev, const double *enu,
                         double *lla, int *steps) {
     if (h->geo_trig)
@@ -591,7 +599,8 @@ int generate_dev(msnap_context *h, const msnap_config *cfg, double sd, double v_
     if (rc) return rc;
     if (h->wp_frame) {  // the waypoints arrive as WGS84 rows: wgs84ToENU_Batch (cpp:2640) into the workspace first
         double *enu = arena_take<double>(h->ws, n_pts * 3);
-        MS_LAUNCH(h, k_wgs84_to_enu, geo_grid(h, (long long)n_pts), GEO_BLOCK, h->wp_geo, (long long)n_pts, wp, enu);
+        rc = launch_wgs84_to_enu(h, h->wp_geo, (long long)n_pts, wp, enu);
+        if (rc) return rc;
         wp = enu;
     }
     if (ragged) {  // segment -> trajectory map, so that the per-segment kernels need no binary search
@@ -1286,8 +1295,7 @@ int msnap_wgs84_to_enu_dev(msnap_handle h, const double *reference_lla, long lon
     DeviceGuard guard(h->device);
     GeoFrame f;
     geo_make_frame(reference_lla, f);
-    MS_LAUNCH(h, k_wgs84_to_enu, geo_grid(h, n), GEO_BLOCK, f, n, lla, enu_out);
-    return MSNAP_OK;
+    return launch_wgs84_to_enu(h, f, n, lla, enu_out);
 }
 
 // Host rows in, host rows out: the batch is cut into pieces that alternate between the handle's two streams, so that a
@@ -1314,8 +1322,10 @@ static int geo_host(msnap_handle h, const double *reference_lla, long long n, co
             if (to_wgs) {
                 const int rc2 = launch_enu_to_wgs84(h, f, m, nullptr, d + 3 * r0, d + 3 * r0, nullptr);
                 if (rc2) return rc2;
-            } else
-                MS_LAUNCH(h, k_wgs84_to_enu, geo_grid(h, m), GEO_BLOCK, f, m, d + 3 * r0, d + 3 * r0);
+            } else {
+                const int rc2 = launch_wgs84_to_enu(h, f, m, d + 3 * r0, d + 3 * r0);
+                if (rc2) return rc2;
+            }
             MS_CUDA(h, cudaMemcpyAsync(out + 3 * r0, d + 3 * r0, (size_t)m * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
             return MSNAP_OK;
         }();
@@ -1480,7 +1490,8 @@ int msnap_sample_bound_dev(msnap_handle h, const msnap_config *cfg, double v_avg
         rc = arena_reserve(h, h->ws, padded((size_t)n_pts * 3 * sizeof(double)));
         if (rc) return rc;
         double *enu = arena_take<double>(h->ws, (size_t)n_pts * 3);
-        MS_LAUNCH(h, k_wgs84_to_enu, geo_grid(h, n_pts), GEO_BLOCK, h->wp_geo, n_pts, waypoints, enu);
+        rc = launch_wgs84_to_enu(h, h->wp_geo, n_pts, waypoints, enu);
+        if (rc) return rc;
         waypoints = enu;
     }
     MS_LAUNCH(h, k_bound, grid_for(n_seg, 256), 256, bi, waypoints, va, cfg->min_time_s,

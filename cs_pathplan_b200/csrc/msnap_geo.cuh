@@ -30,6 +30,7 @@
 #include <cmath>
 
 #include "msnap_geo_atan.h"
+#include "msnap_geo_sincos.h"
 
 namespace msnap {
 
@@ -168,6 +169,36 @@ __device__ __forceinline__ double geo_atan2(double y, double x) {
     if (mx == 0.0) a = 0.0;
     return copysign(a, y);
 }
+// sin and cos of an angle in radians as it comes out of deg2rad (|x| of a few): Cody-Waite reduction by pi/2 in three
+// pieces (k * piece exact for |k| < 2^20), then the two polynomials of msnap_geo_sincos.h on |r| <= pi/4 and the
+// quadrant fix-up; ~1 ulp.  Far outside that range (|x| > 1e5, or NaN) libm's sincos with its full reduction takes over.
+__constant__ double GEO_SIN_C[GEO_SIN_N] = GEO_SIN_COEFFS;
+__constant__ double GEO_COS_C[GEO_COS_N] = GEO_COS_COEFFS;
+__device__ __forceinline__ void geo_sincos(double x, double &sn_out, double &cs_out) {
+    if (!(fabs(x) <= 1.0e5)) {
+        sincos(x, &sn_out, &cs_out);
+        return;
+    }
+    const double kf = rint(x * 0.63661977236758134308);  // 2 / pi
+    const int k = (int)kf;
+    double r = fma(-kf, GEO_PIO2_1, x);
+    r = fma(-kf, GEO_PIO2_2, r);
+    r = fma(-kf, GEO_PIO2_3, r);
+    const double u = r * r;
+    double ps = GEO_SIN_C[GEO_SIN_N - 1], pc = GEO_COS_C[GEO_COS_N - 1];
+#pragma unroll
+    for (int i = GEO_SIN_N - 2; i >= 0; --i) ps = fma(ps, u, GEO_SIN_C[i]);
+#pragma unroll
+    for (int i = GEO_COS_N - 2; i >= 0; --i) pc = fma(pc, u, GEO_COS_C[i]);
+    const double sn = fma(r * u, ps, r), cs = fma(u * u, pc, fma(-0.5, u, 1.0));
+    // x = r + k pi/2:  k mod 4 = 0: (sn, cs)   1: (cs, -sn)   2: (-sn, -cs)   3: (-cs, sn)
+    double s = (k & 1) ? cs : sn, c = (k & 1) ? sn : cs;
+    if (k & 2) s = -s;
+    if ((k + 1) & 2) c = -c;
+    sn_out = s;
+    cs_out = c;
+}
+
 __device__ __forceinline__ double geo_rad2deg(double rad) {  // (rad * 180) / pi, hpp:171-173, division by residual fix-up
     constexpr double INV_PI = 0.318309886183790671538;
     const double n = rad * 180.0, q = n * INV_PI;
@@ -280,6 +311,9 @@ __global__ void __launch_bounds__(GEO_BLOCK) k_enu_to_wgs84(GeoFrame f, long lon
 }
 
 // wgs84ToENU_Batch (cpp:1085-1095): rows [lon_deg, lat_deg, alt_m] -> rows [east, north, up].
+// TRIG = true: libm sincos and the reference's a / sqrt(..) (msnap_set_geo_exact_trig); false (default): geo_sincos and
+// a * rsqrt(..), ~1 ulp each (1e-9 m).
+template <bool TRIG>
 __global__ void __launch_bounds__(GEO_BLOCK) k_wgs84_to_enu(GeoFrame f, long long n, const double *lla, double *enu) {
     __shared__ double sm_all[GEO_BLOCK / 32][96];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -294,9 +328,16 @@ __global__ void __launch_bounds__(GEO_BLOCK) k_wgs84_to_enu(GeoFrame f, long lon
         // wgs84ToECEF (cpp:894-910)
         const double lat_rad = lat_deg * GEO_PI / 180.0, lon_rad = lon_deg * GEO_PI / 180.0;
         double sin_lat, cos_lat, sin_lon, cos_lon;
-        sincos(lat_rad, &sin_lat, &cos_lat);
-        sincos(lon_rad, &sin_lon, &cos_lon);
-        const double N = geo_calcN(sin_lat);
+        double N;
+        if (TRIG) {
+            sincos(lat_rad, &sin_lat, &cos_lat);
+            sincos(lon_rad, &sin_lon, &cos_lon);
+            N = geo_calcN(sin_lat);
+        } else {
+            geo_sincos(lat_rad, sin_lat, cos_lat);
+            geo_sincos(lon_rad, sin_lon, cos_lon);
+            N = GEO_A * geo_rsqrt(fma(-GEO_E2 * sin_lat, sin_lat, 1.0));
+        }
         const double x = (N + h) * cos_lat * cos_lon;
         const double y = (N + h) * cos_lat * sin_lon;
         const double z = (N * (1 - GEO_E2) + h) * sin_lat;

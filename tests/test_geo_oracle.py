@@ -96,3 +96,26 @@ def test_generated_atan_header_is_current():
     out = subprocess.run([sys.executable, os.path.join(root, "cs_pathplan_b200", "csrc", "gen_geo_atan.py")],
                          capture_output=True, text=True, check=True).stdout
     assert out == open(os.path.join(root, "cs_pathplan_b200", "csrc", "msnap_geo_atan.h")).read()
+
+
+def test_device_sincos_on_the_host(tmp_path):
+    """geo_sincos (msnap_geo.cuh) restated on the host with the same generated constants and fma sequence
+    (tests/cpp/geo_sincos_host.cpp): within 2 units of 2^-53 of libm's sinl / cosl on [-7, 7] and up to |x| = 1e5."""
+    import subprocess
+
+    root = os.path.dirname(HERE)
+    exe = str(tmp_path / "geo_sincos_host")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-mfma", "-I", os.path.join(root, "cs_pathplan_b200", "csrc"),
+                           os.path.join(HERE, "cpp", "geo_sincos_host.cpp"), "-o", exe])
+    worst = float(subprocess.run([exe], capture_output=True, text=True, check=True).stdout)
+    assert worst <= 2.5
+
+
+def test_generated_sincos_header_is_current():
+    import subprocess
+    import sys
+
+    root = os.path.dirname(HERE)
+    out = subprocess.run([sys.executable, os.path.join(root, "cs_pathplan_b200", "csrc", "gen_geo_sincos.py")],
+                         capture_output=True, text=True, check=True).stdout
+    assert out == open(os.path.join(root, "cs_pathplan_b200", "csrc", "msnap_geo_sincos.h")).read()

@@ -199,6 +199,11 @@ __device__ __forceinline__ void geo_sincos(double x, double &sn_out, double &cs_
     cs_out = c;
 }
 
+__device__ __forceinline__ double geo_deg2rad(double deg) {  // (deg * pi) / 180, hpp:166-168, division by residual fix-up
+    constexpr double INV_180 = 1.0 / 180.0;
+    const double n = deg * GEO_PI, q = n * INV_180;
+    return fma(fma(-q, 180.0, n), INV_180, q);
+}
 __device__ __forceinline__ double geo_rad2deg(double rad) {  // (rad * 180) / pi, hpp:171-173, division by residual fix-up
     constexpr double INV_PI = 0.318309886183790671538;
     const double n = rad * 180.0, q = n * INV_PI;
@@ -326,7 +331,8 @@ __global__ void __launch_bounds__(GEO_BLOCK) k_wgs84_to_enu(GeoFrame f, long lon
         next = geo_rows_fetch(lla, row0 + warps * 32, n, lane);
         const double lon_deg = sm[3 * lane], lat_deg = sm[3 * lane + 1], h = sm[3 * lane + 2];
         // wgs84ToECEF (cpp:894-910)
-        const double lat_rad = lat_deg * GEO_PI / 180.0, lon_rad = lon_deg * GEO_PI / 180.0;
+        const double lat_rad = TRIG ? lat_deg * GEO_PI / 180.0 : geo_deg2rad(lat_deg);
+        const double lon_rad = TRIG ? lon_deg * GEO_PI / 180.0 : geo_deg2rad(lon_deg);
         double sin_lat, cos_lat, sin_lon, cos_lon;
         double N;
         if (TRIG) {

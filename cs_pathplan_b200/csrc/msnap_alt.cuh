@@ -63,24 +63,20 @@ __global__ void __launch_bounds__(256) k_cost_lookup(const float *__restrict__ g
     }
 }
 
-// Row-parallel preparation: w1 / w2 = climb weight of the edge (g, g + 1) in pass 1 / pass 2 (0 for the last row of a
-// trajectory and for skipped edges), tgt = follow target of pass 1 (NaN where the map has no value).
+// Row-parallel preparation: w1 / w2 = climb weight of the edge (g, g + 1) in pass 1 / pass 2 (0 for skipped edges), tgt =
+// follow target of pass 1 (NaN where the map has no value), act = 0.  Every row is treated as if its successor belonged to
+// the same trajectory; k_alt_ends (one thread per trajectory, launched right after) zeroes the weights of each
+// trajectory's last row, so no row has to search for its trajectory.
 __global__ void __launch_bounds__(256) k_alt_prep(AltParams p, long long B, const long long *__restrict__ row_offset,
                                                   const double *__restrict__ rows, const double *__restrict__ elev,
                                                   double *__restrict__ w1, double *__restrict__ w2, double *__restrict__ tgt,
                                                   double *__restrict__ act) {
     const long long n = row_offset[B];
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += (long long)gridDim.x * blockDim.x) {
-        long long lo = 0, hi = B;  // trajectory of row g: largest b with row_offset[b] <= g
-        while (hi - lo > 1) {
-            const long long mid = (lo + hi) >> 1;
-            if (row_offset[mid] <= g) lo = mid;
-            else hi = mid;
-        }
-        const bool last = g + 1 >= row_offset[lo + 1];
+        const double x0 = rows[3 * g], y0 = rows[3 * g + 1], up = rows[3 * g + 2];
         double a1 = 0.0, a2 = 0.0;
-        if (!last) {
-            const double dist = hypot(rows[3 * (g + 1)] - rows[3 * g], rows[3 * (g + 1) + 1] - rows[3 * g + 1]);
+        if (g + 1 < n) {
+            const double dist = hypot(rows[3 * (g + 1)] - x0, rows[3 * (g + 1) + 1] - y0);
             if (dist > 1e-9) {  // cpp:1655, 1765
                 const double d1 = dist * p.max_climb_rate, d2 = dist * (p.max_climb_rate * 0.5);
                 if (p.max_climb_rate > 0.0 && d1 > 1e-12) a1 = 1.0 / (d1 * d1);
@@ -91,7 +87,17 @@ __global__ void __launch_bounds__(256) k_alt_prep(AltParams p, long long B, cons
         w2[g] = a2;
         act[g] = 0.0;
         const double el = elev ? elev[g] : NAN;
-        tgt[g] = el == el ? fmax(rows[3 * g + 2], el + p.safe_distance) : NAN;  // cpp:1637-1638
+        tgt[g] = el == el ? fmax(up, el + p.safe_distance) : NAN;  // cpp:1637-1638
+    }
+}
+__global__ void __launch_bounds__(256) k_alt_ends(long long B, const long long *__restrict__ row_offset, double *__restrict__ w1,
+                                                  double *__restrict__ w2) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const long long first = row_offset[b], end = row_offset[b + 1];
+    if (end > first) {  // the last row of a trajectory has no edge to a successor
+        w1[end - 1] = 0.0;
+        w2[end - 1] = 0.0;
     }
 }
 

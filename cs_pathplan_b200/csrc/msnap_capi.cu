@@ -1407,6 +1407,7 @@ int msnap_altitude_optimize_batch_dev(msnap_handle h, const msnap_altitude_param
                       params->safe_distance};
     const long long want = (n_rows_cap + 255) / 256, cap = (long long)h->sm_count * 8;
     MS_LAUNCH(h, k_alt_prep, (unsigned)(want < cap ? want : cap), 256, p, B, row_offset, rows_inout, elev, w1, w2, tgt, act);
+    MS_LAUNCH(h, k_alt_ends, grid_for(B, 256), 256, B, row_offset, w1, w2);
     if (!h->alt_smem_opted) {  // > 48 KB of dynamic shared memory needs the opt-in (per device; once per handle)
         MS_CUDA(h, cudaFuncSetAttribute(k_alt_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ALT_SMEM_BYTES));
         MS_CUDA(h, cudaFuncSetAttribute(k_alt_solve_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ALT_SMEM_BYTES));

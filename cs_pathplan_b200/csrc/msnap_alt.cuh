@@ -371,9 +371,11 @@ __device__ __forceinline__ void alt_sweep_pair(double *sm, const double *const (
         if (DESC) {
             q = mine + dir * (cnt - 1);
             int k = S.row(i0 + cnt - 1);
+#pragma unroll 4
             for (int j = cnt - 1; j >= 0; --j, q -= dir, k -= dir) row(i0 + j, k, j, T);
         } else {
             int k = S.row(i0);
+#pragma unroll 4
             for (int j = 0; j < cnt; ++j, q += dir, k += dir) row(i0 + j, k, j, T);
         }
         __syncwarp();

@@ -60,7 +60,13 @@ def _lib(fast: bool = False):
     if name not in _LIBS:
         path = os.path.join(_HERE, "_ref", name)
         if not os.path.exists(path):
-            raise RuntimeError(f"{path} is missing: run `make -C oracle`")
+            # geo_port.c needs nothing but gcc: build it where it is missing (e.g. a box that received the sources only)
+            import subprocess
+
+            try:
+                subprocess.check_call(["make", "-C", _HERE, "port"], stdout=subprocess.DEVNULL)
+            except Exception as e:
+                raise RuntimeError(f"{path} is missing and `make -C oracle port` failed: {e}")
         L = C.CDLL(path)
         L.geo_port_wgs84_to_enu_batch.argtypes = [C.c_longlong, _dp, _dp, _dp, C.c_int]
         L.geo_port_wgs84_to_enu_batch.restype = None

@@ -157,7 +157,7 @@ __device__ __forceinline__ double geo_atan2(double y, double x) {
     const double ax = fabs(x), ay = fabs(y);
     const bool sw = ay > ax, xneg = x < 0.0;
     const double mx = sw ? ay : ax, mn = sw ? ax : ay;
-    const double t = geo_div(mn, mx), u = t * t;
+    const double t = mn * geo_rcp(mx), u = t * t;  // <= 1.5 ulp: plenty for a result that is rounded to ~1 ulp of pi anyway
     double pl = GEO_ATAN_C[GEO_ATAN_N - 1];
 #pragma unroll
     for (int i = GEO_ATAN_N - 2; i >= 0; --i) pl = fma(pl, u, GEO_ATAN_C[i]);  // DFMA with a constant-bank operand
@@ -222,11 +222,13 @@ __device__ __forceinline__ int geo_ecef_to_wgs84_fast(double x, double y, double
     double S = z + E2A * (st * st * st);            // z + e2 a (1-e2) sin^3 / (1-e2), cpp:931
     double C = fma(-E2A, ct * ct * ct, p);          // p - e2 a cos^3,                  cpp:932
     int steps = 0;
+    const double zs = z * SCALE, ps = p * SCALE;  // the per-step rescaling by 2^-23 folded into the constants (exact)
+    constexpr double E2AS = E2A * SCALE;
 #pragma unroll
     for (int i = 0; i < GEO_MAX_STEPS; ++i) {
         const double q = fma(C, C, OME2 * S * S);
         const double W = q * geo_rsqrt(q);
-        const double Sn = z * W * SCALE, Cn = fma(p, W, -E2A * C) * SCALE;
+        const double Sn = zs * W, Cn = fma(ps, W, -E2AS * C);
         const double cross = fma(Sn, C, -(Cn * S)), dot = fma(Sn, S, Cn * C);
         const bool done = fabs(cross) < GEO_TOL * dot;
         S = Sn;

@@ -19,10 +19,11 @@
 // SPD pentadiagonal, so here each trajectory runs a banded LDL' recurrence (half-bandwidth 2) in natural order: same
 // system, same solution, different rounding (compare DESIGN.md section 10 for the bar).
 //
-// Work decomposition: k_alt_prep is row-parallel (edge weights of both passes and the follow target: hypot, two divisions
-// per row, off the recurrences); k_alt_solve runs one trajectory per lane through pass 1 and the whole active-set loop --
-// a dependent chain of n steps per solve (one reciprocal and ~14 multiply-adds per row forward, 2 per row backward), so
-// the kernel is latency-bound and is launched with one warp per CTA to spread the chains over all SMs; k_alt_finish
+// Work decomposition: k_alt_prep + k_alt_ends are row- / trajectory-parallel (edge weights of both passes and the follow
+// target: hypot, two divisions per row, off the recurrences); k_alt_solve_pair (default: a lane pair per trajectory,
+// two-sided elimination) or k_alt_solve (one lane per trajectory) runs pass 1 and the whole active-set loop -- dependent
+// chains of n (or n/2) steps per solve, one reciprocal and ~14 multiply-adds per row forward, 2 per row backward -- so the
+// kernels are latency-bound and are launched with one warp per CTA to spread the chains over all SMs; k_alt_finish
 // (row-parallel) writes the heights back into the rows.
 #ifndef MSNAP_ALT_CUH
 #define MSNAP_ALT_CUH

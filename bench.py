@@ -7,7 +7,9 @@ shipped penalty weights (path_weight 1e-7, vel_zero_weight 0.01) so that every r
 allocation, pass-1 solve, worst-deviation search, penalised solve, the 10-step reweighting loop, coefficient
 recovery and the distance-thresholded sampler.  A "step" is one full GenerateTrajectoryMatrix pass over one batch.
 The plain-weights variant (path_weight = vel_zero_weight = 0: one solve, HBM-bound) is measured as well and reported
-under "variants".
+under "variants".  Two more objects describe the same step widened into the neighbouring stages of getPlan (SURVEY.md
+section 8f): "wgs84_frame" (the sampled rows leave as WGS84 lon/lat/alt) and "leader_chain" (WGS84 waypoints -> ENU ->
+minimum snap -> samples -> cost-map lookup -> altitude optimisation -> WGS84 rows, all on the device).
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
     python bench.py --impl reference [--steps K] [--warmup W]      # the reference's own CPU code (oracle/_ref)

@@ -25,7 +25,7 @@
 // (out == in); the next trip's rows are fetched into registers before the current trip's arithmetic.  ENU -> WGS84 is
 // bound by the FP64 pipe, not by HBM (measured, B200: statement-by-statement form 1 950 issued instructions per row at
 // the usual 4 fixed-point steps -- 7 atan2, 6 sincos, 6 sqrt, ~13 divisions -- 15 G rows/s; direction form ~430 issued,
-// ~230 of them FP64, 54 G rows/s = 40 % of the HBM peak); WGS84 -> ENU runs at 75 % of the HBM peak (102 G rows/s) with the
+// ~230 of them FP64, 54 G rows/s = 40 % of the HBM peak); WGS84 -> ENU runs at 77 % of the HBM peak (106 G rows/s) with the
 // in-kernel sincos.  48 bytes of traffic per row either way.
 #ifndef MSNAP_GEO_CUH
 #define MSNAP_GEO_CUH
@@ -194,12 +194,10 @@ __device__ __forceinline__ void geo_sincos(double x, double &sn_out, double &cs_
 #pragma unroll
     for (int i = GEO_COS_N - 2; i >= 0; --i) pc = fma(pc, u, GEO_COS_C[i]);
     const double sn = fma(r * u, ps, r), cs = fma(u * u, pc, fma(-0.5, u, 1.0));
-    // x = r + k pi/2:  k mod 4 = 0: (sn, cs)   1: (cs, -sn)   2: (-sn, -cs)   3: (-cs, sn)
-    double s = (k & 1) ? cs : sn, c = (k & 1) ? sn : cs;
-    if (k & 2) s = -s;
-    if ((k + 1) & 2) c = -c;
-    sn_out = s;
-    cs_out = c;
+    // x = r + k pi/2:  k mod 4 = 0: (sn, cs)   1: (cs, -sn)   2: (-sn, -cs)   3: (-cs, sn); signs flipped in the sign bit
+    const double s = (k & 1) ? cs : sn, c = (k & 1) ? sn : cs;
+    sn_out = __hiloint2double(__double2hiint(s) ^ ((k & 2) << 30), __double2loint(s));
+    cs_out = __hiloint2double(__double2hiint(c) ^ (((k + 1) & 2) << 30), __double2loint(c));
 }
 
 __device__ __forceinline__ double geo_deg2rad(double deg) {  // (deg * pi) / 180, hpp:166-168, division by residual fix-up
@@ -355,9 +353,15 @@ __global__ void __launch_bounds__(GEO_BLOCK) k_wgs84_to_enu(GeoFrame f, long lon
         // delta (cpp:1053-1056) and ecefToENU (cpp:1023-1032)
         const double dx = x - f.ref_ecef[0], dy = y - f.ref_ecef[1], dz = z - f.ref_ecef[2];
         __syncwarp();
-        sm[3 * lane] = f.R[0] * dx + f.R[1] * dy + f.R[2] * dz;
-        sm[3 * lane + 1] = f.R[3] * dx + f.R[4] * dy + f.R[5] * dz;
-        sm[3 * lane + 2] = f.R[6] * dx + f.R[7] * dy + f.R[8] * dz;
+        if (TRIG) {  // the reference's unfused products and sums (cpp:1028-1030)
+            sm[3 * lane] = f.R[0] * dx + f.R[1] * dy + f.R[2] * dz;
+            sm[3 * lane + 1] = f.R[3] * dx + f.R[4] * dy + f.R[5] * dz;
+            sm[3 * lane + 2] = f.R[6] * dx + f.R[7] * dy + f.R[8] * dz;
+        } else {
+            sm[3 * lane] = fma(f.R[2], dz, fma(f.R[1], dy, f.R[0] * dx));
+            sm[3 * lane + 1] = fma(f.R[5], dz, fma(f.R[4], dy, f.R[3] * dx));
+            sm[3 * lane + 2] = fma(f.R[8], dz, fma(f.R[7], dy, f.R[6] * dx));
+        }
         geo_rows_out(enu, row0, n, sm, lane);
     }
 }

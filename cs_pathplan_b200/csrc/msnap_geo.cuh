@@ -25,7 +25,7 @@
 // (out == in); the next trip's rows are fetched into registers before the current trip's arithmetic.  ENU -> WGS84 is
 // bound by the FP64 pipe, not by HBM (measured, B200: statement-by-statement form 1 950 issued instructions per row at
 // the usual 4 fixed-point steps -- 7 atan2, 6 sincos, 6 sqrt, ~13 divisions -- 15 G rows/s; direction form ~430 issued,
-// ~230 of them FP64, 54 G rows/s = 40 % of the HBM peak); WGS84 -> ENU runs at 77 % of the HBM peak (106 G rows/s) with the
+// ~225 of them FP64, 56 G rows/s = 41 % of the HBM peak); WGS84 -> ENU runs at 77 % of the HBM peak (106 G rows/s) with the
 // in-kernel sincos.  48 bytes of traffic per row either way.
 #ifndef MSNAP_GEO_CUH
 #define MSNAP_GEO_CUH
@@ -217,7 +217,7 @@ __device__ __forceinline__ int geo_ecef_to_wgs84_fast(double x, double y, double
     const double p2 = fma(x, x, y * y);
     const double p = p2 > 0.0 ? geo_sqrt_pos(p2, geo_rsqrt(p2)) : 0.0;
     // theta = atan2(z a, p a (1 - e2)): only sin(theta), cos(theta) are used (cpp:929-932)
-    const double u = z * GEO_A, v = p * GEO_A * OME2;
+    const double u = z, v = p * OME2;  // the common factor a of both arguments does not change the direction
     const double ih = geo_rsqrt(fma(u, u, v * v));
     const double st = u * ih, ct = v * ih;
     double S = z + E2A * (st * st * st);            // z + e2 a (1-e2) sin^3 / (1-e2), cpp:931
@@ -303,11 +303,18 @@ __global__ void __launch_bounds__(GEO_BLOCK) k_enu_to_wgs84(GeoFrame f, long lon
         next = geo_rows_fetch(enu, row0 + warps * 32, n, lane);
         const double e = sm[3 * lane], no = sm[3 * lane + 1], u = sm[3 * lane + 2];
         // enuToECEF (cpp:1035-1044) and the shift by the reference point (cpp:1076-1079)
-        const double dx = f.Rinv[0] * e + f.Rinv[1] * no + f.Rinv[2] * u;
-        const double dy = f.Rinv[3] * e + f.Rinv[4] * no + f.Rinv[5] * u;
-        const double dz = f.Rinv[6] * e + f.Rinv[7] * no + f.Rinv[8] * u;
+        double X, Y, Z;
+        if (TRIG) {  // the reference's unfused products and sums
+            const double dx = f.Rinv[0] * e + f.Rinv[1] * no + f.Rinv[2] * u;
+            const double dy = f.Rinv[3] * e + f.Rinv[4] * no + f.Rinv[5] * u;
+            const double dz = f.Rinv[6] * e + f.Rinv[7] * no + f.Rinv[8] * u;
+            X = f.ref_ecef[0] + dx, Y = f.ref_ecef[1] + dy, Z = f.ref_ecef[2] + dz;
+        } else {
+            X = f.ref_ecef[0] + fma(f.Rinv[2], u, fma(f.Rinv[1], no, f.Rinv[0] * e));  // small terms first, then the shift
+            Y = f.ref_ecef[1] + fma(f.Rinv[5], u, fma(f.Rinv[4], no, f.Rinv[3] * e));
+            Z = f.ref_ecef[2] + fma(f.Rinv[8], u, fma(f.Rinv[7], no, f.Rinv[6] * e));
+        }
         double lon, lat, alt;
-        const double X = f.ref_ecef[0] + dx, Y = f.ref_ecef[1] + dy, Z = f.ref_ecef[2] + dz;
         const int steps = TRIG ? geo_ecef_to_wgs84(X, Y, Z, lon, lat, alt) : geo_ecef_to_wgs84_fast(X, Y, Z, lon, lat, alt);
         __syncwarp();
         sm[3 * lane] = lon;

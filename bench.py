@@ -13,6 +13,7 @@ minimum snap -> samples -> cost-map lookup -> altitude optimisation -> WGS84 row
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
     python bench.py --impl reference [--steps K] [--warmup W]      # the reference's own CPU code (oracle/_ref)
+    python bench.py --impl rows-cpu                                # CPU baselines of the section-8f stages (oracle ports)
 
 Prints ONE JSON line (rank 0).  See the task contract for the keys; numbers are never taken under a profiler.
 """
@@ -42,7 +43,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "rows-cpu"])
     ap.add_argument("--weights", default="shipped", choices=["shipped", "plain"])
     ap.add_argument("--batch", type=int, default=B_DEFAULT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -168,6 +169,39 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def run_rows_cpu(args):
+    """CPU baselines of the two neighbouring stages, timed on this host's cores on bounded samples:
+    the C port of the WGS84 <-> ENU transforms (oracle/geo_port.c, -O3, 1 thread and OpenMP over rows) and a banded-
+    Cholesky stand-in for the altitude optimiser's per-trajectory SimplicialLDLT loop (oracle/alt_oracle.py, 1 thread).
+    Reported beside scripts/geo_bench.py and scripts/alt_bench.py; not a target."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from cs_pathplan_b200 import workloads
+    from oracle import alt_oracle as ao
+    from oracle import geo
+
+    cores = os.cpu_count() or 1
+    ref = np.array([109.56059880227296, 40.86719901015758, 0.0])
+    enu = workloads.enu_rows(2_000_000)
+    out = {"impl": "rows-cpu", "cores": cores, "geo": {"sample_rows": enu.shape[0], "kind": "port (oracle/geo_port.c, -O3)"}}
+    lla = geo.enu_to_wgs84_batch(enu, ref, threads=cores, fast=True)
+    for name, fn, src in (("enu_to_wgs84", geo.enu_to_wgs84_batch, enu), ("wgs84_to_enu", geo.wgs84_to_enu_batch, lla)):
+        for threads in (1, cores):
+            fn(src[:1000], ref, threads=threads, fast=True)
+            t0 = time.perf_counter()
+            fn(src, ref, threads=threads, fast=True)
+            out["geo"][f"{name}_rows_per_s_{'1thread' if threads == 1 else 'all_cores'}"] = src.shape[0] / (time.perf_counter() - t0)
+    rows, off, elev = workloads.sampled_rows(4096)
+    m = 256
+    t0 = time.perf_counter()
+    for b in range(m):
+        sl = slice(int(off[b]), int(off[b + 1]))
+        ao.optimize_segment_altitude_enu_banded(rows[sl], ao.shipped_params(), elev[sl])
+    out["alt"] = {"trajectories_per_s_1thread": m / (time.perf_counter() - t0), "sample_trajectories": m,
+                  "kind": "port (oracle/alt_oracle.py: numpy assembly + LAPACK dpbsv per solve, Python driver)"}
+    print(json.dumps(out))
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -517,6 +551,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "rows-cpu":
+        run_rows_cpu(args)
     else:
         run_b200(args)
 

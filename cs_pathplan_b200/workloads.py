@@ -89,3 +89,23 @@ def cfg5(B: int = 65536, seed: int = 1237, ns_min: int = 2, ns_max: int = 256):
     traj_of_pt = np.repeat(np.arange(B), ns + 1)
     wp = cs - start_val[traj_of_pt]
     return wp, seg_offset
+
+
+def sampled_rows(B: int = 4096, seed: int = 4):
+    """A cfg2-sized sampler output for the altitude-optimisation stage: B trajectories of
+    150..259 rows at 25 m spacing, cruise height 1300 +- 40 m over an analytic terrain of 1250 +- 80 m.  Returns
+    (rows [n,3], row_offset [B+1], elev [n])."""
+    rng = np.random.default_rng(seed)
+    ns = rng.integers(150, 260, B)
+    off = np.concatenate([[0], np.cumsum(ns)]).astype(np.int64)
+    n = int(off[-1])
+    t = np.arange(n) - np.repeat(off[:-1], ns)
+    rows = np.column_stack([t * 25.0, np.repeat(rng.uniform(-1e3, 1e3, B), ns), 1300.0 + 40.0 * np.sin(t / 9.0)])
+    elev = 1250.0 + 80.0 * np.sin(rows[:, 0] / 400.0 + np.repeat(rng.uniform(0, 6, B), ns))
+    return rows, off, elev
+
+
+def enu_rows(n: int, seed: int = 11) -> np.ndarray:
+    """n ENU rows of a mission area: east/north ~ N(0, 20 km), up ~ U(0, 5 km) (the WGS84 <-> ENU benchmark rows)."""
+    rng = np.random.default_rng(seed)
+    return np.column_stack([rng.normal(0.0, 2.0e4, n), rng.normal(0.0, 2.0e4, n), rng.uniform(0.0, 5000.0, n)])

@@ -1,9 +1,9 @@
 #!/usr/bin/env python3
 """Time the batched altitude optimisation (k_alt_prep + k_alt_solve; device-resident rows, per-kernel CUDA events on the
-launching stream through msnap_profile_begin/end) on a cfg2-sized sampler output, and beside it a banded-Cholesky CPU
-stand-in for the reference's per-trajectory SimplicialLDLT loop.  One JSON line.
+launching stream through msnap_profile_begin/end) on a cfg2-sized sampler output.  One JSON line.  The CPU leg (a
+banded-Cholesky stand-in for the reference's per-trajectory SimplicialLDLT loop) is `python bench.py --impl rows-cpu`.
 
-    python scripts/alt_bench.py [--B 4096] [--iters 20] [--cpu-traj 256]
+    python scripts/alt_bench.py [--B 4096] [--iters 20]
 """
 import argparse
 import json
@@ -16,38 +16,17 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from cs_pathplan_b200 import TrajectoryGeneratorTool, shipped_altitude_params  # noqa: E402
+from cs_pathplan_b200 import TrajectoryGeneratorTool, shipped_altitude_params, workloads  # noqa: E402
 
 
 def workload(B, seed=4):
-    rng = np.random.default_rng(seed)
-    ns = rng.integers(150, 260, B)
-    off = np.concatenate([[0], np.cumsum(ns)]).astype(np.int64)
-    n = int(off[-1])
-    t = np.arange(n) - np.repeat(off[:-1], ns)
-    rows = np.column_stack([t * 25.0, np.repeat(rng.uniform(-1e3, 1e3, B), ns), 1300.0 + 40.0 * np.sin(t / 9.0)])
-    elev = 1250.0 + 80.0 * np.sin(rows[:, 0] / 400.0 + np.repeat(rng.uniform(0, 6, B), ns))
-    return rows, off, elev
-
-
-def cpu_banded(rows, off, elev, p, n_traj):
-    """The same two passes per trajectory with LAPACK's banded Cholesky (oracle/alt_oracle.py,
-    optimize_segment_altitude_enu_banded): an O(n) CPU stand-in for the reference's Eigen::SimplicialLDLT loop
-    (cpp:1575-1827).  Returns seconds for n_traj trajectories."""
-    from oracle import alt_oracle as ao
-
-    t0 = time.perf_counter()
-    for b in range(n_traj):
-        sl = slice(int(off[b]), int(off[b + 1]))
-        ao.optimize_segment_altitude_enu_banded(rows[sl], p, elev[sl])
-    return time.perf_counter() - t0
+    return workloads.sampled_rows(B, seed)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--B", type=int, default=4096)
     ap.add_argument("--iters", type=int, default=20)
-    ap.add_argument("--cpu-traj", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
     rows, off, elev = workload(a.B)
@@ -87,13 +66,6 @@ def main():
            "algorithmic_bytes_per_row": 40, "achieved_GBps": 40.0 * n / (total * 1e-3) / 1e9,
            "hbm_frac": 40.0 * n / (total * 1e-3) / 1e9 / hbm_peak,
            "bound": "latency: one dependent chain of n rows per solve and trajectory, (1 + solves) chains per trajectory"}
-    if not a.no_cpu:
-        from oracle import alt_oracle as ao
-
-        m = min(a.cpu_traj, a.B)
-        dt = cpu_banded(rows, off, elev, ao.shipped_params(), m)
-        out["cpu_banded_cholesky_trajectories_per_s_1thread"] = m / dt
-        out["cpu_sample"] = f"first {m} trajectories, scipy.linalg.solveh_banded (LAPACK dpbsv) per solve, one thread"
     print(json.dumps(out))
 
 

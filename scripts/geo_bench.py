@@ -1,8 +1,8 @@
 #!/usr/bin/env python3
-"""Time the batched WGS84 <-> ENU kernels (device-resident rows, CUDA events on the launching stream) and, beside them,
-oracle/geo_port.c on the host cores.  One JSON line per direction.
+"""Time the batched WGS84 <-> ENU kernels (device-resident rows, CUDA events on the launching stream).  One JSON line per
+kernel.  The CPU leg (oracle/geo_port.c on the host cores) is `python bench.py --impl rows-cpu`.
 
-    python scripts/geo_bench.py [--rows 16777216] [--iters 20] [--cpu-rows 2000000]
+    python scripts/geo_bench.py [--rows 16777216] [--iters 20]
 """
 import argparse
 import json
@@ -22,7 +22,6 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows", type=int, default=1 << 24)
     ap.add_argument("--iters", type=int, default=20)
-    ap.add_argument("--cpu-rows", type=int, default=2_000_000)
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
     n = a.rows
@@ -69,23 +68,6 @@ def main():
                         "input": "rows 402 MB >> L2 (126 MB)"})
         tool.set_geo_exact_trig(False)
         tool.set_stream(None)
-    if not a.no_cpu:
-        from oracle import geo
-
-        m = min(a.cpu_rows, n)
-        h_enu = enu[:m].cpu().numpy()
-        cores = os.cpu_count() or 1
-        for o, (name, fn, src) in zip(out, (("enu_to_wgs84", geo.enu_to_wgs84_batch, h_enu),
-                                            ("wgs84_to_enu", geo.wgs84_to_enu_batch, None))):
-            src = src if src is not None else lla[:m].cpu().numpy()
-            for threads in (1, cores):
-                fn(src[:1000], ref, threads=threads, fast=True)
-                t0 = time.perf_counter()
-                fn(src, ref, threads=threads, fast=True)
-                dt = time.perf_counter() - t0
-                o[f"cpu_port_rows_per_s_{'1thread' if threads == 1 else 'all_cores'}"] = m / dt
-            o["cpu_cores"] = cores
-            o["cpu_sample_rows"] = m
     for o in out:
         print(json.dumps(o))
 

@@ -10,10 +10,11 @@ timeout 400 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.log 2>&1; e
 tail -4 $OUT/${TAG}_pytest.log
 timeout 400 python scripts/alt_bench.py > $OUT/${TAG}_alt_bench.json 2> $OUT/${TAG}_alt_bench.err; echo "alt bench rc=$?"
 cat $OUT/${TAG}_alt_bench.json; tail -3 $OUT/${TAG}_alt_bench.err
+timeout 400 python bench.py --impl rows-cpu > $OUT/${TAG}_rows_cpu.json 2> $OUT/${TAG}_rows_cpu.err; echo "rows-cpu rc=$?"
 if [ "${NCU:-1}" = "1" ]; then
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/${TAG}_alt_launches.csv \
-    python scripts/alt_bench.py --iters 2 --no-cpu > $OUT/${TAG}_alt_ncu1.log 2>&1
+    python scripts/alt_bench.py --iters 2 > $OUT/${TAG}_alt_ncu1.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_alt_solve -s 3 -c 1 -o $OUT/${TAG}_alt_solve -f \
-    python scripts/alt_bench.py --iters 2 --no-cpu > $OUT/${TAG}_alt_ncu2.log 2>&1
+    python scripts/alt_bench.py --iters 2 > $OUT/${TAG}_alt_ncu2.log 2>&1
 fi
 ls $OUT | grep ${TAG}

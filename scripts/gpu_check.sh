@@ -16,6 +16,7 @@ timeout 400 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/${TAG}_
 timeout 400 python scripts/geo_bench.py > $OUT/${TAG}_geo_bench.jsonl 2> $OUT/${TAG}_geo_bench.err; echo "geo bench rc=$?"
 timeout 400 python scripts/alt_bench.py > $OUT/${TAG}_alt_bench.json 2> $OUT/${TAG}_alt_bench.err; echo "alt bench rc=$?"
 kill $SMI
+timeout 400 python bench.py --impl rows-cpu > $OUT/${TAG}_rows_cpu.json 2> $OUT/${TAG}_rows_cpu.err; echo "rows-cpu rc=$?"
 if [ "${NCU:-1}" = "1" ]; then
 timeout 400 python scripts/profile_run.py --weights shipped --iters 4 > $OUT/${TAG}_plain.log 2>&1 &&
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/${TAG}_launches.csv \

@@ -47,6 +47,10 @@ def parse():
     ap.add_argument("--weights", default="shipped", choices=["shipped", "plain"])
     ap.add_argument("--batch", type=int, default=B_DEFAULT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--configs", default="all",
+                    help="comma list out of cfg1,cfg3,cfg4,cfg5 (the other BASELINE.json configs, reported under "
+                         "'variants'), 'all' or 'none'; cfg3 and cfg5 are ONE batch sharded over the ranks")
+    ap.add_argument("--no-parity", action="store_true", help="skip the whole-batch parity check of the cpu_baseline leg")
     ap.add_argument("--streams", type=int, default=2,
                     help="solver handles (each with its own CUDA stream) per GPU that consecutive steps alternate between")
     return ap.parse_args()
@@ -115,7 +119,7 @@ def cpu_rate(weights, wp, n_traj, threads):
     """Trajectories/s of the reference CPU code on `n_traj` trajectories with `threads` OpenMP threads."""
     from oracle import ref
 
-    off = np.arange(n_traj + 1, dtype=np.int64) * NS
+    off = np.arange(n_traj + 1, dtype=np.int64) * (NS + 1)   # CSR over waypoint rows: NS + 1 points per trajectory
     t0 = time.perf_counter()
     counts, used, _ = ref.generate_batch(off, wp[: n_traj * (NS + 1)], ref_config(weights), nthreads=threads, kind="fast")
     dt = time.perf_counter() - t0
@@ -131,8 +135,11 @@ def cpu_baseline(weights, wp, budget_s=12.0):
     return {"value": rN, "unit": UNIT, "cores": used, "kind": "reference",
             "sample": f"first {n} of the {wp.shape[0] // (NS + 1)} trajectories, one GenerateTrajectoryMatrix call each, "
                       f"OpenMP over trajectories on {used} threads; unmodified reference minimum_snap.cpp built against "
-                      f"the oracle's Eigen shim (real Eigen is not installable here), -O3 -march=x86-64-v3/v4",
-            "single_thread_value": r1}
+                      f"the oracle's Eigen shim -- NOT real Eigen (not installable here): the shim's inverse()/operator* "
+                      f"skip zero multiplicands, which makes this baseline faster than a naive dense backend "
+                      f"(conservative for the ratio); -O3 -march=x86-64-v3/v4; single_thread_value = 8 trajectories, "
+                      f"1 thread, as-shipped call sequence",
+            "sample_trajectories": n, "single_thread_value": r1}
 
 
 def run_reference(args):
@@ -159,8 +166,9 @@ def run_reference(args):
         _, used, _ = cpu_rate(args.weights, wp, n, cores)
     dt = time.perf_counter() - t0
     value = n * args.steps / dt
-    sample = (f"each step = first {n} trajectories of the batch, one GenerateTrajectoryMatrix call each, OpenMP over "
-              f"trajectories on {used} threads; unmodified reference minimum_snap.cpp + oracle Eigen shim")
+    sample = (f"each step = a {n}-trajectory subsample (the first {n}) of the {args.batch}-trajectory batch, one "
+              f"GenerateTrajectoryMatrix call each, OpenMP over trajectories on {used} threads; value = subsample / time; "
+              f"unmodified reference minimum_snap.cpp + the oracle's zero-skipping Eigen shim (not real Eigen)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -453,6 +461,153 @@ def run_b200(args):
             footprint=footprint)
         del sets
         torch.cuda.empty_cache()
+
+    # ------------------------------------------------------------------------------------------ the other configs
+    # BASELINE.json configs[0], [2], [3], [4] on the same line ("variants").  cfg3 and cfg5 are ONE batch sharded by
+    # trajectory index over the ranks (contiguous for cfg3, balanced on the segment count for cfg5; no collective on the
+    # data path): strong scaling, value = whole batch / max-over-ranks time, per-rank times reported (load imbalance).
+    from cs_pathplan_b200 import sharding
+
+    L2_BYTES = 126e6
+    flush_buf = torch.empty(64 << 20, dtype=torch.float32, device=dev)   # 256 MB > L2
+
+    def gather_floats(x):
+        if world == 1:
+            return [float(x)]
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
+    def config_variant(wp_full, cfg, ns=None, seg_offset=None, steps=10, warmup=3, sdo=-1.0, vo=-1.0):
+        wp_l, ns_l, so_l, (b0, b1) = sharding.shard_batch(wp_full, rank, world, ns=ns, seg_offset=seg_offset)
+        Bl = b1 - b0
+        n_seg_l = Bl * ns_l if ns_l else int(so_l[-1])
+        m_ = 2 * cfg.order
+        wp_l = np.ascontiguousarray(wp_l)
+        d_wp = torch.from_numpy(wp_l).to(dev)
+        d_so = None if so_l is None else torch.from_numpy(np.ascontiguousarray(so_l)).to(dev)
+        cap = tool.sample_bound(cfg, wp_l, ns=ns_l, seg_offset=so_l, v_avg_override=vo)
+        o = dict(times=torch.empty(n_seg_l, dtype=torch.float64, device=dev),
+                 coeff=torch.empty(n_seg_l * 3 * m_, dtype=torch.float64, device=dev),
+                 max_dev=torch.empty(Bl, dtype=torch.float64, device=dev),
+                 vw_final=torch.empty(Bl, dtype=torch.float64, device=dev),
+                 iters=torch.empty(Bl, dtype=torch.int32, device=dev),
+                 flags=torch.empty(Bl, dtype=torch.int32, device=dev))
+        off = torch.empty(Bl + 1, dtype=torch.int64, device=dev)
+        samples = torch.empty((cap, 3), dtype=torch.float64, device=dev)
+
+        def one():
+            tool.generate_batch_dev(cfg, d_wp, off, samples, ns=ns_l, seg_offset=d_so, sample_distance_override=sdo,
+                                    v_avg_override=vo, **o)
+
+        for _ in range(warmup):
+            one()
+        torch.cuda.synchronize()
+        rows_l = int(off[-1].item())
+        abytes_l = roofline.algorithmic_bytes(Bl, n_seg_l, cfg.order, rows_l)
+        small = abytes_l < 2 * L2_BYTES      # the batch would stay in L2 between steps: flush it, time step by step
+        barrier()
+        l0 = tool.launch_count
+        if small:
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            with torch.cuda.stream(stream):
+                for a, b in ev:
+                    flush_buf.zero_()
+                    a.record(stream)
+                    one()
+                    b.record(stream)
+            torch.cuda.synchronize()
+            ms_l = sum(a.elapsed_time(b) for a, b in ev) / steps
+        else:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(steps):
+                one()
+            e1.record(stream)
+            e1.synchronize()
+            torch.cuda.synchronize()
+            ms_l = e0.elapsed_time(e1) / steps
+        launches = (tool.launch_count - l0) / steps
+        per_rank = gather_floats(ms_l)
+        ms = max(per_rank)
+        barrier()
+        tool.profile_begin()
+        for _ in range(3):
+            one()
+        prof = tool.profile_end()
+        torch.cuda.synchronize()
+        rows = [int(v) for v in gather_floats(rows_l)]
+        segs = [int(v) for v in gather_floats(n_seg_l)]
+        trajs = [int(v) for v in gather_floats(Bl)]
+        solves_l = float((o["iters"].to(torch.int64) + 1).sum().item())
+        solves = sum(gather_floats(solves_l))
+        flags_bad = int(sum(gather_floats(float((o["flags"] != 0).sum().item()))))
+        base, total_rows = sharding.global_sample_base(rows_l)       # this rank's first row in the global CSR output
+        B_tot, seg_tot = sum(trajs), sum(segs)
+        t_np = o["times"].cpu().numpy()
+        cand_l = float(np.sum(np.floor((t_np + 1e-12) / np.minimum(0.1, t_np / 10.0) + 1e-9)))
+        cand = sum(gather_floats(cand_l))
+        ab = roofline.algorithmic_bytes(B_tot, seg_tot, cfg.order, total_rows)
+        af = roofline.algorithmic_flops(B_tot, seg_tot, cfg.order, cfg.path_weight > 0, solves, cand)
+        return dict(value=B_tot / (ms * 1e-3), unit=UNIT, ms_per_step=ms, steps=steps,
+                    scaling="strong: ONE batch sharded by trajectory index over the ranks, no collective",
+                    per_rank_ms=per_rank, imbalance_worst_over_mean=ms / (sum(per_rank) / len(per_rank)),
+                    per_rank_trajectories=trajs, per_rank_segments=segs, per_rank_rows=rows,
+                    segments_per_s=seg_tot / (ms * 1e-3), rows_per_step=total_rows, launches_per_step=launches,
+                    mean_reweight_iters=solves / B_tot - 1.0, flagged_trajectories=flags_bad,
+                    l2_policy=("256 MB flush write between steps, steps timed one by one" if small else
+                               f"inputs + outputs {abytes_l / 1e6:.0f} MB per GPU > 126 MB L2, steps back to back"),
+                    algorithmic_bytes=ab, algorithmic_flops=af,
+                    kernels_ms_per_step={k: v["total_ms"] / 3 for k, v in prof.items()} if rank == 0 else None)
+
+    want = {"cfg1", "cfg3", "cfg4", "cfg5"} if args.configs == "all" else \
+        (set() if args.configs == "none" else set(args.configs.split(",")))
+    if world > 1:
+        want &= {"cfg3", "cfg5"}            # only the configs BASELINE.json shards; the others are single-GPU lines
+    extra = {}
+    if "cfg3" in want:
+        wp3, ns3 = workloads.cfg3()
+        for w_ in ("shipped", "plain"):
+            v = config_variant(wp3, workloads.synthetic_config(ORDER, w_), ns=ns3, steps=10 if w_ == "shipped" else 20)
+            v["workload"] = (f"cfg3: ONE batch of {1 << 20} trajectories x 8 segments, order 4, fp64, rng 1235, {w_} weights, "
+                             f"contiguous shards over {world} GPU(s)")
+            extra["cfg3_sharded" if w_ == "shipped" else "cfg3_sharded_plain"] = v
+        del wp3
+    if "cfg5" in want:
+        wp5, so5 = workloads.cfg5()
+        for w_ in ("shipped", "plain"):
+            v = config_variant(wp5, workloads.synthetic_config(ORDER, w_, sample_distance=0.0), seg_offset=so5,
+                               steps=10 if w_ == "shipped" else 20)
+            v["workload"] = (f"cfg5: ONE batch of 65536 trajectories, 2-256 segments (log-uniform, rng 1237), order 4, dense "
+                             f"10 Hz output (sample_distance 0), {w_} weights, shards balanced on the segment count over "
+                             f"{world} GPU(s)")
+            extra["cfg5_sharded" if w_ == "shipped" else "cfg5_sharded_plain"] = v
+        del wp5
+    if "cfg4" in want:
+        wp4, ns4 = workloads.cfg4()
+        for w_ in ("shipped", "plain"):
+            v = config_variant(wp4, workloads.synthetic_config(ORDER, w_), ns=ns4, steps=20)
+            v["workload"] = f"cfg4: 1024 boustrophedon patrols x 512 segments, order 4, fp64, rng 1236, {w_} weights"
+            extra["cfg4" if w_ == "shipped" else "cfg4_plain"] = v
+        del wp4
+    if "cfg1" in want:
+        wp1, cfg1, sdo1, vo1 = workloads.cfg1()
+        lat = []
+        for _ in range(25):
+            t0 = time.perf_counter()
+            s1 = tool.GenerateTrajectoryMatrix(wp1, cfg1, sdo1, vo1)
+            lat.append((time.perf_counter() - t0) * 1e3)
+        rep = 4096
+        v = config_variant(np.tile(wp1, (rep, 1)), cfg1, ns=wp1.shape[0] - 1, steps=50, sdo=sdo1, vo=vo1)
+        v["workload"] = ("cfg1: uav31_0, the 7 ENU leader waypoints of readme.md:14-20, shipped YAML (order 2), getPlan's "
+                         f"overrides (sample distance 300 m, leader_speed 30 m/s); value = the same trajectory replicated {rep}x")
+        v["single_call_ms"] = statistics.median(lat[5:])
+        v["single_call"] = ("B = 1 through the drop-in call TrajectoryGeneratorTool::GenerateTrajectoryMatrix with host "
+                            "buffers (sample bound + H2D + kernels + D2H), wall clock, median of 20 calls")
+        v["single_call_samples"] = int(s1.shape[0])
+        extra["cfg1"] = v
+    del flush_buf
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:
@@ -477,15 +632,19 @@ def run_b200(args):
             tf = kf / t / 1e12
             tr = traffic.get(weights, {}).get(r["dom"]) if isinstance(traffic, dict) else None
             t_all = r["all_kernels_ms"] * 1e-3
-            return {"bound": "hbm", "kernel": r["dom"], "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": gbs / hbm_peak, "traffic": tr, "peak_source": peak_src,
+            # the binding roofline = whichever of (bytes / HBM peak, flops / FP64 peak) gives the larger time floor
+            hbm = {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": peak_src}
+            fp64 = {"achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+                    "peak_source": "msnap_measure_fp64_peak (own DFMA micro-benchmark, measured this run)"}
+            bound = "fp64" if kf / (fp64_peak * 1e12) > kb / (hbm_peak * 1e9) else "hbm"
+            bind, other = (fp64, hbm) if bound == "fp64" else (hbm, fp64)
+            return {"bound": bound, "kernel": r["dom"], "achieved": bind["achieved"], "peak": bind["peak"],
+                    "unit": bind["unit"], "frac": bind["frac"], "traffic": tr, "peak_source": bind["peak_source"],
                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
                                       "(profiles/dominant_kernel_traffic.json)" if tr else None,
+                    "non_binding": dict(other, bound="hbm" if bound == "fp64" else "fp64"),
                     "kernel_ms_per_step": r["dom_ms"], "all_kernels_ms_per_step": r["all_kernels_ms"],
                     "algorithmic_bytes_per_launch": kb, "algorithmic_flops_per_launch": kf,
-                    "fp64": {"achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
-                             "peak_source": "msnap_measure_fp64_peak (own DFMA micro-benchmark, measured this run)"},
-                    "limiter": "fp64 issue/latency" if tf / fp64_peak > gbs / hbm_peak else "hbm",
                     "whole_step": {"algorithmic_bytes": r["abytes"], "algorithmic_flops": r["aflops"],
                                    "hbm_frac": r["abytes"] / t_all / 1e9 / hbm_peak,
                                    "fp64_frac": r["aflops"] / t_all / 1e12 / fp64_peak},
@@ -514,6 +673,12 @@ def run_b200(args):
                              "roofline": roof(r, w), "workload": workload_name(w, B)}
                          for w, r in results.items() if w != args.weights},
         }
+        for k_, v_ in extra.items():
+            t_ = v_["ms_per_step"] * 1e-3
+            v_["roofline_whole_step"] = {"hbm_frac": v_["algorithmic_bytes"] / t_ / 1e9 / (hbm_peak * world),
+                                         "fp64_frac": v_["algorithmic_flops"] / t_ / 1e12 / (fp64_peak * world),
+                                         "hbm_peak_GBps": hbm_peak, "fp64_peak_TFLOPs": fp64_peak}
+            line["variants"][k_] = v_
         if h.get("geo"):
             g = dict(h["geo"])
             gbs = g["algorithmic_bytes_per_launch"] / (g["kernel_ms_per_step"] * 1e-3) / 1e9
@@ -540,6 +705,22 @@ def run_b200(args):
                                             "sample": "oracle/_ref not built on this box"}
             except Exception as e:  # the baseline must never take the GPU number down with it
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": repr(e)}
+            # Whole-batch parity, outside every timed region: ALL trajectories of the timed batch (workloads.cfg2(), the
+            # headline weights) through the unmodified reference (oracle/_ref, parity build) -- sample counts, every row,
+            # and on 512 of them the reweighting decisions and coefficients (oracle/parity.py).
+            if not args.no_parity:
+                try:
+                    from oracle import parity
+
+                    cfg_h = workloads.synthetic_config(ORDER, args.weights)
+                    res_h = tool.generate_batch(cfg_h, wp, ns=NS)
+                    pr = parity.batch_parity(res_h, wp, np.arange(B + 1, dtype=np.int64) * NS, cfg_h, n_coeff=512)
+                    pr["against"] = ("oracle/_ref/libmsnap_ref.so = unmodified minimum_snap.cpp, -O2 without FMA "
+                                     "contraction, GenerateTrajectoryMatrix per trajectory; bars: counts equal, rows "
+                                     "<= 1e-6 m, coefficients <= 1e-8 (position-scaled)")
+                    line["parity"] = pr
+                except Exception as e:
+                    line["parity"] = {"checked": 0, "error": repr(e)}
         print(json.dumps(line))
     for t_ in tools:
         t_.close()

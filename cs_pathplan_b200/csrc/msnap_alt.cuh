@@ -45,6 +45,10 @@ constexpr double ALT_CON_WEIGHT = 1e8;    // cpp:1787
 constexpr double ALT_VIOLATION = 1e-3;    // cpp:1805
 constexpr int ALT_MAX_ITER = 10;          // cpp:1733
 constexpr unsigned ALT_FLAG_PIVOT = 1u;   // a non-positive or non-finite pivot appeared (the reference's "decomposition failed")
+constexpr unsigned ALT_FLAG_TRUNCATED = 2u;  // the trajectory's rows do not fit n_rows_cap: skipped, rows untouched
+constexpr unsigned ALT_FLAG_PASS2 = 4u;   // the failure happened in pass 2: the pass-1 heights were kept (cpp:1356)
+// per-trajectory outcome handed from the solve kernel to k_alt_mark / k_alt_finish
+constexpr int ALT_ST_OK = 0, ALT_ST_KEEP_INPUT = 1, ALT_ST_KEEP_PASS1 = 2;
 
 // ElevationCostMap::getCostAt (elevation_cost_map.cpp:373-380): nearest cell of a row-major float grid with a top-left
 // origin; NaN where the reference returns false.
@@ -71,8 +75,8 @@ __global__ void __launch_bounds__(256) k_cost_lookup(const float *__restrict__ g
 __global__ void __launch_bounds__(256) k_alt_prep(AltParams p, long long B, const long long *__restrict__ row_offset,
                                                   const double *__restrict__ rows, const double *__restrict__ elev,
                                                   double *__restrict__ w1, double *__restrict__ w2, double *__restrict__ tgt,
-                                                  double *__restrict__ act) {
-    const long long n = row_offset[B];
+                                                  double *__restrict__ act, long long n_cap) {
+    const long long n = row_offset[B] < n_cap ? row_offset[B] : n_cap;  // rows beyond the caller's buffers do not exist
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += (long long)gridDim.x * blockDim.x) {
         const double x0 = rows[3 * g], y0 = rows[3 * g + 1], up = rows[3 * g + 2];
         double a1 = 0.0, a2 = 0.0;
@@ -92,11 +96,11 @@ __global__ void __launch_bounds__(256) k_alt_prep(AltParams p, long long B, cons
     }
 }
 __global__ void __launch_bounds__(256) k_alt_ends(long long B, const long long *__restrict__ row_offset, double *__restrict__ w1,
-                                                  double *__restrict__ w2) {
+                                                  double *__restrict__ w2, long long n_cap) {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const long long first = row_offset[b], end = row_offset[b + 1];
-    if (end > first) {  // the last row of a trajectory has no edge to a successor
+    if (end > first && end <= n_cap) {  // the last row of a trajectory has no edge to a successor
         w1[end - 1] = 0.0;
         w2[end - 1] = 0.0;
     }
@@ -234,14 +238,15 @@ __global__ void __launch_bounds__(32) k_alt_solve(AltParams p, long long B, cons
                                                   const double *elev, const double *w1, const double *w2, const double *tgt,
                                                   double *l1, double *l2, double *yd, double *zin, double *cur, double *act,
                                                   double *z_pass1_out, int *__restrict__ solves_out,
-                                                  unsigned *__restrict__ flags_out) {
+                                                  unsigned *__restrict__ flags_out, long long n_cap, int *__restrict__ st_out) {
     extern __shared__ double alt_sm[];
     const int lane = threadIdx.x;
     const long long b = (long long)blockIdx.x * 32 + lane;
     const long long base = b < B ? row_offset[b] : 0;
-    const int n = b < B ? (int)(row_offset[b + 1] - base) : 0;
+    const bool truncated = b < B && row_offset[b + 1] > n_cap;  // rows missing from the caller's buffers: skip the trajectory
+    const int n = (b < B && !truncated) ? (int)(row_offset[b + 1] - base) : 0;
     const int nmax = __reduce_max_sync(0xffffffffu, n);
-    bool ok = true;
+    bool ok = true, ok2 = true;
 
     // ---- pass 1: optimizeHeights (cpp:1575-1712)
     {
@@ -291,7 +296,7 @@ __global__ void __launch_bounds__(32) k_alt_solve(AltParams p, long long B, cons
             l2[base + k] = o2;
             yd[base + k] = o3;
         });
-        if (running) ok = ok && f.ok;
+        if (running) ok2 = ok2 && f.ok;
         AltBwd r;
         bool violation = false;
         const double *const in_b[5] = {l1, l2, yd, zin, act};
@@ -310,7 +315,9 @@ __global__ void __launch_bounds__(32) k_alt_solve(AltParams p, long long B, cons
     }
     if (b < B) {
         if (solves_out) solves_out[b] = solves;
-        if (flags_out) flags_out[b] = ok ? 0u : ALT_FLAG_PIVOT;
+        if (flags_out)
+            flags_out[b] = truncated ? ALT_FLAG_TRUNCATED : (!ok ? ALT_FLAG_PIVOT : (!ok2 ? (ALT_FLAG_PIVOT | ALT_FLAG_PASS2) : 0u));
+        st_out[b] = (truncated || !ok) ? ALT_ST_KEEP_INPUT : (!ok2 ? ALT_ST_KEEP_PASS1 : ALT_ST_OK);
     }
 }
 
@@ -399,7 +406,8 @@ __global__ void __launch_bounds__(32) k_alt_solve_pair(AltParams p, long long B,
                                                        const double *elev, const double *w1, const double *w2,
                                                        const double *tgt, double *l1, double *l2, double *yd, double *zin,
                                                        double *cur, double *act, double *z_pass1_out,
-                                                       int *__restrict__ solves_out, unsigned *__restrict__ flags_out) {
+                                                       int *__restrict__ solves_out, unsigned *__restrict__ flags_out,
+                                                       long long n_cap, int *__restrict__ st_out) {
     extern __shared__ double alt_sm[];
     const int lane = threadIdx.x;
     const unsigned FULL = 0xffffffffu;
@@ -407,7 +415,8 @@ __global__ void __launch_bounds__(32) k_alt_solve_pair(AltParams p, long long B,
     AltSpan S;
     S.side = lane & 1;
     S.base = b < B ? row_offset[b] : 0;
-    S.n = b < B ? (int)(row_offset[b + 1] - S.base) : 0;
+    const bool truncated = b < B && row_offset[b + 1] > n_cap;  // rows missing from the caller's buffers: skip the trajectory
+    S.n = (b < B && !truncated) ? (int)(row_offset[b + 1] - S.base) : 0;
     S.twisted = S.n >= ALT_TWIST_MIN;
     const int n = S.n, m = (n - 2) / 2;  // middle rows m, m + 1
     S.cnt = S.twisted ? (S.side ? n - m - 1 : m + 1) : (S.side ? 0 : n);
@@ -419,7 +428,7 @@ __global__ void __launch_bounds__(32) k_alt_solve_pair(AltParams p, long long B,
     double *const l1_b = l1 + base, *const l2_b = l2 + base, *const yd_b = yd + base, *const zin_b = zin + base,
                   *const cur_b = cur + base, *const act_b = act + base,
                   *const z_pass1_out_b = z_pass1_out ? z_pass1_out + base : nullptr;
-    bool ok = true;
+    bool ok = true, ok2 = true;
     auto X = [&](double v) { return __shfl_xor_sync(FULL, v, 1); };
 
     // one solve: forward sweeps of both sides, the middle 2 x 2 system, back substitution outwards.
@@ -521,27 +530,50 @@ __global__ void __launch_bounds__(32) k_alt_solve_pair(AltParams p, long long B,
         const bool partner_violation = __shfl_xor_sync(FULL, violation, 1);  // (no short circuit around a warp collective)
         violation = violation || partner_violation;
         if (running) {
-            ok = ok && good;
+            ok2 = ok2 && good;
             ++solves;
             if (!violation) running = false;  // converged (cpp:1814)
         }
     }
-    const bool partner_ok = __shfl_xor_sync(FULL, ok, 1);
+    const bool partner_ok = __shfl_xor_sync(FULL, ok, 1), partner_ok2 = __shfl_xor_sync(FULL, ok2, 1);
     ok = ok && partner_ok;
+    ok2 = ok2 && partner_ok2;
     if (b < B && S.side == 0) {
         if (solves_out) solves_out[b] = solves;
-        if (flags_out) flags_out[b] = ok ? 0u : ALT_FLAG_PIVOT;
+        if (flags_out)
+            flags_out[b] = truncated ? ALT_FLAG_TRUNCATED : (!ok ? ALT_FLAG_PIVOT : (!ok2 ? (ALT_FLAG_PIVOT | ALT_FLAG_PASS2) : 0u));
+        st_out[b] = (truncated || !ok) ? ALT_ST_KEEP_INPUT : (!ok2 ? ALT_ST_KEEP_PASS1 : ALT_ST_OK);
     }
 }
 
-// cpp:1817-1821 and the write-back of cpp:1357-1359: up_i = max(z_i, z1_i), row-parallel.
+// Failure semantics of optimizeSegmentAltitudeENU (cpp:1342-1344, 1356): if pass 1 fails the rows stay untouched, if pass 2
+// fails the pass-1 heights are kept.  Thread per trajectory; a trajectory that did not finish both passes poisons its scratch
+// heights with NaN (zin and cur, or cur alone), which k_alt_finish reads as "keep".  Failures are rare, so this kernel
+// normally only reads B status words.
+__global__ void __launch_bounds__(256) k_alt_mark(long long B, const long long *__restrict__ row_offset, long long n_cap,
+                                                  const int *__restrict__ st, double *__restrict__ zin, double *__restrict__ cur) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int s = st[b];
+    if (s == ALT_ST_OK) return;
+    const long long first = row_offset[b];
+    long long end = row_offset[b + 1];
+    if (end > n_cap) end = n_cap;
+    for (long long g = first; g < end; ++g) {
+        cur[g] = NAN;
+        if (s == ALT_ST_KEEP_INPUT) zin[g] = NAN;
+    }
+}
+
+// cpp:1817-1821 and the write-back of cpp:1357-1359: up_i = max(z_i, z1_i), row-parallel.  NaN marks from k_alt_mark: no
+// pass-1 height => the row keeps its input `up`; no pass-2 height => the pass-1 height.
 __global__ void __launch_bounds__(256) k_alt_finish(long long B, const long long *__restrict__ row_offset,
                                                     const double *__restrict__ cur, const double *__restrict__ zin,
-                                                    double *__restrict__ rows) {
-    const long long n = row_offset[B];
+                                                    double *__restrict__ rows, long long n_cap) {
+    const long long n = row_offset[B] < n_cap ? row_offset[B] : n_cap;
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += (long long)gridDim.x * blockDim.x) {
         const double z = cur[g], zi = zin[g];
-        rows[3 * g + 2] = z < zi ? zi : z;
+        if (zi == zi) rows[3 * g + 2] = z >= zi ? z : zi;  // (z NaN => zi)
     }
 }
 

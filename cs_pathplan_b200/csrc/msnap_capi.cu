@@ -504,7 +504,7 @@ int run_sample(msnap_context *h, const BatchIdx &bi, const double *coeff, const 
     }
     const int blk = 128;
     const unsigned gs = grid_for(bi.n_seg, blk), gb = grid_for(bi.B, blk);
-    MS_LAUNCH(h, (k_count<O>), gs, blk, bi, coeff, T, sd, s.seg_count, s.seg_mask, s.seg_last);
+    MS_LAUNCH(h, (k_count<O>), gs, blk, bi, coeff, T, sd, s.seg_count, s.seg_mask, s.seg_last, flags);
     MS_LAUNCH(h, (k_traj_count<O>), gb, blk, bi, coeff, T, s.seg_count, s.seg_last, s.seg_start, s.append_end,
               s.traj_count);
     const int nblk = (int)grid_for(bi.B, SCAN_BLOCK);
@@ -515,6 +515,12 @@ int run_sample(msnap_context *h, const BatchIdx &bi, const double *coeff, const 
               sample_offset, s.append_end, capacity, samples, flags);
     if (stats) MS_LAUNCH(h, k_stats, grid_for(bi.B * 32, 256), 256, bi.B, sample_offset, samples, capacity, stats);
     return MSNAP_OK;
+}
+
+// Parameters the sampler cannot run with (its candidate loop would not terminate): see SAMPLE_T_MAX in msnap_generic.cuh.
+bool valid_generate_config(const msnap_config *cfg, double sd, double va) {
+    return cfg->min_time_s > 0.0 && cfg->min_time_s <= SAMPLE_T_MAX && std::isfinite(va) && std::isfinite(sd) &&
+           std::isfinite(cfg->path_weight) && std::isfinite(cfg->vel_zero_weight);
 }
 
 int check_batch(long long B, int ns_uniform, const long long *seg_offset, const double *waypoints) {
@@ -1017,6 +1023,7 @@ int msnap_generate_batch_dev(msnap_handle h, const msnap_config *cfg, double sam
     if (rc) return rc;
     const double sd = sample_distance_override > 0.0 ? sample_distance_override : cfg->sample_distance;  // ms.cpp:42-44
     const double va = v_avg_override > 0.0 ? v_avg_override : cfg->V_avg;                                // ms.cpp:46-48
+    if (!valid_generate_config(cfg, sd, va)) return MSNAP_ERR_INVALID_ARG;
     MS_DISPATCH_ORDER(cfg->order,
                       return generate_dev<O>(h, cfg, sd, va, B, ns_uniform, seg_offset, n_seg, waypoints, times_out,
                                              coeff_out, max_dev_out, iters_out, vw_final_out, best_s_out, sample_capacity,
@@ -1159,6 +1166,7 @@ int msnap_generate_batch_host(msnap_handle h, const msnap_config *cfg, double sa
     DeviceGuard guard(h->device);
     const double sd = sample_distance_override > 0.0 ? sample_distance_override : cfg->sample_distance;
     const double va = v_avg_override > 0.0 ? v_avg_override : cfg->V_avg;
+    if (!valid_generate_config(cfg, sd, va)) return MSNAP_ERR_INVALID_ARG;
     // Chunks: results cross PCIe at ~50 GB/s while the kernels take a fraction of that time, so a big batch is cut into
     // chunks whose kernels run (on a second stream) while the previous chunk's results are still being copied out.
     // (Measured on B200/PCIe 5: at 4 096 trajectories the extra API calls of chunking cost more than the overlap wins;
@@ -1397,17 +1405,19 @@ int msnap_altitude_optimize_batch_dev(msnap_handle h, const msnap_altitude_param
     if (B == 0 || n_rows_cap == 0) return MSNAP_OK;
     DeviceGuard guard(h->device);
     const size_t n = (size_t)n_rows_cap;
-    int rc = arena_reserve(h, h->ws, 9 * padded(n * sizeof(double)));
+    int rc = arena_reserve(h, h->ws, 9 * padded(n * sizeof(double)) + padded((size_t)B * sizeof(int)));
     if (rc) return rc;
     double *w1 = arena_take<double>(h->ws, n), *w2 = arena_take<double>(h->ws, n), *tgt = arena_take<double>(h->ws, n);
     double *l1 = arena_take<double>(h->ws, n), *l2 = arena_take<double>(h->ws, n), *yd = arena_take<double>(h->ws, n);
     double *zin = arena_take<double>(h->ws, n), *cur = arena_take<double>(h->ws, n);
     double *act = arena_take<double>(h->ws, n);  // active-set marks of pass 2 (0.0 / 1.0: staged like the other fields)
+    int *st = arena_take<int>(h->ws, (size_t)B);  // per-trajectory outcome (ALT_ST_*)
     const AltParams p{params->lambda_smooth, params->lambda_follow, params->max_climb_rate, params->uav_R,
                       params->safe_distance};
     const long long want = (n_rows_cap + 255) / 256, cap = (long long)h->sm_count * 8;
-    MS_LAUNCH(h, k_alt_prep, (unsigned)(want < cap ? want : cap), 256, p, B, row_offset, rows_inout, elev, w1, w2, tgt, act);
-    MS_LAUNCH(h, k_alt_ends, grid_for(B, 256), 256, B, row_offset, w1, w2);
+    MS_LAUNCH(h, k_alt_prep, (unsigned)(want < cap ? want : cap), 256, p, B, row_offset, rows_inout, elev, w1, w2, tgt, act,
+              n_rows_cap);
+    MS_LAUNCH(h, k_alt_ends, grid_for(B, 256), 256, B, row_offset, w1, w2, n_rows_cap);
     if (!h->alt_smem_opted) {  // > 48 KB of dynamic shared memory needs the opt-in (per device; once per handle)
         MS_CUDA(h, cudaFuncSetAttribute(k_alt_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ALT_SMEM_BYTES));
         MS_CUDA(h, cudaFuncSetAttribute(k_alt_solve_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ALT_SMEM_BYTES));
@@ -1416,16 +1426,19 @@ int msnap_altitude_optimize_batch_dev(msnap_handle h, const msnap_altitude_param
     if (h->alt_policy == 1) {  // one lane per trajectory
         prof_before(h, "k_alt_solve");
         k_alt_solve<<<grid_for(B, 32), 32, ALT_SMEM_BYTES, h->stream>>>(p, B, row_offset, elev, w1, w2, tgt, l1, l2, yd, zin,
-                                                                        cur, act, z_pass1_out, solves_out, flags_out);
+                                                                        cur, act, z_pass1_out, solves_out, flags_out,
+                                                                        n_rows_cap, st);
     } else {  // lane pairs (two-sided elimination)
         prof_before(h, "k_alt_solve_pair");
         k_alt_solve_pair<<<grid_for(B, 16), 32, ALT_SMEM_BYTES, h->stream>>>(p, B, row_offset, elev, w1, w2, tgt, l1, l2, yd,
-                                                                             zin, cur, act, z_pass1_out, solves_out, flags_out);
+                                                                             zin, cur, act, z_pass1_out, solves_out, flags_out,
+                                                                             n_rows_cap, st);
     }
     prof_after(h);
     ++h->launches;
     MS_CUDA(h, cudaPeekAtLastError());
-    MS_LAUNCH(h, k_alt_finish, (unsigned)(want < cap ? want : cap), 256, B, row_offset, cur, zin, rows_inout);
+    MS_LAUNCH(h, k_alt_mark, grid_for(B, 256), 256, B, row_offset, n_rows_cap, st, zin, cur);
+    MS_LAUNCH(h, k_alt_finish, (unsigned)(want < cap ? want : cap), 256, B, row_offset, cur, zin, rows_inout, n_rows_cap);
     return MSNAP_OK;
 }
 

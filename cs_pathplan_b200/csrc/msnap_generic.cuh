@@ -506,6 +506,13 @@ __device__ __forceinline__ double sample_dt(double T) {
     return dt;
 }
 
+// A segment whose duration is not a positive finite number of at most MSNAP_MAX_SEGMENT_TIME seconds (an inf / NaN /
+// absurd waypoint, or min_time_s <= 0 with coincident waypoints: T = 0 => dt = 0) would keep the reference's candidate
+// loop `t += dt` spinning forever.  The reference only loses that one call; here one such row would hang the launch of
+// the whole batch, so the sampler treats the segment as failed: no candidates, trajectory flagged MSNAP_FLAG_NONFINITE.
+constexpr double SAMPLE_T_MAX = 1.0e6;  // == MSNAP_MAX_SEGMENT_TIME (include/msnap.h): at most 1e7 candidates per segment
+__device__ __forceinline__ bool sample_time_ok(double T) { return T > 0.0 && T <= SAMPLE_T_MAX; }
+
 constexpr int SAMPLE_MASK_BITS = 128;            // candidates per segment the acceptance mask can describe
 constexpr int SAMPLE_TTAB_N = SAMPLE_MASK_BITS + 2;  // entries of t_table a write pass needs
 
@@ -532,7 +539,7 @@ __device__ __forceinline__ void count_candidates(const double (&c)[3][2 * O], do
                                                  int &n_out, bool &usable, unsigned long long &m0,
                                                  unsigned long long &m1, double (&last)[3]) {
     const double dt = sample_dt(Tk);
-    const double tmax = Tk + 1e-12;
+    const double tmax = sample_time_ok(Tk) ? Tk + 1e-12 : -1.0;  // a failed segment has no candidates
     double prev[3], ca[3], cb[3];
     eval_xyz<O>(c, 0.0, prev);
     int n = 0, idx = 0;
@@ -596,7 +603,8 @@ __device__ __forceinline__ void write_candidates(const double (&c)[3][2 * O], do
     } else {
         double prev[3];
         eval_xyz<O>(c, 0.0, prev);
-        for (double t = dt; t <= Tk + 1e-12; t += dt) {
+        const double tmax = sample_time_ok(Tk) ? Tk + 1e-12 : -1.0;
+        for (double t = dt; t <= tmax; t += dt) {
             eval_xyz<O>(c, fmin(t, Tk), cur);
             if (accept(cur, prev)) {
                 prev[0] = cur[0]; prev[1] = cur[1]; prev[2] = cur[2];
@@ -670,7 +678,7 @@ template <int O>
 __global__ void __launch_bounds__(128) k_count(BatchIdx bi, const double *__restrict__ coeff,
                                                const double *__restrict__ T, double sample_distance,
                                                int *__restrict__ seg_count, unsigned long long *__restrict__ seg_mask,
-                                               double *__restrict__ seg_last) {
+                                               double *__restrict__ seg_last, unsigned *__restrict__ flags) {
     const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (g >= bi.n_seg) return;
     double c[3][2 * O];
@@ -681,6 +689,11 @@ __global__ void __launch_bounds__(128) k_count(BatchIdx bi, const double *__rest
     unsigned long long m0, m1;
     double last[3];
     count_candidates<O>(c, T[g], accept, n, usable, m0, m1, last);
+    if (!sample_time_ok(T[g]) && flags) {
+        long long b; int k, ns;
+        bi.locate(g, b, k, ns);
+        atomicOr(flags + b, 1u);
+    }
     seg_count[g] = usable ? n : -n - 1;
     seg_mask[2 * g] = m0;
     seg_mask[2 * g + 1] = m1;
@@ -984,6 +997,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_sample_scan(
                 unsigned long long m0, m1;
                 double lp[3];
                 count_candidates<O>(c, segT[i], accept, n, usable, m0, m1, lp);
+                if (!sample_time_ok(segT[i]) && flags) atomicOr(flags + b0 + i / ns, 1u);
                 cnt[i] = usable ? n : -n - 1;
                 mask[2 * i] = m0;
                 mask[2 * i + 1] = m1;
@@ -1236,7 +1250,7 @@ __global__ void k_bound(BatchIdx bi, const double *__restrict__ wp, double v_avg
         double t = (v_avg > 1e-6) ? __ddiv_rn(len, v_avg) : min_time;
         if (t < min_time) t = min_time;
         const double dt = sample_dt(t);
-        n = (dt == 0.1) ? (unsigned long long)(t / 0.1) + 2ull : 12ull;
+        n = !sample_time_ok(t) ? 0ull : (dt == 0.1) ? (unsigned long long)(t / 0.1) + 2ull : 12ull;
         if (k == 0) n += 2ull;
     }
 #pragma unroll

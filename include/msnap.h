@@ -59,6 +59,11 @@ typedef struct msnap_config {
 /* per-trajectory flag bits written to flags_out */
 #define MSNAP_FLAG_NONFINITE 1u /* a non-finite value or a non-positive pivot appeared in the solve */
 #define MSNAP_FLAG_TRUNCATED 2u /* samples of this trajectory did not fit the caller's buffer       */
+/* Longest segment duration the sampler walks (seconds; 1e7 candidates at 10 Hz).  A segment whose allocated time is not a
+ * positive finite number <= this (an inf / NaN / absurd waypoint) gets no sampled candidates and its trajectory
+ * MSNAP_FLAG_NONFINITE: in the reference such an input keeps ms.cpp:140's `t += dt` loop spinning for that one call; in a
+ * batch it must not take the launch of every other trajectory down with it. */
+#define MSNAP_MAX_SEGMENT_TIME 1.0e6
 
 typedef struct msnap_context *msnap_handle;
 
@@ -118,6 +123,8 @@ int msnap_solve_qp_batch_host(msnap_handle h, int order, double path_weight, dou
  * Time allocation (ms.cpp:63-72), the reweighting loop around the closed-form solve (ms.cpp:76-90), the
  * distance-thresholded sampler (ms.cpp:97-161) and the climb/turn statistics (ms.cpp:163-195), for B trajectories.
  *   sample_distance_override / v_avg_override: used iff > 0 (ms.cpp:42-48)
+ * MSNAP_ERR_INVALID_ARG for parameters the sampler's candidate loop cannot terminate with: min_time_s <= 0 (coincident
+ * waypoints would give T = 0, dt = 0) or > MSNAP_MAX_SEGMENT_TIME, non-finite V_avg / sample_distance / weights.
  * Outputs (any optional pointer may be NULL):
  *   times_out     [sum ns]            optional   allocated segment times
  *   coeff_out     [sum ns][3][2o]     optional   final polynomial coefficients
@@ -213,9 +220,15 @@ int msnap_debug_geo_steps_dev(msnap_handle h, const double *reference_lla, long 
  *                 NaN where it has no value; NULL = no terrain anywhere.  msnap_cost_map_lookup_dev fills it from a grid.
  *   z_pass1_out : [rows] optional, the heights after optimizeHeights (before the global smoothing pass)
  *   solves_out  : [B] optional, solves the active-set loop of pass 2 took (1..10, cpp:1733-1814)
- *   flags_out   : [B] optional, bit 0 = a non-positive pivot appeared (the reference's "decomposition failed")
- * _dev: device pointers, n_rows_cap = allocated rows (the exact count is read from row_offset[B] on the device), enqueued on
- * the handle's stream.  _host: host pointers, returns when the outputs are complete. */
+ *   flags_out   : [B] optional, bit 0 = a non-positive pivot appeared (the reference's "decomposition failed"); bit 2 =
+ *                 it appeared in pass 2; bit 1 (== MSNAP_FLAG_TRUNCATED) = the trajectory's rows reach beyond n_rows_cap
+ * Failure behaviour is the reference's (cpp:1342-1344, 1356): a trajectory whose pass 1 fails keeps its input `up` values,
+ * one whose pass 2 fails keeps the pass-1 heights.
+ * _dev: device pointers, n_rows_cap = allocated rows of rows_inout / elev / z_pass1_out (the exact count is read from
+ * row_offset[B] on the device), enqueued on the handle's stream.  No row at or beyond n_rows_cap is read or written: when
+ * row_offset comes from a msnap_generate_batch_dev call that ran out of sample capacity (MSNAP_FLAG_TRUNCATED), the
+ * trajectories whose rows do not fit entirely are skipped (bit 1 of flags_out) and keep whatever rows they have.
+ * _host: host pointers, returns when the outputs are complete. */
 typedef struct msnap_altitude_params {
     double lambda_smooth, lambda_follow, max_climb_rate, uav_R, safe_distance;
 } msnap_altitude_params;

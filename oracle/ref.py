@@ -103,6 +103,10 @@ def lib(kind: str = "parity"):
         [C.c_int] + [C.c_double] * 5 + [_dp, C.c_double, C.c_double, C.c_int, _lp, _dp, C.c_int, _ip, C.c_int, _dp]
     )
     L.msnap_ref_generate_batch.restype = C.c_int
+    L.msnap_ref_reweighted_solve_batch.argtypes = (
+        [C.c_int] + [C.c_double] * 4 + [_dp, C.c_double, C.c_int, _lp, _dp, C.c_int, _dp, _dp, _dp, _ip, _dp]
+    )
+    L.msnap_ref_reweighted_solve_batch.restype = C.c_int
     _LIBS[kind] = L
     return L
 
@@ -196,6 +200,28 @@ def generate_batch(pt_offset, waypoints, cfg: RefConfig, sample_distance_overrid
         counts.ctypes.data_as(_ip), cap, _d(samples) if samples is not None else None,
     )
     return counts, used, samples
+
+
+def reweighted_solve_batch(pt_offset, waypoints, cfg: RefConfig, v_avg_override=-1.0, nthreads=0, kind="parity"):
+    """`reweighted_solve` for B trajectories (CSR pt_offset[B+1] into waypoint rows), OpenMP over trajectories.
+
+    Returns (times [sum ns], coeff [sum ns, 3, 2*order], max_dev [B], iters [B], vw_final [B])."""
+    pt_offset = np.ascontiguousarray(pt_offset, dtype=np.int64)
+    waypoints = _f64(waypoints)
+    B = pt_offset.shape[0] - 1
+    n_seg = int(pt_offset[-1] - pt_offset[0]) - B
+    bc = cfg.bc()
+    t = np.zeros(n_seg)
+    co = np.zeros((n_seg, 3, 2 * cfg.order))
+    md = np.zeros(B)
+    it = np.zeros(B, dtype=np.int32)
+    vwf = np.zeros(B)
+    assert pt_offset[0] == 0
+    lib(kind).msnap_ref_reweighted_solve_batch(
+        cfg.order, cfg.path_weight, cfg.vel_zero_weight, cfg.V_avg, cfg.min_time_s, _d(bc), v_avg_override, B,
+        pt_offset.ctypes.data_as(_lp), _d(waypoints), nthreads, _d(t), _d(co), _d(md), it.ctypes.data_as(_ip), _d(vwf),
+    )
+    return t, co, md, it, vwf
 
 
 # readme.md:14-20 -- the only pinned numbers in the reference: ENU waypoints of the uav31_0 leader route

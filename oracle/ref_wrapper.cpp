@@ -183,4 +183,30 @@ int msnap_ref_generate_batch(int order, double pw, double vw, double v_avg, doub
     return used;
 }
 
+// Batched msnap_ref_reweighted_solve: B independent trajectories (CSR pt_offset[B+1] into wp rows), OpenMP over
+// trajectories.  time_out / coeff_out are laid out per segment in batch order (segment offset of trajectory b =
+// pt_offset[b] - b).  Returns the number of threads used.
+int msnap_ref_reweighted_solve_batch(int order, double pw, double vw, double v_avg, double min_time, const double *bc,
+                                     double v_avg_override, int B, const long long *pt_offset, const double *wp,
+                                     int nthreads, double *time_out, double *coeff_out, double *max_dev_out,
+                                     int *iters_out, double *vw_final_out) {
+    static Quiet quiet;
+    int used = 1;
+    const int w = 3 * 2 * order;
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+    used = nthreads;
+#pragma omp parallel for schedule(dynamic) num_threads(nthreads)
+#else
+    (void)nthreads;
+#endif
+    for (int b = 0; b < B; ++b) {
+        const long long p0 = pt_offset[b], g0 = p0 - b;
+        const int n_pts = static_cast<int>(pt_offset[b + 1] - p0);
+        msnap_ref_reweighted_solve(order, pw, vw, v_avg, min_time, bc, v_avg_override, n_pts, wp + 3 * p0,
+                                   time_out + g0, coeff_out + g0 * w, max_dev_out + b, iters_out + b, vw_final_out + b);
+    }
+    return used;
+}
+
 }  // extern "C"

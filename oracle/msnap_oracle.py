@@ -340,6 +340,47 @@ def _norm3(v):
     return math.sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2])
 
 
+def sample_polynomials(polyCoeff, Time, order, sample_distance):
+    """The sampler of GenerateTrajectoryMatrix, ms.cpp:97-161, on given coefficients (PolyCoeff matrix, ns x 3*2*order)
+    and segment times.  Returns (list of points, per-segment accepted counts, per-segment candidate counts, min
+    |seg_len - sample_distance| over all candidates)."""
+    num_segments = len(Time)
+    p_num1d = 2 * order
+    dt_default = 0.1                                  # ms.cpp:100
+    samples = []
+    has_last = False
+    seg_counts = np.zeros(num_segments, dtype=np.int64)
+    n_cand = np.zeros(num_segments, dtype=np.int64)
+    margin = math.inf
+    for seg in range(num_segments):                   # ms.cpp:123-161
+        T = Time[seg]
+        dt = dt_default
+        if dt > T / 10.0:
+            dt = T / 10.0
+        t0_pt = eval_poly_at(polyCoeff, p_num1d, seg, 0.0)
+        if not has_last:
+            samples.append(t0_pt)
+            has_last = True
+        prev_pt = t0_pt
+        t = dt
+        while t <= T + 1e-12:
+            tt = min(t, T)
+            cur_pt = eval_poly_at(polyCoeff, p_num1d, seg, tt)
+            seg_len = _norm3(cur_pt - prev_pt)
+            margin = min(margin, abs(seg_len - sample_distance))
+            n_cand[seg] += 1
+            if seg_len >= sample_distance:
+                prev_pt = cur_pt
+                samples.append(cur_pt)
+                seg_counts[seg] += 1
+            t += dt
+        if seg == num_segments - 1:
+            endpt = eval_poly_at(polyCoeff, p_num1d, seg, T)
+            if len(samples) == 0 or _norm3(samples[-1] - endpt) > 1e-6:
+                samples.append(endpt)
+    return samples, seg_counts, n_cand, margin
+
+
 def generate_trajectory_matrix(Path, cfg: MinimumSnapConfig, sample_distance_override=-1.0, v_avg_override=-1.0):
     """TrajectoryGeneratorTool::GenerateTrajectoryMatrix, ms.cpp:22-206.  Returns (samples (S,3), GenerateInfo);
     an input with fewer than 2 rows or 3 columns returns an empty (0,0) matrix like ms.cpp:54-57."""
@@ -374,39 +415,7 @@ def generate_trajectory_matrix(Path, cfg: MinimumSnapConfig, sample_distance_ove
         else:
             break
 
-    p_num1d = 2 * order
-    dt_default = 0.1                                  # ms.cpp:100
-    samples = []
-    has_last = False
-    seg_counts = np.zeros(num_segments, dtype=np.int64)
-    n_cand = np.zeros(num_segments, dtype=np.int64)
-    margin = math.inf
-    for seg in range(num_segments):                   # ms.cpp:123-161
-        T = Time[seg]
-        dt = dt_default
-        if dt > T / 10.0:
-            dt = T / 10.0
-        t0_pt = eval_poly_at(polyCoeff, p_num1d, seg, 0.0)
-        if not has_last:
-            samples.append(t0_pt)
-            has_last = True
-        prev_pt = t0_pt
-        t = dt
-        while t <= T + 1e-12:
-            tt = min(t, T)
-            cur_pt = eval_poly_at(polyCoeff, p_num1d, seg, tt)
-            seg_len = _norm3(cur_pt - prev_pt)
-            margin = min(margin, abs(seg_len - sample_distance))
-            n_cand[seg] += 1
-            if seg_len >= sample_distance:
-                prev_pt = cur_pt
-                samples.append(cur_pt)
-                seg_counts[seg] += 1
-            t += dt
-        if seg == num_segments - 1:
-            endpt = eval_poly_at(polyCoeff, p_num1d, seg, T)
-            if len(samples) == 0 or _norm3(samples[-1] - endpt) > 1e-6:
-                samples.append(endpt)
+    samples, seg_counts, n_cand, margin = sample_polynomials(polyCoeff, Time, order, sample_distance)
 
     # climb / turn statistics, ms.cpp:163-195 (printed by the reference, returned here)
     max_climb_rate, min_turn_radius = 0.0, 1.0e12

@@ -2,7 +2,10 @@
 the benchmark's batches, not a spot check.  Sample counts must be equal for every trajectory (the acceptance test
 `seg_len >= sample_distance` of ms.cpp:145 and the loop test `max_dev > 0.2` of ms.cpp:82 are 1-ulp-sensitive discrete
 decisions), every row within 1e-6 m, reweighting iterations / final weights / segment times equal, coefficients within
-1e-8 (position-scaled).  The worst observed margins are printed (pytest -s) so the slack is visible.  (pytest -m gpu)"""
+1e-8 (position-scaled).  Trajectories on which the reference itself is unsound (its dense inverse of M loses up to 12 digits
+when a 0.1 s segment sits among 5 s ones; two builds of the unmodified reference then disagree with each other) are checked
+against 40-digit arithmetic instead -- see oracle/parity.py.  The worst observed margins are printed (pytest -s) and
+appended to gpurun_out/parity_margins.jsonl so the slack is visible.  (pytest -m gpu)"""
 import json
 import os
 
@@ -16,10 +19,17 @@ pytestmark = pytest.mark.gpu
 
 
 def _report(name, p):
-    print(f"\n[parity] {name}: checked {p['checked']} trajectories / {p['rows_checked']} rows, count mismatches "
-          f"{p['count_mismatch']}, max row error {p['max_row_err_m']:.3e} m; coefficients on {p.get('coeff_checked', 0)}: "
-          f"max scaled error {p.get('max_coeff_err', 0.0):.3e}, iters mismatches {p.get('iters_mismatch', 0)}, "
-          f"max |max_dev - ref| {p.get('max_dev_err', 0.0):.3e}  ({p['seconds']:.1f} s on {p['threads']} threads)")
+    ex = p["reference_unsound"]
+    print(f"\n[parity] {name}: {p['checked']} trajectories / {p['rows_checked']} rows vs the compiled reference "
+          f"({p['seconds']:.1f} s on {p['threads']} threads): {p['within_bars_of_reference']} within the bars of the reference "
+          f"(max row error {p['max_row_err_m']:.3e} m, max scaled coefficient error {p['max_coeff_err']:.3e}, "
+          f"max |max_dev - ref| {p['max_dev_err']:.3e}); iters / final-weight / time mismatches "
+          f"{p.get('iters_mismatch', 0)}/{p.get('vw_final_mismatch', 0)}/{p.get('time_mismatch', 0)}; "
+          f"{ex['trajectories']} where the reference itself is unsound, checked against 40-digit arithmetic: GPU max "
+          f"coefficient error {ex['max_coeff_err_vs_exact']:.3e} / row error {ex['max_row_err_vs_exact_m']:.3e} m, the "
+          f"reference's own {ex['max_reference_coeff_err_vs_exact']:.3e} / {ex['max_reference_row_err_vs_exact_m']:.3e} m, "
+          f"worst GPU/reference error ratio {ex['max_gpu_over_reference_coeff_err']:.3g}, decision ties {ex['decision_ties']}, "
+          f"decision mismatches {ex['decision_mismatch']}; unexplained {p['unexplained']}, count mismatches {p['count_mismatch']}")
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     if os.path.isdir(out):                         # kept for profiles/: the observed margins of this run
         with open(os.path.join(out, "parity_margins.jsonl"), "a") as f:
@@ -33,10 +43,10 @@ def test_cfg2_every_trajectory_vs_reference(tool, weights):
     cfg = workloads.synthetic_config(4, weights)
     res = tool.generate_batch(cfg, wp, ns=ns)
     so = np.arange(4097, dtype=np.int64) * ns
-    p = parity.batch_parity(res, wp, so, cfg, n_coeff=512)
+    p = parity.batch_parity(res, wp, so, cfg)
     _report(f"cfg2 {weights}", p)
     parity.assert_parity(p)
-    assert p["checked"] == 4096 and p["coeff_checked"] == 512
+    assert p["checked"] == 4096 == p["coeff_checked"]
 
 
 def test_cfg3_slice_vs_reference(tool):
@@ -46,7 +56,7 @@ def test_cfg3_slice_vs_reference(tool):
     res = tool.generate_batch(cfg, wp, ns=ns)
     so = np.arange((1 << 17) + 1, dtype=np.int64) * ns
     picks = np.arange(60000, 60000 + 2048)
-    p = parity.batch_parity(res, wp, so, cfg, picks=picks, n_coeff=512)
+    p = parity.batch_parity(res, wp, so, cfg, picks=picks)
     _report("cfg3 slice", p)
     parity.assert_parity(p)
 
@@ -62,6 +72,6 @@ def test_cfg5_short_members_vs_reference(tool):
     cost = 0.08 * (ns[order] / 16.0) ** 3                       # thread-seconds per trajectory (shipped weights)
     picks = np.sort(order[np.cumsum(cost) <= 160.0])
     assert picks.shape[0] >= 256 and ns[picks].max() >= 48
-    p = parity.batch_parity(res, wp, so, cfg, picks=picks, n_coeff=128)
+    p = parity.batch_parity(res, wp, so, cfg, picks=picks)
     _report(f"cfg5 members ns<=64 (max ns {ns[picks].max()})", p)
     parity.assert_parity(p)

@@ -8,6 +8,8 @@ from .api import (  # noqa: F401
     AltitudeParams,
     shipped_altitude_params,
     BatchResult,
+    Bezier,
+    BezierConfig,
     MinimumSnapConfig,
     TrajectoryGeneratorTool,
     load_minimum_snap_config,
@@ -19,6 +21,8 @@ __all__ = [
     "AltitudeParams",
     "shipped_altitude_params",
     "BatchResult",
+    "Bezier",
+    "BezierConfig",
     "MinimumSnapConfig",
     "TrajectoryGeneratorTool",
     "load_minimum_snap_config",

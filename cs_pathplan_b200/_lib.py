@@ -82,6 +82,10 @@ SIGNATURES = {
     "msnap_altitude_optimize_batch_host": (_i, [_vp, C.POINTER(msnap_altitude_params), _ll] + [_vp] * 6),
     "msnap_set_altitude_policy": (_i, [_vp, _i]),
     "msnap_cost_map_lookup_dev": (_i, [_vp, _vp, _i, _i, _d, _d, _d, _ll, _vp, _vp, _vp]),
+    "msnap_bezier_generate_batch_dev": (_i, [_vp, _d, _d, _ll, _i, _vp, _vp, _ll, _vp, _vp, _vp]),
+    "msnap_bezier_generate_batch_host": (_i, [_vp, _d, _d, _ll, _i, _vp, _vp, _ll, _vp, _vp, _vp]),
+    "msnap_patrol_postprocess_dev": (_i, [_vp, _d, _ll, _i, _vp, _vp, _vp, _vp, _ll, _vp, _ll, _vp, _vp, _vp]),
+    "msnap_patrol_postprocess_host": (_i, [_vp, _d, _ll, _i, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp]),
     "msnap_profile_begin": (_i, [_vp]),
     "msnap_profile_end": (_i, [_vp, C.c_char_p, _ll]),
     "msnap_debug_phase_clocks": (_i, [_vp, _i, _vp]),

@@ -388,6 +388,113 @@ class TrajectoryGeneratorTool:
         ref = None if reference is None else _f64(reference).reshape(3)
         self._check(self._L.msnap_set_waypoint_frame(self._h, 1 if frame == "wgs84" else 0, _ptr(ref)))
 
+    # ------------------------------------------------------------------ Bezier generator (bezier.cpp:127-189)
+    def bezier_generate_batch(self, waypoints, ns=None, seg_offset=None, sample_distance_override=-1.0, min_radius=1.0,
+                              capacity: Optional[int] = None):
+        """B independent math_util::Bezier::GenerateTrajectoryMatrix calls; host arrays in and out.  ``min_radius`` is
+        BezierConfig::min_radius (1.0 = unconstrained).  Returns (sample_offset [B+1], samples [rows,3], flags [B]).
+        Without ``capacity`` a sizing call (exact row layout, nothing written) precedes the real one."""
+        wp = _f64(waypoints)
+        B, nsu, so, _ = _layout(wp, ns, seg_offset)
+        off = np.zeros(B + 1, dtype=np.int64)
+        flags = np.zeros(B, dtype=np.uint32)
+
+        def call(cap, rows):
+            return self._L.msnap_bezier_generate_batch_host(self._h, float(sample_distance_override), float(min_radius), B, nsu,
+                                                            _ptr(so), _ptr(wp), int(cap), _ptr(off), _ptr(rows), _ptr(flags))
+
+        if capacity is None:
+            self._check(call(0, None), allow=(_lib.ERR_CAPACITY,))
+            capacity = int(off[B])
+        rows = np.empty((max(int(capacity), 1), 3))
+        rc = call(capacity, rows)
+        n = int(min(off[B], capacity))
+        if rc != _lib.OK:
+            err = MsnapError(rc, self._L.msnap_last_error(self._h).decode())
+            err.partial = (off, rows[:n], flags)
+            raise err
+        return off, rows[:n], flags
+
+    def bezier_generate_batch_dev(self, waypoints, sample_offset, samples, ns=None, seg_offset=None,
+                                  sample_distance_override=-1.0, min_radius=1.0, flags=None):
+        """Device tensors (CUDA torch): enqueued on the handle's stream.  samples may be None (sizing call)."""
+        def dp(t):
+            return None if t is None else int(t.data_ptr())
+
+        B = int(sample_offset.numel()) - 1
+        self._check(self._L.msnap_bezier_generate_batch_dev(
+            self._h, float(sample_distance_override), float(min_radius), B, int(ns or 0), dp(seg_offset), dp(waypoints),
+            0 if samples is None else int(samples.shape[0]), dp(sample_offset), dp(samples), dp(flags)))
+
+    def Bezier_3D(self, Enu_waypoint, distance, V_avg_override=-1.0, min_radius=0.0) -> np.ndarray:
+        """UavPathPlanner::Bezier_3D (uavPathPlanning.cpp:4477-4505): fewer than 2 waypoints -> empty; BezierConfig::
+        min_radius = 300 whenever ``min_radius`` > 0 (the planner's own hard-coded value, cpp:4491-4494)."""
+        wp = np.asarray(Enu_waypoint, dtype=np.float64).reshape(-1, 3)
+        if wp.shape[0] < 2:
+            return np.zeros((0, 3))
+        _, rows, _ = self.bezier_generate_batch(wp, ns=wp.shape[0] - 1, sample_distance_override=distance,
+                                                min_radius=300.0 if min_radius > 0 else 1.0)
+        return rows
+
+    # ------------------------------------------------------------------ single-loop patrols (cpp:1829-1906)
+    @staticmethod
+    def close_patrol_zone(patrol_zone) -> np.ndarray:
+        """The waypoint list gen_single_patrol hands to Minisnap_3D: P0..Pn-1, P0, P1 (cpp:1841-1847)."""
+        z = np.asarray(patrol_zone, dtype=np.float64).reshape(-1, 3)
+        return np.vstack([z, z[:1], z[1:2]])
+
+    def patrol_postprocess(self, waypoints, sample_offset, samples, distance, ns=None, seg_offset=None, keep_up=None,
+                           capacity: Optional[int] = None):
+        """gen_single_patrol's post-processing of Minisnap_3D's rows for B closed loops (cpp:1857-1903); host arrays.
+        ``waypoints`` are the CLOSED lists (close_patrol_zone).  Returns (out_offset [B+1], out_rows, flags [B])."""
+        wp = _f64(waypoints)
+        B, nsu, so, _ = _layout(wp, ns, seg_offset)
+        soff = np.ascontiguousarray(sample_offset, dtype=np.int64)
+        rows = _f64(samples).reshape(-1, 3)
+        if soff.shape != (B + 1,) or soff[-1] > rows.shape[0]:
+            raise ValueError("sample_offset must have B + 1 entries covering `samples`")
+        ku = None if keep_up is None else _f64(keep_up).reshape(B)
+        off = np.zeros(B + 1, dtype=np.int64)
+        flags = np.zeros(B, dtype=np.uint32)
+
+        def call(cap, out):
+            return self._L.msnap_patrol_postprocess_host(self._h, float(distance), B, nsu, _ptr(so), _ptr(wp), _ptr(soff),
+                                                         _ptr(rows), _ptr(ku), int(cap), _ptr(off), _ptr(out), _ptr(flags))
+
+        if capacity is None:
+            self._check(call(0, None), allow=(_lib.ERR_CAPACITY,))
+            capacity = int(off[B])
+        out = np.empty((max(int(capacity), 1), 3))
+        self._check(call(capacity, out))
+        return off, out[:int(off[B])], flags
+
+    def patrol_postprocess_dev(self, waypoints, sample_offset, samples, distance, out_offset, out_rows, ns=None,
+                               seg_offset=None, keep_up=None, flags=None):
+        """Device tensors; enqueued on the handle's stream.  out_rows may be None (sizing call: out_offset only)."""
+        def dp(t):
+            return None if t is None else int(t.data_ptr())
+
+        B = int(sample_offset.numel()) - 1
+        self._check(self._L.msnap_patrol_postprocess_dev(
+            self._h, float(distance), B, int(ns or 0), dp(seg_offset), dp(waypoints), dp(sample_offset), dp(samples),
+            int(samples.shape[0]), dp(keep_up), 0 if out_rows is None else int(out_rows.shape[0]), dp(out_offset), dp(out_rows),
+            dp(flags)))
+
+    def gen_single_patrol(self, patrol_zone, distance, cfg: MinimumSnapConfig, leader_speed: float, trajectory_enu=None):
+        """UavPathPlanner::gen_single_patrol (cpp:1829-1906) for one polygon: close it, Minisnap_3D(closed, distance,
+        leader_speed), trim / level / close / self-intersection fallback.  ``trajectory_enu``: the rows flown before the
+        patrol (its last `up` is kept, cpp:1839).  Fewer than 3 vertices or an empty generator result -> (0,3)."""
+        zone = np.asarray(patrol_zone, dtype=np.float64).reshape(-1, 3)
+        if zone.shape[0] < 3:
+            return np.zeros((0, 3))
+        closed = self.close_patrol_zone(zone)
+        res = self.generate_batch(cfg, closed, ns=closed.shape[0] - 1, sample_distance_override=distance,
+                                  v_avg_override=leader_speed, stats=False)
+        te = None if trajectory_enu is None else np.asarray(trajectory_enu, dtype=np.float64).reshape(-1, 3)
+        keep = None if te is None or te.shape[0] == 0 else np.array([te[-1, 2]])
+        _, rows, _ = self.patrol_postprocess(closed, res.sample_offset, res.samples, distance, ns=closed.shape[0] - 1, keep_up=keep)
+        return rows
+
     # ------------------------------------------------------------------ batched, host buffers
     def solve_qp_batch(self, order, waypoints, times, ns=None, seg_offset=None, vel=None, acc=None,
                        path_weight=0.0, vel_zero_weight=0.0):
@@ -493,3 +600,32 @@ class TrajectoryGeneratorTool:
             None if seg_offset is None else int(seg_offset.data_ptr()), int(waypoints.data_ptr()),
             int(rows_out.data_ptr()))
         self._check(rc)
+
+
+@dataclass
+class BezierConfig:
+    """struct BezierConfig, bezier.hpp:91-96."""
+
+    min_radius: float = 1.0
+
+
+class Bezier:
+    """GPU-backed stand-in for math_util::Bezier (bezier.hpp:98-120): SetConfig + GenerateTrajectoryMatrix."""
+
+    def __init__(self, tool: Optional[TrajectoryGeneratorTool] = None, device: int = 0):
+        self._tool = tool or TrajectoryGeneratorTool(device)
+        self._config = BezierConfig()
+
+    def SetConfig(self, config: BezierConfig):
+        self._config = config
+
+    def GenerateTrajectoryMatrix(self, Path, yaml_path: str = "", sample_distance_override=-1.0, v_avg_override=-1.0):
+        """bezier.cpp:127-189.  Path (n,3) -> sampled points (M,3); fewer than 2 rows -> an empty (0,3) matrix
+        (bezier.cpp:129-131).  yaml_path and v_avg_override are unused, as in the reference."""
+        Path = np.asarray(Path, dtype=np.float64)
+        if Path.ndim != 2 or Path.shape[0] < 2:
+            return np.zeros((0, 3))
+        wp = _f64(Path[:, :3])
+        _, rows, _ = self._tool.bezier_generate_batch(wp, ns=wp.shape[0] - 1, sample_distance_override=sample_distance_override,
+                                                      min_radius=self._config.min_radius)
+        return rows

@@ -19,6 +19,8 @@
 #include "msnap_fused.cuh"
 #include "msnap_geo.cuh"
 #include "msnap_alt.cuh"
+#include "msnap_bezier.cuh"
+#include "msnap_patrol.cuh"
 
 static const MsnapOrderTab h_tab[MSNAP_MAX_ORDER - MSNAP_MIN_ORDER + 1] = MSNAP_ORDER_TABLES;
 
@@ -1538,6 +1540,185 @@ int msnap_sample_bound_host(msnap_handle h, const msnap_config *cfg, double v_av
     MS_CUDA(h, cudaMemcpyAsync(rows_out, d_rows, sizeof(long long), cudaMemcpyDeviceToHost, st));
     MS_CUDA(h, cudaStreamSynchronize(st));
     return MSNAP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- Bezier generator
+// math_util::Bezier::GenerateTrajectoryMatrix for B trajectories (bezier.cpp:127-189); see msnap_bezier.cuh.
+static int bezier_dev(msnap_context *h, double resolution, double min_radius, long long B, int ns_uniform,
+                      const long long *seg_offset, long long n_seg, const double *wp, long long capacity,
+                      long long *sample_offset, double *samples, unsigned *flags) {
+    BatchIdx bi{B, n_seg, ns_uniform > 0 ? ns_uniform : 0, ns_uniform > 0 ? nullptr : seg_offset};
+    const bool ragged = bi.ns_uniform <= 0 && B < 2000000000LL;
+    int rc = arena_reserve(h, h->ws, padded((size_t)n_seg * BEZ_WS * sizeof(double)) + padded(n_seg * sizeof(long long)) +
+                                         padded(B * sizeof(long long)) + padded((size_t)(B / SCAN_BLOCK + 2) * sizeof(long long)) +
+                                         (ragged ? padded(n_seg * sizeof(int)) : 0));
+    if (rc) return rc;
+    double *ws = arena_take<double>(h->ws, (size_t)n_seg * BEZ_WS);
+    long long *seg_start = arena_take<long long>(h->ws, n_seg);
+    long long *traj_count = arena_take<long long>(h->ws, B);
+    long long *partial = arena_take<long long>(h->ws, B / SCAN_BLOCK + 2);
+    if (ragged) {
+        int *st = arena_take<int>(h->ws, n_seg);
+        MS_LAUNCH(h, k_seg_traj, grid_for(B * 32, 256), 256, B, seg_offset, st);
+        bi.seg_traj = st;
+    }
+    if (flags) MS_CUDA(h, cudaMemsetAsync(flags, 0, B * sizeof(unsigned), h->stream));
+    MS_LAUNCH(h, k_bezier_prep, grid_for(n_seg, 128), 128, bi, wp, resolution, min_radius, ws, flags);
+    MS_LAUNCH(h, k_bezier_rows, grid_for(B, 128), 128, bi, ws, seg_start, traj_count);
+    const int nblk = (int)grid_for(B, SCAN_BLOCK);
+    MS_LAUNCH(h, k_scan_reduce, nblk, SCAN_BLOCK, traj_count, B, partial);
+    MS_LAUNCH(h, k_scan_partials, 1, SCAN_BLOCK, partial, nblk, sample_offset + B);
+    MS_LAUNCH(h, k_scan_apply, nblk, SCAN_BLOCK, traj_count, B, partial, sample_offset);
+    if (capacity > 0)
+        MS_LAUNCH(h, k_bezier_write, grid_for(n_seg, 128), 128, bi, wp, ws, seg_start, sample_offset, capacity, samples, flags);
+    return MSNAP_OK;
+}
+
+extern "C" int msnap_bezier_generate_batch_dev(msnap_handle h, double sample_distance_override, double min_radius, long long B,
+                                               int ns_uniform, const long long *seg_offset, const double *waypoints,
+                                               long long sample_capacity, long long *sample_offset_out, double *samples_out,
+                                               unsigned *flags_out) {
+    if (!h) return MSNAP_ERR_INVALID_ARG;
+    int rc = check_batch(B, ns_uniform, seg_offset, waypoints);
+    if (rc) return rc;
+    if (!sample_offset_out || (!samples_out && sample_capacity > 0) || sample_capacity < 0 || !std::isfinite(sample_distance_override) ||
+        !(min_radius == min_radius))
+        return MSNAP_ERR_INVALID_ARG;
+    if (B == 0) return MSNAP_OK;
+    DeviceGuard guard(h->device);
+    long long n_seg = 0;
+    rc = device_total_segments(h, B, ns_uniform, seg_offset, &n_seg);
+    if (rc) return rc;
+    const double resolution = sample_distance_override > 0.0 ? sample_distance_override : 1.0;  // bezier.cpp:133-136
+    return bezier_dev(h, resolution, min_radius, B, ns_uniform, seg_offset, n_seg, waypoints, sample_capacity, sample_offset_out,
+                      samples_out, flags_out);
+}
+
+extern "C" int msnap_bezier_generate_batch_host(msnap_handle h, double sample_distance_override, double min_radius, long long B,
+                                                int ns_uniform, const long long *seg_offset, const double *waypoints,
+                                                long long sample_capacity, long long *sample_offset_out, double *samples_out,
+                                                unsigned *flags_out) {
+    if (!h) return MSNAP_ERR_INVALID_ARG;
+    int rc = check_batch(B, ns_uniform, seg_offset, waypoints);
+    if (rc) return rc;
+    if (!sample_offset_out || (!samples_out && sample_capacity > 0) || sample_capacity < 0 || !std::isfinite(sample_distance_override) ||
+        !(min_radius == min_radius))
+        return MSNAP_ERR_INVALID_ARG;
+    if (B == 0) { sample_offset_out[0] = 0; return MSNAP_OK; }
+    if (!valid_host_offsets(B, ns_uniform, seg_offset)) return MSNAP_ERR_INVALID_ARG;
+    DeviceGuard guard(h->device);
+    const long long n_seg = host_total_segments(B, ns_uniform, seg_offset);
+    const size_t n_pts = (size_t)(n_seg + B);
+    MS_CUDA(h, cudaStreamSynchronize(h->aux));
+    rc = arena_reserve(h, h->io, 2 * padded((B + 1) * sizeof(long long)) + padded(n_pts * 3 * sizeof(double)) +
+                                     padded(B * sizeof(unsigned)) + padded((size_t)sample_capacity * 3 * sizeof(double)));
+    if (rc) return rc;
+    long long *d_off = arena_take<long long>(h->io, B + 1), *d_so = arena_take<long long>(h->io, B + 1);
+    double *d_wp = arena_take<double>(h->io, n_pts * 3);
+    unsigned *d_fl = arena_take<unsigned>(h->io, B);
+    double *d_s = arena_take<double>(h->io, (size_t)sample_capacity * 3);
+    cudaStream_t st = h->stream;
+    if (ns_uniform <= 0) MS_CUDA(h, cudaMemcpyAsync(d_off, seg_offset, (B + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    MS_CUDA(h, cudaMemcpyAsync(d_wp, waypoints, n_pts * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    const double resolution = sample_distance_override > 0.0 ? sample_distance_override : 1.0;
+    rc = bezier_dev(h, resolution, min_radius, B, ns_uniform, ns_uniform > 0 ? nullptr : d_off, n_seg, d_wp, sample_capacity, d_so,
+                    d_s, d_fl);
+    if (rc) return rc;
+    MS_CUDA(h, cudaMemcpyAsync(sample_offset_out, d_so, (B + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    if (flags_out) MS_CUDA(h, cudaMemcpyAsync(flags_out, d_fl, B * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    MS_CUDA(h, cudaStreamSynchronize(st));
+    const long long total = sample_offset_out[B], rows = total < sample_capacity ? total : sample_capacity;
+    if (rows > 0) {
+        MS_CUDA(h, cudaMemcpyAsync(samples_out, d_s, (size_t)rows * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        MS_CUDA(h, cudaStreamSynchronize(st));
+    }
+    return total > sample_capacity ? MSNAP_ERR_CAPACITY : MSNAP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- patrol post-processing
+// gen_single_patrol after Minisnap_3D (uavPathPlanning.cpp:1857-1903); see msnap_patrol.cuh.
+extern "C" int msnap_patrol_postprocess_dev(msnap_handle h, double distance, long long B, int ns_uniform,
+                                            const long long *seg_offset, const double *waypoints,
+                                            const long long *sample_offset, const double *samples, long long sample_capacity,
+                                            const double *keep_up, long long out_capacity, long long *out_offset,
+                                            double *out_rows, unsigned *flags_out) {
+    if (!h) return MSNAP_ERR_INVALID_ARG;
+    int rc = check_batch(B, ns_uniform, seg_offset, waypoints);
+    if (rc) return rc;
+    if (!sample_offset || (!samples && sample_capacity > 0) || sample_capacity < 0 || !out_offset || out_capacity < 0 ||
+        (!out_rows && out_capacity > 0) || !(distance == distance) || (ns_uniform > 0 && ns_uniform < 4))
+        return MSNAP_ERR_INVALID_ARG;  // a patrol polygon has >= 3 vertices: >= 5 closed waypoints, >= 4 segments
+    if (B == 0) return MSNAP_OK;
+    DeviceGuard guard(h->device);
+    long long n_seg = 0;
+    rc = device_total_segments(h, B, ns_uniform, seg_offset, &n_seg);
+    if (rc) return rc;
+    BatchIdx bi{B, n_seg, ns_uniform > 0 ? ns_uniform : 0, ns_uniform > 0 ? nullptr : seg_offset};
+    rc = arena_reserve(h, h->ws, 2 * padded(B * sizeof(long long)) + padded((size_t)(B / SCAN_BLOCK + 2) * sizeof(long long)) +
+                                     padded(B * sizeof(unsigned)));
+    if (rc) return rc;
+    long long *best = arena_take<long long>(h->ws, B), *count = arena_take<long long>(h->ws, B);
+    long long *partial = arena_take<long long>(h->ws, B / SCAN_BLOCK + 2);
+    unsigned *fl = flags_out ? flags_out : arena_take<unsigned>(h->ws, B);
+    MS_LAUNCH(h, k_patrol_count, (unsigned)B, PATROL_THREADS, bi, waypoints, sample_offset, samples, sample_capacity, keep_up,
+              distance, best, count, fl);
+    const int nblk = (int)grid_for(B, SCAN_BLOCK);
+    MS_LAUNCH(h, k_scan_reduce, nblk, SCAN_BLOCK, count, B, partial);
+    MS_LAUNCH(h, k_scan_partials, 1, SCAN_BLOCK, partial, nblk, out_offset + B);
+    MS_LAUNCH(h, k_scan_apply, nblk, SCAN_BLOCK, count, B, partial, out_offset);
+    if (out_capacity > 0)
+        MS_LAUNCH(h, k_patrol_write, (unsigned)B, PATROL_THREADS, bi, waypoints, sample_offset, samples, keep_up, distance, best,
+                  out_offset, out_capacity, out_rows, fl);
+    return MSNAP_OK;
+}
+
+extern "C" int msnap_patrol_postprocess_host(msnap_handle h, double distance, long long B, int ns_uniform,
+                                             const long long *seg_offset, const double *waypoints,
+                                             const long long *sample_offset, const double *samples, const double *keep_up,
+                                             long long out_capacity, long long *out_offset, double *out_rows,
+                                             unsigned *flags_out) {
+    if (!h) return MSNAP_ERR_INVALID_ARG;
+    int rc = check_batch(B, ns_uniform, seg_offset, waypoints);
+    if (rc) return rc;
+    if (!sample_offset || !out_offset || out_capacity < 0 || (!out_rows && out_capacity > 0)) return MSNAP_ERR_INVALID_ARG;
+    if (B == 0) { out_offset[0] = 0; return MSNAP_OK; }
+    if (!valid_host_offsets(B, ns_uniform, seg_offset) || sample_offset[0] != 0) return MSNAP_ERR_INVALID_ARG;
+    for (long long b = 0; b < B; ++b)
+        if (sample_offset[b + 1] < sample_offset[b]) return MSNAP_ERR_INVALID_ARG;
+    const long long n_rows = sample_offset[B];
+    if (n_rows > 0 && !samples) return MSNAP_ERR_INVALID_ARG;
+    DeviceGuard guard(h->device);
+    const long long n_seg = host_total_segments(B, ns_uniform, seg_offset);
+    const size_t n_pts = (size_t)(n_seg + B);
+    MS_CUDA(h, cudaStreamSynchronize(h->aux));
+    rc = arena_reserve(h, h->io, 3 * padded((B + 1) * sizeof(long long)) + padded(n_pts * 3 * sizeof(double)) +
+                                     padded((size_t)n_rows * 3 * sizeof(double)) + padded(B * sizeof(double)) +
+                                     padded(B * sizeof(unsigned)) + padded((size_t)out_capacity * 3 * sizeof(double)));
+    if (rc) return rc;
+    long long *d_off = arena_take<long long>(h->io, B + 1), *d_so = arena_take<long long>(h->io, B + 1),
+              *d_oo = arena_take<long long>(h->io, B + 1);
+    double *d_wp = arena_take<double>(h->io, n_pts * 3), *d_s = arena_take<double>(h->io, (size_t)n_rows * 3);
+    double *d_up = arena_take<double>(h->io, B);
+    unsigned *d_fl = arena_take<unsigned>(h->io, B);
+    double *d_out = arena_take<double>(h->io, (size_t)out_capacity * 3);
+    cudaStream_t st = h->stream;
+    if (ns_uniform <= 0) MS_CUDA(h, cudaMemcpyAsync(d_off, seg_offset, (B + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    MS_CUDA(h, cudaMemcpyAsync(d_so, sample_offset, (B + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    MS_CUDA(h, cudaMemcpyAsync(d_wp, waypoints, n_pts * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (n_rows > 0) MS_CUDA(h, cudaMemcpyAsync(d_s, samples, (size_t)n_rows * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (keep_up) MS_CUDA(h, cudaMemcpyAsync(d_up, keep_up, B * sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = msnap_patrol_postprocess_dev(h, distance, B, ns_uniform, ns_uniform > 0 ? nullptr : d_off, d_wp, d_so, d_s, n_rows,
+                                      keep_up ? d_up : nullptr, out_capacity, d_oo, d_out, d_fl);
+    if (rc) return rc;
+    MS_CUDA(h, cudaMemcpyAsync(out_offset, d_oo, (B + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    if (flags_out) MS_CUDA(h, cudaMemcpyAsync(flags_out, d_fl, B * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    MS_CUDA(h, cudaStreamSynchronize(st));
+    const long long total = out_offset[B], rows = total < out_capacity ? total : out_capacity;
+    if (rows > 0) {
+        MS_CUDA(h, cudaMemcpyAsync(out_rows, d_out, (size_t)rows * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        MS_CUDA(h, cudaStreamSynchronize(st));
+    }
+    return total > out_capacity ? MSNAP_ERR_CAPACITY : MSNAP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------- single

@@ -251,6 +251,57 @@ int msnap_cost_map_lookup_dev(msnap_handle h, const float *grid, int width, int 
                               double origin_y, long long n_rows_cap, const long long *n_rows_dev, const double *rows,
                               double *elev_out);
 
+/* ---- Bezier generator, batched -----------------------------------------------------
+ * Drop-in for math_util::Bezier::GenerateTrajectoryMatrix (/root/reference/math_util/bezier.hpp:98-120, bezier.cpp:127-189
+ * around Bezier::GeneratePath, bezier.cpp:29-118): the reference's alternative trajectory generator, selected by
+ * getPlan(algorithm == "bezier") through UavPathPlanner::Bezier_3D (uavPathPlanning.cpp:3691-3692, 4477-4505).  Same batch
+ * layout as msnap_generate_batch_*: one call = B independent GenerateTrajectoryMatrix calls.
+ *   sample_distance_override : the path resolution in metres; <= 0 means 1.0 (bezier.cpp:133-136)
+ *   min_radius               : BezierConfig::min_radius (bezier.hpp:91-96; default 1.0 = no curvature constraint; Bezier_3D
+ *                              sets 300 whenever its own min_radius argument is > 0, cpp:4491-4494)
+ *   sample_offset_out [B+1]  : exact CSR layout of the rows (always complete, also with sample_capacity = 0: the sizing call)
+ *   samples_out [capacity][3]: rows beyond sample_capacity are dropped (MSNAP_FLAG_TRUNCATED; _host: MSNAP_ERR_CAPACITY)
+ *   flags_out [B]            : optional; MSNAP_FLAG_NONFINITE = a non-finite or absurdly long segment (more than 1e7 samples)
+ *                              was replaced by its end waypoint instead of spinning in bezier.cpp:109
+ * Row counts are the reference's (the number of accumulated `t += resolution / dis` steps <= 1, bezier.cpp:109), rows agree
+ * to the rounding of atan2 / cos / sin / hypot (1e-12 m; tests: 1e-9 m).  yaml_path and v_avg_override of the reference
+ * signature are unused there (bezier.cpp:127) and have no counterpart here. */
+int msnap_bezier_generate_batch_dev(msnap_handle h, double sample_distance_override, double min_radius, long long B,
+                                    int ns_uniform, const long long *seg_offset, const double *waypoints,
+                                    long long sample_capacity, long long *sample_offset_out, double *samples_out,
+                                    unsigned *flags_out);
+int msnap_bezier_generate_batch_host(msnap_handle h, double sample_distance_override, double min_radius, long long B,
+                                     int ns_uniform, const long long *seg_offset, const double *waypoints,
+                                     long long sample_capacity, long long *sample_offset_out, double *samples_out,
+                                     unsigned *flags_out);
+
+/* ---- single-loop patrol post-processing on the sampled rows ----------------------------
+ * What UavPathPlanner::gen_single_patrol does with Minisnap_3D's output (/root/reference/uavPathPlanning.cpp:1829-1906,
+ * helpers cpp:118-206).  The caller closes each patrol polygon P0..Pn-1 into the waypoints P0..Pn-1, P0, P1 (cpp:1841-1847)
+ * and runs msnap_generate_batch_* on them with getPlan's overrides (cpp:1849); this call then, per trajectory: trims the loop
+ * at the sample closest to the second P0 (cpp:1857-1879), sets `up` to keep_up and closes the loop with its first sample
+ * (cpp:1885-1892), tests it for a horizontal self-intersection (hasSelfIntersection2D, cpp:152-177) and, if there is one,
+ * replaces it by the polygon boundary sampled every `distance` metres (sampleClosedPolygonBoundary, cpp:179-206, 1897-1903).
+ *   waypoints / ns_uniform / seg_offset : the CLOSED waypoint lists the generate call took (>= 5 points per trajectory)
+ *   sample_offset [B+1], samples        : that call's outputs; rows at or beyond sample_capacity are treated as absent
+ *   keep_up [B] or NULL                 : the height the loop is flown at (cpp:1839: the last `up` of the trajectory flown
+ *                                         before it); NULL = the polygon's first vertex
+ *   out_offset [B+1]                    : exact CSR layout of the result (always complete, also with out_capacity = 0)
+ *   out_rows [out_capacity][3]          : the patrol loops; rows beyond the capacity are dropped (MSNAP_FLAG_TRUNCATED; _host
+ *                                         returns MSNAP_ERR_CAPACITY)
+ *   flags_out [B], optional             : bit 0 = the generator had produced no rows (cpp:1850-1855: empty result), bit 2 =
+ *                                         self-intersection, boundary sampling used
+ * Decisions (trim index, intersection verdict, fallback row count) are the reference's bit for bit: they are comparisons of
+ * sums and products of the input doubles evaluated in the reference's order. */
+int msnap_patrol_postprocess_dev(msnap_handle h, double distance, long long B, int ns_uniform, const long long *seg_offset,
+                                 const double *waypoints, const long long *sample_offset, const double *samples,
+                                 long long sample_capacity, const double *keep_up, long long out_capacity,
+                                 long long *out_offset, double *out_rows, unsigned *flags_out);
+int msnap_patrol_postprocess_host(msnap_handle h, double distance, long long B, int ns_uniform, const long long *seg_offset,
+                                  const double *waypoints, const long long *sample_offset, const double *samples,
+                                  const double *keep_up, long long out_capacity, long long *out_offset, double *out_rows,
+                                  unsigned *flags_out);
+
 /* ---- per-kernel timing (bench.py's roofline pass) ------------------------------------------------------------
  * Between begin and end every kernel the handle launches is bracketed by a CUDA event pair on the launching stream.
  * msnap_profile_end synchronises and writes a JSON object {"<kernel>": {"launches": n, "total_ms": t}, ...}. */

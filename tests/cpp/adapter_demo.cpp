@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <exception>
 
+#include "bezier_gpu.hpp"
 #include "geo_transform_gpu.hpp"
 #include "minimum_snap_gpu.hpp"
 
@@ -74,6 +75,15 @@ int main(int argc, char **argv) {
         for (size_t i = 0; i < e.size(); ++i)
             std::printf("%.17g %.17g %.17g %.17g %.17g %.17g\n", e[i].east, e[i].north, e[i].up, back[i].lon, back[i].lat,
                         back[i].alt);
+        // the alternative generator, as UavPathPlanner::Bezier_3D drives it (uavPathPlanning.cpp:4489-4499)
+        math_util::Bezier bezier;
+        math_util::BezierConfig bconfig;
+        bezier.SetConfig(bconfig);
+        Eigen::MatrixXd bz = bezier.GenerateTrajectoryMatrix(route, "", 300.0, leader_speed);
+        std::printf("bezier %ld\n", static_cast<long>(bz.rows()));
+        for (long i = 0; i < static_cast<long>(bz.rows()); ++i) std::printf("%.17g %.17g %.17g\n", bz(i, 0), bz(i, 1), bz(i, 2));
+        std::printf("bezier_short %ld %ld\n", static_cast<long>(bezier.GenerateTrajectoryMatrix(one, "").rows()),
+                    static_cast<long>(bezier.GenerateTrajectoryMatrix(one, "").cols()));
     } catch (const std::exception &e) {
         std::printf("exception %s\n", e.what());
         return 3;

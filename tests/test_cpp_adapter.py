@@ -1,4 +1,4 @@
-"""The C++ drop-in header include/minimum_snap_gpu.hpp: compiles against an Eigen API (the oracle shim here), links
+"""The C++ drop-in headers include/minimum_snap_gpu.hpp, include/bezier_gpu.hpp and include/geo_transform_gpu.hpp: compiles against an Eigen API (the oracle shim here), links
 with the C-ABI library, refuses to run without a GPU (CPU test) and reproduces the golden vectors on one (GPU test)."""
 import os
 import subprocess
@@ -62,3 +62,12 @@ def test_adapter_reproduces_golden(golden, speed, name):
     assert np.abs(rows[:, :3] - geo.README_ENU).max() <= 1e-7
     assert np.abs(rows[:, 3:5] - geo.README_WGS84_BACK[:, :2]).max() <= 1e-12
     assert np.abs(rows[:, 5] - geo.README_WGS84_BACK[:, 2]).max() <= 1e-6
+    # the Bezier drop-in (include/bezier_gpu.hpp) against the compiled reference's golden rows
+    k = 4 + n + 6 + 7
+    assert lines[k].split()[0] == "bezier"
+    nb = int(lines[k].split()[1])
+    bz = np.array([[float(v) for v in ln.split()] for ln in lines[k + 1:k + 1 + nb]])
+    z = np.load(os.path.join(ROOT, "tests", "golden", "bezier_golden.npz"))
+    want = z["uav31_0_d300/rows"]
+    assert bz.shape == want.shape and np.abs(bz - want).max() <= 1e-9
+    assert lines[k + 1 + nb].split() == ["bezier_short", "0", "3"]

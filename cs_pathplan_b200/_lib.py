@@ -86,6 +86,9 @@ SIGNATURES = {
     "msnap_bezier_generate_batch_host": (_i, [_vp, _d, _d, _ll, _i, _vp, _vp, _ll, _vp, _vp, _vp]),
     "msnap_patrol_postprocess_dev": (_i, [_vp, _d, _ll, _i, _vp, _vp, _vp, _vp, _ll, _vp, _ll, _vp, _vp, _vp]),
     "msnap_patrol_postprocess_host": (_i, [_vp, _d, _ll, _i, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp]),
+    "msnap_formation_distance": (_d, [_d, _d, _d]),
+    "msnap_followers_dev": (_i, [_vp, _i, _d, _i, _i, _i, _vp, _vp, _ll, _vp, _vp, _ll, _ll, _vp]),
+    "msnap_followers_host": (_i, [_vp, _i, _d, _i, _i, _i, _vp, _vp, _ll, _vp, _vp, _vp]),
     "msnap_profile_begin": (_i, [_vp]),
     "msnap_profile_end": (_i, [_vp, C.c_char_p, _ll]),
     "msnap_debug_phase_clocks": (_i, [_vp, _i, _vp]),

@@ -495,6 +495,69 @@ class TrajectoryGeneratorTool:
         _, rows, _ = self.patrol_postprocess(closed, res.sample_offset, res.samples, distance, ns=closed.shape[0] - 1, keep_up=keep)
         return rows
 
+    # ------------------------------------------------------------------ follower formations (cpp:3931-4398)
+    @staticmethod
+    def formation_parameters(cfg_formation_distance=50.0, cfg_position_misalignment=0.0, cfg_uav_formation_max_row=8,
+                             cfg_uav_R=2.0, in_formation_distance=-1.0, in_position_misalignment=-1.0, in_uav_R=-1.0,
+                             in_uav_formation_max_row=0):
+        """(formation_distance, uav_formation_max_row) as generateFollowerTrajectories derives them: config.yaml values
+        (hpp:185, 190, 198-199) overridden by the input JSON's (hpp:85-89; cpp:4036-4042), max_row >= 1, and the lower bound
+        (2 * position_misalignment + uav_R) * 1.41421 on the distance (cpp:4044-4051)."""
+        d, pm, mr, r = cfg_formation_distance, cfg_position_misalignment, cfg_uav_formation_max_row, cfg_uav_R
+        if in_formation_distance > 0.0:
+            d = in_formation_distance
+        if in_position_misalignment >= 0.0:
+            pm = in_position_misalignment
+        if in_uav_R > 0.0:
+            r = in_uav_R
+        if in_uav_formation_max_row > 0:
+            mr = in_uav_formation_max_row
+        return float(_lib.lib().msnap_formation_distance(float(d), float(pm), float(r))), max(int(mr), 1)
+
+    def followers_batch(self, leader_rows, row_offset, formation_model, formation_distance, n_followers,
+                        uav_formation_max_row=8, frame="wgs84", reference=None, starts_wgs84=None) -> np.ndarray:
+        """Follower trajectories of B leader trajectories (rows [n,3] ENU with CSR row_offset [B+1]); host arrays.
+        Returns rows [n_followers * n, 3]: trajectory b's block starts at n_followers * row_offset[b], follower-major.
+        ``formation_distance`` is the value AFTER the lower bound (formation_parameters)."""
+        rows = _f64(leader_rows).reshape(-1, 3)
+        off = np.ascontiguousarray(row_offset, dtype=np.int64)
+        B = off.shape[0] - 1
+        if B < 0 or off[0] != 0 or off[-1] != rows.shape[0]:
+            raise ValueError("row_offset must start at 0 and end at the number of rows")
+        if frame not in ("enu", "wgs84"):
+            raise ValueError("frame must be 'enu' or 'wgs84'")
+        ref = None if reference is None else _f64(reference).reshape(3)
+        st = None if starts_wgs84 is None else _f64(starts_wgs84).reshape(int(n_followers), 3)
+        out = np.empty((int(n_followers) * rows.shape[0], 3))
+        self._check(self._L.msnap_followers_host(self._h, int(formation_model), float(formation_distance),
+                                                 int(uav_formation_max_row), int(n_followers), 1 if frame == "wgs84" else 0,
+                                                 _ptr(ref), _ptr(st), B, _ptr(off), _ptr(rows), _ptr(out)))
+        return out
+
+    def followers_dev(self, leader_rows, row_offset, out_rows, formation_model, formation_distance, n_followers,
+                      uav_formation_max_row=8, frame="wgs84", reference=None, starts_wgs84=None):
+        """Device tensors (leader_rows fp64 [cap,3], row_offset int64 [B+1], out_rows fp64 [>= n_followers * rows, 3],
+        starts_wgs84 fp64 [n_followers,3] or None); enqueued on the handle's stream."""
+        ref = None if reference is None else _f64(reference).reshape(3)
+        self._check(self._L.msnap_followers_dev(
+            self._h, int(formation_model), float(formation_distance), int(uav_formation_max_row), int(n_followers),
+            1 if frame == "wgs84" else 0, _ptr(ref), None if starts_wgs84 is None else int(starts_wgs84.data_ptr()),
+            int(row_offset.numel()) - 1, int(row_offset.data_ptr()), int(leader_rows.data_ptr()), int(leader_rows.shape[0]),
+            int(out_rows.shape[0]), int(out_rows.data_ptr())))
+
+    def generateFollowerTrajectories(self, Trajectory_ENU, origin, formation_model, uav_start_point_wgs84, **params):
+        """UavPathPlanner::generateFollowerTrajectories (cpp:3931-4074) for one leader trajectory: returns [F, N, 3] rows
+        {lon, lat, alt}, one block per follower (the reference's JSON rows without the uav ids).  ``params`` are the
+        keyword arguments of ``formation_parameters``."""
+        traj = _f64(Trajectory_ENU).reshape(-1, 3)
+        starts = _f64(uav_start_point_wgs84).reshape(-1, 3)
+        d, mr = self.formation_parameters(**params)
+        F, N = starts.shape[0], traj.shape[0]
+        if F == 0 or N == 0:
+            return np.zeros((F, N, 3))
+        out = self.followers_batch(traj, np.array([0, N], dtype=np.int64), formation_model, d, F, mr, "wgs84", origin, starts)
+        return out.reshape(F, N, 3)
+
     # ------------------------------------------------------------------ batched, host buffers
     def solve_qp_batch(self, order, waypoints, times, ns=None, seg_offset=None, vel=None, acc=None,
                        path_weight=0.0, vel_zero_weight=0.0):

@@ -21,6 +21,7 @@
 #include "msnap_alt.cuh"
 #include "msnap_bezier.cuh"
 #include "msnap_patrol.cuh"
+#include "msnap_follow.cuh"
 
 static const MsnapOrderTab h_tab[MSNAP_MAX_ORDER - MSNAP_MIN_ORDER + 1] = MSNAP_ORDER_TABLES;
 
@@ -1719,6 +1720,74 @@ extern "C" int msnap_patrol_postprocess_host(msnap_handle h, double distance, lo
         MS_CUDA(h, cudaStreamSynchronize(st));
     }
     return total > out_capacity ? MSNAP_ERR_CAPACITY : MSNAP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- follower formations
+// generateFollowerTrajectories (uavPathPlanning.cpp:3931-4398); see msnap_follow.cuh.
+extern "C" double msnap_formation_distance(double formation_distance, double position_misalignment, double uav_R) {
+    const double min_d = (2.0 * position_misalignment + uav_R) * 1.41421;  // cpp:4044-4051
+    return formation_distance < min_d ? min_d : formation_distance;
+}
+
+extern "C" int msnap_followers_dev(msnap_handle h, int formation_model, double formation_distance, int uav_formation_max_row,
+                                   int n_followers, int frame, const double *reference_lla, const double *starts_wgs84_dev,
+                                   long long B, const long long *row_offset, const double *leader_rows, long long n_rows_cap,
+                                   long long out_capacity, double *out_rows) {
+    if (!h || B < 0 || n_followers < 0 || n_rows_cap < 0 || out_capacity < 0 || (frame != 0 && frame != 1) ||
+        !(formation_distance == formation_distance) || (B > 0 && (!row_offset || (n_rows_cap > 0 && !leader_rows))) ||
+        (out_capacity > 0 && !out_rows) || (frame == 1 && !geo_reference_ok(reference_lla)))
+        return MSNAP_ERR_INVALID_ARG;
+    if (B == 0 || n_followers == 0 || n_rows_cap == 0 || out_capacity == 0) return MSNAP_OK;
+    DeviceGuard guard(h->device);
+    int rc = arena_reserve(h, h->ws, 2 * padded((size_t)n_rows_cap * sizeof(double)) + 256);
+    if (rc) return rc;
+    double *ws_sin = arena_take<double>(h->ws, (size_t)n_rows_cap), *ws_cos = arena_take<double>(h->ws, (size_t)n_rows_cap);
+    long long *total = arena_take<long long>(h->ws, 1);
+    FollowParams p{formation_model, n_followers, uav_formation_max_row < 1 ? 1 : uav_formation_max_row, formation_distance};
+    MS_LAUNCH(h, k_follow_enu, (unsigned)B, FOLLOW_THREADS, p, B, row_offset, leader_rows, n_rows_cap, ws_sin, ws_cos, out_rows,
+              out_capacity);
+    if (frame == 0) return MSNAP_OK;
+    GeoFrame f;
+    geo_make_frame(reference_lla, f);
+    MS_LAUNCH(h, k_follow_total, 1, 32, B, row_offset, n_rows_cap, n_followers, total);
+    rc = launch_enu_to_wgs84(h, f, out_capacity, total, out_rows, out_rows, nullptr);
+    if (rc) return rc;
+    if (starts_wgs84_dev && formation_model >= 2 && formation_model <= 4)
+        MS_LAUNCH(h, k_follow_starts, grid_for(B * n_followers, 128), 128, n_followers, B, row_offset, leader_rows, n_rows_cap,
+                  starts_wgs84_dev, out_rows, out_capacity);
+    return MSNAP_OK;
+}
+
+extern "C" int msnap_followers_host(msnap_handle h, int formation_model, double formation_distance, int uav_formation_max_row,
+                                    int n_followers, int frame, const double *reference_lla, const double *starts_wgs84,
+                                    long long B, const long long *row_offset, const double *leader_rows, double *out_rows) {
+    if (!h || B < 0 || n_followers < 0 || (B > 0 && !row_offset)) return MSNAP_ERR_INVALID_ARG;
+    if (B == 0 || n_followers == 0) return MSNAP_OK;
+    if (row_offset[0] != 0) return MSNAP_ERR_INVALID_ARG;
+    for (long long b = 0; b < B; ++b)
+        if (row_offset[b + 1] < row_offset[b]) return MSNAP_ERR_INVALID_ARG;
+    const long long n = row_offset[B];
+    if (n == 0) return MSNAP_OK;
+    if (!leader_rows || !out_rows) return MSNAP_ERR_INVALID_ARG;
+    DeviceGuard guard(h->device);
+    MS_CUDA(h, cudaStreamSynchronize(h->aux));
+    const size_t n_out = (size_t)n * n_followers;
+    int rc = arena_reserve(h, h->io, padded((B + 1) * sizeof(long long)) + padded((size_t)n * 3 * sizeof(double)) +
+                                         padded((size_t)n_followers * 3 * sizeof(double)) + padded(n_out * 3 * sizeof(double)));
+    if (rc) return rc;
+    long long *d_off = arena_take<long long>(h->io, B + 1);
+    double *d_rows = arena_take<double>(h->io, (size_t)n * 3), *d_st = arena_take<double>(h->io, (size_t)n_followers * 3);
+    double *d_out = arena_take<double>(h->io, n_out * 3);
+    cudaStream_t st = h->stream;
+    MS_CUDA(h, cudaMemcpyAsync(d_off, row_offset, (B + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    MS_CUDA(h, cudaMemcpyAsync(d_rows, leader_rows, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (starts_wgs84) MS_CUDA(h, cudaMemcpyAsync(d_st, starts_wgs84, (size_t)n_followers * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = msnap_followers_dev(h, formation_model, formation_distance, uav_formation_max_row, n_followers, frame, reference_lla,
+                             starts_wgs84 ? d_st : nullptr, B, d_off, d_rows, n, (long long)n_out, d_out);
+    if (rc) return rc;
+    MS_CUDA(h, cudaMemcpyAsync(out_rows, d_out, n_out * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    MS_CUDA(h, cudaStreamSynchronize(st));
+    return MSNAP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------- single

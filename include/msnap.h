@@ -302,6 +302,31 @@ int msnap_patrol_postprocess_host(msnap_handle h, double distance, long long B, 
                                   const double *keep_up, long long out_capacity, long long *out_offset, double *out_rows,
                                   unsigned *flags_out);
 
+/* ---- follower formation trajectories on the leader's sampled rows ---------------------
+ * Drop-in for the numeric core of UavPathPlanner::generateFollowerTrajectories (/root/reference/uavPathPlanning.cpp:3931-4074)
+ * and its four formation generators (cpp:4076-4398): smoothed leader headings (central differences, +-10-sample circular
+ * mean when the trajectory has more than 5 rows), one fixed body-frame offset per follower from the formation model, the
+ * offset rotated into the leader's heading at every row, the result converted to WGS84.  One call = B leader trajectories
+ * (e.g. the sample_offset_out / samples_out of msnap_generate_batch_*, after msnap_altitude_optimize_batch_*).
+ *   formation_model        : 1 V shape, 2 line abreast, 3 trail (columns of uav_formation_max_row), 4 triangle; other = 1
+ *   formation_distance     : metres, AFTER the reference's lower bound -- msnap_formation_distance() applies it (cpp:4044-4051)
+ *   frame                  : 0 = rows {east, north, up}; 1 = rows {lon, lat, alt} about reference_lla (cpp:4141), with the
+ *                            reference's rule for models 2-4 that a follower's first row is {its start lon, its start lat,
+ *                            the leader's first up} (cpp:4188-4195) when starts_wgs84 is given
+ *   starts_wgs84 [n_followers][3] : uav_start_point_wgs84, may be NULL (frame 0 ignores it)
+ *   row_offset [B+1], leader_rows : CSR rows of the leaders; rows at or beyond n_rows_cap are treated as absent
+ *   out_rows [n_followers * rows][3] : trajectory b owns the block starting at n_followers * row_offset[b], follower-major
+ *                            ([follower][row]); rows beyond out_capacity are not written
+ * _dev: device pointers (reference_lla is a HOST pointer), enqueued on the handle's stream; _host: host pointers. */
+double msnap_formation_distance(double formation_distance, double position_misalignment, double uav_R);
+int msnap_followers_dev(msnap_handle h, int formation_model, double formation_distance, int uav_formation_max_row,
+                        int n_followers, int frame, const double *reference_lla, const double *starts_wgs84_dev, long long B,
+                        const long long *row_offset, const double *leader_rows, long long n_rows_cap, long long out_capacity,
+                        double *out_rows);
+int msnap_followers_host(msnap_handle h, int formation_model, double formation_distance, int uav_formation_max_row,
+                         int n_followers, int frame, const double *reference_lla, const double *starts_wgs84, long long B,
+                         const long long *row_offset, const double *leader_rows, double *out_rows);
+
 /* ---- per-kernel timing (bench.py's roofline pass) ------------------------------------------------------------
  * Between begin and end every kernel the handle launches is bracketed by a CUDA event pair on the launching stream.
  * msnap_profile_end synchronises and writes a JSON object {"<kernel>": {"launches": n, "total_ms": t}, ...}. */

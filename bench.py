@@ -356,39 +356,53 @@ def run_b200(args):
         e2e_steps = max(3 * S, min(steps, 30 * S))
         e2e_steps -= e2e_steps % S
 
-        def e2e_worker(which, n):
+        def e2e_worker(which, n, outputs):
             res = None
             for i in range(which, n, S):
                 res = tools[which].generate_batch(cfg, wp_np[i % ROTATE], ns=NS, capacity=sets[0].cap, out=outs[which],
-                                                  stats=False)
+                                                  stats=False, outputs=outputs)
             return res
 
-        def e2e_run(n):
+        def e2e_run(n, outputs):
             if S == 1:
-                return e2e_worker(0, n)
-            th = [threading.Thread(target=e2e_worker, args=(k, n)) for k in range(1, S)]
+                return e2e_worker(0, n, outputs)
+            th = [threading.Thread(target=e2e_worker, args=(k, n, outputs)) for k in range(1, S)]
             for t_ in th:
                 t_.start()
-            res = e2e_worker(0, n)
+            res = e2e_worker(0, n, outputs)
             for t_ in th:
                 t_.join()
             return res
 
-        e2e_run(3 * S)
-        barrier()
-        t0 = time.perf_counter()
-        r = e2e_run(e2e_steps)
-        torch.cuda.synchronize()
-        e2e_s = max_over_ranks(time.perf_counter() - t0)
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(6):
-            tool.generate_batch(cfg, wp_np[i % ROTATE], ns=NS, capacity=sets[0].cap, out=out, stats=False)
-        e2e_single_ms = (time.perf_counter() - t0) / 6 * 1e3   # one call at a time on one handle
-        h2d = wp_np[0].nbytes
-        d2h = int(r.samples.nbytes + out["times"].nbytes + out["coeff"].nbytes + out["max_dev"].nbytes +
-                  out["iters"].nbytes + out["vw_final"].nbytes + out["sample_offset"].nbytes +
-                  out["flags"].nbytes + out["best_s"].nbytes)
+        def e2e_measure(outputs):
+            e2e_run(3 * S, outputs)
+            barrier()
+            t0 = time.perf_counter()
+            r = e2e_run(e2e_steps, outputs)
+            torch.cuda.synchronize()
+            sec = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(6):
+                tool.generate_batch(cfg, wp_np[i % ROTATE], ns=NS, capacity=sets[0].cap, out=out, stats=False, outputs=outputs)
+            single_ms = (time.perf_counter() - t0) / 6 * 1e3   # one call at a time on one handle
+            d2h = int(r.samples.nbytes + out["sample_offset"].nbytes + out["flags"].nbytes)
+            if outputs == "all":
+                d2h += int(out["times"].nbytes + out["coeff"].nbytes + out["max_dev"].nbytes + out["iters"].nbytes +
+                           out["vw_final"].nbytes + out["best_s"].nbytes)
+            return dict(value=world * B * e2e_steps / sec, unit=UNIT, h2d_bytes_per_step=wp_np[0].nbytes, d2h_bytes_per_step=d2h,
+                        steps=e2e_steps, ms_per_step=sec / e2e_steps * 1e3, host_threads=S, single_call_ms=single_ms,
+                        d2h_GBps_per_gpu=d2h / (sec / e2e_steps) / 1e9)
+
+        # headline e2e = the reference call's own outputs: GenerateTrajectoryMatrix returns the sampled rows and nothing else
+        # (ms.hpp:60-61; the caller copies exactly those, cpp:4464-4470).  The all-outputs figure (coefficients, times,
+        # decisions: 1.7x the bytes) is kept beside it.
+        e2e_main = e2e_measure("samples")
+        e2e_main["outputs"] = ("the reference call's outputs: sampled rows [S,3] + CSR offsets + per-trajectory flags "
+                               "(optional arrays passed as NULL)")
+        e2e_all = e2e_measure("all")
+        e2e_all["outputs"] = "every array of include/msnap.h: + coefficients, segment times, max_dev, iters, final weight, best_s"
+        e2e_main["all_outputs"] = e2e_all
         # the same step with the sampled rows leaving as WGS84 [lon, lat, alt] (getPlan's
         # enuToWGS84_Batch, uavPathPlanning.cpp:3699, applied on the device by k_enu_to_wgs84 after the sampler)
         geo = None
@@ -419,11 +433,17 @@ def run_b200(args):
             gx = torch.arange(128, dtype=torch.float64, device=dev)
             grid = (-60.0 + 25.0 * torch.sin(gx[None, :] / 9.0) * torch.cos(gx[:, None] / 7.0)).to(torch.float32).contiguous()
             g_res, g_ox, g_oy = 8.0, -512.0, 512.0            # 128 x 128 cells of 8 m around the origin, terrain -85..-35 m
+            N_FOLLOWERS = 6
             for s_ in sets:
                 s_.lla_wp = torch.from_numpy(tool.enuToWGS84_Batch(s_.wp_h.numpy(), origin)).to(dev)
                 s_.elev = torch.empty(s_.cap, dtype=torch.float64, device=dev)
                 s_.lla = torch.empty((s_.cap, 3), dtype=torch.float64, device=dev)
                 s_.solves = torch.empty(B, dtype=torch.int32, device=dev)
+                s_.followers = torch.empty((N_FOLLOWERS * s_.cap, 3), dtype=torch.float64, device=dev)
+
+            f_dist, f_rows = tool.formation_parameters()        # config.yaml defaults: 50 m, 8 rows per column
+            d_starts = torch.from_numpy(np.column_stack([origin[0] + 1e-3 * np.arange(N_FOLLOWERS), np.full(N_FOLLOWERS, origin[1]),
+                                                         np.zeros(N_FOLLOWERS)])).to(dev)
 
             def chain_step(cfg_, s_, which=0):
                 t_ = tools[which]
@@ -431,6 +451,7 @@ def run_b200(args):
                                       max_dev=s_.max_dev, iters=s_.iters, vw_final=s_.vw, flags=s_.flags)
                 t_.cost_map_lookup_dev(grid, g_res, g_ox, g_oy, s_.samples, s_.elev, n_rows=s_.off[B:])
                 t_.altitude_optimize_batch_dev(alt_p, s_.off, s_.samples, s_.elev, solves=s_.solves)
+                t_.followers_dev(s_.samples, s_.off, s_.followers, 1, f_dist, N_FOLLOWERS, f_rows, "wgs84", origin, d_starts)
                 t_.enu_to_wgs84_dev(origin, s_.samples, s_.lla, n_rows=s_.off[B:])
 
             for t_ in tools:
@@ -452,9 +473,7 @@ def run_b200(args):
                          kernels_ms_per_step={k: v["total_ms"] / prof_steps for k, v in cprof.items()})
         results[weights] = dict(
             geo=geo, chain=chain, ms=ms, steps=steps, launches=launches, value=world * B * steps / (ms * 1e-3), latency_ms=latency_ms,
-            e2e=dict(value=world * B * e2e_steps / e2e_s, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                     steps=e2e_steps, ms_per_step=e2e_s / e2e_steps * 1e3, host_threads=S,
-                     single_call_ms=e2e_single_ms),
+            e2e=e2e_main,
             prof=prof, dom=dom, dom_ms=dom_ms, all_kernels_ms=all_ms, abytes=abytes, aflops=aflops, kbytes=kbytes,
             kflops=kflops,
             samples=tot_samples, candidates=cand, mean_iters=float(iters0.double().mean().item()), flags_bad=flags_bad,
@@ -691,7 +710,8 @@ def run_b200(args):
             c = dict(h["chain"])
             c["note"] = ("getPlan's leader chain per batch, device resident, same two-stream driver as `value`: WGS84 waypoints -> "
                          "ENU (k_wgs84_to_enu) -> minimum snap + sampler -> cost-map lookup -> altitude optimisation (shipped "
-                         "config.yaml parameters, synthetic 128 x 128 terrain grid) -> WGS84 rows; SURVEY.md section 8f ranks 1-2")
+                         "config.yaml parameters, synthetic 128 x 128 terrain grid) -> 6 followers in V formation as WGS84 rows "
+                         "-> leader WGS84 rows; SURVEY.md section 8f ranks 1-3")
             line["leader_chain"] = c
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -590,11 +590,16 @@ class TrajectoryGeneratorTool:
 
     def generate_batch(self, cfg: MinimumSnapConfig, waypoints, ns=None, seg_offset=None,
                        sample_distance_override=-1.0, v_avg_override=-1.0, capacity: Optional[int] = None,
-                       out: Optional[dict] = None, stats: bool = True) -> BatchResult:
+                       out: Optional[dict] = None, stats: bool = True, outputs: str = "all") -> BatchResult:
         """B independent GenerateTrajectoryMatrix calls in one launch sequence; host arrays in, host arrays out.
         ``capacity`` rows are reserved for the samples (default: the exact-safe upper bound from
         ``msnap_sample_bound``); if it is too small MsnapError(ERR_CAPACITY) is raised with the exact layout
-        available in ``.sample_offset`` of the exception's ``partial`` attribute."""
+        available in ``.sample_offset`` of the exception's ``partial`` attribute.
+        ``outputs``: "all" = every array include/msnap.h offers; "samples" = what the reference's
+        GenerateTrajectoryMatrix returns -- the sampled rows (with their CSR offsets and the per-trajectory flags): the
+        optional pointers are passed as NULL, nothing else is computed for or copied to the host."""
+        if outputs not in ("all", "samples"):
+            raise ValueError("outputs must be 'all' or 'samples'")
         wp = _f64(waypoints)
         B, nsu, so, n_seg = _layout(wp, ns, seg_offset)
         c = cfg.to_c()
@@ -602,15 +607,16 @@ class TrajectoryGeneratorTool:
             capacity = self.sample_bound(cfg, wp, ns=ns, seg_offset=seg_offset, v_avg_override=v_avg_override)
         m = 2 * int(cfg.order)
         o = out or {}
-        times = o.get("times", np.empty(n_seg))
-        coeff = o.get("coeff", np.empty((n_seg, 3, m)))
-        max_dev = o.get("max_dev", np.empty(B))
-        iters = o.get("iters", np.empty(B, dtype=np.int32))
-        vw_final = o.get("vw_final", np.empty(B))
-        best_s = o.get("best_s", np.zeros(n_seg, dtype=np.int32))
+        full = outputs == "all"
+        times = o.get("times", np.empty(n_seg)) if full else None
+        coeff = o.get("coeff", np.empty((n_seg, 3, m))) if full else None
+        max_dev = o.get("max_dev", np.empty(B)) if full else None
+        iters = o.get("iters", np.empty(B, dtype=np.int32)) if full else None
+        vw_final = o.get("vw_final", np.empty(B)) if full else None
+        best_s = o.get("best_s", np.zeros(n_seg, dtype=np.int32)) if full else None
         sample_offset = o.get("sample_offset", np.empty(B + 1, dtype=np.int64))
         samples = o.get("samples", np.empty((max(int(capacity), 1), 3)))
-        stats = o.get("stats", np.empty((B, 2))) if stats else None   # (the reference only prints them, ms.cpp:194)
+        stats = o.get("stats", np.empty((B, 2))) if (stats and full) else None   # (the reference only prints them, ms.cpp:194)
         flags = o.get("flags", np.zeros(B, dtype=np.uint32))
         rc = self._L.msnap_generate_batch_host(
             self._h, C.byref(c), float(sample_distance_override), float(v_avg_override), B, nsu, _ptr(so), _ptr(wp),

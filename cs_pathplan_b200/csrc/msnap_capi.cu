@@ -790,7 +790,23 @@ int msnap_destroy(msnap_handle h) {
 
 int msnap_set_stream(msnap_handle h, void *cuda_stream) {
     if (!h) return MSNAP_ERR_INVALID_ARG;
-    h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+    cudaStream_t next = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+    if (next != h->stream) {
+        // The handle has ONE workspace arena, reset by every call: work still queued on the old stream must not be
+        // overtaken by calls on the new one.  The new stream waits for an event recorded behind everything enqueued so far
+        // (no host synchronisation).
+        DeviceGuard guard(h->device);
+        cudaEvent_t ev = nullptr;
+        MS_CUDA(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        cudaError_t e = cudaEventRecord(ev, h->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(next, ev, 0);
+        cudaEventDestroy(ev);
+        if (e != cudaSuccess) {
+            h->last_error = std::string("msnap_set_stream: ") + cudaGetErrorString(e);
+            return MSNAP_ERR_CUDA;
+        }
+    }
+    h->stream = next;
     return MSNAP_OK;
 }
 

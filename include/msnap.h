@@ -76,7 +76,12 @@ const char *msnap_last_error(msnap_handle h);
 /* Bind a solver instance to CUDA device `device` (creates a stream, uploads the constant tables). */
 int msnap_create(int device, msnap_handle *out);
 int msnap_destroy(msnap_handle h);
-/* Use the caller's cudaStream_t (passed as void*) for all subsequent _dev work; NULL restores the handle's own. */
+/* Use the caller's cudaStream_t (passed as void*) for all subsequent _dev work; NULL restores the handle's own.  The new
+ * stream is made to wait (event, no host synchronisation) for everything the handle has enqueued on the old one: a handle
+ * owns ONE workspace that every call reuses, so calls of one handle are always ordered.  Use one handle per concurrent
+ * stream.  Host synchronisation points of the _dev entry points: the first call of a larger problem size grows the
+ * workspace (cudaStreamSynchronize + cudaFree + cudaMalloc); ragged batches (seg_offset given) read seg_offset[B] back
+ * (8 bytes, one synchronisation) -- neither is CUDA-graph capturable; uniform batches at a warmed-up size only enqueue. */
 int msnap_set_stream(msnap_handle h, void *cuda_stream);
 /* Block until everything enqueued on the handle's stream has finished. */
 int msnap_synchronize(msnap_handle h);

@@ -22,6 +22,8 @@
 
 #include "msnap_tables.h"
 
+#include <type_traits>
+
 
 namespace msnap {
 
@@ -194,14 +196,27 @@ __device__ __forceinline__ void assemble_row(double Ta, double Tc, const double 
 // (all cofactors in parallel, ONE reciprocal); every term of a cofactor carries the same powers of the segment
 // times, so the formula is as scale-invariant as a Cholesky factorisation of the same block.  B >= 4 falls back to
 // Cholesky.  Returns false if the block is not positive definite (or not finite).
+// 1/x for the pivot determinants: hardware seed (rcp.approx.ftz.f64, 2^-23) + two Newton steps, error <= 1 ulp for normal x.
+// An IEEE-rounded `1.0 / x` compiles to the same seed and steps PLUS a range check and an out-of-line slow path; that
+// subroutine call sits in the row loop of every sweep and costs registers (spills) and ~40 cycles of dependent latency per
+// row.  Pivots that are not positive normal numbers are reported through the caller's status flag either way.
+__device__ __forceinline__ double pivot_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
 template <int B>
 __device__ __forceinline__ bool sym_inverse(const double (&a)[B * (B + 1) / 2], double (&p)[B * (B + 1) / 2]) {
     if constexpr (B == 1) {
-        p[0] = 1.0 / a[0];
+        p[0] = pivot_rcp(a[0]);
         return a[0] > 0.0;
     } else if constexpr (B == 2) {
         const double det = fma(a[0], a[2], -(a[1] * a[1]));
-        const double r = 1.0 / det;
+        const double r = pivot_rcp(det);
         p[0] = a[2] * r;
         p[1] = -a[1] * r;
         p[2] = a[0] * r;
@@ -215,7 +230,7 @@ __device__ __forceinline__ bool sym_inverse(const double (&a)[B * (B + 1) / 2], 
         const double c21 = fma(a[1], a[3], -(a[0] * a[4]));
         const double c22 = fma(a[0], a[2], -(a[1] * a[1]));
         const double det = fma(a[3], c20, fma(a[1], c10, a[0] * c00));
-        const double r = 1.0 / det;
+        const double r = pivot_rcp(det);
         p[0] = c00 * r;
         p[1] = c10 * r;
         p[2] = c11 * r;
@@ -387,7 +402,10 @@ __device__ __forceinline__ bool elim_half(int n_rows, int cnt, bool mirror, doub
     double z[NR];  // z of the previously eliminated row, [r][axis]
     const int step = mirror ? -1 : 1;
     int j = mirror ? n_rows - 1 : 0;
-    for (int i = 0; i < cnt; ++i, j += step) {
+    // One row; FIRST (a compile-time flag) = the outermost row, which has no previously eliminated neighbour.  The first
+    // row is peeled off the loop so that W and z are plain loop-carried values, defined on every path into the loop body.
+    auto row = [&](auto first_tag) {
+        constexpr bool FIRST = decltype(first_tag)::value;
         base_at.prefetch(j + step);  // the next row towards the split row (which always exists)
         const double *b = base_at(j);
         double *s = state_at(j);
@@ -395,7 +413,7 @@ __device__ __forceinline__ bool elim_half(int n_rows, int cnt, bool mirror, doub
         row_load<BaseAt, D::F_D, ND>(b, d);
         row_load<BaseAt, D::F_R, NR>(b, r);
         d[0] += add00;
-        if (i > 0) {
+        if constexpr (!FIRST) {
             // coupling to the previously eliminated row: U_{j-1} (stored in row j-1), or U_j' (row j) when mirrored;
             // re-read (a broadcast LDS) rather than carried in registers
             double C[NU];
@@ -445,7 +463,11 @@ __device__ __forceinline__ bool elim_half(int n_rows, int cnt, bool mirror, doub
                 }
             row_store<StateAt, D::SW, NU>(s, W);
         }
-    }
+        j += step;
+    };
+    if (cnt <= 0) return ok;
+    row(std::true_type{});
+    for (int i = 1; i < cnt; ++i) row(std::false_type{});
     return ok;
 }
 

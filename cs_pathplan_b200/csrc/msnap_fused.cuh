@@ -250,20 +250,26 @@ __device__ __forceinline__ void fused_probe_item(const FusedParams &p, double *b
 //
 // One speculative chain of trajectory block `blk` with diagonal shift add00 by ONE lane (split row n-1): elimination
 // into `state_at`, back-substitution with the deviation probes, leaving x nowhere.  Returns the pivot status.
+struct ChainResult {
+    double max_dev;
+    bool ok;
+};
+
 template <int O, class StateAt>
-__device__ __noinline__ bool fused_chain_spec(const double *blk, int ns, double add00, const StateAt state_at,
-                                              double *max_dev_out, long long *clk = nullptr) {
+__device__ __forceinline__ ChainResult fused_chain_spec(const double *blk, int ns, double add00, const StateAt state_at,
+                                                        long long *clk = nullptr) {
     using D = Dim<O>;
     const FusedSmem<O> L(ns);
     const FBaseRows<O> base_at{blk + L.oBase};
     const int n = ns - 1, m = split_row(n, false);
-    const bool ok = thomas_forward<O>(n, m, add00, base_at, state_at);
+    ChainResult r;
+    r.ok = thomas_forward<O>(n, m, add00, base_at, state_at);
     if (clk) clk[0] = clock64();
     const FSegxRows<O> segx_at{blk + L.oSegx};
     const FPos pos{blk + L.oP};
-    *max_dev_out = thomas_backward<O, true, true>(n, m, state_at, NoOut{}, segx_at, pos, blk + L.oBC, blk + L.oBC + D::NR);
+    r.max_dev = thomas_backward<O, true, true>(n, m, state_at, NoOut{}, segx_at, pos, blk + L.oBC, blk + L.oBC + D::NR);
     if (clk) clk[1] = clock64();
-    return ok;
+    return r;
 }
 
 // One latency-critical chain (pass 1, the last reweighting iteration, a bare solve) by TWO adjacent lanes of a warp
@@ -271,7 +277,7 @@ __device__ __noinline__ bool fused_chain_spec(const double *blk, int ns, double 
 // bottom half.  `pair_mask` = the lanes of the warp that call this function (all of them must).  The solution is left
 // in `state_at` (shared memory).  Both lanes return the combined pivot status and the max deviation (0 when !EVAL).
 template <int O, bool EVAL, class StateAt>
-__device__ __noinline__ bool fused_chain_pair(const double *blk, int ns, double add00, const StateAt state_at, int side,
+__device__ __forceinline__ bool fused_chain_pair(const double *blk, int ns, double add00, const StateAt state_at, int side,
                                               unsigned pair_mask, double *max_dev_out) {
     using D = Dim<O>;
     const FusedSmem<O> L(ns);
@@ -339,6 +345,80 @@ __device__ __forceinline__ bool fused_coeff_item(const double *blk, const double
         finite = finite && (fabs(co[2 * q]) <= 1.7976931348623157e308) && (fabs(co[2 * q + 1]) <= 1.7976931348623157e308);
     }
     return finite;
+}
+
+// Pointers into a CTA's dynamic shared memory behind the trajectory blocks.
+template <int O>
+struct FusedTail {
+    double *state1, *md;
+    int *okf, *sel, *ok1;
+    __device__ __forceinline__ FusedTail(double *smem, int ns, int tpc, int nit, int tstride) {
+        state1 = smem + (size_t)tpc * tstride;                            // [nr][NSTATE][SL]: pass-1 sweep, then the final x
+        md = state1 + (size_t)(ns - 1) * Dim<O>::NSTATE * FUSED_SMEM_LANES;  // [tpc][nit] max deviation of every solve
+        okf = reinterpret_cast<int *>(md + tpc * nit);                    // [tpc][nit] pivot status
+        sel = okf + tpc * nit;                                            // [tpc] selected iteration
+        ok1 = sel + tpc;                                                  // [tpc] pass-1 pivot status
+    }
+};
+
+// The chain phases are functions of their own that derive everything from (p, tile, threadIdx): a callee may not touch
+// the registers its caller keeps live across the call, and the kernel's tile loop kept 54 of the 168 there -- enough to
+// make the row sweeps spill six doubles of W per row into local memory, whose reloads (26 % L1 misses: the L1 is what two
+// 112 KB CTAs leave of it) sat on the critical path of every row.  Called like this, only `tile` survives the call.
+//
+// pass 1 (ms.cpp:357-405): one lane pair per trajectory, solution left in the shared-memory state rows
+template <int O>
+__device__ __noinline__ void fused_phase_pass1(const FusedParams &p, int nt) {
+    extern __shared__ double smem[];  // (declared here, not passed in: the compiler then knows every pointer below is shared)
+    const int tid = threadIdx.x;
+    if (tid >= 2 * nt) return;
+    const FusedTail<O> T(smem, p.ns, p.tpc, p.nit, p.traj_stride);
+    double unused;
+    const int t = tid >> 1;
+    const FStateRows<O, FUSED_SMEM_LANES> st{T.state1 + t};
+    const unsigned pm = 2 * nt >= 32 ? 0xffffffffu : (1u << (2 * nt)) - 1u;
+    const bool ok = fused_chain_pair<O, false>(smem + t * p.traj_stride, p.ns, 0.0, st, tid & 1, pm, &unused);
+    if ((tid & 1) == 0) T.ok1[t] = ok ? 1 : 0;
+}
+
+// Speculative Thomas over (trajectory, reweighting iteration), see the kernel.
+template <int O>
+__device__ __noinline__ void fused_phase_spec(const FusedParams &p, long long tile, int nt) {
+    extern __shared__ double smem[];
+    constexpr int SL = FUSED_SMEM_LANES, GL = FUSED_SLOT_LANES;
+    using D = Dim<O>;
+    const int tid = threadIdx.x;
+    const int ns = p.ns, nit = p.nit, tstride = p.traj_stride;
+    const FusedTail<O> T(smem, ns, p.tpc, nit, tstride);
+    const bool use_pw = p.sp.pw > 0.0;
+    const int n_glob = nt * (nit - 1);
+    const int g0l = (2 * p.tpc + 31) & ~31;  // first speculative lane
+    if (tid >= g0l && tid < g0l + n_glob) {
+        const int l = tid - g0l;
+        const int t = l / (nit - 1), q = l - t * (nit - 1);
+        const double vw = reweighted_vw(p.sp.vw0, q);
+        const double add00 = vw > 0.0 ? 2.0 * vw : 0.0;
+        double *slot = p.state_ws + (size_t)blockIdx.x * (ns - 1) * D::NSTATE * GL;
+        const FStateRows<O, GL, L2KeepMem> st{slot + l};
+        long long *clk = nullptr;  // dev instrumentation: speculative lanes 0, 64 and 128 of the CTA's first tile
+        if (p.phase_clocks && tile == blockIdx.x && (l & 63) == 0) clk = p.phase_clocks + blockIdx.x * 16 + 10 + 2 * (l >> 6);
+        const ChainResult r = fused_chain_spec<O>(smem + t * tstride, ns, add00, st, clk);
+        T.md[t * nit + q] = r.max_dev;
+        T.okf[t * nit + q] = r.ok ? 1 : 0;
+    } else if (tid < 2 * nt) {  // two lanes per trajectory (fused_chain_pair)
+        const int t = tid >> 1, q = nit - 1;
+        const double vw = reweighted_vw(p.sp.vw0, q);
+        const double add00 = vw > 0.0 ? 2.0 * vw : 0.0;
+        const FStateRows<O, SL> st{T.state1 + t};
+        const unsigned pm = 2 * nt >= 32 ? 0xffffffffu : (1u << (2 * nt)) - 1u;
+        double mdv;
+        const bool ok = use_pw ? fused_chain_pair<O, true>(smem + t * tstride, ns, add00, st, tid & 1, pm, &mdv)
+                               : fused_chain_pair<O, false>(smem + t * tstride, ns, add00, st, tid & 1, pm, &mdv);
+        if ((tid & 1) == 0) {
+            T.md[t * nit + q] = mdv;
+            T.okf[t * nit + q] = ok ? 1 : 0;
+        }
+    }
 }
 
 template <int O>
@@ -421,14 +501,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_c
                 fused_row_item<O>(p, smem + (i / nr) * tstride, ns, i % nr + 1, false);
             __syncthreads();
             MSNAP_STAMP();
-            if (tid < 2 * nt) {  // two lanes per trajectory (fused_chain_pair)
-                double unused;
-                const int t = tid >> 1;
-                const FStateRows<O, SL> st{state1 + t};
-                const unsigned pm = 2 * nt >= 32 ? 0xffffffffu : (1u << (2 * nt)) - 1u;
-                const bool ok = fused_chain_pair<O, false>(smem + t * tstride, ns, 0.0, st, tid & 1, pm, &unused);
-                if ((tid & 1) == 0) ok1[t] = ok ? 1 : 0;
-            }
+            fused_phase_pass1<O>(p, nt);
             __syncthreads();
             MSNAP_STAMP();
             for (int i = tid; i < nt * ns; i += FUSED_THREADS) {
@@ -456,37 +529,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_c
         {
             // The last-iteration group sits in warp 0 .. (the CTA's oldest warps, which the scheduler favours): its
             // full backward sweep is the longest chain of this phase.  Speculative lanes start at the next warp boundary.
-            const int n_glob = nt * (nit - 1);
-            const int g0l = (2 * tpc + 31) & ~31;  // first speculative lane
-            if (tid >= g0l && tid < g0l + n_glob) {
-                const int l = tid - g0l;
-                const int t = l / (nit - 1), q = l - t * (nit - 1);
-                double vw = p.sp.vw0;
-                for (int i = 0; i < q; ++i) vw = (vw < 1e-6) ? 0.01 : vw * 2.0;
-                const double add00 = vw > 0.0 ? 2.0 * vw : 0.0;
-                const FStateRows<O, GL, L2KeepMem> st{slot + l};
-                long long *clk = nullptr;  // dev instrumentation: speculative lanes 0, 64 and 128 of the CTA's first tile
-                if (p.phase_clocks && tile == blockIdx.x && (l & 63) == 0)
-                    clk = p.phase_clocks + blockIdx.x * 16 + 10 + 2 * (l >> 6);
-                double mdv;
-                const bool ok = fused_chain_spec<O>(smem + t * tstride, ns, add00, st, &mdv, clk);
-                md[t * nit + q] = mdv;
-                okf[t * nit + q] = ok ? 1 : 0;
-            } else if (tid < 2 * nt) {  // two lanes per trajectory (fused_chain_pair)
-                const int t = tid >> 1, q = nit - 1;
-                double vw = p.sp.vw0;
-                for (int i = 0; i < q; ++i) vw = (vw < 1e-6) ? 0.01 : vw * 2.0;
-                const double add00 = vw > 0.0 ? 2.0 * vw : 0.0;
-                const FStateRows<O, SL> st{state1 + t};
-                const unsigned pm = 2 * nt >= 32 ? 0xffffffffu : (1u << (2 * nt)) - 1u;
-                double mdv;
-                const bool ok = use_pw ? fused_chain_pair<O, true>(smem + t * tstride, ns, add00, st, tid & 1, pm, &mdv)
-                                       : fused_chain_pair<O, false>(smem + t * tstride, ns, add00, st, tid & 1, pm, &mdv);
-                if ((tid & 1) == 0) {
-                    md[t * nit + q] = mdv;
-                    okf[t * nit + q] = ok ? 1 : 0;
-                }
-            }
+            fused_phase_spec<O>(p, tile, nt);
             __syncthreads();
             // the iteration the sequential loop would have stopped at (ms.cpp:82)
             if (tid < nt) {
@@ -497,6 +540,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_c
             __syncthreads();
             // a trajectory that stopped early: the lane that solved that iteration replays its backward sweep, this
             // time leaving the solution in the shared-memory state rows
+            const int n_glob = nt * (nit - 1), g0l = (2 * tpc + 31) & ~31;
             if (tid >= g0l && tid < g0l + n_glob) {
                 const int l = tid - g0l;
                 const int t = l / (nit - 1), q = l - t * (nit - 1);

@@ -224,6 +224,14 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # keep this rank's host threads and the pinned buffers they first touch on the GPU's own NUMA node (matters for the
+    # end-to-end figure when several ranks share the box; MSNAP_BENCH_NUMA=0 switches it off)
+    numa_cpus = None
+    all_cpus = os.sched_getaffinity(0)
+    if os.environ.get("MSNAP_BENCH_NUMA", "1") != "0":
+        from cs_pathplan_b200.hostpin import pin_to_gpu_numa
+
+        numa_cpus = pin_to_gpu_numa(local)
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
@@ -392,7 +400,8 @@ def run_b200(args):
                            out["vw_final"].nbytes + out["best_s"].nbytes)
             return dict(value=world * B * e2e_steps / sec, unit=UNIT, h2d_bytes_per_step=wp_np[0].nbytes, d2h_bytes_per_step=d2h,
                         steps=e2e_steps, ms_per_step=sec / e2e_steps * 1e3, host_threads=S, single_call_ms=single_ms,
-                        d2h_GBps_per_gpu=d2h / (sec / e2e_steps) / 1e9)
+                        d2h_GBps_per_gpu=d2h / (sec / e2e_steps) / 1e9,
+                        host_cpus_pinned=None if numa_cpus is None else len(numa_cpus))
 
         # headline e2e = the reference call's own outputs: GenerateTrajectoryMatrix returns the sampled rows and nothing else
         # (ms.hpp:60-61; the caller copies exactly those, cpp:4464-4470).  The all-outputs figure (coefficients, times,
@@ -714,6 +723,7 @@ def run_b200(args):
                          "-> leader WGS84 rows; SURVEY.md section 8f ranks 1-3")
             line["leader_chain"] = c
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, all_cpus)     # the CPU legs use every core of the box again
             try:
                 from oracle import ref
 

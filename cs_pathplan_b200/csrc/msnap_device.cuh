@@ -302,6 +302,8 @@ __device__ __forceinline__ bool sym_inverse(const double (&a)[B * (B + 1) / 2], 
 struct PlainMem {
     __device__ static __forceinline__ double ld(const double *p) { return *p; }
     __device__ static __forceinline__ void st(double *p, double v) { *p = v; }
+    __device__ static __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+    __device__ static __forceinline__ void st2(double *p, double a, double b) { *reinterpret_cast<double2 *>(p) = make_double2(a, b); }
 };
 struct L2KeepMem {
     __device__ static __forceinline__ unsigned long long policy() {
@@ -317,14 +319,40 @@ struct L2KeepMem {
     __device__ static __forceinline__ void st(double *p, double v) {
         asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(policy()) : "memory");
     }
+    __device__ static __forceinline__ double2 ld2(const double *p) {
+        double2 v;
+        asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(policy()));
+        return v;
+    }
+    __device__ static __forceinline__ void st2(double *p, double a, double b) {
+        asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(a), "d"(b), "l"(policy()) : "memory");
+    }
 };
+
+// Accessors may declare `static constexpr int PAIR = LANES`: the row is then laid out [field / 2][lane][2] -- two consecutive
+// fields of one lane sit side by side, so a lane moves them as one 128-bit word and a warp's access is 512 contiguous bytes
+// (the speculative lanes' L2 scratch: the sweeps are issue-bound and this halves their state stores and loads).
+template <class T, class = void>
+struct RowPair { static constexpr int LANES = 0; };
+template <class T>
+struct RowPair<T, std::void_t<decltype(T::PAIR)>> { static constexpr int LANES = T::PAIR; };
 
 // Consecutive fields F0 .. F0+N-1 of a row.  Accessors whose rows are contiguous and 16-byte aligned (Rows::VEC: the
 // per-trajectory rows of the generic path in HBM) move them as 128-bit words: those sweeps touch 32 different cache lines
 // per warp access and are bound by the number of load/store transactions.  All other accessors go field by field.
 template <class Rows, int F0, int N>
 __device__ __forceinline__ void row_load(const double *row, double (&out)[N]) {
-    if constexpr (Rows::VEC) {
+    if constexpr (RowPair<Rows>::LANES > 0) {
+        constexpr int PL = 2 * RowPair<Rows>::LANES, H = F0 & 1;
+        if (H) out[0] = Rows::Mem::ld(row + (F0 >> 1) * PL + 1);
+#pragma unroll
+        for (int k = H; k + 1 < N; k += 2) {
+            const double2 v = Rows::Mem::ld2(row + ((F0 + k) >> 1) * PL);
+            out[k] = v.x;
+            out[k + 1] = v.y;
+        }
+        if ((N - H) & 1) out[N - 1] = Rows::Mem::ld(row + ((F0 + N - 1) >> 1) * PL);
+    } else if constexpr (Rows::VEC) {
         constexpr int H = F0 & 1;
         if (H) out[0] = row[F0];
 #pragma unroll
@@ -341,7 +369,13 @@ __device__ __forceinline__ void row_load(const double *row, double (&out)[N]) {
 }
 template <class Rows, int F0, int N>
 __device__ __forceinline__ void row_store(double *row, const double (&in)[N]) {
-    if constexpr (Rows::VEC) {
+    if constexpr (RowPair<Rows>::LANES > 0) {
+        constexpr int PL = 2 * RowPair<Rows>::LANES, H = F0 & 1;
+        if (H) Rows::Mem::st(row + (F0 >> 1) * PL + 1, in[0]);
+#pragma unroll
+        for (int k = H; k + 1 < N; k += 2) Rows::Mem::st2(row + ((F0 + k) >> 1) * PL, in[k], in[k + 1]);
+        if ((N - H) & 1) Rows::Mem::st(row + ((F0 + N - 1) >> 1) * PL, in[N - 1]);
+    } else if constexpr (Rows::VEC) {
         constexpr int H = F0 & 1;
         if (H) row[F0] = in[0];
 #pragma unroll

@@ -24,7 +24,8 @@
 //
 // The sweeps are issue-bound, so every array in the hot loops has COMPILE-TIME strides (addresses are base +
 // immediate): shared-memory rows are [row][fields] with an odd row pitch, sweep state is [row][field][lanes] with
-// a fixed lane count (16 in shared memory, 128 in the per-CTA L2-resident scratch slot of the speculative lanes).
+// a fixed lane count (14 in shared memory, 160 in the per-CTA L2-resident scratch slot of the speculative lanes), two
+// consecutive fields of a lane side by side (RowPair): 128-bit state loads / stores.
 #ifndef MSNAP_FUSED_CUH
 #define MSNAP_FUSED_CUH
 
@@ -32,7 +33,7 @@
 
 namespace msnap {
 
-constexpr int FUSED_THREADS = 192;     // 2 CTAs per SM at <= 170 registers per thread
+constexpr int FUSED_THREADS = 224;     // 2 CTAs per SM at <= 144 registers per thread; 14 x 16 (trajectory, segment) items = one round
 constexpr int FUSED_SLOT_LANES = 160;  // lanes per state row of the global scratch slot (>= 16 trajectories x 10 speculative iterations)
 constexpr int FUSED_SMEM_LANES = 14;   // lanes per state row in shared memory (= max trajectories per tile)
 
@@ -41,7 +42,7 @@ struct FusedParams {
     int ns;
     int tpc;           // trajectories per tile (<= FUSED_SMEM_LANES)
     int nit;           // solves per trajectory in the speculative phase: max_iter + 1 if pw > 0 else 1
-    int traj_stride;   // doubles per trajectory block in shared memory (odd: conflict-free broadcast)
+    int traj_stride;   // doubles per trajectory block in shared memory (FusedSmem::size: even, 2 mod 4)
     long long n_tiles;
     const double *wp;
     const double *times_in;  // nullptr => allocate from v_avg / min_time
@@ -64,19 +65,24 @@ template <int O>
 struct FusedSmem {
     using D = Dim<O>;
     static constexpr int ST = 3;                 // per segment: T, 1/T (powers are re-multiplied, not stored)
-    static constexpr int BS = D::NBASE | 1;      // per row: D, U, r
-    static constexpr int XS = D::NSEGX | 1;      // per segment: deviation probe
+    // Base rows (D, U, r) are read by the sweeps with 128-bit loads: even row pitch, even offsets, and a pitch that is
+    // 2 mod 4 doubles apart from a multiple of 32 banks so that the (traj, row)-parallel writers spread over the banks
+    // (24 doubles = 48 words would put all rows of a trajectory on two bank groups).
+    static constexpr int BS = ((D::NBASE + 1) & ~1) + ((((D::NBASE + 1) & ~1) % 4 == 0) ? 2 : 0);
+    static constexpr int XS = D::NSEGX | 1;      // per segment: deviation probe (scalar reads: odd pitch)
     int oSeg, oP, oBC, oBase, oSegx, oS, size;
+    __host__ __device__ static constexpr int even(int x) { return (x + 1) & ~1; }
     __host__ __device__ FusedSmem(int ns) {
         const int nr = ns - 1;
         oSeg = 0;
         oP = oSeg + ST * ns;              // [w][3]
         oBC = oP + 3 * (ns + 1);          // d0[NR], dN[NR]: fixed boundary derivatives, [r-1][axis]
-        oBase = oBC + 2 * D::NR;
+        oBase = even(oBC + 2 * D::NR);    // 16-byte aligned rows
         oSegx = oBase + BS * nr;
         oS = oSegx + XS * ns;             // ns ints
-        size = oS + (ns + 1) / 2;
-        size |= 1;                        // odd pitch: t * size (mod 16) is distinct for 16 consecutive t
+        size = even(oS + (ns + 1) / 2);
+        if (size % 4 == 0) size += 2;     // even (alignment) and 2 mod 4: the blocks of the ~4 trajectories a warp of
+                                          // sweep lanes reads at the same offsets start 4 banks apart, not on top of each other
     }
 };
 
@@ -84,7 +90,7 @@ template <int O>
 struct FBaseRows {
     const double *p;
     static constexpr int FS = 1;
-    static constexpr bool VEC = false;  // odd row pitch
+    static constexpr bool VEC = true;  // rows are 16-byte aligned (FusedSmem): 128-bit shared-memory loads
     using Mem = PlainMem;
     __device__ __forceinline__ const double *operator()(int j) const { return p + j * FusedSmem<O>::BS; }
     __device__ __forceinline__ void prefetch(int) const {}
@@ -108,14 +114,34 @@ struct FPos {
 };
 template <int O, int LANES, class MemT = PlainMem>
 struct FStateRows {
-    double *p;  // this lane's column
-    static constexpr int FS = LANES;
+    double *p;  // this lane's column: base + 2 * lane (rows are [field / 2][lane][2], see RowPair)
+    static constexpr int FS = 1;
     static constexpr bool VEC = false;
     static constexpr bool ENABLED = true;  // usable as the solution sink of thomas_backward
+    static constexpr int PAIR = LANES;
     using Mem = MemT;
     __device__ __forceinline__ double *operator()(int j) const { return p + (size_t)j * (Dim<O>::NSTATE * LANES); }
     __device__ __forceinline__ void prefetch(int) const {}
 };
+
+// Sweep state of the speculative lanes in the CTA's L2-resident scratch slot: rows [row][field / 2][lane][2] (RowPair).
+template <int O, int LANES>
+struct FSlotRows {
+    double *p;  // slot + 2 * lane
+    static constexpr int FS = 1;
+    static constexpr bool VEC = false;
+    static constexpr bool ENABLED = true;
+    static constexpr int PAIR = LANES;
+    using Mem = L2KeepMem;
+    __device__ __forceinline__ double *operator()(int j) const { return p + (size_t)j * (Dim<O>::NSTATE * LANES); }
+    __device__ __forceinline__ void prefetch(int) const {}
+};
+
+// field f of state row j in a paired-layout state array of LANES lanes, relative to the lane's column pointer
+template <int O, int LANES>
+__device__ __forceinline__ constexpr int state_at_idx(int j, int f) {
+    return j * (Dim<O>::NSTATE * LANES) + (f >> 1) * (2 * LANES) + (f & 1);
+}
 
 // segment time powers from smem: ip[e] = T^-e (e = 0..2o-1), pT[r] = T^r (r = 0..o-1)
 template <int O>
@@ -138,7 +164,7 @@ __device__ __forceinline__ void fused_derivs(const double *bcs, const double *st
     for (int i = 0; i < D::NR; ++i) {
         if (w == 0) d[i] = bcs[i];
         else if (w == ns) d[i] = bcs[D::NR + i];
-        else d[i] = state_lane[((w - 1) * D::NSTATE + D::SX + i) * FUSED_SMEM_LANES];
+        else d[i] = state_lane[state_at_idx<O, FUSED_SMEM_LANES>(w - 1, D::SX + i)];
     }
 }
 
@@ -330,8 +356,8 @@ __device__ __forceinline__ bool fused_coeff_item(const double *blk, const double
 #pragma unroll
     for (int d = 1; d < O; ++d) {
         const int f = (d - 1) * 3 + a;
-        yk[d] = (k == 0) ? bcs[f] : state_lane[((k - 1) * D::NSTATE + D::SX + f) * FUSED_SMEM_LANES];
-        yk1[d] = (k == ns - 1) ? bcs[D::NR + f] : state_lane[(k * D::NSTATE + D::SX + f) * FUSED_SMEM_LANES];
+        yk[d] = (k == 0) ? bcs[f] : state_lane[state_at_idx<O, FUSED_SMEM_LANES>(k - 1, D::SX + f)];
+        yk1[d] = (k == ns - 1) ? bcs[D::NR + f] : state_lane[state_at_idx<O, FUSED_SMEM_LANES>(k, D::SX + f)];
     }
     double ip[2 * O], pT[O], co[M];
     fused_powers<O>(blk + L.oSeg + k * L.ST, ip, pT);
@@ -375,7 +401,7 @@ __device__ __noinline__ void fused_phase_pass1(const FusedParams &p, int nt) {
     const FusedTail<O> T(smem, p.ns, p.tpc, p.nit, p.traj_stride);
     double unused;
     const int t = tid >> 1;
-    const FStateRows<O, FUSED_SMEM_LANES> st{T.state1 + t};
+    const FStateRows<O, FUSED_SMEM_LANES> st{T.state1 + 2 * t};
     const unsigned pm = 2 * nt >= 32 ? 0xffffffffu : (1u << (2 * nt)) - 1u;
     const bool ok = fused_chain_pair<O, false>(smem + t * p.traj_stride, p.ns, 0.0, st, tid & 1, pm, &unused);
     if ((tid & 1) == 0) T.ok1[t] = ok ? 1 : 0;
@@ -399,7 +425,7 @@ __device__ __noinline__ void fused_phase_spec(const FusedParams &p, long long ti
         const double vw = reweighted_vw(p.sp.vw0, q);
         const double add00 = vw > 0.0 ? 2.0 * vw : 0.0;
         double *slot = p.state_ws + (size_t)blockIdx.x * (ns - 1) * D::NSTATE * GL;
-        const FStateRows<O, GL, L2KeepMem> st{slot + l};
+        const FSlotRows<O, GL> st{slot + 2 * l};
         long long *clk = nullptr;  // dev instrumentation: speculative lanes 0, 64 and 128 of the CTA's first tile
         if (p.phase_clocks && tile == blockIdx.x && (l & 63) == 0) clk = p.phase_clocks + blockIdx.x * 16 + 10 + 2 * (l >> 6);
         const ChainResult r = fused_chain_spec<O>(smem + t * tstride, ns, add00, st, clk);
@@ -409,7 +435,7 @@ __device__ __noinline__ void fused_phase_spec(const FusedParams &p, long long ti
         const int t = tid >> 1, q = nit - 1;
         const double vw = reweighted_vw(p.sp.vw0, q);
         const double add00 = vw > 0.0 ? 2.0 * vw : 0.0;
-        const FStateRows<O, SL> st{T.state1 + t};
+        const FStateRows<O, SL> st{T.state1 + 2 * t};
         const unsigned pm = 2 * nt >= 32 ? 0xffffffffu : (1u << (2 * nt)) - 1u;
         double mdv;
         const bool ok = use_pw ? fused_chain_pair<O, true>(smem + t * tstride, ns, add00, st, tid & 1, pm, &mdv)
@@ -506,7 +532,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_c
             MSNAP_STAMP();
             for (int i = tid; i < nt * ns; i += FUSED_THREADS) {
                 const int t = i / ns, k = i - t * ns;
-                const int s = fused_search_item<O>(smem + t * tstride, state1 + t, ns, k);
+                const int s = fused_search_item<O>(smem + t * tstride, state1 + 2 * t, ns, k);
                 reinterpret_cast<int *>(smem + t * tstride + L.oS)[k] = s;
                 if (p.best_s_out) p.best_s_out[g0 + i] = s;
             }
@@ -545,8 +571,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_c
                 const int l = tid - g0l;
                 const int t = l / (nit - 1), q = l - t * (nit - 1);
                 if (sel[t] == q) {
-                    const FStateRows<O, GL, L2KeepMem> st{slot + l};
-                    const FStateRows<O, SL> xo{state1 + t};
+                    const FSlotRows<O, GL> st{slot + 2 * l};
+                    const FStateRows<O, SL> xo{state1 + 2 * t};
                     fused_replay<O>(smem + t * tstride, ns, st, xo);
                 }
             }
@@ -581,7 +607,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_c
             const int t = i / (ns * 3), r = i - t * ns * 3;
             const int k = r / 3, a = r - 3 * k;
             const long long row = ((g0 + (long long)t * ns + k) * 3 + a) * D::M;
-            const bool finite = fused_coeff_item<O>(smem + t * tstride, state1 + t, ns, k, a, p.coeff_out + row,
+            const bool finite = fused_coeff_item<O>(smem + t * tstride, state1 + 2 * t, ns, k, a, p.coeff_out + row,
                                                     p.coeff_mirror ? p.coeff_mirror + row : nullptr);
             if (!finite && p.flags) atomicOr(p.flags + b0 + t, 1u);
         }

@@ -24,6 +24,9 @@ for weights in ("shipped", "plain"):
         print(f"{weights} B={B} ns={ns}: fused CTAs {len(f)}, first tile {((f[:, len(names)] - f[:, 0]) / GHZ).mean():.1f} us mean, "
               f"span {(f[:, len(names)].max() - f[:, 0].min()) / GHZ:.1f} us")
         print("   " + "  ".join(f"{n} {m:.1f}" for n, m in zip(names, d.mean(0))))
+        tot = (f[:, len(names)] - f[:, 0]) / GHZ
+        print("   per-CTA tile time: min %.1f  p50 %.1f  p90 %.1f  max %.1f us;  phase maxima: " % (tot.min(), np.median(tot), np.quantile(tot, 0.9), tot.max())
+              + "  ".join(f"{n} {m:.1f}" for n, m in zip(names, d.max(0))))
         if weights == "shipped":
             for w in range(3):
                 fe, be = f[:, 10 + 2 * w], f[:, 11 + 2 * w]

@@ -15,6 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--mb", type=float, default=33.0)
 ap.add_argument("--iters", type=int, default=200)
 ap.add_argument("--numa", type=int, default=0)
+ap.add_argument("--out", default="")
 a = ap.parse_args()
 rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
 torch.cuda.set_device(local)
@@ -53,6 +54,10 @@ for name, fn in (("d2h", lambda: h.copy_(d, non_blocking=True)),
         per = [gbs]
     out[name] = {"per_rank_GBps": per, "total_GBps": sum(per), "min_GBps": min(per)}
 if rank == 0:
-    print(json.dumps({"n_gpus": world, "mb_per_copy": a.mb, "numa_pinned": bool(a.numa), "cpus": pinned_to and len(pinned_to), **out}))
+    line = json.dumps({"n_gpus": world, "mb_per_copy": a.mb, "numa_pinned": bool(a.numa), "cpus": pinned_to and len(pinned_to), **out})
+    print(line)
+    if a.out:
+        with open(a.out, "a") as f:
+            f.write(line + "\n")
 if world > 1:
     dist.destroy_process_group()

@@ -435,7 +435,12 @@ struct SampleWs {
 };
 // Tile size of the single-launch sampler.  One segment per thread while that still gives every CTA slot of the GPU a
 // tile; two segments per thread for big batches (half as many tiles to look back over).
-int scan_tpt(int ns, long long B, int sm_count) {
+// `capacity` (the caller's row capacity, normally msnap_sample_bound = the number of candidates) is the only hint the host
+// has about the segment durations: a batch with thousands of candidates per trajectory (kilometre-long legs: the
+// reference's shipped mission) has segments that a whole warp walks (warp_sample_long), and gets one trajectory per tile so
+// that those warps spread over all SMs.
+int scan_tpt(int ns, long long B, int sm_count, long long capacity) {
+    if (capacity / (B > 0 ? B : 1) > 16LL * SAMPLE_MASK_BITS) return 1;
     const int one = ns >= SCAN_THREADS ? 1 : SCAN_THREADS / ns;
     const int two = ns >= 2 * SCAN_THREADS ? 1 : 2 * SCAN_THREADS / ns;
     const long long tiles_two = (B + two - 1) / two;
@@ -444,13 +449,13 @@ int scan_tpt(int ns, long long B, int sm_count) {
 
 // The single-launch sampler keeps a tile's per-segment bookkeeping in shared memory: uniform batches only, and only
 // while a one-trajectory tile fits (very long trajectories take the per-pass kernels).
-bool use_scan_sampler(int ns_uniform, long long B, int policy, int sm_count) {
+bool use_scan_sampler(int ns_uniform, long long B, int policy, int sm_count, long long capacity) {
     if (ns_uniform <= 0 || policy == 1) return false;
-    return scan_smem_bytes(scan_tpt(ns_uniform, B, sm_count), ns_uniform, 4, false) <= 96 * 1024;
+    return scan_smem_bytes(scan_tpt(ns_uniform, B, sm_count, capacity), ns_uniform, 4, false) <= 96 * 1024;
 }
 
-size_t sample_ws_bytes(long long n_seg, long long B, int ns_uniform, int policy, int sm_count) {
-    if (use_scan_sampler(ns_uniform, B, policy, sm_count)) {
+size_t sample_ws_bytes(long long n_seg, long long B, int ns_uniform, int policy, int sm_count, long long capacity) {
+    if (use_scan_sampler(ns_uniform, B, policy, sm_count, capacity)) {
         const long long n_tiles = B;  // upper bound on the tile count (tpt >= 1)
         return padded((size_t)(n_tiles + 1 + 256) * sizeof(unsigned long long)) + 256;  // + ticket + per-SM counters
     }
@@ -458,9 +463,10 @@ size_t sample_ws_bytes(long long n_seg, long long B, int ns_uniform, int policy,
            padded((size_t)n_seg * 3 * sizeof(double)) + padded(n_seg * sizeof(long long)) +
            padded(B * sizeof(long long)) + padded((size_t)(B / SCAN_BLOCK + 2) * sizeof(long long));
 }
-void carve_sample_ws(Arena &a, long long n_seg, long long B, int ns_uniform, int policy, int sm_count, SampleWs &s) {
-    if (use_scan_sampler(ns_uniform, B, policy, sm_count)) {
-        s.tpt = scan_tpt(ns_uniform, B, sm_count);
+void carve_sample_ws(Arena &a, long long n_seg, long long B, int ns_uniform, int policy, int sm_count, long long capacity,
+                     SampleWs &s) {
+    if (use_scan_sampler(ns_uniform, B, policy, sm_count, capacity)) {
+        s.tpt = scan_tpt(ns_uniform, B, sm_count, capacity);
         s.n_tiles = (B + s.tpt - 1) / s.tpt;
         s.status = arena_take<unsigned long long>(a, s.n_tiles + 1 + 256);  // + ticket + per-SM arrival counters
         s.ticket = reinterpret_cast<unsigned int *>(s.status + s.n_tiles);
@@ -602,7 +608,7 @@ int generate_dev(msnap_context *h, const msnap_config *cfg, double sd, double v_
     const bool ragged = bi.ns_uniform <= 0 && B < 2000000000LL;
     const size_t n_pts = (size_t)(n_seg + B);
     int rc = arena_reserve(h, h->ws, solve_ws_bytes<O>(n_seg, B, true, coeff_out == nullptr, f, spec) +
-                                        sample_ws_bytes(n_seg, B, bi.ns_uniform, h->policy, h->sm_count) +
+                                        sample_ws_bytes(n_seg, B, bi.ns_uniform, h->policy, h->sm_count, capacity) +
                                         (ragged ? padded(n_seg * sizeof(int)) : 0) +
                                         (h->wp_frame ? padded(n_pts * 3 * sizeof(double)) : 0));
     if (rc) return rc;
@@ -620,7 +626,7 @@ int generate_dev(msnap_context *h, const msnap_config *cfg, double sd, double v_
     SolveWs w;
     carve_solve_ws<O>(h->ws, n_seg, B, true, coeff_out, f, spec, w);
     SampleWs s;
-    carve_sample_ws(h->ws, n_seg, B, bi.ns_uniform, h->policy, h->sm_count, s);
+    carve_sample_ws(h->ws, n_seg, B, bi.ns_uniform, h->policy, h->sm_count, capacity, s);
     SolveIO io;
     io.wp = wp;
     io.v_avg = v_avg;

@@ -614,6 +614,71 @@ __device__ __forceinline__ void write_candidates(const double (&c)[3][2 * O], do
     }
 }
 
+// Warp-cooperative form of the acceptance loop for a segment with MANY candidates (more than the 128 the acceptance
+// mask describes: T > 12.8 s -- the reference's shipped mission, 22 km legs at 30 m/s, has 7 000 per segment).  One lane
+// walking them costs ~50 dependent instructions per candidate; here the warp evaluates 32 consecutive candidates at once
+// and then resolves the acceptances in order: the first lane whose distance to the last accepted point reaches the
+// threshold is accepted (ballot + find-first), its point becomes the reference point of the lanes behind it, which are
+// tested again, until no lane of the block passes.  Same candidates (t accumulated by repeated addition, every lane
+// running the 32 additions of a block), same tests in the same order as ms.cpp:138-152, so the rows are the sequential
+// loop's bit for bit.  All 32 lanes call with the same arguments; returns the number of accepted candidates and the last
+// accepted point (the segment's start point if none).  WRITE: row `row + k` receives the k-th accepted point.
+template <int O, bool WRITE>
+__device__ __forceinline__ int warp_sample_long(const double (&c)[3][2 * O], double Tk, const AcceptTest &accept, long long row,
+                                                long long capacity, double *__restrict__ samples, bool &dropped,
+                                                double (&last)[3]) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const double dt = sample_dt(Tk);
+    const double tmax = sample_time_ok(Tk) ? Tk + 1e-12 : -1.0;
+    double prev[3];
+    eval_xyz<O>(c, 0.0, prev);
+    int n = 0;
+    double tb = 0.0;  // t of the last candidate of the previous block (t_1 = 0 + dt = dt exactly)
+    bool more = true;
+    while (more) {
+        double t = tb, mine = 0.0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            t = __dadd_rn(t, dt);
+            if (j == lane) mine = t;
+        }
+        tb = t;
+        const bool valid = mine <= tmax;  // the candidate times increase: the valid lanes are a prefix of the warp
+        more = __all_sync(FULL, valid);
+        double cur[3];
+        eval_xyz<O>(c, fmin(mine, Tk), cur);
+        int start = 0;
+        while (true) {
+            const bool ok = valid && lane >= start && accept(cur, prev);
+            const unsigned m = __ballot_sync(FULL, ok);
+            if (!m) break;
+            const int f = __ffs(m) - 1;
+            prev[0] = __shfl_sync(FULL, cur[0], f);
+            prev[1] = __shfl_sync(FULL, cur[1], f);
+            prev[2] = __shfl_sync(FULL, cur[2], f);
+            if (WRITE && lane == f) {
+                const long long r = row + n;
+                if (r < capacity) {
+                    samples[3 * r] = cur[0]; samples[3 * r + 1] = cur[1]; samples[3 * r + 2] = cur[2];
+                } else {
+                    dropped = true;
+                }
+            }
+            ++n;
+            start = f + 1;
+        }
+    }
+    last[0] = prev[0]; last[1] = prev[1]; last[2] = prev[2];
+    return n;
+}
+
+// A segment is "long" when it has more candidates than the acceptance mask describes: the 129th tabulated candidate time
+// (ttab[129]) still lies within T + 1e-12.  (Segments shorter than 1 s use dt = T/10 and have 10 or 11 candidates.)
+__device__ __forceinline__ bool sample_is_long(double Tk, const double *ttab) {
+    return sample_time_ok(Tk) && sample_dt(Tk) == 0.1 && ttab[SAMPLE_MASK_BITS + 1] <= Tk + 1e-12;
+}
+
 // Stores one sample row unless it lies beyond the caller's capacity.
 struct RowSink {
     double *__restrict__ samples;
@@ -863,7 +928,7 @@ __host__ __device__ inline size_t scan_smem_bytes(int tpt, int ns, int order, bo
     const size_t seg_cap = (size_t)tpt * ns;
     return SAMPLE_TTAB_N * sizeof(double) + seg_cap * 2 * sizeof(unsigned long long) + seg_cap * 3 * sizeof(double) +
            seg_cap * sizeof(double) + (coef_smem ? seg_cap * (6 * order + 1) * sizeof(double) : 0) +
-           (size_t)(tpt + 1) * sizeof(long long) + seg_cap * 3 * sizeof(int) +
+           (size_t)(tpt + 1) * sizeof(long long) + seg_cap * 4 * sizeof(int) +
            (size_t)tpt * sizeof(int) + SCAN_DESC_CAP * sizeof(unsigned) + 16;
 }
 
@@ -886,7 +951,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_sample_scan(
     int *cnt = reinterpret_cast<int *>(traj_base + tpt + 1);                              // [seg_cap] signed count
     int *seg_start = cnt + seg_cap;                                                       // [seg_cap] row in trajectory
     int *perm = seg_start + seg_cap;                                                      // [seg_cap] longest first
-    int *append = perm + seg_cap;                                                         // [tpt]
+    int *long_list = perm + seg_cap;                                                      // [seg_cap] segments with > 128 candidates
+    int *append = long_list + seg_cap;                                                    // [tpt]
     unsigned *desc = reinterpret_cast<unsigned *>(append + tpt);                          // [SCAN_DESC_CAP]
     const AcceptTest accept(sample_distance);
     __shared__ double wstage[(SCAN_THREADS / 32) * 96];  // per warp: 32 rows x 3 doubles staged for coalesced stores
@@ -896,6 +962,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_sample_scan(
     __shared__ long long sh_part[SCAN_THREADS / 32];
     __shared__ int sh_first[SCAN_THREADS / 32];
     __shared__ int sh_slot, sh_sched[SCAN_THREADS / 32];
+    __shared__ int sh_n_long;
     for (int i = tid; i < SAMPLE_TTAB_N; i += SCAN_THREADS) ttab[i] = t_table[i];
     // Which chunk of the ranking a warp takes in phase A: (its scheduler + the CTA's arrival order on this SM) mod 4,
     // a Latin square over (scheduler, co-resident CTA), so that every scheduler of the SM gets one chunk of each rank.
@@ -931,7 +998,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_sample_scan(
     };
 
     while (true) {
-        if (tid == 0) sh_tile = (long long)atomicAdd(ticket, 1u);
+        if (tid == 0) {
+            sh_tile = (long long)atomicAdd(ticket, 1u);
+            sh_n_long = 0;
+        }
         for (int i = tid; i <= SAMPLE_MASK_BITS; i += SCAN_THREADS) hist[i] = 0;
         __syncthreads();
         const long long tile = sh_tile;
@@ -984,6 +1054,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_sample_scan(
                 const int rk = half == 0 ? r0 + rot_tid : r0 + 2 * SCAN_THREADS - 1 - rot_tid;
                 if (rk >= nseg) continue;
                 const int i = perm[rk];
+                if (sample_is_long(segT[i], ttab)) {  // left to a whole warp (below)
+                    long_list[atomicAdd(&sh_n_long, 1)] = i;
+                    continue;
+                }
                 double c[3][2 * O];
                 load_coeff<O>(coeff, g0 + i, c);
                 if (coef_smem) {
@@ -1005,6 +1079,28 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_sample_scan(
             }
         }
         __syncthreads();
+        // long segments: a warp each (warp_sample_long), count only
+        const int n_long = sh_n_long;
+        for (int q = wid; q < n_long; q += SCAN_THREADS / 32) {
+            const int i = long_list[q];
+            double c[3][2 * O], lp[3];
+            load_coeff<O>(coeff, g0 + i, c);
+            if (coef_smem && lane == 0) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int j = 0; j < 2 * O; ++j) csm[i * CP + a * 2 * O + j] = c[a][j];
+            }
+            bool dropped = false;
+            const int n = warp_sample_long<O, false>(c, segT[i], accept, 0, 0, nullptr, dropped, lp);
+            if (lane == 0) {
+                cnt[i] = -n - 1;  // negative: no acceptance mask; the rows are written by a warp again (phase D)
+                mask[2 * i] = 0ull;
+                mask[2 * i + 1] = 0ull;
+                last[3 * i] = lp[0]; last[3 * i + 1] = lp[1]; last[3 * i + 2] = lp[2];
+            }
+        }
+        if (n_long > 0) __syncthreads();
         SCAN_STAMP();
         // ---- B: per trajectory: segment start rows, end-point rule (ms.cpp:157-160), row count
         if (tid < nt) {
@@ -1077,9 +1173,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_sample_scan(
                         }
                     }
                 } else {
-                    for (int j = 0; j < n; ++j, ++row)
-                        if (row >= 0 && row < SCAN_DESC_CAP)
-                            desc[row] = ((unsigned)i << 8) | (j == 0 ? DESC_SLOW : DESC_SKIP);
+                    for (int j = 0; j < n; ++j, ++row)  // rows of a long segment: written by a whole warp after the chunk loop
+                        if (row >= 0 && row < SCAN_DESC_CAP) desc[row] = ((unsigned)i << 8) | DESC_SKIP;
                 }
             }
         };
@@ -1149,13 +1244,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_sample_scan(
                         double c[3][2 * O];
                         staged_coeff(g0, i, c);
                         const double Tk = segT[i];
-                        if (code == DESC_SLOW) {  // > SAMPLE_MASK_BITS candidates: this lane redoes the segment
-                            bool dropped = false;
-                            const RowSink put{samples, capacity, &dropped};
-                            write_candidates<O>(c, Tk, false, 0ull, 0ull, accept, ttab, tile_base + r, put);
-                            if (dropped && flags) atomicOr(flags + b0 + i / ns, 2u);
-                            hole = true;
-                        } else {
+                        {
                             double tt;
                             if (code == DESC_FIRST) tt = 0.0;
                             else if (code == DESC_END) tt = Tk;
@@ -1188,6 +1277,16 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_sample_scan(
                 }
                 __syncwarp();
             }
+        }
+        // long segments: the same warp-cooperative walk again, this time writing the rows
+        for (int q = wid; q < n_long; q += SCAN_THREADS / 32) {
+            const int i = long_list[q];
+            const int t = i / ns;
+            double c[3][2 * O], lp[3];
+            staged_coeff(g0, i, c);
+            bool dropped = false;
+            warp_sample_long<O, true>(c, segT[i], accept, tile_base + traj_base[t] + seg_start[i], capacity, samples, dropped, lp);
+            if (__any_sync(0xffffffffu, dropped) && lane == 0 && flags) atomicOr(flags + b0 + t, 2u);
         }
         __syncthreads();  // smem is reused by the next tile
         SCAN_STAMP();

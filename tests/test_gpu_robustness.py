@@ -107,3 +107,43 @@ def test_altitude_failure_semantics_follow_the_reference(tool):
         out, _, _, fl = tool.altitude_optimize_batch(rows, off, bad, elev, return_info=True)
         assert np.all(fl & 1) and np.array_equal(out, rows)          # untouched
     tool.set_altitude_policy(0)
+
+
+@pytest.mark.parametrize("sd,v", [(300.0, 30.0), (5.0, 30.0), (40.0, 200.0)])
+def test_long_segments_warp_cooperative_sampler_equals_sequential_loop(tool, sd, v):
+    """Segments with more than 128 candidates (T > 12.8 s: the reference's shipped mission has 7 000 per segment) are walked by
+    a whole warp in the single-launch sampler.  Rows must equal, bit for bit, those of the per-pass kernels (policy 1), where
+    one lane walks the candidates in the reference's order -- on a batch that mixes sub-second, ordinary and very long
+    segments -- and the compiled reference on a few of them."""
+    from cs_pathplan_b200 import shipped_config
+    from oracle import ref
+
+    rng = np.random.default_rng(17)
+    B, ns = 300, 6
+    legs = rng.choice([3.0, 40.0, 300.0, 2500.0, 22000.0], size=(B, ns, 1)) * rng.uniform(0.5, 1.5, (B, ns, 1))
+    d = rng.normal(size=(B, ns, 3))
+    d[..., 2] *= 0.05
+    d /= np.linalg.norm(d, axis=2, keepdims=True)
+    wp = np.concatenate([np.zeros((B, 1, 3)), np.cumsum(d * legs, axis=1)], axis=1).reshape(-1, 3)
+    cfg = shipped_config()
+    fast = tool.generate_batch(cfg, wp, ns=ns, sample_distance_override=sd, v_avg_override=v)
+    assert not fast.flags.any() and (fast.times > 12.8).sum() > B and (fast.times < 1.0 + 1e-9).sum() > 0
+    tool.set_reweight_policy(1)
+    try:
+        slow = tool.generate_batch(cfg, wp, ns=ns, sample_distance_override=sd, v_avg_override=v)
+    finally:
+        tool.set_reweight_policy(0)
+    assert np.array_equal(fast.sample_offset, slow.sample_offset) and np.array_equal(fast.samples, slow.samples)
+    assert np.array_equal(fast.stats, slow.stats)
+    rc = ref.shipped_config()
+    for b in (0, 7, 150, B - 1):
+        want = ref.generate(wp[b * (ns + 1):(b + 1) * (ns + 1)], rc, sd, v)
+        got = fast.trajectory(b)
+        assert got.shape == want.shape and np.abs(got - want).max() <= 1e-6, b
+    # a capacity that cuts through the rows of a long segment: exact layout, rows that fit are right, flagged
+    cap = int(fast.sample_offset[B // 2]) + 3
+    with pytest.raises(MsnapError) as e:
+        tool.generate_batch(cfg, wp, ns=ns, sample_distance_override=sd, v_avg_override=v, capacity=cap)
+    part = e.value.partial
+    assert np.array_equal(part.sample_offset, fast.sample_offset) and np.array_equal(part.samples, fast.samples[:cap])
+    assert (part.flags[B // 2 + 1:] & 2).all() and not (part.flags[: B // 2] & 2).any()

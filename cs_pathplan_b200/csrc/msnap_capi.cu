@@ -27,7 +27,7 @@ static const MsnapOrderTab h_tab[MSNAP_MAX_ORDER - MSNAP_MIN_ORDER + 1] = MSNAP_
 
 using namespace msnap;
 
-static constexpr int T_TABLE_N = 256;  // candidate-time table of the sampler's write pass (>= SAMPLE_TTAB_N)
+static constexpr int T_TABLE_N = SAMPLE_TTAB_BIG;  // candidate-time table of the sampler (>= SAMPLE_TTAB_N; long segments index all of it)
 
 // ------------------------------------------------------------------------------------------------------------
 // handle

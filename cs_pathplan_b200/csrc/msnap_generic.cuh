@@ -515,6 +515,7 @@ __device__ __forceinline__ bool sample_time_ok(double T) { return T > 0.0 && T <
 
 constexpr int SAMPLE_MASK_BITS = 128;            // candidates per segment the acceptance mask can describe
 constexpr int SAMPLE_TTAB_N = SAMPLE_MASK_BITS + 2;  // entries of t_table a write pass needs
+constexpr int SAMPLE_TTAB_BIG = 1 << 14;         // entries of the handle's table in global memory (T up to 1 638 s)
 
 template <int O>
 __device__ __forceinline__ void load_coeff(const double *__restrict__ coeff, long long g, double (&c)[3][2 * O]) {
@@ -624,9 +625,9 @@ __device__ __forceinline__ void write_candidates(const double (&c)[3][2 * O], do
 // loop's bit for bit.  All 32 lanes call with the same arguments; returns the number of accepted candidates and the last
 // accepted point (the segment's start point if none).  WRITE: row `row + k` receives the k-th accepted point.
 template <int O, bool WRITE>
-__device__ __forceinline__ int warp_sample_long(const double (&c)[3][2 * O], double Tk, const AcceptTest &accept, long long row,
-                                                long long capacity, double *__restrict__ samples, bool &dropped,
-                                                double (&last)[3]) {
+__device__ __forceinline__ int warp_sample_long(const double (&c)[3][2 * O], double Tk, const AcceptTest &accept,
+                                                const double *__restrict__ t_table, long long row, long long capacity,
+                                                double *__restrict__ samples, bool &dropped, double (&last)[3]) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const double dt = sample_dt(Tk);
@@ -635,15 +636,24 @@ __device__ __forceinline__ int warp_sample_long(const double (&c)[3][2 * O], dou
     eval_xyz<O>(c, 0.0, prev);
     int n = 0;
     double tb = 0.0;  // t of the last candidate of the previous block (t_1 = 0 + dt = dt exactly)
+    int base = 0;     // candidates before this block
     bool more = true;
     while (more) {
-        double t = tb, mine = 0.0;
+        double mine;
+        if (dt == 0.1 && base + 32 < SAMPLE_TTAB_BIG) {  // t_table[i] = the i-th accumulated time (msnap_create)
+            mine = __ldg(t_table + base + lane + 1);
+            tb = __shfl_sync(FULL, mine, 31);
+        } else {  // beyond the table: every lane runs the block's 32 additions
+            double t = tb;
+            mine = 0.0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            t = __dadd_rn(t, dt);
-            if (j == lane) mine = t;
+            for (int j = 0; j < 32; ++j) {
+                t = __dadd_rn(t, dt);
+                if (j == lane) mine = t;
+            }
+            tb = t;
         }
-        tb = t;
+        base += 32;
         const bool valid = mine <= tmax;  // the candidate times increase: the valid lanes are a prefix of the warp
         more = __all_sync(FULL, valid);
         double cur[3];
@@ -1092,7 +1102,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_sample_scan(
                     for (int j = 0; j < 2 * O; ++j) csm[i * CP + a * 2 * O + j] = c[a][j];
             }
             bool dropped = false;
-            const int n = warp_sample_long<O, false>(c, segT[i], accept, 0, 0, nullptr, dropped, lp);
+            const int n = warp_sample_long<O, false>(c, segT[i], accept, t_table, 0, 0, nullptr, dropped, lp);
             if (lane == 0) {
                 cnt[i] = -n - 1;  // negative: no acceptance mask; the rows are written by a warp again (phase D)
                 mask[2 * i] = 0ull;
@@ -1285,7 +1295,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_sample_scan(
             double c[3][2 * O], lp[3];
             staged_coeff(g0, i, c);
             bool dropped = false;
-            warp_sample_long<O, true>(c, segT[i], accept, tile_base + traj_base[t] + seg_start[i], capacity, samples, dropped, lp);
+            warp_sample_long<O, true>(c, segT[i], accept, t_table, tile_base + traj_base[t] + seg_start[i], capacity, samples, dropped,
+                                      lp);
             if (__any_sync(0xffffffffu, dropped) && lane == 0 && flags) atomicOr(flags + b0 + t, 2u);
         }
         __syncthreads();  // smem is reused by the next tile

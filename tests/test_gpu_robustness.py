@@ -109,7 +109,7 @@ def test_altitude_failure_semantics_follow_the_reference(tool):
     tool.set_altitude_policy(0)
 
 
-@pytest.mark.parametrize("sd,v", [(300.0, 30.0), (5.0, 30.0), (40.0, 200.0)])
+@pytest.mark.parametrize("sd,v", [(300.0, 30.0), (5.0, 30.0), (40.0, 200.0), (300.0, 8.0)])   # (v = 8: T up to 4 000 s, beyond the time table)
 def test_long_segments_warp_cooperative_sampler_equals_sequential_loop(tool, sd, v):
     """Segments with more than 128 candidates (T > 12.8 s: the reference's shipped mission has 7 000 per segment) are walked by
     a whole warp in the single-launch sampler.  Rows must equal, bit for bit, those of the per-pass kernels (policy 1), where

@@ -57,7 +57,6 @@ SIGNATURES = {
     "msnap_synchronize": (_i, [_vp]),
     "msnap_set_reweight_policy": (_i, [_vp, _i]),
     "msnap_set_host_chunks": (_i, [_vp, _i]),
-    "msnap_set_sampler": (_i, [_vp, _i]),
     "msnap_set_zero_copy": (_i, [_vp, _i]),
     "msnap_launch_count": (_ll, [_vp]),
     "msnap_config_default": (None, [_cfgp]),

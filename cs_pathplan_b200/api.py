@@ -193,10 +193,6 @@ class TrajectoryGeneratorTool:
     def set_reweight_policy(self, policy: int):
         self._check(self._L.msnap_set_reweight_policy(self._h, int(policy)))
 
-    def set_sampler(self, mode: int):
-        """0 = evaluate-once staged sampler (default), 1 = count-then-re-evaluate sampler; identical rows."""
-        self._check(self._L.msnap_set_sampler(self._h, int(mode)))
-
     def set_host_chunks(self, n_chunks: int):
         """0 = automatic pipelining of the host-pointer path, 1 = one chunk (no overlap of copies and kernels)."""
         self._check(self._L.msnap_set_host_chunks(self._h, int(n_chunks)))

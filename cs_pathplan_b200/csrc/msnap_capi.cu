@@ -17,7 +17,6 @@
 #include "msnap_device.cuh"
 #include "msnap_generic.cuh"
 #include "msnap_fused.cuh"
-#include "msnap_sampler.cuh"
 #include "msnap_geo.cuh"
 #include "msnap_alt.cuh"
 #include "msnap_bezier.cuh"
@@ -58,8 +57,6 @@ struct msnap_context {
     long long launches = 0;
     int policy = 0;
     bool scan_coef_smem = false;      // sampler: stage the tile's coefficients in shared memory (MSNAP_SCAN_COEF_SMEM=1)
-    int sampler_mode = 0;             // uniform batches: 0 = k_sample_stage (every candidate evaluated once, rows staged in an
-                                      // L2-resident slot), 1 = k_sample_scan (count, then re-evaluate) -- MSNAP_SAMPLER=scan
     std::vector<FusedPlan> plans;     // cached launch plans
     // optional per-kernel timing (msnap_profile_begin/end): one event pair per launch on the launching stream
     long long *phase_clocks = nullptr;  // dev instrumentation (msnap_debug_phase_clocks)
@@ -435,18 +432,7 @@ struct SampleWs {
     int *sm_ctr = nullptr;  // [512] arrival order of the CTAs on each SM
     long long n_tiles = 0;
     int tpt = 0;
-    double *stage_ws = nullptr;  // k_sample_stage: [grid][slot_rows][3] staging slots (L2-resident: reused tile after tile)
-    long long slot_rows = 0;
-    unsigned stage_grid = 0;
 };
-constexpr size_t STAGE_WS_LIMIT = (size_t)1 << 30;  // staging slots beyond this: fall back to k_sample_scan
-// grid and slot size of k_sample_stage for a tile plan, or rows == 0 if it is not to be used
-inline void stage_plan(const msnap_context *h, int ns, int tpt, long long n_tiles, unsigned &grid, long long &rows) {
-    const long long resident = (long long)h->sm_count * 4;
-    grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
-    rows = (long long)tpt * ns * STAGE_ROWS_PER_SEG;
-    if (h->sampler_mode != 0 || (size_t)grid * rows * 24 > STAGE_WS_LIMIT || stage_smem_bytes(tpt, ns) > 52 * 1024) rows = 0;
-}
 // Tile size of the single-launch sampler.  One segment per thread while that still gives every CTA slot of the GPU a
 // tile; two segments per thread for big batches (half as many tiles to look back over).
 // `capacity` (the caller's row capacity, normally msnap_sample_bound = the number of candidates) is the only hint the host
@@ -468,31 +454,23 @@ bool use_scan_sampler(int ns_uniform, long long B, int policy, int sm_count, lon
     return scan_smem_bytes(scan_tpt(ns_uniform, B, sm_count, capacity), ns_uniform, 4, false) <= 96 * 1024;
 }
 
-size_t sample_ws_bytes(const msnap_context *h, long long n_seg, long long B, int ns_uniform, int policy, int sm_count,
-                       long long capacity) {
+size_t sample_ws_bytes(long long n_seg, long long B, int ns_uniform, int policy, int sm_count, long long capacity) {
     if (use_scan_sampler(ns_uniform, B, policy, sm_count, capacity)) {
         const long long n_tiles = B;  // upper bound on the tile count (tpt >= 1)
-        const int tpt = scan_tpt(ns_uniform, B, sm_count, capacity);
-        unsigned grid;
-        long long rows;
-        stage_plan(h, ns_uniform, tpt, (B + tpt - 1) / tpt, grid, rows);
-        return padded((size_t)(n_tiles + 1 + 256) * sizeof(unsigned long long)) + 256 +  // + ticket + per-SM counters
-               padded((size_t)grid * rows * 24);
+        return padded((size_t)(n_tiles + 1 + 256) * sizeof(unsigned long long)) + 256;  // + ticket + per-SM counters
     }
     return padded(n_seg * sizeof(int)) + padded(B * sizeof(int)) + padded((size_t)n_seg * 2 * sizeof(unsigned long long)) +
            padded((size_t)n_seg * 3 * sizeof(double)) + padded(n_seg * sizeof(long long)) +
            padded(B * sizeof(long long)) + padded((size_t)(B / SCAN_BLOCK + 2) * sizeof(long long));
 }
-void carve_sample_ws(const msnap_context *h, Arena &a, long long n_seg, long long B, int ns_uniform, int policy, int sm_count,
-                     long long capacity, SampleWs &s) {
+void carve_sample_ws(Arena &a, long long n_seg, long long B, int ns_uniform, int policy, int sm_count, long long capacity,
+                     SampleWs &s) {
     if (use_scan_sampler(ns_uniform, B, policy, sm_count, capacity)) {
         s.tpt = scan_tpt(ns_uniform, B, sm_count, capacity);
         s.n_tiles = (B + s.tpt - 1) / s.tpt;
         s.status = arena_take<unsigned long long>(a, s.n_tiles + 1 + 256);  // + ticket + per-SM arrival counters
         s.ticket = reinterpret_cast<unsigned int *>(s.status + s.n_tiles);
         s.sm_ctr = reinterpret_cast<int *>(s.status + s.n_tiles + 1);
-        stage_plan(h, ns_uniform, s.tpt, s.n_tiles, s.stage_grid, s.slot_rows);
-        if (s.slot_rows > 0) s.stage_ws = arena_take<double>(a, (size_t)s.stage_grid * s.slot_rows * 3);
         return;
     }
     s.seg_count = arena_take<int>(a, n_seg);
@@ -508,27 +486,6 @@ template <int O>
 int run_sample(msnap_context *h, const BatchIdx &bi, const double *coeff, const double *T, double sd,
                long long capacity, long long *sample_offset, double *samples, double *stats, unsigned *flags,
                SampleWs &s) {
-    if (s.status && s.stage_ws) {  // uniform batch: count + stage, scan, copy in one launch (every candidate evaluated once)
-        const int ns = bi.ns_uniform;
-        const size_t smem = stage_smem_bytes(s.tpt, ns);
-        MS_CUDA(h, cudaMemsetAsync(s.status, 0, (size_t)(s.n_tiles + 1 + 256) * sizeof(unsigned long long), h->stream));
-        if (smem > 40 * 1024) cudaFuncSetAttribute(k_sample_stage<O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        prof_before(h, "k_sample_stage");
-        k_sample_stage<O><<<s.stage_grid, STAGE_THREADS, smem, h->stream>>>(bi.B, ns, s.tpt, s.n_tiles, coeff, T, sd, h->d_ttab,
-                                                                            s.status, s.ticket, capacity, sample_offset, samples,
-                                                                            flags, s.sm_ctr, s.stage_ws, s.slot_rows,
-                                                                            h->phase_clocks);
-        prof_after(h);
-        ++h->launches;
-        cudaError_t e = cudaPeekAtLastError();
-        if (e != cudaSuccess) {
-            h->last_error = std::string("k_sample_stage: ") + cudaGetErrorString(e);
-            cudaGetLastError();
-            return MSNAP_ERR_CUDA;
-        }
-        if (stats) MS_LAUNCH(h, k_stats, grid_for(bi.B * 32, 256), 256, bi.B, sample_offset, samples, capacity, stats);
-        return MSNAP_OK;
-    }
     if (s.status) {  // uniform batch: count + scan + write in one launch
         const int ns = bi.ns_uniform;
         // stage the tile's coefficients in shared memory while four CTAs still fit an SM
@@ -651,7 +608,7 @@ int generate_dev(msnap_context *h, const msnap_config *cfg, double sd, double v_
     const bool ragged = bi.ns_uniform <= 0 && B < 2000000000LL;
     const size_t n_pts = (size_t)(n_seg + B);
     int rc = arena_reserve(h, h->ws, solve_ws_bytes<O>(n_seg, B, true, coeff_out == nullptr, f, spec) +
-                                        sample_ws_bytes(h, n_seg, B, bi.ns_uniform, h->policy, h->sm_count, capacity) +
+                                        sample_ws_bytes(n_seg, B, bi.ns_uniform, h->policy, h->sm_count, capacity) +
                                         (ragged ? padded(n_seg * sizeof(int)) : 0) +
                                         (h->wp_frame ? padded(n_pts * 3 * sizeof(double)) : 0));
     if (rc) return rc;
@@ -669,7 +626,7 @@ int generate_dev(msnap_context *h, const msnap_config *cfg, double sd, double v_
     SolveWs w;
     carve_solve_ws<O>(h->ws, n_seg, B, true, coeff_out, f, spec, w);
     SampleWs s;
-    carve_sample_ws(h, h->ws, n_seg, B, bi.ns_uniform, h->policy, h->sm_count, capacity, s);
+    carve_sample_ws(h->ws, n_seg, B, bi.ns_uniform, h->policy, h->sm_count, capacity, s);
     SolveIO io;
     io.wp = wp;
     io.v_avg = v_avg;
@@ -809,7 +766,6 @@ int msnap_create(int device, msnap_handle *out) {
         return MSNAP_ERR_CUDA;
     }
     if (const char *e = std::getenv("MSNAP_SCAN_COEF_SMEM")) h->scan_coef_smem = std::atoi(e) != 0;
-    if (const char *e = std::getenv("MSNAP_SAMPLER")) h->sampler_mode = std::string(e) == "scan" ? 1 : 0;
     if (const char *e = std::getenv("MSNAP_HOST_CHUNKS")) h->host_chunks = std::atoi(e);
     if (const char *e = std::getenv("MSNAP_ZERO_COPY")) h->zero_copy = std::atoi(e) != 0;
     if (const char *e = std::getenv("MSNAP_DISCARD_STATE")) h->discard_state = std::atoi(e) != 0;
@@ -870,13 +826,6 @@ int msnap_synchronize(msnap_handle h) {
 int msnap_set_reweight_policy(msnap_handle h, int policy) {
     if (!h || policy < 0 || policy > 2) return MSNAP_ERR_INVALID_ARG;
     h->policy = policy;
-    return MSNAP_OK;
-}
-
-int msnap_set_sampler(msnap_handle h, int mode) {
-    if (!h || mode < 0 || mode > 1) return MSNAP_ERR_INVALID_ARG;
-    h->sampler_mode = mode;
-    for (msnap_context *k : h->kids) k->sampler_mode = mode;
     return MSNAP_OK;
 }
 
@@ -1258,12 +1207,10 @@ int msnap_generate_batch_host(msnap_handle h, const msnap_config *cfg, double sa
             rc = msnap_create(h->device, &k);
             if (rc) return rc;
             k->policy = h->policy;
-            k->sampler_mode = h->sampler_mode;
             h->kids.push_back(k);
         }
         for (msnap_context *k : h->kids) {
             k->policy = h->policy;
-            k->sampler_mode = h->sampler_mode;
             k->scan_coef_smem = h->scan_coef_smem;
             k->zero_copy = h->zero_copy;
             k->frame = h->frame;

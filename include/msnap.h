@@ -89,10 +89,6 @@ int msnap_synchronize(msnap_handle h);
  * 2 = speculative (all 11 velocity weights solved concurrently, the first admissible one selected). Results are
  * identical; this is a throughput/latency knob only. */
 int msnap_set_reweight_policy(msnap_handle h, int policy);
-/* Execution form of the sampler for uniform batches (ms.cpp:97-161): 0 (default) = every candidate is evaluated once, accepted
- * points are staged in an L2-resident slot and copied to their final rows after the batch-wide scan; 1 = count first
- * (acceptance masks), then evaluate the accepted candidates again at their final position.  Identical rows; speed only. */
-int msnap_set_sampler(msnap_handle h, int mode);
 /* Host-pointer entry points cut big batches into chunks whose kernels overlap the previous chunk's device-to-host
  * copies (two internal streams).  n_chunks = 0: automatic (one chunk per 8 192 trajectories, at most 8); 1: no
  * pipelining.  Results do not depend on the chunking. */

@@ -229,26 +229,3 @@ def test_misaligned_device_coefficient_buffer_is_rejected(tool):
     tool.generate_batch_dev(cfg, d_wp, off, samples, ns=ns, coeff=raw[:-1])
     tool.synchronize()
     assert int(off[-1]) > 8
-
-
-@pytest.mark.parametrize("order,ns,sd", [(4, 16, 1.0), (4, 16, 0.0), (2, 6, 0.3), (3, 40, 2.5), (5, 3, 1.0), (4, 200, 1.0)])
-def test_staged_sampler_equals_count_then_evaluate_sampler(tool, order, ns, sd):
-    """The two execution forms of the uniform-batch sampler (msnap_set_sampler) must produce the same rows, offsets, flags and
-    statistics bit for bit -- also when the capacity cuts through a tile."""
-    B = 700 if ns <= 40 else 40
-    wp, _ = workloads.cfg2(B=B, ns=ns, seed=31 + ns)
-    cfg = workloads.synthetic_config(order, "shipped", sample_distance=sd)
-    tool.set_sampler(1)
-    try:
-        old = tool.generate_batch(cfg, wp, ns=ns)
-    finally:
-        tool.set_sampler(0)
-    new = tool.generate_batch(cfg, wp, ns=ns)
-    for k in ("sample_offset", "samples", "flags", "stats", "coeff"):
-        assert np.array_equal(getattr(old, k), getattr(new, k)), k
-    cap = int(new.sample_offset[B // 3]) + 7
-    with pytest.raises(MsnapError) as e:
-        tool.generate_batch(cfg, wp, ns=ns, capacity=cap)
-    part = e.value.partial
-    assert np.array_equal(part.sample_offset, new.sample_offset) and np.array_equal(part.samples, new.samples[:cap])
-    assert (part.flags[B // 3 + 1:] & 2).all() and not (part.flags[: B // 3] & 2).any()

@@ -520,12 +520,8 @@ int run_sample(msnap_context *h, const BatchIdx &bi, const double *coeff, const 
     MS_LAUNCH(h, k_scan_reduce, nblk, SCAN_BLOCK, s.traj_count, bi.B, s.partial);
     MS_LAUNCH(h, k_scan_partials, 1, SCAN_BLOCK, s.partial, nblk, sample_offset + bi.B);
     MS_LAUNCH(h, k_scan_apply, nblk, SCAN_BLOCK, s.traj_count, bi.B, s.partial, sample_offset);
-    if (h->policy != 1)  // warp per segment: mask-directed parallel evaluation, coalesced rows
-        MS_LAUNCH(h, (k_write_warp<O>), grid_for(bi.n_seg * 32, blk), blk, bi, coeff, T, sd, h->d_ttab, s.seg_count, s.seg_mask,
-                  s.seg_start, sample_offset, s.append_end, capacity, samples, flags);
-    else  // thread per segment: the sequential definition
-        MS_LAUNCH(h, (k_write<O>), gs, blk, bi, coeff, T, sd, h->d_ttab, s.seg_count, s.seg_mask, s.seg_start,
-                  sample_offset, s.append_end, capacity, samples, flags);
+    MS_LAUNCH(h, (k_write<O>), gs, blk, bi, coeff, T, sd, h->d_ttab, s.seg_count, s.seg_mask, s.seg_start,
+              sample_offset, s.append_end, capacity, samples, flags);
     if (stats) MS_LAUNCH(h, k_stats, grid_for(bi.B * 32, 256), 256, bi.B, sample_offset, samples, capacity, stats);
     return MSNAP_OK;
 }

@@ -849,95 +849,6 @@ __global__ void __launch_bounds__(128) k_write(BatchIdx bi, const double *__rest
     if (dropped && flags) atomicOr(flags + b, 2u);
 }
 
-// k_write_warp: warp per segment (CSR batches, the default).  The acceptance mask says which candidates to evaluate, so the
-// 32 lanes take 32 consecutive candidates at once: a lane whose bit is set evaluates its candidate and its row is the
-// number of set bits before it (popcount) -- no search, no sequential walk -- and the rows of a step leave through a
-// per-warp staging buffer as contiguous, coalesced stores.  Same candidate times and evaluation code as k_write (thread per
-// segment, which stays the sequential definition under policy 1): identical rows.  Segments without a usable mask (more
-// than 128 candidates) are walked by the warp (warp_sample_long).
-template <int O>
-__global__ void __launch_bounds__(128) k_write_warp(BatchIdx bi, const double *__restrict__ coeff, const double *__restrict__ T,
-                                                    double sample_distance, const double *__restrict__ t_table,
-                                                    const int *__restrict__ seg_count,
-                                                    const unsigned long long *__restrict__ seg_mask,
-                                                    const long long *__restrict__ seg_start,
-                                                    const long long *__restrict__ sample_offset,
-                                                    const int *__restrict__ append_end, long long capacity,
-                                                    double *__restrict__ samples, unsigned *__restrict__ flags) {
-    __shared__ double wstage[4][96];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const long long g = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-    if (g >= bi.n_seg) return;
-    long long b; int k, ns;
-    bi.locate(g, b, k, ns);
-    double c[3][2 * O], cur[3];
-    load_coeff<O>(coeff, g, c);
-    const double Tk = T[g];
-    const long long row0 = sample_offset[b];
-    const long long row_base = row0 + seg_start[g];
-    bool dropped = false;
-    auto put = [&](long long r, const double (&v)[3]) {
-        if (r < capacity) {
-            samples[3 * r] = v[0]; samples[3 * r + 1] = v[1]; samples[3 * r + 2] = v[2];
-        } else {
-            dropped = true;
-        }
-    };
-    if (k == 0 && lane == 0) {  // very first point of the trajectory (ms.cpp:132-137)
-        eval_xyz<O>(c, 0.0, cur);
-        put(row0, cur);
-    }
-    if (k == ns - 1 && lane == 1 && append_end[b]) {  // end point appended after the last segment (ms.cpp:157-160)
-        eval_xyz<O>(c, Tk, cur);
-        put(sample_offset[b + 1] - 1, cur);
-    }
-    const int sc = seg_count[g];
-    if (sc >= 0) {
-        const double dt = sample_dt(Tk);
-        const bool tabulated = dt == 0.1;
-        const unsigned long long m0 = seg_mask[2 * g], m1 = seg_mask[2 * g + 1];
-        double *stage = wstage[wid];
-        int n_prev = 0;
-#pragma unroll 1
-        for (int w = 0; w < 4; ++w) {
-            const unsigned word = (unsigned)((w < 2 ? m0 : m1) >> (32 * (w & 1)));
-            if (!word) continue;  // (uniform)
-            const bool set = (word >> lane) & 1u;
-            const int rank = __popc(word & ((1u << lane) - 1u));
-            if (set) {
-                const int bit = 32 * w + lane;
-                double t;
-                if (tabulated) {
-                    t = __ldg(t_table + bit + 1);
-                } else {
-                    t = dt;
-                    for (int i = 0; i < bit; ++i) t += dt;
-                }
-                eval_xyz<O>(c, fmin(t, Tk), cur);
-                stage[3 * rank] = cur[0]; stage[3 * rank + 1] = cur[1]; stage[3 * rank + 2] = cur[2];
-            }
-            __syncwarp();
-            const int n = __popc(word);
-            const long long r_first = row_base + n_prev;
-            long long room = capacity - r_first;
-            const int n_fit = room >= n ? n : (room > 0 ? (int)room : 0);
-            if (n_fit < n) dropped = true;
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const int e = lane + 32 * j;
-                if (e < 3 * n_fit) samples[3 * r_first + e] = stage[e];
-            }
-            __syncwarp();
-            n_prev += n;
-        }
-    } else {
-        const AcceptTest accept(sample_distance);
-        double lp[3];
-        warp_sample_long<O, true>(c, Tk, accept, t_table, row_base, capacity, samples, dropped, lp);
-    }
-    if (__any_sync(0xffffffffu, dropped) && lane == 0 && flags) atomicOr(flags + b, 2u);
-}
-
 // Exclusive scan of int64 counts into offsets[n+1], three small kernels (n up to millions; traffic negligible).
 constexpr int SCAN_BLOCK = 1024;
 __global__ void k_scan_reduce(const long long *__restrict__ in, long long n, long long *__restrict__ partial) {

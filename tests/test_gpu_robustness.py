@@ -147,34 +147,3 @@ def test_long_segments_warp_cooperative_sampler_equals_sequential_loop(tool, sd,
     part = e.value.partial
     assert np.array_equal(part.sample_offset, fast.sample_offset) and np.array_equal(part.samples, fast.samples[:cap])
     assert (part.flags[B // 2 + 1:] & 2).all() and not (part.flags[: B // 2] & 2).any()
-
-
-@pytest.mark.parametrize("sd", [0.0, 1.0, 7.5])
-def test_csr_warp_writer_equals_thread_per_segment_writer(tool, sd):
-    """Ragged batches: the default write pass (k_write_warp: a warp per segment, mask-directed) against the sequential
-    definition (policy 1: k_write, a lane per segment), bit for bit -- short, ordinary and > 128-candidate segments, and a
-    capacity that cuts through a trajectory."""
-    wp, so = workloads.cfg5(B=1500, seed=91, ns_max=60)
-    wp = wp.copy()
-    B = so.shape[0] - 1
-    # stretch every 7th trajectory by 40: segments of ~130 s (1 300 candidates)
-    first = so[:-1] + np.arange(B)
-    for b in range(0, B, 7):
-        sl = slice(int(first[b]), int(first[b] + (so[b + 1] - so[b]) + 1))
-        wp[sl] = wp[sl][0] + (wp[sl] - wp[sl][0]) * 40.0
-    cfg = workloads.synthetic_config(4, "shipped", sample_distance=sd)
-    fast = tool.generate_batch(cfg, wp, seg_offset=so)
-    tool.set_reweight_policy(1)
-    try:
-        slow = tool.generate_batch(cfg, wp, seg_offset=so)
-    finally:
-        tool.set_reweight_policy(0)
-    assert (fast.times > 12.9).any() and (fast.times < 1.0).any() and not fast.flags.any()
-    for k in ("sample_offset", "samples", "stats", "coeff", "iters"):
-        assert np.array_equal(getattr(fast, k), getattr(slow, k)), k
-    cap = int(fast.sample_offset[B // 2]) + 11
-    with pytest.raises(MsnapError) as e:
-        tool.generate_batch(cfg, wp, seg_offset=so, capacity=cap)
-    part = e.value.partial
-    assert np.array_equal(part.sample_offset, fast.sample_offset) and np.array_equal(part.samples, fast.samples[:cap])
-    assert (part.flags[B // 2 + 1:] & 2).all() and not (part.flags[: B // 2] & 2).any()

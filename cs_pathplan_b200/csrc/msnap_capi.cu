@@ -40,6 +40,7 @@ struct Arena {  // grow-only device buffer with bump allocation, reset per call
 // Launch plan of the fused kernel for a uniform batch, or tpc == 0 if the batch does not qualify.
 struct FusedPlan {
     int tpc = 0, nit = 1, lane_stride = 32, traj_stride = 0, grid = 0;
+    int variant = 0;  // 0: FUSED_THREADS x 2 CTAs per SM, 1: FUSED_THREADS_3 x 3 CTAs per SM (many-wave batches)
     long long n_tiles = 0;
     size_t smem = 0, state_bytes = 0;
     // cache key
@@ -234,6 +235,22 @@ FusedPlan plan_fused(msnap_context *h, const BatchIdx &bi, const SolveParams &sp
             f.tpc = tpc;
         }
     }
+    // Many waves deep: what counts is how many chains an SM keeps in flight.  The 192-thread build of the kernel fits three
+    // CTAs per SM when the tile's shared memory allows it (short trajectories): half again as many warps.
+    static const bool allow3 = !(std::getenv("MSNAP_FUSED_3CTA") && std::atoi(std::getenv("MSNAP_FUSED_3CTA")) == 0);  // (A/B knob)
+    // (measured at cfg3, 2^20 x 8: 6.05 -> 5.50 ms with the reweighting lanes; a single solve per trajectory is 7 % slower with it)
+    if (allow3 && nit > 1 && f.tpc > 0 && best_waves >= 4 && 32 + f.tpc * (nit - 1) <= FUSED_THREADS_3) {
+        const size_t sm = smem_for(f.tpc);
+        int occ3 = 0;
+        cudaFuncSetAttribute((k_fused_solve<O, FUSED_THREADS_3, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hard);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, (k_fused_solve<O, FUSED_THREADS_3, 3>), FUSED_THREADS_3, sm) ==
+                cudaSuccess && occ3 > best_occ) {
+            f.variant = 1;
+            best_occ = occ3;
+        } else {
+            cudaGetLastError();
+        }
+    }
     if (f.tpc == 0) return f;  // a single trajectory does not fit: generic path
     f.traj_stride = L.size;
     f.smem = smem_for(f.tpc);
@@ -330,7 +347,10 @@ int run_solve(msnap_context *h, const BatchIdx &bi, const SolveParams &sp, const
         fp.state_ws = w.state;
         fp.phase_clocks = h->phase_clocks;
         prof_before(h, "k_fused_solve");
-        k_fused_solve<O><<<f.grid, FUSED_THREADS, f.smem, h->stream>>>(fp);
+        if (f.variant == 1)
+            k_fused_solve<O, FUSED_THREADS_3, 3><<<f.grid, FUSED_THREADS_3, f.smem, h->stream>>>(fp);
+        else
+            k_fused_solve<O><<<f.grid, FUSED_THREADS, f.smem, h->stream>>>(fp);
         prof_after(h);
         ++h->launches;
         cudaError_t e = cudaPeekAtLastError();

@@ -33,7 +33,11 @@
 
 namespace msnap {
 
-constexpr int FUSED_THREADS = 224;     // 2 CTAs per SM at <= 144 registers per thread; 14 x 16 (trajectory, segment) items = one round
+constexpr int FUSED_THREADS = 224;     // default variant: 2 CTAs per SM (<= 144 registers per thread); 14 x 16 (trajectory, segment)
+                                       // items = one round of the segment-parallel phases
+constexpr int FUSED_THREADS_3 = 192;   // big-batch variant: 3 CTAs per SM (<= 112 registers; the row sweeps stay spill-free, the
+                                       // segment-parallel phases spill a little): half again as many warps per SM when the
+                                       // batch is many waves deep and the shared-memory tile is small enough
 constexpr int FUSED_SLOT_LANES = 160;  // lanes per state row of the global scratch slot (>= 16 trajectories x 10 speculative iterations)
 constexpr int FUSED_SMEM_LANES = 14;   // lanes per state row in shared memory (= max trajectories per tile)
 
@@ -444,11 +448,12 @@ __device__ __noinline__ void fused_phase_spec(const FusedParams &p, long long ti
             T.md[t * nit + q] = mdv;
             T.okf[t * nit + q] = ok ? 1 : 0;
         }
+        if (p.phase_clocks && tile == blockIdx.x && tid == 0) p.phase_clocks[blockIdx.x * 16 + 9] = clock64();  // pair chain done
     }
 }
 
-template <int O>
-__global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_constant__ FusedParams p) {
+template <int O, int NT = FUSED_THREADS, int MINB = 2>
+__global__ void __launch_bounds__(NT, MINB) k_fused_solve(const __grid_constant__ FusedParams p) {
     using D = Dim<O>;
     constexpr int SL = FUSED_SMEM_LANES, GL = FUSED_SLOT_LANES;
     extern __shared__ double smem[];
@@ -478,12 +483,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_c
         {
             const double *src = p.wp + 3 * (g0 + b0);
             const int per = 3 * (ns + 1), n = nt * per;
-            for (int i = tid; i < n; i += FUSED_THREADS) {
+            for (int i = tid; i < n; i += NT) {
                 const int t = i / per;
                 smem[t * tstride + L.oP + (i - t * per)] = src[i];
             }
             // fixed boundary derivatives (velocity, acceleration; higher ones zero -- ms.cpp:526-555), [r-1][axis]
-            for (int i = tid; i < nt * 2 * D::NR; i += FUSED_THREADS) {
+            for (int i = tid; i < nt * 2 * D::NR; i += NT) {
                 const int t = i / (2 * D::NR), r = i - t * 2 * D::NR;
                 const int end = r / D::NR, d = (r % D::NR) / 3 + 1, a = r % 3;  // derivative order d
                 double v = 0.0;
@@ -495,7 +500,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_c
         __syncthreads();
         MSNAP_STAMP();
         // ---- times (plain IEEE mul/add: bit-identical to the reference's allocation, ms.cpp:63-72) and powers
-        for (int i = tid; i < nt * ns; i += FUSED_THREADS) {
+        for (int i = tid; i < nt * ns; i += NT) {
             const int t = i / ns, k = i - t * ns;
             double *blk = smem + t * tstride;
             double Tk;
@@ -523,14 +528,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_c
 
         if (use_pw) {
             // ---- pass 1: snap cost only -> worst-deviation sample per segment
-            for (int i = tid; i < nt * nr; i += FUSED_THREADS)
+            for (int i = tid; i < nt * nr; i += NT)
                 fused_row_item<O>(p, smem + (i / nr) * tstride, ns, i % nr + 1, false);
             __syncthreads();
             MSNAP_STAMP();
             fused_phase_pass1<O>(p, nt);
             __syncthreads();
             MSNAP_STAMP();
-            for (int i = tid; i < nt * ns; i += FUSED_THREADS) {
+            for (int i = tid; i < nt * ns; i += NT) {
                 const int t = i / ns, k = i - t * ns;
                 const int s = fused_search_item<O>(smem + t * tstride, state1 + 2 * t, ns, k);
                 reinterpret_cast<int *>(smem + t * tstride + L.oS)[k] = s;
@@ -538,10 +543,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_c
             }
             __syncthreads();
             MSNAP_STAMP();
-            for (int i = tid; i < nt * ns; i += FUSED_THREADS) fused_probe_item<O>(p, smem + (i / ns) * tstride, ns, i % ns);
+            for (int i = tid; i < nt * ns; i += NT) fused_probe_item<O>(p, smem + (i / ns) * tstride, ns, i % ns);
         }
         // ---- rows of the final system
-        for (int i = tid; i < nt * nr; i += FUSED_THREADS)
+        for (int i = tid; i < nt * nr; i += NT)
             fused_row_item<O>(p, smem + (i / nr) * tstride, ns, i % nr + 1, use_pw);
         __syncthreads();
         MSNAP_STAMP();
@@ -599,11 +604,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_solve(const __grid_c
         if (nit > 1 && p.discard_state) {
             char *sb = reinterpret_cast<char *>(slot);
             const int n_lines = (int)(((size_t)nr * D::NSTATE * GL * sizeof(double)) / 128);
-            for (int i = tid; i < n_lines; i += FUSED_THREADS)
+            for (int i = tid; i < n_lines; i += NT)
                 asm volatile("discard.global.L2 [%0], 128;" ::"l"(sb + (size_t)i * 128) : "memory");
         }
         // ---- coefficients: items (t, k, axis), 64-byte rows straight to HBM
-        for (int i = tid; i < nt * ns * 3; i += FUSED_THREADS) {
+        for (int i = tid; i < nt * ns * 3; i += NT) {
             const int t = i / (ns * 3), r = i - t * ns * 3;
             const int k = r / 3, a = r - 3 * k;
             const long long row = ((g0 + (long long)t * ns + k) * 3 + a) * D::M;

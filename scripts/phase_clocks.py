@@ -28,6 +28,11 @@ for weights in ("shipped", "plain"):
         print("   per-CTA tile time: min %.1f  p50 %.1f  p90 %.1f  max %.1f us;  phase maxima: " % (tot.min(), np.median(tot), np.quantile(tot, 0.9), tot.max())
               + "  ".join(f"{n} {m:.1f}" for n, m in zip(names, d.max(0))))
         if weights == "shipped":
+            pe = f[:, 9]
+            okp = pe > 0
+            if okp.any():
+                print("   last-iteration lane pair (warp 0) ends %.1f us after the rows2 barrier (max %.1f)" %
+                      (((pe - f[:, 6])[okp] / GHZ).mean(), ((pe - f[:, 6])[okp] / GHZ).max()))
             for w in range(3):
                 fe, be = f[:, 10 + 2 * w], f[:, 11 + 2 * w]
                 ok = fe > 0

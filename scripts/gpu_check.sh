@@ -8,11 +8,11 @@ OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv -lms 500 > $OUT/${TAG}_clocks.csv 2>&1 &
 SMI=$!
-timeout 400 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/${TAG}_pytest.log
+timeout 1200 python -m pytest tests -m gpu -x -q -s > $OUT/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/${TAG}_pytest.log
 tail -5 $OUT/${TAG}_pytest.log
 timeout 400 python __graft_entry__.py smoke > $OUT/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $OUT/${TAG}_smoke.log
-timeout 400 python bench.py --steps 1000 --warmup 20 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"
-timeout 400 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err; echo "bench ref rc=$?"
+timeout 900 python bench.py --steps 1000 --warmup 20 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"
+timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err; echo "bench ref rc=$?"
 timeout 400 python scripts/geo_bench.py > $OUT/${TAG}_geo_bench.jsonl 2> $OUT/${TAG}_geo_bench.err; echo "geo bench rc=$?"
 timeout 400 python scripts/alt_bench.py > $OUT/${TAG}_alt_bench.json 2> $OUT/${TAG}_alt_bench.err; echo "alt bench rc=$?"
 kill $SMI

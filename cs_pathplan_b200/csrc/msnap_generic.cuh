@@ -546,6 +546,31 @@ __device__ __forceinline__ void count_candidates(const double (&c)[3][2 * O], do
     int n = 0, idx = 0;
     unsigned long long w0 = 0ull, w1 = 0ull;
     double t = dt;
+    // Dense output (sample_distance <= 0): the test `distance >= 0` holds for every candidate whose position is a number,
+    // so the walk only has to count the candidate times.  Taken when no position on [0, T] can overflow or be NaN
+    // (|c_i| < 1e100 and T <= 1e6: |p| < 8e142, its square is finite); anything else goes through the tests below.
+    if (accept.sd <= 0.0) {
+        bool tame = true;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int i = 0; i < 2 * O; ++i) tame = tame && fabs(c[a][i]) < 1e100;
+        if (tame) {
+            double tl = 0.0;
+            while (t <= tmax) {
+                tl = t;
+                ++idx;
+                t += dt;
+            }
+            if (idx > 0) eval_xyz<O>(c, fmin(tl, Tk), prev);
+            n_out = idx;
+            usable = idx <= SAMPLE_MASK_BITS;
+            m0 = idx >= 64 ? ~0ull : (1ull << idx) - 1ull;
+            m1 = idx >= 128 ? ~0ull : (idx > 64 ? (1ull << (idx - 64)) - 1ull : 0ull);
+            last[0] = prev[0]; last[1] = prev[1]; last[2] = prev[2];
+            return;
+        }
+    }
     while (t <= tmax) {
         const double t2 = t + dt;
         eval_xyz<O>(c, fmin(t, Tk), ca);
@@ -1158,7 +1183,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_sample_scan(
         const int total = (int)traj_base[nt];
         // ---- EXPAND rows [c0, c0 + SCAN_DESC_CAP) of the tile into descriptors (first chunk before the look-back)
         auto expand = [&](int c0) {
-            for (int i = tid; i < nseg; i += SCAN_THREADS) {
+            // segments in ranking order: the lanes of a warp expand masks of similar population
+            for (int rk = tid; rk < nseg; rk += SCAN_THREADS) {
+                const int i = perm[rk];
                 const int t = i / ns, k = i - t * ns;
                 const int tb = (int)traj_base[t] - c0;
                 if (k == 0 && tb >= 0 && tb < SCAN_DESC_CAP) desc[tb] = ((unsigned)i << 8) | DESC_FIRST;
@@ -1172,14 +1199,28 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_sample_scan(
                 if (row >= SCAN_DESC_CAP || row + n <= 0) continue;
                 if (sc >= 0) {
                     const unsigned head = ((unsigned)i << 8) | (segT[i] < 1.0 ? DESC_ACCUM : 0u);
+                    const uint4 mw = *reinterpret_cast<const uint4 *>(mask + 2 * i);  // 128 acceptance bits, 32 at a time
+                    const unsigned words[4] = {mw.x, mw.y, mw.z, mw.w};
+                    if (row >= 0 && row + n <= SCAN_DESC_CAP) {  // the whole segment lies inside this chunk
+                        unsigned *dst = desc + row;
 #pragma unroll
-                    for (int w = 0; w < 2; ++w) {
-                        unsigned long long m = mask[2 * i + w];
-                        while (m) {
-                            const int bit = __ffsll((long long)m) - 1 + 64 * w;
-                            m &= m - 1;
-                            if (row >= 0 && row < SCAN_DESC_CAP) desc[row] = head | (unsigned)bit;
-                            ++row;
+                        for (int w = 0; w < 4; ++w) {
+                            unsigned m = words[w];
+                            while (m) {
+                                *dst++ = head | (unsigned)(__ffs((int)m) - 1 + 32 * w);
+                                m &= m - 1;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) {
+                            unsigned m = words[w];
+                            while (m) {
+                                const int bit = __ffs((int)m) - 1 + 32 * w;
+                                m &= m - 1;
+                                if (row >= 0 && row < SCAN_DESC_CAP) desc[row] = head | (unsigned)bit;
+                                ++row;
+                            }
                         }
                     }
                 } else {

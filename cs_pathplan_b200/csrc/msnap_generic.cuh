@@ -834,8 +834,9 @@ __global__ void k_traj_count(BatchIdx bi, const double *__restrict__ coeff, cons
 
 // k_write: thread per segment.  Rows sample_offset[b] + seg_start[g] + i, plus the trajectory's first point (k == 0)
 // and the appended end point (k == ns-1); rows >= capacity are dropped and flagged.
+// (4 CTAs per SM: compiled for 5 or 6 the kernel spills and runs 1.44 / 2.03 ms instead of 1.31 ms at cfg5)
 template <int O>
-__global__ void __launch_bounds__(128) k_write(BatchIdx bi, const double *__restrict__ coeff,
+__global__ void __launch_bounds__(128, 4) k_write(BatchIdx bi, const double *__restrict__ coeff,
                                                const double *__restrict__ T, double sample_distance,
                                                const double *__restrict__ t_table, const int *__restrict__ seg_count,
                                                const unsigned long long *__restrict__ seg_mask,

@@ -450,6 +450,11 @@ __device__ __noinline__ void fused_phase_spec(const FusedParams &p, long long ti
         }
         if (p.phase_clocks && tile == blockIdx.x && tid == 0) p.phase_clocks[blockIdx.x * 16 + 9] = clock64();  // pair chain done
     }
+#ifdef MSNAP_WARP_END_STAMPS  // dev instrumentation: when does every warp leave the phase (replaces the lane stamps)
+    __syncwarp();
+    if (p.phase_clocks && tile == blockIdx.x && (tid & 31) == 0 && (tid >> 5) >= 1 && (tid >> 5) <= 6)
+        p.phase_clocks[blockIdx.x * 16 + 9 + (tid >> 5)] = clock64();
+#endif
 }
 
 template <int O, int NT = FUSED_THREADS, int MINB = 2>

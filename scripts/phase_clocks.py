@@ -8,7 +8,7 @@ names_plain = ["load", "times", "rows", "solve+select", "outputs+coeff"]
 scan_names = ["sort+count", "rows", "scan+expand+lookback", "write"]
 tool = TrajectoryGeneratorTool(0)
 tool.set_host_chunks(1)  # the stamps are taken on this handle's own launches
-cases = [(4096, 16), (1 << 15, 8)] if len(sys.argv) < 2 else [(int(sys.argv[1]), int(sys.argv[2]))]
+cases = [(4096, 16), (1 << 15, 8)] if len(sys.argv) < 3 else [(int(sys.argv[1]), int(sys.argv[2]))]
 for weights in ("shipped", "plain"):
     for B, ns in cases:
         cfg = workloads.synthetic_config(4, weights)
@@ -33,7 +33,14 @@ for weights in ("shipped", "plain"):
             if okp.any():
                 print("   last-iteration lane pair (warp 0) ends %.1f us after the rows2 barrier (max %.1f)" %
                       (((pe - f[:, 6])[okp] / GHZ).mean(), ((pe - f[:, 6])[okp] / GHZ).max()))
-            for w in range(3):
+            if "--warp-ends" in sys.argv:
+                for w in range(1, 7):
+                    we = f[:, 9 + w]
+                    ok = we > 0
+                    if ok.any():
+                        print("   warp %d leaves the phase %.1f us after the rows2 barrier (p90 %.1f, max %.1f)" %
+                              (w, ((we - f[:, 6])[ok] / GHZ).mean(), np.quantile((we - f[:, 6])[ok] / GHZ, 0.9), ((we - f[:, 6])[ok] / GHZ).max()))
+            for w in range(0 if "--warp-ends" in sys.argv else 3):
                 fe, be = f[:, 10 + 2 * w], f[:, 11 + 2 * w]
                 ok = fe > 0
                 if ok.any():

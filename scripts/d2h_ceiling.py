@@ -4,7 +4,7 @@ back, all at once; reports GB/s per rank and in total.  The e2e figure of bench.
 
     python scripts/d2h_ceiling.py                                            # 1 GPU
     python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 scripts/d2h_ceiling.py
-Options: --numa 1 pins the rank's host threads (and so its pinned pages, first touch) to the GPU's NUMA node first."""
+Options: --pin 1 pins the rank's host threads (and so its pinned pages, first touch) to the GPU's NUMA node first."""
 import argparse, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -14,15 +14,15 @@ from cs_pathplan_b200.hostpin import pin_to_gpu_numa
 ap = argparse.ArgumentParser()
 ap.add_argument("--mb", type=float, default=33.0)
 ap.add_argument("--iters", type=int, default=200)
-ap.add_argument("--numa", type=int, default=0)
+ap.add_argument("--pin", type=int, default=0)
 ap.add_argument("--out", default="")
 a = ap.parse_args()
 rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
 torch.cuda.set_device(local)
-pinned_to = pin_to_gpu_numa(local) if a.numa else None
+pinned_to = pin_to_gpu_numa(local) if a.pin else None
 dev = torch.device("cuda", local)
 if world > 1:
-    os.environ.setdefault("NCCL_DEBUG", "WARN")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", device_id=dev)
 n = int(a.mb * 1e6) // 8
 d = torch.empty(n, dtype=torch.float64, device=dev).normal_()
@@ -54,7 +54,7 @@ for name, fn in (("d2h", lambda: h.copy_(d, non_blocking=True)),
         per = [gbs]
     out[name] = {"per_rank_GBps": per, "total_GBps": sum(per), "min_GBps": min(per)}
 if rank == 0:
-    line = json.dumps({"n_gpus": world, "mb_per_copy": a.mb, "numa_pinned": bool(a.numa), "cpus": pinned_to and len(pinned_to), **out})
+    line = json.dumps({"n_gpus": world, "mb_per_copy": a.mb, "numa_pinned": bool(a.pin), "cpus": pinned_to and len(pinned_to), **out})
     print(line)
     if a.out:
         with open(a.out, "a") as f:

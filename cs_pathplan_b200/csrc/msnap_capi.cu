@@ -1083,6 +1083,7 @@ struct HostChunk {
     long long *d_so = nullptr;
     double *d_s = nullptr;
     bool single = false;               // the only chunk of the call
+    long long capacity = 0;            // rows of the chunk's device mirror: min(caller's capacity, the chunk's own row bound)
     double *samples_direct = nullptr;  // zero-copy: the kernels wrote the rows straight into the caller's pinned buffer
 };
 
@@ -1097,6 +1098,28 @@ static void *device_view_of_pinned(const void *p) {
     return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
 }
 
+// Upper bound of the rows a chunk can produce, from its waypoints on the host: k_bound's formula (candidates from the
+// segment duration alone, + first and end point per trajectory) with one spare candidate per segment, so that a last-bit
+// difference between the host's and the device's duration cannot make it too small.
+static long long host_rows_bound(const msnap_config *cfg, double va, const double *wp, long long p0, long long B,
+                                 int ns_uniform, const std::vector<long long> &off_local) {
+    unsigned long long n = 0;
+    for (long long b = 0; b < B; ++b) {
+        const long long g0 = ns_uniform > 0 ? b * ns_uniform : off_local[(size_t)b];
+        const long long g1 = ns_uniform > 0 ? g0 + ns_uniform : off_local[(size_t)b + 1];
+        const double *p = wp + 3 * (p0 + g0 + b);
+        n += 2;
+        for (long long g = g0; g < g1; ++g, p += 3) {
+            const double dx = p[3] - p[0], dy = p[4] - p[1], dz = p[5] - p[2];
+            double t = va > 1e-6 ? std::sqrt(dx * dx + dy * dy + dz * dz) / va : cfg->min_time_s;
+            if (t < cfg->min_time_s) t = cfg->min_time_s;
+            if (!(t > 0.0 && t <= SAMPLE_T_MAX)) continue;  // a failed segment has no candidates (sample_time_ok)
+            n += t >= 1.0 ? (unsigned long long)(t / 0.1) + 3ull : 13ull;
+        }
+    }
+    return (long long)n;
+}
+
 static int host_chunk_enqueue(msnap_context *k, const msnap_config *cfg, double sd, double va, HostChunk &j,
                               int ns_uniform, const double *waypoints, double *times_out, double *coeff_out,
                               double *max_dev_out, int *iters_out, double *vw_final_out, int *best_s_out,
@@ -1106,7 +1129,7 @@ static int host_chunk_enqueue(msnap_context *k, const msnap_config *cfg, double 
     size_t bytes = padded((B + 1) * sizeof(long long)) + padded(n_pts * 3 * sizeof(double)) +
                    padded(n_seg * sizeof(double)) + padded((size_t)n_seg * m3 * sizeof(double)) +
                    2 * padded(B * sizeof(double)) + padded(B * sizeof(int)) + padded((B + 1) * sizeof(long long)) +
-                   padded((size_t)sample_capacity * 3 * sizeof(double)) + padded((size_t)B * 2 * sizeof(double)) +
+                   padded((size_t)j.capacity * 3 * sizeof(double)) + padded((size_t)B * 2 * sizeof(double)) +
                    padded(B * sizeof(unsigned)) + padded(n_seg * sizeof(int));
     MS_CUDA(k, cudaStreamSynchronize(k->aux));  // copies of this context's previous chunk still read its device buffers
     int rc = arena_reserve(k, k->io, bytes);
@@ -1129,7 +1152,7 @@ static int host_chunk_enqueue(msnap_context *k, const msnap_config *cfg, double 
     double *d_vw = arena_take<double>(k->io, B);
     int *d_it = arena_take<int>(k->io, B);
     j.d_so = arena_take<long long>(k->io, B + 1);
-    j.d_s = arena_take<double>(k->io, (size_t)sample_capacity * 3);
+    j.d_s = arena_take<double>(k->io, (size_t)j.capacity * 3);
     double *d_st = arena_take<double>(k->io, (size_t)B * 2);
     unsigned *d_fl = arena_take<unsigned>(k->io, B);
     int *d_bs = arena_take<int>(k->io, n_seg);
@@ -1152,7 +1175,7 @@ static int host_chunk_enqueue(msnap_context *k, const msnap_config *cfg, double 
     MS_DISPATCH_ORDER(cfg->order,
                       rc = generate_dev<O>(k, cfg, sd, va, B, ns_uniform, ns_uniform > 0 ? nullptr : d_off, n_seg, d_wp,
                                            times_out ? d_t : nullptr, coeff_out ? d_c : nullptr, d_md, d_it, d_vw,
-                                           best_s_out ? d_bs : nullptr, sample_capacity, j.d_so,
+                                           best_s_out ? d_bs : nullptr, j.capacity, j.d_so,
                                            j.samples_direct ? j.samples_direct : j.d_s, stats_out ? d_st : nullptr, d_fl,
                                            coeff_zc ? coeff_zc + j.g0 * m3 : nullptr, &coeff_direct));
     k->mark_solved = false;
@@ -1182,7 +1205,8 @@ static int host_chunk_finish(msnap_context *k, HostChunk &j, long long &rows_bas
     const long long total = k->h_off[j.B];
     long long room = sample_capacity - rows_base;
     if (room < 0) room = 0;
-    const long long rows = total < room ? total : room;
+    long long rows = total < room ? total : room;
+    if (rows > j.capacity) rows = j.capacity;  // (the mirror never holds more; the kernels flagged what they dropped)
     if (rows > 0 && !j.samples_direct)
         MS_CUDA(k, cudaMemcpyAsync(samples_out + 3 * rows_base, j.d_s, (size_t)rows * 3 * sizeof(double),
                                    cudaMemcpyDeviceToHost, k->stream));
@@ -1232,6 +1256,7 @@ int msnap_generate_batch_host(msnap_handle h, const msnap_config *cfg, double sa
         for (msnap_context *k : h->kids) {
             k->policy = h->policy;
             k->scan_coef_smem = h->scan_coef_smem;
+            k->discard_state = h->discard_state;
             k->zero_copy = h->zero_copy;
             k->frame = h->frame;
             k->geo = h->geo;
@@ -1259,7 +1284,15 @@ int msnap_generate_batch_host(msnap_handle h, const msnap_config *cfg, double sa
         j.p0 = j.g0 + b0;
     }
     auto enqueue = [&](long long c) {
-        jobs[(size_t)c].single = n_chunks == 1;
+        HostChunk &jc = jobs[(size_t)c];
+        jc.single = n_chunks == 1;
+        // a chunk's device mirror holds the chunk's own rows, not the whole batch's (the caller's capacity bounds it too)
+        jc.capacity = sample_capacity;
+        if (n_chunks > 1) {
+            const long long bound = host_rows_bound(cfg, va, waypoints, jc.p0, jc.B,
+                                                    ns_uniform, jc.off_local);
+            if (bound < jc.capacity) jc.capacity = bound;
+        }
         return host_chunk_enqueue(ctx[(size_t)c % ctx.size()], cfg, sd, va, jobs[(size_t)c], ns_uniform, waypoints,
                                   times_out, coeff_out, max_dev_out, iters_out, vw_final_out, best_s_out,
                                   sample_capacity, samples_out, stats_out, flags_out);

@@ -1,3 +1,13 @@
-python scripts/d2h_ceiling.py --numa 0 --mb 20 --out gpurun_out/r2_d2h_ceiling.jsonl 2>&1 | tail -5
-timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29532 scripts/d2h_ceiling.py --numa 0 --mb 20 --out gpurun_out/r2_d2h_ceiling.jsonl 2>&1 | tail -30
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 200 --warmup 5 --configs none --no-parity > gpurun_out/r2_b2.json 2> gpurun_out/r2_b2.err; head -c 200 gpurun_out/r2_b2.json; echo; wc -l gpurun_out/r2_b2.json
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_scale.py tests/test_gpu_robustness.py tests/test_gpu_geo.py -m gpu -q -x --tb=short 2>&1 | tail -4
+python - <<'PY'
+import sys, time; sys.path.insert(0, ".")
+import numpy as np, torch
+from cs_pathplan_b200 import TrajectoryGeneratorTool, workloads
+tool = TrajectoryGeneratorTool(0)
+wp, ns = workloads.cfg3(B=1 << 18)
+cfg = workloads.synthetic_config(4, "shipped")
+free0 = torch.cuda.mem_get_info()[0]
+for i in range(2):
+    t0 = time.perf_counter(); r = tool.generate_batch(cfg, wp, ns=ns, outputs="samples"); dt = time.perf_counter() - t0
+print("host path 262144 x 8: %.1f ms, rows %d, device memory held %.2f GB" % (dt * 1e3, r.samples.shape[0], (free0 - torch.cuda.mem_get_info()[0]) / 1e9))
+PY

@@ -201,8 +201,15 @@ __device__ __forceinline__ void assemble_row(double Ta, double Tc, const double 
 // subroutine call sits in the row loop of every sweep and costs registers (spills) and ~40 cycles of dependent latency per
 // row.  Pivots that are not positive normal numbers are reported through the caller's status flag either way.
 __device__ __forceinline__ double pivot_rcp(double x) {
+#ifdef MSNAP_HOST_EMULATION  // CPU baseline build of these kernels (oracle/structured_cpu.cpp): an IEEE reciprocal
+    return 1.0 / x;
+#endif
     double r;
+#ifndef MSNAP_HOST_EMULATION
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#else
+    r = 0.0;
+#endif
     double e = fma(-x, r, 1.0);
     r = fma(r, e, r);
     e = fma(-x, r, 1.0);
@@ -305,6 +312,7 @@ struct PlainMem {
     __device__ static __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
     __device__ static __forceinline__ void st2(double *p, double a, double b) { *reinterpret_cast<double2 *>(p) = make_double2(a, b); }
 };
+#ifndef MSNAP_HOST_EMULATION  // (sm_100a cache-hint accesses: no host counterpart; the CPU baseline uses PlainMem only)
 struct L2KeepMem {
     __device__ static __forceinline__ unsigned long long policy() {
         unsigned long long pol;
@@ -328,6 +336,8 @@ struct L2KeepMem {
         asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(a), "d"(b), "l"(policy()) : "memory");
     }
 };
+
+#endif
 
 // Accessors may declare `static constexpr int PAIR = LANES`: the row is then laid out [field / 2][lane][2] -- two consecutive
 // fields of one lane sit side by side, so a lane moves them as one 128-bit word and a warp's access is 512 contiguous bytes

@@ -89,7 +89,13 @@ struct GlobalRows {
     __device__ __forceinline__ void prefetch(int j) const {
         const char *q = reinterpret_cast<const char *>(p + (size_t)j * NF);
 #pragma unroll
-        for (int o = 0; o < NF * 8 + 127; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(q + o));
+        for (int o = 0; o < NF * 8 + 127; o += 128) {
+#ifndef MSNAP_HOST_EMULATION  // (oracle/structured_cpu.cpp compiles these kernels for the host as a CPU baseline)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(q + o));
+#else
+            __builtin_prefetch(q + o);
+#endif
+        }
     }
 };
 struct GlobalPos {  // waypoint positions of one trajectory, [w][3]

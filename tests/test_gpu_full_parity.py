@@ -75,3 +75,27 @@ def test_cfg5_short_members_vs_reference(tool):
     p = parity.batch_parity(res, wp, so, cfg, picks=picks)
     _report(f"cfg5 members ns<=64 (max ns {ns[picks].max()})", p)
     parity.assert_parity(p)
+
+
+@pytest.mark.parametrize("kind", ["cfg2", "cfg5_dense"])
+def test_gpu_equals_its_own_algorithm_on_the_cpu(tool, kind):
+    """The library's sequential kernel set compiled for the host (oracle/structured_cpu.cpp, the "good CPU" baseline of the
+    bench line) on the bench's own batches: same segment times bit for bit, same reweighting decisions, same sample count for
+    EVERY trajectory, rows within 1e-7 m (the two differ in the pivot reciprocal -- Newton on the GPU, IEEE division on the
+    host -- and in which chains are twisted)."""
+    from oracle import structured_ref as sr
+
+    if kind == "cfg2":
+        wp, ns = workloads.cfg2()
+        cfg, kw = workloads.synthetic_config(4, "shipped"), dict(ns=ns)
+    else:
+        wp, so = workloads.cfg5(B=2048, seed=1237)
+        cfg, kw = workloads.synthetic_config(4, "shipped", 0.0), dict(seg_offset=so)
+    g = tool.generate_batch(cfg, wp, **kw)
+    c = sr.generate_batch(wp, cfg, **kw)
+    assert np.array_equal(g.times, c["times"])
+    assert np.array_equal(g.sample_offset, c["sample_offset"])
+    assert np.array_equal(g.iters, c["iters"]) and np.array_equal(g.vw_final, c["vw_final"])
+    err = float(np.max(np.abs(g.samples - c["samples"])))
+    print(f"\n[structured cpu] {kind}: {g.samples.shape[0]} rows, max |GPU - CPU build| = {err:.3e} m")
+    assert err <= 1e-7

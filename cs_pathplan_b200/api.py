@@ -369,7 +369,8 @@ class TrajectoryGeneratorTool:
             dp(z_pass1), dp(solves), dp(flags)))
 
     def set_altitude_policy(self, policy: int):
-        """0 = lane pairs (two-sided elimination, default), 1 = one lane per trajectory."""
+        """0 = lane pairs (two-sided elimination), 1 = one lane per trajectory, 2 = partitioned over 8 / 32 lanes, the
+        whole stage in one launch (default)."""
         self._check(self._L.msnap_set_altitude_policy(self._h, int(policy)))
 
     def cost_map_lookup_dev(self, grid, resolution, origin_x, origin_y, rows, elev_out, n_rows=None):

@@ -19,6 +19,7 @@
 #include "msnap_fused.cuh"
 #include "msnap_geo.cuh"
 #include "msnap_alt.cuh"
+#include "msnap_alt_part.cuh"
 #include "msnap_bezier.cuh"
 #include "msnap_patrol.cuh"
 #include "msnap_follow.cuh"
@@ -85,7 +86,8 @@ struct msnap_context {
     int wp_frame = 0;       // msnap_set_waypoint_frame: 1 = generate / sample_bound take WGS84 waypoints (cpp:2640)
     GeoFrame wp_geo{};
     bool alt_smem_opted = false;
-    int alt_policy = 0;     // msnap_set_altitude_policy: 0 = lane pairs (two-sided elimination), 1 = one lane per trajectory
+    int alt_policy = 2;     // msnap_set_altitude_policy: 0 = lane pairs (two-sided elimination), 1 = one lane per trajectory,
+                            // 2 = partitioned over 8 / 32 lanes, one launch (default)
     bool geo_trig = false;  // msnap_set_geo_exact_trig: ENU -> WGS84 with the reference's per-step sin/cos/atan2
 };
 
@@ -1456,7 +1458,7 @@ void msnap_altitude_params_default(msnap_altitude_params *p) {  // uavPathPlanni
 }
 
 int msnap_set_altitude_policy(msnap_handle h, int policy) {
-    if (!h || policy < 0 || policy > 1) return MSNAP_ERR_INVALID_ARG;
+    if (!h || policy < 0 || policy > 2) return MSNAP_ERR_INVALID_ARG;
     h->alt_policy = policy;
     return MSNAP_OK;
 }
@@ -1492,15 +1494,26 @@ int msnap_altitude_optimize_batch_dev(msnap_handle h, const msnap_altitude_param
     int *st = arena_take<int>(h->ws, (size_t)B);  // per-trajectory outcome (ALT_ST_*)
     const AltParams p{params->lambda_smooth, params->lambda_follow, params->max_climb_rate, params->uav_R,
                       params->safe_distance};
+    if (!h->alt_smem_opted) {  // > 48 KB of dynamic shared memory needs the opt-in (per device; once per handle)
+        MS_CUDA(h, cudaFuncSetAttribute(k_alt_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ALT_SMEM_BYTES));
+        MS_CUDA(h, cudaFuncSetAttribute(k_alt_solve_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ALT_SMEM_BYTES));
+        MS_CUDA(h, cudaFuncSetAttribute(k_alt_part, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ALTP_SMEM_BYTES));
+        h->alt_smem_opted = true;
+    }
+    if (h->alt_policy == 2) {  // partitioned solves, the whole stage in one launch (msnap_alt_part.cuh)
+        const AltPartScratch sc{{w1, tgt, zin, l1, l2, yd, w2, cur}};
+        prof_before(h, "k_alt_part");
+        k_alt_part<<<grid_for(B, 32 / ALTP_GROUP), 32, ALTP_SMEM_BYTES, h->stream>>>(p, B, row_offset, rows_inout, elev, z_pass1_out,
+                                                                                   solves_out, flags_out, n_rows_cap, sc);
+        prof_after(h);
+        ++h->launches;
+        MS_CUDA(h, cudaPeekAtLastError());
+        return MSNAP_OK;
+    }
     const long long want = (n_rows_cap + 255) / 256, cap = (long long)h->sm_count * 8;
     MS_LAUNCH(h, k_alt_prep, (unsigned)(want < cap ? want : cap), 256, p, B, row_offset, rows_inout, elev, w1, w2, tgt, act,
               n_rows_cap);
     MS_LAUNCH(h, k_alt_ends, grid_for(B, 256), 256, B, row_offset, w1, w2, n_rows_cap);
-    if (!h->alt_smem_opted) {  // > 48 KB of dynamic shared memory needs the opt-in (per device; once per handle)
-        MS_CUDA(h, cudaFuncSetAttribute(k_alt_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ALT_SMEM_BYTES));
-        MS_CUDA(h, cudaFuncSetAttribute(k_alt_solve_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ALT_SMEM_BYTES));
-        h->alt_smem_opted = true;
-    }
     if (h->alt_policy == 1) {  // one lane per trajectory
         prof_before(h, "k_alt_solve");
         k_alt_solve<<<grid_for(B, 32), 32, ALT_SMEM_BYTES, h->stream>>>(p, B, row_offset, elev, w1, w2, tgt, l1, l2, yd, zin,

@@ -244,9 +244,11 @@ int msnap_altitude_optimize_batch_dev(msnap_handle h, const msnap_altitude_param
 int msnap_altitude_optimize_batch_host(msnap_handle h, const msnap_altitude_params *params, long long B,
                                        const long long *row_offset, double *rows_inout, const double *elev,
                                        double *z_pass1_out, int *solves_out, unsigned *flags_out);
-/* Execution form of the per-trajectory banded solves: 0 (default) = a lane pair per trajectory (two-sided elimination
- * meeting at the two middle rows: half the dependent steps), 1 = one lane per trajectory (plain downward LDL').  Same
- * systems, same active-set decisions; heights differ by rounding (~1e-9 m). */
+/* Execution form of the per-trajectory banded solves: 2 (default) = partitioned: a trajectory's rows are cut into up to
+ * 8 chunks (32 for trajectories of more than 262 rows) eliminated by one lane each, the 2-row separators between them are
+ * solved across the lanes, and the whole stage (edge weights, both passes, write-back) is one launch; 0 = a lane pair per
+ * trajectory (two-sided elimination meeting at the two middle rows), 1 = one lane per trajectory (plain downward LDL').
+ * Same systems, same active-set decisions; heights differ by rounding (~1e-9 m). */
 int msnap_set_altitude_policy(msnap_handle h, int policy);
 /* ElevationCostMap::getCostAt (elevation_cost_map.cpp:373-380) for every row: grid is a DEVICE float array
  * [height][width], row-major, top-left origin at (origin_x, origin_y) in ENU metres, square cells of `resolution` metres;

@@ -20,12 +20,15 @@ pytestmark = pytest.mark.gpu
 Z_TOL = 1e-6
 
 
-@pytest.fixture(params=["lane_pairs", "one_lane"])
+POLICIES = {"lane_pairs": 0, "one_lane": 1, "partitioned": 2}
+
+
+@pytest.fixture(params=list(POLICIES))
 def alt_tool(tool, request):
-    """Both execution forms of the banded solves (msnap_set_altitude_policy) must meet the same bars."""
-    tool.set_altitude_policy(0 if request.param == "lane_pairs" else 1)
+    """All execution forms of the banded solves (msnap_set_altitude_policy) must meet the same bars."""
+    tool.set_altitude_policy(POLICIES[request.param])
     yield tool
-    tool.set_altitude_policy(0)
+    tool.set_altitude_policy(2)
 
 
 def oracle_params(p):
@@ -169,27 +172,31 @@ def test_full_size_properties(alt_tool):
         assert np.abs(out[sl, 2] - z2).max() <= Z_TOL
 
 
-def test_lane_pairs_equal_one_lane(tool):
-    """Two-sided elimination against the plain downward recurrence: same active-set decisions, heights equal to rounding;
-    lengths around the pairing threshold (8 rows) and odd / even lengths included."""
+def test_lane_pairs_and_partitions_equal_one_lane(tool):
+    """Two-sided elimination and the partitioned (nested-dissection) form against the plain downward recurrence: same
+    active-set decisions, heights equal to rounding; lengths around the pairing threshold (8 rows), around the partition
+    counts (n / 4 lanes up to 8; 262 rows = the last length a group of 8 lanes holds) and odd / even lengths included."""
     grid, res, ox, oy = terrain_grid()
     rows, off = sampled_paths(200, seed=77, n_min=1, n_max=40)
     rows2, off2 = sampled_paths(60, seed=78, n_min=100, n_max=400)
-    rows = np.vstack([rows, rows2])
+    rows3, off3 = sampled_paths(24, seed=79, n_min=255, n_max=270)
+    rows = np.vstack([rows, rows2, rows3])
     off = np.concatenate([off, off[-1] + off2[1:]])
+    off = np.concatenate([off, off[-1] + off3[1:]])
     elev = lookup(grid, res, ox, oy, rows)
     p = shipped_altitude_params()
     out = {}
     try:
-        for pol in (0, 1):
+        for pol in (0, 1, 2):
             tool.set_altitude_policy(pol)
             out[pol] = tool.altitude_optimize_batch(rows, off, p, elev, return_info=True)
     finally:
-        tool.set_altitude_policy(0)
-    assert np.array_equal(out[0][2], out[1][2])                       # solves of the active-set loop
-    assert not out[0][3].any() and not out[1][3].any()
-    assert np.abs(out[0][1] - out[1][1]).max() <= 1e-6                # pass 1 (rows outside the map are weakly held)
-    assert np.abs(out[0][0][:, 2] - out[1][0][:, 2]).max() <= 1e-6   # final heights
+        tool.set_altitude_policy(2)
+    for pol in (0, 2):
+        assert np.array_equal(out[pol][2], out[1][2]), pol                     # solves of the active-set loop
+        assert not out[pol][3].any() and not out[1][3].any()
+        assert np.abs(out[pol][1] - out[1][1]).max() <= 1e-6, pol              # pass 1 (rows outside the map are weakly held)
+        assert np.abs(out[pol][0][:, 2] - out[1][0][:, 2]).max() <= 1e-6, pol  # final heights
 
 
 def test_long_trajectories_many_chunks(alt_tool):

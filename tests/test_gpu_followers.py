@@ -87,7 +87,7 @@ def test_altitude_matches_reference_statements_golden(tool):
     grid, res, ox, oy = terrain_grid()
     dev = torch.device("cuda")
     worst = 0.0
-    for policy in (0, 1):
+    for policy in (0, 1, 2):
         tool.set_altitude_policy(policy)
         for i, c in enumerate(man["altitude"]):
             rows, off = z[f"alt/{i}/rows"], z[f"alt/{i}/off"]
@@ -103,8 +103,8 @@ def test_altitude_matches_reference_statements_golden(tool):
             assert not d_fl.cpu().numpy().any()
             worst = max(worst, float(np.abs(d_rows.cpu().numpy() - z[f"alt/{i}/out"]).max()),
                         float(np.abs(d_z1.cpu().numpy() - z[f"alt/{i}/z1"]).max()))
-    tool.set_altitude_policy(0)
-    print(f"\n[altitude] 4 golden batches x 2 execution forms vs the reference's statements: max height error {worst:.3e} m")
+    tool.set_altitude_policy(2)
+    print(f"\n[altitude] 4 golden batches x 3 execution forms vs the reference's statements: max height error {worst:.3e} m")
     assert worst <= 1e-6
 
 

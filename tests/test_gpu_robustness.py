@@ -102,11 +102,11 @@ def test_altitude_failure_semantics_follow_the_reference(tool):
     good, _, _, fl0 = tool.altitude_optimize_batch(rows, off, shipped_altitude_params(), elev, return_info=True)
     assert not fl0.any() and not np.array_equal(good, rows)
     bad = AltitudeParams(lambda_smooth=1.0, lambda_follow=float("nan"), max_climb_rate=0.3, safe_distance=10.0)
-    for policy in (0, 1):
+    for policy in (0, 1, 2):
         tool.set_altitude_policy(policy)
         out, _, _, fl = tool.altitude_optimize_batch(rows, off, bad, elev, return_info=True)
         assert np.all(fl & 1) and np.array_equal(out, rows)          # untouched
-    tool.set_altitude_policy(0)
+    tool.set_altitude_policy(2)
 
 
 @pytest.mark.parametrize("sd,v", [(300.0, 30.0), (5.0, 30.0), (40.0, 200.0), (300.0, 8.0)])   # (v = 8: T up to 4 000 s, beyond the time table)

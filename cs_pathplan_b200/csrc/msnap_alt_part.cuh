@@ -98,22 +98,50 @@ __device__ __forceinline__ void alt_part_set(const AltParams &p, const AltPartFl
     const AltPartFld<GLOBAL> F = fields.at(base + start);
     const double lf = p.lambda_follow, safe = p.safe_distance;
 
-    // ---- load: edge weights (k_alt_prep's arithmetic), follow targets, elevations of this lane's rows
+    // ---- load: edge weights (k_alt_prep's arithmetic), follow targets, elevations of this lane's rows.  In the
+    // shared-memory form the raw rows are first copied into the (still unused) factor slots with cp.async -- every copy
+    // of the lane is in flight at once, one wait -- and the row loop below then runs out of shared memory.
     double wlast = 0.0;
     {
         const double *r = rows + 3 * (base + start);
+        const bool more = mine && start + len < n;  // the row after this lane's last one (its x, y close the last edge)
+        if constexpr (!GLOBAL) {
+            for (int i = 0; i < len; ++i) {
+                __pipeline_memcpy_async(F.q + (AF_L1 * ALTP_SLOTS + i) * 32, r + 3 * i, sizeof(double));
+                __pipeline_memcpy_async(F.q + (AF_L2 * ALTP_SLOTS + i) * 32, r + 3 * i + 1, sizeof(double));
+                __pipeline_memcpy_async(F.q + (AF_YD * ALTP_SLOTS + i) * 32, r + 3 * i + 2, sizeof(double));
+                if (elev) __pipeline_memcpy_async(F.q + (AF_E * ALTP_SLOTS + i) * 32, elev + base + start + i, sizeof(double));
+            }
+            if (more) {
+                __pipeline_memcpy_async(F.q + (AF_V1 * ALTP_SLOTS) * 32, r + 3 * len, sizeof(double));
+                __pipeline_memcpy_async(F.q + (AF_V2 * ALTP_SLOTS) * 32, r + 3 * len + 1, sizeof(double));
+            }
+            __pipeline_commit();
+            __pipeline_wait_prior(0);
+        }
+        auto rx = [&](int i) {
+            if constexpr (GLOBAL) return r[3 * i];
+            else return i < len ? F.ld(AF_L1, i) : F.ld(AF_V1, 0);
+        };
+        auto ry = [&](int i) {
+            if constexpr (GLOBAL) return r[3 * i + 1];
+            else return i < len ? F.ld(AF_L2, i) : F.ld(AF_V2, 0);
+        };
         double x0 = 0.0, y0 = 0.0;
         if (len > 0) {
-            x0 = r[0];
-            y0 = r[1];
+            x0 = rx(0);
+            y0 = ry(0);
         }
+#pragma unroll 2
         for (int i = 0; i < len; ++i) {
             const int k = start + i;
-            const double up = r[3 * i + 2];
+            double up;
+            if constexpr (GLOBAL) up = r[3 * i + 2];
+            else up = F.ld(AF_YD, i);
             double enc = 0.0, x1 = 0.0, y1 = 0.0;
             if (k + 1 < n) {
-                x1 = r[3 * i + 3];
-                y1 = r[3 * i + 4];
+                x1 = rx(i + 1);
+                y1 = ry(i + 1);
                 const double dist = hypot(x1 - x0, y1 - y0);
                 if (dist > 1e-9) {  // cpp:1655, 1765
                     const double d1 = dist * p.max_climb_rate, d2 = dist * (p.max_climb_rate * 0.5);
@@ -123,10 +151,14 @@ __device__ __forceinline__ void alt_part_set(const AltParams &p, const AltPartFl
                     }
                 }
             }
-            const double el = elev ? elev[base + k] : NAN;
+            double el = NAN;
+            if (elev) {
+                if constexpr (GLOBAL) el = elev[base + k];
+                else el = F.ld(AF_E, i);
+            }
             F.st(AF_W, i, enc);
             F.st(AF_T, i, el == el ? fmax(up, el + safe) : NAN);  // cpp:1637-1638
-            F.st(AF_E, i, el);
+            if (GLOBAL || !elev) F.st(AF_E, i, el);
             x0 = x1;
             y0 = y1;
             wlast = enc;
@@ -139,8 +171,9 @@ __device__ __forceinline__ void alt_part_set(const AltParams &p, const AltPartFl
     // Returns this lane's pivot status (combine with group_any).
     auto solve = [&](auto pass_tag, double s, bool active) -> bool {
         constexpr int PASS = decltype(pass_tag)::value;
-        const bool smooth = n >= 3 && s > 0.0;
-        auto in = [&](int j) { return (smooth && j >= 1 && j <= n - 2) ? s : 0.0; };  // s * [row j is interior], cpp:1588-1604
+        const double s_eff = (n >= 3 && s > 0.0) ? s : 0.0;
+        // s * [row j is interior: 1 <= j <= n-2], cpp:1588-1604 (one unsigned compare; n < 3 has s_eff = 0)
+        auto in = [&](int j) { return (unsigned)(j - 1) <= (unsigned)(n - 3) ? s_eff : 0.0; };
         auto coef = [&](int k, int i, double &extra, double &rhs) {  // what the pass adds to H[k,k] and b[k]
             if constexpr (PASS == 1) {
                 const double t = F.ld(AF_T, i);
@@ -148,10 +181,7 @@ __device__ __forceinline__ void alt_part_set(const AltParams &p, const AltPartFl
                 extra = has ? lf : 0.0;
                 rhs = has ? lf * t : 0.0;
             } else {
-                double x = 0.0;
-                if (k == 0) x += ALT_FIX_WEIGHT;  // cpp:1779-1784
-                if (k == n - 1) x += ALT_FIX_WEIGHT;
-                if (k >= 1 && k < n - 1 && F.ld(AF_T, i) != 0.0) x += ALT_CON_WEIGHT;  // cpp:1787-1793
+                const double x = fabs(F.ld(AF_T, i));  // the row's penalty weight (see the conversion after pass 1)
                 extra = x;
                 rhs = x * F.ld(AF_E, i);
             }
@@ -164,9 +194,12 @@ __device__ __forceinline__ void alt_part_set(const AltParams &p, const AltPartFl
                 if (z_pass1_out) z_pass1_out[base + k] = z;
             } else {
                 F.st(AF_YD, i, z);
-                if (z < F.ld(AF_E, i) - ALT_VIOLATION && F.ld(AF_T, i) == 0.0) {  // cpp:1805-1810
-                    F.st(AF_T, i, 1.0);
-                    violation = true;
+                if (z < F.ld(AF_E, i) - ALT_VIOLATION) {  // cpp:1805-1810
+                    const double t = F.ld(AF_T, i);
+                    if (!(t < 0.0 || t == ALT_CON_WEIGHT)) {  // not in the active set yet
+                        F.st(AF_T, i, t == 0.0 ? ALT_CON_WEIGHT : -t);
+                        violation = true;
+                    }
                 }
             }
         };
@@ -177,14 +210,16 @@ __device__ __forceinline__ void alt_part_set(const AltParams &p, const AltPartFl
         double a1 = 0.0, a2 = 0.0, cc = 0.0, Dm1 = 0.0, Dm2 = 0.0, ym1 = 0.0, ym2 = 0.0;
         double v1m1 = 0.0, v1m2 = 0.0, v2m1 = 0.0, v2m2 = 0.0;
         double sm_ = in(start - 1), s0_ = in(start);
-        double wm1 = a_hl ? alt_part_weight<PASS>(wprev) : 0.0;
+        double wm1 = a_hl ? alt_part_weight<PASS>(wprev) : 0.0;  // (wprev stays encoded; the stored W is converted after pass 1)
         // H[start, start-2], H[start, start-1], H[start+1, start-1]: the chunk's coupling to the separator above
         const double hL0 = a_hl ? sm_ : 0.0, eL1 = a_hl ? -2.0 * (sm_ + s0_) - wm1 : 0.0, hL1 = a_hl ? s0_ : 0.0;
         double q11 = 0.0, q12 = 0.0, q22 = 0.0, r1 = 0.0, r2 = 0.0;  // V' D^-1 V and V' D^-1 y
+        double H1 = hL0, H2 = eL1, H2n = hL1;  // direct couplings of local rows 0 and 1 to the separator above
         bool ok = true;
+#pragma unroll 4
         for (int i = 0; i < cn; ++i) {
             const int k = start + i;
-            const double wk = alt_part_weight<PASS>(F.ld(AF_W, i));
+            const double wk = PASS == 1 ? fabs(F.ld(AF_W, i)) : F.ld(AF_W, i);
             double extra, rhs;
             coef(k, i, extra, rhs);
             const double sp = in(k + 1);
@@ -192,8 +227,10 @@ __device__ __forceinline__ void alt_part_set(const AltParams &p, const AltPartFl
             const double e = -2.0 * (s0_ + sp) - wk;
             const double D = fma(-a2 * a2, Dm2, fma(-a1 * a1, Dm1, d));
             const double y = fma(-a2, ym2, fma(-a1, ym1, rhs));
-            const double H1 = i == 0 ? hL0 : 0.0, H2 = i == 0 ? eL1 : (i == 1 ? hL1 : 0.0);
             const double v1 = fma(-a2, v1m2, fma(-a1, v1m1, H1)), v2 = fma(-a2, v2m2, fma(-a1, v2m1, H2));
+            H1 = 0.0;
+            H2 = H2n;
+            H2n = 0.0;
             ok = ok && D > 0.0 && D < 1e300;
             const double inv = alt_rcp(D);
             const double n1 = fma(-cc * Dm1, a1, e) * inv, n2 = sp * inv;
@@ -228,7 +265,7 @@ __device__ __forceinline__ void alt_part_set(const AltParams &p, const AltPartFl
         if (a_hr) {
             int i = cn, k = start + cn;
             double extra, rhs;
-            const double wk0 = alt_part_weight<PASS>(F.ld(AF_W, i));
+            const double wk0 = PASS == 1 ? fabs(F.ld(AF_W, i)) : F.ld(AF_W, i);
             coef(k, i, extra, rhs);
             const double sp0 = in(k + 1);
             const double d0 = fma(4.0, s0_, sp0 + sm_) + (wm1 + wk0) + extra + ALT_REG;
@@ -239,7 +276,7 @@ __device__ __forceinline__ void alt_part_set(const AltParams &p, const AltPartFl
             C01 = -fma(a2, v2m2, a1 * v2m1);
             A01 = e0 - cc * Dm1 * a1;
             ++i, ++k;
-            const double wk1 = alt_part_weight<PASS>(F.ld(AF_W, i));
+            const double wk1 = PASS == 1 ? fabs(F.ld(AF_W, i)) : F.ld(AF_W, i);
             coef(k, i, extra, rhs);
             const double sp1 = in(k + 1);
             const double d1 = fma(4.0, sp0, sp1 + s0_) + (wk0 + wk1) + extra + ALT_REG;
@@ -306,6 +343,7 @@ __device__ __forceinline__ void alt_part_set(const AltParams &p, const AltPartFl
             sink(start + cn, cn, s0v);
         }
         const double uL0 = a_hl ? sL0 : 0.0, uL1 = a_hl ? sL1 : 0.0;
+#pragma unroll 2
         for (int i = cn - 1; i >= 0; --i) {
             const double ydk = fma(-F.ld(AF_V2, i), uL1, fma(-F.ld(AF_V1, i), uL0, F.ld(AF_YD, i)));
             const double z = alt_bwd_row(r, F.ld(AF_L1, i), F.ld(AF_L2, i), ydk);
@@ -316,7 +354,14 @@ __device__ __forceinline__ void alt_part_set(const AltParams &p, const AltPartFl
 
     // ---- pass 1 (cpp:1575-1712), then the active-set loop of pass 2 with lambda_smooth * 10, max_climb_rate * 0.5
     const bool ok = !group_any(!solve(std::integral_constant<int, 1>{}, p.lambda_smooth, mine));
-    for (int i = 0; i < len; ++i) F.st(AF_T, i, 0.0);  // the follow targets are dead: T becomes the active-set mark
+    // The follow targets are dead: T becomes the row's penalty weight in pass 2 -- 1e10 per end the row is (cpp:1779-1784),
+    // 1e8 once an interior row has joined the active set (cpp:1787-1793), negated once an end row has (its weight does not
+    // change, but like the reference's flag it reports a violation only once) -- and W the climb weight of pass 2.
+    for (int i = 0; i < len; ++i) {
+        const int k = start + i;
+        F.st(AF_T, i, (k == 0 ? ALT_FIX_WEIGHT : 0.0) + (k == n - 1 ? ALT_FIX_WEIGHT : 0.0));
+        F.st(AF_W, i, alt_part_weight<2>(F.ld(AF_W, i)));
+    }
     int solves = 0;
     bool ok2 = true, running = n > 0;
     for (int iter = 0; iter < ALT_MAX_ITER; ++iter) {

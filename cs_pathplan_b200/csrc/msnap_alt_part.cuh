@@ -21,8 +21,9 @@
 // row because every per-row field lives in shared memory, laid out [field][slot][lane] -- a lane's rows are private to it,
 // addresses are base + immediate, nothing is staged and nothing synchronises inside a sweep.
 //
-// Shared memory: 8 fields x 33 slots x 32 lanes x 8 B = 66 KB per warp, one warp per CTA, three CTAs per SM; a group of 8
-// lanes holds trajectories of up to 8 * 31 + 14 = 262 rows.  Longer trajectories are taken one at a time by all 32 lanes
+// Shared memory: 7 fields; the three a separator row needs (W, E, YD) have 33 slots per lane, the four only interior rows
+// use (L1, L2, V1, V2) have 31: 223 x 32 lanes x 8 B = 55.75 KB per warp, one warp per CTA, FOUR CTAs per SM (228 KB);
+// a group of 8 lanes holds trajectories of up to 8 * 31 + 14 = 262 rows.  Longer trajectories are taken one at a time by all 32 lanes
 // of the warp with the same code, the fields in the caller's global scratch arrays (natural row order) instead.
 #ifndef MSNAP_ALT_PART_CUH
 #define MSNAP_ALT_PART_CUH
@@ -35,14 +36,22 @@ constexpr int ALTP_CMAX = 31;              // interior rows of a chunk that fit 
 constexpr int ALTP_SLOTS = ALTP_CMAX + 2;  // + the lane's two separator rows
 constexpr int ALTP_GROUP = 8;              // lanes per trajectory in the shared-memory form
 constexpr int ALTP_NMAX = ALTP_GROUP * ALTP_CMAX + 2 * (ALTP_GROUP - 1);  // 262 rows
-enum AltPartField { AF_W = 0, AF_T, AF_E, AF_L1, AF_L2, AF_YD, AF_V1, AF_V2, AF_COUNT };
-constexpr size_t ALTP_SMEM_BYTES = (size_t)AF_COUNT * ALTP_SLOTS * 32 * sizeof(double);
+enum AltPartField { AF_W = 0, AF_E, AF_YD, AF_L1, AF_L2, AF_V1, AF_V2, AF_COUNT };
+// first slot of a field: W, E, YD hold every row of the lane (ALTP_SLOTS), the factor fields interior rows only (ALTP_CMAX)
+__host__ __device__ constexpr int altp_off(int f) { return f <= AF_L1 ? f * ALTP_SLOTS : AF_L1 * ALTP_SLOTS + (f - AF_L1) * ALTP_CMAX; }
+constexpr int ALTP_SLOT_ROWS = altp_off(AF_COUNT);  // 223
+constexpr size_t ALTP_SMEM_BYTES = (size_t)ALTP_SLOT_ROWS * 32 * sizeof(double);
+// staging homes of the raw x / y columns during the load (ALTP_SLOTS + 1 entries each, over fields that are still unused)
+constexpr int ALTP_STAGE_X = altp_off(AF_L1), ALTP_STAGE_Y = altp_off(AF_V1);
+static_assert(ALTP_STAGE_X + ALTP_SLOTS + 1 <= ALTP_STAGE_Y && ALTP_STAGE_Y + ALTP_SLOTS + 1 <= ALTP_SLOT_ROWS, "staging overlaps");
 
 // Per-row fields of a lane's chunk (local row i = 0 .. len-1; the separator rows come last):
-//   W   climb weight of the edge (k, k+1) of pass 1; negative when pass 2 has no such edge (see alt_part_weight)
-//   T   pass 1: follow target (NaN: the map has no value here); pass 2: 1.0 where the row is in the active set
+//   W   pass 1: climb weight of the edge (k, k+1), negative when pass 2 has no such edge (see alt_part_weight);
+//       pass 2: that pass's climb weight, sign bit set once the row has joined the active set
 //   E   terrain elevation (NaN: none); from the back substitution of pass 1 on: the pass-1 height z1
-//   L1, L2, YD   L[k,k-1], L[k,k-2], y_k / D_k; YD holds z_k after a back substitution
+//   YD  before a row's elimination in pass 1: its follow target (NaN: the map has no value here); then y_k / D_k; z_k after
+//       a back substitution
+//   L1, L2       L[k,k-1], L[k,k-2]
 //   V1, V2       the chunk's coupling columns, V_k / D_k
 template <bool GLOBAL>
 struct AltPartFld;
@@ -50,8 +59,8 @@ template <>
 struct AltPartFld<false> {  // shared memory, [field][slot][lane]
     double *q;              // alt_sm + lane
     __device__ __forceinline__ AltPartFld at(long long) const { return *this; }
-    __device__ __forceinline__ double ld(int f, int i) const { return q[(f * ALTP_SLOTS + i) * 32]; }
-    __device__ __forceinline__ void st(int f, int i, double v) const { q[(f * ALTP_SLOTS + i) * 32] = v; }
+    __device__ __forceinline__ double ld(int f, int i) const { return q[(altp_off(f) + i) * 32]; }
+    __device__ __forceinline__ void st(int f, int i, double v) const { q[(altp_off(f) + i) * 32] = v; }
 };
 template <>
 struct AltPartFld<true> {  // global scratch arrays, natural row order: field f of row k at g[f][k]
@@ -107,25 +116,25 @@ __device__ __forceinline__ void alt_part_set(const AltParams &p, const AltPartFl
         const bool more = mine && start + len < n;  // the row after this lane's last one (its x, y close the last edge)
         if constexpr (!GLOBAL) {
             for (int i = 0; i < len; ++i) {
-                __pipeline_memcpy_async(F.q + (AF_L1 * ALTP_SLOTS + i) * 32, r + 3 * i, sizeof(double));
-                __pipeline_memcpy_async(F.q + (AF_L2 * ALTP_SLOTS + i) * 32, r + 3 * i + 1, sizeof(double));
-                __pipeline_memcpy_async(F.q + (AF_YD * ALTP_SLOTS + i) * 32, r + 3 * i + 2, sizeof(double));
-                if (elev) __pipeline_memcpy_async(F.q + (AF_E * ALTP_SLOTS + i) * 32, elev + base + start + i, sizeof(double));
+                __pipeline_memcpy_async(F.q + (ALTP_STAGE_X + i) * 32, r + 3 * i, sizeof(double));
+                __pipeline_memcpy_async(F.q + (ALTP_STAGE_Y + i) * 32, r + 3 * i + 1, sizeof(double));
+                __pipeline_memcpy_async(F.q + (altp_off(AF_YD) + i) * 32, r + 3 * i + 2, sizeof(double));
+                if (elev) __pipeline_memcpy_async(F.q + (altp_off(AF_E) + i) * 32, elev + base + start + i, sizeof(double));
             }
             if (more) {
-                __pipeline_memcpy_async(F.q + (AF_V1 * ALTP_SLOTS) * 32, r + 3 * len, sizeof(double));
-                __pipeline_memcpy_async(F.q + (AF_V2 * ALTP_SLOTS) * 32, r + 3 * len + 1, sizeof(double));
+                __pipeline_memcpy_async(F.q + (ALTP_STAGE_X + len) * 32, r + 3 * len, sizeof(double));
+                __pipeline_memcpy_async(F.q + (ALTP_STAGE_Y + len) * 32, r + 3 * len + 1, sizeof(double));
             }
             __pipeline_commit();
             __pipeline_wait_prior(0);
         }
         auto rx = [&](int i) {
             if constexpr (GLOBAL) return r[3 * i];
-            else return i < len ? F.ld(AF_L1, i) : F.ld(AF_V1, 0);
+            else return F.q[(ALTP_STAGE_X + i) * 32];
         };
         auto ry = [&](int i) {
             if constexpr (GLOBAL) return r[3 * i + 1];
-            else return i < len ? F.ld(AF_L2, i) : F.ld(AF_V2, 0);
+            else return F.q[(ALTP_STAGE_Y + i) * 32];
         };
         double x0 = 0.0, y0 = 0.0;
         if (len > 0) {
@@ -142,11 +151,14 @@ __device__ __forceinline__ void alt_part_set(const AltParams &p, const AltPartFl
             if (k + 1 < n) {
                 x1 = rx(i + 1);
                 y1 = ry(i + 1);
-                const double dist = hypot(x1 - x0, y1 - y0);
+                // std::hypot (cpp:1650): a square root of the sum of squares unless that could over- or underflow
+                const double dx = x1 - x0, dy = y1 - y0, q2 = fma(dx, dx, dy * dy);
+                const double dist = (q2 > 1e-280 && q2 < 1e280) ? sqrt(q2) : hypot(dx, dy);
                 if (dist > 1e-9) {  // cpp:1655, 1765
                     const double d1 = dist * p.max_climb_rate, d2 = dist * (p.max_climb_rate * 0.5);
                     if (p.max_climb_rate > 0.0 && d1 > 1e-12) {
-                        const double a1 = 1.0 / (d1 * d1);
+                        const double dd = d1 * d1;
+                        const double a1 = (dd > 1e-280 && dd < 1e280) ? alt_rcp(dd) : 1.0 / dd;
                         enc = (p.max_climb_rate * 0.5 > 0.0 && d2 > 1e-12) ? a1 : -a1;
                     }
                 }
@@ -157,7 +169,7 @@ __device__ __forceinline__ void alt_part_set(const AltParams &p, const AltPartFl
                 else el = F.ld(AF_E, i);
             }
             F.st(AF_W, i, enc);
-            F.st(AF_T, i, el == el ? fmax(up, el + safe) : NAN);  // cpp:1637-1638
+            F.st(AF_YD, i, el == el ? fmax(up, el + safe) : NAN);  // the follow target, cpp:1637-1638
             if (GLOBAL || !elev) F.st(AF_E, i, el);
             x0 = x1;
             y0 = y1;
@@ -172,16 +184,20 @@ __device__ __forceinline__ void alt_part_set(const AltParams &p, const AltPartFl
     auto solve = [&](auto pass_tag, double s, bool active) -> bool {
         constexpr int PASS = decltype(pass_tag)::value;
         const double s_eff = (n >= 3 && s > 0.0) ? s : 0.0;
-        // s * [row j is interior: 1 <= j <= n-2], cpp:1588-1604 (one unsigned compare; n < 3 has s_eff = 0)
-        auto in = [&](int j) { return (unsigned)(j - 1) <= (unsigned)(n - 3) ? s_eff : 0.0; };
+        const double x_end = n == 1 ? 2.0 * ALT_FIX_WEIGHT : ALT_FIX_WEIGHT;  // (pass 2) penalty weight of rows 0 and n-1
+        // s * [row j is interior: 1 <= j <= n-2], cpp:1588-1604 (one unsigned compare)
+        const unsigned n_int = n > 2 ? (unsigned)(n - 2) : 0u;
+        auto in = [&](int j) { return (unsigned)(j - 1) < n_int ? s_eff : 0.0; };
         auto coef = [&](int k, int i, double &extra, double &rhs) {  // what the pass adds to H[k,k] and b[k]
             if constexpr (PASS == 1) {
-                const double t = F.ld(AF_T, i);
+                const double t = F.ld(AF_YD, i);
                 const bool has = t == t;
                 extra = has ? lf : 0.0;
                 rhs = has ? lf * t : 0.0;
             } else {
-                const double x = fabs(F.ld(AF_T, i));  // the row's penalty weight (see the conversion after pass 1)
+                // 1e10 per end the row is (cpp:1779-1784), 1e8 on interior rows of the active set (cpp:1787-1793)
+                const bool interior = (unsigned)(k - 1) < n_int;
+                const double x = interior ? (signbit(F.ld(AF_W, i)) ? ALT_CON_WEIGHT : 0.0) : x_end;
                 extra = x;
                 rhs = x * F.ld(AF_E, i);
             }
@@ -195,9 +211,9 @@ __device__ __forceinline__ void alt_part_set(const AltParams &p, const AltPartFl
             } else {
                 F.st(AF_YD, i, z);
                 if (z < F.ld(AF_E, i) - ALT_VIOLATION) {  // cpp:1805-1810
-                    const double t = F.ld(AF_T, i);
-                    if (!(t < 0.0 || t == ALT_CON_WEIGHT)) {  // not in the active set yet
-                        F.st(AF_T, i, t == 0.0 ? ALT_CON_WEIGHT : -t);
+                    const double w = F.ld(AF_W, i);
+                    if (!signbit(w)) {  // not in the active set yet
+                        F.st(AF_W, i, -w);
                         violation = true;
                     }
                 }
@@ -219,7 +235,7 @@ __device__ __forceinline__ void alt_part_set(const AltParams &p, const AltPartFl
 #pragma unroll 4
         for (int i = 0; i < cn; ++i) {
             const int k = start + i;
-            const double wk = PASS == 1 ? fabs(F.ld(AF_W, i)) : F.ld(AF_W, i);
+            const double wk = fabs(F.ld(AF_W, i));
             double extra, rhs;
             coef(k, i, extra, rhs);
             const double sp = in(k + 1);
@@ -265,7 +281,7 @@ __device__ __forceinline__ void alt_part_set(const AltParams &p, const AltPartFl
         if (a_hr) {
             int i = cn, k = start + cn;
             double extra, rhs;
-            const double wk0 = PASS == 1 ? fabs(F.ld(AF_W, i)) : F.ld(AF_W, i);
+            const double wk0 = fabs(F.ld(AF_W, i));
             coef(k, i, extra, rhs);
             const double sp0 = in(k + 1);
             const double d0 = fma(4.0, s0_, sp0 + sm_) + (wm1 + wk0) + extra + ALT_REG;
@@ -276,7 +292,7 @@ __device__ __forceinline__ void alt_part_set(const AltParams &p, const AltPartFl
             C01 = -fma(a2, v2m2, a1 * v2m1);
             A01 = e0 - cc * Dm1 * a1;
             ++i, ++k;
-            const double wk1 = PASS == 1 ? fabs(F.ld(AF_W, i)) : F.ld(AF_W, i);
+            const double wk1 = fabs(F.ld(AF_W, i));
             coef(k, i, extra, rhs);
             const double sp1 = in(k + 1);
             const double d1 = fma(4.0, sp0, sp1 + s0_) + (wk0 + wk1) + extra + ALT_REG;
@@ -354,14 +370,8 @@ __device__ __forceinline__ void alt_part_set(const AltParams &p, const AltPartFl
 
     // ---- pass 1 (cpp:1575-1712), then the active-set loop of pass 2 with lambda_smooth * 10, max_climb_rate * 0.5
     const bool ok = !group_any(!solve(std::integral_constant<int, 1>{}, p.lambda_smooth, mine));
-    // The follow targets are dead: T becomes the row's penalty weight in pass 2 -- 1e10 per end the row is (cpp:1779-1784),
-    // 1e8 once an interior row has joined the active set (cpp:1787-1793), negated once an end row has (its weight does not
-    // change, but like the reference's flag it reports a violation only once) -- and W the climb weight of pass 2.
-    for (int i = 0; i < len; ++i) {
-        const int k = start + i;
-        F.st(AF_T, i, (k == 0 ? ALT_FIX_WEIGHT : 0.0) + (k == n - 1 ? ALT_FIX_WEIGHT : 0.0));
-        F.st(AF_W, i, alt_part_weight<2>(F.ld(AF_W, i)));
-    }
+    // W becomes the climb weight of pass 2 (non-negative: its sign bit is that pass's active-set mark).
+    for (int i = 0; i < len; ++i) F.st(AF_W, i, alt_part_weight<2>(F.ld(AF_W, i)));
     int solves = 0;
     bool ok2 = true, running = n > 0;
     for (int iter = 0; iter < ALT_MAX_ITER; ++iter) {

@@ -1501,7 +1501,7 @@ int msnap_altitude_optimize_batch_dev(msnap_handle h, const msnap_altitude_param
         h->alt_smem_opted = true;
     }
     if (h->alt_policy == 2) {  // partitioned solves, the whole stage in one launch (msnap_alt_part.cuh)
-        const AltPartScratch sc{{w1, tgt, zin, l1, l2, yd, w2, cur}};
+        const AltPartScratch sc{{w1, zin, yd, l1, l2, w2, cur}};  // W, E, YD, L1, L2, V1, V2
         prof_before(h, "k_alt_part");
         k_alt_part<<<grid_for(B, 32 / ALTP_GROUP), 32, ALTP_SMEM_BYTES, h->stream>>>(p, B, row_offset, rows_inout, elev, z_pass1_out,
                                                                                    solves_out, flags_out, n_rows_cap, sc);

@@ -43,6 +43,10 @@ constexpr int ALTP_SLOT_ROWS = altp_off(AF_COUNT);  // 223
 constexpr size_t ALTP_SMEM_BYTES = (size_t)ALTP_SLOT_ROWS * 32 * sizeof(double);
 // staging homes of the raw x / y columns during the load (ALTP_SLOTS + 1 entries each, over fields that are still unused)
 constexpr int ALTP_STAGE_X = altp_off(AF_L1), ALTP_STAGE_Y = altp_off(AF_V1);
+// bulk-copy staging (doubles per group of lanes): rows [3 n + 1] in the L1 .. V2 slots, elevations [n + 1] in the YD slots
+constexpr int ALTP_STAGE_R = ((ALTP_SLOT_ROWS - ALTP_STAGE_X) * 32 / (32 / ALTP_GROUP)) & ~1;
+constexpr int ALTP_STAGE_E = (ALTP_SLOTS * 32 / (32 / ALTP_GROUP)) & ~1;
+static_assert(3 * ALTP_NMAX + 2 <= ALTP_STAGE_R && ALTP_NMAX + 2 <= ALTP_STAGE_E, "bulk staging does not fit");
 static_assert(ALTP_STAGE_X + ALTP_SLOTS + 1 <= ALTP_STAGE_Y && ALTP_STAGE_Y + ALTP_SLOTS + 1 <= ALTP_SLOT_ROWS, "staging overlaps");
 
 // Per-row fields of a lane's chunk (local row i = 0 .. len-1; the separator rows come last):
@@ -89,7 +93,7 @@ __device__ __forceinline__ double alt_part_weight(double enc) {
 template <int GW, bool GLOBAL>
 __device__ __forceinline__ void alt_part_set(const AltParams &p, const AltPartFld<GLOBAL> fields, int lane, bool valid,
                                              long long base, int n, double *rows, const double *elev, double *z_pass1_out,
-                                             int &solves_ret, bool &ok_ret, bool &ok2_ret) {
+                                             long long n_cap, unsigned mbar, int &solves_ret, bool &ok_ret, bool &ok2_ret) {
     constexpr unsigned FULL = 0xffffffffu;
     const int pp = lane & (GW - 1);
     const unsigned gmask = GW == 32 ? FULL : (((1u << GW) - 1u) << (lane & ~(GW - 1)));
@@ -107,35 +111,87 @@ __device__ __forceinline__ void alt_part_set(const AltParams &p, const AltPartFl
     const AltPartFld<GLOBAL> F = fields.at(base + start);
     const double lf = p.lambda_follow, safe = p.safe_distance;
 
-    // ---- load: edge weights (k_alt_prep's arithmetic), follow targets, elevations of this lane's rows.  In the
-    // shared-memory form the raw rows are first copied into the (still unused) factor slots with cp.async -- every copy
-    // of the lane is in flight at once, one wait -- and the row loop below then runs out of shared memory.
+    // ---- load: edge weights (k_alt_prep's arithmetic), follow targets, elevations of this lane's rows.
+    // Shared-memory form: a trajectory's rows (24 n contiguous bytes) and elevations (8 n) come in by ONE bulk copy each
+    // (cp.async.bulk, issued by the group's first lane, completion counted on the warp's mbarrier) into the still unused
+    // factor / YD slots in natural order; every lane then picks its own rows out of shared memory.  A bulk copy moves
+    // 16-byte units between 16-byte aligned addresses: the window is widened to the next boundaries (never beyond the
+    // caller's arrays: a last odd element is fetched by an ordinary load instead).  Arrays that are not 16-byte aligned
+    // themselves take the per-lane path (cp.async, 8 bytes a copy, every copy of the lane in flight at once).
     double wlast = 0.0;
     {
         const double *r = rows + 3 * (base + start);
-        const bool more = mine && start + len < n;  // the row after this lane's last one (its x, y close the last edge)
+        const double *sx = r, *sy = r + 1, *su = r + 2;  // x, y, up of local row i at s?[i * sstride]
+        int sstride = 3;
         if constexpr (!GLOBAL) {
-            for (int i = 0; i < len; ++i) {
-                __pipeline_memcpy_async(F.q + (ALTP_STAGE_X + i) * 32, r + 3 * i, sizeof(double));
-                __pipeline_memcpy_async(F.q + (ALTP_STAGE_Y + i) * 32, r + 3 * i + 1, sizeof(double));
-                __pipeline_memcpy_async(F.q + (altp_off(AF_YD) + i) * 32, r + 3 * i + 2, sizeof(double));
-                if (elev) __pipeline_memcpy_async(F.q + (altp_off(AF_E) + i) * 32, elev + base + start + i, sizeof(double));
+            double *const sm0 = F.q - lane;
+            const bool bulk = ((reinterpret_cast<unsigned long long>(rows) | reinterpret_cast<unsigned long long>(elev)) & 15ull) == 0ull;
+            if (bulk) {
+                double *Rg = sm0 + ALTP_STAGE_X * 32 + (lane / GW) * ALTP_STAGE_R;       // rows of this group's trajectory
+                double *Eg = sm0 + altp_off(AF_YD) * 32 + (lane / GW) * ALTP_STAGE_E;    // its elevations
+                const long long e0 = 3 * base, e1 = 3 * (base + n), c0 = base, c1 = base + n;
+                const long long f0 = e0 & ~1ll, g0 = c0 & ~1ll;
+                long long f1 = (e1 + 1) & ~1ll, g1 = (c1 + 1) & ~1ll;
+                if (f1 > 3 * n_cap) f1 = e1 & ~1ll;
+                if (g1 > n_cap) g1 = c1 & ~1ll;
+                const int shr = (int)(e0 - f0), she = (int)(c0 - g0);
+                if (pp == 0) {
+                    const unsigned bytes_r = n > 0 ? (unsigned)((f1 - f0) * 8) : 0u;
+                    const unsigned bytes_e = (n > 0 && elev) ? (unsigned)((g1 - g0) * 8) : 0u;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes_r + bytes_e) : "memory");
+                    if (bytes_r)
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                         (unsigned)__cvta_generic_to_shared(Rg)),
+                                     "l"(rows + f0), "r"(bytes_r), "r"(mbar)
+                                     : "memory");
+                    if (bytes_e)
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                         (unsigned)__cvta_generic_to_shared(Eg)),
+                                     "l"(elev + g0), "r"(bytes_e), "r"(mbar)
+                                     : "memory");
+                }
+                {
+                    unsigned done = 0;
+                    while (!done)
+                        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                                     : "=r"(done)
+                                     : "r"(mbar)
+                                     : "memory");
+                }
+                if (pp == 0 && n > 0) {  // an odd last element the window could not cover
+                    if (f1 < e1) Rg[shr + 3 * n - 1] = rows[e1 - 1];
+                    if (elev && g1 < c1) Eg[she + n - 1] = elev[c1 - 1];
+                }
+                __syncwarp();
+                for (int i = 0; i < len; ++i) F.st(AF_E, i, elev ? Eg[she + start + i] : NAN);
+                __syncwarp();  // the elevations' staging area is YD: free it before the follow targets land there
+                sx = Rg + shr + 3 * start;
+                sy = sx + 1;
+                su = sx + 2;
+            } else {
+                const bool more = mine && start + len < n;  // the row after this lane's last one (its x, y close the last edge)
+                for (int i = 0; i < len; ++i) {
+                    __pipeline_memcpy_async(F.q + (ALTP_STAGE_X + i) * 32, r + 3 * i, sizeof(double));
+                    __pipeline_memcpy_async(F.q + (ALTP_STAGE_Y + i) * 32, r + 3 * i + 1, sizeof(double));
+                    __pipeline_memcpy_async(F.q + (altp_off(AF_YD) + i) * 32, r + 3 * i + 2, sizeof(double));
+                    if (elev) __pipeline_memcpy_async(F.q + (altp_off(AF_E) + i) * 32, elev + base + start + i, sizeof(double));
+                }
+                if (more) {
+                    __pipeline_memcpy_async(F.q + (ALTP_STAGE_X + len) * 32, r + 3 * len, sizeof(double));
+                    __pipeline_memcpy_async(F.q + (ALTP_STAGE_Y + len) * 32, r + 3 * len + 1, sizeof(double));
+                }
+                __pipeline_commit();
+                __pipeline_wait_prior(0);
+                if (!elev)
+                    for (int i = 0; i < len; ++i) F.st(AF_E, i, NAN);
+                sx = F.q + ALTP_STAGE_X * 32;
+                sy = F.q + ALTP_STAGE_Y * 32;
+                su = F.q + altp_off(AF_YD) * 32;
+                sstride = 32;
             }
-            if (more) {
-                __pipeline_memcpy_async(F.q + (ALTP_STAGE_X + len) * 32, r + 3 * len, sizeof(double));
-                __pipeline_memcpy_async(F.q + (ALTP_STAGE_Y + len) * 32, r + 3 * len + 1, sizeof(double));
-            }
-            __pipeline_commit();
-            __pipeline_wait_prior(0);
         }
-        auto rx = [&](int i) {
-            if constexpr (GLOBAL) return r[3 * i];
-            else return F.q[(ALTP_STAGE_X + i) * 32];
-        };
-        auto ry = [&](int i) {
-            if constexpr (GLOBAL) return r[3 * i + 1];
-            else return F.q[(ALTP_STAGE_Y + i) * 32];
-        };
+        auto rx = [&](int i) { return sx[i * sstride]; };
+        auto ry = [&](int i) { return sy[i * sstride]; };
         double x0 = 0.0, y0 = 0.0;
         if (len > 0) {
             x0 = rx(0);
@@ -144,9 +200,7 @@ __device__ __forceinline__ void alt_part_set(const AltParams &p, const AltPartFl
 #pragma unroll 2
         for (int i = 0; i < len; ++i) {
             const int k = start + i;
-            double up;
-            if constexpr (GLOBAL) up = r[3 * i + 2];
-            else up = F.ld(AF_YD, i);
+            const double up = su[i * sstride];
             double enc = 0.0, x1 = 0.0, y1 = 0.0;
             if (k + 1 < n) {
                 x1 = rx(i + 1);
@@ -170,11 +224,12 @@ __device__ __forceinline__ void alt_part_set(const AltParams &p, const AltPartFl
             }
             F.st(AF_W, i, enc);
             F.st(AF_YD, i, el == el ? fmax(up, el + safe) : NAN);  // the follow target, cpp:1637-1638
-            if (GLOBAL || !elev) F.st(AF_E, i, el);
+            if (GLOBAL) F.st(AF_E, i, el);
             x0 = x1;
             y0 = y1;
             wlast = enc;
         }
+        if constexpr (!GLOBAL) __syncwarp();  // the staged rows lie in the factor slots the sweeps are about to fill
     }
     const double wprev = __shfl_up_sync(FULL, wlast, 1, GW);  // edge (start-1, start): the last row of the lane above
 
@@ -403,11 +458,11 @@ struct AltPartScratch {
     double *g[AF_COUNT];  // n_rows_cap doubles each (the long-trajectory form)
 };
 
-__global__ void __launch_bounds__(32) k_alt_part(AltParams p, long long B, const long long *__restrict__ row_offset,
+__global__ void __maxnreg__(192) k_alt_part(AltParams p, long long B, const long long *__restrict__ row_offset,
                                                  double *rows, const double *elev, double *z_pass1_out,
                                                  int *__restrict__ solves_out, unsigned *__restrict__ flags_out,
                                                  long long n_cap, AltPartScratch scratch) {
-    extern __shared__ double alt_sm[];
+    extern __shared__ __align__(16) double altp_sm[];
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int TPW = 32 / ALTP_GROUP;  // trajectories per warp
     const int lane = threadIdx.x;
@@ -418,9 +473,17 @@ __global__ void __launch_bounds__(32) k_alt_part(AltParams p, long long B, const
     const int n = n_ll > 0 ? (int)(n_ll < 0x7fffffff ? n_ll : 0x7fffffff) : 0;
     int solves = 0;
     bool ok = true, ok2 = true;
+    __shared__ __align__(8) unsigned long long alt_mbar;  // completion of the bulk copies: one arrival per group of lanes
+    const unsigned mbar = (unsigned)__cvta_generic_to_shared(&alt_mbar);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(TPW) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
     {
-        const AltPartFld<false> F{alt_sm + lane};
-        alt_part_set<ALTP_GROUP, false>(p, F, lane, n > 0 && n <= ALTP_NMAX, base, n, rows, elev, z_pass1_out, solves, ok, ok2);
+        const AltPartFld<false> F{altp_sm + lane};
+        alt_part_set<ALTP_GROUP, false>(p, F, lane, n > 0 && n <= ALTP_NMAX, base, n, rows, elev, z_pass1_out, n_cap, mbar, solves, ok,
+                                        ok2);
     }
     // trajectories too long for a group's shared memory: one at a time, all 32 lanes, fields in the global scratch
     unsigned longer = __ballot_sync(FULL, lane % ALTP_GROUP == 0 && n > ALTP_NMAX);
@@ -434,7 +497,7 @@ __global__ void __launch_bounds__(32) k_alt_part(AltParams p, long long B, const
         for (int f = 0; f < AF_COUNT; ++f) G.g[f] = scratch.g[f];
         int s2;
         bool o1, o2;
-        alt_part_set<32, true>(p, G, lane, true, lbase, ln, rows, elev, z_pass1_out, s2, o1, o2);
+        alt_part_set<32, true>(p, G, lane, true, lbase, ln, rows, elev, z_pass1_out, n_cap, mbar, s2, o1, o2);
         if (lane / ALTP_GROUP == src / ALTP_GROUP) {
             solves = s2;
             ok = o1;

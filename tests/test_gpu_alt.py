@@ -220,3 +220,42 @@ def test_long_trajectories_many_chunks(alt_tool):
         assert np.abs(z1[sl] - z1_o).max() <= Z_TOL, b
         assert solves[b] == solves_o, b
         assert np.abs(out[sl, 2] - z2_o).max() <= Z_TOL, b
+
+
+def test_partitioned_staging_paths_agree(tool):
+    """k_alt_part stages a trajectory's rows by bulk copies (16-byte units) when the caller's arrays are 16-byte aligned
+    and by per-lane 8-byte copies otherwise; windows that would reach beyond the arrays fetch their last odd element by an
+    ordinary load.  Same rows through device buffers at an 8-byte offset, and with the batch ending exactly at the end of
+    the allocation (odd row count), must give the same bits."""
+    grid, res, ox, oy = terrain_grid()
+    rows, off = sampled_paths(37, seed=91, n_min=1, n_max=262)
+    if rows.shape[0] % 2 == 0:                       # odd number of rows: 3 n and n are odd, the last windows are clipped
+        rows, off = rows[:-1], np.concatenate([off[:-1], [off[-1] - 1]])
+    elev = lookup(grid, res, ox, oy, rows)
+    n = rows.shape[0]
+    p = shipped_altitude_params()
+    dev = torch.device("cuda")
+    tool.set_altitude_policy(2)
+    d_off = torch.from_numpy(off).to(dev)
+    out = {}
+    for shift in (0, 1):                             # storage offset in doubles
+        buf_r = torch.zeros(3 * n + shift, dtype=torch.float64, device=dev)
+        buf_e = torch.zeros(n + shift, dtype=torch.float64, device=dev)
+        d_rows, d_elev = buf_r[shift:].view(n, 3), buf_e[shift:]
+        d_rows.copy_(torch.from_numpy(rows))
+        d_elev.copy_(torch.from_numpy(elev))
+        assert d_rows.data_ptr() % 16 == 8 * shift
+        d_z1 = torch.empty(n, dtype=torch.float64, device=dev)
+        d_solves = torch.zeros(off.shape[0] - 1, dtype=torch.int32, device=dev)
+        tool.altitude_optimize_batch_dev(p, d_off, d_rows, d_elev, z_pass1=d_z1, solves=d_solves)
+        tool.synchronize()
+        out[shift] = (d_rows.cpu().numpy(), d_z1.cpu().numpy(), d_solves.cpu().numpy())
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+    host = tool.altitude_optimize_batch(rows, off, p, elev)
+    assert np.array_equal(host, out[0][0])
+    for b in (0, 5, 36):
+        sl = slice(int(off[b]), int(off[b + 1]))
+        if sl.stop > sl.start:
+            z2 = ao.optimize_segment_altitude_enu(rows[sl], oracle_params(p), elev[sl])
+            assert np.abs(out[0][0][sl, 2] - z2).max() <= Z_TOL

@@ -23,8 +23,9 @@
 //
 // Shared memory: 7 fields; the three a separator row needs (W, E, YD) have 33 slots per lane, the four only interior rows
 // use (L1, L2, V1, V2) have 31: 223 x 32 lanes x 8 B = 55.75 KB per warp, one warp per CTA, FOUR CTAs per SM (228 KB);
-// a group of 8 lanes holds trajectories of up to 8 * 31 + 14 = 262 rows.  Longer trajectories are taken one at a time by all 32 lanes
-// of the warp with the same code, the fields in the caller's global scratch arrays (natural row order) instead.
+// a group of 8 lanes holds trajectories of up to 8 * 31 + 14 = 262 rows.  Longer trajectories are taken one at a time by all 32 lanes of the warp
+// with the same code: up to 32 * 31 + 62 = 1054 rows in the same shared memory, beyond that with the fields in the caller's
+// global scratch arrays (natural row order) instead.
 #ifndef MSNAP_ALT_PART_CUH
 #define MSNAP_ALT_PART_CUH
 
@@ -44,9 +45,11 @@ constexpr size_t ALTP_SMEM_BYTES = (size_t)ALTP_SLOT_ROWS * 32 * sizeof(double);
 // staging homes of the raw x / y columns during the load (ALTP_SLOTS + 1 entries each, over fields that are still unused)
 constexpr int ALTP_STAGE_X = altp_off(AF_L1), ALTP_STAGE_Y = altp_off(AF_V1);
 // bulk-copy staging (doubles per group of lanes): rows [3 n + 1] in the L1 .. V2 slots, elevations [n + 1] in the YD slots
-constexpr int ALTP_STAGE_R = ((ALTP_SLOT_ROWS - ALTP_STAGE_X) * 32 / (32 / ALTP_GROUP)) & ~1;
-constexpr int ALTP_STAGE_E = (ALTP_SLOTS * 32 / (32 / ALTP_GROUP)) & ~1;
-static_assert(3 * ALTP_NMAX + 2 <= ALTP_STAGE_R && ALTP_NMAX + 2 <= ALTP_STAGE_E, "bulk staging does not fit");
+__host__ __device__ constexpr int altp_stage_r(int gw) { return ((ALTP_SLOT_ROWS - ALTP_STAGE_X) * 32 / (32 / gw)) & ~1; }
+__host__ __device__ constexpr int altp_stage_e(int gw) { return (ALTP_SLOTS * 32 / (32 / gw)) & ~1; }
+constexpr int ALTP_NMAX32 = 32 * ALTP_CMAX + 2 * 31;  // 1054 rows: what all 32 lanes hold in shared memory for ONE trajectory
+static_assert(3 * ALTP_NMAX + 2 <= altp_stage_r(ALTP_GROUP) && ALTP_NMAX + 2 <= altp_stage_e(ALTP_GROUP), "bulk staging does not fit");
+static_assert(3 * ALTP_NMAX32 + 2 <= altp_stage_r(32) && ALTP_NMAX32 + 2 <= altp_stage_e(32), "bulk staging does not fit");
 static_assert(ALTP_STAGE_X + ALTP_SLOTS + 1 <= ALTP_STAGE_Y && ALTP_STAGE_Y + ALTP_SLOTS + 1 <= ALTP_SLOT_ROWS, "staging overlaps");
 
 // Per-row fields of a lane's chunk (local row i = 0 .. len-1; the separator rows come last):
@@ -93,7 +96,8 @@ __device__ __forceinline__ double alt_part_weight(double enc) {
 template <int GW, bool GLOBAL>
 __device__ __forceinline__ void alt_part_set(const AltParams &p, const AltPartFld<GLOBAL> fields, int lane, bool valid,
                                              long long base, int n, double *rows, const double *elev, double *z_pass1_out,
-                                             long long n_cap, unsigned mbar, int &solves_ret, bool &ok_ret, bool &ok2_ret) {
+                                             long long n_cap, unsigned mbar, unsigned &phase, int &solves_ret, bool &ok_ret,
+                                             bool &ok2_ret) {
     constexpr unsigned FULL = 0xffffffffu;
     const int pp = lane & (GW - 1);
     const unsigned gmask = GW == 32 ? FULL : (((1u << GW) - 1u) << (lane & ~(GW - 1)));
@@ -127,17 +131,20 @@ __device__ __forceinline__ void alt_part_set(const AltParams &p, const AltPartFl
             double *const sm0 = F.q - lane;
             const bool bulk = ((reinterpret_cast<unsigned long long>(rows) | reinterpret_cast<unsigned long long>(elev)) & 15ull) == 0ull;
             if (bulk) {
-                double *Rg = sm0 + ALTP_STAGE_X * 32 + (lane / GW) * ALTP_STAGE_R;       // rows of this group's trajectory
-                double *Eg = sm0 + altp_off(AF_YD) * 32 + (lane / GW) * ALTP_STAGE_E;    // its elevations
+                double *Rg = sm0 + ALTP_STAGE_X * 32 + (lane / GW) * altp_stage_r(GW);     // rows of this group's trajectory
+                double *Eg = sm0 + altp_off(AF_YD) * 32 + (lane / GW) * altp_stage_e(GW);  // its elevations
                 const long long e0 = 3 * base, e1 = 3 * (base + n), c0 = base, c1 = base + n;
                 const long long f0 = e0 & ~1ll, g0 = c0 & ~1ll;
                 long long f1 = (e1 + 1) & ~1ll, g1 = (c1 + 1) & ~1ll;
                 if (f1 > 3 * n_cap) f1 = e1 & ~1ll;
                 if (g1 > n_cap) g1 = c1 & ~1ll;
                 const int shr = (int)(e0 - f0), she = (int)(c0 - g0);
-                if (pp == 0) {
-                    const unsigned bytes_r = n > 0 ? (unsigned)((f1 - f0) * 8) : 0u;
-                    const unsigned bytes_e = (n > 0 && elev) ? (unsigned)((g1 - g0) * 8) : 0u;
+                // (a later use of the tile: order the warp's ordinary accesses before the copy engine's writes)
+                __syncwarp();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (lane % ALTP_GROUP == 0) {  // the barrier counts 32 / ALTP_GROUP arrivals per use, whatever GW is
+                    const unsigned bytes_r = (pp == 0 && n > 0) ? (unsigned)((f1 - f0) * 8) : 0u;
+                    const unsigned bytes_e = (pp == 0 && n > 0 && elev) ? (unsigned)((g1 - g0) * 8) : 0u;
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes_r + bytes_e) : "memory");
                     if (bytes_r)
                         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -153,10 +160,11 @@ __device__ __forceinline__ void alt_part_set(const AltParams &p, const AltPartFl
                 {
                     unsigned done = 0;
                     while (!done)
-                        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                                      : "=r"(done)
-                                     : "r"(mbar)
+                                     : "r"(mbar), "r"(phase & 1u)
                                      : "memory");
+                    ++phase;
                 }
                 if (pp == 0 && n > 0) {  // an odd last element the window could not cover
                     if (f1 < e1) Rg[shr + 3 * n - 1] = rows[e1 - 1];
@@ -475,6 +483,7 @@ __global__ void __maxnreg__(192) k_alt_part(AltParams p, long long B, const long
     bool ok = true, ok2 = true;
     __shared__ __align__(8) unsigned long long alt_mbar;  // completion of the bulk copies: one arrival per group of lanes
     const unsigned mbar = (unsigned)__cvta_generic_to_shared(&alt_mbar);
+    unsigned phase = 0;  // uses of the barrier so far (its parity)
     if (lane == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(TPW) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -482,22 +491,29 @@ __global__ void __maxnreg__(192) k_alt_part(AltParams p, long long B, const long
     __syncwarp();
     {
         const AltPartFld<false> F{altp_sm + lane};
-        alt_part_set<ALTP_GROUP, false>(p, F, lane, n > 0 && n <= ALTP_NMAX, base, n, rows, elev, z_pass1_out, n_cap, mbar, solves, ok,
-                                        ok2);
+        alt_part_set<ALTP_GROUP, false>(p, F, lane, n > 0 && n <= ALTP_NMAX, base, n, rows, elev, z_pass1_out, n_cap, mbar, phase,
+                                        solves, ok, ok2);
     }
-    // trajectories too long for a group's shared memory: one at a time, all 32 lanes, fields in the global scratch
+    // trajectories too long for a group of 8 lanes: one at a time, all 32 lanes -- in shared memory up to 1054 rows, with the
+    // fields in the global scratch beyond
     unsigned longer = __ballot_sync(FULL, lane % ALTP_GROUP == 0 && n > ALTP_NMAX);
     while (longer) {
         const int src = __ffs(longer) - 1;
         longer &= longer - 1;
         const long long lbase = __shfl_sync(FULL, base, src);
         const int ln = __shfl_sync(FULL, n, src);
-        AltPartFld<true> G;
-#pragma unroll
-        for (int f = 0; f < AF_COUNT; ++f) G.g[f] = scratch.g[f];
         int s2;
         bool o1, o2;
-        alt_part_set<32, true>(p, G, lane, true, lbase, ln, rows, elev, z_pass1_out, n_cap, mbar, s2, o1, o2);
+        __syncwarp();
+        if (ln <= ALTP_NMAX32) {
+            const AltPartFld<false> F{altp_sm + lane};
+            alt_part_set<32, false>(p, F, lane, true, lbase, ln, rows, elev, z_pass1_out, n_cap, mbar, phase, s2, o1, o2);
+        } else {
+            AltPartFld<true> G;
+#pragma unroll
+            for (int f = 0; f < AF_COUNT; ++f) G.g[f] = scratch.g[f];
+            alt_part_set<32, true>(p, G, lane, true, lbase, ln, rows, elev, z_pass1_out, n_cap, mbar, phase, s2, o1, o2);
+        }
         if (lane / ALTP_GROUP == src / ALTP_GROUP) {
             solves = s2;
             ok = o1;

@@ -1827,19 +1827,25 @@ extern "C" int msnap_followers_dev(msnap_handle h, int formation_model, double f
         return MSNAP_ERR_INVALID_ARG;
     if (B == 0 || n_followers == 0 || n_rows_cap == 0 || out_capacity == 0) return MSNAP_OK;
     DeviceGuard guard(h->device);
-    int rc = arena_reserve(h, h->ws, 2 * padded((size_t)n_rows_cap * sizeof(double)) + 256);
+    int rc = arena_reserve(h, h->ws, 4 * padded((size_t)n_rows_cap * sizeof(double)) + 256);
     if (rc) return rc;
     double *ws_sin = arena_take<double>(h->ws, (size_t)n_rows_cap), *ws_cos = arena_take<double>(h->ws, (size_t)n_rows_cap);
-    long long *total = arena_take<long long>(h->ws, 1);
     FollowParams p{formation_model, n_followers, uav_formation_max_row < 1 ? 1 : uav_formation_max_row, formation_distance};
-    MS_LAUNCH(h, k_follow_enu, (unsigned)B, FOLLOW_THREADS, p, B, row_offset, leader_rows, n_rows_cap, ws_sin, ws_cos, out_rows,
-              out_capacity);
-    if (frame == 0) return MSNAP_OK;
+    if (frame == 0) {
+        MS_LAUNCH(h, k_follow_enu, (unsigned)B, FOLLOW_THREADS, p, B, row_offset, leader_rows, n_rows_cap, ws_sin, ws_cos, out_rows,
+                  out_capacity);
+        return MSNAP_OK;
+    }
+    // WGS84 rows: formation offsets and enuToWGS84 (cpp:4141) in one pass over the output
+    double *ws_sin2 = arena_take<double>(h->ws, (size_t)n_rows_cap), *ws_cos2 = arena_take<double>(h->ws, (size_t)n_rows_cap);
     GeoFrame f;
     geo_make_frame(reference_lla, f);
-    MS_LAUNCH(h, k_follow_total, 1, 32, B, row_offset, n_rows_cap, n_followers, total);
-    rc = launch_enu_to_wgs84(h, f, out_capacity, total, out_rows, out_rows, nullptr);
-    if (rc) return rc;
+    if (h->geo_trig)
+        MS_LAUNCH(h, k_follow_lla<true>, (unsigned)B, FOLLOW_THREADS, p, f, B, row_offset, leader_rows, n_rows_cap, ws_sin, ws_cos,
+                  ws_sin2, ws_cos2, out_rows, out_capacity);
+    else
+        MS_LAUNCH(h, k_follow_lla<false>, (unsigned)B, FOLLOW_THREADS, p, f, B, row_offset, leader_rows, n_rows_cap, ws_sin, ws_cos,
+                  ws_sin2, ws_cos2, out_rows, out_capacity);
     if (starts_wgs84_dev && formation_model >= 2 && formation_model <= 4)
         MS_LAUNCH(h, k_follow_starts, grid_for(B * n_followers, 128), 128, n_followers, B, row_offset, leader_rows, n_rows_cap,
                   starts_wgs84_dev, out_rows, out_capacity);

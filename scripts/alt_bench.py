@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Time the batched altitude optimisation (k_alt_prep + k_alt_solve; device-resident rows, per-kernel CUDA events on the
+"""Time the batched altitude optimisation (k_alt_part by default; k_alt_prep + k_alt_solve* + ... with --policy 0 / 1; device-resident rows, per-kernel CUDA events on the
 launching stream through msnap_profile_begin/end) on a cfg2-sized sampler output.  One JSON line.  The CPU leg (a
 banded-Cholesky stand-in for the reference's per-trajectory SimplicialLDLT loop) is `python bench.py --impl rows-cpu`.
 

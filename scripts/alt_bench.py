@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--B", type=int, default=4096)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--policy", type=int, default=2, help="msnap_set_altitude_policy: 2 partitioned (default), 0 lane pairs, 1 one lane")
     a = ap.parse_args()
     rows, off, elev = workload(a.B)
     n = rows.shape[0]
@@ -44,6 +45,7 @@ def main():
         hbm_peak = 6553.3
     with TrajectoryGeneratorTool(0) as tool:
         stream = torch.cuda.Stream()
+        tool.set_altitude_policy(a.policy)
         tool.set_stream(stream.cuda_stream)
         with torch.cuda.stream(stream):
             for _ in range(3):

@@ -3,10 +3,14 @@ tag, ver = sys.argv[1], sys.argv[2]
 G, P = "gpurun_out/", "profiles/"
 shutil.copy(f"{G}{tag}_alt_bench.json", f"{P}{ver}_alt_bench.json")
 shutil.copy(f"{G}{tag}_alt_launches.csv", f"{P}{ver}_alt_launches.csv")
+try:
+    shutil.copy(f"{G}{tag}_alt_bench_pairs.json", f"{P}{ver}_alt_bench_pairs.json")
+except FileNotFoundError:
+    pass
 WANT = ("GPU Speed Of Light Throughput", "Launch Statistics", "Occupancy", "Compute Workload Analysis", "Scheduler Statistics", "Warp State Statistics")
 path = f"{G}{tag}_alt_solve.ncu-rep"
 with open(f"{P}{ver}_alt_ncu_summary.txt", "w") as out:
-    out.write(f"== k_alt_solve, 4096 trajectories x 150-259 rows, shipped altitude parameters  [ncu --set full --clock-control none, {path}]\n")
+    out.write(f"== k_alt_part, 4096 trajectories x 150-259 rows, shipped altitude parameters  [ncu --set full --clock-control none, {path}]\n")
     det = subprocess.run(["ncu", "-i", path, "--page", "details", "--csv"], capture_output=True, text=True).stdout
     for r in csv.reader(io.StringIO(det)):
         if len(r) > 14 and r[11] in WANT:

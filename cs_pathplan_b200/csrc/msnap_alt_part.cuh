@@ -13,7 +13,7 @@
 // (2 x 2 blocks, P-1 of them):
 //     A_p = H[sep_p, sep_p] - (from chunk p above: the continued recurrence) - (from chunk p+1 below: V' D^-1 V)
 //     C_p = coupling sep_p / sep_{p-1} = the V columns continued into sep_p
-// solved across the lanes of the group by shuffles (block Thomas, P-2 dependent steps), after which every lane substitutes
+// solved across the lanes of the group by shuffles (block Thomas from both ends, ~P/2 dependent steps each way), after which every lane substitutes
 // back through its chunk:  z_k = y_k/D_k - V_k/D_k . z[sep_{p-1}] - L[k+1,k] z_{k+1} - L[k+2,k] z_{k+2}.
 // This is Gaussian elimination of the same SPD matrix in a nested-dissection order (the reference's SimplicialLDLT uses a
 // fill-reducing order of its own), so the heights agree with the other two forms to rounding and the active-set decisions
@@ -377,36 +377,70 @@ __device__ __forceinline__ void alt_part_set(const AltParams &p, const AltPartFl
                 g1 -= r2n;
             }
         }
-        // block Thomas over the separators of the group: block t lives on lane t
-        for (int t = 1; t <= Pmax - 2; ++t) {
-            const double B00 = __shfl_sync(FULL, A00, t - 1, GW), B01 = __shfl_sync(FULL, A01, t - 1, GW),
-                         B11 = __shfl_sync(FULL, A11, t - 1, GW), bg0 = __shfl_sync(FULL, g0, t - 1, GW),
-                         bg1 = __shfl_sync(FULL, g1, t - 1, GW);
-            if (a_hr && pp == t) {
-                const double det = fma(B00, B11, -(B01 * B01));
-                ok = ok && B00 > 0.0 && det > 0.0 && det < 1e300;
-                const double idet = alt_rcp(det);
-                const double M00 = fma(C00, B11, -(C01 * B01)) * idet, M01 = fma(C01, B00, -(C00 * B01)) * idet;
-                const double M10 = fma(C10, B11, -(C11 * B01)) * idet, M11 = fma(C11, B00, -(C10 * B01)) * idet;
-                A00 -= fma(M00, C00, M01 * C01);
-                A01 -= fma(M00, C10, M01 * C11);
-                A11 -= fma(M10, C10, M11 * C11);
-                g0 -= fma(M00, bg0, M01 * bg1);
-                g1 -= fma(M10, bg0, M11 * bg1);
+        // Block Thomas over the separators of the group (block t on lane t, nb = P - 1 blocks), eliminated from BOTH ends
+        // towards the middle block m = nb / 2 and substituted back outwards: nb / 2 dependent steps each way instead of nb.
+        // A lane above the middle couples to its upper neighbour through its own C, a lane below it to its lower neighbour
+        // through the transpose of that neighbour's C (Kb); the back substitution uses the other one of the two.
+        const int nb = P - 1, mb = nb / 2, nbmax = Pmax - 1, mbmax = nbmax / 2;
+        const bool top = pp < mb, bot = pp > mb, mid = a_hr && pp == mb;
+        const double Kb00 = __shfl_down_sync(FULL, C00, 1, GW), Kb01 = __shfl_down_sync(FULL, C10, 1, GW),
+                     Kb10 = __shfl_down_sync(FULL, C01, 1, GW), Kb11 = __shfl_down_sync(FULL, C11, 1, GW);
+        // A -= K B^-1 K', g -= K B^-1 bg: B, bg = the eliminated neighbour's block and right-hand side, K = the coupling
+        auto absorb = [&](double K00, double K01, double K10, double K11, double B00, double B01, double B11, double bg0,
+                          double bg1) {
+            const double det = fma(B00, B11, -(B01 * B01));
+            const double idet = alt_rcp(det);
+            const double M00 = fma(K00, B11, -(K01 * B01)) * idet, M01 = fma(K01, B00, -(K00 * B01)) * idet;
+            const double M10 = fma(K10, B11, -(K11 * B01)) * idet, M11 = fma(K11, B00, -(K10 * B01)) * idet;
+            A00 -= fma(M00, K00, M01 * K01);
+            A01 -= fma(M00, K10, M01 * K11);
+            A11 -= fma(M10, K10, M11 * K11);
+            g0 -= fma(M00, bg0, M01 * bg1);
+            g1 -= fma(M10, bg0, M11 * bg1);
+        };
+        {
+            const int src = top ? (pp > 0 ? pp - 1 : 0) : (pp + 1 < GW ? pp + 1 : GW - 1);  // the neighbour away from the middle
+            const double K00 = top ? C00 : Kb00, K01 = top ? C01 : Kb01, K10 = top ? C10 : Kb10, K11 = top ? C11 : Kb11;
+            const int smax = mbmax - 1 > nbmax - 2 - mbmax ? mbmax - 1 : nbmax - 2 - mbmax;
+            for (int st = 1; st <= smax; ++st) {
+                const double B00 = __shfl_sync(FULL, A00, src, GW), B01 = __shfl_sync(FULL, A01, src, GW),
+                             B11 = __shfl_sync(FULL, A11, src, GW), bg0 = __shfl_sync(FULL, g0, src, GW),
+                             bg1 = __shfl_sync(FULL, g1, src, GW);
+                if (a_hr && ((top && pp == st) || (bot && pp == nb - 1 - st))) absorb(K00, K01, K10, K11, B00, B01, B11, bg0, bg1);
             }
         }
-        double s0v = 0.0, s1v = 0.0, pw0 = 0.0, pw1 = 0.0;  // z of this lane's separator; C' z for the block above
-        for (int t = Pmax - 2; t >= 0; --t) {
-            const double w0 = __shfl_sync(FULL, pw0, t + 1, GW), w1 = __shfl_sync(FULL, pw1, t + 1, GW);
-            if (a_hr && pp == t) {
+        {  // the middle block takes both sides
+            const int up = pp > 0 ? pp - 1 : 0, dn = pp + 1 < GW ? pp + 1 : GW - 1;
+            double B00 = __shfl_sync(FULL, A00, up, GW), B01 = __shfl_sync(FULL, A01, up, GW), B11 = __shfl_sync(FULL, A11, up, GW),
+                   bg0 = __shfl_sync(FULL, g0, up, GW), bg1 = __shfl_sync(FULL, g1, up, GW);
+            if (mid && mb >= 1) absorb(C00, C01, C10, C11, B00, B01, B11, bg0, bg1);
+            B00 = __shfl_sync(FULL, A00, dn, GW), B01 = __shfl_sync(FULL, A01, dn, GW), B11 = __shfl_sync(FULL, A11, dn, GW);
+            bg0 = __shfl_sync(FULL, g0, dn, GW), bg1 = __shfl_sync(FULL, g1, dn, GW);
+            if (mid && mb + 1 <= nb - 1) absorb(Kb00, Kb01, Kb10, Kb11, B00, B01, B11, bg0, bg1);
+        }
+        double s0v = 0.0, s1v = 0.0;  // z of this lane's separator
+        {
+            double idet = 0.0;
+            if (a_hr) {  // every block is inverted once, by its own lane
                 const double det = fma(A00, A11, -(A01 * A01));
                 ok = ok && A00 > 0.0 && det > 0.0 && det < 1e300;
-                const double idet = alt_rcp(det);
-                const double h0 = g0 - w0, h1 = g1 - w1;
-                s0v = fma(A11, h0, -(A01 * h1)) * idet;
-                s1v = fma(A00, h1, -(A01 * h0)) * idet;
-                pw0 = fma(C00, s0v, C10 * s1v);
-                pw1 = fma(C01, s0v, C11 * s1v);
+                idet = alt_rcp(det);
+            }
+            if (mid) {
+                s0v = fma(A11, g0, -(A01 * g1)) * idet;
+                s1v = fma(A00, g1, -(A01 * g0)) * idet;
+            }
+            const int src = top ? pp + 1 : (pp > 0 ? pp - 1 : 0);  // the neighbour towards the middle
+            // coupling to that neighbour: (C_{t+1}' x_{t+1}) above the middle, (C_t x_{t-1}) below it
+            const double K00 = top ? Kb00 : C00, K01 = top ? Kb01 : C01, K10 = top ? Kb10 : C10, K11 = top ? Kb11 : C11;
+            const int smax = mbmax > nbmax - 1 - mbmax ? mbmax : nbmax - 1 - mbmax;
+            for (int st = 1; st <= smax; ++st) {
+                const double x0 = __shfl_sync(FULL, s0v, src, GW), x1 = __shfl_sync(FULL, s1v, src, GW);
+                if (a_hr && ((top && pp == mb - st) || (bot && pp == mb + st))) {
+                    const double h0 = g0 - fma(K00, x0, K01 * x1), h1 = g1 - fma(K10, x0, K11 * x1);
+                    s0v = fma(A11, h0, -(A01 * h1)) * idet;
+                    s1v = fma(A00, h1, -(A01 * h0)) * idet;
+                }
             }
         }
         const double sL0 = __shfl_up_sync(FULL, s0v, 1, GW), sL1 = __shfl_up_sync(FULL, s1v, 1, GW);

@@ -1,6 +1,6 @@
 // msnap_alt_part.cuh -- altitude optimisation, partitioned form (msnap_set_altitude_policy 2, the default): the same SPD
 // pentadiagonal systems as msnap_alt.cuh (optimizeHeights cpp:1575-1712, optimizeHeightsGlobalSmooth cpp:1714-1827), every
-// solve spread over up to 8 lanes (32 for long trajectories) and the whole stage -- edge weights, follow targets, both
+// solve spread over up to 16 lanes (32 for long trajectories) and the whole stage -- edge weights, follow targets, both
 // passes, the active-set loop, the write-back -- in ONE launch.
 //
 // Why: k_alt_solve_pair walks ~100 dependent rows per lane and sweep and spends most of its ~75 instructions per row on
@@ -17,15 +17,16 @@
 // back through its chunk:  z_k = y_k/D_k - V_k/D_k . z[sep_{p-1}] - L[k+1,k] z_{k+1} - L[k+2,k] z_{k+2}.
 // This is Gaussian elimination of the same SPD matrix in a nested-dissection order (the reference's SimplicialLDLT uses a
 // fill-reducing order of its own), so the heights agree with the other two forms to rounding and the active-set decisions
-// are the same (tests/test_gpu_alt.py).  Dependent steps per solve: ~n/8 + 2 * 6 instead of n/2, and ~60 instructions per
+// are the same (tests/test_gpu_alt.py).  Dependent steps per solve: ~n/16 + 16 instead of n/2, and ~50 instructions per
 // row because every per-row field lives in shared memory, laid out [field][slot][lane] -- a lane's rows are private to it,
 // addresses are base + immediate, nothing is staged and nothing synchronises inside a sweep.
 //
-// Shared memory: 7 fields; the three a separator row needs (W, E, YD) have 33 slots per lane, the four only interior rows
-// use (L1, L2, V1, V2) have 31: 223 x 32 lanes x 8 B = 55.75 KB per warp, one warp per CTA, FOUR CTAs per SM (228 KB);
-// a group of 8 lanes holds trajectories of up to 8 * 31 + 14 = 262 rows.  Longer trajectories are taken one at a time by all 32 lanes of the warp
-// with the same code: up to 32 * 31 + 62 = 1054 rows in the same shared memory, beyond that with the fields in the caller's
-// global scratch arrays (natural row order) instead.
+// Shared memory: 7 fields; the three a separator row needs (W, E, YD) have 17 slots per lane, the four only interior rows
+// use (L1, L2, V1, V2) have 15: 111 x 32 lanes x 8 B = 27.75 KB per warp, one warp per CTA, SEVEN CTAs per SM; a group of
+// 16 lanes holds trajectories of up to 16 * 15 + 30 = 270 rows (measured: 8 lanes x 31 rows, four CTAs per SM, is 8 % slower
+// -- fewer warps per scheduler).  Longer trajectories are taken one at a time by all 32 lanes of the warp with the same code:
+// up to 32 * 15 + 62 = 542 rows in the same shared memory, beyond that with the fields in the caller's global scratch
+// arrays (natural row order) instead.
 #ifndef MSNAP_ALT_PART_CUH
 #define MSNAP_ALT_PART_CUH
 
@@ -33,21 +34,21 @@
 
 namespace msnap {
 
-constexpr int ALTP_CMAX = 31;              // interior rows of a chunk that fit the shared-memory layout
+constexpr int ALTP_CMAX = 15;              // interior rows of a chunk that fit the shared-memory layout
 constexpr int ALTP_SLOTS = ALTP_CMAX + 2;  // + the lane's two separator rows
-constexpr int ALTP_GROUP = 8;              // lanes per trajectory in the shared-memory form
-constexpr int ALTP_NMAX = ALTP_GROUP * ALTP_CMAX + 2 * (ALTP_GROUP - 1);  // 262 rows
+constexpr int ALTP_GROUP = 16;             // lanes per trajectory in the shared-memory form
+constexpr int ALTP_NMAX = ALTP_GROUP * ALTP_CMAX + 2 * (ALTP_GROUP - 1);  // 270 rows
 enum AltPartField { AF_W = 0, AF_E, AF_YD, AF_L1, AF_L2, AF_V1, AF_V2, AF_COUNT };
 // first slot of a field: W, E, YD hold every row of the lane (ALTP_SLOTS), the factor fields interior rows only (ALTP_CMAX)
 __host__ __device__ constexpr int altp_off(int f) { return f <= AF_L1 ? f * ALTP_SLOTS : AF_L1 * ALTP_SLOTS + (f - AF_L1) * ALTP_CMAX; }
-constexpr int ALTP_SLOT_ROWS = altp_off(AF_COUNT);  // 223
+constexpr int ALTP_SLOT_ROWS = altp_off(AF_COUNT);  // 111
 constexpr size_t ALTP_SMEM_BYTES = (size_t)ALTP_SLOT_ROWS * 32 * sizeof(double);
 // staging homes of the raw x / y columns during the load (ALTP_SLOTS + 1 entries each, over fields that are still unused)
 constexpr int ALTP_STAGE_X = altp_off(AF_L1), ALTP_STAGE_Y = altp_off(AF_V1);
 // bulk-copy staging (doubles per group of lanes): rows [3 n + 1] in the L1 .. V2 slots, elevations [n + 1] in the YD slots
 __host__ __device__ constexpr int altp_stage_r(int gw) { return ((ALTP_SLOT_ROWS - ALTP_STAGE_X) * 32 / (32 / gw)) & ~1; }
 __host__ __device__ constexpr int altp_stage_e(int gw) { return (ALTP_SLOTS * 32 / (32 / gw)) & ~1; }
-constexpr int ALTP_NMAX32 = 32 * ALTP_CMAX + 2 * 31;  // 1054 rows: what all 32 lanes hold in shared memory for ONE trajectory
+constexpr int ALTP_NMAX32 = 32 * ALTP_CMAX + 2 * 31;  // 542 rows: what all 32 lanes hold in shared memory for ONE trajectory
 static_assert(3 * ALTP_NMAX + 2 <= altp_stage_r(ALTP_GROUP) && ALTP_NMAX + 2 <= altp_stage_e(ALTP_GROUP), "bulk staging does not fit");
 static_assert(3 * ALTP_NMAX32 + 2 <= altp_stage_r(32) && ALTP_NMAX32 + 2 <= altp_stage_e(32), "bulk staging does not fit");
 static_assert(ALTP_STAGE_X + ALTP_SLOTS + 1 <= ALTP_STAGE_Y && ALTP_STAGE_Y + ALTP_SLOTS + 1 <= ALTP_SLOT_ROWS, "staging overlaps");
@@ -528,8 +529,8 @@ __global__ void __maxnreg__(192) k_alt_part(AltParams p, long long B, const long
         alt_part_set<ALTP_GROUP, false>(p, F, lane, n > 0 && n <= ALTP_NMAX, base, n, rows, elev, z_pass1_out, n_cap, mbar, phase,
                                         solves, ok, ok2);
     }
-    // trajectories too long for a group of 8 lanes: one at a time, all 32 lanes -- in shared memory up to 1054 rows, with the
-    // fields in the global scratch beyond
+    // trajectories too long for a group of lanes: one at a time, all 32 lanes -- in shared memory up to ALTP_NMAX32 rows,
+    // with the fields in the global scratch beyond
     unsigned longer = __ballot_sync(FULL, lane % ALTP_GROUP == 0 && n > ALTP_NMAX);
     while (longer) {
         const int src = __ffs(longer) - 1;

@@ -175,14 +175,16 @@ def test_full_size_properties(alt_tool):
 def test_lane_pairs_and_partitions_equal_one_lane(tool):
     """Two-sided elimination and the partitioned (nested-dissection) form against the plain downward recurrence: same
     active-set decisions, heights equal to rounding; lengths around the pairing threshold (8 rows), around the partition
-    counts (n / 4 lanes up to 8; 262 rows = the last length a group of 8 lanes holds) and odd / even lengths included."""
+    counts (n / 4 lanes up to 16; 270 rows = the last length a group of 16 lanes holds, 542 the last 32 lanes hold in shared
+    memory) and odd / even lengths included."""
     grid, res, ox, oy = terrain_grid()
     rows, off = sampled_paths(200, seed=77, n_min=1, n_max=40)
     rows2, off2 = sampled_paths(60, seed=78, n_min=100, n_max=400)
-    rows3, off3 = sampled_paths(24, seed=79, n_min=255, n_max=270)
-    rows = np.vstack([rows, rows2, rows3])
-    off = np.concatenate([off, off[-1] + off2[1:]])
-    off = np.concatenate([off, off[-1] + off3[1:]])
+    rows3, off3 = sampled_paths(24, seed=79, n_min=255, n_max=280)
+    rows4, off4 = sampled_paths(12, seed=80, n_min=535, n_max=550)
+    rows = np.vstack([rows, rows2, rows3, rows4])
+    for o in (off2, off3, off4):
+        off = np.concatenate([off, off[-1] + o[1:]])
     elev = lookup(grid, res, ox, oy, rows)
     p = shipped_altitude_params()
     out = {}
@@ -228,7 +230,7 @@ def test_partitioned_staging_paths_agree(tool):
     ordinary load.  Same rows through device buffers at an 8-byte offset, and with the batch ending exactly at the end of
     the allocation (odd row count), must give the same bits."""
     grid, res, ox, oy = terrain_grid()
-    rows, off = sampled_paths(37, seed=91, n_min=1, n_max=262)
+    rows, off = sampled_paths(37, seed=91, n_min=1, n_max=300)
     if rows.shape[0] % 2 == 0:                       # odd number of rows: 3 n and n are odd, the last windows are clipped
         rows, off = rows[:-1], np.concatenate([off[:-1], [off[-1] - 1]])
     elev = lookup(grid, res, ox, oy, rows)

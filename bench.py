@@ -669,6 +669,47 @@ def run_b200(args):
         v["single_call"] = ("B = 1 through the drop-in call TrajectoryGeneratorTool::GenerateTrajectoryMatrix with host "
                             "buffers (sample bound + H2D + kernels + D2H), wall clock, median of 20 calls")
         v["single_call_samples"] = int(s1.shape[0])
+        # The same B = 1 call with device-resident buffers: launched kernel by kernel, and as ONE CUDA-graph replay (the
+        # *_dev entry points only enqueue work, tests/test_gpu_graph.py): what a caller that plans every tick would do.
+        try:
+            ns1 = wp1.shape[0] - 1
+            d_wp1 = torch.from_numpy(wp1).to(dev)
+            cap1 = tool.sample_bound(cfg1, wp1, ns=ns1, v_avg_override=vo1)
+            off1 = torch.zeros(2, dtype=torch.int64, device=dev)
+            rows1 = torch.zeros((cap1, 3), dtype=torch.float64, device=dev)
+
+            def one1():
+                tool.generate_batch_dev(cfg1, d_wp1, off1, rows1, ns=ns1, sample_distance_override=sdo1, v_avg_override=vo1)
+
+            def timed1(fn, n=200):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                with torch.cuda.stream(stream):
+                    for _ in range(5):
+                        fn()
+                    e0.record(stream)
+                    for _ in range(n):
+                        fn()
+                    e1.record(stream)
+                e1.synchronize()
+                return e0.elapsed_time(e1) / n
+
+            eager_ms = timed1(one1)
+            l0 = tool.launch_count
+            one1()
+            n_launch1 = tool.launch_count - l0
+            torch.cuda.synchronize()
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1, stream=stream):
+                one1()
+            graph_ms = timed1(g1.replay)
+            torch.cuda.synchronize()
+            v["dev_call_ms"] = {"eager": eager_ms, "cuda_graph_replay": graph_ms, "kernels_per_call": n_launch1,
+                                "samples": int(off1[1].item()),
+                                "note": "B = 1, device-resident waypoints and rows, back-to-back calls on one stream, CUDA "
+                                        "events; replay = the call captured once into a CUDA graph"}
+            del g1
+        except Exception as exc:  # never lose the line over the extra figure
+            v["dev_call_ms"] = {"error": repr(exc)[:200]}
         extra["cfg1"] = v
     del flush_buf
     clocks = sampler.stop() if sampler else None

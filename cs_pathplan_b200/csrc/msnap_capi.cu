@@ -514,14 +514,25 @@ int run_sample(msnap_context *h, const BatchIdx &bi, const double *coeff, const 
         const bool coef_smem = h->scan_coef_smem && scan_smem_bytes(s.tpt, ns, O, true) <= 52 * 1024;
         const size_t smem = scan_smem_bytes(s.tpt, ns, O, coef_smem);
         MS_CUDA(h, cudaMemsetAsync(s.status, 0, (size_t)(s.n_tiles + 1 + 256) * sizeof(unsigned long long), h->stream));
-        if (smem > 40 * 1024)  // the kernel also has ~4 KB of static shared memory
-            cudaFuncSetAttribute(k_sample_scan<O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // a batch of long legs (scan_tpt's hint: thousands of candidates per trajectory) walks them four blocks at a time
+        const bool long_legs = capacity / (bi.B > 0 ? bi.B : 1) > 16LL * SAMPLE_MASK_BITS;
+        if (smem > 40 * 1024) {  // the kernel also has ~4 KB of static shared memory
+            if (long_legs)
+                cudaFuncSetAttribute(k_sample_scan<O, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            else
+                cudaFuncSetAttribute(k_sample_scan<O, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        }
         const long long resident = (long long)h->sm_count * 4;
         const unsigned grid = (unsigned)(s.n_tiles < resident ? s.n_tiles : resident);
         prof_before(h, "k_sample_scan");
-        k_sample_scan<O><<<grid, SCAN_THREADS, smem, h->stream>>>(bi.B, ns, s.tpt, s.n_tiles, coeff, T, sd, h->d_ttab,
-                                                                   s.status, s.ticket, capacity, sample_offset, samples,
-                                                                   flags, coef_smem ? 1 : 0, s.sm_ctr, h->phase_clocks);
+        if (long_legs)
+            k_sample_scan<O, true><<<grid, SCAN_THREADS, smem, h->stream>>>(bi.B, ns, s.tpt, s.n_tiles, coeff, T, sd, h->d_ttab,
+                                                                            s.status, s.ticket, capacity, sample_offset, samples,
+                                                                            flags, coef_smem ? 1 : 0, s.sm_ctr, h->phase_clocks);
+        else
+            k_sample_scan<O, false><<<grid, SCAN_THREADS, smem, h->stream>>>(bi.B, ns, s.tpt, s.n_tiles, coeff, T, sd, h->d_ttab,
+                                                                             s.status, s.ticket, capacity, sample_offset, samples,
+                                                                             flags, coef_smem ? 1 : 0, s.sm_ctr, h->phase_clocks);
         prof_after(h);
         ++h->launches;
         cudaError_t e = cudaPeekAtLastError();

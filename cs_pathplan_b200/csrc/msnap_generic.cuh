@@ -714,6 +714,150 @@ __device__ __forceinline__ int warp_sample_long(const double (&c)[3][2 * O], dou
     return n;
 }
 
+// Four blocks per trip: the form k_sample_scan<O, true> uses for batches of long legs (the reference's own mission).  Not
+// inlined, and not used by the kernels of ordinary batches: a trip needs ~40 more registers than their thread-per-segment
+// paths, and either way of sharing a kernel with them (inlined, or as a call) cost the headline batch 2.6 %.
+template <int O, bool WRITE>
+__device__ __noinline__ int warp_sample_long4(const double (&c_in)[3][2 * O], double Tk, const AcceptTest &accept_in,
+                                             const double *__restrict__ t_table, long long row, long long capacity,
+                                             double *__restrict__ samples, bool &dropped, double (&last)[3]) {
+    // private copies: the arguments live in the caller's stack frame, where a store to `samples` could alias them
+    double c[3][2 * O];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int i = 0; i < 2 * O; ++i) c[a][i] = c_in[a][i];
+    const AcceptTest accept = accept_in;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const double dt = sample_dt(Tk);
+    const double tmax = sample_time_ok(Tk) ? Tk + 1e-12 : -1.0;
+    double prev[3];
+    eval_xyz<O>(c, 0.0, prev);
+    int n = 0;
+    double tb = 0.0;  // t of the last candidate of the previous block (t_1 = 0 + dt = dt exactly)
+    int base = 0;     // candidates before this block
+    bool more = true;
+    // acceptances among one block's 32 candidates `cur` (lane k = the block's k-th candidate), in order
+    auto resolve = [&](const double (&cur)[3], bool valid) {
+        int start = 0;
+        while (true) {
+            const bool ok = valid && lane >= start && accept(cur, prev);
+            const unsigned m = __ballot_sync(FULL, ok);
+            if (!m) break;
+            const int f = __ffs(m) - 1;
+            prev[0] = __shfl_sync(FULL, cur[0], f);
+            prev[1] = __shfl_sync(FULL, cur[1], f);
+            prev[2] = __shfl_sync(FULL, cur[2], f);
+            if (WRITE && lane == f) {
+                const long long r = row + n;
+                if (r < capacity) {
+                    samples[3 * r] = cur[0]; samples[3 * r + 1] = cur[1]; samples[3 * r + 2] = cur[2];
+                } else {
+                    dropped = true;
+                }
+            }
+            ++n;
+            start = f + 1;
+        }
+    };
+    // Tabulated times (dt = 0.1: t_table[i] = the i-th accumulated time, msnap_create): LONG_U blocks per trip.  A block is a
+    // short DEPENDENT chain -- time, Horner, distance, compare, ballot, branch: ~600 cycles for ~40 instructions on a lone
+    // warp -- and with the reference's spacings (300 m against 3 m between candidates) most blocks accept nothing, so the
+    // chains of LONG_U blocks run side by side and one vote says whether any of them has to be resolved; the times of the next
+    // trip are loaded during the current one.  Same candidates, same tests against the same reference point, same order.
+    constexpr int LONG_U = 4;
+    if (dt == 0.1) {
+        double ahead[LONG_U];
+#pragma unroll
+        for (int j = 0; j < LONG_U; ++j) ahead[j] = __ldg(t_table + 32 * j + lane + 1);  // (the table has >= 32 * LONG_U + 1 entries)
+        while (more && base + 32 * LONG_U < SAMPLE_TTAB_BIG) {
+            double mine[LONG_U], cur[LONG_U][3];
+            bool valid[LONG_U];
+#pragma unroll
+            for (int j = 0; j < LONG_U; ++j) {
+                mine[j] = ahead[j];
+                valid[j] = mine[j] <= tmax;  // the candidate times increase: the valid candidates are a prefix of the trip
+            }
+            if (base + 64 * LONG_U < SAMPLE_TTAB_BIG) {
+#pragma unroll
+                for (int j = 0; j < LONG_U; ++j) ahead[j] = __ldg(t_table + base + 32 * (LONG_U + j) + lane + 1);
+            }
+#pragma unroll
+            for (int j = 0; j < LONG_U; ++j) eval_xyz<O>(c, fmin(mine[j], Tk), cur[j]);
+            more = __all_sync(FULL, valid[LONG_U - 1]);
+            // The trip's first acceptance = the lowest candidate that passes; it becomes the reference point of the
+            // candidates behind it, which are tested again (all blocks at once), until none passes.  The test is
+            // AcceptTest's, with its rare branch (a squared distance within 1e-14 of the threshold, or NaN) taken by the
+            // whole warp or not at all, so that the common case is straight-line code for the four blocks.
+            int from = 0;  // first candidate of the trip (32 * block + lane) not yet decided
+            while (true) {
+                bool ok[LONG_U], band = false;
+#pragma unroll
+                for (int j = 0; j < LONG_U; ++j) {
+                    const double dx = cur[j][0] - prev[0], dy = cur[j][1] - prev[1], dz = cur[j][2] - prev[2];
+                    const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                    ok[j] = d2 >= accept.hi;
+                    band = band || !(ok[j] || d2 < accept.lo);
+                }
+                if (__any_sync(FULL, band)) {
+#pragma unroll
+                    for (int j = 0; j < LONG_U; ++j) ok[j] = accept(cur[j], prev);
+                }
+                unsigned m[LONG_U];
+#pragma unroll
+                for (int j = 0; j < LONG_U; ++j) m[j] = __ballot_sync(FULL, ok[j] && valid[j] && 32 * j + lane >= from);
+                int j0 = -1;
+#pragma unroll
+                for (int j = LONG_U - 1; j >= 0; --j)
+                    if (m[j]) j0 = j;
+                if (j0 < 0) break;
+                unsigned mm = 0u;
+                double sx = 0.0, sy = 0.0, sz = 0.0;
+#pragma unroll
+                for (int j = 0; j < LONG_U; ++j)
+                    if (j == j0) {
+                        mm = m[j];
+                        sx = cur[j][0], sy = cur[j][1], sz = cur[j][2];
+                    }
+                const int f = __ffs(mm) - 1;
+                prev[0] = __shfl_sync(FULL, sx, f);
+                prev[1] = __shfl_sync(FULL, sy, f);
+                prev[2] = __shfl_sync(FULL, sz, f);
+                if (WRITE && lane == f) {
+                    const long long r = row + n;
+                    if (r < capacity) {
+                        samples[3 * r] = sx; samples[3 * r + 1] = sy; samples[3 * r + 2] = sz;
+                    } else {
+                        dropped = true;
+                    }
+                }
+                ++n;
+                from = 32 * j0 + f + 1;
+            }
+            tb = __shfl_sync(FULL, mine[LONG_U - 1], 31);
+            base += 32 * LONG_U;
+        }
+    }
+    while (more) {  // beyond the table, or dt = T / 10: every lane runs the block's 32 additions
+        double t = tb, mine = 0.0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            t = __dadd_rn(t, dt);
+            if (j == lane) mine = t;
+        }
+        tb = t;
+        base += 32;
+        const bool valid = mine <= tmax;
+        more = __all_sync(FULL, valid);
+        double cur[3];
+        eval_xyz<O>(c, fmin(mine, Tk), cur);
+        resolve(cur, valid);
+    }
+    last[0] = prev[0]; last[1] = prev[1]; last[2] = prev[2];
+    return n;
+}
+
 // A segment is "long" when it has more candidates than the acceptance mask describes: the 129th tabulated candidate time
 // (ttab[129]) still lies within T + 1e-12.  (Segments shorter than 1 s use dt = T/10 and have 10 or 11 candidates.)
 __device__ __forceinline__ bool sample_is_long(double Tk, const double *ttab) {
@@ -974,7 +1118,9 @@ __host__ __device__ inline size_t scan_smem_bytes(int tpt, int ns, int order, bo
            (size_t)tpt * sizeof(int) + SCAN_DESC_CAP * sizeof(unsigned) + 16;
 }
 
-template <int O>
+// LONGLEGS: the batch's row capacity says its trajectories have thousands of candidates (scan_tpt: one trajectory per tile);
+// the warp-walked segments then take warp_sample_long4.  Same rows either way.
+template <int O, bool LONGLEGS = false>
 __global__ void __launch_bounds__(SCAN_THREADS, 4) k_sample_scan(
     long long B, int ns, int tpt, long long n_tiles, const double *__restrict__ coeff, const double *__restrict__ T,
     double sample_distance, const double *__restrict__ t_table, unsigned long long *status, unsigned int *ticket,
@@ -1134,7 +1280,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_sample_scan(
                     for (int j = 0; j < 2 * O; ++j) csm[i * CP + a * 2 * O + j] = c[a][j];
             }
             bool dropped = false;
-            const int n = warp_sample_long<O, false>(c, segT[i], accept, t_table, 0, 0, nullptr, dropped, lp);
+            const int n = LONGLEGS ? warp_sample_long4<O, false>(c, segT[i], accept, t_table, 0, 0, nullptr, dropped, lp)
+                                   : warp_sample_long<O, false>(c, segT[i], accept, t_table, 0, 0, nullptr, dropped, lp);
             if (lane == 0) {
                 cnt[i] = -n - 1;  // negative: no acceptance mask; the rows are written by a warp again (phase D)
                 mask[2 * i] = 0ull;
@@ -1343,8 +1490,12 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_sample_scan(
             double c[3][2 * O], lp[3];
             staged_coeff(g0, i, c);
             bool dropped = false;
-            warp_sample_long<O, true>(c, segT[i], accept, t_table, tile_base + traj_base[t] + seg_start[i], capacity, samples, dropped,
-                                      lp);
+            if (LONGLEGS)
+                warp_sample_long4<O, true>(c, segT[i], accept, t_table, tile_base + traj_base[t] + seg_start[i], capacity, samples,
+                                           dropped, lp);
+            else
+                warp_sample_long<O, true>(c, segT[i], accept, t_table, tile_base + traj_base[t] + seg_start[i], capacity, samples,
+                                          dropped, lp);
             if (__any_sync(0xffffffffu, dropped) && lane == 0 && flags) atomicOr(flags + b0 + t, 2u);
         }
         __syncthreads();  // smem is reused by the next tile

@@ -720,7 +720,8 @@ __device__ __forceinline__ int warp_sample_long(const double (&c)[3][2 * O], dou
 template <int O, bool WRITE>
 __device__ __noinline__ int warp_sample_long4(const double (&c_in)[3][2 * O], double Tk, const AcceptTest &accept_in,
                                              const double *__restrict__ t_table, long long row, long long capacity,
-                                             double *__restrict__ samples, bool &dropped, double (&last)[3]) {
+                                             double *__restrict__ samples, bool &dropped, double (&last)[3],
+                                             double *rec = nullptr, int rec_cap = 0) {
     // private copies: the arguments live in the caller's stack frame, where a store to `samples` could alias them
     double c[3][2 * O];
 #pragma unroll
@@ -739,7 +740,7 @@ __device__ __noinline__ int warp_sample_long4(const double (&c_in)[3][2 * O], do
     int base = 0;     // candidates before this block
     bool more = true;
     // acceptances among one block's 32 candidates `cur` (lane k = the block's k-th candidate), in order
-    auto resolve = [&](const double (&cur)[3], bool valid) {
+    auto resolve = [&](const double (&cur)[3], bool valid, double t_mine) {
         int start = 0;
         while (true) {
             const bool ok = valid && lane >= start && accept(cur, prev);
@@ -757,6 +758,7 @@ __device__ __noinline__ int warp_sample_long4(const double (&c_in)[3][2 * O], do
                     dropped = true;
                 }
             }
+            if (rec && lane == f && n < rec_cap) rec[n] = t_mine;
             ++n;
             start = f + 1;
         }
@@ -813,12 +815,12 @@ __device__ __noinline__ int warp_sample_long4(const double (&c_in)[3][2 * O], do
                     if (m[j]) j0 = j;
                 if (j0 < 0) break;
                 unsigned mm = 0u;
-                double sx = 0.0, sy = 0.0, sz = 0.0;
+                double sx = 0.0, sy = 0.0, sz = 0.0, st = 0.0;
 #pragma unroll
                 for (int j = 0; j < LONG_U; ++j)
                     if (j == j0) {
                         mm = m[j];
-                        sx = cur[j][0], sy = cur[j][1], sz = cur[j][2];
+                        sx = cur[j][0], sy = cur[j][1], sz = cur[j][2], st = mine[j];
                     }
                 const int f = __ffs(mm) - 1;
                 prev[0] = __shfl_sync(FULL, sx, f);
@@ -832,6 +834,7 @@ __device__ __noinline__ int warp_sample_long4(const double (&c_in)[3][2 * O], do
                         dropped = true;
                     }
                 }
+                if (rec && lane == f && n < rec_cap) rec[n] = st;  // the accepted candidate's time, for the write pass
                 ++n;
                 from = 32 * j0 + f + 1;
             }
@@ -852,7 +855,7 @@ __device__ __noinline__ int warp_sample_long4(const double (&c_in)[3][2 * O], do
         more = __all_sync(FULL, valid);
         double cur[3];
         eval_xyz<O>(c, fmin(mine, Tk), cur);
-        resolve(cur, valid);
+        resolve(cur, valid, mine);
     }
     last[0] = prev[0]; last[1] = prev[1]; last[2] = prev[2];
     return n;
@@ -1151,6 +1154,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_sample_scan(
     __shared__ int sh_first[SCAN_THREADS / 32];
     __shared__ int sh_slot, sh_sched[SCAN_THREADS / 32];
     __shared__ int sh_n_long;
+    constexpr int LONG_T_CAP = LONGLEGS ? 2048 : 1;  // accepted candidate times of a tile's warp-walked segments (16 KB)
+    __shared__ double long_t[LONG_T_CAP];
     for (int i = tid; i < SAMPLE_TTAB_N; i += SCAN_THREADS) ttab[i] = t_table[i];
     // Which chunk of the ranking a warp takes in phase A: (its scheduler + the CTA's arrival order on this SM) mod 4,
     // a Latin square over (scheduler, co-resident CTA), so that every scheduler of the SM gets one chunk of each rank.
@@ -1280,7 +1285,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_sample_scan(
                     for (int j = 0; j < 2 * O; ++j) csm[i * CP + a * 2 * O + j] = c[a][j];
             }
             bool dropped = false;
-            const int n = LONGLEGS ? warp_sample_long4<O, false>(c, segT[i], accept, t_table, 0, 0, nullptr, dropped, lp)
+            // (long legs: the accepted candidates' times are kept for the write pass, LONG_T_CAP / n_long of them per segment)
+            const int rec_cap = LONG_T_CAP / n_long;
+            const int n = LONGLEGS ? warp_sample_long4<O, false>(c, segT[i], accept, t_table, 0, 0, nullptr, dropped, lp,
+                                                                 long_t + q * rec_cap, rec_cap)
                                    : warp_sample_long<O, false>(c, segT[i], accept, t_table, 0, 0, nullptr, dropped, lp);
             if (lane == 0) {
                 cnt[i] = -n - 1;  // negative: no acceptance mask; the rows are written by a warp again (phase D)
@@ -1490,7 +1498,24 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_sample_scan(
             double c[3][2 * O], lp[3];
             staged_coeff(g0, i, c);
             bool dropped = false;
-            if (LONGLEGS)
+            const int rec_cap = LONG_T_CAP / n_long, n_acc = -cnt[i] - 1;
+            if (LONGLEGS && n_acc <= rec_cap) {
+                // the count pass recorded which candidates it accepted: evaluate those, 32 at a time, instead of walking the
+                // segment's thousands of candidates a second time (same times, same evaluation: the same rows)
+                const long long row0 = tile_base + traj_base[t] + seg_start[i];
+                const double *rec = long_t + q * rec_cap;
+                const double Tk = segT[i];
+                for (int k = lane; k < n_acc; k += 32) {
+                    double cur[3];
+                    eval_xyz<O>(c, fmin(rec[k], Tk), cur);
+                    const long long r = row0 + k;
+                    if (r < capacity) {
+                        samples[3 * r] = cur[0]; samples[3 * r + 1] = cur[1]; samples[3 * r + 2] = cur[2];
+                    } else {
+                        dropped = true;
+                    }
+                }
+            } else if (LONGLEGS)
                 warp_sample_long4<O, true>(c, segT[i], accept, t_table, tile_base + traj_base[t] + seg_start[i], capacity, samples,
                                            dropped, lp);
             else

@@ -514,8 +514,9 @@ int run_sample(msnap_context *h, const BatchIdx &bi, const double *coeff, const 
         const bool coef_smem = h->scan_coef_smem && scan_smem_bytes(s.tpt, ns, O, true) <= 52 * 1024;
         const size_t smem = scan_smem_bytes(s.tpt, ns, O, coef_smem);
         MS_CUDA(h, cudaMemsetAsync(s.status, 0, (size_t)(s.n_tiles + 1 + 256) * sizeof(unsigned long long), h->stream));
-        // a batch of long legs (scan_tpt's hint: thousands of candidates per trajectory) walks them four blocks at a time
-        const bool long_legs = capacity / (bi.B > 0 ? bi.B : 1) > 16LL * SAMPLE_MASK_BITS;
+        // a batch of long legs (the row capacity, normally the number of candidates, averages more than twice what an
+        // acceptance mask describes PER SEGMENT: most of the work is in warp-walked segments) walks them four blocks at a time
+        const bool long_legs = capacity / ((bi.B > 0 ? bi.B : 1) * (long long)ns) > 2LL * SAMPLE_MASK_BITS;
         if (smem > (long_legs ? 24 : 40) * 1024) {  // the kernel also has ~4 KB (long legs: ~20 KB) of static shared memory
             if (long_legs)
                 cudaFuncSetAttribute(k_sample_scan<O, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

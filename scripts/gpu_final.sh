@@ -1,3 +1,7 @@
+#!/bin/bash
+# Final pass of a round on one B200: scripts/gpu_check.sh (all GPU tests, smoke, bench, reference arm, launch list, ncu captures of
+# the solver and sampler) plus the altitude stage (both execution forms timed, launch list, full ncu capture of k_alt_part).
+# Usage (under gpurun): bash scripts/gpu_final.sh   (edit the tag below per version)
 bash scripts/gpu_check.sh r2v7 > gpurun_out/r2v7_check.log 2>&1
 tail -12 gpurun_out/r2v7_check.log | head -8
 NCU=1 TAG=r2v7

@@ -1497,12 +1497,14 @@ int msnap_altitude_optimize_batch_dev(msnap_handle h, const msnap_altitude_param
     if (B == 0 || n_rows_cap == 0) return MSNAP_OK;
     DeviceGuard guard(h->device);
     const size_t n = (size_t)n_rows_cap;
-    int rc = arena_reserve(h, h->ws, 9 * padded(n * sizeof(double)) + padded((size_t)B * sizeof(int)));
+    const bool part = h->alt_policy == 2;  // (its seven arrays are only touched by trajectories beyond ALTP_NMAX32 rows)
+    int rc = arena_reserve(h, h->ws, (part ? AF_COUNT : 9) * padded(n * sizeof(double)) + padded((size_t)B * sizeof(int)));
     if (rc) return rc;
-    double *w1 = arena_take<double>(h->ws, n), *w2 = arena_take<double>(h->ws, n), *tgt = arena_take<double>(h->ws, n);
+    double *w1 = arena_take<double>(h->ws, n), *w2 = arena_take<double>(h->ws, n);
     double *l1 = arena_take<double>(h->ws, n), *l2 = arena_take<double>(h->ws, n), *yd = arena_take<double>(h->ws, n);
     double *zin = arena_take<double>(h->ws, n), *cur = arena_take<double>(h->ws, n);
-    double *act = arena_take<double>(h->ws, n);  // active-set marks of pass 2 (0.0 / 1.0: staged like the other fields)
+    double *tgt = part ? nullptr : arena_take<double>(h->ws, n);
+    double *act = part ? nullptr : arena_take<double>(h->ws, n);  // active-set marks of pass 2 (0.0 / 1.0: staged like the other fields)
     int *st = arena_take<int>(h->ws, (size_t)B);  // per-trajectory outcome (ALT_ST_*)
     const AltParams p{params->lambda_smooth, params->lambda_follow, params->max_climb_rate, params->uav_R,
                       params->safe_distance};

@@ -713,6 +713,172 @@ __device__ __forceinline__ double thomas_backward(int n_rows, int m, const State
     return EVAL ? sqrt(m2) : 0.0;
 }
 
+// ---- one-axis forms of the twisted elimination ------------------------------------------------------------------
+// The factorisation (D', P, W) of a chain is common to the three axes; the right-hand sides are not coupled.  A chain can
+// therefore be walked by THREE lanes per half, each carrying the factorisation and ONE axis' right-hand side: per row 89
+// FP64 instructions instead of 126 forward, 9 instead of 27 backward, on the critical path of a phase in which the other
+// lanes of the CTA have nothing to do (the fused kernel's pass 1).  Every number is produced by the expression that produces
+// it in elim_half / elim_middle / back_half, in the same order: the state rows are bit for bit those of the lane-pair form.
+// `ax` = the lane's axis (0..2); all three lanes store the (identical) W.
+template <class Rows>
+__device__ __forceinline__ int field_off(int f) {
+    if constexpr (RowPair<Rows>::LANES > 0) return (f >> 1) * (2 * RowPair<Rows>::LANES) + (f & 1);
+    else return f * Rows::FS;
+}
+
+template <int O, class BaseAt, class StateAt>
+__device__ __forceinline__ bool elim_half_ax(int n_rows, int cnt, bool mirror, double add00, int ax, const BaseAt base_at,
+                                             const StateAt state_at) {
+    using D = Dim<O>;
+    constexpr int B = D::B, ND = D::ND, NU = D::NU;
+    bool ok = true;
+    double W[NU], z[B];
+    const int step = mirror ? -1 : 1;
+    int j = mirror ? n_rows - 1 : 0;
+    auto row = [&](auto first_tag) {
+        constexpr bool FIRST = decltype(first_tag)::value;
+        const double *b = base_at(j);
+        double *s = state_at(j);
+        double d[ND], r[B];
+        row_load<BaseAt, D::F_D, ND>(b, d);
+#pragma unroll
+        for (int p = 0; p < B; ++p) r[p] = b[field_off<BaseAt>(D::F_R + p * 3 + ax)];
+        d[0] += add00;
+        if constexpr (!FIRST) {
+            double C[NU];
+            load_coupling<O, BaseAt>(mirror ? b : base_at(j - 1), mirror, C);
+#pragma unroll
+            for (int p = 0; p < B; ++p) {
+#pragma unroll
+                for (int q = 0; q <= p; ++q) {
+                    double acc = d[sym(p, q)];
+#pragma unroll
+                    for (int t = 0; t < B; ++t) acc = fma(-C[t * B + p], W[t * B + q], acc);
+                    d[sym(p, q)] = acc;
+                }
+                double acc = r[p];
+#pragma unroll
+                for (int t = 0; t < B; ++t) acc = fma(-C[t * B + p], z[t], acc);
+                r[p] = acc;
+            }
+        }
+        double P[ND];
+        ok = sym_inverse<B>(d, P) && ok;
+#pragma unroll
+        for (int p = 0; p < B; ++p) {
+            double acc = P[sym(p, 0)] * r[0];
+#pragma unroll
+            for (int t = 1; t < B; ++t) acc = fma(P[sym(p, t)], r[t], acc);
+            z[p] = acc;
+        }
+#pragma unroll
+        for (int p = 0; p < B; ++p) s[field_off<StateAt>(D::SX + p * 3 + ax)] = z[p];
+        {
+            double N[NU];
+            load_coupling<O, BaseAt>(mirror ? base_at(j - 1) : b, mirror, N);
+#pragma unroll
+            for (int p = 0; p < B; ++p)
+#pragma unroll
+                for (int q = 0; q < B; ++q) {
+                    double acc = P[sym(p, 0)] * N[q];
+#pragma unroll
+                    for (int t = 1; t < B; ++t) acc = fma(P[sym(p, t)], N[t * B + q], acc);
+                    W[p * B + q] = acc;
+                }
+            row_store<StateAt, D::SW, NU>(s, W);
+        }
+        j += step;
+    };
+    if (cnt <= 0) return ok;
+    row(std::true_type{});
+    for (int i = 1; i < cnt; ++i) row(std::false_type{});
+    return ok;
+}
+
+template <int O, class BaseAt, class StateAt>
+__device__ __forceinline__ bool elim_middle_ax(int n_rows, int m, double add00, int ax, const BaseAt base_at,
+                                               const StateAt state_at) {
+    using D = Dim<O>;
+    constexpr int B = D::B, ND = D::ND, NU = D::NU;
+    const double *b = base_at(m);
+    double d[ND], r[B];
+    row_load<BaseAt, D::F_D, ND>(b, d);
+#pragma unroll
+    for (int p = 0; p < B; ++p) r[p] = b[field_off<BaseAt>(D::F_R + p * 3 + ax)];
+    d[0] += add00;
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        if (side == 0 ? m > 0 : m < n_rows - 1) {
+            const double *sn = state_at(side == 0 ? m - 1 : m + 1);
+            double C[NU], W[NU], z[B];
+            load_coupling<O, BaseAt>(side == 0 ? base_at(m - 1) : b, side != 0, C);
+            row_load<StateAt, D::SW, NU>(sn, W);
+#pragma unroll
+            for (int p = 0; p < B; ++p) z[p] = sn[field_off<StateAt>(D::SX + p * 3 + ax)];
+#pragma unroll
+            for (int p = 0; p < B; ++p) {
+#pragma unroll
+                for (int q = 0; q <= p; ++q) {
+                    double acc = d[sym(p, q)];
+#pragma unroll
+                    for (int t = 0; t < B; ++t) acc = fma(-C[t * B + p], W[t * B + q], acc);
+                    d[sym(p, q)] = acc;
+                }
+                double acc = r[p];
+#pragma unroll
+                for (int t = 0; t < B; ++t) acc = fma(-C[t * B + p], z[t], acc);
+                r[p] = acc;
+            }
+        }
+    }
+    double P[ND];
+    const bool ok = sym_inverse<B>(d, P);
+    double *sm = state_at(m);
+#pragma unroll
+    for (int p = 0; p < B; ++p) {
+        double acc = P[sym(p, 0)] * r[0];
+#pragma unroll
+        for (int t = 1; t < B; ++t) acc = fma(P[sym(p, t)], r[t], acc);
+        sm[field_off<StateAt>(D::SX + p * 3 + ax)] = acc;
+    }
+    return ok;
+}
+
+// back substitution of one half, one axis, solution left in the state rows (back_half<O, false, false> with xout = state_at)
+template <int O, class StateAt>
+__device__ __forceinline__ void back_half_ax(int n_rows, int m, bool mirror, int ax, const StateAt state_at) {
+    using D = Dim<O>;
+    constexpr int B = D::B, NU = D::NU;
+    double xn[B];
+    {
+        const double *sm = state_at(m);
+#pragma unroll
+        for (int p = 0; p < B; ++p) xn[p] = sm[field_off<StateAt>(D::SX + p * 3 + ax)];
+    }
+    const int cnt = mirror ? n_rows - 1 - m : m;
+    const int step = mirror ? 1 : -1;
+    int j = m + step;
+    for (int i = 0; i < cnt; ++i, j += step) {
+        double *s = state_at(j);
+        double x[B], W[NU];
+#pragma unroll
+        for (int p = 0; p < B; ++p) x[p] = s[field_off<StateAt>(D::SX + p * 3 + ax)];
+        row_load<StateAt, D::SW, NU>(s, W);
+#pragma unroll
+        for (int p = 0; p < B; ++p) {
+            double acc = x[p];
+#pragma unroll
+            for (int q = 0; q < B; ++q) acc = fma(-W[p * B + q], xn[q], acc);
+            x[p] = acc;
+        }
+#pragma unroll
+        for (int p = 0; p < B; ++p) {
+            s[field_off<StateAt>(D::SX + p * 3 + ax)] = x[p];
+            xn[p] = x[p];
+        }
+    }
+}
+
 // Polynomial coefficients of one segment and axis from its endpoint derivatives (c = M_k^-1 d, ms.cpp:584-591):
 // out[i], i = 0..M-1, highest power first.  ip[e] = T^-e, pT[r] = T^r.
 template <int O>

@@ -396,19 +396,34 @@ struct FusedTail {
 // make the row sweeps spill six doubles of W per row into local memory, whose reloads (26 % L1 misses: the L1 is what two
 // 112 KB CTAs leave of it) sat on the critical path of every row.  Called like this, only `tile` survives the call.
 //
-// pass 1 (ms.cpp:357-405): one lane pair per trajectory, solution left in the shared-memory state rows
+// pass 1 (ms.cpp:357-405): SIX lanes per trajectory -- two half chains (balanced twisted split) x three axes, the one-axis forms
+// of msnap_device.cuh -- five trajectories per warp; solution left in the shared-memory state rows.  The other lanes of the CTA
+// have nothing to do in this phase, and the per-row instruction stream of the lanes that do is what the phase lasts.
 template <int O>
 __device__ __noinline__ void fused_phase_pass1(const FusedParams &p, int nt) {
     extern __shared__ double smem[];  // (declared here, not passed in: the compiler then knows every pointer below is shared)
-    const int tid = threadIdx.x;
-    if (tid >= 2 * nt) return;
+    const int tid = threadIdx.x, l = tid & 31;
+    const int slot = l / 6, t = (tid >> 5) * 5 + slot;
+    const bool valid = l < 30 && t < nt;
+    const unsigned mask = __ballot_sync(0xffffffffu, valid);
+    if (!valid) return;
     const FusedTail<O> T(smem, p.ns, p.tpc, p.nit, p.traj_stride);
-    double unused;
-    const int t = tid >> 1;
+    const int side = (l % 6) / 3, ax = l % 3;
     const FStateRows<O, FUSED_SMEM_LANES> st{T.state1 + 2 * t};
-    const unsigned pm = 2 * nt >= 32 ? 0xffffffffu : (1u << (2 * nt)) - 1u;
-    const bool ok = fused_chain_pair<O, false>(smem + t * p.traj_stride, p.ns, 0.0, st, tid & 1, pm, &unused);
-    if ((tid & 1) == 0) T.ok1[t] = ok ? 1 : 0;
+    const FusedSmem<O> L(p.ns);
+    const FBaseRows<O> base_at{smem + t * p.traj_stride + L.oBase};
+    const int n = p.ns - 1;
+    bool ok = true;
+    if (n > 0) {
+        const int m = split_row(n, true);
+        ok = elim_half_ax<O>(n, side ? n - 1 - m : m, side != 0, 0.0, ax, base_at, st);
+        __syncwarp(mask);
+        if (side == 0) ok = elim_middle_ax<O>(n, m, 0.0, ax, base_at, st) && ok;
+        __syncwarp(mask);
+        back_half_ax<O>(n, m, side != 0, ax, st);
+    }
+    const unsigned bad = __ballot_sync(mask, !ok);
+    if (l % 6 == 0) T.ok1[t] = ((bad >> (6 * slot)) & 0x3fu) ? 0 : 1;
 }
 
 // Speculative Thomas over (trajectory, reweighting iteration), see the kernel.

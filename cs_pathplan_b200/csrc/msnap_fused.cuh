@@ -426,6 +426,23 @@ __device__ __noinline__ void fused_phase_pass1(const FusedParams &p, int nt) {
     if (l % 6 == 0) T.ok1[t] = ((bad >> (6 * slot)) & 0x3fu) ? 0 : 1;
 }
 
+// pass 1 (ms.cpp:357-405), lane-pair form: one lane pair per trajectory, solution left in the shared-memory state rows.  Used by the
+// many-wave build (three CTAs per SM), where the FP64 pipe is the bound and the six-lane form's threefold factorisation costs
+// more than its shorter rows save (cfg3: 8.18 -> 8.30 ms per batch with it).
+template <int O>
+__device__ __noinline__ void fused_phase_pass1_pair(const FusedParams &p, int nt) {
+    extern __shared__ double smem[];  // (declared here, not passed in: the compiler then knows every pointer below is shared)
+    const int tid = threadIdx.x;
+    if (tid >= 2 * nt) return;
+    const FusedTail<O> T(smem, p.ns, p.tpc, p.nit, p.traj_stride);
+    double unused;
+    const int t = tid >> 1;
+    const FStateRows<O, FUSED_SMEM_LANES> st{T.state1 + 2 * t};
+    const unsigned pm = 2 * nt >= 32 ? 0xffffffffu : (1u << (2 * nt)) - 1u;
+    const bool ok = fused_chain_pair<O, false>(smem + t * p.traj_stride, p.ns, 0.0, st, tid & 1, pm, &unused);
+    if ((tid & 1) == 0) T.ok1[t] = ok ? 1 : 0;
+}
+
 // Speculative Thomas over (trajectory, reweighting iteration), see the kernel.
 template <int O>
 __device__ __noinline__ void fused_phase_spec(const FusedParams &p, long long tile, int nt) {
@@ -552,7 +569,8 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_solve(const __grid_constant_
                 fused_row_item<O>(p, smem + (i / nr) * tstride, ns, i % nr + 1, false);
             __syncthreads();
             MSNAP_STAMP();
-            fused_phase_pass1<O>(p, nt);
+            if constexpr (MINB >= 3) fused_phase_pass1_pair<O>(p, nt);
+            else fused_phase_pass1<O>(p, nt);
             __syncthreads();
             MSNAP_STAMP();
             for (int i = tid; i < nt * ns; i += NT) {
